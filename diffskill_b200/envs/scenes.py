@@ -1,0 +1,61 @@
+"""Scene parameters of the three DiffSkill environments.
+
+These are the *inputs* of the hot path: the numeric values of
+plb/envs/lift_spread.yml, plb/envs/gather_move.yml and
+plb/cut/cut_rearrange.yml (gym ids registered at plb/envs/__init__.py:30-61),
+restated as Python data so no reference file is needed at run time.  A user
+with the reference checkout can equally pass the YAML path to
+``diffskill_b200.scene.load_scene``.
+"""
+
+_WOOD = (0.7568, 0.6039, 0.4196)
+_TILT = (0.707, 0.707, 0., 0.)          # note: not unit norm
+
+LIFT_SPREAD = dict(
+    SIMULATOR=dict(E=5000., n_particles=30000, yield_stress=200., ground_friction=1.5, gravity=(0, -20, 0), quality=1),
+    SHAPES=[dict(shape='sphere', init_pos=(0.65, 0.08, 0.5), radius=0.05, color=100)],
+    PRIMITIVES=[
+        dict(shape='RollingPinExt', h=0.3, r=0.03, init_pos=(0.3, 0.25, 0.5), init_rot=_TILT, color=_WOOD,
+             friction=0.9, action=dict(dim=6, scale=(0.7, 0.005, 0.005, 0.005, 0., 0.)), lower_bound=(0., 0.16, 0.)),
+        dict(shape='Box', size=(0.1, 0.1, 0.02), init_pos=(0.65, 0.02, 0.5), init_rot=_TILT, color=_WOOD,
+             friction=50., action=dict(dim=6, scale=(0.01, 0.01, 0., 0.0, 0., 0.05)), collision_group=(0, 0, 1)),
+        dict(shape='Box', size=(0.2, 0.28, 0.07), init_pos=(0.3, 0.05, 0.5), init_rot=_TILT, color=(0.5, 0.5, 0.5),
+             friction=5., action=dict(dim=0)),
+    ],
+    ENV=dict(cached_state_path='datasets/0202_liftspread', env_name='LiftSpread-v1'),
+)
+
+GATHER_MOVE = dict(
+    SIMULATOR=dict(E=5000., n_particles=30000, yield_stress=200., ground_friction=1.5, gravity=(0, -20, 0), quality=1),
+    SHAPES=[dict(shape='scatter', pos_min=(0.64, 0.02, 0.38), pos_max=(0.76, 0.035, 0.62), color=_WOOD, seed=0)],
+    PRIMITIVES=[
+        dict(shape='Gripper', size=(0.015, 0.09, 0.05), init_pos=(0.7, 0.06, 0.5), init_rot=(0.5, 0.5, -0.5, 0.5),
+             init_gap=0.4, minimal_gap=0.05, color=_WOOD, friction=1.,
+             action=dict(dim=7, scale=(0.015, 0.0, 0.015, 0.0, 0.0, 0.1, 0.03)), collision_group=(0, 0, 1)),
+        dict(shape='Box', size=(0.07, 0.07, 0.02), init_pos=(0.7, 0.01, 0.5), init_rot=_TILT, color=_WOOD,
+             friction=50., action=dict(dim=6, scale=(0.01, 0.01, 0., 0.0, 0., 0.05)), collision_group=(0, 0, 1)),
+        dict(shape='Box', size=(0.2, 0.28, 0.04), init_pos=(0.33, 0.05, 0.5), init_rot=_TILT, color=(0.5, 0.5, 0.5),
+             friction=5., action=dict(dim=0)),
+    ],
+    ENV=dict(cached_state_path='datasets/0202_gathermove', env_name='GatherMove-v1'),
+)
+
+CUT_REARRANGE = dict(
+    SIMULATOR=dict(E=5000., n_particles=30000, quality_multiplier=1.25, yield_stress=150., ground_friction=0.5,
+                   gravity=(0, -10, 0), quality=1, dtype='float32', lower_bound=1.),
+    SHAPES=[dict(shape='box', init_pos=(0.5, 0.12, 0.5), width=(0.2, 0.08, 0.08), color=100, n_particles=5000)],
+    PRIMITIVES=[
+        dict(shape='Knife', h=(0.15, 0.15), size=(0.025, 0.2, 0.06), prot=(1.0, 0.0, 0.0, 0.58),
+             init_pos=(0.5, 0.3, 0.5), color=_WOOD, friction=0., action=dict(dim=3, scale=(0.015, 0.015, 0.0))),
+        dict(shape='Gripper', size=(0.015, 0.1, 0.06), init_pos=(0.5, 0.10, 0.5), init_gap=0.18, minimal_gap=0.08,
+             maximal_gap=0.2, init_rot=(0.707, 0.0, 0.707, 0.0), color=_WOOD, friction=10.,
+             action=dict(dim=7, scale=(0.015, 0.015, 0.015, 0., 0., 0., 0.015))),
+    ],
+    ENV=dict(cached_state_path='datasets/1215_cutrearrange', env_name='CutRearrange-v1'),
+)
+
+SCENES = {
+    'LiftSpread-v1': LIFT_SPREAD,
+    'GatherMove-v1': GATHER_MOVE,
+    'CutRearrange-v1': CUT_REARRANGE,
+}

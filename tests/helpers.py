@@ -1,0 +1,59 @@
+"""Shared helpers for the test-suite (synthetic dough near the tools, losses, error metrics)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from diffskill_b200.scene import load_scene  # noqa: E402
+from diffskill_b200.shapes import Shapes  # noqa: E402
+
+
+def small_dough(name, n, seed=0):
+    """n particles of the env's synthetic dough, squeezed next to the tools so contacts are active."""
+    scene, cfg = load_scene(name)
+    rng = np.random.RandomState(seed)
+    if name == 'LiftSpread-v1':
+        # blob on the lifter plate, touching the rolling pin's influence region
+        x = rng.uniform(-1, 1, (n, 3)) * np.array([0.04, 0.02, 0.04]) + np.array([0.62, 0.075, 0.5])
+    elif name == 'GatherMove-v1':
+        x = rng.uniform(-1, 1, (n, 3)) * np.array([0.05, 0.012, 0.05]) + np.array([0.70, 0.05, 0.5])
+    elif name == 'CutRearrange-v1':
+        x = rng.uniform(-1, 1, (n, 3)) * np.array([0.06, 0.03, 0.03]) + np.array([0.5, 0.06, 0.5])
+    else:
+        x = Shapes(cfg.SHAPES, seed=seed).get()[0][:n]
+    return scene, cfg, x
+
+
+def perturbed_state(x, seed=1, vel=0.3, strain=0.02):
+    """A generic (non-degenerate) particle state: small random v, C, and F = I + noise."""
+    rng = np.random.RandomState(seed)
+    n = len(x)
+    v = rng.normal(size=(n, 3)) * vel
+    C = rng.normal(size=(n, 3, 3)) * 5.0
+    F = np.eye(3)[None] + rng.normal(size=(n, 3, 3)) * strain
+    return v, F, C
+
+
+def tool_start(name, scene):
+    """Tool states at frame 0 moved so that every tool touches the small dough."""
+    st = [np.array(t.init_state, dtype=np.float64) for t in scene.tools]
+    if name == 'LiftSpread-v1':
+        st[0][:3] = (0.60, 0.13, 0.5)     # rolling pin just above the blob
+        st[1][:3] = (0.62, 0.03, 0.5)
+    elif name == 'GatherMove-v1':
+        st[0][7] = 0.12                   # gripper jaws close to the dough
+    elif name == 'CutRearrange-v1':
+        st[0][:3] = (0.5, 0.24, 0.5)      # knife tip inside the slab
+        st[1][:3] = (0.5, 0.09, 0.5)
+        st[1][7] = 0.10
+    return st
+
+
+def relerr(a, b, floor=1e-30):
+    """normwise relative error max|a-b| / max(max|b|, floor)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), floor))
