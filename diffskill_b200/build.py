@@ -1,0 +1,49 @@
+"""Builds libdiffskill_mpm.so (the C-ABI CUDA library) in-tree for sm_100a.
+
+nvcc cross-compiles without a GPU; the built .so travels to the GPU box with the repo snapshot.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+SO = os.path.join(HERE, 'libdiffskill_mpm.so')
+SOURCES = ['engine.cu']
+HEADERS = ['mpm_math.cuh', 'svd3.cuh', 'tools.cuh', 'kernels_common.cuh', 'kernels_aux.cuh', 'kernels_fwd.cuh',
+           'kernels_bwd.cuh', os.path.join('..', '..', 'include', 'diffskill_mpm.h')]
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+              '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC', '-shared']
+
+
+def _nvcc():
+    for c in (os.environ.get('NVCC'), '/usr/local/cuda/bin/nvcc', shutil.which('nvcc')):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError('nvcc not found')
+
+
+def _host_cxx():
+    return '/usr/bin/g++' if os.path.exists('/usr/bin/g++') else (shutil.which('g++') or 'g++')
+
+
+def needs_build():
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False, extra=()):
+    if not force and not needs_build():
+        return SO
+    cmd = [_nvcc(), '-ccbin', _host_cxx()] + NVCC_FLAGS + list(extra) + ['-o', SO] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        print(' '.join(cmd))
+    subprocess.check_call(cmd)
+    return SO
+
+
+if __name__ == '__main__':
+    build(force='--force' in sys.argv, verbose=True, extra=['-Xptxas', '-v'] if '--ptxas' in sys.argv else [])

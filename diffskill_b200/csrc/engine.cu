@@ -1,0 +1,1076 @@
+// Host side of the C ABI (include/diffskill_mpm.h): owns all device state, schedules the
+// kernels of kernels_{aux,fwd,bwd}.cuh on one CUDA stream.  No torch, no CPU fallback: every
+// entry point either launches the sm_100a kernels or fails.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/diffskill_mpm.h"
+#include "kernels_bwd.cuh"
+
+static thread_local std::string g_err;
+static int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return -1;
+}
+#define CK(call)                                                                                    \
+  do {                                                                                              \
+    cudaError_t err__ = (call);                                                                     \
+    if (err__ != cudaSuccess) return fail("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(err__)); \
+  } while (0)
+#define CKE(e)                                                     \
+  do {                                                             \
+    if (!(e)) return fail("null engine");                          \
+    CK(cudaSetDevice((e)->cfg.device));                            \
+  } while (0)
+#define LAUNCH_CHECK() CK(cudaGetLastError())
+
+struct StepSlot {
+  float* frames;     // (S+1) particle frames, sorted order
+  float* mat;        // sorted material arrays [3][stride]
+  int* perm;         // sorted slot -> particle id, [stride]
+  float* poses;      // [B][S+1][K][8]
+  int* cidx;         // [B][S+1][npairs]
+  int src_step = -1; // checkpoint the frames were simulated from (-1: invalid)
+  int action_step = -1;
+};
+
+struct dsk_engine {
+  dsk_config cfg;
+  SimConst k;
+  cudaStream_t stream = 0;
+  int B, Npad, S, H, K, A, slots, ncols;
+  size_t frame_floats, tool_floats;
+  int64_t launches = 0, bytes = 0;
+  std::vector<void*> allocs;
+  // particles
+  float* ckpt = nullptr;      // (H+1) frames, canonical order
+  float* adj_ckpt = nullptr;  // (H+1) adjoint frames
+  float* adjw[2] = {nullptr, nullptr};
+  float* mat = nullptr;  // [3][stride] canonical
+  int* npart = nullptr;
+  std::vector<int> h_npart;
+  std::vector<StepSlot> slot;
+  // sort scratch
+  int *cell_count = nullptr, *key = nullptr, *rank = nullptr;
+  // grids: set index = epoch & 1
+  float4 *G0[2], *Gv[2], *Ga[2];
+  int *tile_epoch[2], *tile_list[2], *tile_count = nullptr;  // tile_count[4] ring
+  int dirty[2] = {0, 0};  // bit0 G0, bit1 Gv, bit2 Ga written in that set since its last clear
+  int epoch = 0;
+  // tools
+  ToolParams* d_tools = nullptr;
+  std::vector<ToolParams> h_tools;
+  float *tool_ckpt = nullptr, *tool_adj_ckpt = nullptr;  // [H+1][B][K][8]
+  float* pose_adj = nullptr;                             // [B][S+1][K][8]
+  float *actions = nullptr, *action_grad = nullptr;      // [H][B][A]
+  float* rand_num = nullptr;
+  // io staging
+  float* stage = nullptr;
+  size_t stage_floats = 0;
+  // fine-grained substep cursor
+  int last_fwd_frame = -1, last_bwd_frame = -1, last_substep_slot = -1, last_substep_j = -1;
+  bool last_was_backward = false;
+  int bwd_cur = 0;  // adjw index holding the adjoint of the current frame
+
+  float* frame_of(float* base, int i) { return base + (size_t)i * frame_floats; }
+  float* tools_of(float* base, int step) { return base + (size_t)step * tool_floats; }
+};
+
+template <class T>
+static int dalloc(dsk_engine* e, T** p, size_t count, bool zero = true) {
+  void* q = nullptr;
+  size_t nb = std::max<size_t>(count, 1) * sizeof(T);
+  CK(cudaMalloc(&q, nb));
+  if (zero) CK(cudaMemset(q, 0, nb));
+  e->allocs.push_back(q);
+  e->bytes += (int64_t)nb;
+  *p = (T*)q;
+  return 0;
+}
+#define DA(p, n)                        \
+  do {                                  \
+    if (dalloc(e, &(p), (n))) return -1; \
+  } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+static void fill_tool(ToolParams& T, const dsk_tool_desc& d) {
+  memset(&T, 0, sizeof T);
+  T.type = d.type;
+  T.action_dim = d.action_dim;
+  for (int j = 0; j < 8; j++) T.action_scale[j] = (float)d.action_scale[j];
+  T.friction = (float)d.friction;
+  T.softness = (float)d.softness;
+  for (int j = 0; j < 3; j++) {
+    T.lo[j] = (float)d.lower_bound[j];
+    T.hi[j] = (float)d.upper_bound[j];
+    T.size[j] = (float)d.size[j];
+  }
+  T.h = (float)d.h;
+  T.half_h = (float)(d.h / 2);
+  T.r = (float)d.r;
+  T.prism_h0 = (float)d.prism_h[0];
+  T.prism_h1 = (float)d.prism_h[1];
+  float w = (float)d.prot[0], x = (float)d.prot[1], y = (float)d.prot[2], z = (float)d.prot[3];
+  T.prot = Q4{w, x, y, z};
+  // normalised conjugate in fp32 with the reference's operation order (primitives.py:713-714)
+  volatile float n2 = w * w;
+  n2 = n2 + x * x;
+  n2 = n2 + y * y;
+  n2 = n2 + z * z;
+  volatile float inv = 1.0f / sqrtf(n2);
+  T.prot_inv = Q4{inv * w, inv * -x, inv * -y, inv * -z};
+  T.min_gap = (float)d.minimal_gap;
+  T.max_gap = (float)d.maximal_gap;
+}
+
+extern "C" {
+
+const char* dsk_last_error(void) { return g_err.c_str(); }
+int dsk_abi_version(void) { return DSK_ABI_VERSION; }
+
+int dsk_create(const dsk_config* c, dsk_engine** out) {
+  if (!c || !out) return fail("null argument");
+  if (c->abi_version != DSK_ABI_VERSION) return fail("ABI version mismatch: header %d, library %d", c->abi_version, DSK_ABI_VERSION);
+  if (c->n_grid % 4 != 0 || c->n_grid < 8) return fail("n_grid must be a multiple of 4 (got %d)", c->n_grid);
+  if (c->n_envs < 1 || c->particle_capacity < 1 || c->substeps < 1 || c->max_steps < 1) return fail("bad sizes");
+  if (c->n_tools < 0 || c->n_tools > DSK_MAX_TOOLS || c->n_pairs < 0 || c->n_pairs > DSK_MAX_PAIRS) return fail("too many tools/pairs");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (c->device < 0 || c->device >= ndev) return fail("CUDA device %d not available (%d devices)", c->device, ndev);
+  CK(cudaSetDevice(c->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, c->device));
+  if (prop.major < 10) return fail("this library contains sm_100a code only; device is sm_%d%d", prop.major, prop.minor);
+  dsk_engine* e = new dsk_engine();
+  e->cfg = *c;
+  e->B = c->n_envs;
+  e->Npad = (c->particle_capacity + 127) / 128 * 128;
+  e->S = c->substeps;
+  e->H = c->max_steps;
+  e->K = c->n_tools;
+  e->slots = std::max(1, std::min(c->step_slots, c->max_steps));
+  SimConst& k = e->k;
+  memset(&k, 0, sizeof k);
+  k.n = c->n_grid;
+  k.nt = k.n / 4;
+  k.ntile = k.nt * k.nt * k.nt;
+  k.nnode = k.n * k.n * k.n;
+  k.B = e->B;
+  k.Npad = e->Npad;
+  k.stride = e->B * e->Npad;
+  k.S = e->S;
+  k.K = e->K;
+  k.npairs = c->n_pairs;
+  k.gf_mode = c->ground_friction == 0.0 ? 0 : (c->ground_friction < 10.0 ? 1 : 2);
+  k.dt = (float)c->dt;
+  k.dx = (float)c->dx;
+  k.inv_dx = (float)c->inv_dx;
+  k.p_mass = (float)c->p_mass;
+  k.c_stress = (float)(-c->dt * c->p_vol * 4 * c->inv_dx * c->inv_dx);  // mpm_simulator.py:214
+  k.c_C = (float)(4 * c->inv_dx);                                       // :279
+  k.x_hi = (float)(1. - 3 * c->dx);                                     // :283
+  k.x_lo = (float)(c->lower_bound * c->dx);
+  k.m_eps = 1e-12f;
+  k.ground_friction = (float)c->ground_friction;
+  for (int d = 0; d < 3; d++) {
+    volatile float t = k.dt * (float)c->gravity[d];
+    k.grav[d] = t * 30.f;
+  }
+  for (int i = 0; i < c->n_pairs; i++) {
+    k.pairs[i][0] = c->pairs[i][0];
+    k.pairs[i][1] = c->pairs[i][1];
+    if (c->pairs[i][0] < 0 || c->pairs[i][0] >= e->K || c->pairs[i][1] < 0 || c->pairs[i][1] >= e->K) {
+      delete e;
+      return fail("bad collision pair");
+    }
+  }
+  e->A = 0;
+  e->ncols = 0;
+  e->h_tools.resize(std::max(1, e->K));
+  for (int i = 0; i < e->K; i++) {
+    fill_tool(e->h_tools[i], c->tools[i]);
+    e->A += c->tools[i].action_dim;
+    e->ncols += c->tools[i].type == DSK_TOOL_GRIPPER ? 2 : 1;
+    if (c->tools[i].type < 0 || c->tools[i].type > DSK_TOOL_KNIFE) {
+      delete e;
+      return fail("unknown tool type %d", c->tools[i].type);
+    }
+  }
+  e->frame_floats = (size_t)FRAME_COMPS * k.stride;
+  e->tool_floats = (size_t)e->B * std::max(1, e->K) * 8;
+  int rc = [&]() -> int {
+    DA(e->ckpt, (size_t)(e->H + 1) * e->frame_floats);
+    DA(e->adj_ckpt, (size_t)(e->H + 1) * e->frame_floats);
+    DA(e->adjw[0], e->frame_floats);
+    DA(e->adjw[1], e->frame_floats);
+    DA(e->mat, (size_t)3 * k.stride);
+    DA(e->npart, e->B);
+    e->h_npart.assign(e->B, 0);
+    e->slot.resize(e->slots);
+    for (auto& s : e->slot) {
+      DA(s.frames, (size_t)(e->S + 1) * e->frame_floats);
+      DA(s.mat, (size_t)3 * k.stride);
+      DA(s.perm, k.stride);
+      DA(s.poses, (size_t)(e->S + 1) * e->tool_floats);
+      DA(s.cidx, (size_t)e->B * (e->S + 1) * std::max(1, k.npairs));
+    }
+    DA(e->cell_count, (size_t)e->B * k.nnode);
+    DA(e->key, k.stride);
+    DA(e->rank, k.stride);
+    for (int s = 0; s < 2; s++) {
+      DA(e->G0[s], (size_t)e->B * k.nnode);
+      DA(e->Gv[s], (size_t)e->B * k.nnode);
+      DA(e->Ga[s], (size_t)e->B * k.nnode);
+      DA(e->tile_epoch[s], (size_t)e->B * k.ntile);
+      DA(e->tile_list[s], (size_t)e->B * k.ntile);
+    }
+    DA(e->tile_count, 4);
+    DA(e->d_tools, std::max(1, e->K));
+    DA(e->tool_ckpt, (size_t)(e->H + 1) * e->tool_floats);
+    DA(e->tool_adj_ckpt, (size_t)(e->H + 1) * e->tool_floats);
+    DA(e->pose_adj, (size_t)(e->S + 1) * e->tool_floats);
+    DA(e->actions, (size_t)e->H * e->B * std::max(1, e->A));
+    DA(e->action_grad, (size_t)e->H * e->B * std::max(1, e->A));
+    DA(e->rand_num, (size_t)std::max(1, k.npairs) * DSK_NUM_COLLISION_POINTS * 3);
+    e->stage_floats = std::max<size_t>((size_t)k.stride * 24, (size_t)e->B * k.nnode * 4);
+    DA(e->stage, e->stage_floats);
+    CK(cudaMemcpy(e->d_tools, e->h_tools.data(), sizeof(ToolParams) * std::max(1, e->K), cudaMemcpyHostToDevice));
+    // material fill, mpm_simulator.py:85-87
+    std::vector<float> m((size_t)3 * k.stride);
+    for (int i = 0; i < k.stride; i++) {
+      m[i] = (float)c->mu;
+      m[k.stride + i] = (float)c->lam;
+      m[2 * (size_t)k.stride + i] = (float)c->yield_stress;
+    }
+    CK(cudaMemcpy(e->mat, m.data(), m.size() * 4, cudaMemcpyHostToDevice));
+    return 0;
+  }();
+  if (rc) {
+    for (void* p : e->allocs) cudaFree(p);
+    delete e;
+    return -1;
+  }
+  *out = e;
+  return 0;
+}
+
+int dsk_destroy(dsk_engine* e) {
+  if (!e) return 0;
+  cudaSetDevice(e->cfg.device);
+  cudaStreamSynchronize(e->stream);
+  for (void* p : e->allocs) cudaFree(p);
+  delete e;
+  return 0;
+}
+int dsk_set_stream(dsk_engine* e, void* s) {
+  CKE(e);
+  e->stream = (cudaStream_t)s;
+  return 0;
+}
+int dsk_synchronize(dsk_engine* e) {
+  CKE(e);
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+int dsk_set_rand_num(dsk_engine* e, const double* rn) {
+  CKE(e);
+  size_t n = (size_t)e->k.npairs * DSK_NUM_COLLISION_POINTS * 3;
+  if (!n) return 0;
+  std::vector<float> f(n);
+  for (size_t i = 0; i < n; i++) f[i] = (float)rn[i];
+  CK(cudaMemcpyAsync(e->rand_num, f.data(), n * 4, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+int dsk_launch_count(dsk_engine* e, int64_t* n) {
+  if (!e) return fail("null engine");
+  *n = e->launches;
+  return 0;
+}
+int dsk_memory_bytes(dsk_engine* e, int64_t* n) {
+  if (!e) return fail("null engine");
+  *n = e->bytes;
+  return 0;
+}
+
+}  // extern "C"
+
+// -------------------------------------------------------------------------------------------------------
+// internal scheduling
+// -------------------------------------------------------------------------------------------------------
+static int check_step(dsk_engine* e, int step, const char* what) {
+  if (step < 0 || step > e->H) return fail("%s: step %d outside [0, %d] (max_steps of this engine)", what, step, e->H);
+  return 0;
+}
+static void invalidate_slots(dsk_engine* e, int step) {
+  // a checkpoint was overwritten: substep frames simulated from it are stale
+  for (auto& s : e->slot)
+    if (s.src_step == step) s.src_step = -1;
+}
+
+// one staging copy in: host or device source -> device pointer valid on the stream
+static int stage_in(dsk_engine* e, const float* src, size_t n, int on_device, size_t offset, const float** out) {
+  if (!src) {
+    *out = nullptr;
+    return 0;
+  }
+  if (on_device) {
+    *out = src;
+    return 0;
+  }
+  if (offset + n > e->stage_floats) return fail("staging buffer too small");
+  CK(cudaMemcpyAsync(e->stage + offset, src, n * 4, cudaMemcpyHostToDevice, e->stream));
+  *out = e->stage + offset;
+  return 0;
+}
+
+static int begin_step(dsk_engine* e, int src_step, int action_step, StepSlot** out) {
+  SimConst& k = e->k;
+  StepSlot& s = e->slot[src_step % e->slots];
+  int nb = cdiv(k.stride, 256);
+  if (e->cfg.sort_particles) {
+    CK(cudaMemsetAsync(e->cell_count, 0, (size_t)e->B * k.nnode * 4, e->stream));
+    k_sort_bin<<<nb, 256, 0, e->stream>>>(k, e->frame_of(e->ckpt, src_step), e->npart, e->cell_count, e->key, e->rank);
+    k_sort_scan<<<e->B, 1024, 0, e->stream>>>(k, e->cell_count);
+    e->launches += 2;
+  }
+  k_sort_scatter<<<nb, 256, 0, e->stream>>>(k, e->frame_of(e->ckpt, src_step), e->mat, e->npart, e->cell_count, e->key,
+                                            e->rank, e->cfg.sort_particles, s.frames, s.mat, s.perm);
+  const float* act = (e->A > 0 && action_step >= 0) ? e->actions + (size_t)action_step * e->B * e->A : nullptr;
+  if (e->K > 0)
+    k_kinematics<<<e->B, KIN_CTA, 0, e->stream>>>(k, e->d_tools, e->tools_of(e->tool_ckpt, src_step), act, e->rand_num,
+                                                  s.poses, s.cidx);
+  e->launches += 2;
+  LAUNCH_CHECK();
+  s.src_step = -1;  // becomes valid once all substeps ran
+  s.action_step = action_step;
+  *out = &s;
+  return 0;
+}
+
+static int grid_ctas(dsk_engine* e) { return 148 * 8; }
+
+// forward substep j of a slot (frames j -> j+1)
+static int run_substep(dsk_engine* e, StepSlot& s, int j, bool write_state) {
+  SimConst& k = e->k;
+  int ep = ++e->epoch;
+  int set = ep & 1, prev = set ^ 1;
+  TileTrack tt{e->tile_epoch[set], e->tile_list[set], e->tile_count + (ep & 3)};
+  int nb = cdiv(k.stride, 128);
+  float* fin = s.frames + (size_t)j * e->frame_floats;
+  float* fout = s.frames + (size_t)(j + 1) * e->frame_floats;
+  if (write_state)
+    k_p2g<true><<<nb, 128, 0, e->stream>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, ep);
+  else
+    k_p2g<false><<<nb, 128, 0, e->stream>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, ep);
+  int pd = e->dirty[prev];
+  k_grid<<<grid_ctas(e), GRID_CTA, 0, e->stream>>>(
+      k, e->d_tools, s.poses, j, e->G0[set], e->G0[set], tt.list, tt.count, pd ? e->tile_list[prev] : nullptr,
+      e->tile_count + ((ep - 1) & 3), (pd & 1) ? e->G0[prev] : nullptr, (pd & 2) ? e->Gv[prev] : nullptr,
+      (pd & 4) ? e->Ga[prev] : nullptr, e->tile_count + ((ep + 2) & 3));
+  e->dirty[prev] = 0;
+  e->dirty[set] = 1;
+  if (write_state) k_g2p<<<nb, 128, 0, e->stream>>>(k, fin, fout, e->npart, e->G0[set]);
+  e->launches += write_state ? 3 : 2;
+  LAUNCH_CHECK();
+  e->last_substep_slot = (int)(&s - e->slot.data());
+  e->last_substep_j = j;
+  e->last_was_backward = false;
+  return 0;
+}
+
+static int end_step(dsk_engine* e, StepSlot& s, int src_step, int dst_step) {
+  SimConst& k = e->k;
+  int nb = cdiv(k.stride, 256);
+  k_unsort<<<nb, 256, 0, e->stream>>>(k, s.frames + (size_t)e->S * e->frame_floats, e->npart, s.perm,
+                                      e->frame_of(e->ckpt, dst_step), 0);
+  e->launches += 1;
+  LAUNCH_CHECK();
+  if (e->K > 0)
+    CK(cudaMemcpy2DAsync(e->tools_of(e->tool_ckpt, dst_step), (size_t)e->K * 8 * 4,
+                         s.poses + (size_t)e->S * e->K * 8, (size_t)(e->S + 1) * e->K * 8 * 4, (size_t)e->K * 8 * 4,
+                         e->B, cudaMemcpyDeviceToDevice, e->stream));
+  invalidate_slots(e, dst_step);
+  s.src_step = (dst_step == src_step) ? -1 : src_step;
+  return 0;
+}
+
+// adjoint substep j of a slot: adjoint of frame j+1 in adjw[cur] -> adjoint of frame j in adjw[cur^1]
+static int run_substep_grad(dsk_engine* e, StepSlot& s, int j) {
+  SimConst& k = e->k;
+  int ep = ++e->epoch;
+  int set = ep & 1, prev = set ^ 1;
+  TileTrack tt{e->tile_epoch[set], e->tile_list[set], e->tile_count + (ep & 3)};
+  int nb = cdiv(k.stride, 128);
+  float* fin = s.frames + (size_t)j * e->frame_floats;
+  float* fnext = s.frames + (size_t)(j + 1) * e->frame_floats;
+  float* ain = e->adjw[e->bwd_cur];
+  float* aout = e->adjw[e->bwd_cur ^ 1];
+  k_p2g<false><<<nb, 128, 0, e->stream>>>(k, fin, nullptr, s.mat, e->npart, e->G0[set], tt, ep);
+  int pd = e->dirty[prev];
+  k_grid<<<grid_ctas(e), GRID_CTA, 0, e->stream>>>(
+      k, e->d_tools, s.poses, j, e->G0[set], e->Gv[set], tt.list, tt.count, pd ? e->tile_list[prev] : nullptr,
+      e->tile_count + ((ep - 1) & 3), (pd & 1) ? e->G0[prev] : nullptr, (pd & 2) ? e->Gv[prev] : nullptr,
+      (pd & 4) ? e->Ga[prev] : nullptr, e->tile_count + ((ep + 2) & 3));
+  e->dirty[prev] = 0;
+  e->dirty[set] = 7;
+  k_g2p_adj<<<nb, 128, 0, e->stream>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]);
+  k_grid_adj<<<grid_ctas(e), GRID_CTA, 0, e->stream>>>(k, e->d_tools, s.poses, j, e->G0[set], e->Ga[set], tt.list,
+                                                       tt.count, e->pose_adj, nullptr, nullptr, nullptr, nullptr,
+                                                       nullptr, nullptr);
+  k_p2g_adj<<<nb, 128, 0, e->stream>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]);
+  e->launches += 5;
+  LAUNCH_CHECK();
+  e->bwd_cur ^= 1;
+  e->last_substep_slot = (int)(&s - e->slot.data());
+  e->last_substep_j = j;
+  e->last_was_backward = true;
+  return 0;
+}
+
+static int ensure_step_frames(dsk_engine* e, int step, StepSlot** out) {
+  StepSlot& s = e->slot[step % e->slots];
+  if (s.src_step != step) {
+    // per-step checkpointing: recompute the substep frames of this step from its checkpoint
+    StepSlot* sp;
+    if (begin_step(e, step, step, &sp)) return -1;
+    for (int j = 0; j < e->S; j++)
+      if (run_substep(e, *sp, j, true)) return -1;
+    sp->src_step = step;
+  }
+  *out = &s;
+  return 0;
+}
+
+static int begin_backward(dsk_engine* e, int step, StepSlot** out) {
+  SimConst& k = e->k;
+  StepSlot* s;
+  if (ensure_step_frames(e, step, &s)) return -1;
+  int nb = cdiv(k.stride, 256);
+  e->bwd_cur = 0;
+  k_gather_sorted<<<nb, 256, 0, e->stream>>>(k, e->frame_of(e->adj_ckpt, step + 1), e->npart, s->perm, e->adjw[0]);
+  e->launches += 1;
+  LAUNCH_CHECK();
+  if (e->K > 0) {
+    CK(cudaMemsetAsync(e->pose_adj, 0, (size_t)(e->S + 1) * e->tool_floats * 4, e->stream));
+    CK(cudaMemcpy2DAsync(e->pose_adj + (size_t)e->S * e->K * 8, (size_t)(e->S + 1) * e->K * 8 * 4,
+                         e->tools_of(e->tool_adj_ckpt, step + 1), (size_t)e->K * 8 * 4, (size_t)e->K * 8 * 4, e->B,
+                         cudaMemcpyDeviceToDevice, e->stream));
+  }
+  *out = s;
+  return 0;
+}
+
+static int end_backward(dsk_engine* e, StepSlot& s, int step) {
+  SimConst& k = e->k;
+  if (e->K > 0) {
+    size_t sh = (size_t)(e->S + 1) * e->K * 8 * 4;
+    const float* act = e->A > 0 ? e->actions + (size_t)step * e->B * e->A : nullptr;
+    float* ag = e->A > 0 ? e->action_grad + (size_t)step * e->B * e->A : nullptr;
+    k_kinematics_adj<<<e->B, 32, sh, e->stream>>>(k, e->d_tools, s.poses, s.cidx, e->rand_num, act, e->pose_adj, ag);
+    e->launches += 1;
+    LAUNCH_CHECK();
+    // tool_adj_ckpt[step] += pose_adj[:, 0]
+    CK(cudaMemcpy2DAsync(e->stage, (size_t)e->K * 8 * 4, e->pose_adj, (size_t)(e->S + 1) * e->K * 8 * 4,
+                         (size_t)e->K * 8 * 4, e->B, cudaMemcpyDeviceToDevice, e->stream));
+    k_axpy<<<cdiv((int)e->tool_floats, 256), 256, 0, e->stream>>>(e->tools_of(e->tool_adj_ckpt, step), e->stage,
+                                                                  (size_t)e->B * e->K * 8);
+    e->launches += 1;
+  }
+  int nb = cdiv(k.stride, 256);
+  k_unsort<<<nb, 256, 0, e->stream>>>(k, e->adjw[e->bwd_cur], e->npart, s.perm, e->frame_of(e->adj_ckpt, step), 1);
+  e->launches += 1;
+  LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" {
+
+// ---- state ---------------------------------------------------------------------------------------------
+int dsk_set_particles(dsk_engine* e, int step, int env, int n, const float* x, const float* v, const float* F,
+                      const float* C, int on_device) {
+  CKE(e);
+  if (check_step(e, step, "dsk_set_particles")) return -1;
+  if (env < 0 || env >= e->B) return fail("env %d outside [0,%d)", env, e->B);
+  if (n < 0 || n > e->cfg.particle_capacity) return fail("n_particles %d exceeds capacity %d", n, e->cfg.particle_capacity);
+  if (!x || !v || !F || !C) return fail("dsk_set_particles needs x, v, F, C");
+  const float *dx, *dv, *dF, *dC;
+  size_t o = 0;
+  if (stage_in(e, x, (size_t)n * 3, on_device, o, &dx)) return -1;
+  o += (size_t)n * 3;
+  if (stage_in(e, v, (size_t)n * 3, on_device, o, &dv)) return -1;
+  o += (size_t)n * 3;
+  if (stage_in(e, F, (size_t)n * 9, on_device, o, &dF)) return -1;
+  o += (size_t)n * 9;
+  if (stage_in(e, C, (size_t)n * 9, on_device, o, &dC)) return -1;
+  if (n > 0) {
+    k_particles_io<<<cdiv(n, 256), 256, 0, e->stream>>>(e->k, e->frame_of(e->ckpt, step), env, n, (float*)dx, (float*)dv,
+                                                        (float*)dF, (float*)dC, 0);
+    e->launches += 1;
+    LAUNCH_CHECK();
+  }
+  e->h_npart[env] = n;
+  CK(cudaMemcpyAsync(e->npart + env, &e->h_npart[env], 4, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  invalidate_slots(e, step);
+  return 0;
+}
+
+static int get_frame_aos(dsk_engine* e, float* frame, int env, float* x, float* v, float* F, float* C, int on_device) {
+  int n = e->h_npart[env];
+  if (n == 0) return 0;
+  float *dx = x, *dv = v, *dF = F, *dC = C;
+  size_t o = 0;
+  if (!on_device) {
+    dx = x ? e->stage + o : nullptr;
+    o += (size_t)n * 3;
+    dv = v ? e->stage + o : nullptr;
+    o += (size_t)n * 3;
+    dF = F ? e->stage + o : nullptr;
+    o += (size_t)n * 9;
+    dC = C ? e->stage + o : nullptr;
+  }
+  k_particles_io<<<cdiv(n, 256), 256, 0, e->stream>>>(e->k, frame, env, n, dx, dv, dF, dC, 1);
+  e->launches += 1;
+  LAUNCH_CHECK();
+  if (!on_device) {
+    if (x) CK(cudaMemcpyAsync(x, dx, (size_t)n * 12, cudaMemcpyDeviceToHost, e->stream));
+    if (v) CK(cudaMemcpyAsync(v, dv, (size_t)n * 12, cudaMemcpyDeviceToHost, e->stream));
+    if (F) CK(cudaMemcpyAsync(F, dF, (size_t)n * 36, cudaMemcpyDeviceToHost, e->stream));
+    if (C) CK(cudaMemcpyAsync(C, dC, (size_t)n * 36, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  return 0;
+}
+
+int dsk_get_particles(dsk_engine* e, int step, int env, float* x, float* v, float* F, float* C, int on_device) {
+  CKE(e);
+  if (check_step(e, step, "dsk_get_particles")) return -1;
+  if (env < 0 || env >= e->B) return fail("env %d outside [0,%d)", env, e->B);
+  return get_frame_aos(e, e->frame_of(e->ckpt, step), env, x, v, F, C, on_device);
+}
+int dsk_get_n_particles(dsk_engine* e, int env, int* n) {
+  if (!e) return fail("null engine");
+  if (env < 0 || env >= e->B) return fail("env %d outside [0,%d)", env, e->B);
+  *n = e->h_npart[env];
+  return 0;
+}
+int dsk_set_tool_state(dsk_engine* e, int step, int env, int tool, const float* st) {
+  CKE(e);
+  if (check_step(e, step, "dsk_set_tool_state")) return -1;
+  if (env < 0 || env >= e->B || tool < 0 || tool >= e->K) return fail("bad env/tool index");
+  CK(cudaMemcpyAsync(e->tools_of(e->tool_ckpt, step) + ((size_t)env * e->K + tool) * 8, st, 32, cudaMemcpyHostToDevice,
+                     e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  invalidate_slots(e, step);
+  return 0;
+}
+int dsk_get_tool_state(dsk_engine* e, int step, int env, int tool, float* st) {
+  CKE(e);
+  if (check_step(e, step, "dsk_get_tool_state")) return -1;
+  if (env < 0 || env >= e->B || tool < 0 || tool >= e->K) return fail("bad env/tool index");
+  CK(cudaMemcpyAsync(st, e->tools_of(e->tool_ckpt, step) + ((size_t)env * e->K + tool) * 8, 32, cudaMemcpyDeviceToHost,
+                     e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+int dsk_copy_step(dsk_engine* e, int src, int dst) {
+  CKE(e);
+  if (check_step(e, src, "dsk_copy_step") || check_step(e, dst, "dsk_copy_step")) return -1;
+  if (src == dst) return 0;
+  CK(cudaMemcpyAsync(e->frame_of(e->ckpt, dst), e->frame_of(e->ckpt, src), e->frame_floats * 4, cudaMemcpyDeviceToDevice,
+                     e->stream));
+  CK(cudaMemcpyAsync(e->tools_of(e->tool_ckpt, dst), e->tools_of(e->tool_ckpt, src), e->tool_floats * 4,
+                     cudaMemcpyDeviceToDevice, e->stream));
+  invalidate_slots(e, dst);
+  return 0;
+}
+int dsk_set_material(dsk_engine* e, int env, const float* mu, const float* lam, const float* ys) {
+  CKE(e);
+  if (env < 0 || env >= e->B) return fail("env %d outside [0,%d)", env, e->B);
+  int n = e->h_npart[env];
+  const float* src[3] = {mu, lam, ys};
+  for (int c = 0; c < 3; c++)
+    if (src[c] && n > 0)
+      CK(cudaMemcpyAsync(e->mat + (size_t)c * e->k.stride + (size_t)env * e->Npad, src[c], (size_t)n * 4,
+                         cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  for (auto& s : e->slot) s.src_step = -1;
+  return 0;
+}
+int dsk_set_tool_param(dsk_engine* e, int tool, int which, double value) {
+  CKE(e);
+  if (tool < 0 || tool >= e->K) return fail("tool %d outside [0,%d)", tool, e->K);
+  ToolParams& T = e->h_tools[tool];
+  float v = (float)value;
+  switch (which) {
+    case DSK_PARAM_FRICTION: T.friction = v; break;
+    case DSK_PARAM_SOFTNESS: T.softness = v; break;
+    case DSK_PARAM_LOWER_X: case DSK_PARAM_LOWER_Y: case DSK_PARAM_LOWER_Z: T.lo[which - DSK_PARAM_LOWER_X] = v; break;
+    case DSK_PARAM_UPPER_X: case DSK_PARAM_UPPER_Y: case DSK_PARAM_UPPER_Z: T.hi[which - DSK_PARAM_UPPER_X] = v; break;
+    default: return fail("unknown tool parameter %d", which);
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemcpy(e->d_tools + tool, &T, sizeof T, cudaMemcpyHostToDevice));
+  for (auto& s : e->slot) s.src_step = -1;
+  return 0;
+}
+int dsk_get_tool_param(dsk_engine* e, int tool, int which, double* value) {
+  if (!e) return fail("null engine");
+  if (tool < 0 || tool >= e->K) return fail("tool %d outside [0,%d)", tool, e->K);
+  const ToolParams& T = e->h_tools[tool];
+  switch (which) {
+    case DSK_PARAM_FRICTION: *value = T.friction; break;
+    case DSK_PARAM_SOFTNESS: *value = T.softness; break;
+    case DSK_PARAM_LOWER_X: case DSK_PARAM_LOWER_Y: case DSK_PARAM_LOWER_Z: *value = T.lo[which - DSK_PARAM_LOWER_X]; break;
+    case DSK_PARAM_UPPER_X: case DSK_PARAM_UPPER_Y: case DSK_PARAM_UPPER_Z: *value = T.hi[which - DSK_PARAM_UPPER_X]; break;
+    default: return fail("unknown tool parameter %d", which);
+  }
+  return 0;
+}
+int dsk_set_gravity(dsk_engine* e, const double* g) {
+  CKE(e);
+  for (int d = 0; d < 3; d++) {
+    volatile float t = e->k.dt * (float)g[d];
+    e->k.grav[d] = t * 30.f;
+    e->cfg.gravity[d] = g[d];
+  }
+  for (auto& s : e->slot) s.src_step = -1;
+  return 0;
+}
+
+// ---- stepping -------------------------------------------------------------------------------------------
+int dsk_set_action(dsk_engine* e, int step, const float* actions, int on_device) {
+  CKE(e);
+  if (step < 0 || step >= e->H) return fail("dsk_set_action: step %d outside [0,%d)", step, e->H);
+  if (e->A == 0) return 0;
+  const float* src;
+  int n = e->B * e->A;
+  if (stage_in(e, actions, n, on_device, 0, &src)) return -1;
+  k_clip_actions<<<cdiv(n, 256), 256, 0, e->stream>>>(e->actions + (size_t)step * n, src, n);
+  e->launches += 1;
+  LAUNCH_CHECK();
+  if (!on_device) CK(cudaStreamSynchronize(e->stream));  // the staging buffer may be reused by the next call
+  for (auto& s : e->slot)
+    if (s.action_step == step) s.src_step = -1;
+  return 0;
+}
+int dsk_forward_step(dsk_engine* e, int src_step, int dst_step, int action_step) {
+  CKE(e);
+  if (check_step(e, src_step, "dsk_forward_step") || check_step(e, dst_step, "dsk_forward_step")) return -1;
+  if (action_step >= e->H) return fail("action step %d outside [0,%d)", action_step, e->H);
+  StepSlot* s;
+  if (begin_step(e, src_step, action_step, &s)) return -1;
+  for (int j = 0; j < e->S; j++)
+    if (run_substep(e, *s, j, true)) return -1;
+  if (end_step(e, *s, src_step, dst_step)) return -1;
+  if (action_step != src_step) s->src_step = -1;  // backward_step(step) assumes action_step == step
+  e->last_fwd_frame = -1;
+  return 0;
+}
+int dsk_backward_step(dsk_engine* e, int step) {
+  CKE(e);
+  if (step < 0 || step >= e->H) return fail("dsk_backward_step: step %d outside [0,%d)", step, e->H);
+  StepSlot* s;
+  if (begin_backward(e, step, &s)) return -1;
+  for (int j = e->S - 1; j >= 0; j--)
+    if (run_substep_grad(e, *s, j)) return -1;
+  if (end_backward(e, *s, step)) return -1;
+  e->last_bwd_frame = -1;
+  return 0;
+}
+int dsk_substep(dsk_engine* e, int f) {
+  CKE(e);
+  if (f < 0 || f >= e->H * e->S) return fail("dsk_substep: frame %d outside the horizon (%d steps x %d substeps)", f, e->H, e->S);
+  int step = f / e->S, j = f % e->S;
+  StepSlot* s = &e->slot[step % e->slots];
+  if (j == 0) {
+    if (begin_step(e, step, step, &s)) return -1;
+  } else if (e->last_fwd_frame != f - 1) {
+    return fail("dsk_substep(%d): substeps of a step must run in ascending order starting at a step boundary (last was %d)", f, e->last_fwd_frame);
+  }
+  if (run_substep(e, *s, j, true)) return -1;
+  e->last_fwd_frame = f;
+  if (j == e->S - 1) {
+    if (end_step(e, *s, step, step + 1)) return -1;
+  }
+  return 0;
+}
+int dsk_substep_grad(dsk_engine* e, int f) {
+  CKE(e);
+  if (f < 0 || f >= e->H * e->S) return fail("dsk_substep_grad: frame %d outside the horizon", f);
+  int step = f / e->S, j = f % e->S;
+  StepSlot* s = &e->slot[step % e->slots];
+  if (j == e->S - 1) {
+    if (begin_backward(e, step, &s)) return -1;
+  } else if (e->last_bwd_frame != f + 1) {
+    return fail("dsk_substep_grad(%d): adjoint substeps of a step must run in descending order from the step's last substep (last was %d)", f, e->last_bwd_frame);
+  }
+  if (run_substep_grad(e, *s, j)) return -1;
+  e->last_bwd_frame = f;
+  if (j == 0) {
+    if (end_backward(e, *s, step)) return -1;
+  }
+  return 0;
+}
+
+// ---- adjoints --------------------------------------------------------------------------------------------
+int dsk_zero_grad(dsk_engine* e) {
+  CKE(e);
+  CK(cudaMemsetAsync(e->adj_ckpt, 0, (size_t)(e->H + 1) * e->frame_floats * 4, e->stream));
+  CK(cudaMemsetAsync(e->tool_adj_ckpt, 0, (size_t)(e->H + 1) * e->tool_floats * 4, e->stream));
+  CK(cudaMemsetAsync(e->action_grad, 0, (size_t)e->H * e->B * std::max(1, e->A) * 4, e->stream));
+  return 0;
+}
+int dsk_add_particle_grad(dsk_engine* e, int step, const float* gx, const float* gv, const float* gF, const float* gC,
+                          int on_device) {
+  CKE(e);
+  if (check_step(e, step, "dsk_add_particle_grad")) return -1;
+  int cap = e->cfg.particle_capacity;
+  size_t n3 = (size_t)e->B * cap * 3, n9 = (size_t)e->B * cap * 9;
+  const float *dx, *dv, *dF, *dC;
+  size_t o = 0;
+  if (stage_in(e, gx, n3, on_device, o, &dx)) return -1;
+  o += gx ? n3 : 0;
+  if (stage_in(e, gv, n3, on_device, o, &dv)) return -1;
+  o += gv ? n3 : 0;
+  if (stage_in(e, gF, n9, on_device, o, &dF)) return -1;
+  o += gF ? n9 : 0;
+  if (stage_in(e, gC, n9, on_device, o, &dC)) return -1;
+  k_add_particle_grad<<<cdiv(e->k.stride, 256), 256, 0, e->stream>>>(e->k, e->frame_of(e->adj_ckpt, step), e->npart, cap,
+                                                                     dx, dv, dF, dC);
+  e->launches += 1;
+  LAUNCH_CHECK();
+  if (!on_device) CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+int dsk_add_tool_grad(dsk_engine* e, int step, const float* g, int on_device) {
+  CKE(e);
+  if (check_step(e, step, "dsk_add_tool_grad")) return -1;
+  if (e->K == 0) return 0;
+  const float* d;
+  if (stage_in(e, g, e->tool_floats, on_device, 0, &d)) return -1;
+  k_axpy<<<cdiv((int)e->tool_floats, 256), 256, 0, e->stream>>>(e->tools_of(e->tool_adj_ckpt, step), d, e->tool_floats);
+  e->launches += 1;
+  LAUNCH_CHECK();
+  if (!on_device) CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+int dsk_get_particle_grad(dsk_engine* e, int step, int env, float* gx, float* gv, float* gF, float* gC, int on_device) {
+  CKE(e);
+  if (check_step(e, step, "dsk_get_particle_grad")) return -1;
+  if (env < 0 || env >= e->B) return fail("env %d outside [0,%d)", env, e->B);
+  return get_frame_aos(e, e->frame_of(e->adj_ckpt, step), env, gx, gv, gF, gC, on_device);
+}
+int dsk_get_tool_grad(dsk_engine* e, int step, int env, int tool, float* g8) {
+  CKE(e);
+  if (check_step(e, step, "dsk_get_tool_grad")) return -1;
+  if (env < 0 || env >= e->B || tool < 0 || tool >= e->K) return fail("bad env/tool index");
+  CK(cudaMemcpyAsync(g8, e->tools_of(e->tool_adj_ckpt, step) + ((size_t)env * e->K + tool) * 8, 32,
+                     cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+int dsk_scale_grad(dsk_engine* e, int step, double alpha) {
+  CKE(e);
+  if (check_step(e, step, "dsk_scale_grad")) return -1;
+  k_scale<<<cdiv((int)e->frame_floats, 256), 256, 0, e->stream>>>(e->frame_of(e->adj_ckpt, step), e->frame_floats, (float)alpha);
+  // decay_kernel scales position.grad and rotation.grad (function.py:74-77); gap.grad is left alone
+  if (e->K > 0) {
+    std::vector<float> h(e->tool_floats);
+    CK(cudaMemcpyAsync(h.data(), e->tools_of(e->tool_adj_ckpt, step), e->tool_floats * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    for (size_t i = 0; i < e->tool_floats; i++)
+      if (i % 8 != 7) h[i] *= (float)alpha;
+    CK(cudaMemcpyAsync(e->tools_of(e->tool_adj_ckpt, step), h.data(), e->tool_floats * 4, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  e->launches += 1;
+  LAUNCH_CHECK();
+  return 0;
+}
+int dsk_get_action_grad(dsk_engine* e, int step, float* out, int on_device) {
+  CKE(e);
+  if (step < 0 || step >= e->H) return fail("dsk_get_action_grad: step %d outside [0,%d)", step, e->H);
+  if (e->A == 0) return 0;
+  size_t n = (size_t)e->B * e->A;
+  CK(cudaMemcpyAsync(out, e->action_grad + (size_t)step * n, n * 4, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
+  if (!on_device) CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+// ---- observations ----------------------------------------------------------------------------------------
+int dsk_get_obs(dsk_engine* e, int step, float* xv, float* tools, int on_device) {
+  CKE(e);
+  if (check_step(e, step, "dsk_get_obs")) return -1;
+  int cap = e->cfg.particle_capacity;
+  size_t n = (size_t)e->B * cap * 6;
+  if (xv) {
+    float* d = on_device ? xv : e->stage;
+    k_get_obs<<<cdiv(e->k.stride, 256), 256, 0, e->stream>>>(e->k, e->frame_of(e->ckpt, step), e->npart, cap, d);
+    e->launches += 1;
+    LAUNCH_CHECK();
+    if (!on_device) CK(cudaMemcpyAsync(xv, d, n * 4, cudaMemcpyDeviceToHost, e->stream));
+  }
+  if (tools && e->K > 0)
+    CK(cudaMemcpyAsync(tools, e->tools_of(e->tool_ckpt, step), e->tool_floats * 4,
+                       on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
+  if (!on_device) CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+int dsk_min_dist_cols(dsk_engine* e, int* ncols) {
+  if (!e) return fail("null engine");
+  *ncols = e->ncols;
+  return 0;
+}
+int dsk_compute_min_dist(dsk_engine* e, int step, float* out, int on_device) {
+  CKE(e);
+  if (check_step(e, step, "dsk_compute_min_dist")) return -1;
+  if (e->ncols == 0) return 0;
+  int cap = e->cfg.particle_capacity;
+  size_t n = (size_t)e->B * cap * e->ncols;
+  if (!on_device && n > e->stage_floats) return fail("staging buffer too small");
+  float* d = on_device ? out : e->stage;
+  k_min_dist<<<cdiv(e->k.stride, 128), 128, 0, e->stream>>>(e->k, e->d_tools, e->frame_of(e->ckpt, step), e->npart,
+                                                           e->tools_of(e->tool_ckpt, step), cap, e->ncols, d);
+  e->launches += 1;
+  LAUNCH_CHECK();
+  if (!on_device) {
+    CK(cudaMemcpyAsync(out, d, n * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  return 0;
+}
+int dsk_compute_min_dist_grad(dsk_engine* e, int step, const float* g, int on_device) {
+  CKE(e);
+  if (check_step(e, step, "dsk_compute_min_dist_grad")) return -1;
+  if (e->ncols == 0) return 0;
+  int cap = e->cfg.particle_capacity;
+  const float* d;
+  if (stage_in(e, g, (size_t)e->B * cap * e->ncols, on_device, 0, &d)) return -1;
+  k_min_dist_adj<<<cdiv(e->k.stride, 128), 128, 0, e->stream>>>(e->k, e->d_tools, e->frame_of(e->ckpt, step), e->npart,
+                                                               e->tools_of(e->tool_ckpt, step), cap, e->ncols, d,
+                                                               e->frame_of(e->adj_ckpt, step),
+                                                               e->tools_of(e->tool_adj_ckpt, step));
+  e->launches += 1;
+  LAUNCH_CHECK();
+  if (!on_device) CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+int dsk_compute_grid_m(dsk_engine* e, int step, float* out, int on_device) {
+  CKE(e);
+  if (check_step(e, step, "dsk_compute_grid_m")) return -1;
+  size_t n = (size_t)e->B * e->k.nnode;
+  float* d = on_device ? out : e->stage;
+  CK(cudaMemsetAsync(d, 0, n * 4, e->stream));
+  k_grid_m<<<cdiv(e->k.stride, 128), 128, 0, e->stream>>>(e->k, e->frame_of(e->ckpt, step), e->npart, d);
+  e->launches += 1;
+  LAUNCH_CHECK();
+  if (!on_device) {
+    CK(cudaMemcpyAsync(out, d, n * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  return 0;
+}
+int dsk_compute_grid_m_grad(dsk_engine* e, int step, const float* gm, int on_device) {
+  CKE(e);
+  if (check_step(e, step, "dsk_compute_grid_m_grad")) return -1;
+  const float* d;
+  if (stage_in(e, gm, (size_t)e->B * e->k.nnode, on_device, 0, &d)) return -1;
+  k_grid_m_adj<<<cdiv(e->k.stride, 128), 128, 0, e->stream>>>(e->k, e->frame_of(e->ckpt, step), e->npart, d,
+                                                             e->frame_of(e->adj_ckpt, step));
+  e->launches += 1;
+  LAUNCH_CHECK();
+  if (!on_device) CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+// ---- introspection ---------------------------------------------------------------------------------------
+__global__ void k_debug_cells(SimConst k, const float* __restrict__ ck, int env, int n, int* base, int* key) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  int gid = env * k.Npad + p;
+  int bx, by, bz;
+  int kk = cell_key(k, ck[gid], ck[k.stride + gid], ck[2 * k.stride + gid], bx, by, bz);
+  base[p * 3] = bx;
+  base[p * 3 + 1] = by;
+  base[p * 3 + 2] = bz;
+  key[p] = kk;
+}
+__global__ void k_debug_occupancy(SimConst k, const float* __restrict__ frame, const int* __restrict__ perm_unused,
+                                  int env, int n, unsigned char* occ) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  int gid = env * k.Npad + p;
+  Stencil s;
+  make_stencil(k, frame[gid], frame[k.stride + gid], frame[2 * k.stride + gid], s);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      for (int l = 0; l < 3; l++) occ[((size_t)(s.bx + i) * k.n + (s.by + j)) * k.n + (s.bz + l)] = 1;
+}
+__global__ void k_svd_probe(int n, const float* F, float* U, float* sg, float* V) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  M3 A, u, v;
+  for (int q = 0; q < 9; q++) A.m[q] = F[i * 9 + q];
+  float3 s;
+  svd3(A, u, s, v);
+  for (int q = 0; q < 9; q++) {
+    U[i * 9 + q] = u.m[q];
+    V[i * 9 + q] = v.m[q];
+  }
+  sg[i * 3] = s.x;
+  sg[i * 3 + 1] = s.y;
+  sg[i * 3 + 2] = s.z;
+}
+
+int dsk_debug_cell_index(dsk_engine* e, int step, int env, int32_t* base, int32_t* key) {
+  CKE(e);
+  if (check_step(e, step, "dsk_debug_cell_index")) return -1;
+  if (env < 0 || env >= e->B) return fail("env %d outside [0,%d)", env, e->B);
+  int n = e->h_npart[env];
+  if (!n) return 0;
+  int* d = (int*)e->stage;
+  k_debug_cells<<<cdiv(n, 256), 256, 0, e->stream>>>(e->k, e->frame_of(e->ckpt, step), env, n, d, d + (size_t)n * 3);
+  e->launches += 1;
+  LAUNCH_CHECK();
+  if (base) CK(cudaMemcpyAsync(base, d, (size_t)n * 12, cudaMemcpyDeviceToHost, e->stream));
+  if (key) CK(cudaMemcpyAsync(key, d + (size_t)n * 3, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+int dsk_debug_sort_order(dsk_engine* e, int env, int32_t* perm) {
+  CKE(e);
+  if (env < 0 || env >= e->B) return fail("env %d outside [0,%d)", env, e->B);
+  if (e->last_substep_slot < 0) return fail("no substep has run yet");
+  int n = e->h_npart[env];
+  CK(cudaMemcpyAsync(perm, e->slot[e->last_substep_slot].perm + (size_t)env * e->Npad, (size_t)n * 4,
+                     cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+static int grid_out(dsk_engine* e, const float4* G, int env, float* v3, float* m) {
+  SimConst& k = e->k;
+  float* dv = e->stage;
+  float* dm = e->stage + (size_t)k.nnode * 3;
+  k_grid_to_dense<<<cdiv(k.nnode, 256), 256, 0, e->stream>>>(k, G, env, v3 ? dv : nullptr, m ? dm : nullptr, nullptr,
+                                                             nullptr, 0);
+  e->launches += 1;
+  LAUNCH_CHECK();
+  if (v3) CK(cudaMemcpyAsync(v3, dv, (size_t)k.nnode * 12, cudaMemcpyDeviceToHost, e->stream));
+  if (m) CK(cudaMemcpyAsync(m, dm, (size_t)k.nnode * 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+int dsk_debug_grid(dsk_engine* e, int env, float* v_in, float* v_out, float* m, uint8_t* occupied) {
+  CKE(e);
+  if (env < 0 || env >= e->B) return fail("env %d outside [0,%d)", env, e->B);
+  if (e->last_substep_slot < 0) return fail("no substep has run yet");
+  int set = e->epoch & 1;
+  if (e->last_was_backward) {
+    if (grid_out(e, e->G0[set], env, v_in, m)) return -1;
+    if (v_out && grid_out(e, e->Gv[set], env, v_out, nullptr)) return -1;
+  } else {
+    if (v_in) return fail("v_in is overwritten in place by the forward grid kernel; run dsk_substep_grad to inspect it");
+    if (grid_out(e, e->G0[set], env, v_out, m)) return -1;
+  }
+  if (occupied) {
+    SimConst& k = e->k;
+    int n = e->h_npart[env];
+    unsigned char* d = (unsigned char*)e->stage;
+    CK(cudaMemsetAsync(d, 0, k.nnode, e->stream));
+    StepSlot& s = e->slot[e->last_substep_slot];
+    if (n)
+      k_debug_occupancy<<<cdiv(n, 256), 256, 0, e->stream>>>(k, s.frames + (size_t)e->last_substep_j * e->frame_floats,
+                                                             nullptr, env, n, d);
+    e->launches += 1;
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(occupied, d, k.nnode, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  return 0;
+}
+int dsk_debug_grid_grad(dsk_engine* e, int env, float* g_v_in, float* g_v_out, float* g_m) {
+  CKE(e);
+  if (env < 0 || env >= e->B) return fail("env %d outside [0,%d)", env, e->B);
+  if (!e->last_was_backward) return fail("grid adjoints exist only after dsk_substep_grad");
+  if (g_v_out) return fail("the adjoint of grid_v_out is overwritten in place by k_grid_adj");
+  return grid_out(e, e->Ga[e->epoch & 1], env, g_v_in, g_m);
+}
+int dsk_debug_frame(dsk_engine* e, int f, int env, float* x, float* v, float* F, float* C) {
+  CKE(e);
+  if (env < 0 || env >= e->B) return fail("env %d outside [0,%d)", env, e->B);
+  int step = f / e->S, j = f % e->S;
+  StepSlot* s = &e->slot[step % e->slots];
+  if (s->src_step != step && !(e->last_substep_slot == step % e->slots)) {
+    if (j == 0 && step <= e->H) return dsk_get_particles(e, step, env, x, v, F, C, 0);
+    if (step >= 1) {  // frame S of the previous step
+      s = &e->slot[(step - 1) % e->slots];
+      if (j == 0 && s->src_step == step - 1) j = e->S;
+      else return fail("frame %d is not resident in the step-slot ring", f);
+    } else {
+      return fail("frame %d is not resident in the step-slot ring", f);
+    }
+  }
+  // un-sort into the staging area, then reuse the AoS reader
+  SimConst& k = e->k;
+  float* tmp = e->adjw[e->bwd_cur ^ 1];  // scratch frame (overwritten by the next adjoint substep anyway)
+  k_unsort<<<cdiv(k.stride, 256), 256, 0, e->stream>>>(k, s->frames + (size_t)j * e->frame_floats, e->npart, s->perm, tmp, 0);
+  e->launches += 1;
+  LAUNCH_CHECK();
+  return get_frame_aos(e, tmp, env, x, v, F, C, 0);
+}
+int dsk_debug_tool_frame(dsk_engine* e, int f, int env, int tool, float* st, int32_t* cidx) {
+  CKE(e);
+  if (env < 0 || env >= e->B || tool < 0 || tool >= e->K) return fail("bad env/tool index");
+  int step = f / e->S, j = f % e->S;
+  if (j == 0 && step >= 1) {
+    step -= 1;
+    j = e->S;
+  }
+  StepSlot& s = e->slot[step % e->slots];
+  if (st)
+    CK(cudaMemcpyAsync(st, s.poses + (((size_t)env * (e->S + 1) + j) * e->K + tool) * 8, 32, cudaMemcpyDeviceToHost, e->stream));
+  if (cidx && e->k.npairs > 0)
+    CK(cudaMemcpyAsync(cidx, s.cidx + ((size_t)env * (e->S + 1) + j) * e->k.npairs, (size_t)e->k.npairs * 4,
+                       cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+int dsk_debug_tool_frame_grad(dsk_engine* e, int f, int env, int tool, float* g8) {
+  CKE(e);
+  if (env < 0 || env >= e->B || tool < 0 || tool >= e->K) return fail("bad env/tool index");
+  int j = f % e->S;
+  if (j == 0 && f > 0 && e->last_bwd_frame != f) j = e->S;
+  CK(cudaMemcpyAsync(g8, e->pose_adj + (((size_t)env * (e->S + 1) + j) * e->K + tool) * 8, 32, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+int dsk_debug_svd(dsk_engine* e, int n, const float* F, float* U, float* sig, float* V) {
+  CKE(e);
+  if ((size_t)n * 30 > e->stage_floats) return fail("too many matrices for the staging buffer");
+  float* d = e->stage;
+  CK(cudaMemcpyAsync(d, F, (size_t)n * 36, cudaMemcpyHostToDevice, e->stream));
+  k_svd_probe<<<cdiv(n, 128), 128, 0, e->stream>>>(n, d, d + (size_t)n * 9, d + (size_t)n * 18, d + (size_t)n * 21);
+  e->launches += 1;
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(U, d + (size_t)n * 9, (size_t)n * 36, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(sig, d + (size_t)n * 18, (size_t)n * 12, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(V, d + (size_t)n * 21, (size_t)n * 36, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,384 @@
+// Per-env-step kernels around the substep loop: counting sort by cell, tool kinematics
+// (forward_kinematics + tool-tool collision projection), state IO, observation helpers.
+#pragma once
+#include "kernels_common.cuh"
+
+// ---- counting sort by cell (key = tile-major linear cell index of the stencil base) -------------------
+DSK_DEV int cell_key(const SimConst& k, float x, float y, float z, int& bx, int& by, int& bz) {
+  float fx, w[3];
+  bspline1(x, k.inv_dx, k.n, bx, fx, w);
+  bspline1(y, k.inv_dx, k.n, by, fx, w);
+  bspline1(z, k.inv_dx, k.n, bz, fx, w);
+  return node_offset(bx, by, bz, k.nt);
+}
+__global__ void k_sort_bin(SimConst k, const float* __restrict__ ck, const int* __restrict__ npart,
+                           int* __restrict__ cell_count, int* __restrict__ key, int* __restrict__ rank) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= k.stride) return;
+  int env = gid / k.Npad, p = gid - env * k.Npad;
+  if (p >= npart[env]) return;
+  int bx, by, bz;
+  int kk = cell_key(k, ck[gid], ck[k.stride + gid], ck[2 * k.stride + gid], bx, by, bz);
+  key[gid] = kk;
+  rank[gid] = atomicAdd(&cell_count[(size_t)env * k.nnode + kk], 1);
+}
+// exclusive scan of cell_count per env, in place.  One 1024-thread CTA per env; each warp owns a
+// contiguous segment and walks it in coalesced 32-wide steps.
+__global__ void __launch_bounds__(1024) k_sort_scan(SimConst k, int* __restrict__ cell_count) {
+  __shared__ int wsum[32];
+  int env = blockIdx.x;
+  int* c = cell_count + (size_t)env * k.nnode;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int seg = (k.nnode + 31) / 32;
+  seg = (seg + 31) & ~31;
+  int lo = warp * seg, hi = min(lo + seg, k.nnode);
+  int tot = 0;
+  for (int i = lo + lane; i < hi; i += 32) tot += c[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+  if (lane == 0) wsum[warp] = tot;
+  __syncthreads();
+  if (warp == 0) {
+    int v = wsum[lane], s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += t;
+    }
+    wsum[lane] = s - v;
+  }
+  __syncthreads();
+  int carry = wsum[warp];
+  for (int i0 = lo; i0 < hi; i0 += 32) {
+    int i = i0 + lane;
+    int v = i < hi ? c[i] : 0, s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += t;
+    }
+    if (i < hi) c[i] = carry + s - v;
+    carry += __shfl_sync(0xffffffffu, s, 31);
+  }
+}
+// scatter checkpoint (canonical order) -> work frame 0 (sorted order); also permutes the material arrays
+__global__ void k_sort_scatter(SimConst k, const float* __restrict__ ck, const float* __restrict__ mat,
+                               const int* __restrict__ npart, const int* __restrict__ cell_start,
+                               const int* __restrict__ key, const int* __restrict__ rank, int use_sort,
+                               float* __restrict__ w0, float* __restrict__ mat_sorted, int* __restrict__ perm) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= k.stride) return;
+  int env = gid / k.Npad, p = gid - env * k.Npad;
+  if (p >= npart[env]) return;
+  int dst = use_sort ? env * k.Npad + cell_start[(size_t)env * k.nnode + key[gid]] + rank[gid] : gid;
+  perm[dst] = p;
+#pragma unroll
+  for (int c = 0; c < FRAME_COMPS; c++) w0[c * k.stride + dst] = ck[c * k.stride + gid];
+#pragma unroll
+  for (int c = 0; c < 3; c++) mat_sorted[c * k.stride + dst] = mat[c * k.stride + gid];
+}
+// sorted frame -> canonical checkpoint.  accumulate=1: += (adjoint checkpoints)
+__global__ void k_unsort(SimConst k, const float* __restrict__ w, const int* __restrict__ npart,
+                         const int* __restrict__ perm, float* __restrict__ ck, int accumulate) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= k.stride) return;
+  int env = gid / k.Npad, d = gid - env * k.Npad;
+  if (d >= npart[env]) return;
+  int dst = env * k.Npad + perm[gid];
+  if (accumulate) {
+#pragma unroll
+    for (int c = 0; c < FRAME_COMPS; c++) ck[c * k.stride + dst] += w[c * k.stride + gid];
+  } else {
+#pragma unroll
+    for (int c = 0; c < FRAME_COMPS; c++) ck[c * k.stride + dst] = w[c * k.stride + gid];
+  }
+}
+// canonical (adjoint) checkpoint -> sorted frame
+__global__ void k_gather_sorted(SimConst k, const float* __restrict__ ck, const int* __restrict__ npart,
+                                const int* __restrict__ perm, float* __restrict__ w) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= k.stride) return;
+  int env = gid / k.Npad, d = gid - env * k.Npad;
+  if (d >= npart[env]) return;
+  int src = env * k.Npad + perm[gid];
+#pragma unroll
+  for (int c = 0; c < FRAME_COMPS; c++) w[c * k.stride + gid] = ck[c * k.stride + src];
+}
+
+// ---- particle-major <-> SoA conversion for the API --------------------------------------------------------
+// aos: x[n,3] v[n,3] F[n,9] C[n,9] (reference layout); direction 0: aos -> frame, 1: frame -> aos, 2: frame += aos
+__global__ void k_particles_io(SimConst k, float* __restrict__ frame, int env, int n, float* x, float* v, float* F,
+                               float* C, int direction) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  int gid = env * k.Npad + p;
+  for (int c = 0; c < FRAME_COMPS; c++) {
+    float* a;
+    int idx;
+    if (c < 3) { a = x; idx = p * 3 + c; }
+    else if (c < 6) { a = v; idx = p * 3 + (c - 3); }
+    else if (c < 15) { a = C; idx = p * 9 + (c - 6); }
+    else { a = F; idx = p * 9 + (c - 15); }
+    if (!a) continue;
+    float* f = frame + c * k.stride + gid;
+    if (direction == 0) *f = a[idx];
+    else if (direction == 1) a[idx] = *f;
+    else *f += a[idx];
+  }
+}
+// batched [B,cap,3]-style adjoint injection (function.py:130-135): gx,gv [B,cap_in,3]; gF,gC [B,cap_in,9]
+__global__ void k_add_particle_grad(SimConst k, float* __restrict__ frame, const int* __restrict__ npart, int cap_in,
+                                    const float* gx, const float* gv, const float* gF, const float* gC) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= k.stride) return;
+  int env = gid / k.Npad, p = gid - env * k.Npad;
+  if (p >= npart[env] || p >= cap_in) return;
+  size_t row = (size_t)env * cap_in + p;
+  if (gx) for (int c = 0; c < 3; c++) frame[(CX + c) * k.stride + gid] += gx[row * 3 + c];
+  if (gv) for (int c = 0; c < 3; c++) frame[(CV + c) * k.stride + gid] += gv[row * 3 + c];
+  if (gC) for (int c = 0; c < 9; c++) frame[(CC + c) * k.stride + gid] += gC[row * 9 + c];
+  if (gF) for (int c = 0; c < 9; c++) frame[(CF + c) * k.stride + gid] += gF[row * 9 + c];
+}
+// observation: xv [B,cap,6] (function.py:90-95)
+__global__ void k_get_obs(SimConst k, const float* __restrict__ frame, const int* __restrict__ npart, int cap_out,
+                          float* __restrict__ xv) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= k.stride) return;
+  int env = gid / k.Npad, p = gid - env * k.Npad;
+  if (p >= cap_out) return;
+  size_t row = (size_t)env * cap_out + p;
+  bool live = p < npart[env];
+  for (int c = 0; c < 6; c++) xv[row * 6 + c] = live ? frame[c * k.stride + gid] : 0.f;
+}
+__global__ void k_scale(float* a, size_t n, float alpha) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] *= alpha;
+}
+__global__ void k_axpy(float* y, const float* x, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] += x[i];
+}
+__global__ void k_clip_actions(float* dst, const float* src, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = fminf(1.f, fmaxf(-1.f, src[i]));
+}
+
+// ---- tool kinematics ---------------------------------------------------------------------------------------
+// forward_kinematics of one tool, primive_base.py:152-156 / primitives.py:120-136 / :456-460
+struct ToolVel {
+  float3 v, w;
+  float gap_vel;
+};
+DSK_DEV Pose tool_fk(const ToolParams& T, const Pose& P, const ToolVel& u) {
+  Pose N;
+  N.gap = P.gap;
+  float3 step = u.v;
+  if (T.type == DSK_TOOL_ROLLINGPIN_EXT) {
+    float dw = u.v.x, dth = u.v.y, dy = u.v.z;
+    float3 y_dir = qrot_rn(P.q, f3(0.f, -1.f, 0.f));
+    float3 x_dir = (dw * 0.03f + u.w.x) * cross(f3(0.f, 1.f, 0.f), y_dir);
+    x_dir.y = dy;
+    N.q = qmul(w2quat(f3(0.f, -dth, 0.f)), qmul(P.q, w2quat(f3(0.f, dw, 0.f))));
+    step = x_dir;
+  } else if (T.type == DSK_TOOL_GRIPPER) {
+    N.gap = tmin(tmax(P.gap - u.gap_vel, T.min_gap), T.max_gap);
+    N.q = qmul(P.q, w2quat(u.w));
+  } else {
+    N.q = qmul(w2quat(u.w), P.q);
+  }
+  N.p = f3(tmax(tmin(P.p.x + step.x, T.hi[0]), T.lo[0]), tmax(tmin(P.p.y + step.y, T.hi[1]), T.lo[1]),
+           tmax(tmin(P.p.z + step.z, T.hi[2]), T.lo[2]));
+  return N;
+}
+// adjoint of tool_fk: given g(N) accumulates g(P), g(u)
+DSK_DEV void tool_fk_adj(const ToolParams& T, const Pose& P, const ToolVel& u, const PoseAdj& gN, PoseAdj& gP,
+                         ToolVel& gu) {
+  float3 step = u.v;
+  float3 y_dir = f3(0, 0, 0), cr = f3(0, 0, 0);
+  float sc = 0.f;
+  if (T.type == DSK_TOOL_ROLLINGPIN_EXT) {
+    y_dir = qrot_rn(P.q, f3(0.f, -1.f, 0.f));
+    cr = cross(f3(0.f, 1.f, 0.f), y_dir);
+    sc = u.v.x * 0.03f + u.w.x;
+    step = sc * cr;
+    step.y = u.v.z;
+  }
+  // position clamp: max(min(a, hi), lo)
+  float3 gstep;
+  {
+    float a0 = P.p.x + step.x, a1 = P.p.y + step.y, a2 = P.p.z + step.z;
+    float g0 = (a0 < T.hi[0] && T.lo[0] < tmin(a0, T.hi[0])) ? gN.p.x : 0.f;
+    float g1 = (a1 < T.hi[1] && T.lo[1] < tmin(a1, T.hi[1])) ? gN.p.y : 0.f;
+    float g2 = (a2 < T.hi[2] && T.lo[2] < tmin(a2, T.hi[2])) ? gN.p.z : 0.f;
+    gstep = f3(g0, g1, g2);
+    gP.p += gstep;
+  }
+  if (T.type == DSK_TOOL_ROLLINGPIN_EXT) {
+    float dw = u.v.x, dth = u.v.y;
+    // step = (sc*cr.x, dy, sc*cr.z)
+    gu.v.z += gstep.y;
+    float gsc = gstep.x * cr.x + gstep.z * cr.z;
+    float3 gcr = f3(sc * gstep.x, 0.f, sc * gstep.z);
+    gu.v.x += 0.03f * gsc;
+    gu.w.x += gsc;
+    // cr = e_y x y_dir  -> g(y_dir) = gcr x e_y
+    float3 gy = cross(gcr, f3(0.f, 1.f, 0.f));
+    float3 gdummy = f3(0, 0, 0);
+    qrot_adj(P.q, f3(0.f, -1.f, 0.f), gy, gP.q, gdummy);
+    // N.q = qmul(qa, qmul(P.q, qb)), qa = w2quat(0,-dth,0), qb = w2quat(0,dw,0)
+    Q4 qa = w2quat(f3(0.f, -dth, 0.f)), qb = w2quat(f3(0.f, dw, 0.f));
+    Q4 inner = qmul(P.q, qb);
+    Q4 gqa = {0, 0, 0, 0}, ginner = {0, 0, 0, 0}, gqb = {0, 0, 0, 0};
+    qmul_adj(qa, inner, gN.q, gqa, ginner);
+    qmul_adj(P.q, qb, ginner, gP.q, gqb);
+    float3 ga = f3(0, 0, 0), gb = f3(0, 0, 0);
+    w2quat_adj(f3(0.f, -dth, 0.f), gqa, ga);
+    w2quat_adj(f3(0.f, dw, 0.f), gqb, gb);
+    gu.v.y += -ga.y;
+    gu.v.x += gb.y;
+  } else if (T.type == DSK_TOOL_GRIPPER) {
+    gu.v += gstep;
+    float a = P.gap - u.gap_vel;
+    float m1 = tmax(a, T.min_gap);
+    float g = (m1 < T.max_gap) ? gN.gap : 0.f;     // min(m1, max_gap): m1 gets it iff m1 < max_gap
+    g = (T.min_gap < a) ? g : 0.f;                 // max(a, min_gap): a gets it iff min_gap < a
+    gP.gap += g;
+    gu.gap_vel -= g;
+    Q4 qw = w2quat(u.w);
+    Q4 gqw = {0, 0, 0, 0};
+    qmul_adj(P.q, qw, gN.q, gP.q, gqw);
+    w2quat_adj(u.w, gqw, gu.w);
+  } else {
+    gu.v += gstep;
+    Q4 qw = w2quat(u.w);
+    Q4 gqw = {0, 0, 0, 0};
+    qmul_adj(qw, P.q, gN.q, gqw, gP.q);
+    w2quat_adj(u.w, gqw, gu.w);
+  }
+  if (T.type != DSK_TOOL_GRIPPER) gP.gap += gN.gap;
+}
+
+DSK_DEV void store_pose(float* s, const Pose& P) {
+  s[0] = P.p.x; s[1] = P.p.y; s[2] = P.p.z;
+  s[3] = P.q.w; s[4] = P.q.x; s[5] = P.q.y; s[6] = P.q.z;
+  s[7] = P.gap;
+}
+// get_surface_pos(project(rand*size)), mpm_simulator.py:291-292, primitives.py:369-372
+DSK_DEV float3 surface_point(const ToolParams& Tj, const Pose& Pj, const float* rn) {
+  float3 q;
+  q.x = tmax(tmin(mul_rn(rn[0], Tj.size[0]), Tj.size[0]), -Tj.size[0]);
+  q.y = tmax(tmin(mul_rn(rn[1], Tj.size[1]), Tj.size[1]), -Tj.size[1]);
+  q.z = tmax(tmin(mul_rn(rn[2], Tj.size[2]), Tj.size[2]), -Tj.size[2]);
+  return add3_rn(qrot_rn(Pj.q, q), Pj.p);
+}
+DSK_DEV ToolVel action_to_vel(const ToolParams& T, const float* a, int S) {  // set_velocity, primive_base.py:260-268
+  ToolVel u;
+  u.v = f3(0, 0, 0);
+  u.w = f3(0, 0, 0);
+  u.gap_vel = 0.f;
+  float fs = (float)S;
+  if (T.action_dim > 0) {
+    u.v = f3(a[0] * T.action_scale[0] / fs, a[1] * T.action_scale[1] / fs, a[2] * T.action_scale[2] / fs);
+    if (T.action_dim > 3) u.w = f3(a[3] * T.action_scale[3] / fs, a[4] * T.action_scale[4] / fs, a[5] * T.action_scale[5] / fs);
+    if (T.type == DSK_TOOL_GRIPPER) u.gap_vel = a[6] * T.action_scale[6] / fs;
+  }
+  return u;
+}
+
+#define KIN_CTA 128
+// One CTA per env: S substeps of forward_kinematics for every tool, then (if any pair) set_surface_points,
+// set_collision_idx (deterministic first minimum) and apply_collision_projection (mpm_simulator.py:286-305).
+__global__ void __launch_bounds__(KIN_CTA)
+    k_kinematics(SimConst k, const ToolParams* __restrict__ tools, const float* __restrict__ state0 /*[B][K][8]*/,
+                 const float* __restrict__ action /*[B][A] or null*/, const float* __restrict__ rand_num,
+                 float* __restrict__ poses /*[B][S+1][K][8]*/, int* __restrict__ cidx /*[B][S+1][npairs]*/) {
+  __shared__ ToolParams sT[DSK_MAX_TOOLS];
+  __shared__ float sP[DSK_MAX_TOOLS][8];    // current poses (frame j+1 under construction)
+  __shared__ float sPre[DSK_MAX_TOOLS][8];  // poses after FK, before any projection
+  __shared__ float red_d[KIN_CTA / 32];
+  __shared__ int red_i[KIN_CTA / 32];
+  __shared__ int s_idx[DSK_MAX_PAIRS];
+  int env = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < k.K * (int)(sizeof(ToolParams) / 4); i += blockDim.x) ((int*)sT)[i] = ((const int*)tools)[i];
+  for (int i = tid; i < k.K * 8; i += blockDim.x) sP[i / 8][i % 8] = state0[(size_t)env * k.K * 8 + i];
+  __syncthreads();
+  float* out = poses + (size_t)env * (k.S + 1) * k.K * 8;
+  for (int i = tid; i < k.K * 8; i += blockDim.x) out[i] = sP[i / 8][i % 8];
+  int A = 0;
+  for (int t = 0; t < k.K; t++) A += sT[t].action_dim;
+  for (int j = 0; j < k.S; j++) {
+    if (tid < k.K) {
+      int off = 0;
+      for (int t = 0; t < tid; t++) off += sT[t].action_dim;
+      float zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      const float* a = action ? action + (size_t)env * A + off : zero;
+      ToolVel u = action_to_vel(sT[tid], a, k.S);
+      Pose N = tool_fk(sT[tid], load_pose(sP[tid]), u);
+      store_pose(sP[tid], N);
+      store_pose(sPre[tid], N);
+    }
+    __syncthreads();
+    if (k.npairs > 0) {
+      for (int c = 0; c < k.npairs; c++) {
+        int ti = k.pairs[c][0], tj = k.pairs[c][1];
+        Pose Pi = load_pose(sPre[ti]), Pj = load_pose(sPre[tj]);
+        float best = 0.f;
+        int bi = -1;
+        for (int q = tid; q < DSK_NUM_COLLISION_POINTS; q += blockDim.x) {
+          float3 pt = surface_point(sT[tj], Pj, rand_num + ((size_t)c * DSK_NUM_COLLISION_POINTS + q) * 3);
+          float d = tool_sdf(sT[ti], Pi, pt);
+          if (d < best) {
+            best = d;
+            bi = q;
+          }
+        }
+        // block arg-min, ties -> smaller index ("first minimum")
+        for (int o = 16; o > 0; o >>= 1) {
+          float od = __shfl_xor_sync(0xffffffffu, best, o);
+          int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (oi >= 0 && (bi < 0 || od < best || (od == best && oi < bi))) {
+            best = od;
+            bi = oi;
+          }
+        }
+        if ((tid & 31) == 0) {
+          red_d[tid >> 5] = best;
+          red_i[tid >> 5] = bi;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          for (int w = 1; w < KIN_CTA / 32; w++) {
+            float od = red_d[w];
+            int oi = red_i[w];
+            if (oi >= 0 && (bi < 0 || od < best || (od == best && oi < bi))) {
+              best = od;
+              bi = oi;
+            }
+          }
+          s_idx[c] = bi;
+        }
+        __syncthreads();
+      }
+      if (tid == 0) {
+        for (int c = 0; c < k.npairs; c++) {
+          int ti = k.pairs[c][0], tj = k.pairs[c][1];
+          cidx[((size_t)env * (k.S + 1) + (j + 1)) * k.npairs + c] = s_idx[c];
+          if (s_idx[c] >= 0) {  // collision_projection, primive_base.py:145-150
+            float3 pt = surface_point(sT[tj], load_pose(sPre[tj]),
+                                      rand_num + ((size_t)c * DSK_NUM_COLLISION_POINTS + s_idx[c]) * 3);
+            Pose Pi = load_pose(sP[ti]);
+            float d = tool_sdf(sT[ti], Pi, pt);
+            float3 nr = tool_normal(sT[ti], Pi, pt);
+            float inv = __fdiv_rn(1.f, __fsqrt_rn(dot_rn(nr, nr)));
+            sP[ti][0] = add_rn(Pi.p.x, mul_rn(mul_rn(inv, nr.x), d));
+            sP[ti][1] = add_rn(Pi.p.y, mul_rn(mul_rn(inv, nr.y), d));
+            sP[ti][2] = add_rn(Pi.p.z, mul_rn(mul_rn(inv, nr.z), d));
+          }
+        }
+      }
+      __syncthreads();
+    }
+    for (int i = tid; i < k.K * 8; i += blockDim.x) out[(size_t)(j + 1) * k.K * 8 + i] = sP[i / 8][i % 8];
+    __syncthreads();
+  }
+}

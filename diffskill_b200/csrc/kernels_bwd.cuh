@@ -1,0 +1,513 @@
+// Hand-derived adjoint kernels of one substep (MPMSimulator.substep_grad,
+// plb/engine/mpm_simulator.py:325-345).  The reference gets these from Taichi's autodiff
+// (`g2p.grad`, `grid_op.grad`, `p2g.grad`, `compute_F_tmp.grad`, `forward_kinematics.grad`,
+// `apply_collision_projection.grad`, `set_surface_points.grad`) plus the hand-written
+// `svd_grad`; here every one is written out by hand and checked against the oracle's tape AD.
+//
+//   schedule of substep_grad(j):  k_p2g<false> (recompute v_in,m)  ->  k_grid (recompute v_out, out of place)
+//        -> k_g2p_adj -> k_grid_adj -> k_p2g_adj       (tool adjoints: k_kinematics_adj once per env step)
+#pragma once
+#include "kernels_aux.cuh"
+#include "kernels_fwd.cuh"
+
+// g2p.grad : reads adjoints of (x,v,C)[j+1], scatters adjoint of grid_v_out, writes the g2p part of x.grad[j]
+__global__ void __launch_bounds__(128)
+    k_g2p_adj(SimConst k, const float* __restrict__ fin, const float* __restrict__ fnext,
+              const float* __restrict__ adj_in, float* __restrict__ adj_out, const int* __restrict__ npart,
+              const float4* __restrict__ Gv, float4* __restrict__ Ga) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= k.stride) return;
+  int env = gid / k.Npad, p = gid - env * k.Npad;
+  if (p >= npart[env]) return;
+  float3 x = load_v3(fin, CX, k.stride, gid);
+  float3 xn = load_v3(fnext, CX, k.stride, gid);
+  float3 gxn = load_v3(adj_in, CX, k.stride, gid);
+  float3 gvn = load_v3(adj_in, CV, k.stride, gid);
+  M3 gC = load_m3(adj_in, CC, k.stride, gid);
+  // x' = max(min(x + dt v', hi), lo): the adjoint passes iff lo < x' < hi
+  float3 gt = f3((k.x_lo < xn.x && xn.x < k.x_hi) ? gxn.x : 0.f, (k.x_lo < xn.y && xn.y < k.x_hi) ? gxn.y : 0.f,
+                 (k.x_lo < xn.z && xn.z < k.x_hi) ? gxn.z : 0.f);
+  gvn += k.dt * gt;
+  float3 gx = gt;
+  Stencil s;
+  make_stencil(k, x.x, x.y, x.z, s);
+  const float4* Gve = Gv + (size_t)env * k.nnode;
+  float4* Gae = Ga + (size_t)env * k.nnode;
+  float gwx[3] = {0, 0, 0}, gwy[3] = {0, 0, 0}, gwz[3] = {0, 0, 0};
+  float3 gf = f3(0, 0, 0);  // adjoint of fx (through dpos)
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int l = 0; l < 3; l++) {
+        int node = s.ox[i] + s.oy[j] + s.oz[l];
+        float4 g4 = Gve[node];
+        float3 g = f3(g4.x, g4.y, g4.z);
+        float w = s.wx[i] * s.wy[j] * s.wz[l];
+        float cw = k.c_C * w;
+        float3 dpos = f3((float)i - s.fx, (float)j - s.fy, (float)l - s.fz);
+        float3 Cd = mv(gC, dpos);   // sum_b gC_ab dpos_b
+        float3 Ctg = mTv(gC, g);    // sum_a gC_ab g_a
+        red_add4(&Gae[node], make_float4(w * gvn.x + cw * Cd.x, w * gvn.y + cw * Cd.y, w * gvn.z + cw * Cd.z, 0.f));
+        float gw = dot(g, gvn) + k.c_C * dot(g, Cd);
+        gf -= cw * Ctg;
+        gwx[i] += gw * s.wy[j] * s.wz[l];
+        gwy[j] += gw * s.wx[i] * s.wz[l];
+        gwz[l] += gw * s.wx[i] * s.wy[j];
+      }
+  float dw[3];
+  bspline1_grad(s.fx, dw);
+  gf.x += gwx[0] * dw[0] + gwx[1] * dw[1] + gwx[2] * dw[2];
+  bspline1_grad(s.fy, dw);
+  gf.y += gwy[0] * dw[0] + gwy[1] * dw[1] + gwy[2] * dw[2];
+  bspline1_grad(s.fz, dw);
+  gf.z += gwz[0] * dw[0] + gwz[1] * dw[1] + gwz[2] * dw[2];
+  gx += k.inv_dx * gf;
+  store_v3(adj_out, CX, k.stride, gid, gx);
+}
+
+// grid_op.grad over the active tiles.  G0: (momentum, mass) of the recomputed p2g.  Ga: in = adjoint of
+// grid_v_out (xyz), out = adjoint of (grid_v_in, grid_m), in place.  pose_adj: [B][S+1][K][8] accumulators.
+__global__ void __launch_bounds__(GRID_CTA)
+    k_grid_adj(SimConst k, const ToolParams* __restrict__ tools, const float* __restrict__ poses, int j,
+               const float4* __restrict__ G0, float4* __restrict__ Ga, const int* __restrict__ list,
+               const int* __restrict__ count, float* __restrict__ pose_adj,
+               const int* __restrict__ clr_list, const int* __restrict__ clr_count, float4* clr0, float4* clr1,
+               float4* clr2, int* zero_count) {
+  __shared__ ToolParams sT[DSK_MAX_TOOLS];
+  for (int i = threadIdx.x; i < k.K * (int)(sizeof(ToolParams) / 4); i += blockDim.x)
+    ((int*)sT)[i] = ((const int*)tools)[i];
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0 && zero_count) *zero_count = 0;
+  if (clr_list) clear_tiles(k, clr_list, *clr_count, clr0, clr1, clr2);
+  int n_active = *count;
+  for (int it = blockIdx.x; it < n_active; it += gridDim.x) {
+    int gt = list[it];
+    int env = gt / k.ntile, tile = gt - env * k.ntile;
+    size_t o = ((size_t)gt << 6) + threadIdx.x;
+    float4 gin = G0[o];
+    float4 ga4 = Ga[o];
+    bool live = gin.w > k.m_eps;
+    int tz = tile % k.nt, ty = (tile / k.nt) % k.nt, tx = tile / (k.nt * k.nt);
+    int l = threadIdx.x;
+    int I0 = tx * 4 + (l >> 4), I1 = ty * 4 + ((l >> 2) & 3), I2 = tz * 4 + (l & 3);
+    float inv = live ? 1.f / gin.w : 0.f;
+    float3 gp = f3(mul_rn((float)I0, k.dx), mul_rn((float)I1, k.dx), mul_rn((float)I2, k.dx));
+    const float* pa = poses + ((size_t)(env * (k.S + 1) + j) * k.K) * 8;
+    const float* pb = pa + (size_t)k.K * 8;
+    float3 vs[DSK_MAX_TOOLS + 1];
+    float3 g = f3(0.f, 0.f, 0.f);
+    if (live) {
+      float3 v = f3(inv * gin.x + k.grav[0], inv * gin.y + k.grav[1], inv * gin.z + k.grav[2]);
+      for (int t = 0; t < k.K; t++) {
+        vs[t] = v;
+        v = tool_collide(sT[t], load_pose(pa + t * 8), load_pose(pb + t * 8), gp, v, k.dt);
+      }
+      g = grid_boundary_adj(k, I0, I1, I2, v, f3(ga4.x, ga4.y, ga4.z));
+    }
+    float* adj0 = pose_adj + ((size_t)(env * (k.S + 1) + j) * k.K) * 8;
+    float* adj1 = adj0 + (size_t)k.K * 8;
+    for (int t = k.K - 1; t >= 0; t--) {
+      PoseAdj a0 = pose_adj_zero(), a1 = pose_adj_zero();
+      if (live) g = tool_collide_adj(sT[t], load_pose(pa + t * 8), load_pose(pb + t * 8), gp, vs[t], k.dt, g, a0, a1);
+      float vals[16] = {a0.p.x, a0.p.y, a0.p.z, a0.q.w, a0.q.x, a0.q.y, a0.q.z, a0.gap,
+                        a1.p.x, a1.p.y, a1.p.z, a1.q.w, a1.q.x, a1.q.y, a1.q.z, a1.gap};
+      float mag = 0.f;
+#pragma unroll
+      for (int q = 0; q < 16; q++) mag += fabsf(vals[q]);
+      if (__any_sync(0xffffffffu, mag != 0.f)) {
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+          float s = warp_sum(vals[q]);
+          if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd((q < 8 ? adj0 : adj1) + t * 8 + (q & 7), s);
+        }
+      }
+    }
+    float4 outv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+      // v0 = (1/m) * v_in  ->  g(v_in) = g/m ; g(m) = -(v_in . g)/m^2
+      outv = make_float4(inv * g.x, inv * g.y, inv * g.z, -(inv * inv) * (gin.x * g.x + gin.y * g.y + gin.z * g.z));
+    }
+    Ga[o] = outv;
+  }
+}
+
+// p2g.grad + svd_grad + compute_F_tmp.grad fused: gathers adjoints of (grid_v_in, grid_m), reads F.grad[j+1],
+// writes x.grad (adding the g2p part already stored), v.grad, C.grad, F.grad of frame j.
+__global__ void __launch_bounds__(128)
+    k_p2g_adj(SimConst k, const float* __restrict__ fin, const float* __restrict__ adj_in, float* __restrict__ adj_out,
+              const float* __restrict__ mat, const int* __restrict__ npart, const float4* __restrict__ Ga) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= k.stride) return;
+  int env = gid / k.Npad, p = gid - env * k.Npad;
+  if (p >= npart[env]) return;
+  float3 x = load_v3(fin, CX, k.stride, gid);
+  float3 v = load_v3(fin, CV, k.stride, gid);
+  M3 C = load_m3(fin, CC, k.stride, gid);
+  M3 F = load_m3(fin, CF, k.stride, gid);
+  float mu = mat[gid], lam = mat[k.stride + gid], ys = mat[2 * k.stride + gid];
+  P2GParticle o;
+  p2g_particle(k, C, F, mu, lam, ys, o);
+  Stencil s;
+  make_stencil(k, x.x, x.y, x.z, s);
+  const float4* Gae = Ga + (size_t)env * k.nnode;
+  float3 pmv = k.p_mass * v;
+  float gwx[3] = {0, 0, 0}, gwy[3] = {0, 0, 0}, gwz[3] = {0, 0, 0};
+  float3 gf = f3(0, 0, 0), gv = f3(0, 0, 0);
+  M3 gA;  // adjoint of affine
+#pragma unroll
+  for (int i = 0; i < 9; i++) gA.m[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int l = 0; l < 3; l++) {
+        float4 g4 = Gae[s.ox[i] + s.oy[j] + s.oz[l]];
+        float3 G = f3(g4.x, g4.y, g4.z);
+        float w = s.wx[i] * s.wy[j] * s.wz[l];
+        float3 dpos = f3(((float)i - s.fx) * k.dx, ((float)j - s.fy) * k.dx, ((float)l - s.fz) * k.dx);
+        float3 a = pmv + mv(o.affine, dpos);
+        float gw = dot(G, a) + g4.w * k.p_mass;
+        gv += (w * k.p_mass) * G;
+        float3 wG = w * G;
+        gA.m[0] += wG.x * dpos.x; gA.m[1] += wG.x * dpos.y; gA.m[2] += wG.x * dpos.z;
+        gA.m[3] += wG.y * dpos.x; gA.m[4] += wG.y * dpos.y; gA.m[5] += wG.y * dpos.z;
+        gA.m[6] += wG.z * dpos.x; gA.m[7] += wG.z * dpos.y; gA.m[8] += wG.z * dpos.z;
+        gf -= k.dx * mTv(o.affine, wG);
+        gwx[i] += gw * s.wy[j] * s.wz[l];
+        gwy[j] += gw * s.wx[i] * s.wz[l];
+        gwz[l] += gw * s.wx[i] * s.wy[j];
+      }
+  float dw[3];
+  bspline1_grad(s.fx, dw);
+  gf.x += gwx[0] * dw[0] + gwx[1] * dw[1] + gwx[2] * dw[2];
+  bspline1_grad(s.fy, dw);
+  gf.y += gwy[0] * dw[0] + gwy[1] * dw[1] + gwy[2] * dw[2];
+  bspline1_grad(s.fz, dw);
+  gf.z += gwz[0] * dw[0] + gwz[1] * dw[1] + gwz[2] * dw[2];
+  float3 gx = load_v3(adj_out, CX, k.stride, gid) + k.inv_dx * gf;
+
+  // affine = c_stress * stress + p_mass * C
+  M3 gCm, gS;
+#pragma unroll
+  for (int i = 0; i < 9; i++) {
+    gCm.m[i] = k.p_mass * gA.m[i];
+    gS.m[i] = k.c_stress * gA.m[i];
+  }
+  // stress = A N^T + vol I,  A = 2mu (N - R),  vol = (lam J)(J - 1)
+  M3 R = mmT(o.U, o.V);
+  M3 A;
+#pragma unroll
+  for (int i = 0; i < 9; i++) A.m[i] = (2.f * mu) * (o.newF.m[i] - R.m[i]);
+  M3 gAm = mm(gS, o.newF);   // g(A) = gS N
+  M3 gN = mTm(gS, A);        // g(N) = gS^T A
+  M3 gR;
+#pragma unroll
+  for (int i = 0; i < 9; i++) {
+    gN.m[i] += (2.f * mu) * gAm.m[i];
+    gR.m[i] = -(2.f * mu) * gAm.m[i];
+  }
+  float gJ = lam * (2.f * o.J - 1.f) * (gS.m[0] + gS.m[4] + gS.m[8]);
+  M3 cf = cof3(o.newF);
+  M3 gFn = load_m3(adj_in, CF, k.stride, gid);  // F.grad[j+1]
+#pragma unroll
+  for (int i = 0; i < 9; i++) gN.m[i] += gJ * cf.m[i] + gFn.m[i];
+  // R = U V^T
+  M3 gU = mm(gR, o.V);
+  M3 gV = mTm(gR, o.U);
+  float3 gsig = f3(0, 0, 0);
+  M3 gFt;
+  if (!o.rm.yields) {
+    gFt = gN;
+  } else {
+    const ReturnMap& r = o.rm;
+    float e[3] = {r.e.x, r.e.y, r.e.z};
+    // N = U diag(e) V^T
+    M3 NV = mm(gN, o.V);     // gN V
+    M3 NtU = mTm(gN, o.U);   // gN^T U
+    M3 UtNV = mTm(o.U, NV);  // U^T gN V
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        gU.m[i * 3 + q] += NV.m[i * 3 + q] * e[q];
+        gV.m[i * 3 + q] += NtU.m[i * 3 + q] * e[q];
+      }
+    float3 ge = f3(UtNV.m[0], UtNV.m[4], UtNV.m[8]);
+    float3 gep = f3(ge.x * r.e.x, ge.y * r.e.y, ge.z * r.e.z);  // adjoint of the returned log strain
+    float kf = r.dg / r.ehn;
+    float3 geps = gep;
+    float gk = -dot(gep, r.eh);
+    float3 geh = (-kf) * gep;
+    float gdg = gk / r.ehn;
+    float gehn = -gk * r.dg / (r.ehn * r.ehn) + gdg;
+    geh += (gehn / r.ehn) * r.eh;
+    float gm = (geh.x + geh.y + geh.z) / 3.f;
+    geps += f3(geh.x - gm, geh.y - gm, geh.z - gm);
+    gsig = f3((0.05f < o.sig.x) ? geps.x / r.sc.x : 0.f, (0.05f < o.sig.y) ? geps.y / r.sc.y : 0.f,
+              (0.05f < o.sig.z) ? geps.z / r.sc.z : 0.f);
+#pragma unroll
+    for (int i = 0; i < 9; i++) gFt.m[i] = 0.f;
+  }
+  M3 gsv = svd3_backward(gU, gsig, gV, o.U, o.sig, o.V);
+#pragma unroll
+  for (int i = 0; i < 9; i++) gFt.m[i] += gsv.m[i];
+  // F_tmp = (I + dt C) F
+  M3 Mx;
+#pragma unroll
+  for (int i = 0; i < 9; i++) Mx.m[i] = ((i % 4 == 0) ? 1.f : 0.f) + k.dt * C.m[i];
+  M3 gM = mmT(gFt, F);
+  M3 gF = mTm(Mx, gFt);
+#pragma unroll
+  for (int i = 0; i < 9; i++) gCm.m[i] += k.dt * gM.m[i];
+  store_v3(adj_out, CX, k.stride, gid, gx);
+  store_v3(adj_out, CV, k.stride, gid, gv);
+  store_m3(adj_out, CC, k.stride, gid, gCm);
+  store_m3(adj_out, CF, k.stride, gid, gF);
+}
+
+// Tool adjoints of one env step: for j = S-1..0: apply_collision_projection.grad, set_surface_points.grad,
+// forward_kinematics.grad (tools in reverse order), then set_velocity.grad (primive_base.py:260-268).
+// One warp per env; lane t owns tool t.
+__global__ void __launch_bounds__(32)
+    k_kinematics_adj(SimConst k, const ToolParams* __restrict__ tools, const float* __restrict__ poses,
+                     const int* __restrict__ cidx, const float* __restrict__ rand_num,
+                     const float* __restrict__ action, float* __restrict__ pose_adj,
+                     float* __restrict__ action_grad /*[B][A] of this step, +=*/) {
+  __shared__ ToolParams sT[DSK_MAX_TOOLS];
+  extern __shared__ float sadj[];  // [(S+1)][K][8]
+  int env = blockIdx.x, lane = threadIdx.x;
+  for (int i = lane; i < k.K * (int)(sizeof(ToolParams) / 4); i += 32) ((int*)sT)[i] = ((const int*)tools)[i];
+  int tot = (k.S + 1) * k.K * 8;
+  float* gadj = pose_adj + (size_t)env * tot;
+  const float* P = poses + (size_t)env * tot;
+  for (int i = lane; i < tot; i += 32) sadj[i] = gadj[i];
+  __syncwarp();
+  int A = 0, off = 0;
+  for (int t = 0; t < k.K; t++) {
+    if (t == lane) off = A;
+    A += sT[t].action_dim;
+  }
+  ToolVel u, gu;
+  gu.v = f3(0, 0, 0);
+  gu.w = f3(0, 0, 0);
+  gu.gap_vel = 0.f;
+  float zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (lane < k.K) u = action_to_vel(sT[lane], action ? action + (size_t)env * A + off : zero, k.S);
+  for (int j = k.S - 1; j >= 0; j--) {
+    float* a1 = sadj + (size_t)(j + 1) * k.K * 8;
+    float* a0 = sadj + (size_t)j * k.K * 8;
+    const float* P1 = P + (size_t)(j + 1) * k.K * 8;
+    const float* P0 = P + (size_t)j * k.K * 8;
+    if (k.npairs > 0 && lane == 0) {
+      for (int c = k.npairs - 1; c >= 0; c--) {
+        int idx = cidx[((size_t)env * (k.S + 1) + (j + 1)) * k.npairs + c];
+        if (idx < 0) continue;
+        int ti = k.pairs[c][0], tj = k.pairs[c][1];
+        // NOTE: obstacle pose is the post-step pose of frame j+1 (obstacles are never projected in the
+        // reference's scenes); tool i is evaluated at its POST-projection pose, as Taichi's grad kernel does.
+        const float* rn = rand_num + ((size_t)c * DSK_NUM_COLLISION_POINTS + idx) * 3;
+        Pose Pj = load_pose(P1 + tj * 8), Pi = load_pose(P1 + ti * 8);
+        float3 pt = surface_point(sT[tj], Pj, rn);
+        float d = tool_sdf(sT[ti], Pi, pt);
+        float3 nr = tool_normal(sT[ti], Pi, pt);
+        float n2 = dot(nr, nr);
+        float inv = 1.f / sqrtf(n2);
+        // new_pos = pos + (inv*nr)*d ; seed = current position.grad
+        float3 gs = f3(a1[ti * 8 + 0], a1[ti * 8 + 1], a1[ti * 8 + 2]);
+        float3 un = inv * nr;
+        float gd = dot(gs, un);
+        float3 gun = d * gs;
+        float ginv = dot(gun, nr);
+        float3 gnr = inv * gun;
+        // inv = n2^-1/2
+        gnr += (2.f * (-0.5f * ginv * inv / n2)) * nr;
+        PoseAdj gPi = pose_adj_zero();
+        float3 gpt = f3(0, 0, 0);
+        tool_sdf_adj(sT[ti], Pi, pt, gd, gPi, gpt);
+        tool_normal_adj(sT[ti], Pi, pt, gnr, gPi, gpt);
+        a1[ti * 8 + 0] += gPi.p.x; a1[ti * 8 + 1] += gPi.p.y; a1[ti * 8 + 2] += gPi.p.z;
+        a1[ti * 8 + 3] += gPi.q.w; a1[ti * 8 + 4] += gPi.q.x; a1[ti * 8 + 5] += gPi.q.y; a1[ti * 8 + 6] += gPi.q.z;
+        a1[ti * 8 + 7] += gPi.gap;
+        // set_surface_points.grad: pt = qrot(rot_j, proj) + pos_j
+        float3 q;
+        q.x = tmax(tmin(rn[0] * sT[tj].size[0], sT[tj].size[0]), -sT[tj].size[0]);
+        q.y = tmax(tmin(rn[1] * sT[tj].size[1], sT[tj].size[1]), -sT[tj].size[1]);
+        q.z = tmax(tmin(rn[2] * sT[tj].size[2], sT[tj].size[2]), -sT[tj].size[2]);
+        Q4 gq = {0, 0, 0, 0};
+        float3 gdm = f3(0, 0, 0);
+        qrot_adj(Pj.q, q, gpt, gq, gdm);
+        a1[tj * 8 + 0] += gpt.x; a1[tj * 8 + 1] += gpt.y; a1[tj * 8 + 2] += gpt.z;
+        a1[tj * 8 + 3] += gq.w; a1[tj * 8 + 4] += gq.x; a1[tj * 8 + 5] += gq.y; a1[tj * 8 + 6] += gq.z;
+      }
+    }
+    __syncwarp();
+    if (lane < k.K) {
+      PoseAdj gN;
+      const float* g = a1 + lane * 8;
+      gN.p = f3(g[0], g[1], g[2]);
+      gN.q.w = g[3]; gN.q.x = g[4]; gN.q.y = g[5]; gN.q.z = g[6];
+      gN.gap = g[7];
+      PoseAdj gP = pose_adj_zero();
+      tool_fk_adj(sT[lane], load_pose(P0 + lane * 8), u, gN, gP, gu);
+      float* o = a0 + lane * 8;
+      o[0] += gP.p.x; o[1] += gP.p.y; o[2] += gP.p.z;
+      o[3] += gP.q.w; o[4] += gP.q.x; o[5] += gP.q.y; o[6] += gP.q.z;
+      o[7] += gP.gap;
+    }
+    __syncwarp();
+  }
+  for (int i = lane; i < tot; i += 32) gadj[i] = sadj[i];
+  if (lane < k.K && sT[lane].action_dim > 0 && action_grad) {
+    const ToolParams& T = sT[lane];
+    float fs = (float)k.S;
+    float* ga = action_grad + (size_t)env * A + off;
+    ga[0] += gu.v.x * (T.action_scale[0] / fs);
+    ga[1] += gu.v.y * (T.action_scale[1] / fs);
+    ga[2] += gu.v.z * (T.action_scale[2] / fs);
+    if (T.action_dim > 3) {
+      ga[3] += gu.w.x * (T.action_scale[3] / fs);
+      ga[4] += gu.w.y * (T.action_scale[4] / fs);
+      ga[5] += gu.w.z * (T.action_scale[5] / fs);
+    }
+    if (T.type == DSK_TOOL_GRIPPER) ga[6] += gu.gap_vel * (T.action_scale[6] / fs);
+  }
+}
+
+// compute_min_dist (+grad), function.py:79-88 : one thread per particle, loops over tools.
+// out [B,cap_out,ncols]
+__global__ void k_min_dist(SimConst k, const ToolParams* __restrict__ tools, const float* __restrict__ frame,
+                           const int* __restrict__ npart, const float* __restrict__ tool_state /*[B][K][8]*/,
+                           int cap_out, int ncols, float* __restrict__ out) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= k.stride) return;
+  int env = gid / k.Npad, p = gid - env * k.Npad;
+  if (p >= cap_out) return;
+  float* o = out + ((size_t)env * cap_out + p) * ncols;
+  if (p >= npart[env]) {
+    for (int c = 0; c < ncols; c++) o[c] = 0.f;
+    return;
+  }
+  float3 x = load_v3(frame, CX, k.stride, gid);
+  int col = 0;
+  for (int t = 0; t < k.K; t++) {
+    ToolParams T = tools[t];
+    Pose P = load_pose(tool_state + ((size_t)env * k.K + t) * 8);
+    if (T.type == DSK_TOOL_GRIPPER) {
+      o[col++] = frame_sdf(T, SDF_BOX, jaw_frame(P, -1.f), x);
+      o[col++] = frame_sdf(T, SDF_BOX, jaw_frame(P, 1.f), x);
+    } else {
+      o[col++] = tool_sdf(T, P, x);
+    }
+  }
+}
+__global__ void k_min_dist_adj(SimConst k, const ToolParams* __restrict__ tools, const float* __restrict__ frame,
+                               const int* __restrict__ npart, const float* __restrict__ tool_state, int cap_in,
+                               int ncols, const float* __restrict__ gout, float* __restrict__ adj_frame,
+                               float* __restrict__ tool_adj /*[B][K][8]*/) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  int env = gid < k.stride ? gid / k.Npad : 0, p = gid - env * k.Npad;
+  bool live = gid < k.stride && p < npart[env] && p < cap_in;
+  float3 x = live ? load_v3(frame, CX, k.stride, gid) : f3(0, 0, 0);
+  const float* g = gout + ((size_t)env * cap_in + (live ? p : 0)) * ncols;
+  float3 gx = f3(0, 0, 0);
+  int col = 0;
+  // all lanes of a warp belong to one env when Npad is a multiple of 32 (it is)
+  for (int t = 0; t < k.K; t++) {
+    ToolParams T = tools[t];
+    PoseAdj gP = pose_adj_zero();
+    if (live) {
+      Pose P = load_pose(tool_state + ((size_t)env * k.K + t) * 8);
+      if (T.type == DSK_TOOL_GRIPPER) {
+        FrameAdj fa = frame_adj_zero();
+        frame_sdf_adj(T, SDF_BOX, jaw_frame(P, -1.f), x, g[col], fa, gx);
+        jaw_frame_adj(P, -1.f, fa, gP);
+        fa = frame_adj_zero();
+        frame_sdf_adj(T, SDF_BOX, jaw_frame(P, 1.f), x, g[col + 1], fa, gx);
+        jaw_frame_adj(P, 1.f, fa, gP);
+      } else {
+        tool_sdf_adj(T, P, x, g[col], gP, gx);
+      }
+    }
+    col += T.type == DSK_TOOL_GRIPPER ? 2 : 1;
+    float vals[8] = {gP.p.x, gP.p.y, gP.p.z, gP.q.w, gP.q.x, gP.q.y, gP.q.z, gP.gap};
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      float s = warp_sum(vals[q]);
+      if ((threadIdx.x & 31) == 0 && s != 0.f && gid < k.stride) atomicAdd(tool_adj + ((size_t)env * k.K + t) * 8 + q, s);
+    }
+  }
+  if (live) {
+    adj_frame[(CX + 0) * k.stride + gid] += gx.x;
+    adj_frame[(CX + 1) * k.stride + gid] += gx.y;
+    adj_frame[(CX + 2) * k.stride + gid] += gx.z;
+  }
+}
+
+// compute_grid_m_kernel (+grad), mpm_simulator.py:456-466.  dense [B,n,n,n] output (row-major x,y,z)
+__global__ void k_grid_m(SimConst k, const float* __restrict__ frame, const int* __restrict__ npart,
+                         float* __restrict__ out) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= k.stride) return;
+  int env = gid / k.Npad, p = gid - env * k.Npad;
+  if (p >= npart[env]) return;
+  float3 x = load_v3(frame, CX, k.stride, gid);
+  Stencil s;
+  make_stencil(k, x.x, x.y, x.z, s);
+  float* o = out + (size_t)env * k.nnode;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      for (int l = 0; l < 3; l++)
+        atomicAdd(&o[((size_t)(s.bx + i) * k.n + (s.by + j)) * k.n + (s.bz + l)],
+                  s.wx[i] * s.wy[j] * s.wz[l] * k.p_mass);
+}
+__global__ void k_grid_m_adj(SimConst k, const float* __restrict__ frame, const int* __restrict__ npart,
+                             const float* __restrict__ gm, float* __restrict__ adj_frame) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= k.stride) return;
+  int env = gid / k.Npad, p = gid - env * k.Npad;
+  if (p >= npart[env]) return;
+  float3 x = load_v3(frame, CX, k.stride, gid);
+  Stencil s;
+  make_stencil(k, x.x, x.y, x.z, s);
+  const float* g = gm + (size_t)env * k.nnode;
+  float gwx[3] = {0, 0, 0}, gwy[3] = {0, 0, 0}, gwz[3] = {0, 0, 0};
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      for (int l = 0; l < 3; l++) {
+        float gw = g[((size_t)(s.bx + i) * k.n + (s.by + j)) * k.n + (s.bz + l)] * k.p_mass;
+        gwx[i] += gw * s.wy[j] * s.wz[l];
+        gwy[j] += gw * s.wx[i] * s.wz[l];
+        gwz[l] += gw * s.wx[i] * s.wy[j];
+      }
+  float dw[3];
+  float3 gf;
+  bspline1_grad(s.fx, dw);
+  gf.x = gwx[0] * dw[0] + gwx[1] * dw[1] + gwx[2] * dw[2];
+  bspline1_grad(s.fy, dw);
+  gf.y = gwy[0] * dw[0] + gwy[1] * dw[1] + gwy[2] * dw[2];
+  bspline1_grad(s.fz, dw);
+  gf.z = gwz[0] * dw[0] + gwz[1] * dw[1] + gwz[2] * dw[2];
+  adj_frame[(CX + 0) * k.stride + gid] += k.inv_dx * gf.x;
+  adj_frame[(CX + 1) * k.stride + gid] += k.inv_dx * gf.y;
+  adj_frame[(CX + 2) * k.stride + gid] += k.inv_dx * gf.z;
+}
+
+// tile-major grid -> dense [n,n,n,*] for the debug getters
+__global__ void k_grid_to_dense(SimConst k, const float4* __restrict__ G, int env, float* v3, float* m,
+                                unsigned char* occ, const int* __restrict__ tile_epoch, int epoch) {
+  int node = blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= k.nnode) return;
+  int Z = node % k.n, Y = (node / k.n) % k.n, X = node / (k.n * k.n);
+  int o = node_offset(X, Y, Z, k.nt);
+  float4 g = G ? G[(size_t)env * k.nnode + o] : make_float4(0, 0, 0, 0);
+  if (v3) {
+    v3[(size_t)node * 3] = g.x;
+    v3[(size_t)node * 3 + 1] = g.y;
+    v3[(size_t)node * 3 + 2] = g.z;
+  }
+  if (m) m[node] = g.w;
+  if (occ) occ[node] = tile_epoch[env * k.ntile + (o >> 6)] == epoch ? 1 : 0;
+}

@@ -1,0 +1,289 @@
+// Forward substep kernels (MPMSimulator.substep, plb/engine/mpm_simulator.py:307-323).
+//   k_p2g   : compute_F_tmp + svd + p2g (mpm_simulator.py:121-129,198-225) fused; per particle
+//   k_grid  : grid_op (mpm_simulator.py:230-262) over the ACTIVE tiles only, in place
+//   k_g2p   : g2p (mpm_simulator.py:264-283); per particle
+// clear_grid (mpm_simulator.py:100-110) is folded into k_grid: it zeroes the tiles the
+// previous substep touched in the other grid buffer.
+#pragma once
+#include "kernels_common.cuh"
+#include "svd3.cuh"
+
+// ---- plasticity: compute_von_mises, mpm_simulator.py:165-182 ---------------------------------------
+struct ReturnMap {
+  bool yields;
+  float3 sc;   // clamped sigma
+  float3 eps;  // log sc
+  float3 eh;   // deviatoric part
+  float ehn;   // its eps-norm
+  float dg;    // delta_gamma
+  float3 e;    // exp of the returned log-strain
+};
+DSK_DEV M3 von_mises(const M3& Ftmp, const M3& U, float3 sig, const M3& V, float ys, float mu, ReturnMap& r) {
+  r.sc = f3(tmax(sig.x, 0.05f), tmax(sig.y, 0.05f), tmax(sig.z, 0.05f));
+  r.eps = f3(logf(r.sc.x), logf(r.sc.y), logf(r.sc.z));
+  float mean = (r.eps.x + r.eps.y + r.eps.z) / 3.f;
+  r.eh = f3(r.eps.x - mean, r.eps.y - mean, r.eps.z - mean);
+  r.ehn = sqrtf(dot(r.eh, r.eh) + 1e-8f);
+  r.dg = r.ehn - ys / (2.f * mu);
+  r.yields = r.dg > 0.f;
+  if (r.yields) {
+    float kf = r.dg / r.ehn;
+    r.e = f3(expf(r.eps.x - kf * r.eh.x), expf(r.eps.y - kf * r.eh.y), expf(r.eps.z - kf * r.eh.z));
+    M3 US;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      US.m[i * 3 + 0] = U.m[i * 3 + 0] * r.e.x;
+      US.m[i * 3 + 1] = U.m[i * 3 + 1] * r.e.y;
+      US.m[i * 3 + 2] = U.m[i * 3 + 2] * r.e.z;
+    }
+    return mmT(US, V);
+  }
+  return Ftmp;
+}
+
+// everything p2g computes per particle before the scatter
+struct P2GParticle {
+  M3 Ftmp, U, V, newF, affine;
+  float3 sig;
+  ReturnMap rm;
+  float J;
+};
+DSK_DEV void p2g_particle(const SimConst& k, const M3& C, const M3& F, float mu, float lam, float ys, P2GParticle& o) {
+  M3 Mx;
+#pragma unroll
+  for (int i = 0; i < 9; i++) Mx.m[i] = ((i % 4 == 0) ? 1.f : 0.f) + k.dt * C.m[i];
+  o.Ftmp = mm(Mx, F);  // compute_F_tmp
+  svd3(o.Ftmp, o.U, o.sig, o.V);
+  o.newF = von_mises(o.Ftmp, o.U, o.sig, o.V, ys, mu, o.rm);
+  o.J = det3(o.newF);
+  M3 R = mmT(o.U, o.V);
+  M3 A;
+#pragma unroll
+  for (int i = 0; i < 9; i++) A.m[i] = (2.f * mu) * (o.newF.m[i] - R.m[i]);
+  M3 st = mmT(A, o.newF);
+  float vol = (lam * o.J) * (o.J - 1.f);
+  st.m[0] += vol;
+  st.m[4] += vol;
+  st.m[8] += vol;
+#pragma unroll
+  for (int i = 0; i < 9; i++) o.affine.m[i] = k.c_stress * st.m[i] + k.p_mass * C.m[i];
+}
+
+template <bool WRITE_F>
+__global__ void __launch_bounds__(128)
+    k_p2g(SimConst k, const float* __restrict__ fin, float* __restrict__ fout, const float* __restrict__ mat,
+          const int* __restrict__ npart, float4* __restrict__ G, TileTrack tt, int epoch) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= k.stride) return;
+  int env = gid / k.Npad, p = gid - env * k.Npad;
+  if (p >= npart[env]) return;
+  float3 x = load_v3(fin, CX, k.stride, gid);
+  float3 v = load_v3(fin, CV, k.stride, gid);
+  M3 C = load_m3(fin, CC, k.stride, gid);
+  M3 F = load_m3(fin, CF, k.stride, gid);
+  float mu = mat[gid], lam = mat[k.stride + gid], ys = mat[2 * k.stride + gid];
+  P2GParticle o;
+  p2g_particle(k, C, F, mu, lam, ys, o);
+  if (WRITE_F) store_m3(fout, CF, k.stride, gid, o.newF);
+  Stencil s;
+  make_stencil(k, x.x, x.y, x.z, s);
+  mark_stencil_tiles(k, tt, env, s, epoch);
+  float4* Ge = G + (size_t)env * k.nnode;
+  float3 pmv = k.p_mass * v;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int l = 0; l < 3; l++) {
+        float3 dpos = f3(((float)i - s.fx) * k.dx, ((float)j - s.fy) * k.dx, ((float)l - s.fz) * k.dx);
+        float w = s.wx[i] * s.wy[j] * s.wz[l];
+        float3 a = pmv + mv(o.affine, dpos);
+        red_add4(&Ge[s.ox[i] + s.oy[j] + s.oz[l]], make_float4(w * a.x, w * a.y, w * a.z, w * k.p_mass));
+      }
+}
+
+// ---- grid_op for one node ---------------------------------------------------------------------------
+// boundary conditions of mpm_simulator.py:241-260; returns the post-boundary velocity
+DSK_DEV float3 grid_boundary(const SimConst& k, int I0, int I1, int I2, float3 v) {
+  const int bound = 3;
+  int I[3] = {I0, I1, I2};
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    if (I[d] < bound && comp(v, d) < 0.f) {
+      if (d != 1 || k.gf_mode == 0) {
+        setcomp(v, d, 0.f);
+      } else if (k.gf_mode == 1) {
+        float lin = v.y + 1e-30f;
+        float3 off = f3((float)I0 * 1e-30f, (float)I1 * 1e-30f, (float)I2 * 1e-30f);
+        float3 vit = f3(v.x - off.x, v.y - lin - off.y, v.z - off.z);
+        float lit = sqrtf(dot(vit, vit) + 1e-8f);
+        float sc = tmax(1.f + k.ground_friction * lin / lit, 0.f);
+        v = f3(sc * (vit.x + off.x), 0.f, sc * (vit.z + off.z));
+      } else {
+        v = f3(0.f, 0.f, 0.f);
+      }
+    }
+    if (I[d] > k.n - bound && comp(v, d) > 0.f) setcomp(v, d, 0.f);
+  }
+  return v;
+}
+DSK_DEV float3 grid_boundary_adj(const SimConst& k, int I0, int I1, int I2, float3 v, float3 g) {
+  // replay forward, remember the inputs of the three stages, then reverse
+  const int bound = 3;
+  int I[3] = {I0, I1, I2};
+  float3 vin[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    vin[d] = v;
+    if (I[d] < bound && comp(v, d) < 0.f) {
+      if (d != 1 || k.gf_mode == 0) {
+        setcomp(v, d, 0.f);
+      } else if (k.gf_mode == 1) {
+        float lin = v.y + 1e-30f;
+        float3 off = f3((float)I0 * 1e-30f, (float)I1 * 1e-30f, (float)I2 * 1e-30f);
+        float3 vit = f3(v.x - off.x, v.y - lin - off.y, v.z - off.z);
+        float lit = sqrtf(dot(vit, vit) + 1e-8f);
+        float sc = tmax(1.f + k.ground_friction * lin / lit, 0.f);
+        v = f3(sc * (vit.x + off.x), 0.f, sc * (vit.z + off.z));
+      } else {
+        v = f3(0.f, 0.f, 0.f);
+      }
+    }
+    if (I[d] > k.n - bound && comp(v, d) > 0.f) setcomp(v, d, 0.f);
+  }
+#pragma unroll
+  for (int d = 2; d >= 0; d--) {
+    float3 u = vin[d];
+    // state after the first `if` of stage d
+    float3 mid = u;
+    bool lower = I[d] < bound && comp(u, d) < 0.f;
+    float lin = 0.f, lit = 1.f, a = 0.f, sc = 0.f;
+    float3 vit = f3(0, 0, 0), off = f3(0, 0, 0);
+    if (lower) {
+      if (d != 1 || k.gf_mode == 0) {
+        setcomp(mid, d, 0.f);
+      } else if (k.gf_mode == 1) {
+        lin = u.y + 1e-30f;
+        off = f3((float)I0 * 1e-30f, (float)I1 * 1e-30f, (float)I2 * 1e-30f);
+        vit = f3(u.x - off.x, u.y - lin - off.y, u.z - off.z);
+        lit = sqrtf(dot(vit, vit) + 1e-8f);
+        a = 1.f + k.ground_friction * lin / lit;
+        sc = tmax(a, 0.f);
+        mid = f3(sc * (vit.x + off.x), 0.f, sc * (vit.z + off.z));
+      } else {
+        mid = f3(0.f, 0.f, 0.f);
+      }
+    }
+    if (I[d] > k.n - bound && comp(mid, d) > 0.f) setcomp(g, d, 0.f);
+    if (lower) {
+      if (d != 1 || k.gf_mode == 0) {
+        setcomp(g, d, 0.f);
+      } else if (k.gf_mode == 1) {
+        g.y = 0.f;  // v_out[1] = 0
+        float3 w = f3(vit.x + off.x, vit.y + off.y, vit.z + off.z);
+        float gsc = dot(g, w);
+        float3 gvit = sc * g;
+        float ga = (0.f < a) ? gsc : 0.f;  // max(a, 0): a gets it iff 0 < a
+        float glin = ga * k.ground_friction / lit;
+        float glit = -ga * k.ground_friction * lin / (lit * lit);
+        gvit += (glit / lit) * vit;
+        // vit = u - lin*e_y - off ; lin = u.y + 1e-30
+        glin -= gvit.y;
+        g = gvit;
+        g.y += glin;
+      } else {
+        g = f3(0.f, 0.f, 0.f);
+      }
+    }
+  }
+  return g;
+}
+
+#define GRID_CTA 64
+// poses: [B][S+1][K][8]; grid kernels use frames j (P0) and j+1 (P1) of the tile's env
+DSK_DEV void clear_tiles(const SimConst& k, const int* __restrict__ list, int count, float4* c0, float4* c1,
+                         float4* c2) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = blockIdx.x; i < count; i += gridDim.x) {
+    size_t o = ((size_t)list[i] << 6) + threadIdx.x;  // list holds env*ntile+tile and nnode == ntile*64
+    if (c0) c0[o] = z;
+    if (c1) c1[o] = z;
+    if (c2) c2[o] = z;
+  }
+}
+
+// grid_op over active tiles.  Gin holds (momentum, mass); Gout receives (velocity, mass) and may alias Gin.
+__global__ void __launch_bounds__(GRID_CTA)
+    k_grid(SimConst k, const ToolParams* __restrict__ tools, const float* __restrict__ poses, int j,
+           const float4* Gin, float4* Gout, const int* __restrict__ list, const int* __restrict__ count,
+           // tiles of the previous substep to zero (clear_grid), may be null
+           const int* __restrict__ clr_list, const int* __restrict__ clr_count, float4* clr0, float4* clr1,
+           float4* clr2, int* zero_count) {
+  __shared__ ToolParams sT[DSK_MAX_TOOLS];
+  for (int i = threadIdx.x; i < k.K * (int)(sizeof(ToolParams) / 4); i += blockDim.x)
+    ((int*)sT)[i] = ((const int*)tools)[i];
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0 && zero_count) *zero_count = 0;
+  if (clr_list) clear_tiles(k, clr_list, *clr_count, clr0, clr1, clr2);
+  int n_active = *count;
+  for (int it = blockIdx.x; it < n_active; it += gridDim.x) {
+    int gt = list[it];
+    int env = gt / k.ntile, tile = gt - env * k.ntile;
+    size_t o = ((size_t)gt << 6) + threadIdx.x;
+    float4 g = Gin[o];
+    float3 vout = f3(0.f, 0.f, 0.f);
+    if (g.w > k.m_eps) {
+      int tz = tile % k.nt, ty = (tile / k.nt) % k.nt, tx = tile / (k.nt * k.nt);
+      int l = threadIdx.x;
+      int I0 = tx * 4 + (l >> 4), I1 = ty * 4 + ((l >> 2) & 3), I2 = tz * 4 + (l & 3);
+      float inv = 1.f / g.w;
+      float3 v = f3(inv * g.x + k.grav[0], inv * g.y + k.grav[1], inv * g.z + k.grav[2]);
+      float3 gp = f3(mul_rn((float)I0, k.dx), mul_rn((float)I1, k.dx), mul_rn((float)I2, k.dx));
+      const float* a = poses + ((size_t)(env * (k.S + 1) + j) * k.K) * 8;
+      const float* b = a + (size_t)k.K * 8;
+      for (int t = 0; t < k.K; t++) v = tool_collide(sT[t], load_pose(a + t * 8), load_pose(b + t * 8), gp, v, k.dt);
+      vout = grid_boundary(k, I0, I1, I2, v);
+    }
+    Gout[o] = make_float4(vout.x, vout.y, vout.z, g.w);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+    k_g2p(SimConst k, const float* __restrict__ fin, float* __restrict__ fout, const int* __restrict__ npart,
+          const float4* __restrict__ G) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= k.stride) return;
+  int env = gid / k.Npad, p = gid - env * k.Npad;
+  if (p >= npart[env]) return;
+  float3 x = load_v3(fin, CX, k.stride, gid);
+  Stencil s;
+  make_stencil(k, x.x, x.y, x.z, s);
+  const float4* Ge = G + (size_t)env * k.nnode;
+  float3 nv = f3(0.f, 0.f, 0.f);
+  M3 nC;
+#pragma unroll
+  for (int i = 0; i < 9; i++) nC.m[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int l = 0; l < 3; l++) {
+        float4 g = Ge[s.ox[i] + s.oy[j] + s.oz[l]];
+        float w = s.wx[i] * s.wy[j] * s.wz[l];
+        float3 dpos = f3((float)i - s.fx, (float)j - s.fy, (float)l - s.fz);
+        float cw = k.c_C * w;
+        nv.x += w * g.x;
+        nv.y += w * g.y;
+        nv.z += w * g.z;
+        nC.m[0] += cw * (g.x * dpos.x); nC.m[1] += cw * (g.x * dpos.y); nC.m[2] += cw * (g.x * dpos.z);
+        nC.m[3] += cw * (g.y * dpos.x); nC.m[4] += cw * (g.y * dpos.y); nC.m[5] += cw * (g.y * dpos.z);
+        nC.m[6] += cw * (g.z * dpos.x); nC.m[7] += cw * (g.z * dpos.y); nC.m[8] += cw * (g.z * dpos.z);
+      }
+  float3 nx = f3(tmax(tmin(x.x + k.dt * nv.x, k.x_hi), k.x_lo), tmax(tmin(x.y + k.dt * nv.y, k.x_hi), k.x_lo),
+                 tmax(tmin(x.z + k.dt * nv.z, k.x_hi), k.x_lo));
+  store_v3(fout, CX, k.stride, gid, nx);
+  store_v3(fout, CV, k.stride, gid, nv);
+  store_m3(fout, CC, k.stride, gid, nC);
+}

@@ -1,0 +1,462 @@
+// Rigid-tool signed distance fields, contact response and their hand-derived adjoints.
+//
+// Replaces the Taichi ti.funcs of plb/engine/primitive/primive_base.py:75-120
+// (sdf / normal / collider_v / collide) and primitives.py (Capsule :54-66, Box :374-393,
+// Gripper :471-536, Prism :711-731, Knife :769-807), plus the `.grad` code Taichi's
+// autodiff derives from them (call site mpm_simulator.py:336).
+//
+// Forward values use non-contracting `_rn` arithmetic in the reference's operation
+// order: the finite-difference normals amplify 1-ulp differences by 0.5/1e-4.
+// Adjoints follow Taichi's per-op rules: min(a,b) -> a iff a<b; max(a,b) -> a iff b<a;
+// abs -> sgn; predicates and selects carry no gradient; the FD stencil is
+// differentiated through (six SDF-gradient evaluations).
+#pragma once
+#include "../../include/diffskill_mpm.h"
+#include "mpm_math.cuh"
+
+struct ToolParams {
+  int type, action_dim;
+  float action_scale[8];
+  float friction, softness;
+  float lo[3], hi[3];
+  float size[3];
+  float h, half_h, r;
+  float prism_h0, prism_h1;
+  Q4 prot_inv;  // normalised conjugate of prot (computed on device in fp32 like the reference)
+  Q4 prot;
+  float min_gap, max_gap;
+};
+
+struct Pose {  // position[f], rotation[f], gap[f]
+  float3 p;
+  Q4 q;
+  float gap;
+};
+struct PoseAdj {
+  float3 p;
+  Q4 q;
+  float gap;
+};
+DSK_DEV PoseAdj pose_adj_zero() {
+  PoseAdj a;
+  a.p = f3(0, 0, 0);
+  a.q.w = a.q.x = a.q.y = a.q.z = 0.f;
+  a.gap = 0.f;
+  return a;
+}
+DSK_DEV Pose load_pose(const float* s) {
+  Pose P;
+  P.p = f3(s[0], s[1], s[2]);
+  P.q.w = s[3];
+  P.q.x = s[4];
+  P.q.y = s[5];
+  P.q.z = s[6];
+  P.gap = s[7];
+  return P;
+}
+
+// a rigid frame: origin + (unnormalised) rotation; tools use (position, rotation), gripper
+// jaws use (get_pos(flag), rotation)
+struct Frame {
+  float3 o;
+  Q4 q;
+};
+struct FrameAdj {
+  float3 o;
+  Q4 q;
+};
+DSK_DEV FrameAdj frame_adj_zero() {
+  FrameAdj a;
+  a.o = f3(0, 0, 0);
+  a.q.w = a.q.x = a.q.y = a.q.z = 0.f;
+  return a;
+}
+
+enum { SDF_CAPSULE = 0, SDF_BOX = 1, SDF_KNIFE = 2 };
+DSK_DEV int sdf_kind(int tool_type) {
+  return (tool_type == DSK_TOOL_CAPSULE || tool_type == DSK_TOOL_ROLLINGPIN_EXT)
+             ? SDF_CAPSULE
+             : (tool_type == DSK_TOOL_KNIFE ? SDF_KNIFE : SDF_BOX);
+}
+
+// ---- local SDFs (value) ----------------------------------------------------------------------
+DSK_DEV float len14_rn(float3 v) { return __fsqrt_rn(add_rn(dot_rn(v, v), 1e-14f)); }
+DSK_DEV float len8_rn(float3 v) { return __fsqrt_rn(add_rn(dot_rn(v, v), 1e-8f)); }
+
+DSK_DEV float box_sdf(const ToolParams& T, float3 p) {  // primitives.py:374-380
+  float q0 = sub_rn(fabsf(p.x), T.size[0]), q1 = sub_rn(fabsf(p.y), T.size[1]), q2 = sub_rn(fabsf(p.z), T.size[2]);
+  float3 mq = f3(tmax(q0, 0.f), tmax(q1, 0.f), tmax(q2, 0.f));
+  float out = len14_rn(mq);
+  return add_rn(out, tmin(tmax(q0, tmax(q1, q2)), 0.f));
+}
+DSK_DEV float3 capsule_p2(const ToolParams& T, float3 p) {  // primitives.py:56-58
+  float y = add_rn(p.y, T.half_h);
+  y = sub_rn(y, tmin(tmax(y, 0.f), T.h));
+  return f3(p.x, y, p.z);
+}
+DSK_DEV float prism_sdf(const ToolParams& T, float3 p0) {  // primitives.py:711-718
+  float3 p = qrot_rn(T.prot_inv, p0);
+  float a = add_rn(mul_rn(fabsf(p.x), 0.866025f), mul_rn(p.y, 0.5f));
+  return tmax(sub_rn(fabsf(p.z), T.prism_h1), sub_rn(tmax(a, -p.y), mul_rn(T.prism_h0, 0.5f)));
+}
+DSK_DEV float local_sdf(const ToolParams& T, int kind, float3 p) {
+  if (kind == SDF_CAPSULE) return sub_rn(len14_rn(capsule_p2(T, p)), T.r);
+  if (kind == SDF_BOX) return box_sdf(T, p);
+  return tmax(prism_sdf(T, p), box_sdf(T, p));  // primitives.py:769-773
+}
+
+// ---- local SDFs (gradient wrt the local point, Taichi AD rules) ---------------------------------
+DSK_DEV float sgnf(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
+DSK_DEV float3 box_sdf_grad(const ToolParams& T, float3 p) {
+  float q0 = fabsf(p.x) - T.size[0], q1 = fabsf(p.y) - T.size[1], q2 = fabsf(p.z) - T.size[2];
+  float3 mq = f3(tmax(q0, 0.f), tmax(q1, 0.f), tmax(q2, 0.f));
+  float L = sqrtf(dot(mq, mq) + 1e-14f);
+  // d len / d q_i = mq_i / L, only where 0 < q_i
+  float g0 = (0.f < q0) ? mq.x / L : 0.f;
+  float g1 = (0.f < q1) ? mq.y / L : 0.f;
+  float g2 = (0.f < q2) ? mq.z / L : 0.f;
+  // min(max(q0, max(q1,q2)), 0)
+  float m12 = tmax(q1, q2);
+  float m012 = tmax(q0, m12);
+  if (m012 < 0.f) {
+    if (m12 < q0) g0 += 1.f;
+    else if (q2 < q1) g1 += 1.f;
+    else g2 += 1.f;
+  }
+  return f3(g0 * sgnf(p.x), g1 * sgnf(p.y), g2 * sgnf(p.z));
+}
+DSK_DEV float3 capsule_sdf_grad(const ToolParams& T, float3 p) {
+  float y = p.y + T.half_h;
+  float t = tmax(y, 0.f);
+  float dyy = 1.f - (((0.f < y) && (t < T.h)) ? 1.f : 0.f);
+  float3 p2 = capsule_p2(T, p);
+  float L = sqrtf(dot(p2, p2) + 1e-14f);
+  return f3(p2.x / L, dyy * p2.y / L, p2.z / L);
+}
+DSK_DEV float3 prism_sdf_grad(const ToolParams& T, float3 p0) {
+  float3 p = qrot_rn(T.prot_inv, p0);
+  float a = fabsf(p.x) * 0.866025f + p.y * 0.5f;
+  float b = -p.y;
+  float inner = tmax(a, b) - T.prism_h0 * 0.5f;
+  float outer_l = fabsf(p.z) - T.prism_h1;
+  float3 g = f3(0, 0, 0);
+  if (inner < outer_l) {
+    g.z = sgnf(p.z);
+  } else if (b < a) {
+    g.x = 0.866025f * sgnf(p.x);
+    g.y = 0.5f;
+  } else {
+    g.y = -1.f;
+  }
+  Q4 gq = {0, 0, 0, 0};
+  float3 gp0 = f3(0, 0, 0);
+  qrot_adj(T.prot_inv, p0, g, gq, gp0);
+  return gp0;
+}
+DSK_DEV float3 local_sdf_grad(const ToolParams& T, int kind, float3 p) {
+  if (kind == SDF_CAPSULE) return capsule_sdf_grad(T, p);
+  if (kind == SDF_BOX) return box_sdf_grad(T, p);
+  float a = prism_sdf(T, p), b = box_sdf(T, p);
+  return (b < a) ? prism_sdf_grad(T, p) : box_sdf_grad(T, p);
+}
+
+// ---- local normals ---------------------------------------------------------------------------------
+#define DSK_FD_D 1e-4f
+DSK_DEV float3 local_normal_raw(const ToolParams& T, int kind, float3 p, float& L) {
+  // returns the un-normalised n and its length (eps 1e-14)
+  float3 n;
+  if (kind == SDF_CAPSULE) {
+    n = capsule_p2(T, p);
+  } else {  // primitives.py:382-393 / 796-807
+    const float d = DSK_FD_D;
+    const float c = __fdiv_rn(0.5f, d);
+    n.x = mul_rn(c, sub_rn(local_sdf(T, kind, f3(add_rn(p.x, d), p.y, p.z)), local_sdf(T, kind, f3(sub_rn(p.x, d), p.y, p.z))));
+    n.y = mul_rn(c, sub_rn(local_sdf(T, kind, f3(p.x, add_rn(p.y, d), p.z)), local_sdf(T, kind, f3(p.x, sub_rn(p.y, d), p.z))));
+    n.z = mul_rn(c, sub_rn(local_sdf(T, kind, f3(p.x, p.y, add_rn(p.z, d))), local_sdf(T, kind, f3(p.x, p.y, sub_rn(p.z, d)))));
+  }
+  L = len14_rn(n);
+  return n;
+}
+DSK_DEV float3 local_normal(const ToolParams& T, int kind, float3 p) {
+  float L;
+  float3 n = local_normal_raw(T, kind, p, L);
+  return f3(__fdiv_rn(n.x, L), __fdiv_rn(n.y, L), __fdiv_rn(n.z, L));
+}
+// adjoint of N = local_normal(p) wrt p
+DSK_DEV float3 local_normal_adj(const ToolParams& T, int kind, float3 p, float3 gN) {
+  float L;
+  float3 n = local_normal_raw(T, kind, p, L);
+  // N = n / L, L = sqrt(n.n + eps)
+  float3 gn = (1.f / L) * gN - (dot(n, gN) / (L * L * L)) * n;
+  if (kind == SDF_CAPSULE) {
+    float y = p.y + T.half_h;
+    float t = tmax(y, 0.f);
+    float dyy = 1.f - (((0.f < y) && (t < T.h)) ? 1.f : 0.f);
+    return f3(gn.x, dyy * gn.y, gn.z);
+  }
+  const float d = DSK_FD_D;
+  const float c = 0.5f / d;
+  float3 gp = f3(0, 0, 0);
+  gp += (c * gn.x) * (local_sdf_grad(T, kind, f3(p.x + d, p.y, p.z)) - local_sdf_grad(T, kind, f3(p.x - d, p.y, p.z)));
+  gp += (c * gn.y) * (local_sdf_grad(T, kind, f3(p.x, p.y + d, p.z)) - local_sdf_grad(T, kind, f3(p.x, p.y - d, p.z)));
+  gp += (c * gn.z) * (local_sdf_grad(T, kind, f3(p.x, p.y, p.z + d)) - local_sdf_grad(T, kind, f3(p.x, p.y, p.z - d)));
+  return gp;
+}
+
+// ---- world <-> tool frame -----------------------------------------------------------------------
+DSK_DEV float3 inv_trans(const Frame& F, float3 p) {  // utils.py:50-54
+  return qrot_rn(qconj_normalized_rn(F.q), sub3_rn(p, F.o));
+}
+// adjoint of pl = inv_trans(F, p) given g(pl); accumulates into gF and gp
+DSK_DEV void inv_trans_adj(const Frame& F, float3 p, float3 gpl, FrameAdj& gF, float3& gp) {
+  Q4 qn = qconj_normalized_rn(F.q);
+  float3 d = p - F.o;
+  Q4 gqn = {0, 0, 0, 0};
+  float3 gd = f3(0, 0, 0);
+  qrot_adj(qn, d, gpl, gqn, gd);
+  qconj_normalized_adj(F.q, gqn, gF.q);
+  gF.o -= gd;
+  gp += gd;
+}
+
+DSK_DEV float frame_sdf(const ToolParams& T, int kind, const Frame& F, float3 p) {
+  return local_sdf(T, kind, inv_trans(F, p));
+}
+DSK_DEV void frame_sdf_adj(const ToolParams& T, int kind, const Frame& F, float3 p, float gd, FrameAdj& gF,
+                           float3& gp) {
+  float3 pl = inv_trans(F, p);
+  float3 g = gd * local_sdf_grad(T, kind, pl);
+  inv_trans_adj(F, p, g, gF, gp);
+}
+DSK_DEV float3 frame_normal(const ToolParams& T, int kind, const Frame& F, float3 p) {  // primive_base.py:80-85
+  return qrot_rn(F.q, local_normal(T, kind, inv_trans(F, p)));
+}
+DSK_DEV void frame_normal_adj(const ToolParams& T, int kind, const Frame& F, float3 p, float3 gD, FrameAdj& gF,
+                              float3& gp) {
+  float3 pl = inv_trans(F, p);
+  float3 Nl = local_normal(T, kind, pl);
+  float3 gNl = f3(0, 0, 0);
+  qrot_adj(F.q, Nl, gD, gF.q, gNl);
+  float3 gpl = local_normal_adj(T, kind, pl, gNl);
+  inv_trans_adj(F, p, gpl, gF, gp);
+}
+// collider_v, primive_base.py:87-94
+DSK_DEV float3 frame_collider_v(const Frame& F0, const Frame& F1, float3 p, float dt) {
+  float3 rel = qrot_rn(qconj_normalized_rn(F0.q), sub3_rn(p, F0.o));
+  float3 np = add3_rn(qrot_rn(F1.q, rel), F1.o);
+  return f3(__fdiv_rn(sub_rn(np.x, p.x), dt), __fdiv_rn(sub_rn(np.y, p.y), dt), __fdiv_rn(sub_rn(np.z, p.z), dt));
+}
+DSK_DEV void frame_collider_v_adj(const Frame& F0, const Frame& F1, float3 p, float dt, float3 gcv, FrameAdj& g0,
+                                  FrameAdj& g1) {
+  float3 rel = qrot_rn(qconj_normalized_rn(F0.q), sub3_rn(p, F0.o));
+  float3 gnp = (1.f / dt) * gcv;
+  g1.o += gnp;
+  float3 grel = f3(0, 0, 0);
+  qrot_adj(F1.q, rel, gnp, g1.q, grel);
+  float3 gp_unused = f3(0, 0, 0);
+  inv_trans_adj(F0, p, grel, g0, gp_unused);
+}
+
+// ---- contact response ------------------------------------------------------------------------------
+// Primitive.collide (primive_base.py:96-120, eps14 = false) / Gripper.collide2 (primitives.py:513-536, eps14 = true)
+DSK_DEV bool contact_active(float dist, float softness, float& influence) {
+  influence = tmin(expf(-dist * softness), 1.f);
+  return (softness > 0.f && influence > 0.1f) || dist <= 0.f;
+}
+DSK_DEV float3 contact_response(float3 v, float3 D, float3 cv, float influence, float friction, bool eps14) {
+  float3 u = v - cv;
+  float nc = dot(u, D);
+  float mn = tmin(nc, 0.f);
+  float3 t = u - mn * D;
+  float tn = sqrtf(dot(t, t) + (eps14 ? 1e-14f : 1e-8f));
+  float mx = tmax(0.f, tn + nc * friction);
+  bool flag = (nc < 0.f) && (sqrtf(dot(t, t)) > 1e-30f);
+  float3 t2 = flag ? f3(t.x / tn * mx, t.y / tn * mx, t.z / tn * mx) : t;
+  return cv + u * (1.f - influence) + t2 * influence;
+}
+// forward of one contact against frame (F0 at f, F1 at f+1)
+DSK_DEV float3 contact_forward(const ToolParams& T, int kind, const Frame& F0, const Frame& F1, float3 p, float3 v,
+                               float dt, bool eps14) {
+  float dist = frame_sdf(T, kind, F0, p);
+  float influence;
+  if (contact_active(dist, T.softness, influence)) {
+    float3 D = frame_normal(T, kind, F0, p);
+    float3 cv = frame_collider_v(F0, F1, p, dt);
+    v = contact_response(v, D, cv, influence, T.friction, eps14);
+  }
+  return v;
+}
+// adjoint: given g(v_out) returns g(v_in) and accumulates frame adjoints
+DSK_DEV float3 contact_adjoint(const ToolParams& T, int kind, const Frame& F0, const Frame& F1, float3 p, float3 v,
+                               float dt, bool eps14, float3 gout, FrameAdj& g0, FrameAdj& g1) {
+  float dist = frame_sdf(T, kind, F0, p);
+  float influence;
+  if (!contact_active(dist, T.softness, influence)) return gout;
+  float3 D = frame_normal(T, kind, F0, p);
+  float3 cv = frame_collider_v(F0, F1, p, dt);
+  float friction = T.friction;
+  // recompute forward intermediates
+  float3 u = v - cv;
+  float nc = dot(u, D);
+  float mn = tmin(nc, 0.f);
+  float3 t = u - mn * D;
+  float tn = sqrtf(dot(t, t) + (eps14 ? 1e-14f : 1e-8f));
+  float a2 = tn + nc * friction;
+  float mx = tmax(0.f, a2);
+  bool flag = (nc < 0.f) && (sqrtf(dot(t, t)) > 1e-30f);
+  float3 q = (1.f / tn) * t;
+  float3 t2 = flag ? mx * q : t;
+  // out = cv + u*(1-infl) + t2*infl
+  float3 gcv = gout;
+  float3 gu = (1.f - influence) * gout;
+  float ginfl = dot(gout, t2 - u);
+  float3 gt2 = influence * gout;
+  float3 gt = f3(0, 0, 0);
+  float gnc = 0.f;
+  if (flag) {
+    // t2 = (t/tn) * mx
+    float3 gq = mx * gt2;
+    float gmx = dot(gt2, q);
+    float ga2 = (a2 < 0.f) ? 0.f : gmx;  // max(0, a2): rhs gets it unless a2 < 0
+    float gtn = ga2 - dot(gq, t) / (tn * tn);
+    gt += (1.f / tn) * gq;
+    gnc += ga2 * friction;
+    gt += (gtn / tn) * t;  // tn = sqrt(t.t + eps)
+  } else {
+    gt += gt2;
+  }
+  // t = u - mn*D
+  gu += gt;
+  float gmn = -dot(gt, D);
+  float3 gD = (-mn) * gt;
+  if (nc < 0.f) gnc += gmn;  // min(nc, 0)
+  // nc = u.D
+  gu += gnc * D;
+  gD += gnc * u;
+  // u = v - cv
+  float3 gv = gu;
+  gcv -= gu;
+  // influence = min(exp(-dist*softness), 1)
+  float e = expf(-dist * T.softness);
+  float gdist = (e < 1.f) ? (-T.softness * e * ginfl) : 0.f;
+  float3 gp_unused = f3(0, 0, 0);
+  frame_normal_adj(T, kind, F0, p, gD, g0, gp_unused);
+  frame_collider_v_adj(F0, F1, p, dt, gcv, g0, g1);
+  frame_sdf_adj(T, kind, F0, p, gdist, g0, gp_unused);
+  return gv;
+}
+
+// ---- tool level: frames of a tool, gripper jaws ----------------------------------------------------
+DSK_DEV Frame tool_frame(const Pose& P) {
+  Frame F;
+  F.o = P.p;
+  F.q = P.q;
+  return F;
+}
+DSK_DEV Frame jaw_frame(const Pose& P, float flag) {  // Gripper.get_pos, primitives.py:471-473
+  Frame F;
+  float off = mul_rn(__fdiv_rn(P.gap, 2.f), flag);
+  F.o = add3_rn(P.p, qrot_rn(P.q, f3(off, 0.f, 0.f)));
+  F.q = P.q;
+  return F;
+}
+DSK_DEV void jaw_frame_adj(const Pose& P, float flag, const FrameAdj& gF, PoseAdj& gP) {
+  gP.p += gF.o;
+  gP.q.w += gF.q.w;
+  gP.q.x += gF.q.x;
+  gP.q.y += gF.q.y;
+  gP.q.z += gF.q.z;
+  float off = P.gap / 2.f * flag;
+  float3 goff = f3(0, 0, 0);
+  qrot_adj(P.q, f3(off, 0.f, 0.f), gF.o, gP.q, goff);
+  gP.gap += goff.x * flag * 0.5f;
+}
+DSK_DEV void tool_frame_adj(const FrameAdj& gF, PoseAdj& gP) {
+  gP.p += gF.o;
+  gP.q.w += gF.q.w;
+  gP.q.x += gF.q.x;
+  gP.q.y += gF.q.y;
+  gP.q.z += gF.q.z;
+}
+
+// Primitive.collide / Gripper.collide for one tool at one grid node
+DSK_DEV float3 tool_collide(const ToolParams& T, const Pose& P0, const Pose& P1, float3 p, float3 v, float dt) {
+  if (T.type == DSK_TOOL_GRIPPER) {  // primitives.py:507-511: jaws applied sequentially
+    v = contact_forward(T, SDF_BOX, jaw_frame(P0, -1.f), jaw_frame(P1, -1.f), p, v, dt, true);
+    v = contact_forward(T, SDF_BOX, jaw_frame(P0, 1.f), jaw_frame(P1, 1.f), p, v, dt, true);
+    return v;
+  }
+  return contact_forward(T, sdf_kind(T.type), tool_frame(P0), tool_frame(P1), p, v, dt, false);
+}
+// adjoint; v is the velocity ENTERING this tool
+DSK_DEV float3 tool_collide_adj(const ToolParams& T, const Pose& P0, const Pose& P1, float3 p, float3 v, float dt,
+                                float3 gout, PoseAdj& g0, PoseAdj& g1) {
+  if (T.type == DSK_TOOL_GRIPPER) {
+    Frame a0 = jaw_frame(P0, -1.f), a1 = jaw_frame(P1, -1.f), b0 = jaw_frame(P0, 1.f), b1 = jaw_frame(P1, 1.f);
+    float3 vmid = contact_forward(T, SDF_BOX, a0, a1, p, v, dt, true);
+    FrameAdj ga0 = frame_adj_zero(), ga1 = frame_adj_zero(), gb0 = frame_adj_zero(), gb1 = frame_adj_zero();
+    float3 gmid = contact_adjoint(T, SDF_BOX, b0, b1, p, vmid, dt, true, gout, gb0, gb1);
+    float3 gin = contact_adjoint(T, SDF_BOX, a0, a1, p, v, dt, true, gmid, ga0, ga1);
+    jaw_frame_adj(P0, 1.f, gb0, g0);
+    jaw_frame_adj(P1, 1.f, gb1, g1);
+    jaw_frame_adj(P0, -1.f, ga0, g0);
+    jaw_frame_adj(P1, -1.f, ga1, g1);
+    return gin;
+  }
+  FrameAdj f0 = frame_adj_zero(), f1 = frame_adj_zero();
+  float3 gin = contact_adjoint(T, sdf_kind(T.type), tool_frame(P0), tool_frame(P1), p, v, dt, false, gout, f0, f1);
+  tool_frame_adj(f0, g0);
+  tool_frame_adj(f1, g1);
+  return gin;
+}
+
+// Primitive.sdf / Gripper.sdf and normals at tool level (collision projection, min-dist observation)
+DSK_DEV float tool_sdf(const ToolParams& T, const Pose& P, float3 p) {
+  if (T.type == DSK_TOOL_GRIPPER)
+    return tmin(frame_sdf(T, SDF_BOX, jaw_frame(P, -1.f), p), frame_sdf(T, SDF_BOX, jaw_frame(P, 1.f), p));
+  return frame_sdf(T, sdf_kind(T.type), tool_frame(P), p);
+}
+DSK_DEV void tool_sdf_adj(const ToolParams& T, const Pose& P, float3 p, float gd, PoseAdj& gP, float3& gp) {
+  if (T.type == DSK_TOOL_GRIPPER) {
+    Frame a = jaw_frame(P, -1.f), b = jaw_frame(P, 1.f);
+    float da = frame_sdf(T, SDF_BOX, a, p), db = frame_sdf(T, SDF_BOX, b, p);
+    FrameAdj g = frame_adj_zero();
+    if (da < db) {
+      frame_sdf_adj(T, SDF_BOX, a, p, gd, g, gp);
+      jaw_frame_adj(P, -1.f, g, gP);
+    } else {
+      frame_sdf_adj(T, SDF_BOX, b, p, gd, g, gp);
+      jaw_frame_adj(P, 1.f, g, gP);
+    }
+    return;
+  }
+  FrameAdj g = frame_adj_zero();
+  frame_sdf_adj(T, sdf_kind(T.type), tool_frame(P), p, gd, g, gp);
+  tool_frame_adj(g, gP);
+}
+DSK_DEV float3 tool_normal(const ToolParams& T, const Pose& P, float3 p) {
+  if (T.type == DSK_TOOL_GRIPPER) {  // primitives.py:489-496
+    Frame a = jaw_frame(P, -1.f), b = jaw_frame(P, 1.f);
+    float da = frame_sdf(T, SDF_BOX, a, p), db = frame_sdf(T, SDF_BOX, b, p);
+    return (da <= db) ? frame_normal(T, SDF_BOX, a, p) : frame_normal(T, SDF_BOX, b, p);
+  }
+  return frame_normal(T, sdf_kind(T.type), tool_frame(P), p);
+}
+DSK_DEV void tool_normal_adj(const ToolParams& T, const Pose& P, float3 p, float3 gN, PoseAdj& gP, float3& gp) {
+  if (T.type == DSK_TOOL_GRIPPER) {
+    Frame a = jaw_frame(P, -1.f), b = jaw_frame(P, 1.f);
+    float da = frame_sdf(T, SDF_BOX, a, p), db = frame_sdf(T, SDF_BOX, b, p);
+    FrameAdj g = frame_adj_zero();
+    if (da <= db) {
+      frame_normal_adj(T, SDF_BOX, a, p, gN, g, gp);
+      jaw_frame_adj(P, -1.f, g, gP);
+    } else {
+      frame_normal_adj(T, SDF_BOX, b, p, gN, g, gp);
+      jaw_frame_adj(P, 1.f, g, gP);
+    }
+    return;
+  }
+  FrameAdj g = frame_adj_zero();
+  frame_normal_adj(T, sdf_kind(T.type), tool_frame(P), p, gN, g, gp);
+  tool_frame_adj(g, gP);
+}

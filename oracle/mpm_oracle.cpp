@@ -629,6 +629,9 @@ struct Sim {
   std::vector<T> mu, lam, ys;
   std::vector<T> Ftmp, U, sig, V, gFtmp, gU, gsig, gV;
   std::vector<T> grid_v_in, grid_v_out, grid_m, g_grid_v_in, g_grid_v_out, g_grid_m;
+  // The reference scatters with float atomics whose order is unspecified (GPU) -- the oracle accumulates every
+  // scatter in double and rounds once: the order-independent centre of all valid fp32 results.
+  std::vector<double> acc4, acc3;
   std::vector<ToolState<T>> tools;
   std::vector<T> rand_num, rand_points, g_rand_points;
   std::vector<int> collision_idx;
@@ -671,6 +674,8 @@ struct Sim {
     for (auto* p : {&grid_v_in, &grid_v_out, &g_grid_v_in, &g_grid_v_out}) p->assign((size_t)G * 3, 0);
     grid_m.assign(G, 0);
     g_grid_m.assign(G, 0);
+    acc4.assign((size_t)G * 4, 0.0);
+    acc3.assign((size_t)G * 3, 0.0);
     tools.resize(K);
     for (int i = 0; i < K; i++) {
       const orc_tool_cfg& tc = c.tools[i];
@@ -795,6 +800,7 @@ struct Sim {
     for (int p = 0; p < n; p++) svd3<T>(&Ftmp[(size_t)p * 9], &U[(size_t)p * 9], &sig[(size_t)p * 3], &V[(size_t)p * 9]);
   }
   void p2g(int f) {
+    std::fill(acc4.begin(), acc4.end(), 0.0);
 #pragma omp parallel for schedule(static)
     for (int p = 0; p < n; p++) {
       size_t fp = (size_t)f * cap + p;
@@ -807,11 +813,16 @@ struct Sim {
       for (int q = 0; q < 27; q++) {
         for (int d = 0; d < 3; d++) {
 #pragma omp atomic
-          grid_v_in[(size_t)o.node[q] * 3 + d] += o.mv[q][d];
+          acc4[(size_t)o.node[q] * 4 + d] += (double)o.mv[q][d];
         }
 #pragma omp atomic
-        grid_m[o.node[q]] += o.m[q];
+        acc4[(size_t)o.node[q] * 4 + 3] += (double)o.m[q];
       }
+    }
+#pragma omp parallel for schedule(static)
+    for (int g = 0; g < G; g++) {
+      for (int d = 0; d < 3; d++) grid_v_in[(size_t)g * 3 + d] = (T)acc4[(size_t)g * 4 + d];
+      grid_m[g] = (T)acc4[(size_t)g * 4 + 3];
     }
   }
   void forward_kinematics(int i, int f) {
@@ -946,6 +957,7 @@ struct Sim {
 
   // ---- adjoint kernels ------------------------------------------------------
   void g2p_grad(int f) {
+    std::fill(acc3.begin(), acc3.end(), 0.0);
 #pragma omp parallel for schedule(static)
     for (int p = 0; p < n; p++) {
       typedef Var<T> S;
@@ -980,22 +992,25 @@ struct Sim {
       for (int d = 0; d < 3; d++) gx[fp * 3 + d] += xx[d].grad();
       for (q = 0; q < 27; q++)
         for (int d = 0; d < 3; d++) {
-          T g = gvv[q][d].grad();
+          double g = (double)gvv[q][d].grad();
 #pragma omp atomic
-          g_grid_v_out[nodes[q] * 3 + d] += g;
+          acc3[nodes[q] * 3 + d] += g;
         }
     }
+#pragma omp parallel for schedule(static)
+    for (int g = 0; g < G; g++)
+      for (int d = 0; d < 3; d++) g_grid_v_out[(size_t)g * 3 + d] += (T)acc3[(size_t)g * 3 + d];
   }
   void grid_op_grad(int f) {
     int nn = k.n;
     std::vector<ToolC<T>> tc(K);
     for (int i = 0; i < K; i++) tc[i] = tools[i].c;
     int nth = omp_get_max_threads();
-    std::vector<std::vector<T>> acc(nth, std::vector<T>((size_t)K * 16, T(0)));
+    std::vector<std::vector<double>> acc(nth, std::vector<double>((size_t)K * 16, 0.0));
 #pragma omp parallel
     {
       typedef Var<T> S;
-      std::vector<T>& my = acc[omp_get_thread_num()];
+      std::vector<double>& my = acc[omp_get_thread_num()];
       std::vector<Pose<S>> P0(K), P1(K);
 #pragma omp for schedule(static)
       for (int g = 0; g < G; g++) {
@@ -1017,7 +1032,7 @@ struct Sim {
         for (int d = 0; d < 3; d++) g_grid_v_in[(size_t)g * 3 + d] += vin[d].grad();
         g_grid_m[g] += m.grad();
         for (int i = 0; i < K; i++) {
-          T* a = &my[(size_t)i * 16];
+          double* a = &my[(size_t)i * 16];
           for (int d = 0; d < 3; d++) a[d] += P0[i].pos[d].grad();
           for (int d = 0; d < 4; d++) a[3 + d] += P0[i].rot[d].grad();
           a[7] += P0[i].gap.grad();
@@ -1027,16 +1042,18 @@ struct Sim {
         }
       }
     }
-    for (int t = 0; t < nth; t++)
+    for (int t = 1; t < nth; t++)
+      for (size_t q = 0; q < (size_t)K * 16; q++) acc[0][q] += acc[t][q];
+    for (int t = 0; t < 1; t++)
       for (int i = 0; i < K; i++) {
-        const T* a = &acc[t][(size_t)i * 16];
+        const double* a = &acc[t][(size_t)i * 16];
         ToolState<T>& ts = tools[i];
-        for (int d = 0; d < 3; d++) ts.g_pos[f * 3 + d] += a[d];
-        for (int d = 0; d < 4; d++) ts.g_rot[f * 4 + d] += a[3 + d];
-        ts.g_gap[f] += a[7];
-        for (int d = 0; d < 3; d++) ts.g_pos[(f + 1) * 3 + d] += a[8 + d];
-        for (int d = 0; d < 4; d++) ts.g_rot[(f + 1) * 4 + d] += a[11 + d];
-        ts.g_gap[f + 1] += a[15];
+        for (int d = 0; d < 3; d++) ts.g_pos[f * 3 + d] += (T)a[d];
+        for (int d = 0; d < 4; d++) ts.g_rot[f * 4 + d] += (T)a[3 + d];
+        ts.g_gap[f] += (T)a[7];
+        for (int d = 0; d < 3; d++) ts.g_pos[(f + 1) * 3 + d] += (T)a[8 + d];
+        for (int d = 0; d < 4; d++) ts.g_rot[(f + 1) * 4 + d] += (T)a[11 + d];
+        ts.g_gap[f + 1] += (T)a[15];
       }
   }
   void apply_collision_projection_grad(int s) {
@@ -1323,13 +1340,14 @@ struct Sim {
         }
   }
   void compute_grid_m(int f) {
-    std::fill(grid_m.begin(), grid_m.end(), T(0));
+    std::fill(acc4.begin(), acc4.end(), 0.0);
     for (int p = 0; p < n; p++) {
       T o[27];
       size_t nodes[27];
       grid_m_body<T>(load_v3<T>(x, (size_t)f * cap + p, false), o, nodes);
-      for (int q = 0; q < 27; q++) grid_m[nodes[q]] += o[q];
+      for (int q = 0; q < 27; q++) acc4[nodes[q] * 4 + 3] += (double)o[q];
     }
+    for (int g = 0; g < G; g++) grid_m[g] = (T)acc4[(size_t)g * 4 + 3];
   }
   void compute_grid_m_grad(int f) {
     typedef Var<T> S;
