@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: differentiable MLS-MPM substeps, forward + backward.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+Metric (BASELINE.json): particle-substeps/sec fwd+bwd.  One *step* of this benchmark is one
+trajectory-optimisation iteration of the workload: H env steps forward (H*S substeps), the loss at
+every step boundary, H env steps backward (H*S adjoint substeps), action gradients out.
+
+Default workload = BASELINE.json configs[1]: LiftSpread-v1, 50-step forward+backward action-gradient
+iteration, single env (15 707-particle synthetic dough), one env per GPU (weak scaling over GPUs).
+
+JSON keys follow the driver contract; see DESIGN.md "Measurement" for the byte accounting.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-substeps/sec fwd+bwd"
+UNIT = "particle-substeps/s"
+
+# algorithmic bytes (SURVEY.md section 8d / BASELINE.md section 2), apportioned per kernel class:
+# (bytes per particle, bytes per occupied node) of ONE launch
+KERNEL_BYTES = {
+    'p2g': (132, 16), 'grid_op': (0, 28), 'g2p': (60, 12),                                     # fwd: 192 / 56
+    'p2g_recompute': (96, 16), 'grid_op_recompute': (0, 28), 'g2p_adj': (60, 24),               # bwd: 288 / 112
+    'grid_op_adj': (0, 28), 'p2g_adj': (132, 16),
+}
+
+
+def workload_spec(name):
+    if name == 'liftspread':
+        return dict(env='LiftSpread-v1', horizon=50, envs_per_gpu=1, desc='LiftSpread-v1 H=50 fwd+bwd, 1 env/GPU')
+    if name == 'gathermove':
+        return dict(env='GatherMove-v1', horizon=50, envs_per_gpu=None, total_envs=64,
+                    desc='GatherMove-v1 H=50 fwd+bwd, 64 envs sharded over the GPUs')
+    if name == 'cutrearrange':
+        return dict(env='CutRearrange-v1', horizon=42, envs_per_gpu=32, desc='CutRearrange-v1 H=42 fwd+bwd, 32 envs/GPU')
+    raise SystemExit(f'unknown workload {name}')
+
+
+def make_inputs(spec, rank, n_envs):
+    """Synthetic start/goal pairs (the Google-Drive dataset is unavailable offline): SURVEY.md section 8d."""
+    from diffskill_b200.scene import load_scene
+    from diffskill_b200.shapes import Shapes
+    scene, cfg = load_scene(spec['env'])
+    H = spec['horizon']
+    xs, targets, actions = [], [], []
+    for b in range(n_envs):
+        gid = rank * n_envs + b
+        shapes = [dict(s) for s in cfg.SHAPES]
+        if shapes[0]['shape'] == 'scatter':
+            shapes[0]['seed'] = gid
+        x = Shapes(shapes, seed=gid).get()[0].astype(np.float32)
+        # goal: the same dough flattened to half height, spread by sqrt(2) and moved 0.1 towards -x
+        c = x.mean(0)
+        t = (x - c) * np.array([1.414, 0.5, 1.414], np.float32) + c + np.array([-0.1, -0.25 * (x[:, 1].max() - x[:, 1].min()), 0.], np.float32)
+        xs.append(x)
+        targets.append(t.astype(np.float32))
+        actions.append(np.random.RandomState(100 + gid).uniform(-1, 1, (H, scene.action_dim)).astype(np.float32))
+    return scene, cfg, xs, targets, np.stack(actions, 1)   # actions [H, B, A]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def occupied_nodes(eng, steps, n_envs):
+    """Mean number of occupied grid nodes (inside the 3^3 stencil of >= 1 particle; integer-derived) per env,
+    sampled at step boundaries -- the N_occ of the byte accounting."""
+    tot, cnt = 0, 0
+    n = eng.n_grid
+    for s in steps:
+        for b in range(n_envs):
+            base, _ = eng.debug_cell_index(s, b)
+            occ = np.zeros((n, n, n), bool)
+            for i in range(3):
+                for j in range(3):
+                    for l in range(3):
+                        occ[base[:, 0] + i, base[:, 1] + j, base[:, 2] + l] = True
+            tot += int(occ.sum())
+            cnt += 1
+    return tot / max(cnt, 1)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def cpu_oracle_sample(spec, threads, env_steps=1, repeats=1):
+    """Times the CPU oracle (a port of the reference; Taichi is not installable offline) on a bounded sample:
+    `env_steps` env steps forward + backward of env 0 of the workload.  Returns particle-substeps/s."""
+    from oracle import oracle as orc
+    scene, cfg, xs, targets, actions = make_inputs(spec, 0, 1)
+    x0 = xs[0]
+    n = len(x0)
+    S = scene.substeps
+    o = orc.Oracle(scene, n, env_steps * S + 1, f64=False, threads=threads)
+    best = None
+    for _ in range(repeats):
+        o.reset(x0.astype(np.float64))
+        for i, t in enumerate(scene.tools):
+            o.set_tool_state(0, i, t.init_state)
+        o.zero_grad()
+        t0 = time.perf_counter()
+        for s in range(env_steps):
+            o.forward_step(s, actions[s, 0])
+            x = o.get_frame((s + 1) * S)[0]
+            o.add_frame_grad((s + 1) * S, gx=2.0 * (x - targets[0]) / n)
+        for s in range(env_steps - 1, -1, -1):
+            o.backward_step(s)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n * S * env_steps / best, best, n, S
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  The reference's Taichi
+    backend cannot be installed offline, so this times the oracle port (oracle/), all host threads."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    spec = workload_spec(args.workload)
+    threads = os.cpu_count() or 1
+    env_steps = 1
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt, n, S = cpu_oracle_sample(spec, threads, env_steps)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    v = float(np.mean([a for a, _ in vals]))
+    ms = float(np.mean([b for _, b in vals]) * 1e3)
+    sample = (f'{env_steps} env step ({S} substeps fwd + {S} adjoint substeps) of env 0 ({n} particles) per step; '
+              'adjoints via the oracle tape AD (about 10x the arithmetic of a hand-written reverse pass)')
+    out = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+               ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+               impl='reference',
+               config=dict(workload=spec['desc'], horizon=spec['horizon'], l2='n/a (CPU)'),
+               cpu_baseline=dict(value=v, unit=UNIT, cores=threads, kind='port', sample=sample),
+               e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='liftspread')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--step-slots', type=int, default=1, help='substep-frame ring (1 = per-step checkpointing)')
+    ap.add_argument('--no-sort', action='store_true')
+    ap.add_argument('--no-graphs', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    assert args.warmup >= 3, 'timing rules: at least 3 warm-up steps'
+
+    import torch
+    import torch.distributed as dist
+    from diffskill_b200.engine import Engine
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    spec = workload_spec(args.workload)
+    B = spec['envs_per_gpu'] or spec['total_envs'] // world
+    H = spec['horizon']
+    scene, cfg, xs, targets, actions = make_inputs(spec, rank, B)
+    cap = max(len(x) for x in xs)
+    eng = Engine(scene, n_envs=B, capacity=cap, max_steps=H, step_slots=args.step_slots, sort=not args.no_sort,
+                 device=local_rank)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    if args.no_graphs:
+        eng.set_graphs(False)
+    S, A = scene.substeps, scene.action_dim
+    tgt = np.zeros((B, cap, 3), np.float32)
+    for b in range(B):
+        eng.set_particles(0, b, xs[b])
+        tgt[b, :len(xs[b])] = targets[b]
+    n_particles = sum(len(x) for x in xs)
+    tgt_dev = torch.from_numpy(tgt).to(dev)
+    act_host = torch.from_numpy(actions).pin_memory()           # [H,B,A] pinned host
+    act_dev = act_host.to(dev)
+    grads_host = torch.zeros((H, B, A)).pin_memory()
+    loss_host = torch.zeros(B).pin_memory()
+    grads_dev = torch.zeros((H, B, A), device=dev)
+    loss_dev = torch.zeros(B, device=dev)
+    if world > 1:
+        all_grads = torch.zeros((world, H, B, A), device=dev)
+        all_loss = torch.zeros((world, B), device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    w = 1.0 / H
+
+    def iteration(e2e):
+        eng.zero_grad()
+        eng.loss_reset()
+        for s in range(H):
+            eng.set_action(s, act_host[s].numpy() if e2e else act_dev[s])   # e2e: H2D copy of this step's action
+            eng.forward_step(s)
+            eng.loss_add_l2(s + 1, tgt_dev, w)
+        for s in range(H - 1, -1, -1):
+            eng.backward_step(s)
+        if world > 1:   # the planner's exchange step: per-env losses and action gradients of every rank
+            eng.get_action_grads(0, H, grads_dev)
+            eng.loss_get(loss_dev)
+            dist.all_gather_into_tensor(all_grads, grads_dev)
+            dist.all_gather_into_tensor(all_loss, loss_dev)
+        if e2e:         # D2H read of the step's result
+            eng.get_action_grads(0, H, grads_host.numpy())
+            eng.loss_get(loss_host.numpy())
+
+    def timed(e2e, iters):
+        ms = []
+        for _ in range(iters):
+            flush.zero_()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            iteration(e2e)
+            b.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+        t = torch.tensor(ms, device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)   # max over ranks, per iteration
+        return t.cpu().numpy()
+
+    for _ in range(args.warmup):
+        iteration(False)
+    iteration(True)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count()
+    ms_dev = timed(False, args.steps)
+    launches = (eng.launch_count() - l0) // args.steps
+    ms_e2e = timed(True, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-kernel durations: one more iteration, launched eagerly with CUDA events around every kernel --------
+    eng.profile_enable(True)
+    eng.profile_report(reset=True)
+    iteration(False)
+    prof = eng.profile_report(reset=True)
+    eng.profile_enable(False)
+    n_occ = occupied_nodes(eng, range(0, H + 1, max(1, H // 10)), B) * B   # per launch, all envs
+    final_loss = float(eng.loss_get().sum())
+    g = eng.get_action_grads(0, H)
+    finite = bool(np.isfinite(g).all() and np.isfinite(final_loss))
+
+    if rank == 0:
+        ms_step = float(ms_dev.mean())
+        units = n_particles * world * H * S                 # particle-substeps (fwd+bwd) per iteration, all ranks
+        value = units / (ms_step * 1e-3)
+        e2e_value = units / (float(ms_e2e.mean()) * 1e-3)
+        peak, peak_src = measured_peak()
+        total_ms = sum(v[0] for v in prof.values())
+        shares = {k: v[0] / total_ms for k, v in prof.items()}
+        dom = max((k for k in prof if k in KERNEL_BYTES), key=lambda k: prof[k][0])
+        bp, bn = KERNEL_BYTES[dom]
+        alg_bytes = bp * n_particles + bn * n_occ
+        dur_ms = prof[dom][0] / prof[dom][1]
+        achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
+        step_bytes = (480 * n_particles + 168 * n_occ) * H * S
+        roof = dict(bound='hbm', kernel=dom, achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
+                    traffic=None, peak_source=peak_src, algorithmic_bytes_per_launch=alg_bytes,
+                    avg_launch_us=dur_ms * 1e3, kernel_share_of_step=shares[dom],
+                    step_achieved_gbs=step_bytes / (ms_step * 1e-3) / 1e9,
+                    step_frac=step_bytes / (ms_step * 1e-3) / 1e9 / peak,
+                    method='CUDA events around every launch of one eager (graph-free) iteration on the engine stream',
+                    per_kernel_us={k: round(v[0] / v[1] * 1e3, 2) for k, v in prof.items()},
+                    per_kernel_share={k: round(s_, 4) for k, s_ in shares.items()})
+        out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                   ms_per_step=ms_step, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                   data='synthetic',
+                   config=dict(workload=spec['desc'], env=spec['env'], horizon=H, substeps=S, envs_per_gpu=B,
+                               particles_per_gpu=n_particles, n_grid=scene.n_grid, occupied_nodes=round(n_occ),
+                               checkpointing=f'per env step, {args.step_slots} step slot(s) of substep frames',
+                               sort=not args.no_sort, cuda_graphs=not args.no_graphs,
+                               l2='flushed between timed iterations (256 MiB write)',
+                               parallelism=f'env-sharded x{world}' if world > 1 else 'single GPU'),
+                   e2e=dict(value=e2e_value, unit=UNIT, ms_per_step=float(ms_e2e.mean()),
+                            h2d_bytes_per_step=int(act_host.numel() * 4),
+                            d2h_bytes_per_step=int(grads_host.numel() * 4 + loss_host.numel() * 4)),
+                   gpu_launches=int(launches), roofline=roof, clocks=clocks,
+                   loss=final_loss, finite=finite, engine_bytes=eng.memory_bytes())
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, dt, n_, S_ = cpu_oracle_sample(spec, threads, env_steps=1)
+            out['cpu_baseline'] = dict(value=v, unit=UNIT, cores=threads, kind='port',
+                                       sample=f'1 env step ({S_} substeps fwd + {S_} adjoint substeps) of env 0 ({n_} particles), '
+                                              f'{dt:.1f} s; oracle port of the reference (taichi is not installable offline), '
+                                              'adjoints via tape AD')
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

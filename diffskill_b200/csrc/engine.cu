@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -45,8 +46,25 @@ struct StepSlot {
   int action_step = -1;
 };
 
+enum KernelId {
+  KID_SORT = 0, KID_KINEMATICS, KID_P2G, KID_GRID, KID_G2P, KID_P2G_RECOMPUTE, KID_GRID_RECOMPUTE, KID_G2P_ADJ,
+  KID_GRID_ADJ, KID_P2G_ADJ, KID_KINEMATICS_ADJ, KID_REORDER, KID_IO, KID_LOSS, KID_COUNT
+};
+static const char* kKernelNames[KID_COUNT] = {
+    "sort", "kinematics", "p2g", "grid_op", "g2p", "p2g_recompute", "grid_op_recompute", "g2p_adj",
+    "grid_op_adj", "p2g_adj", "kinematics_adj", "reorder", "io", "loss"};
+
+struct ProfRec {
+  int kid;
+  cudaEvent_t a, b;
+};
+
 struct dsk_engine {
   dsk_config cfg;
+  bool profiling = false;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  int64_t kid_launches[KID_COUNT] = {0};
   SimConst k;
   cudaStream_t stream = 0;
   int B, Npad, S, H, K, A, slots, ncols;
@@ -82,10 +100,54 @@ struct dsk_engine {
   int last_fwd_frame = -1, last_bwd_frame = -1, last_substep_slot = -1, last_substep_j = -1;
   bool last_was_backward = false;
   int bwd_cur = 0;  // adjw index holding the adjoint of the current frame
+  // sequences / graphs
+  struct GraphSet {
+    cudaGraphExec_t fwd = nullptr, recompute = nullptr, bwd = nullptr;
+    int64_t n_launch[3] = {0, 0, 0};
+    int64_t kid[3][KID_COUNT] = {{0}};
+  };
+  std::vector<GraphSet> graphs;
+  bool use_graphs = true;
+  cudaStream_t cap_stream = nullptr, qs = 0;  // capture stream; stream KL currently enqueues on
+  StepArgs* d_args = nullptr;
+  int epoch_base = 0;
+  int* done = nullptr;
+  int pending_q = -1;  // fine-grained mode: last substep's grids still hold data
+  bool pending_bwd = false, grids_valid = false;
+  float* loss = nullptr;  // [B]
 
   float* frame_of(float* base, int i) { return base + (size_t)i * frame_floats; }
   float* tools_of(float* base, int step) { return base + (size_t)step * tool_floats; }
 };
+
+static cudaEvent_t prof_event(dsk_engine* e) {
+  if (!e->ev_pool.empty()) {
+    cudaEvent_t ev = e->ev_pool.back();
+    e->ev_pool.pop_back();
+    return ev;
+  }
+  cudaEvent_t ev;
+  cudaEventCreate(&ev);
+  return ev;
+}
+// every kernel launch of the engine goes through KL: counts it and, when profiling, brackets it with events
+#define KL(kid_, ...)                                          \
+  do {                                                         \
+    ProfRec pr__;                                              \
+    if (e->profiling) {                                        \
+      pr__.kid = (kid_);                                       \
+      pr__.a = prof_event(e);                                  \
+      pr__.b = prof_event(e);                                  \
+      cudaEventRecord(pr__.a, e->qs);                      \
+    }                                                          \
+    __VA_ARGS__;                                               \
+    if (e->profiling) {                                        \
+      cudaEventRecord(pr__.b, e->qs);                      \
+      e->prof.push_back(pr__);                                 \
+    }                                                          \
+    e->launches += 1;                                          \
+    e->kid_launches[(kid_)] += 1;                              \
+  } while (0)
 
 template <class T>
 static int dalloc(dsk_engine* e, T** p, size_t count, bool zero = true) {
@@ -104,6 +166,7 @@ static int dalloc(dsk_engine* e, T** p, size_t count, bool zero = true) {
   } while (0)
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static void drop_graphs(dsk_engine* e);
 
 static void fill_tool(ToolParams& T, const dsk_tool_desc& d) {
   memset(&T, 0, sizeof T);
@@ -237,6 +300,12 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
       DA(e->tile_list[s], (size_t)e->B * k.ntile);
     }
     DA(e->tile_count, 4);
+    DA(e->done, 1);
+    DA(e->d_args, 1);
+    DA(e->loss, e->B);
+    e->graphs.resize(e->slots);
+    CK(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+    e->use_graphs = getenv("DSK_NO_GRAPHS") == nullptr;
     DA(e->d_tools, std::max(1, e->K));
     DA(e->tool_ckpt, (size_t)(e->H + 1) * e->tool_floats);
     DA(e->tool_adj_ckpt, (size_t)(e->H + 1) * e->tool_floats);
@@ -270,6 +339,13 @@ int dsk_destroy(dsk_engine* e) {
   if (!e) return 0;
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);
+  drop_graphs(e);
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  for (auto& r : e->prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  for (auto ev : e->ev_pool) cudaEventDestroy(ev);
   for (void* p : e->allocs) cudaFree(p);
   delete e;
   return 0;
@@ -277,6 +353,7 @@ int dsk_destroy(dsk_engine* e) {
 int dsk_set_stream(dsk_engine* e, void* s) {
   CKE(e);
   e->stream = (cudaStream_t)s;
+  e->qs = e->stream;
   return 0;
 }
 int dsk_synchronize(dsk_engine* e) {
@@ -309,6 +386,12 @@ int dsk_memory_bytes(dsk_engine* e, int64_t* n) {
 
 // -------------------------------------------------------------------------------------------------------
 // internal scheduling
+//
+// A "sequence" is the kernel train of one env step: forward (sort, kinematics, S x {p2g, grid_op, g2p}, store),
+// recompute (the same without the store) or backward (gather, S x {p2g, grid_op, g2p_adj, grid_op_adj,
+// p2g_adj}, tool adjoints, scatter).  Every sequence starts and ends with all grids zero and all tile counters
+// zero, and takes its step-dependent pointers from the device-resident StepArgs, so each of the three is
+// captured ONCE per step slot into a CUDA graph and replayed for every env step.
 // -------------------------------------------------------------------------------------------------------
 static int check_step(dsk_engine* e, int step, const char* what) {
   if (step < 0 || step > e->H) return fail("%s: step %d outside [0, %d] (max_steps of this engine)", what, step, e->H);
@@ -318,6 +401,17 @@ static void invalidate_slots(dsk_engine* e, int step) {
   // a checkpoint was overwritten: substep frames simulated from it are stale
   for (auto& s : e->slot)
     if (s.src_step == step) s.src_step = -1;
+}
+static void invalidate_all(dsk_engine* e) {
+  for (auto& s : e->slot) s.src_step = -1;
+}
+static void drop_graphs(dsk_engine* e) {
+  for (auto& g : e->graphs)
+    for (cudaGraphExec_t* x : {&g.fwd, &g.recompute, &g.bwd})
+      if (*x) {
+        cudaGraphExecDestroy(*x);
+        *x = nullptr;
+      }
 }
 
 // one staging copy in: host or device source -> device pointer valid on the stream
@@ -336,163 +430,203 @@ static int stage_in(dsk_engine* e, const float* src, size_t n, int on_device, si
   return 0;
 }
 
-static int begin_step(dsk_engine* e, int src_step, int action_step, StepSlot** out) {
-  SimConst& k = e->k;
-  StepSlot& s = e->slot[src_step % e->slots];
-  int nb = cdiv(k.stride, 256);
-  if (e->cfg.sort_particles) {
-    CK(cudaMemsetAsync(e->cell_count, 0, (size_t)e->B * k.nnode * 4, e->stream));
-    k_sort_bin<<<nb, 256, 0, e->stream>>>(k, e->frame_of(e->ckpt, src_step), e->npart, e->cell_count, e->key, e->rank);
-    k_sort_scan<<<e->B, 1024, 0, e->stream>>>(k, e->cell_count);
-    e->launches += 2;
-  }
-  k_sort_scatter<<<nb, 256, 0, e->stream>>>(k, e->frame_of(e->ckpt, src_step), e->mat, e->npart, e->cell_count, e->key,
-                                            e->rank, e->cfg.sort_particles, s.frames, s.mat, s.perm);
-  const float* act = (e->A > 0 && action_step >= 0) ? e->actions + (size_t)action_step * e->B * e->A : nullptr;
-  if (e->K > 0)
-    k_kinematics<<<e->B, KIN_CTA, 0, e->stream>>>(k, e->d_tools, e->tools_of(e->tool_ckpt, src_step), act, e->rand_num,
-                                                  s.poses, s.cidx);
-  e->launches += 2;
+static int grid_ctas(dsk_engine* e) { return 148 * 8; }
+
+// zero the grids of the last substep of a fine-grained (dsk_substep / dsk_substep_grad) sequence
+static int flush_pending_clear(dsk_engine* e) {
+  if (e->pending_q < 0) return 0;
+  int q = e->pending_q, set = (q + 1) & 1;
+  bool bwd = e->pending_bwd;
+  KL(KID_GRID, k_end_clear<<<grid_ctas(e), GRID_CTA, 0, e->qs>>>(e->k, e->tile_list[set], e->tile_count + ((q + 1) & 3),
+                                                                 e->G0[set], bwd ? e->Gv[set] : nullptr,
+                                                                 bwd ? e->Ga[set] : nullptr, e->tile_count, e->done));
   LAUNCH_CHECK();
-  s.src_step = -1;  // becomes valid once all substeps ran
-  s.action_step = action_step;
-  *out = &s;
+  e->pending_q = -1;
+  e->grids_valid = false;
   return 0;
 }
 
-static int grid_ctas(dsk_engine* e) { return 148 * 8; }
+static StepArgs make_args(dsk_engine* e, int src, int dst, int action_step, int adj_step) {
+  StepArgs a;
+  memset(&a, 0, sizeof a);
+  a.ck_src = e->frame_of(e->ckpt, src);
+  a.ck_dst = e->frame_of(e->ckpt, dst);
+  a.tool_src = e->tools_of(e->tool_ckpt, src);
+  a.tool_dst = e->tools_of(e->tool_ckpt, dst);
+  a.action = (e->A > 0 && action_step >= 0) ? e->actions + (size_t)action_step * e->B * e->A : nullptr;
+  if (adj_step >= 0) {
+    a.adj_in = e->frame_of(e->adj_ckpt, adj_step + 1);
+    a.adj_out = e->frame_of(e->adj_ckpt, adj_step);
+    a.tool_adj_in = e->tools_of(e->tool_adj_ckpt, adj_step + 1);
+    a.tool_adj_out = e->tools_of(e->tool_adj_ckpt, adj_step);
+    a.action_grad = e->A > 0 ? e->action_grad + (size_t)adj_step * e->B * e->A : nullptr;
+  }
+  e->epoch_base += 4 * ((e->S + 8) / 4);
+  a.epoch_base = e->epoch_base;
+  return a;
+}
+static int push_args(dsk_engine* e, const StepArgs& a) {
+  KL(KID_IO, k_set_args<<<1, 1, 0, e->stream>>>(e->d_args, a));
+  LAUNCH_CHECK();
+  return 0;
+}
 
-// forward substep j of a slot (frames j -> j+1)
-static int run_substep(dsk_engine* e, StepSlot& s, int j, bool write_state) {
+// ---- pieces of a sequence (all enqueue on e->qs) --------------------------------------------------------------
+static int seq_begin_forward(dsk_engine* e, StepSlot& s) {
   SimConst& k = e->k;
-  int ep = ++e->epoch;
-  int set = ep & 1, prev = set ^ 1;
-  TileTrack tt{e->tile_epoch[set], e->tile_list[set], e->tile_count + (ep & 3)};
+  int nb = cdiv(k.stride, 256);
+  if (e->cfg.sort_particles) {
+    CK(cudaMemsetAsync(e->cell_count, 0, (size_t)e->B * k.nnode * 4, e->qs));
+    KL(KID_SORT, k_sort_bin<<<nb, 256, 0, e->qs>>>(k, e->d_args, e->npart, e->cell_count, e->key, e->rank));
+    KL(KID_SORT, k_sort_scan<<<e->B, 1024, 0, e->qs>>>(k, e->cell_count));
+  }
+  KL(KID_SORT, k_sort_scatter<<<nb, 256, 0, e->qs>>>(k, e->d_args, e->mat, e->npart, e->cell_count, e->key, e->rank,
+                                                     e->cfg.sort_particles, s.frames, s.mat, s.perm));
+  if (e->K > 0)
+    KL(KID_KINEMATICS, k_kinematics<<<e->B, KIN_CTA, 0, e->qs>>>(k, e->d_tools, e->d_args, e->rand_num, s.poses, s.cidx));
+  LAUNCH_CHECK();
+  return 0;
+}
+// forward substep: q = position in the sequence, j = substep index within the step (frames j -> j+1)
+static int seq_substep(dsk_engine* e, StepSlot& s, int q, int j, bool write_state) {
+  SimConst& k = e->k;
+  int set = (q + 1) & 1, prev = set ^ 1;
+  TileTrack tt{e->tile_epoch[set], e->tile_list[set], e->tile_count + ((q + 1) & 3)};
   int nb = cdiv(k.stride, 128);
   float* fin = s.frames + (size_t)j * e->frame_floats;
   float* fout = s.frames + (size_t)(j + 1) * e->frame_floats;
   if (write_state)
-    k_p2g<true><<<nb, 128, 0, e->stream>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, ep);
+    KL(KID_P2G, k_p2g<true><<<nb, 128, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q));
   else
-    k_p2g<false><<<nb, 128, 0, e->stream>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, ep);
-  int pd = e->dirty[prev];
-  k_grid<<<grid_ctas(e), GRID_CTA, 0, e->stream>>>(
-      k, e->d_tools, s.poses, j, e->G0[set], e->G0[set], tt.list, tt.count, pd ? e->tile_list[prev] : nullptr,
-      e->tile_count + ((ep - 1) & 3), (pd & 1) ? e->G0[prev] : nullptr, (pd & 2) ? e->Gv[prev] : nullptr,
-      (pd & 4) ? e->Ga[prev] : nullptr, e->tile_count + ((ep + 2) & 3));
-  e->dirty[prev] = 0;
-  e->dirty[set] = 1;
-  if (write_state) k_g2p<<<nb, 128, 0, e->stream>>>(k, fin, fout, e->npart, e->G0[set]);
-  e->launches += write_state ? 3 : 2;
+    KL(KID_P2G_RECOMPUTE, k_p2g<false><<<nb, 128, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q));
+  bool clr = q > 0;
+  KL(KID_GRID, k_grid<<<grid_ctas(e), GRID_CTA, 0, e->qs>>>(
+                   k, e->d_tools, s.poses, j, e->G0[set], e->G0[set], tt.list, tt.count,
+                   clr ? e->tile_list[prev] : nullptr, e->tile_count + (q & 3), clr ? e->G0[prev] : nullptr, nullptr,
+                   nullptr, e->tile_count + ((q + 3) & 3)));
+  if (write_state) KL(KID_G2P, k_g2p<<<nb, 128, 0, e->qs>>>(k, fin, fout, e->npart, e->G0[set]));
   LAUNCH_CHECK();
-  e->last_substep_slot = (int)(&s - e->slot.data());
-  e->last_substep_j = j;
-  e->last_was_backward = false;
   return 0;
 }
-
-static int end_step(dsk_engine* e, StepSlot& s, int src_step, int dst_step) {
+static int seq_end_forward(dsk_engine* e, StepSlot& s, bool store) {
   SimConst& k = e->k;
-  int nb = cdiv(k.stride, 256);
-  k_unsort<<<nb, 256, 0, e->stream>>>(k, s.frames + (size_t)e->S * e->frame_floats, e->npart, s.perm,
-                                      e->frame_of(e->ckpt, dst_step), 0);
-  e->launches += 1;
+  if (store) {
+    KL(KID_REORDER, k_unsort<<<cdiv(k.stride, 256), 256, 0, e->qs>>>(k, s.frames + (size_t)e->S * e->frame_floats,
+                                                                    e->npart, s.perm, &e->d_args->ck_dst, 0));
+    if (e->K > 0) KL(KID_IO, k_tool_store<<<cdiv(e->B * e->K * 8, 128), 128, 0, e->qs>>>(k, s.poses, e->d_args));
+  }
   LAUNCH_CHECK();
+  return 0;
+}
+static int seq_clear(dsk_engine* e, int last_q, bool bwd) {
+  int set = (last_q + 1) & 1;
+  KL(KID_GRID, k_end_clear<<<grid_ctas(e), GRID_CTA, 0, e->qs>>>(e->k, e->tile_list[set], e->tile_count + ((last_q + 1) & 3),
+                                                                 e->G0[set], bwd ? e->Gv[set] : nullptr,
+                                                                 bwd ? e->Ga[set] : nullptr, e->tile_count, e->done));
+  LAUNCH_CHECK();
+  return 0;
+}
+static int seq_begin_backward(dsk_engine* e, StepSlot& s) {
+  SimConst& k = e->k;
+  e->bwd_cur = 0;
+  KL(KID_REORDER, k_gather_sorted<<<cdiv(k.stride, 256), 256, 0, e->qs>>>(k, &e->d_args->adj_in, e->npart, s.perm, e->adjw[0]));
   if (e->K > 0)
-    CK(cudaMemcpy2DAsync(e->tools_of(e->tool_ckpt, dst_step), (size_t)e->K * 8 * 4,
-                         s.poses + (size_t)e->S * e->K * 8, (size_t)(e->S + 1) * e->K * 8 * 4, (size_t)e->K * 8 * 4,
-                         e->B, cudaMemcpyDeviceToDevice, e->stream));
-  invalidate_slots(e, dst_step);
-  s.src_step = (dst_step == src_step) ? -1 : src_step;
+    KL(KID_IO, k_pose_adj_init<<<cdiv(e->B * (e->S + 1) * e->K * 8, 128), 128, 0, e->qs>>>(k, e->pose_adj, e->d_args));
+  LAUNCH_CHECK();
   return 0;
 }
-
-// adjoint substep j of a slot: adjoint of frame j+1 in adjw[cur] -> adjoint of frame j in adjw[cur^1]
-static int run_substep_grad(dsk_engine* e, StepSlot& s, int j) {
+// adjoint substep: adjoint of frame j+1 in adjw[cur] -> adjoint of frame j in adjw[cur^1]
+static int seq_substep_grad(dsk_engine* e, StepSlot& s, int q, int j) {
   SimConst& k = e->k;
-  int ep = ++e->epoch;
-  int set = ep & 1, prev = set ^ 1;
-  TileTrack tt{e->tile_epoch[set], e->tile_list[set], e->tile_count + (ep & 3)};
+  int set = (q + 1) & 1, prev = set ^ 1;
+  TileTrack tt{e->tile_epoch[set], e->tile_list[set], e->tile_count + ((q + 1) & 3)};
   int nb = cdiv(k.stride, 128);
   float* fin = s.frames + (size_t)j * e->frame_floats;
   float* fnext = s.frames + (size_t)(j + 1) * e->frame_floats;
   float* ain = e->adjw[e->bwd_cur];
   float* aout = e->adjw[e->bwd_cur ^ 1];
-  k_p2g<false><<<nb, 128, 0, e->stream>>>(k, fin, nullptr, s.mat, e->npart, e->G0[set], tt, ep);
-  int pd = e->dirty[prev];
-  k_grid<<<grid_ctas(e), GRID_CTA, 0, e->stream>>>(
-      k, e->d_tools, s.poses, j, e->G0[set], e->Gv[set], tt.list, tt.count, pd ? e->tile_list[prev] : nullptr,
-      e->tile_count + ((ep - 1) & 3), (pd & 1) ? e->G0[prev] : nullptr, (pd & 2) ? e->Gv[prev] : nullptr,
-      (pd & 4) ? e->Ga[prev] : nullptr, e->tile_count + ((ep + 2) & 3));
-  e->dirty[prev] = 0;
-  e->dirty[set] = 7;
-  k_g2p_adj<<<nb, 128, 0, e->stream>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]);
-  k_grid_adj<<<grid_ctas(e), GRID_CTA, 0, e->stream>>>(k, e->d_tools, s.poses, j, e->G0[set], e->Ga[set], tt.list,
-                                                       tt.count, e->pose_adj, nullptr, nullptr, nullptr, nullptr,
-                                                       nullptr, nullptr);
-  k_p2g_adj<<<nb, 128, 0, e->stream>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]);
-  e->launches += 5;
+  KL(KID_P2G_RECOMPUTE, k_p2g<false><<<nb, 128, 0, e->qs>>>(k, fin, nullptr, s.mat, e->npart, e->G0[set], tt, e->d_args, q));
+  bool clr = q > 0;
+  KL(KID_GRID_RECOMPUTE, k_grid<<<grid_ctas(e), GRID_CTA, 0, e->qs>>>(
+                             k, e->d_tools, s.poses, j, e->G0[set], e->Gv[set], tt.list, tt.count,
+                             clr ? e->tile_list[prev] : nullptr, e->tile_count + (q & 3), clr ? e->G0[prev] : nullptr,
+                             clr ? e->Gv[prev] : nullptr, clr ? e->Ga[prev] : nullptr, e->tile_count + ((q + 3) & 3)));
+  KL(KID_G2P_ADJ, k_g2p_adj<<<nb, 128, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
+  KL(KID_GRID_ADJ, k_grid_adj<<<grid_ctas(e), GRID_CTA, 0, e->qs>>>(k, e->d_tools, s.poses, j, e->G0[set], e->Ga[set],
+                                                                    tt.list, tt.count, e->pose_adj, nullptr, nullptr,
+                                                                    nullptr, nullptr, nullptr, nullptr));
+  KL(KID_P2G_ADJ, k_p2g_adj<<<nb, 128, 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]));
   LAUNCH_CHECK();
   e->bwd_cur ^= 1;
-  e->last_substep_slot = (int)(&s - e->slot.data());
-  e->last_substep_j = j;
-  e->last_was_backward = true;
   return 0;
 }
-
-static int ensure_step_frames(dsk_engine* e, int step, StepSlot** out) {
-  StepSlot& s = e->slot[step % e->slots];
-  if (s.src_step != step) {
-    // per-step checkpointing: recompute the substep frames of this step from its checkpoint
-    StepSlot* sp;
-    if (begin_step(e, step, step, &sp)) return -1;
-    for (int j = 0; j < e->S; j++)
-      if (run_substep(e, *sp, j, true)) return -1;
-    sp->src_step = step;
-  }
-  *out = &s;
-  return 0;
-}
-
-static int begin_backward(dsk_engine* e, int step, StepSlot** out) {
-  SimConst& k = e->k;
-  StepSlot* s;
-  if (ensure_step_frames(e, step, &s)) return -1;
-  int nb = cdiv(k.stride, 256);
-  e->bwd_cur = 0;
-  k_gather_sorted<<<nb, 256, 0, e->stream>>>(k, e->frame_of(e->adj_ckpt, step + 1), e->npart, s->perm, e->adjw[0]);
-  e->launches += 1;
-  LAUNCH_CHECK();
-  if (e->K > 0) {
-    CK(cudaMemsetAsync(e->pose_adj, 0, (size_t)(e->S + 1) * e->tool_floats * 4, e->stream));
-    CK(cudaMemcpy2DAsync(e->pose_adj + (size_t)e->S * e->K * 8, (size_t)(e->S + 1) * e->K * 8 * 4,
-                         e->tools_of(e->tool_adj_ckpt, step + 1), (size_t)e->K * 8 * 4, (size_t)e->K * 8 * 4, e->B,
-                         cudaMemcpyDeviceToDevice, e->stream));
-  }
-  *out = s;
-  return 0;
-}
-
-static int end_backward(dsk_engine* e, StepSlot& s, int step) {
+static int seq_end_backward(dsk_engine* e, StepSlot& s) {
   SimConst& k = e->k;
   if (e->K > 0) {
     size_t sh = (size_t)(e->S + 1) * e->K * 8 * 4;
-    const float* act = e->A > 0 ? e->actions + (size_t)step * e->B * e->A : nullptr;
-    float* ag = e->A > 0 ? e->action_grad + (size_t)step * e->B * e->A : nullptr;
-    k_kinematics_adj<<<e->B, 32, sh, e->stream>>>(k, e->d_tools, s.poses, s.cidx, e->rand_num, act, e->pose_adj, ag);
-    e->launches += 1;
-    LAUNCH_CHECK();
-    // tool_adj_ckpt[step] += pose_adj[:, 0]
-    CK(cudaMemcpy2DAsync(e->stage, (size_t)e->K * 8 * 4, e->pose_adj, (size_t)(e->S + 1) * e->K * 8 * 4,
-                         (size_t)e->K * 8 * 4, e->B, cudaMemcpyDeviceToDevice, e->stream));
-    k_axpy<<<cdiv((int)e->tool_floats, 256), 256, 0, e->stream>>>(e->tools_of(e->tool_adj_ckpt, step), e->stage,
-                                                                  (size_t)e->B * e->K * 8);
-    e->launches += 1;
+    KL(KID_KINEMATICS_ADJ, k_kinematics_adj<<<e->B, 32, sh, e->qs>>>(k, e->d_tools, s.poses, s.cidx, e->rand_num, e->d_args, e->pose_adj));
+    KL(KID_IO, k_tool_adj_accum<<<cdiv(e->B * e->K * 8, 128), 128, 0, e->qs>>>(k, e->pose_adj, e->d_args));
   }
-  int nb = cdiv(k.stride, 256);
-  k_unsort<<<nb, 256, 0, e->stream>>>(k, e->adjw[e->bwd_cur], e->npart, s.perm, e->frame_of(e->adj_ckpt, step), 1);
-  e->launches += 1;
+  KL(KID_REORDER, k_unsort<<<cdiv(k.stride, 256), 256, 0, e->qs>>>(k, e->adjw[e->bwd_cur], e->npart, s.perm, &e->d_args->adj_out, 1));
   LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- whole sequences, eager or as a replayed graph ---------------------------------------------------------------
+enum SeqKind { SEQ_FWD, SEQ_RECOMPUTE, SEQ_BWD };
+static int enqueue_sequence(dsk_engine* e, StepSlot& s, SeqKind kind) {
+  if (kind == SEQ_BWD) {
+    if (seq_begin_backward(e, s)) return -1;
+    for (int q = 0; q < e->S; q++)
+      if (seq_substep_grad(e, s, q, e->S - 1 - q)) return -1;
+    if (seq_end_backward(e, s)) return -1;
+    return seq_clear(e, e->S - 1, true);
+  }
+  if (seq_begin_forward(e, s)) return -1;
+  for (int q = 0; q < e->S; q++)
+    if (seq_substep(e, s, q, q, true)) return -1;
+  if (seq_end_forward(e, s, kind == SEQ_FWD)) return -1;
+  return seq_clear(e, e->S - 1, false);
+}
+static int run_sequence(dsk_engine* e, int slot_idx, SeqKind kind) {
+  StepSlot& s = e->slot[slot_idx];
+  if (flush_pending_clear(e)) return -1;
+  e->grids_valid = false;
+  if (e->profiling || !e->use_graphs) {
+    e->qs = e->stream;
+    return enqueue_sequence(e, s, kind);
+  }
+  dsk_engine::GraphSet& g = e->graphs[slot_idx];
+  cudaGraphExec_t* ex = kind == SEQ_FWD ? &g.fwd : (kind == SEQ_RECOMPUTE ? &g.recompute : &g.bwd);
+  if (!*ex) {
+    int64_t l0 = e->launches;
+    int64_t kl0[KID_COUNT];
+    memcpy(kl0, e->kid_launches, sizeof kl0);
+    CK(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+    e->qs = e->cap_stream;
+    int rc = enqueue_sequence(e, s, kind);
+    e->qs = e->stream;
+    cudaGraph_t graph = nullptr;
+    cudaError_t err = cudaStreamEndCapture(e->cap_stream, &graph);
+    if (rc) {
+      if (graph) cudaGraphDestroy(graph);
+      return -1;
+    }
+    if (err != cudaSuccess) return fail("cudaStreamEndCapture: %s", cudaGetErrorString(err));
+    err = cudaGraphInstantiate(ex, graph, 0);
+    cudaGraphDestroy(graph);
+    if (err != cudaSuccess) return fail("cudaGraphInstantiate: %s", cudaGetErrorString(err));
+    // launches counted during capture are the per-replay launch counts of this graph
+    int idx = (int)kind;
+    g.n_launch[idx] = e->launches - l0;
+    for (int i = 0; i < KID_COUNT; i++) g.kid[idx][i] = e->kid_launches[i] - kl0[i];
+    e->launches = l0;
+    memcpy(e->kid_launches, kl0, sizeof kl0);
+  }
+  CK(cudaGraphLaunch(*ex, e->stream));
+  int idx = (int)kind;
+  e->launches += g.n_launch[idx];
+  for (int i = 0; i < KID_COUNT; i++) e->kid_launches[i] += g.kid[idx][i];
   return 0;
 }
 
@@ -516,9 +650,8 @@ int dsk_set_particles(dsk_engine* e, int step, int env, int n, const float* x, c
   o += (size_t)n * 9;
   if (stage_in(e, C, (size_t)n * 9, on_device, o, &dC)) return -1;
   if (n > 0) {
-    k_particles_io<<<cdiv(n, 256), 256, 0, e->stream>>>(e->k, e->frame_of(e->ckpt, step), env, n, (float*)dx, (float*)dv,
-                                                        (float*)dF, (float*)dC, 0);
-    e->launches += 1;
+    KL(KID_IO, k_particles_io<<<cdiv(n, 256), 256, 0, e->stream>>>(e->k, e->frame_of(e->ckpt, step), env, n, (float*)dx, (float*)dv,
+                                                        (float*)dF, (float*)dC, 0));
     LAUNCH_CHECK();
   }
   e->h_npart[env] = n;
@@ -542,8 +675,7 @@ static int get_frame_aos(dsk_engine* e, float* frame, int env, float* x, float* 
     o += (size_t)n * 9;
     dC = C ? e->stage + o : nullptr;
   }
-  k_particles_io<<<cdiv(n, 256), 256, 0, e->stream>>>(e->k, frame, env, n, dx, dv, dF, dC, 1);
-  e->launches += 1;
+  KL(KID_IO, k_particles_io<<<cdiv(n, 256), 256, 0, e->stream>>>(e->k, frame, env, n, dx, dv, dF, dC, 1));
   LAUNCH_CHECK();
   if (!on_device) {
     if (x) CK(cudaMemcpyAsync(x, dx, (size_t)n * 12, cudaMemcpyDeviceToHost, e->stream));
@@ -607,7 +739,7 @@ int dsk_set_material(dsk_engine* e, int env, const float* mu, const float* lam, 
       CK(cudaMemcpyAsync(e->mat + (size_t)c * e->k.stride + (size_t)env * e->Npad, src[c], (size_t)n * 4,
                          cudaMemcpyHostToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
-  for (auto& s : e->slot) s.src_step = -1;
+  invalidate_all(e);
   return 0;
 }
 int dsk_set_tool_param(dsk_engine* e, int tool, int which, double value) {
@@ -647,7 +779,9 @@ int dsk_set_gravity(dsk_engine* e, const double* g) {
     e->k.grav[d] = t * 30.f;
     e->cfg.gravity[d] = g[d];
   }
-  for (auto& s : e->slot) s.src_step = -1;
+  invalidate_all(e);
+  CK(cudaStreamSynchronize(e->stream));
+  drop_graphs(e);  // SimConst is baked into the captured kernel parameters
   return 0;
 }
 
@@ -659,8 +793,7 @@ int dsk_set_action(dsk_engine* e, int step, const float* actions, int on_device)
   const float* src;
   int n = e->B * e->A;
   if (stage_in(e, actions, n, on_device, 0, &src)) return -1;
-  k_clip_actions<<<cdiv(n, 256), 256, 0, e->stream>>>(e->actions + (size_t)step * n, src, n);
-  e->launches += 1;
+  KL(KID_IO, k_clip_actions<<<cdiv(n, 256), 256, 0, e->stream>>>(e->actions + (size_t)step * n, src, n));
   LAUNCH_CHECK();
   if (!on_device) CK(cudaStreamSynchronize(e->stream));  // the staging buffer may be reused by the next call
   for (auto& s : e->slot)
@@ -671,40 +804,66 @@ int dsk_forward_step(dsk_engine* e, int src_step, int dst_step, int action_step)
   CKE(e);
   if (check_step(e, src_step, "dsk_forward_step") || check_step(e, dst_step, "dsk_forward_step")) return -1;
   if (action_step >= e->H) return fail("action step %d outside [0,%d)", action_step, e->H);
-  StepSlot* s;
-  if (begin_step(e, src_step, action_step, &s)) return -1;
-  for (int j = 0; j < e->S; j++)
-    if (run_substep(e, *s, j, true)) return -1;
-  if (end_step(e, *s, src_step, dst_step)) return -1;
-  if (action_step != src_step) s->src_step = -1;  // backward_step(step) assumes action_step == step
+  int si = src_step % e->slots;
+  StepSlot& s = e->slot[si];
+  if (push_args(e, make_args(e, src_step, dst_step, action_step, -1))) return -1;
+  s.src_step = -1;
+  s.action_step = action_step;
+  if (run_sequence(e, si, SEQ_FWD)) return -1;
+  invalidate_slots(e, dst_step);
+  // the slot's substep frames can serve backward_step(src_step) iff the step was (src, src+?, src) shaped
+  s.src_step = (dst_step != src_step && action_step == src_step) ? src_step : -1;
   e->last_fwd_frame = -1;
+  e->last_substep_slot = si;
   return 0;
 }
 int dsk_backward_step(dsk_engine* e, int step) {
   CKE(e);
   if (step < 0 || step >= e->H) return fail("dsk_backward_step: step %d outside [0,%d)", step, e->H);
-  StepSlot* s;
-  if (begin_backward(e, step, &s)) return -1;
-  for (int j = e->S - 1; j >= 0; j--)
-    if (run_substep_grad(e, *s, j)) return -1;
-  if (end_backward(e, *s, step)) return -1;
+  int si = step % e->slots;
+  StepSlot& s = e->slot[si];
+  if (s.src_step != step) {
+    // per-step checkpointing: recompute the substep frames of this step from its checkpoint
+    if (push_args(e, make_args(e, step, step, step, -1))) return -1;
+    s.action_step = step;
+    if (run_sequence(e, si, SEQ_RECOMPUTE)) return -1;
+    s.src_step = step;
+  }
+  if (push_args(e, make_args(e, step, step, step, step))) return -1;
+  if (run_sequence(e, si, SEQ_BWD)) return -1;
   e->last_bwd_frame = -1;
+  e->last_substep_slot = si;
   return 0;
 }
 int dsk_substep(dsk_engine* e, int f) {
   CKE(e);
   if (f < 0 || f >= e->H * e->S) return fail("dsk_substep: frame %d outside the horizon (%d steps x %d substeps)", f, e->H, e->S);
   int step = f / e->S, j = f % e->S;
-  StepSlot* s = &e->slot[step % e->slots];
+  int si = step % e->slots;
+  StepSlot& s = e->slot[si];
+  e->qs = e->stream;
+  if (flush_pending_clear(e)) return -1;
   if (j == 0) {
-    if (begin_step(e, step, step, &s)) return -1;
+    if (push_args(e, make_args(e, step, step + 1, step, -1))) return -1;
+    s.src_step = -1;
+    s.action_step = step;
+    if (seq_begin_forward(e, s)) return -1;
   } else if (e->last_fwd_frame != f - 1) {
     return fail("dsk_substep(%d): substeps of a step must run in ascending order starting at a step boundary (last was %d)", f, e->last_fwd_frame);
   }
-  if (run_substep(e, *s, j, true)) return -1;
+  // every fine-grained substep is its own one-substep sequence (q = 0) so its grids stay inspectable
+  if (seq_substep(e, s, 0, j, true)) return -1;
+  e->pending_q = 0;
+  e->pending_bwd = false;
+  e->grids_valid = true;
+  e->last_was_backward = false;
+  e->last_substep_slot = si;
+  e->last_substep_j = j;
   e->last_fwd_frame = f;
   if (j == e->S - 1) {
-    if (end_step(e, *s, step, step + 1)) return -1;
+    if (seq_end_forward(e, s, true)) return -1;
+    invalidate_slots(e, step + 1);
+    s.src_step = step;
   }
   return 0;
 }
@@ -712,16 +871,35 @@ int dsk_substep_grad(dsk_engine* e, int f) {
   CKE(e);
   if (f < 0 || f >= e->H * e->S) return fail("dsk_substep_grad: frame %d outside the horizon", f);
   int step = f / e->S, j = f % e->S;
-  StepSlot* s = &e->slot[step % e->slots];
+  int si = step % e->slots;
+  StepSlot& s = e->slot[si];
+  e->qs = e->stream;
   if (j == e->S - 1) {
-    if (begin_backward(e, step, &s)) return -1;
+    if (s.src_step != step) {
+      if (push_args(e, make_args(e, step, step, step, -1))) return -1;
+      s.action_step = step;
+      if (run_sequence(e, si, SEQ_RECOMPUTE)) return -1;
+      s.src_step = step;
+    }
+    if (flush_pending_clear(e)) return -1;
+    if (push_args(e, make_args(e, step, step, step, step))) return -1;
+    e->qs = e->stream;
+    if (seq_begin_backward(e, s)) return -1;
   } else if (e->last_bwd_frame != f + 1) {
     return fail("dsk_substep_grad(%d): adjoint substeps of a step must run in descending order from the step's last substep (last was %d)", f, e->last_bwd_frame);
+  } else if (flush_pending_clear(e)) {
+    return -1;
   }
-  if (run_substep_grad(e, *s, j)) return -1;
+  if (seq_substep_grad(e, s, 0, j)) return -1;
+  e->pending_q = 0;
+  e->pending_bwd = true;
+  e->grids_valid = true;
+  e->last_was_backward = true;
+  e->last_substep_slot = si;
+  e->last_substep_j = j;
   e->last_bwd_frame = f;
   if (j == 0) {
-    if (end_backward(e, *s, step)) return -1;
+    if (seq_end_backward(e, s)) return -1;
   }
   return 0;
 }
@@ -749,9 +927,8 @@ int dsk_add_particle_grad(dsk_engine* e, int step, const float* gx, const float*
   if (stage_in(e, gF, n9, on_device, o, &dF)) return -1;
   o += gF ? n9 : 0;
   if (stage_in(e, gC, n9, on_device, o, &dC)) return -1;
-  k_add_particle_grad<<<cdiv(e->k.stride, 256), 256, 0, e->stream>>>(e->k, e->frame_of(e->adj_ckpt, step), e->npart, cap,
-                                                                     dx, dv, dF, dC);
-  e->launches += 1;
+  KL(KID_IO, k_add_particle_grad<<<cdiv(e->k.stride, 256), 256, 0, e->stream>>>(e->k, e->frame_of(e->adj_ckpt, step), e->npart, cap,
+                                                                     dx, dv, dF, dC));
   LAUNCH_CHECK();
   if (!on_device) CK(cudaStreamSynchronize(e->stream));
   return 0;
@@ -762,8 +939,7 @@ int dsk_add_tool_grad(dsk_engine* e, int step, const float* g, int on_device) {
   if (e->K == 0) return 0;
   const float* d;
   if (stage_in(e, g, e->tool_floats, on_device, 0, &d)) return -1;
-  k_axpy<<<cdiv((int)e->tool_floats, 256), 256, 0, e->stream>>>(e->tools_of(e->tool_adj_ckpt, step), d, e->tool_floats);
-  e->launches += 1;
+  KL(KID_IO, k_axpy<<<cdiv((int)e->tool_floats, 256), 256, 0, e->stream>>>(e->tools_of(e->tool_adj_ckpt, step), d, e->tool_floats));
   LAUNCH_CHECK();
   if (!on_device) CK(cudaStreamSynchronize(e->stream));
   return 0;
@@ -786,7 +962,7 @@ int dsk_get_tool_grad(dsk_engine* e, int step, int env, int tool, float* g8) {
 int dsk_scale_grad(dsk_engine* e, int step, double alpha) {
   CKE(e);
   if (check_step(e, step, "dsk_scale_grad")) return -1;
-  k_scale<<<cdiv((int)e->frame_floats, 256), 256, 0, e->stream>>>(e->frame_of(e->adj_ckpt, step), e->frame_floats, (float)alpha);
+  KL(KID_IO, k_scale<<<cdiv((int)e->frame_floats, 256), 256, 0, e->stream>>>(e->frame_of(e->adj_ckpt, step), e->frame_floats, (float)alpha));
   // decay_kernel scales position.grad and rotation.grad (function.py:74-77); gap.grad is left alone
   if (e->K > 0) {
     std::vector<float> h(e->tool_floats);
@@ -797,7 +973,6 @@ int dsk_scale_grad(dsk_engine* e, int step, double alpha) {
     CK(cudaMemcpyAsync(e->tools_of(e->tool_adj_ckpt, step), h.data(), e->tool_floats * 4, cudaMemcpyHostToDevice, e->stream));
     CK(cudaStreamSynchronize(e->stream));
   }
-  e->launches += 1;
   LAUNCH_CHECK();
   return 0;
 }
@@ -811,6 +986,17 @@ int dsk_get_action_grad(dsk_engine* e, int step, float* out, int on_device) {
   return 0;
 }
 
+// action gradients of steps [step0, step0+nsteps): [nsteps, n_envs, action_dim] in one copy
+int dsk_get_action_grads(dsk_engine* e, int step0, int nsteps, float* out, int on_device) {
+  CKE(e);
+  if (step0 < 0 || nsteps < 0 || step0 + nsteps > e->H) return fail("dsk_get_action_grads: [%d,%d) outside [0,%d)", step0, step0 + nsteps, e->H);
+  if (e->A == 0 || nsteps == 0) return 0;
+  size_t n = (size_t)e->B * e->A;
+  CK(cudaMemcpyAsync(out, e->action_grad + (size_t)step0 * n, n * nsteps * 4, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
+  if (!on_device) CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
 // ---- observations ----------------------------------------------------------------------------------------
 int dsk_get_obs(dsk_engine* e, int step, float* xv, float* tools, int on_device) {
   CKE(e);
@@ -819,8 +1005,7 @@ int dsk_get_obs(dsk_engine* e, int step, float* xv, float* tools, int on_device)
   size_t n = (size_t)e->B * cap * 6;
   if (xv) {
     float* d = on_device ? xv : e->stage;
-    k_get_obs<<<cdiv(e->k.stride, 256), 256, 0, e->stream>>>(e->k, e->frame_of(e->ckpt, step), e->npart, cap, d);
-    e->launches += 1;
+    KL(KID_IO, k_get_obs<<<cdiv(e->k.stride, 256), 256, 0, e->stream>>>(e->k, e->frame_of(e->ckpt, step), e->npart, cap, d));
     LAUNCH_CHECK();
     if (!on_device) CK(cudaMemcpyAsync(xv, d, n * 4, cudaMemcpyDeviceToHost, e->stream));
   }
@@ -843,9 +1028,8 @@ int dsk_compute_min_dist(dsk_engine* e, int step, float* out, int on_device) {
   size_t n = (size_t)e->B * cap * e->ncols;
   if (!on_device && n > e->stage_floats) return fail("staging buffer too small");
   float* d = on_device ? out : e->stage;
-  k_min_dist<<<cdiv(e->k.stride, 128), 128, 0, e->stream>>>(e->k, e->d_tools, e->frame_of(e->ckpt, step), e->npart,
-                                                           e->tools_of(e->tool_ckpt, step), cap, e->ncols, d);
-  e->launches += 1;
+  KL(KID_IO, k_min_dist<<<cdiv(e->k.stride, 128), 128, 0, e->stream>>>(e->k, e->d_tools, e->frame_of(e->ckpt, step), e->npart,
+                                                           e->tools_of(e->tool_ckpt, step), cap, e->ncols, d));
   LAUNCH_CHECK();
   if (!on_device) {
     CK(cudaMemcpyAsync(out, d, n * 4, cudaMemcpyDeviceToHost, e->stream));
@@ -860,11 +1044,10 @@ int dsk_compute_min_dist_grad(dsk_engine* e, int step, const float* g, int on_de
   int cap = e->cfg.particle_capacity;
   const float* d;
   if (stage_in(e, g, (size_t)e->B * cap * e->ncols, on_device, 0, &d)) return -1;
-  k_min_dist_adj<<<cdiv(e->k.stride, 128), 128, 0, e->stream>>>(e->k, e->d_tools, e->frame_of(e->ckpt, step), e->npart,
+  KL(KID_IO, k_min_dist_adj<<<cdiv(e->k.stride, 128), 128, 0, e->stream>>>(e->k, e->d_tools, e->frame_of(e->ckpt, step), e->npart,
                                                                e->tools_of(e->tool_ckpt, step), cap, e->ncols, d,
                                                                e->frame_of(e->adj_ckpt, step),
-                                                               e->tools_of(e->tool_adj_ckpt, step));
-  e->launches += 1;
+                                                               e->tools_of(e->tool_adj_ckpt, step)));
   LAUNCH_CHECK();
   if (!on_device) CK(cudaStreamSynchronize(e->stream));
   return 0;
@@ -875,8 +1058,7 @@ int dsk_compute_grid_m(dsk_engine* e, int step, float* out, int on_device) {
   size_t n = (size_t)e->B * e->k.nnode;
   float* d = on_device ? out : e->stage;
   CK(cudaMemsetAsync(d, 0, n * 4, e->stream));
-  k_grid_m<<<cdiv(e->k.stride, 128), 128, 0, e->stream>>>(e->k, e->frame_of(e->ckpt, step), e->npart, d);
-  e->launches += 1;
+  KL(KID_IO, k_grid_m<<<cdiv(e->k.stride, 128), 128, 0, e->stream>>>(e->k, e->frame_of(e->ckpt, step), e->npart, d));
   LAUNCH_CHECK();
   if (!on_device) {
     CK(cudaMemcpyAsync(out, d, n * 4, cudaMemcpyDeviceToHost, e->stream));
@@ -889,9 +1071,8 @@ int dsk_compute_grid_m_grad(dsk_engine* e, int step, const float* gm, int on_dev
   if (check_step(e, step, "dsk_compute_grid_m_grad")) return -1;
   const float* d;
   if (stage_in(e, gm, (size_t)e->B * e->k.nnode, on_device, 0, &d)) return -1;
-  k_grid_m_adj<<<cdiv(e->k.stride, 128), 128, 0, e->stream>>>(e->k, e->frame_of(e->ckpt, step), e->npart, d,
-                                                             e->frame_of(e->adj_ckpt, step));
-  e->launches += 1;
+  KL(KID_IO, k_grid_m_adj<<<cdiv(e->k.stride, 128), 128, 0, e->stream>>>(e->k, e->frame_of(e->ckpt, step), e->npart, d,
+                                                             e->frame_of(e->adj_ckpt, step)));
   LAUNCH_CHECK();
   if (!on_device) CK(cudaStreamSynchronize(e->stream));
   return 0;
@@ -943,8 +1124,7 @@ int dsk_debug_cell_index(dsk_engine* e, int step, int env, int32_t* base, int32_
   int n = e->h_npart[env];
   if (!n) return 0;
   int* d = (int*)e->stage;
-  k_debug_cells<<<cdiv(n, 256), 256, 0, e->stream>>>(e->k, e->frame_of(e->ckpt, step), env, n, d, d + (size_t)n * 3);
-  e->launches += 1;
+  KL(KID_IO, k_debug_cells<<<cdiv(n, 256), 256, 0, e->stream>>>(e->k, e->frame_of(e->ckpt, step), env, n, d, d + (size_t)n * 3));
   LAUNCH_CHECK();
   if (base) CK(cudaMemcpyAsync(base, d, (size_t)n * 12, cudaMemcpyDeviceToHost, e->stream));
   if (key) CK(cudaMemcpyAsync(key, d + (size_t)n * 3, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
@@ -965,9 +1145,8 @@ static int grid_out(dsk_engine* e, const float4* G, int env, float* v3, float* m
   SimConst& k = e->k;
   float* dv = e->stage;
   float* dm = e->stage + (size_t)k.nnode * 3;
-  k_grid_to_dense<<<cdiv(k.nnode, 256), 256, 0, e->stream>>>(k, G, env, v3 ? dv : nullptr, m ? dm : nullptr, nullptr,
-                                                             nullptr, 0);
-  e->launches += 1;
+  KL(KID_IO, k_grid_to_dense<<<cdiv(k.nnode, 256), 256, 0, e->stream>>>(k, G, env, v3 ? dv : nullptr, m ? dm : nullptr, nullptr,
+                                                             nullptr, 0));
   LAUNCH_CHECK();
   if (v3) CK(cudaMemcpyAsync(v3, dv, (size_t)k.nnode * 12, cudaMemcpyDeviceToHost, e->stream));
   if (m) CK(cudaMemcpyAsync(m, dm, (size_t)k.nnode * 4, cudaMemcpyDeviceToHost, e->stream));
@@ -977,8 +1156,9 @@ static int grid_out(dsk_engine* e, const float4* G, int env, float* v3, float* m
 int dsk_debug_grid(dsk_engine* e, int env, float* v_in, float* v_out, float* m, uint8_t* occupied) {
   CKE(e);
   if (env < 0 || env >= e->B) return fail("env %d outside [0,%d)", env, e->B);
-  if (e->last_substep_slot < 0) return fail("no substep has run yet");
-  int set = e->epoch & 1;
+  if (!e->grids_valid)
+    return fail("grids are only inspectable right after dsk_substep / dsk_substep_grad (whole-step calls clear them)");
+  int set = (e->pending_q + 1) & 1;
   if (e->last_was_backward) {
     if (grid_out(e, e->G0[set], env, v_in, m)) return -1;
     if (v_out && grid_out(e, e->Gv[set], env, v_out, nullptr)) return -1;
@@ -993,9 +1173,8 @@ int dsk_debug_grid(dsk_engine* e, int env, float* v_in, float* v_out, float* m, 
     CK(cudaMemsetAsync(d, 0, k.nnode, e->stream));
     StepSlot& s = e->slot[e->last_substep_slot];
     if (n)
-      k_debug_occupancy<<<cdiv(n, 256), 256, 0, e->stream>>>(k, s.frames + (size_t)e->last_substep_j * e->frame_floats,
-                                                             nullptr, env, n, d);
-    e->launches += 1;
+      KL(KID_IO, k_debug_occupancy<<<cdiv(n, 256), 256, 0, e->stream>>>(k, s.frames + (size_t)e->last_substep_j * e->frame_floats,
+                                                             nullptr, env, n, d));
     LAUNCH_CHECK();
     CK(cudaMemcpyAsync(occupied, d, k.nnode, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -1005,31 +1184,28 @@ int dsk_debug_grid(dsk_engine* e, int env, float* v_in, float* v_out, float* m, 
 int dsk_debug_grid_grad(dsk_engine* e, int env, float* g_v_in, float* g_v_out, float* g_m) {
   CKE(e);
   if (env < 0 || env >= e->B) return fail("env %d outside [0,%d)", env, e->B);
-  if (!e->last_was_backward) return fail("grid adjoints exist only after dsk_substep_grad");
+  if (!e->grids_valid || !e->last_was_backward) return fail("grid adjoints exist only right after dsk_substep_grad");
   if (g_v_out) return fail("the adjoint of grid_v_out is overwritten in place by k_grid_adj");
-  return grid_out(e, e->Ga[e->epoch & 1], env, g_v_in, g_m);
+  return grid_out(e, e->Ga[(e->pending_q + 1) & 1], env, g_v_in, g_m);
 }
 int dsk_debug_frame(dsk_engine* e, int f, int env, float* x, float* v, float* F, float* C) {
   CKE(e);
   if (env < 0 || env >= e->B) return fail("env %d outside [0,%d)", env, e->B);
+  if (f < 0 || f > e->H * e->S) return fail("frame %d outside the horizon", f);
   int step = f / e->S, j = f % e->S;
+  if (j == 0) return dsk_get_particles(e, step, env, x, v, F, C, 0);
   StepSlot* s = &e->slot[step % e->slots];
-  if (s->src_step != step && !(e->last_substep_slot == step % e->slots)) {
-    if (j == 0 && step <= e->H) return dsk_get_particles(e, step, env, x, v, F, C, 0);
-    if (step >= 1) {  // frame S of the previous step
-      s = &e->slot[(step - 1) % e->slots];
-      if (j == 0 && s->src_step == step - 1) j = e->S;
-      else return fail("frame %d is not resident in the step-slot ring", f);
-    } else {
-      return fail("frame %d is not resident in the step-slot ring", f);
-    }
-  }
-  // un-sort into the staging area, then reuse the AoS reader
+  if (s->src_step != step && !(e->last_substep_slot == step % e->slots && e->last_fwd_frame >= f - 1 && e->last_fwd_frame / e->S == step))
+    return fail("frame %d is not resident in the step-slot ring", f);
+  // un-sort into a scratch frame (rewritten by the next adjoint substep anyway), then reuse the AoS reader
   SimConst& k = e->k;
-  float* tmp = e->adjw[e->bwd_cur ^ 1];  // scratch frame (overwritten by the next adjoint substep anyway)
-  k_unsort<<<cdiv(k.stride, 256), 256, 0, e->stream>>>(k, s->frames + (size_t)j * e->frame_floats, e->npart, s->perm, tmp, 0);
-  e->launches += 1;
+  float* tmp = e->adjw[e->bwd_cur ^ 1];
+  float** dptr = (float**)e->stage;  // device slot holding the destination pointer
+  CK(cudaMemcpyAsync(dptr, &tmp, sizeof(float*), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  KL(KID_IO, k_unsort<<<cdiv(k.stride, 256), 256, 0, e->stream>>>(k, s->frames + (size_t)j * e->frame_floats, e->npart, s->perm, dptr, 0));
   LAUNCH_CHECK();
+  CK(cudaStreamSynchronize(e->stream));
   return get_frame_aos(e, tmp, env, x, v, F, C, 0);
 }
 int dsk_debug_tool_frame(dsk_engine* e, int f, int env, int tool, float* st, int32_t* cidx) {
@@ -1063,13 +1239,81 @@ int dsk_debug_svd(dsk_engine* e, int n, const float* F, float* U, float* sig, fl
   if ((size_t)n * 30 > e->stage_floats) return fail("too many matrices for the staging buffer");
   float* d = e->stage;
   CK(cudaMemcpyAsync(d, F, (size_t)n * 36, cudaMemcpyHostToDevice, e->stream));
-  k_svd_probe<<<cdiv(n, 128), 128, 0, e->stream>>>(n, d, d + (size_t)n * 9, d + (size_t)n * 18, d + (size_t)n * 21);
-  e->launches += 1;
+  KL(KID_IO, k_svd_probe<<<cdiv(n, 128), 128, 0, e->stream>>>(n, d, d + (size_t)n * 9, d + (size_t)n * 18, d + (size_t)n * 21));
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(U, d + (size_t)n * 9, (size_t)n * 36, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaMemcpyAsync(sig, d + (size_t)n * 18, (size_t)n * 12, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaMemcpyAsync(V, d + (size_t)n * 21, (size_t)n * 36, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+// ---- measurement helpers ------------------------------------------------------------------------------------
+int dsk_set_graphs(dsk_engine* e, int on) {
+  CKE(e);
+  e->use_graphs = on != 0;
+  return 0;
+}
+int dsk_profile_enable(dsk_engine* e, int on) {
+  CKE(e);
+  CK(cudaStreamSynchronize(e->stream));
+  e->profiling = on != 0;
+  return 0;
+}
+int dsk_kernel_class_count(void) { return KID_COUNT; }
+const char* dsk_kernel_class_name(int i) { return (i >= 0 && i < KID_COUNT) ? kKernelNames[i] : ""; }
+int dsk_profile_report(dsk_engine* e, double* ms, int64_t* launches, int n, int reset) {
+  CKE(e);
+  CK(cudaStreamSynchronize(e->stream));
+  for (int i = 0; i < n; i++) {
+    if (ms) ms[i] = 0.0;
+    if (launches) launches[i] = 0;
+  }
+  for (auto& r : e->prof) {
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, r.a, r.b));
+    if (r.kid < n) {
+      if (ms) ms[r.kid] += t;
+      if (launches) launches[r.kid] += 1;
+    }
+  }
+  if (reset) {
+    for (auto& r : e->prof) {
+      e->ev_pool.push_back(r.a);
+      e->ev_pool.push_back(r.b);
+    }
+    e->prof.clear();
+  }
+  return 0;
+}
+int dsk_launch_counts(dsk_engine* e, int64_t* per_class, int n) {
+  if (!e) return fail("null engine");
+  for (int i = 0; i < n && i < KID_COUNT; i++) per_class[i] = e->kid_launches[i];
+  return 0;
+}
+// deterministic stand-in for the reference's torch-side losses (taichi_env.py:246-275 needs geomloss):
+// loss[env] += weight * mean_p |x_p - target_p|^2 at checkpoint `step`, gradient += into the adjoint checkpoint
+int dsk_loss_reset(dsk_engine* e) {
+  CKE(e);
+  CK(cudaMemsetAsync(e->loss, 0, (size_t)e->B * 4, e->stream));
+  return 0;
+}
+int dsk_loss_add_l2(dsk_engine* e, int step, const float* target, double weight, int on_device) {
+  CKE(e);
+  if (check_step(e, step, "dsk_loss_add_l2")) return -1;
+  int cap = e->cfg.particle_capacity;
+  const float* d;
+  if (stage_in(e, target, (size_t)e->B * cap * 3, on_device, 0, &d)) return -1;
+  KL(KID_LOSS, k_loss_l2<<<cdiv(e->k.stride, 128), 128, 0, e->stream>>>(e->k, e->frame_of(e->ckpt, step), e->frame_of(e->adj_ckpt, step),
+                                                                        e->npart, d, cap, (float)weight, e->loss));
+  LAUNCH_CHECK();
+  if (!on_device) CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+int dsk_loss_get(dsk_engine* e, float* out, int on_device) {
+  CKE(e);
+  CK(cudaMemcpyAsync(out, e->loss, (size_t)e->B * 4, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
+  if (!on_device) CK(cudaStreamSynchronize(e->stream));
   return 0;
 }
 

@@ -11,10 +11,11 @@ DSK_DEV int cell_key(const SimConst& k, float x, float y, float z, int& bx, int&
   bspline1(z, k.inv_dx, k.n, bz, fx, w);
   return node_offset(bx, by, bz, k.nt);
 }
-__global__ void k_sort_bin(SimConst k, const float* __restrict__ ck, const int* __restrict__ npart,
+__global__ void k_sort_bin(SimConst k, const StepArgs* __restrict__ args, const int* __restrict__ npart,
                            int* __restrict__ cell_count, int* __restrict__ key, int* __restrict__ rank) {
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= k.stride) return;
+  const float* __restrict__ ck = args->ck_src;
   int env = gid / k.Npad, p = gid - env * k.Npad;
   if (p >= npart[env]) return;
   int bx, by, bz;
@@ -62,12 +63,13 @@ __global__ void __launch_bounds__(1024) k_sort_scan(SimConst k, int* __restrict_
   }
 }
 // scatter checkpoint (canonical order) -> work frame 0 (sorted order); also permutes the material arrays
-__global__ void k_sort_scatter(SimConst k, const float* __restrict__ ck, const float* __restrict__ mat,
+__global__ void k_sort_scatter(SimConst k, const StepArgs* __restrict__ args, const float* __restrict__ mat,
                                const int* __restrict__ npart, const int* __restrict__ cell_start,
                                const int* __restrict__ key, const int* __restrict__ rank, int use_sort,
                                float* __restrict__ w0, float* __restrict__ mat_sorted, int* __restrict__ perm) {
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= k.stride) return;
+  const float* __restrict__ ck = args->ck_src;
   int env = gid / k.Npad, p = gid - env * k.Npad;
   if (p >= npart[env]) return;
   int dst = use_sort ? env * k.Npad + cell_start[(size_t)env * k.nnode + key[gid]] + rank[gid] : gid;
@@ -79,9 +81,10 @@ __global__ void k_sort_scatter(SimConst k, const float* __restrict__ ck, const f
 }
 // sorted frame -> canonical checkpoint.  accumulate=1: += (adjoint checkpoints)
 __global__ void k_unsort(SimConst k, const float* __restrict__ w, const int* __restrict__ npart,
-                         const int* __restrict__ perm, float* __restrict__ ck, int accumulate) {
+                         const int* __restrict__ perm, float* const* __restrict__ pck, int accumulate) {
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= k.stride) return;
+  float* __restrict__ ck = *pck;
   int env = gid / k.Npad, d = gid - env * k.Npad;
   if (d >= npart[env]) return;
   int dst = env * k.Npad + perm[gid];
@@ -94,10 +97,11 @@ __global__ void k_unsort(SimConst k, const float* __restrict__ w, const int* __r
   }
 }
 // canonical (adjoint) checkpoint -> sorted frame
-__global__ void k_gather_sorted(SimConst k, const float* __restrict__ ck, const int* __restrict__ npart,
+__global__ void k_gather_sorted(SimConst k, float* const* __restrict__ pck, const int* __restrict__ npart,
                                 const int* __restrict__ perm, float* __restrict__ w) {
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= k.stride) return;
+  const float* __restrict__ ck = *pck;
   int env = gid / k.Npad, d = gid - env * k.Npad;
   if (d >= npart[env]) return;
   int src = env * k.Npad + perm[gid];
@@ -285,13 +289,62 @@ DSK_DEV ToolVel action_to_vel(const ToolParams& T, const float* a, int S) {  // 
   return u;
 }
 
+// tool states of the last substep frame -> destination checkpoint
+__global__ void k_tool_store(SimConst k, const float* __restrict__ poses, const StepArgs* __restrict__ args) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int per = k.K * 8;
+  if (i >= k.B * per) return;
+  int env = i / per, r = i - env * per;
+  args->tool_dst[i] = poses[((size_t)env * (k.S + 1) + k.S) * per + r];
+}
+// pose_adj[B][S+1][K][8] = 0 except frame S = adjoint checkpoint step+1
+__global__ void k_pose_adj_init(SimConst k, float* __restrict__ pose_adj, const StepArgs* __restrict__ args) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int per = k.K * 8;
+  if (i >= k.B * (k.S + 1) * per) return;
+  int env = i / ((k.S + 1) * per), r = i - env * (k.S + 1) * per;
+  int f = r / per, q = r - f * per;
+  pose_adj[i] = (f == k.S) ? args->tool_adj_in[env * per + q] : 0.f;
+}
+// adjoint checkpoint step += pose_adj frame 0
+__global__ void k_tool_adj_accum(SimConst k, const float* __restrict__ pose_adj, const StepArgs* __restrict__ args) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int per = k.K * 8;
+  if (i >= k.B * per) return;
+  int env = i / per, r = i - env * per;
+  args->tool_adj_out[i] += pose_adj[(size_t)env * (k.S + 1) * per + r];
+}
+// sum_t w * mean_p |x - target|^2 per env (a deterministic stand-in for the reference's torch-side losses) and its
+// gradient accumulated into an adjoint checkpoint.  target [B,cap,3]; loss [B] (+=)
+__global__ void k_loss_l2(SimConst k, const float* __restrict__ frame, float* __restrict__ adj,
+                          const int* __restrict__ npart, const float* __restrict__ target, int cap, float weight,
+                          float* __restrict__ loss) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  int env = gid < k.stride ? gid / k.Npad : 0, p = gid - env * k.Npad;
+  int n = npart[env];
+  float l = 0.f;
+  if (gid < k.stride && p < n && p < cap) {
+    float sc = weight / (float)n;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      float d = frame[c * k.stride + gid] - target[((size_t)env * cap + p) * 3 + c];
+      l += sc * d * d;
+      adj[c * k.stride + gid] += 2.f * sc * d;
+    }
+  }
+  l = warp_sum(l);
+  if ((threadIdx.x & 31) == 0 && l != 0.f && gid < k.stride) atomicAdd(&loss[env], l);
+}
+
 #define KIN_CTA 128
 // One CTA per env: S substeps of forward_kinematics for every tool, then (if any pair) set_surface_points,
 // set_collision_idx (deterministic first minimum) and apply_collision_projection (mpm_simulator.py:286-305).
 __global__ void __launch_bounds__(KIN_CTA)
-    k_kinematics(SimConst k, const ToolParams* __restrict__ tools, const float* __restrict__ state0 /*[B][K][8]*/,
-                 const float* __restrict__ action /*[B][A] or null*/, const float* __restrict__ rand_num,
-                 float* __restrict__ poses /*[B][S+1][K][8]*/, int* __restrict__ cidx /*[B][S+1][npairs]*/) {
+    k_kinematics(SimConst k, const ToolParams* __restrict__ tools, const StepArgs* __restrict__ args,
+                 const float* __restrict__ rand_num, float* __restrict__ poses /*[B][S+1][K][8]*/,
+                 int* __restrict__ cidx /*[B][S+1][npairs]*/) {
+  const float* __restrict__ state0 = args->tool_src;  // [B][K][8]
+  const float* __restrict__ action = args->action;    // [B][A] or null
   __shared__ ToolParams sT[DSK_MAX_TOOLS];
   __shared__ float sP[DSK_MAX_TOOLS][8];    // current poses (frame j+1 under construction)
   __shared__ float sPre[DSK_MAX_TOOLS][8];  // poses after FK, before any projection

@@ -16,14 +16,14 @@ __global__ void __launch_bounds__(128)
               const float* __restrict__ adj_in, float* __restrict__ adj_out, const int* __restrict__ npart,
               const float4* __restrict__ Gv, float4* __restrict__ Ga) {
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= k.stride) return;
-  int env = gid / k.Npad, p = gid - env * k.Npad;
-  if (p >= npart[env]) return;
-  float3 x = load_v3(fin, CX, k.stride, gid);
-  float3 xn = load_v3(fnext, CX, k.stride, gid);
-  float3 gxn = load_v3(adj_in, CX, k.stride, gid);
-  float3 gvn = load_v3(adj_in, CV, k.stride, gid);
-  M3 gC = load_m3(adj_in, CC, k.stride, gid);
+  int env = min(gid / k.Npad, k.B - 1), p = gid - env * k.Npad;
+  bool active = gid < k.stride && p < npart[env];
+  int gi = active ? gid : env * k.Npad;
+  float3 x = load_v3(fin, CX, k.stride, gi);
+  float3 xn = load_v3(fnext, CX, k.stride, gi);
+  float3 gxn = load_v3(adj_in, CX, k.stride, gi);
+  float3 gvn = load_v3(adj_in, CV, k.stride, gi);
+  M3 gC = load_m3(adj_in, CC, k.stride, gi);
   // x' = max(min(x + dt v', hi), lo): the adjoint passes iff lo < x' < hi
   float3 gt = f3((k.x_lo < xn.x && xn.x < k.x_hi) ? gxn.x : 0.f, (k.x_lo < xn.y && xn.y < k.x_hi) ? gxn.y : 0.f,
                  (k.x_lo < xn.z && xn.z < k.x_hi) ? gxn.z : 0.f);
@@ -33,6 +33,15 @@ __global__ void __launch_bounds__(128)
   make_stencil(k, x.x, x.y, x.z, s);
   const float4* Gve = Gv + (size_t)env * k.nnode;
   float4* Gae = Ga + (size_t)env * k.nnode;
+  // adjoint of grid_v_out: warp-aggregated scatter
+  TileTrack none{nullptr, nullptr, nullptr};
+  warp_scatter27(k, active, s, Gae, none, false, env, 0, [&](int i, int j, int l) {
+    float w = s.wx[i] * s.wy[j] * s.wz[l];
+    float cw = k.c_C * w;
+    float3 Cd = mv(gC, f3((float)i - s.fx, (float)j - s.fy, (float)l - s.fz));
+    return make_float4(w * gvn.x + cw * Cd.x, w * gvn.y + cw * Cd.y, w * gvn.z + cw * Cd.z, 0.f);
+  });
+  if (!active) return;
   float gwx[3] = {0, 0, 0}, gwy[3] = {0, 0, 0}, gwz[3] = {0, 0, 0};
   float3 gf = f3(0, 0, 0);  // adjoint of fx (through dpos)
 #pragma unroll
@@ -41,15 +50,13 @@ __global__ void __launch_bounds__(128)
     for (int j = 0; j < 3; j++)
 #pragma unroll
       for (int l = 0; l < 3; l++) {
-        int node = s.ox[i] + s.oy[j] + s.oz[l];
-        float4 g4 = Gve[node];
+        float4 g4 = Gve[s.ox[i] + s.oy[j] + s.oz[l]];
         float3 g = f3(g4.x, g4.y, g4.z);
         float w = s.wx[i] * s.wy[j] * s.wz[l];
         float cw = k.c_C * w;
         float3 dpos = f3((float)i - s.fx, (float)j - s.fy, (float)l - s.fz);
         float3 Cd = mv(gC, dpos);   // sum_b gC_ab dpos_b
         float3 Ctg = mTv(gC, g);    // sum_a gC_ab g_a
-        red_add4(&Gae[node], make_float4(w * gvn.x + cw * Cd.x, w * gvn.y + cw * Cd.y, w * gvn.z + cw * Cd.z, 0.f));
         float gw = dot(g, gvn) + k.c_C * dot(g, Cd);
         gf -= cw * Ctg;
         gwx[i] += gw * s.wy[j] * s.wz[l];
@@ -274,8 +281,9 @@ __global__ void __launch_bounds__(128)
 __global__ void __launch_bounds__(32)
     k_kinematics_adj(SimConst k, const ToolParams* __restrict__ tools, const float* __restrict__ poses,
                      const int* __restrict__ cidx, const float* __restrict__ rand_num,
-                     const float* __restrict__ action, float* __restrict__ pose_adj,
-                     float* __restrict__ action_grad /*[B][A] of this step, +=*/) {
+                     const StepArgs* __restrict__ args, float* __restrict__ pose_adj) {
+  const float* __restrict__ action = args->action;
+  float* __restrict__ action_grad = args->action_grad;  // [B][A] of this step, +=
   __shared__ ToolParams sT[DSK_MAX_TOOLS];
   extern __shared__ float sadj[];  // [(S+1)][K][8]
   int env = blockIdx.x, lane = threadIdx.x;

@@ -90,6 +90,23 @@ DSK_DEV void store_v3(float* __restrict__ f, int comp0, int stride, int gid, flo
 // vector reduction to global memory: one RED.E.ADD.F32x4 (sm_90+) instead of four scalar REDs
 DSK_DEV void red_add4(float4* addr, float4 v) { atomicAdd(addr, v); }
 
+// Step-dependent pointers live in device memory so that ONE captured CUDA graph per step slot can be replayed
+// for every env step: boundary kernels dereference these instead of taking the pointers as launch parameters.
+struct StepArgs {
+  float* ck_src;        // particle checkpoint the step starts from
+  float* ck_dst;        // particle checkpoint the step writes
+  float* tool_src;      // tool states [B][K][8] at the source checkpoint
+  float* tool_dst;
+  const float* action;  // clipped actions [B][A] of the step (or null)
+  float* adj_in;        // adjoint checkpoint step+1
+  float* adj_out;       // adjoint checkpoint step (accumulated into)
+  float* tool_adj_in;
+  float* tool_adj_out;
+  float* action_grad;   // [B][A] of the step (accumulated into)
+  int epoch_base;       // multiple of 4; substep q of the sequence runs as epoch epoch_base + q + 1
+};
+__global__ void k_set_args(StepArgs* dst, StepArgs v) { *dst = v; }
+
 // Per-substep sparse-grid bookkeeping: tiles touched by a stencil are appended (once) to the
 // active list of the current epoch.
 struct TileTrack {
@@ -110,4 +127,83 @@ DSK_DEV void mark_stencil_tiles(const SimConst& k, const TileTrack& t, int env, 
   for (int a = tx0; a <= tx1; a++)
     for (int b = ty0; b <= ty1; b++)
       for (int c = tz0; c <= tz1; c++) mark_tile(t, base + (a * k.nt + b) * k.nt + c, epoch);
+}
+
+
+// ---- warp-aggregated 27-node scatter ------------------------------------------------------------------------
+// Particles are sorted by cell, so the lanes of a warp fall into a few groups that share one stencil.  For each
+// group the 27 float4 contributions of every lane are summed across the warp with a recursive-halving butterfly
+// (124 shuffles instead of 27*4*5): after the five steps lane l holds the complete sum for stencil node l, and
+// lanes 0..26 issue ONE vector reduction each -- 27 RED.128 per group instead of 27 per particle.  Groups of
+// fewer than SCATTER_MIN_GROUP lanes fall back to per-lane reductions.
+#define SCATTER_MIN_GROUP 4
+DSK_DEV float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+DSK_DEV float4 f4sel(bool c, float4 a, float4 b) { return c ? a : b; }
+DSK_DEV float4 f4shfl_xor(float4 v, int m) {
+  return make_float4(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m),
+                     __shfl_xor_sync(0xffffffffu, v.z, m), __shfl_xor_sync(0xffffffffu, v.w, m));
+}
+template <int Q, class F>
+DSK_DEV float4 slot_value(bool mine, F& val) {
+  if (Q >= 27) return make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 v = val(Q / 9, (Q / 3) % 3, Q % 3);
+  return mine ? v : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+template <int Q, class F>
+DSK_DEV void butterfly_first(bool mine, bool hi, F& val, float4* acc) {
+  float4 a = slot_value<Q>(mine, val), b = slot_value<Q + 16>(mine, val);
+  acc[Q] = f4add(f4sel(hi, b, a), f4shfl_xor(f4sel(hi, a, b), 16));
+}
+// val(i,j,l) -> float4 contribution of this lane to stencil node (i,j,l); must be callable by every lane
+template <class F>
+DSK_DEV void warp_scatter27(const SimConst& k, bool active, const Stencil& s, float4* __restrict__ Ge,
+                            const TileTrack& tt, bool mark, int env, int epoch, F val) {
+  const int lane = threadIdx.x & 31;
+  int key = active ? node_offset(s.bx, s.by, s.bz, k.nt) : -1;
+  unsigned todo = __ballot_sync(0xffffffffu, active);
+  while (todo) {
+    int leader = __ffs(todo) - 1;
+    int lkey = __shfl_sync(0xffffffffu, key, leader);
+    bool mine = active && key == lkey;
+    unsigned grp = __ballot_sync(0xffffffffu, mine);
+    todo &= ~grp;
+    if (mark && lane == leader) mark_stencil_tiles(k, tt, env, s, epoch);
+    if (__popc(grp) < SCATTER_MIN_GROUP) {
+      if (mine) {
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int l = 0; l < 3; l++) red_add4(&Ge[s.ox[i] + s.oy[j] + s.oz[l]], val(i, j, l));
+      }
+      continue;
+    }
+    float4 acc[16];
+    {
+      bool hi = lane & 16;
+      butterfly_first<0>(mine, hi, val, acc);  butterfly_first<1>(mine, hi, val, acc);
+      butterfly_first<2>(mine, hi, val, acc);  butterfly_first<3>(mine, hi, val, acc);
+      butterfly_first<4>(mine, hi, val, acc);  butterfly_first<5>(mine, hi, val, acc);
+      butterfly_first<6>(mine, hi, val, acc);  butterfly_first<7>(mine, hi, val, acc);
+      butterfly_first<8>(mine, hi, val, acc);  butterfly_first<9>(mine, hi, val, acc);
+      butterfly_first<10>(mine, hi, val, acc); butterfly_first<11>(mine, hi, val, acc);
+      butterfly_first<12>(mine, hi, val, acc); butterfly_first<13>(mine, hi, val, acc);
+      butterfly_first<14>(mine, hi, val, acc); butterfly_first<15>(mine, hi, val, acc);
+    }
+#pragma unroll
+    for (int half = 8; half >= 1; half >>= 1) {
+      bool hi = lane & half;
+#pragma unroll
+      for (int q = 0; q < half; q++)
+        acc[q] = f4add(f4sel(hi, acc[q + half], acc[q]), f4shfl_xor(f4sel(hi, acc[q], acc[q + half]), half));
+    }
+    // lane l now owns stencil node l of the group's cell
+    int bx = __shfl_sync(0xffffffffu, s.bx, leader), by = __shfl_sync(0xffffffffu, s.by, leader),
+        bz = __shfl_sync(0xffffffffu, s.bz, leader);
+    if (lane < 27) {
+      int i = lane / 9, j = (lane / 3) % 3, l = lane % 3;
+      red_add4(&Ge[node_offset(bx + i, by + j, bz + l, k.nt)], acc[0]);
+    }
+  }
 }

@@ -72,35 +72,30 @@ DSK_DEV void p2g_particle(const SimConst& k, const M3& C, const M3& F, float mu,
 template <bool WRITE_F>
 __global__ void __launch_bounds__(128)
     k_p2g(SimConst k, const float* __restrict__ fin, float* __restrict__ fout, const float* __restrict__ mat,
-          const int* __restrict__ npart, float4* __restrict__ G, TileTrack tt, int epoch) {
+          const int* __restrict__ npart, float4* __restrict__ G, TileTrack tt, const StepArgs* __restrict__ args,
+          int q) {
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= k.stride) return;
-  int env = gid / k.Npad, p = gid - env * k.Npad;
-  if (p >= npart[env]) return;
-  float3 x = load_v3(fin, CX, k.stride, gid);
-  float3 v = load_v3(fin, CV, k.stride, gid);
-  M3 C = load_m3(fin, CC, k.stride, gid);
-  M3 F = load_m3(fin, CF, k.stride, gid);
-  float mu = mat[gid], lam = mat[k.stride + gid], ys = mat[2 * k.stride + gid];
+  int env = min(gid / k.Npad, k.B - 1), p = gid - env * k.Npad;   // a warp never straddles envs (Npad % 128 == 0)
+  bool active = gid < k.stride && p < npart[env];
+  int g = active ? gid : env * k.Npad;                            // inactive lanes shadow slot 0 (loads stay in bounds)
+  float3 x = load_v3(fin, CX, k.stride, g);
+  float3 v = load_v3(fin, CV, k.stride, g);
+  M3 C = load_m3(fin, CC, k.stride, g);
+  M3 F = load_m3(fin, CF, k.stride, g);
+  float mu = mat[g], lam = mat[k.stride + g], ys = mat[2 * k.stride + g];
   P2GParticle o;
   p2g_particle(k, C, F, mu, lam, ys, o);
-  if (WRITE_F) store_m3(fout, CF, k.stride, gid, o.newF);
+  if (WRITE_F && active) store_m3(fout, CF, k.stride, gid, o.newF);
   Stencil s;
   make_stencil(k, x.x, x.y, x.z, s);
-  mark_stencil_tiles(k, tt, env, s, epoch);
   float4* Ge = G + (size_t)env * k.nnode;
   float3 pmv = k.p_mass * v;
-#pragma unroll
-  for (int i = 0; i < 3; i++)
-#pragma unroll
-    for (int j = 0; j < 3; j++)
-#pragma unroll
-      for (int l = 0; l < 3; l++) {
-        float3 dpos = f3(((float)i - s.fx) * k.dx, ((float)j - s.fy) * k.dx, ((float)l - s.fz) * k.dx);
-        float w = s.wx[i] * s.wy[j] * s.wz[l];
-        float3 a = pmv + mv(o.affine, dpos);
-        red_add4(&Ge[s.ox[i] + s.oy[j] + s.oz[l]], make_float4(w * a.x, w * a.y, w * a.z, w * k.p_mass));
-      }
+  warp_scatter27(k, active, s, Ge, tt, true, env, args->epoch_base + q + 1, [&](int i, int j, int l) {
+    float3 dpos = f3(((float)i - s.fx) * k.dx, ((float)j - s.fy) * k.dx, ((float)l - s.fz) * k.dx);
+    float w = s.wx[i] * s.wy[j] * s.wz[l];
+    float3 a = pmv + mv(o.affine, dpos);
+    return make_float4(w * a.x, w * a.y, w * a.z, w * k.p_mass);
+  });
 }
 
 // ---- grid_op for one node ---------------------------------------------------------------------------
@@ -210,6 +205,22 @@ DSK_DEV void clear_tiles(const SimConst& k, const int* __restrict__ list, int co
     if (c0) c0[o] = z;
     if (c1) c1[o] = z;
     if (c2) c2[o] = z;
+  }
+}
+
+// end of a step sequence: zero the tiles of the last substep and reset the active-tile counters, so that every
+// sequence (and every replay of its CUDA graph) starts from all-zero grids
+__global__ void __launch_bounds__(GRID_CTA)
+    k_end_clear(SimConst k, const int* __restrict__ list, const int* __restrict__ count, float4* c0, float4* c1,
+                float4* c2, int* counts4, int* done) {
+  clear_tiles(k, list, *count, c0, c1, c2);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(done, 1) == (int)gridDim.x - 1) {  // last CTA: nobody reads the counters any more
+      counts4[0] = counts4[1] = counts4[2] = counts4[3] = 0;
+      *done = 0;
+    }
   }
 }
 

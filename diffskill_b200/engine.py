@@ -51,10 +51,12 @@ SYMBOLS = [
     'dsk_get_tool_state', 'dsk_copy_step', 'dsk_set_material', 'dsk_set_tool_param', 'dsk_get_tool_param',
     'dsk_set_gravity', 'dsk_set_action', 'dsk_forward_step', 'dsk_backward_step', 'dsk_substep', 'dsk_substep_grad',
     'dsk_zero_grad', 'dsk_add_particle_grad', 'dsk_add_tool_grad', 'dsk_get_particle_grad', 'dsk_get_tool_grad',
-    'dsk_scale_grad', 'dsk_get_action_grad', 'dsk_get_obs', 'dsk_min_dist_cols', 'dsk_compute_min_dist',
+    'dsk_scale_grad', 'dsk_get_action_grad', 'dsk_get_action_grads', 'dsk_get_obs', 'dsk_min_dist_cols', 'dsk_compute_min_dist',
     'dsk_compute_min_dist_grad', 'dsk_compute_grid_m', 'dsk_compute_grid_m_grad', 'dsk_debug_cell_index',
     'dsk_debug_sort_order', 'dsk_debug_grid', 'dsk_debug_grid_grad', 'dsk_debug_frame', 'dsk_debug_tool_frame',
-    'dsk_debug_tool_frame_grad', 'dsk_debug_svd', 'dsk_launch_count', 'dsk_memory_bytes',
+    'dsk_debug_tool_frame_grad', 'dsk_debug_svd', 'dsk_launch_count', 'dsk_memory_bytes', 'dsk_set_graphs',
+    'dsk_profile_enable', 'dsk_kernel_class_count', 'dsk_kernel_class_name', 'dsk_profile_report',
+    'dsk_launch_counts', 'dsk_loss_reset', 'dsk_loss_add_l2', 'dsk_loss_get',
 ]
 
 
@@ -67,6 +69,7 @@ def load_library():
                               "(or __graft_entry__.build()). There is no CPU fallback.")
         L = C.CDLL(LIB_PATH)
         L.dsk_last_error.restype = C.c_char_p
+        L.dsk_kernel_class_name.restype = C.c_char_p
         _LIB = L
     return _LIB
 
@@ -302,6 +305,14 @@ class Engine:
         self._ck(self.L.dsk_get_action_grad(self.h, step, p, dev))
         return out
 
+    def get_action_grads(self, step0=0, nsteps=None, out=None):
+        nsteps = self.H - step0 if nsteps is None else nsteps
+        if out is None:
+            out = np.zeros((nsteps, self.B, self.A), np.float32)
+        p, dev = _ptr(out)
+        self._ck(self.L.dsk_get_action_grads(self.h, step0, nsteps, p, dev))
+        return out
+
     # ---- observations --------------------------------------------------------------------------------
     def get_obs(self, step, xv=None, tools=None):
         if xv is None:
@@ -397,3 +408,41 @@ class Engine:
         n = C.c_int64()
         self._ck(self.L.dsk_memory_bytes(self.h, C.byref(n)))
         return n.value
+
+    # ---- measurement helpers -------------------------------------------------------------------------
+    def set_graphs(self, on):
+        self._ck(self.L.dsk_set_graphs(self.h, int(on)))
+
+    def profile_enable(self, on):
+        self._ck(self.L.dsk_profile_enable(self.h, int(on)))
+
+    def kernel_classes(self):
+        return [self.L.dsk_kernel_class_name(i).decode() for i in range(self.L.dsk_kernel_class_count())]
+
+    def profile_report(self, reset=True):
+        n = self.L.dsk_kernel_class_count()
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        self._ck(self.L.dsk_profile_report(self.h, ms, cnt, n, int(reset)))
+        return {name: (ms[i], cnt[i]) for i, name in enumerate(self.kernel_classes()) if cnt[i]}
+
+    def launch_counts(self):
+        n = self.L.dsk_kernel_class_count()
+        cnt = (C.c_int64 * n)()
+        self._ck(self.L.dsk_launch_counts(self.h, cnt, n))
+        return {name: cnt[i] for i, name in enumerate(self.kernel_classes())}
+
+    def loss_reset(self):
+        self._ck(self.L.dsk_loss_reset(self.h))
+
+    def loss_add_l2(self, step, target, weight=1.0):
+        p, dev = _ptr(_f32(target) if isinstance(target, np.ndarray) else target)
+        self._keep_t = target
+        self._ck(self.L.dsk_loss_add_l2(self.h, step, p, C.c_double(weight), dev))
+
+    def loss_get(self, out=None):
+        if out is None:
+            out = np.zeros(self.B, np.float32)
+        p, dev = _ptr(out)
+        self._ck(self.L.dsk_loss_get(self.h, p, dev))
+        return out

@@ -159,6 +159,8 @@ int dsk_get_tool_grad(dsk_engine* e, int step, int env, int tool, float* g8);
 int dsk_scale_grad(dsk_engine* e, int step, double alpha);
 /* Primitive.get_action_grad(s, 1) for every tool, concatenated (primive_base.py:254-258,276-282): [n_envs, action_dim] */
 int dsk_get_action_grad(dsk_engine* e, int step, float* out, int on_device);
+/* the same for steps [step0, step0+nsteps) in one copy: [nsteps, n_envs, action_dim] (Primitives.get_grad(n), primitives.py:869-875) */
+int dsk_get_action_grads(dsk_engine* e, int step0, int nsteps, float* out, int on_device);
 
 /* ---- observations ----------------------------------------------------------------------------- */
 /* GradModel._get_obs (function.py:90-102): xv [n_envs,cap,6] (x then v), tools [n_envs,n_tools,8] */
@@ -186,6 +188,22 @@ int dsk_debug_tool_frame(dsk_engine* e, int f, int env, int tool, float* state8,
 int dsk_debug_tool_frame_grad(dsk_engine* e, int f, int env, int tool, float* g8);
 /* device SVD probe: F [n,9] -> U,sig,V (host pointers) */
 int dsk_debug_svd(dsk_engine* e, int n, const float* F, float* U, float* sig, float* V);
+/* ---- measurement helpers (bench.py) ---------------------------------------------------------------------- */
+/* Whole-step calls replay one captured CUDA graph per step slot (default on; DSK_NO_GRAPHS=1 disables). */
+int dsk_set_graphs(dsk_engine* e, int on);
+/* Profiling mode: whole-step calls launch eagerly and every kernel is bracketed by CUDA events on the engine's
+ * stream; dsk_profile_report sums milliseconds / launches per kernel class (dsk_kernel_class_name). */
+int dsk_profile_enable(dsk_engine* e, int on);
+int dsk_kernel_class_count(void);
+const char* dsk_kernel_class_name(int i);
+int dsk_profile_report(dsk_engine* e, double* ms, int64_t* launches, int n, int reset);
+int dsk_launch_counts(dsk_engine* e, int64_t* per_class, int n);
+/* Deterministic stand-in for the reference's torch-side losses (taichi_env.py:246-275 needs geomloss):
+ * loss[env] += weight * mean_p |x_p - target_p|^2 at checkpoint `step`; its gradient is added to the adjoint
+ * checkpoint.  target: [n_envs, particle_capacity, 3]; dsk_loss_get: [n_envs]. */
+int dsk_loss_reset(dsk_engine* e);
+int dsk_loss_add_l2(dsk_engine* e, int step, const float* target, double weight, int on_device);
+int dsk_loss_get(dsk_engine* e, float* out, int on_device);
 /* launches issued by this engine since creation (bench.py's gpu_launches) */
 int dsk_launch_count(dsk_engine* e, int64_t* n);
 /* bytes of device memory owned by the engine */
