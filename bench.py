@@ -216,6 +216,7 @@ def main():
     import torch
     import torch.distributed as dist
     from diffskill_b200.engine import Engine
+    from diffskill_b200.parallel import gather_planner_inputs
 
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -249,9 +250,6 @@ def main():
     loss_host = torch.zeros(B).pin_memory()
     grads_dev = torch.zeros((H, B, A), device=dev)
     loss_dev = torch.zeros(B, device=dev)
-    if world > 1:
-        all_grads = torch.zeros((world, H, B, A), device=dev)
-        all_loss = torch.zeros((world, B), device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     w = 1.0 / H
 
@@ -267,8 +265,7 @@ def main():
         if world > 1:   # the planner's exchange step: per-env losses and action gradients of every rank
             eng.get_action_grads(0, H, grads_dev)
             eng.loss_get(loss_dev)
-            dist.all_gather_into_tensor(all_grads, grads_dev)
-            dist.all_gather_into_tensor(all_loss, loss_dev)
+            gather_planner_inputs(loss_dev, grads_dev)
         if e2e:         # D2H read of the step's result
             eng.get_action_grads(0, H, grads_host.numpy())
             eng.loss_get(loss_host.numpy())

@@ -202,6 +202,8 @@ extern "C" {
 
 const char* dsk_last_error(void) { return g_err.c_str(); }
 int dsk_abi_version(void) { return DSK_ABI_VERSION; }
+int dsk_sizeof_config(void) { return (int)sizeof(dsk_config); }
+int dsk_sizeof_tool_desc(void) { return (int)sizeof(dsk_tool_desc); }
 
 int dsk_create(const dsk_config* c, dsk_engine** out) {
   if (!c || !out) return fail("null argument");

@@ -46,7 +46,7 @@ _LIB = None
 
 # every symbol include/diffskill_mpm.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
-    'dsk_last_error', 'dsk_abi_version', 'dsk_create', 'dsk_destroy', 'dsk_set_stream', 'dsk_synchronize',
+    'dsk_last_error', 'dsk_abi_version', 'dsk_sizeof_config', 'dsk_sizeof_tool_desc', 'dsk_create', 'dsk_destroy', 'dsk_set_stream', 'dsk_synchronize',
     'dsk_set_rand_num', 'dsk_set_particles', 'dsk_get_particles', 'dsk_get_n_particles', 'dsk_set_tool_state',
     'dsk_get_tool_state', 'dsk_copy_step', 'dsk_set_material', 'dsk_set_tool_param', 'dsk_get_tool_param',
     'dsk_set_gravity', 'dsk_set_action', 'dsk_forward_step', 'dsk_backward_step', 'dsk_substep', 'dsk_substep_grad',

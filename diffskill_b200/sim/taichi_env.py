@@ -1,0 +1,274 @@
+"""``TaichiEnv`` with the reference's interface (plb/engine/taichi_env.py:45-393), minus rendering.
+
+Scene assembly (Primitives, Shapes, MPMSimulator), step / state / observation wrappers and the torch
+losses.  ``taichi`` is not imported anywhere: the simulator is the CUDA engine.  Rendering
+(``TinaRenderer``) is out of scope and raises.
+"""
+import numpy as np
+
+from ..shapes import Shapes
+from .mpm_simulator import MPMSimulator
+from .primitives import Gripper, Primitives
+
+
+def sinkhorn_emd(x, y, blur=0.001, p=1, scaling=0.5, iters_cap=200):
+    """Debiased Sinkhorn divergence between two uniform point clouds, in plain torch.
+
+    Stand-in for ``geomloss.SamplesLoss('sinkhorn', p=1, blur=0.001)`` (taichi_env.py:23-26), which is not
+    installable offline: epsilon-scaling from the cloud diameter down to blur**p, log-domain updates,
+    S(x,y) = OT(x,y) - (OT(x,x) + OT(y,y)) / 2.  Differentiable by autograd through the final potentials."""
+    import torch
+
+    def cost(a, b):
+        d = torch.cdist(a, b)
+        return d if p == 1 else d ** p / p
+
+    def ot(a, b):
+        n, m = a.shape[0], b.shape[0]
+        C = cost(a, b)
+        la = torch.full((n,), -np.log(n), device=a.device, dtype=a.dtype)
+        lb = torch.full((m,), -np.log(m), device=a.device, dtype=a.dtype)
+        with torch.no_grad():
+            diam = float(C.max().clamp_min(1e-6))
+            eps_t, eps_list = blur ** p, []
+            e = diam ** p if p > 1 else diam
+            while e > eps_t and len(eps_list) < iters_cap:
+                eps_list.append(e)
+                e *= scaling ** p
+            eps_list.append(eps_t)
+            f, g = torch.zeros(n, device=a.device, dtype=a.dtype), torch.zeros(m, device=a.device, dtype=a.dtype)
+            Cd = C.detach()
+            for e in eps_list:
+                f = -e * torch.logsumexp(lb[None, :] + (g[None, :] - Cd) / e, dim=1)
+                g = -e * torch.logsumexp(la[None, :] + (f[None, :] - Cd.t()) / e, dim=1)
+        e = eps_list[-1]
+        # one differentiable half-step at the final temperature (envelope theorem: gradients w.r.t. the points)
+        f2 = -e * torch.logsumexp(lb[None, :] + (g[None, :] - C) / e, dim=1)
+        g2 = -e * torch.logsumexp(la[None, :] + (f[None, :] - C.t()) / e, dim=1)
+        return f2.mean() + g2.mean()
+
+    return ot(x, y) - 0.5 * (ot(x, x) + ot(y, y))
+
+
+def create_emd_loss():
+    try:
+        from geomloss import SamplesLoss
+        return SamplesLoss(loss='sinkhorn', p=1, blur=0.001)
+    except ImportError:
+        return sinkhorn_emd
+
+
+def chamfer_loss(bidirectional):
+    import torch
+
+    def fn(a, b):            # a,b: [1,N,3]; mirrors chamferdist.ChamferDistance()(a, b, bidirectional=...)
+        d = torch.cdist(a[0], b[0]) ** 2
+        out = d.min(dim=1)[0].sum()
+        if bidirectional:
+            out = out + d.min(dim=0)[0].sum()
+        return out
+    return fn
+
+
+class TaichiEnv:
+    def __init__(self, cfg, nn=False, loss=True, return_dist=False, n_envs=1, device_index=0, step_slots=None,
+                 max_env_steps=None):
+        if nn:
+            raise NotImplementedError("the Taichi MLP policy (plb/engine/nn) is out of scope (SURVEY.md section 2 row 9)")
+        self.has_loss = loss
+        self.full_cfg = cfg
+        self.cfg = cfg.ENV
+        self.env_name = self.cfg.env_name if 'env_name' in self.cfg else None
+        self.primitives = Primitives(cfg.PRIMITIVES)
+        self.shapes = Shapes(cfg.SHAPES)
+        self.init_particles, self.particle_colors = self.shapes.get()
+        self.n_particles = len(self.init_particles)
+        self.simulator = MPMSimulator(cfg.SIMULATOR, self.primitives, n_envs=n_envs, env_cfg=cfg.ENV,
+                                      device=device_index, step_slots=step_slots, max_env_steps=max_env_steps)
+        self.dim = self.simulator.dim
+        self.renderer, self.renderer_name = None, 'none'
+        self._is_copy = True
+        self.target_x, self.tensor_target_x = None, None
+        self.device = 'cuda'
+        self.contact_loss_mask = None
+        self.return_dist = return_dist
+        self.dists_start_idx = []
+        k = 0
+        for p in self.primitives:
+            self.dists_start_idx.append(k)
+            k += 2 if isinstance(p, Gripper) else 1
+        self.dists_start_idx.append(k)
+
+    def set_copy(self, is_copy: bool):
+        self._is_copy = is_copy
+
+    def initialize(self, cfg=None, target_path=None):
+        if cfg is not None:
+            self.full_cfg = cfg
+            self.cfg = cfg.ENV
+            self.shapes = Shapes(cfg.SHAPES)
+            self.init_particles, self.particle_colors = self.shapes.get()
+            self.primitives.update_cfgs(cfg.PRIMITIVES)
+            if self.has_loss and target_path is not None:
+                self.load_target_x(target_path)
+        self.n_particles = len(self.init_particles)
+        self.primitives.initialize(self.cfg.cached_state_path)
+        self.simulator.initialize(self.n_particles)
+        self.simulator.reset(self.init_particles)
+
+    def load_target_x(self, path):
+        import torch
+        self.target_x = np.load(path)
+        self.tensor_target_x = torch.FloatTensor(self.target_x).to(self.device)
+
+    def render(self, mode='human', **kwargs):
+        assert self._is_copy, "The environment must be in the copy mode for render ..."
+        raise NotImplementedError("rendering (tina) is out of scope of the engine (SURVEY.md section 2 rows 10-11)")
+
+    def step(self, action=None):
+        if action is not None:
+            action = np.array(action)
+        self.simulator.step(is_copy=self._is_copy, action=action)
+
+    def get_state(self):
+        assert self.simulator.cur == 0
+        return {'state': self.simulator.get_state(0), 'softness': self.primitives.get_softness(), 'is_copy': self._is_copy}
+
+    def set_state(self, state, softness=None, is_copy=None, **kwargs):
+        if softness is None:
+            softness, is_copy, state = state['softness'], state['is_copy'], state['state']
+        self.n_particles = len(state[0])
+        self.simulator.cur = 0
+        self.simulator.set_state(0, state)
+        self.primitives.set_softness(softness)
+        self._is_copy = is_copy
+
+    def set_primitive_state(self, state, softness, is_copy, **kwargs):
+        self.simulator.set_primitive_state(0, state)
+
+    def get_use_gripper_primitive(self):
+        return any(isinstance(i, Gripper) for i in self.primitives.primitives)
+
+    # ---- losses (torch side; taichi_env.py:191-275) ------------------------------------------------------------
+    def get_contact_loss(self, shape, tool, contact_mask=None):
+        import torch
+        if contact_mask is not None:
+            assert len(shape) == len(contact_mask)
+            shape = shape[contact_mask]
+        if self.env_name in ('CutRearrange-v1', 'CutRearrange-v2'):
+            center, gap = tool[1][:3], tool[1][7]
+            z1, z2 = center[2] - gap / 2 + 0.015, center[2] + gap / 2 - 0.015
+            a, b = torch.stack([center[0], center[1], z1]), torch.stack([center[0], center[1], z2])
+            d1 = ((a[None, :] - shape[:, :3]) ** 2).sum(axis=1).min()
+            d2 = ((b[None, :] - shape[:, :3]) ** 2).sum(axis=1).min()
+            gripper_dist = d1.clamp(0.00005, 1e9) + d2.clamp(0.00005, 1e9) - 0.0001
+            knife_dist = shape[:, 6:7].min(axis=0)[0].clamp(0, 1e9)
+            dists = torch.cat([knife_dist, gripper_dist[None]])
+            assert self.contact_loss_mask.shape == dists.shape
+            return (self.contact_loss_mask * dists).sum()
+        if self.get_use_gripper_primitive():
+            dists = shape[:, -len(self.primitives) - 1:]
+            dists = torch.cat([(dists[:, 0] + dists[:, 1])[:, None], dists[:, 2:]], dim=1)
+        else:
+            dists = shape[:, -len(self.primitives):]
+        min_ = dists.min(axis=0)[0].clamp(0, 1e9)
+        assert self.contact_loss_mask.shape == min_.shape
+        return ((self.contact_loss_mask * min_) ** 2).sum() * 1e-3
+
+    def update_loss_fn(self, loss_type='emd'):
+        self.loss_type = loss_type
+        self.loss_fn = {'emd': create_emd_loss, 'oneway_chamfer': lambda: chamfer_loss(False),
+                        'twoway_chamfer': lambda: chamfer_loss(True)}[loss_type]()
+
+    def compute_loss(self, idxes, observations, vel_loss_weight, state_mask=None, goal_mask=None, loss_type='emd'):
+        import torch
+        loss = 0
+        if not hasattr(self, 'loss_fn'):
+            self.update_loss_fn(loss_type=loss_type)
+        xs = []
+        for idx, (shape, tool, *args) in zip(idxes, observations):
+            loss = loss + self.get_contact_loss(shape, tool, contact_mask=state_mask)
+            xs.append(shape[state_mask, :3] if state_mask is not None else shape[:, :3])
+        sampled_idx = np.random.choice(xs[0].shape[0], min(500, xs[0].shape[0]), replace=False)
+        xs = torch.stack(xs).contiguous()[:, sampled_idx]
+        tx = self.tensor_target_x[goal_mask] if goal_mask is not None else self.tensor_target_x
+        target_x = tx[sampled_idx].repeat([len(xs), 1, 1])
+        for i in range(len(xs)):
+            if self.loss_type == 'emd':
+                loss = loss + self.loss_fn(xs[i], target_x[i])
+            else:
+                loss = loss + self.loss_fn(target_x[i].unsqueeze(0), xs[i].unsqueeze(0))
+        final_v = observations[-1][0]
+        return loss + vel_loss_weight * torch.sum(torch.mean(final_v[:, 3:6], dim=0) ** 2)
+
+    def set_contact_loss_mask(self, mask):
+        self.contact_loss_mask = mask
+
+    def get_curr_emd(self):
+        if self.tensor_target_x is None:
+            return 0.
+        if not hasattr(self, 'emd_loss_fn'):
+            self.emd_loss_fn = create_emd_loss()
+        return self.emd_loss_fn(self.simulator.get_torch_x(0, self.device).contiguous(), self.tensor_target_x)
+
+    def set_init_emd(self):
+        e = self.get_curr_emd()
+        self.init_emd = e.item() if hasattr(e, 'item') else e
+
+    def get_reward_and_info(self):
+        import torch
+        if self.tensor_target_x is None:
+            return 0., {}
+        if not hasattr(self, 'emd_loss_fn'):
+            self.emd_loss_fn = create_emd_loss()
+        curr_x = self.simulator.get_torch_x(0, self.device).contiguous()
+        sampled_idx = np.random.choice(curr_x.shape[0], min(500, curr_x.shape[0]), replace=False)
+        curr_x, target_x = curr_x[sampled_idx], self.tensor_target_x[sampled_idx]
+        emd = self.emd_loss_fn(curr_x, target_x)
+        prim = torch.cat([i.get_state_tensor(0)[None, :3] for i in self.primitives], dim=0)
+        dists = torch.min(torch.cdist(prim[None], curr_x[None])[0], dim=1)[0]
+        contact_loss = (self.contact_loss_mask * dists).sum() * 1e-3
+        reward, emd = -emd - contact_loss, emd.item()
+        if not hasattr(self, 'init_emd'):
+            perf = 0.
+        elif self.init_emd == 0.:
+            perf = 1.
+        else:
+            perf = (self.init_emd - emd) / self.init_emd
+        return reward.item(), {'info_emd': emd, 'info_normalized_performance': perf,
+                               'info_contact_loss': contact_loss.item()}
+
+    # ---- observations (taichi_env.py:342-383) -----------------------------------------------------------------
+    def get_obs(self, s, device='cuda', env=0):
+        import torch
+        eng = self.simulator.engine
+        n = eng.n_particles(env)
+        xv = torch.zeros((eng.B, eng.capacity, 6), device=device)
+        c = torch.zeros((eng.B, eng.K, 8), device=device)
+        if xv.is_cuda:
+            eng.get_obs(s, xv, c)
+        else:
+            a, b = eng.get_obs(s)
+            xv, c = torch.from_numpy(a), torch.from_numpy(b)
+        x = xv[env, :n, :3]
+        if self.return_dist:
+            d = self.compute_min_dist(s * self.simulator.substeps, device)[env, :n]
+            merged = [d[:, l:r].sum(dim=1, keepdim=True) for l, r in zip(self.dists_start_idx[:-1], self.dists_start_idx[1:])]
+            x = torch.cat((x, *merged), 1)
+        return x.clone(), c[env].clone()
+
+    def compute_min_dist(self, f, device='cuda'):
+        import torch
+        eng = self.simulator.engine
+        out = torch.zeros((eng.B, eng.capacity, eng.ncols), device=device)
+        step = self.simulator._frame_to_step(f)
+        if out.is_cuda:
+            eng.compute_min_dist(step, out)
+            return out
+        return torch.from_numpy(eng.compute_min_dist(step))
+
+    def get_tool_particles(self, s):
+        pts = []
+        for prim in (p for p in self.primitives if p.action_dim > 0):
+            pts.append(prim.get_surface_points(s) if hasattr(prim, 'init_points') else np.zeros((100, 3)))
+        return np.vstack(pts)

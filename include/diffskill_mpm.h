@@ -97,6 +97,9 @@ typedef struct dsk_engine dsk_engine;
 
 const char* dsk_last_error(void);
 int dsk_abi_version(void);
+/* struct sizes, so that foreign-function bindings can verify their layout without a GPU */
+int dsk_sizeof_config(void);
+int dsk_sizeof_tool_desc(void);
 
 /* MPMSimulator.__init__ + Primitives.__init__ + initialize (mpm_simulator.py:8-97, primitives.py:820-838) */
 int dsk_create(const dsk_config* cfg, dsk_engine** out);

@@ -18,7 +18,7 @@ def small_dough(name, n, seed=0):
     rng = np.random.RandomState(seed)
     if name == 'LiftSpread-v1':
         # blob on the lifter plate, touching the rolling pin's influence region
-        x = rng.uniform(-1, 1, (n, 3)) * np.array([0.04, 0.02, 0.04]) + np.array([0.62, 0.075, 0.5])
+        x = rng.uniform(-1, 1, (n, 3)) * np.array([0.04, 0.035, 0.04]) + np.array([0.62, 0.10, 0.5])
     elif name == 'GatherMove-v1':
         x = rng.uniform(-1, 1, (n, 3)) * np.array([0.05, 0.012, 0.05]) + np.array([0.70, 0.05, 0.5])
     elif name == 'CutRearrange-v1':
@@ -42,8 +42,8 @@ def tool_start(name, scene):
     """Tool states at frame 0 moved so that every tool touches the small dough."""
     st = [np.array(t.init_state, dtype=np.float64) for t in scene.tools]
     if name == 'LiftSpread-v1':
-        st[0][:3] = (0.60, 0.13, 0.5)     # rolling pin just above the blob
-        st[1][:3] = (0.62, 0.03, 0.5)
+        st[0][:3] = (0.60, 0.16, 0.5)     # rolling pin (y clamped to >= 0.16 by its lower_bound) 5 mm into the blob
+        st[1][:3] = (0.62, 0.05, 0.5)     # lifter plate 5 mm into its underside
     elif name == 'GatherMove-v1':
         st[0][7] = 0.12                   # gripper jaws close to the dough
     elif name == 'CutRearrange-v1':

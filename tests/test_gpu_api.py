@@ -1,0 +1,127 @@
+"""The reference-shaped Python API (MPMSimulator / Primitives / TaichiEnv / GradModel) over the C ABI, on the GPU,
+checked against the oracle driven through the reference's own call sequences."""
+import numpy as np
+import pytest
+
+from helpers import relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_for(env, frames):
+    from oracle import oracle as orc
+    sim = env.simulator
+    st = env.get_state()['state']
+    o = orc.Oracle(sim.scene, len(st[0]), frames, f64=False, threads=8)
+    o.set_frame(0, *[np.asarray(a, np.float32) for a in st[:4]])
+    for i, s in enumerate(st[4:]):
+        o.set_tool_state(0, i, np.asarray(s, np.float32))
+    return o
+
+
+@pytest.mark.parametrize('name', ['LiftSpread-v1', 'CutRearrange-v1'])
+def test_random_rollout_copy_mode(name):
+    """configs[0]: scripts/random_env.py -- env.step(action_space.sample()) in copy mode."""
+    from diffskill_b200.envs import make
+    env = make(name, seed=100)
+    te = env.taichi_env
+    env.reset()
+    o = _oracle_for(te, te.simulator.substeps + 1)
+    for t in range(3):
+        a = env.sample_action()
+        env.step(a)
+        o.step_copy(a)
+        x, v = te.simulator.get_x(0), te.simulator.get_v(0)
+        ox, ov, _, _ = o.get_frame(0)
+        assert relerr(x, ox) < 2e-6 * (t + 1), (t, relerr(x, ox))
+        assert relerr(v, ov) < 5e-4, (t, relerr(v, ov))
+        ts = np.stack([p.get_state(0)[:7] for p in te.primitives])
+        assert relerr(ts, o.get_tool_states(0)[:, :7]) < 1e-6
+    st = te.get_state()
+    assert st['state'][0].dtype == np.float64 and st['state'][2].shape[1:] == (3, 3)   # mpm_simulator.py:382-385
+    assert te.simulator.cur == 0
+
+
+@pytest.mark.parametrize('name,return_dist', [('GatherMove-v1', True), ('LiftSpread-v1', False)])
+def test_gradmodel_autograd_matches_oracle(name, return_dist):
+    """Solver.solve_one_plan pattern (plb/optimizer/solver.py:111-127): reset, H x forward.apply, torch loss,
+    backward -- the action gradient must match the oracle's taped gradient."""
+    import torch
+    from diffskill_b200.config import load
+    from diffskill_b200.envs.scenes import SCENES
+    from diffskill_b200.sim import GradModel, TaichiEnv
+    cfg = load(data=SCENES[name])
+    if name == 'LiftSpread-v1':
+        cfg.SHAPES[0]['radius'] = 0.02          # 1005 particles: the oracle's tape AD stays fast
+    te = TaichiEnv(cfg, loss=False, return_dist=return_dist, max_env_steps=4)
+    te.initialize()
+    n = te.n_particles
+    func = GradModel(te, softness=666., return_dist=return_dist)
+    H, S, A = 3, te.simulator.substeps, te.primitives.action_dim
+    o = _oracle_for(te, H * S + 1)
+    rng = np.random.RandomState(0)
+    acts = torch.tensor(rng.uniform(-1, 1, (H, A)), device='cuda', dtype=torch.float32, requires_grad=True)
+    ncol = 6 + (func.eng.ncols if return_dist else 0)
+    W = torch.tensor(rng.normal(size=(H, n, ncol)), device='cuda', dtype=torch.float32)
+    Wc = torch.tensor(rng.normal(size=(H, len(te.primitives), 8)) * 0.1, device='cuda', dtype=torch.float32)
+    obs = func.reset(device='cuda')
+    assert obs[0].shape == (n, ncol) and obs[1].shape == (len(te.primitives), 8)
+    loss = 0
+    for s in range(H):
+        obs = func.forward(s, acts[s], *obs)
+        loss = loss + (obs[0] * W[s]).sum() + (obs[1] * Wc[s]).sum()
+    loss.backward()
+    g = acts.grad.cpu().numpy()
+    # oracle: same call sequence on the tape
+    o.zero_grad()
+    an = acts.detach().cpu().numpy().astype(np.float64)
+    for s in range(H):
+        o.forward_step(s, an[s])
+    Wn, Wcn = W.cpu().numpy().astype(np.float64), Wc.cpu().numpy().astype(np.float64)
+    og = np.zeros((H, A))
+    for s in range(H - 1, -1, -1):
+        f = (s + 1) * S
+        if return_dist:
+            o.compute_min_dist_grad(f, Wn[s][:, 6:])
+        o.add_frame_grad(f, gx=Wn[s][:, :3], gv=Wn[s][:, 3:6])
+        for i in range(len(te.primitives)):
+            o.add_tool_grad(f, i, Wcn[s][i])
+        og[s] = o.backward_step(s)
+    e = relerr(g, og)
+    print(name, 'GradModel action-grad err %.2e' % e, 'loss', float(loss))
+    assert e < 1e-3
+
+
+def test_field_proxies_and_errors():
+    from diffskill_b200.config import load
+    from diffskill_b200.envs.scenes import SCENES
+    from diffskill_b200.engine import EngineError
+    from diffskill_b200.sim import TaichiEnv
+    cfg = load(data=SCENES['CutRearrange-v1'])
+    te = TaichiEnv(cfg, loss=False, max_env_steps=2)
+    te.initialize()
+    sim, prims = te.simulator, te.primitives
+    assert sim.n_particles[None] == 5000 and sim.substeps == 24 and sim.n_grid == 80
+    prims[1].friction[None] = 3.5
+    assert sim.engine.get_tool_param(1, 0) == pytest.approx(3.5)
+    prims.set_softness(123.)
+    assert prims.get_softness() == 123. and sim.engine.get_tool_param(0, 1) == pytest.approx(123.)
+    prims[0].xyz_limit[1] = (0.9, 0.8, 0.7)
+    assert sim.engine.get_tool_param(0, 6) == pytest.approx(0.8)
+    sim.yield_stress.fill(77.)
+    assert sim.yield_stress[0] == 77.
+    assert prims[1].gap[0] == pytest.approx(0.18)
+    with pytest.raises(AssertionError):
+        prims[1].set_state(0, [0.5, 0.1, 0.5, 1, 0, 0, 0])          # gripper needs 8 values (primitives.py:551)
+    with pytest.raises(AssertionError):
+        prims.set_action(0, sim.substeps, np.zeros(3))               # wrong action length (primitives.py:865)
+    prims[0].set_state(0, [0.4, 0.3, 0.5])                           # short state pads (primive_base.py:188-191)
+    assert np.allclose(prims[0].get_state(0)[:3], [0.4, 0.3, 0.5]) and prims[0].get_state(0)[3] == pytest.approx(1.0)
+    te.step(np.zeros(10))
+    with pytest.raises(IndexError):
+        sim.get_x(5)                                                   # not a step boundary and not resident
+    with pytest.raises(EngineError):
+        sim.engine.forward_step(7, 8, 7)                               # beyond the horizon
+    sim.x.grad.fill(0)
+    with pytest.raises(NotImplementedError):
+        te.render()

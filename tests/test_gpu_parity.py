@@ -209,3 +209,33 @@ def test_multi_step_action_gradient(name, slots):
     print(name, 'slots', slots, 'action grad err %.2e' % e, 'x.grad[0] err %.2e' % relerr(a[0], b[0]))
     assert e < TOL_ACTION_GRAD
     assert relerr(a[0], b[0]) < 5 * TOL_ACTION_GRAD
+
+
+@pytest.mark.parametrize('name', ENVS)
+def test_against_committed_golden_fixture(name):
+    """CUDA path vs tests/golden/*.npz (oracle fp64, generated by tests/golden/make_golden.py): one env step of
+    the real substep count forward + backward."""
+    import os
+    from helpers import small_dough
+    from diffskill_b200.engine import Engine
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', f'{name}.npz'))
+    n = len(g['x0'])
+    scene, _, _ = small_dough(name, n)
+    eng = Engine(scene, capacity=n, max_steps=1)
+    eng.set_particles(0, 0, g['x0'], g['v0'], g['F0'], g['C0'])
+    for i, s in enumerate(g['tools0']):
+        eng.set_tool_state(0, 0, i, s)
+    base, _ = eng.debug_cell_index(0)
+    assert np.array_equal(base, g['base0'])
+    eng.set_action(0, g['action'][None])
+    eng.forward_step(0)
+    x, v, F, C = eng.get_particles(1)
+    assert relerr(x, g['x1']) < 1e-5 and relerr(F, g['F1']) < 1e-4 and relerr(v, g['v1']) < 2e-3
+    assert relerr(eng.get_tool_states(1), g['tools1']) < 1e-6
+    eng.zero_grad()
+    eng.add_particle_grad(1, f32(g['gx'])[None], f32(g['gv'])[None])
+    eng.backward_step(0)
+    ga = eng.get_action_grad(0)[0]
+    e = relerr(ga, g['action_grad'])
+    print(name, 'golden: x %.1e v %.1e action grad %.1e' % (relerr(x, g['x1']), relerr(v, g['v1']), e))
+    assert e < 2e-2          # same bound the fp32 oracle is held to against its fp64 twin (tests/test_oracle.py)

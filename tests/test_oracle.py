@@ -1,0 +1,173 @@
+"""CPU tests of the oracle itself (no GPU): golden fixtures, finite differences of the adjoints in fp64,
+conservation invariants, the SVD contract, and the reference's own property (checkpointed == taped gradient)."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import perturbed_state, relerr, small_dough, tool_start
+from oracle import oracle as orc
+
+ENVS = ['LiftSpread-v1', 'GatherMove-v1', 'CutRearrange-v1']
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _replay(name, f64):
+    g = np.load(os.path.join(GOLD, f'{name}.npz'))
+    scene, _, _ = small_dough(name, len(g['x0']))
+    S = scene.substeps
+    o = orc.Oracle(scene, len(g['x0']), S + 1, f64=f64, threads=2)
+    o.set_frame(0, g['x0'], g['v0'], g['F0'], g['C0'])
+    for i, s in enumerate(g['tools0']):
+        o.set_tool_state(0, i, s)
+    base, _ = o.cell_index(0)
+    occ = o.occupancy(0)
+    o.forward_step(0, g['action'])
+    x, v, F, C = o.get_frame(S)
+    o.zero_grad()
+    o.add_frame_grad(S, g['gx'], g['gv'])
+    ga = o.backward_step(0)
+    return g, dict(base0=base, occ=occ, x1=x, v1=v, F1=F, C1=C, tools1=o.get_tool_states(S), action_grad=ga,
+                   gx0=o.get_frame_grad(0)[0])
+
+
+@pytest.mark.parametrize('name', ENVS)
+def test_golden_fp64_regression(name):
+    g, r = _replay(name, True)
+    assert np.array_equal(r['base0'], g['base0'])
+    assert np.array_equal(np.packbits(r['occ']), g['occupancy0'])
+    for k in ('x1', 'v1', 'F1', 'C1', 'tools1', 'action_grad', 'gx0'):
+        assert relerr(r[k], g[k]) < 1e-9, k
+
+
+@pytest.mark.parametrize('name', ENVS)
+def test_golden_fp32_within_tolerance(name):
+    """The fp32 oracle (the reference's precision) against the fp64 fixtures: integer work bit-exact, one env step
+    of state within 1e-4, action gradient within the north-star's 1e-3 class (the fp32 noise floor of the
+    reference formulation: collider velocity = pose difference / dt)."""
+    g, r = _replay(name, False)
+    assert np.array_equal(r['base0'], g['base0'])
+    assert np.array_equal(np.packbits(r['occ']), g['occupancy0'])
+    assert relerr(r['x1'], g['x1']) < 1e-5
+    assert relerr(r['v1'], g['v1']) < 2e-3
+    assert relerr(r['F1'], g['F1']) < 1e-4
+    assert relerr(r['action_grad'], g['action_grad']) < 2e-2
+
+
+@pytest.mark.parametrize('name', ENVS)
+def test_adjoint_matches_finite_differences_fp64(name):
+    scene, cfg, x0 = small_dough(name, 60)
+    v0, F0, C0 = perturbed_state(x0)
+    st0 = tool_start(name, scene)
+    S = scene.substeps
+    rng = np.random.RandomState(5)
+    act = rng.uniform(-0.8, 0.8, scene.action_dim)
+    wx, wv = rng.normal(size=(60, 3)), rng.normal(size=(60, 3)) * 0.01
+
+    def run(a, x, grad=False):
+        o = orc.Oracle(scene, 60, S + 1, f64=True, threads=2)
+        o.set_frame(0, x, v0, F0, C0)
+        for i, s in enumerate(st0):
+            o.set_tool_state(0, i, s)
+        o.forward_step(0, a)
+        xx, vv, _, _ = o.get_frame(S)
+        L = (wx * xx).sum() + (wv * vv).sum()
+        if not grad:
+            return L
+        o.zero_grad()
+        o.add_frame_grad(S, wx, wv)
+        return L, o.backward_step(0), o.get_frame_grad(0)[0]
+
+    L, ga, gx = run(act, x0, True)
+    scale = np.abs(ga).max()
+    checked = 0
+    for j in range(scene.action_dim):
+        if ga[j] == 0:
+            continue
+        a1, a2 = act.copy(), act.copy()
+        a1[j] += 1e-6
+        a2[j] -= 1e-6
+        fd = (run(a1, x0) - run(a2, x0)) / 2e-6
+        assert abs(fd - ga[j]) < 2e-4 * scale + 1e-7, (j, fd, ga[j])
+        checked += 1
+    assert checked >= 3
+    for p, d in [(3, 0), (17, 1), (41, 2)]:
+        x1, x2 = x0.copy(), x0.copy()
+        x1[p, d] += 1e-7
+        x2[p, d] -= 1e-7
+        fd = (run(act, x1) - run(act, x2)) / 2e-7
+        assert abs(fd - gx[p, d]) < 1e-4 * np.abs(gx).max(), (p, d, fd, gx[p, d])
+
+
+def test_mass_and_momentum_conservation_without_tools():
+    """p2g -> g2p with no collider, no gravity, away from the walls conserves mass and linear momentum."""
+    import copy
+    scene, cfg, x0 = small_dough('CutRearrange-v1', 400)
+    scene = copy.deepcopy(scene)
+    scene.tools, scene.pairs, scene.gravity = [], [], (0., 0., 0.)
+    x0 = x0 + np.array([0., 0.3, 0.])
+    rng = np.random.RandomState(0)
+    v0 = rng.normal(size=(400, 3)) * 0.1
+    o = orc.Oracle(scene, 400, 2, f64=True, threads=1)
+    o.set_frame(0, x0, v0, np.tile(np.eye(3), (400, 1, 1)), np.zeros((400, 3, 3)))
+    o.substep(0)
+    _, _, m = o.get_grid()
+    assert m.sum() == pytest.approx(400 * scene.p_mass, rel=1e-12)
+    _, v1, _, _ = o.get_frame(1)
+    assert np.allclose(v1.sum(0), v0.sum(0), rtol=0, atol=1e-6)   # nodes with m <= 1e-12 are skipped by grid_op
+
+
+def test_svd_contract():
+    rng = np.random.RandomState(0)
+    for f64, tol in ((False, 3e-6), (True, 1e-13)):
+        for _ in range(300):
+            F = np.eye(3) + rng.normal(size=(3, 3)) * rng.choice([1e-7, 1e-3, 0.1, 1.0])
+            if rng.rand() < 0.2:
+                F[:, 0] *= -1        # inverted element: the sign goes to the smallest singular value
+            F = F.astype(np.float32).astype(np.float64)
+            U, s, V = orc.svd3(F, f64)
+            assert np.abs(U @ np.diag(s) @ V.T - F).max() < tol * max(1, np.abs(F).max())
+            assert np.linalg.det(U) > 0.999 and np.linalg.det(V) > 0.999
+            assert s[0] >= s[1] >= abs(s[2]) - 1e-6
+    U, s, V = orc.svd3(np.eye(3), False)
+    assert np.array_equal(U, np.eye(3)) and np.array_equal(V, np.eye(3)) and np.array_equal(s, np.ones(3))
+
+
+def test_checkpointed_gradient_equals_taped_gradient():
+    """plb/optimizer/long_term_gradient.ipynb: backward from per-step checkpoints == full tape (assert < 1e-4)."""
+    name = 'CutRearrange-v1'
+    scene, cfg, x0 = small_dough(name, 80)
+    v0, F0, C0 = perturbed_state(x0, vel=0.05, strain=0.01)
+    st0 = tool_start(name, scene)
+    S, H = scene.substeps, 3
+    rng = np.random.RandomState(2)
+    acts = rng.uniform(-0.7, 0.7, (H, scene.action_dim))
+    wx = rng.normal(size=(80, 3))
+    full = orc.Oracle(scene, 80, H * S + 1, f64=True, threads=2)
+    full.set_frame(0, x0, v0, F0, C0)
+    for i, s in enumerate(st0):
+        full.set_tool_state(0, i, s)
+    ckpt = []
+    for s in range(H):
+        ckpt.append((full.get_frame(s * S), full.get_tool_states(s * S)))
+        full.forward_step(s, acts[s])
+    full.zero_grad()
+    full.add_frame_grad(H * S, wx)
+    g_full = np.stack([full.backward_step(s) for s in range(H - 1, -1, -1)][::-1])
+    # checkpointed: one-step tapes restarted from the stored states, adjoints handed over at the boundaries
+    g_ck = np.zeros_like(g_full)
+    adj = (wx, np.zeros((80, 3)), np.zeros((80, 3, 3)), np.zeros((80, 3, 3)))
+    tool_adj = np.zeros((len(scene.tools), 8))
+    for s in range(H - 1, -1, -1):
+        o = orc.Oracle(scene, 80, S + 1, f64=True, threads=2)
+        o.set_frame(0, *ckpt[s][0])
+        for i, st in enumerate(ckpt[s][1]):
+            o.set_tool_state(0, i, st)
+        o.forward_step(0, acts[s])
+        o.zero_grad()
+        o.add_frame_grad(S, *adj)
+        for i in range(len(scene.tools)):
+            o.add_tool_grad(S, i, tool_adj[i])
+        g_ck[s] = o.backward_step(0)
+        adj, tool_adj = o.get_frame_grad(0), o.get_tool_grads(0)
+    assert np.abs(g_ck - g_full).max() < 1e-9 * max(1.0, np.abs(g_full).max())
