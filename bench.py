@@ -205,7 +205,9 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='liftspread')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--step-slots', type=int, default=1, help='substep-frame ring (1 = per-step checkpointing)')
+    ap.add_argument('--step-slots', type=int, default=0,
+                    help='substep-frame ring in env steps (1 = pure per-step checkpointing + recompute, H = full tape; '
+                         '0 = auto: H if the tape fits in 16 GB else 1)')
     ap.add_argument('--no-sort', action='store_true')
     ap.add_argument('--no-graphs', action='store_true')
     args = ap.parse_args()
@@ -232,6 +234,9 @@ def main():
     H = spec['horizon']
     scene, cfg, xs, targets, actions = make_inputs(spec, rank, B)
     cap = max(len(x) for x in xs)
+    if args.step_slots <= 0:
+        tape_bytes = H * (scene.substeps + 1) * 24 * B * ((cap + 127) // 128 * 128) * 4
+        args.step_slots = H if tape_bytes <= 16e9 else 1
     eng = Engine(scene, n_envs=B, capacity=cap, max_steps=H, step_slots=args.step_slots, sort=not args.no_sort,
                  device=local_rank)
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
