@@ -208,6 +208,8 @@ def main():
     ap.add_argument('--step-slots', type=int, default=0,
                     help='substep-frame ring in env steps (1 = pure per-step checkpointing + recompute, H = full tape; '
                          '0 = auto: H if the tape fits in 16 GB else 1)')
+    ap.add_argument('--grid-tape-mib', type=int, default=8192,
+                    help='device memory budget for taping active grid tiles (adjoint skips the p2g/grid_op recompute); 0 = off')
     ap.add_argument('--no-sort', action='store_true')
     ap.add_argument('--no-graphs', action='store_true')
     args = ap.parse_args()
@@ -238,7 +240,7 @@ def main():
         tape_bytes = H * (scene.substeps + 1) * 24 * B * ((cap + 127) // 128 * 128) * 4
         args.step_slots = H if tape_bytes <= 16e9 else 1
     eng = Engine(scene, n_envs=B, capacity=cap, max_steps=H, step_slots=args.step_slots, sort=not args.no_sort,
-                 device=local_rank)
+                 device=local_rank, grid_tape_mib=args.grid_tape_mib)
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
     if args.no_graphs:
         eng.set_graphs(False)
@@ -345,7 +347,7 @@ def main():
                    config=dict(workload=spec['desc'], env=spec['env'], horizon=H, substeps=S, envs_per_gpu=B,
                                particles_per_gpu=n_particles, n_grid=scene.n_grid, occupied_nodes=round(n_occ),
                                checkpointing=f'per env step, {args.step_slots} step slot(s) of substep frames',
-                               sort=not args.no_sort, cuda_graphs=not args.no_graphs,
+                               sort=not args.no_sort, cuda_graphs=not args.no_graphs, grid_tape_mib=args.grid_tape_mib,
                                l2='flushed between timed iterations (256 MiB write)',
                                parallelism=f'env-sharded x{world}' if world > 1 else 'single GPU'),
                    e2e=dict(value=e2e_value, unit=UNIT, ms_per_step=float(ms_e2e.mean()),

@@ -42,6 +42,8 @@ struct StepSlot {
   int* perm;         // sorted slot -> particle id, [stride]
   float* poses;      // [B][S+1][K][8]
   int* cidx;         // [B][S+1][npairs]
+  GridTape tape = {nullptr, nullptr, nullptr, nullptr, 0};
+  bool tape_written = false;  // the slot's tape belongs to src_step
   int src_step = -1; // checkpoint the frames were simulated from (-1: invalid)
   int action_step = -1;
 };
@@ -67,7 +69,7 @@ struct dsk_engine {
   int64_t kid_launches[KID_COUNT] = {0};
   SimConst k;
   cudaStream_t stream = 0;
-  int B, Npad, S, H, K, A, slots, ncols;
+  int B, Npad, S, H, K, A, slots, ncols, n_frames = 1;
   size_t frame_floats, tool_floats;
   int64_t launches = 0, bytes = 0;
   std::vector<void*> allocs;
@@ -102,9 +104,9 @@ struct dsk_engine {
   int bwd_cur = 0;  // adjw index holding the adjoint of the current frame
   // sequences / graphs
   struct GraphSet {
-    cudaGraphExec_t fwd = nullptr, recompute = nullptr, bwd = nullptr;
-    int64_t n_launch[3] = {0, 0, 0};
-    int64_t kid[3][KID_COUNT] = {{0}};
+    cudaGraphExec_t fwd = nullptr, recompute = nullptr, bwd = nullptr, bwd_tape = nullptr;
+    int64_t n_launch[4] = {0, 0, 0, 0};
+    int64_t kid[4][KID_COUNT] = {{0}};
   };
   std::vector<GraphSet> graphs;
   bool use_graphs = true;
@@ -112,9 +114,13 @@ struct dsk_engine {
   StepArgs* d_args = nullptr;
   int epoch_base = 0;
   int* done = nullptr;
+  bool seq_use_tape = false;  // the backward sequence being enqueued restores grids from the slot's tape
   int pending_q = -1;  // fine-grained mode: last substep's grids still hold data
   bool pending_bwd = false, grids_valid = false;
   float* loss = nullptr;  // [B]
+  int tape_cap = 0;       // grid-tape capacity per step slot, in tiles (0: taping off)
+  bool tape_flags_stale = true;
+  std::vector<int> tape_overflow;  // host copy of the slots' overflow flags
 
   float* frame_of(float* base, int i) { return base + (size_t)i * frame_floats; }
   float* tools_of(float* base, int step) { return base + (size_t)step * tool_floats; }
@@ -226,6 +232,12 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
   e->H = c->max_steps;
   e->K = c->n_tools;
   e->slots = std::max(1, std::min(c->step_slots, c->max_steps));
+  if (c->grid_tape_mib > 0) {
+    size_t per_slot = ((size_t)c->grid_tape_mib << 20) / e->slots;
+    e->tape_cap = (int)std::min<size_t>(per_slot / 2052, (size_t)1 << 30);
+    if (e->tape_cap < c->substeps * 8) e->tape_cap = 0;
+  }
+  e->tape_overflow.assign(e->slots, 1);
   SimConst& k = e->k;
   memset(&k, 0, sizeof k);
   k.n = c->n_grid;
@@ -268,6 +280,7 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
     fill_tool(e->h_tools[i], c->tools[i]);
     e->A += c->tools[i].action_dim;
     e->ncols += c->tools[i].type == DSK_TOOL_GRIPPER ? 2 : 1;
+    e->n_frames = std::max(1, e->ncols);
     if (c->tools[i].type < 0 || c->tools[i].type > DSK_TOOL_KNIFE) {
       delete e;
       return fail("unknown tool type %d", c->tools[i].type);
@@ -290,6 +303,13 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
       DA(s.perm, k.stride);
       DA(s.poses, (size_t)(e->S + 1) * e->tool_floats);
       DA(s.cidx, (size_t)e->B * (e->S + 1) * std::max(1, k.npairs));
+      if (e->tape_cap > 0) {
+        s.tape.cap = e->tape_cap;
+        DA(s.tape.base, e->S + 1);
+        DA(s.tape.list, e->tape_cap);
+        DA(s.tape.data, (size_t)e->tape_cap * 128);
+        DA(s.tape.overflow, 1);
+      }
     }
     DA(e->cell_count, (size_t)e->B * k.nnode);
     DA(e->key, k.stride);
@@ -409,7 +429,7 @@ static void invalidate_all(dsk_engine* e) {
 }
 static void drop_graphs(dsk_engine* e) {
   for (auto& g : e->graphs)
-    for (cudaGraphExec_t* x : {&g.fwd, &g.recompute, &g.bwd})
+    for (cudaGraphExec_t* x : {&g.fwd, &g.recompute, &g.bwd, &g.bwd_tape})
       if (*x) {
         cudaGraphExecDestroy(*x);
         *x = nullptr;
@@ -432,7 +452,8 @@ static int stage_in(dsk_engine* e, const float* src, size_t n, int on_device, si
   return 0;
 }
 
-static int grid_ctas(dsk_engine* e) { return 148 * 8; }
+static int grid_ctas(dsk_engine* e) { return 148 * 4; }
+static dim3 grid_block(dsk_engine* e) { return dim3(GRID_NODES, std::min(e->n_frames, MAX_FRAMES)); }
 
 // zero the grids of the last substep of a fine-grained (dsk_substep / dsk_substep_grad) sequence
 static int flush_pending_clear(dsk_engine* e) {
@@ -498,14 +519,14 @@ static int seq_substep(dsk_engine* e, StepSlot& s, int q, int j, bool write_stat
   float* fin = s.frames + (size_t)j * e->frame_floats;
   float* fout = s.frames + (size_t)(j + 1) * e->frame_floats;
   if (write_state)
-    KL(KID_P2G, k_p2g<true><<<nb, 128, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q));
+    KL(KID_P2G, k_p2g<true><<<nb, 128, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q, nullptr));
   else
-    KL(KID_P2G_RECOMPUTE, k_p2g<false><<<nb, 128, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q));
+    KL(KID_P2G_RECOMPUTE, k_p2g<false><<<nb, 128, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q, nullptr));
   bool clr = q > 0;
-  KL(KID_GRID, k_grid<<<grid_ctas(e), GRID_CTA, 0, e->qs>>>(
+  KL(KID_GRID, k_grid<<<grid_ctas(e), grid_block(e), 0, e->qs>>>(
                    k, e->d_tools, s.poses, j, e->G0[set], e->G0[set], tt.list, tt.count,
                    clr ? e->tile_list[prev] : nullptr, e->tile_count + (q & 3), clr ? e->G0[prev] : nullptr, nullptr,
-                   nullptr, e->tile_count + ((q + 3) & 3)));
+                   nullptr, e->tile_count + ((q + 3) & 3), write_state ? s.tape : GridTape{nullptr, nullptr, nullptr, nullptr, 0}, nullptr));
   if (write_state) KL(KID_G2P, k_g2p<<<nb, 128, 0, e->qs>>>(k, fin, fout, e->npart, e->G0[set]));
   LAUNCH_CHECK();
   return 0;
@@ -547,16 +568,25 @@ static int seq_substep_grad(dsk_engine* e, StepSlot& s, int q, int j) {
   float* fnext = s.frames + (size_t)(j + 1) * e->frame_floats;
   float* ain = e->adjw[e->bwd_cur];
   float* aout = e->adjw[e->bwd_cur ^ 1];
-  KL(KID_P2G_RECOMPUTE, k_p2g<false><<<nb, 128, 0, e->qs>>>(k, fin, nullptr, s.mat, e->npart, e->G0[set], tt, e->d_args, q));
   bool clr = q > 0;
-  KL(KID_GRID_RECOMPUTE, k_grid<<<grid_ctas(e), GRID_CTA, 0, e->qs>>>(
+  const int* run_if = nullptr;
+  if (e->seq_use_tape) {
+    // complete tape: restore the grids; the two recompute kernels below then return at once
+    KL(KID_GRID_RECOMPUTE, k_tape_restore<<<grid_ctas(e), GRID_NODES, 0, e->qs>>>(
+                               k, s.tape, j, e->G0[set], e->Gv[set], tt.list, tt.count,
+                               clr ? e->tile_list[prev] : nullptr, e->tile_count + (q & 3), clr ? e->G0[prev] : nullptr,
+                               clr ? e->Gv[prev] : nullptr, clr ? e->Ga[prev] : nullptr, e->tile_count + ((q + 3) & 3)));
+    run_if = s.tape.overflow;
+  }
+  KL(KID_P2G_RECOMPUTE, k_p2g<false><<<nb, 128, 0, e->qs>>>(k, fin, nullptr, s.mat, e->npart, e->G0[set], tt, e->d_args, q, run_if));
+  KL(KID_GRID_RECOMPUTE, k_grid<<<grid_ctas(e), grid_block(e), 0, e->qs>>>(
                              k, e->d_tools, s.poses, j, e->G0[set], e->Gv[set], tt.list, tt.count,
                              clr ? e->tile_list[prev] : nullptr, e->tile_count + (q & 3), clr ? e->G0[prev] : nullptr,
-                             clr ? e->Gv[prev] : nullptr, clr ? e->Ga[prev] : nullptr, e->tile_count + ((q + 3) & 3)));
+                             clr ? e->Gv[prev] : nullptr, clr ? e->Ga[prev] : nullptr, e->tile_count + ((q + 3) & 3),
+                             GridTape{nullptr, nullptr, nullptr, nullptr, 0}, run_if));
   KL(KID_G2P_ADJ, k_g2p_adj<<<nb, 128, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
-  KL(KID_GRID_ADJ, k_grid_adj<<<grid_ctas(e), GRID_CTA, 0, e->qs>>>(k, e->d_tools, s.poses, j, e->G0[set], e->Ga[set],
-                                                                    tt.list, tt.count, e->pose_adj, nullptr, nullptr,
-                                                                    nullptr, nullptr, nullptr, nullptr));
+  KL(KID_GRID_ADJ, k_grid_adj<<<grid_ctas(e), grid_block(e), 0, e->qs>>>(k, e->d_tools, s.poses, j, e->G0[set], e->Ga[set],
+                                                                      tt.list, tt.count, e->pose_adj));
   KL(KID_P2G_ADJ, k_p2g_adj<<<nb, 128, 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]));
   LAUNCH_CHECK();
   e->bwd_cur ^= 1;
@@ -575,9 +605,10 @@ static int seq_end_backward(dsk_engine* e, StepSlot& s) {
 }
 
 // ---- whole sequences, eager or as a replayed graph ---------------------------------------------------------------
-enum SeqKind { SEQ_FWD, SEQ_RECOMPUTE, SEQ_BWD };
+enum SeqKind { SEQ_FWD, SEQ_RECOMPUTE, SEQ_BWD, SEQ_BWD_TAPE };
 static int enqueue_sequence(dsk_engine* e, StepSlot& s, SeqKind kind) {
-  if (kind == SEQ_BWD) {
+  if (kind == SEQ_BWD || kind == SEQ_BWD_TAPE) {
+    e->seq_use_tape = kind == SEQ_BWD_TAPE;
     if (seq_begin_backward(e, s)) return -1;
     for (int q = 0; q < e->S; q++)
       if (seq_substep_grad(e, s, q, e->S - 1 - q)) return -1;
@@ -599,7 +630,7 @@ static int run_sequence(dsk_engine* e, int slot_idx, SeqKind kind) {
     return enqueue_sequence(e, s, kind);
   }
   dsk_engine::GraphSet& g = e->graphs[slot_idx];
-  cudaGraphExec_t* ex = kind == SEQ_FWD ? &g.fwd : (kind == SEQ_RECOMPUTE ? &g.recompute : &g.bwd);
+  cudaGraphExec_t* ex = kind == SEQ_FWD ? &g.fwd : (kind == SEQ_RECOMPUTE ? &g.recompute : (kind == SEQ_BWD ? &g.bwd : &g.bwd_tape));
   if (!*ex) {
     int64_t l0 = e->launches;
     int64_t kl0[KID_COUNT];
@@ -812,6 +843,7 @@ int dsk_forward_step(dsk_engine* e, int src_step, int dst_step, int action_step)
   s.src_step = -1;
   s.action_step = action_step;
   if (run_sequence(e, si, SEQ_FWD)) return -1;
+  s.tape_written = true;
   invalidate_slots(e, dst_step);
   // the slot's substep frames can serve backward_step(src_step) iff the step was (src, src+?, src) shaped
   s.src_step = (dst_step != src_step && action_step == src_step) ? src_step : -1;
@@ -830,9 +862,10 @@ int dsk_backward_step(dsk_engine* e, int step) {
     s.action_step = step;
     if (run_sequence(e, si, SEQ_RECOMPUTE)) return -1;
     s.src_step = step;
+    s.tape_written = true;
   }
   if (push_args(e, make_args(e, step, step, step, step))) return -1;
-  if (run_sequence(e, si, SEQ_BWD)) return -1;
+  if (run_sequence(e, si, (e->tape_cap > 0 && s.tape_written) ? SEQ_BWD_TAPE : SEQ_BWD)) return -1;
   e->last_bwd_frame = -1;
   e->last_substep_slot = si;
   return 0;
@@ -892,6 +925,7 @@ int dsk_substep_grad(dsk_engine* e, int f) {
   } else if (flush_pending_clear(e)) {
     return -1;
   }
+  e->seq_use_tape = false;   // fine-grained adjoint substeps always recompute (their grids stay inspectable)
   if (seq_substep_grad(e, s, 0, j)) return -1;
   e->pending_q = 0;
   e->pending_bwd = true;

@@ -74,69 +74,173 @@ __global__ void __launch_bounds__(128)
   store_v3(adj_out, CX, k.stride, gid, gx);
 }
 
-// grid_op.grad over the active tiles.  G0: (momentum, mass) of the recomputed p2g.  Ga: in = adjoint of
-// grid_v_out (xyz), out = adjoint of (grid_v_in, grid_m), in place.  pose_adj: [B][S+1][K][8] accumulators.
-__global__ void __launch_bounds__(GRID_CTA)
+// adjoint of contact_response given the geometry (D, cv, influence): returns g(v_in), outputs g(D), g(cv), g(influence)
+DSK_DEV float3 contact_response_adj(float3 v, float3 D, float3 cv, float influence, float friction, bool eps14,
+                                    float3 gout, float3& gD, float3& gcv, float& ginfl) {
+  float3 u = v - cv;
+  float nc = dot(u, D);
+  float mn = tmin(nc, 0.f);
+  float3 t = u - mn * D;
+  float tn = sqrtf(dot(t, t) + (eps14 ? 1e-14f : 1e-8f));
+  float a2 = tn + nc * friction;
+  float mx = tmax(0.f, a2);
+  bool flag = (nc < 0.f) && (sqrtf(dot(t, t)) > 1e-30f);
+  float3 q = (1.f / tn) * t;
+  float3 t2 = flag ? mx * q : t;
+  gcv = gout;
+  float3 gu = (1.f - influence) * gout;
+  ginfl = dot(gout, t2 - u);
+  float3 gt2 = influence * gout;
+  float3 gt = f3(0, 0, 0);
+  float gnc = 0.f;
+  if (flag) {
+    float3 gq = mx * gt2;
+    float gmx = dot(gt2, q);
+    float ga2 = (a2 < 0.f) ? 0.f : gmx;
+    float gtn = ga2 - dot(gq, t) / (tn * tn);
+    gt += (1.f / tn) * gq;
+    gnc += ga2 * friction;
+    gt += (gtn / tn) * t;
+  } else {
+    gt += gt2;
+  }
+  gu += gt;
+  float gmn = -dot(gt, D);
+  gD = (-mn) * gt;
+  if (nc < 0.f) gnc += gmn;
+  gu += gnc * D;
+  gD += gnc * u;
+  gcv -= gu;
+  return gu;
+}
+struct ContactGeomAdj {   // per (node, frame), shared memory
+  float3 gD, gcv;
+  float gdist;
+};
+
+// grid_op.grad over the active tiles, blockDim = (64, n_frames).  G0: (momentum, mass) of the recomputed p2g.
+// Ga: in = adjoint of grid_v_out (xyz), out = adjoint of (grid_v_in, grid_m), in place.
+// pose_adj: [B][S+1][K][8] accumulators.
+__global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
     k_grid_adj(SimConst k, const ToolParams* __restrict__ tools, const float* __restrict__ poses, int j,
                const float4* __restrict__ G0, float4* __restrict__ Ga, const int* __restrict__ list,
-               const int* __restrict__ count, float* __restrict__ pose_adj,
-               const int* __restrict__ clr_list, const int* __restrict__ clr_count, float4* clr0, float4* clr1,
-               float4* clr2, int* zero_count) {
+               const int* __restrict__ count, float* __restrict__ pose_adj) {
   __shared__ ToolParams sT[DSK_MAX_TOOLS];
-  for (int i = threadIdx.x; i < k.K * (int)(sizeof(ToolParams) / 4); i += blockDim.x)
-    ((int*)sT)[i] = ((const int*)tools)[i];
+  __shared__ FrameTable ft;
+  __shared__ TileFrames tf;
+  __shared__ ContactGeom geo[MAX_FRAMES][GRID_NODES];
+  __shared__ ContactGeomAdj gadj[MAX_FRAMES][GRID_NODES];
+  __shared__ float red[MAX_FRAMES][2][14];
+  __shared__ int any_contact[MAX_FRAMES];
+  const int l = threadIdx.x, y = threadIdx.y, tid = y * GRID_NODES + l, nthr = GRID_NODES * blockDim.y;
+  for (int i = tid; i < k.K * (int)(sizeof(ToolParams) / 4); i += nthr) ((int*)sT)[i] = ((const int*)tools)[i];
   __syncthreads();
-  if (blockIdx.x == 0 && threadIdx.x == 0 && zero_count) *zero_count = 0;
-  if (clr_list) clear_tiles(k, clr_list, *clr_count, clr0, clr1, clr2);
+  if (tid == 0) build_frame_table(k, sT, ft);
+  __syncthreads();
   int n_active = *count;
   for (int it = blockIdx.x; it < n_active; it += gridDim.x) {
     int gt = list[it];
     int env = gt / k.ntile, tile = gt - env * k.ntile;
-    size_t o = ((size_t)gt << 6) + threadIdx.x;
-    float4 gin = G0[o];
-    float4 ga4 = Ga[o];
-    bool live = gin.w > k.m_eps;
     int tz = tile % k.nt, ty = (tile / k.nt) % k.nt, tx = tile / (k.nt * k.nt);
-    int l = threadIdx.x;
+    size_t o = ((size_t)gt << 6) + l;
+    float4 gin = G0[o];
+    bool live = gin.w > k.m_eps;
     int I0 = tx * 4 + (l >> 4), I1 = ty * 4 + ((l >> 2) & 3), I2 = tz * 4 + (l & 3);
-    float inv = live ? 1.f / gin.w : 0.f;
     float3 gp = f3(mul_rn((float)I0, k.dx), mul_rn((float)I1, k.dx), mul_rn((float)I2, k.dx));
-    const float* pa = poses + ((size_t)(env * (k.S + 1) + j) * k.K) * 8;
-    const float* pb = pa + (size_t)k.K * 8;
-    float3 vs[DSK_MAX_TOOLS + 1];
-    float3 g = f3(0.f, 0.f, 0.f);
-    if (live) {
-      float3 v = f3(inv * gin.x + k.grav[0], inv * gin.y + k.grav[1], inv * gin.z + k.grav[2]);
-      for (int t = 0; t < k.K; t++) {
-        vs[t] = v;
-        v = tool_collide(sT[t], load_pose(pa + t * 8), load_pose(pb + t * 8), gp, v, k.dt);
-      }
-      g = grid_boundary_adj(k, I0, I1, I2, v, f3(ga4.x, ga4.y, ga4.z));
+    if (l == 0 && y < ft.n) {
+      prepare_tile_frame(k, sT, ft, y, poses, env, j, tx, ty, tz, tf);
+      any_contact[y] = 0;
     }
-    float* adj0 = pose_adj + ((size_t)(env * (k.S + 1) + j) * k.K) * 8;
-    float* adj1 = adj0 + (size_t)k.K * 8;
-    for (int t = k.K - 1; t >= 0; t--) {
-      PoseAdj a0 = pose_adj_zero(), a1 = pose_adj_zero();
-      if (live) g = tool_collide_adj(sT[t], load_pose(pa + t * 8), load_pose(pb + t * 8), gp, vs[t], k.dt, g, a0, a1);
-      float vals[16] = {a0.p.x, a0.p.y, a0.p.z, a0.q.w, a0.q.x, a0.q.y, a0.q.z, a0.gap,
-                        a1.p.x, a1.p.y, a1.p.z, a1.q.w, a1.q.x, a1.q.y, a1.q.z, a1.gap};
-      float mag = 0.f;
-#pragma unroll
-      for (int q = 0; q < 16; q++) mag += fabsf(vals[q]);
-      if (__any_sync(0xffffffffu, mag != 0.f)) {
-#pragma unroll
-        for (int q = 0; q < 16; q++) {
-          float s = warp_sum(vals[q]);
-          if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd((q < 8 ? adj0 : adj1) + t * 8 + (q & 7), s);
+    __syncthreads();
+    // phase A: contact geometry per (node, frame)
+    if (y < ft.n) {
+      if (live && tf.active[y]) {
+        const ToolParams& T = sT[ft.tool[y]];
+        contact_geometry(T, ft.flag[y] != 0.f ? SDF_BOX : sdf_kind(T.type), tf.F0[y], tf.F1[y], gp, k.dt, geo[y][l]);
+        if (geo[y][l].influence >= 0.f) any_contact[y] = 1;
+      } else {
+        geo[y][l].influence = -1.f;
+      }
+    }
+    __syncthreads();
+    // phase B: velocity chain forward and backward (one thread per node)
+    if (y == 0) {
+      float4 outv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) {
+        float4 ga4 = Ga[o];
+        float inv = 1.f / gin.w;
+        float3 vs[MAX_FRAMES];
+        float3 v = f3(inv * gin.x + k.grav[0], inv * gin.y + k.grav[1], inv * gin.z + k.grav[2]);
+        for (int f = 0; f < ft.n; f++) {
+          vs[f] = v;
+          const ContactGeom& c = geo[f][l];
+          if (c.influence >= 0.f) v = contact_response(v, c.D, c.cv, c.influence, sT[ft.tool[f]].friction, ft.flag[f] != 0.f);
         }
+        float3 g = grid_boundary_adj(k, I0, I1, I2, v, f3(ga4.x, ga4.y, ga4.z));
+        for (int f = ft.n - 1; f >= 0; f--) {
+          const ContactGeom& c = geo[f][l];
+          if (c.influence >= 0.f) {
+            float ginfl;
+            ContactGeomAdj& a = gadj[f][l];
+            g = contact_response_adj(vs[f], c.D, c.cv, c.influence, sT[ft.tool[f]].friction, ft.flag[f] != 0.f, g, a.gD,
+                                     a.gcv, ginfl);
+            // influence = min(exp(-dist*softness), 1): exp(..) = influence when it is < 1
+            float soft = sT[ft.tool[f]].softness;
+            a.gdist = (c.influence < 1.f) ? (-soft * c.influence * ginfl) : 0.f;
+          }
+        }
+        outv = make_float4(inv * g.x, inv * g.y, inv * g.z, -(inv * inv) * (gin.x * g.x + gin.y * g.y + gin.z * g.z));
+      }
+      Ga[o] = outv;
+    }
+    __syncthreads();
+    // phase C: geometry adjoints per (node, frame), reduced over the tile's nodes
+    if (y < ft.n && any_contact[y]) {
+      FrameAdj a0 = frame_adj_zero(), a1 = frame_adj_zero();
+      if (geo[y][l].influence >= 0.f) {
+        const ToolParams& T = sT[ft.tool[y]];
+        int kind = ft.flag[y] != 0.f ? SDF_BOX : sdf_kind(T.type);
+        const ContactGeomAdj& a = gadj[y][l];
+        float3 unused = f3(0, 0, 0);
+        frame_normal_adj(T, kind, tf.F0[y], gp, a.gD, a0, unused);
+        frame_collider_v_adj(tf.F0[y], tf.F1[y], gp, k.dt, a.gcv, a0, a1);
+        frame_sdf_adj(T, kind, tf.F0[y], gp, a.gdist, a0, unused);
+      }
+      float vals[14] = {a0.o.x, a0.o.y, a0.o.z, a0.q.w, a0.q.x, a0.q.y, a0.q.z,
+                        a1.o.x, a1.o.y, a1.o.z, a1.q.w, a1.q.x, a1.q.y, a1.q.z};
+#pragma unroll
+      for (int q = 0; q < 14; q++) {
+        float s = warp_sum(vals[q]);
+        if ((l & 31) == 0) red[y][l >> 5][q] = s;
       }
     }
-    float4 outv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) {
-      // v0 = (1/m) * v_in  ->  g(v_in) = g/m ; g(m) = -(v_in . g)/m^2
-      outv = make_float4(inv * g.x, inv * g.y, inv * g.z, -(inv * inv) * (gin.x * g.x + gin.y * g.y + gin.z * g.z));
+    __syncthreads();
+    if (l == 0 && y < ft.n && any_contact[y]) {
+      FrameAdj a0, a1;
+      float r[14];
+      for (int q = 0; q < 14; q++) r[q] = red[y][0][q] + red[y][1][q];
+      a0.o = f3(r[0], r[1], r[2]); a0.q.w = r[3]; a0.q.x = r[4]; a0.q.y = r[5]; a0.q.z = r[6];
+      a1.o = f3(r[7], r[8], r[9]); a1.q.w = r[10]; a1.q.x = r[11]; a1.q.y = r[12]; a1.q.z = r[13];
+      int t = ft.tool[y];
+      const float* pa = poses + ((size_t)(env * (k.S + 1) + j) * k.K + t) * 8;
+      PoseAdj g0 = pose_adj_zero(), g1 = pose_adj_zero();
+      if (ft.flag[y] != 0.f) {   // jaw_frame_adj is linear in the frame adjoint: apply it after the reduction
+        jaw_frame_adj(load_pose(pa), ft.flag[y], a0, g0);
+        jaw_frame_adj(load_pose(pa + (size_t)k.K * 8), ft.flag[y], a1, g1);
+      } else {
+        tool_frame_adj(a0, g0);
+        tool_frame_adj(a1, g1);
+      }
+      float* adj0 = pose_adj + ((size_t)(env * (k.S + 1) + j) * k.K + t) * 8;
+      float* adj1 = adj0 + (size_t)k.K * 8;
+      float v0[8] = {g0.p.x, g0.p.y, g0.p.z, g0.q.w, g0.q.x, g0.q.y, g0.q.z, g0.gap};
+      float v1[8] = {g1.p.x, g1.p.y, g1.p.z, g1.q.w, g1.q.x, g1.q.y, g1.q.z, g1.gap};
+      for (int q = 0; q < 8; q++) {
+        if (v0[q] != 0.f) atomicAdd(adj0 + q, v0[q]);
+        if (v1[q] != 0.f) atomicAdd(adj1 + q, v1[q]);
+      }
     }
-    Ga[o] = outv;
+    __syncthreads();
   }
 }
 

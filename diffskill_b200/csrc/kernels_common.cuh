@@ -107,6 +107,15 @@ struct StepArgs {
 };
 __global__ void k_set_args(StepArgs* dst, StepArgs v) { *dst = v; }
 
+// Compact per-step record of the active grid tiles of every substep (see k_grid / k_tape_restore)
+struct GridTape {
+  int* base;      // [S+1] prefix offsets into list/data (null: taping off)
+  int* list;      // [cap] packed env*ntile + tile
+  float4* data;   // [cap][2][64]: (momentum, mass) then (velocity, mass)
+  int* overflow;  // set when a step needed more than cap tiles
+  int cap;
+};
+
 // Per-substep sparse-grid bookkeeping: tiles touched by a stencil are appended (once) to the
 // active list of the current epoch.
 struct TileTrack {
@@ -155,19 +164,53 @@ DSK_DEV void butterfly_first(bool mine, bool hi, F& val, float4* acc) {
   acc[Q] = f4add(f4sel(hi, b, a), f4shfl_xor(f4sel(hi, a, b), 16));
 }
 // val(i,j,l) -> float4 contribution of this lane to stencil node (i,j,l); must be callable by every lane
+DSK_DEV float4 f4shfl_down(float4 v, int d) {
+  return make_float4(__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d),
+                     __shfl_down_sync(0xffffffffu, v.z, d), __shfl_down_sync(0xffffffffu, v.w, d));
+}
+// val(i,j,l) -> float4 contribution of this lane to stencil node (i,j,l); must be callable by every lane.
+// Three regimes, chosen per warp from the number of runs of equal cell keys:
+//   <= 2 runs : recursive-halving butterfly per run (dense dough: a whole warp shares one cell)
+//   > 2 runs  : ONE segmented shuffle-down reduction over all runs at once (log2(longest run) steps per node),
+//               run heads issue the vector reductions
 template <class F>
 DSK_DEV void warp_scatter27(const SimConst& k, bool active, const Stencil& s, float4* __restrict__ Ge,
                             const TileTrack& tt, bool mark, int env, int epoch, F val) {
   const int lane = threadIdx.x & 31;
   int key = active ? node_offset(s.bx, s.by, s.bz, k.nt) : -1;
-  unsigned todo = __ballot_sync(0xffffffffu, active);
+  unsigned act = __ballot_sync(0xffffffffu, active);
+  if (!act) return;
+  int prev = __shfl_up_sync(0xffffffffu, key, 1);
+  bool head = active && (lane == 0 || prev != key);
+  unsigned heads = __ballot_sync(0xffffffffu, head);
+  if (mark && head) mark_stencil_tiles(k, tt, env, s, epoch);
+  if (__popc(heads) > 2) {
+    unsigned above = lane == 31 ? 0u : (heads & (0xffffffffu << (lane + 1)));
+    int next_head = above ? (__ffs(above) - 1) : 32;
+    int end = min(next_head - 1, 31 - __clz(act));   // last lane of my run
+    int maxlen = __reduce_max_sync(0xffffffffu, head ? end - lane + 1 : 0);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int l = 0; l < 3; l++) {
+          float4 v = active ? val(i, j, l) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int d = 1; d < maxlen; d <<= 1) {
+            float4 t = f4shfl_down(v, d);
+            if (lane + d <= end) v = f4add(v, t);
+          }
+          if (head) red_add4(&Ge[s.ox[i] + s.oy[j] + s.oz[l]], v);
+        }
+    return;
+  }
+  unsigned todo = act;
   while (todo) {
     int leader = __ffs(todo) - 1;
     int lkey = __shfl_sync(0xffffffffu, key, leader);
     bool mine = active && key == lkey;
     unsigned grp = __ballot_sync(0xffffffffu, mine);
     todo &= ~grp;
-    if (mark && lane == leader) mark_stencil_tiles(k, tt, env, s, epoch);
     if (__popc(grp) < SCATTER_MIN_GROUP) {
       if (mine) {
 #pragma unroll

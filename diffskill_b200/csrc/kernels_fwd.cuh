@@ -73,7 +73,8 @@ template <bool WRITE_F>
 __global__ void __launch_bounds__(128)
     k_p2g(SimConst k, const float* __restrict__ fin, float* __restrict__ fout, const float* __restrict__ mat,
           const int* __restrict__ npart, float4* __restrict__ G, TileTrack tt, const StepArgs* __restrict__ args,
-          int q) {
+          int q, const int* __restrict__ run_if) {
+  if (run_if && *run_if == 0) return;   // adjoint recompute is skipped when the grid tape of the step is complete
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   int env = min(gid / k.Npad, k.B - 1), p = gid - env * k.Npad;   // a warp never straddles envs (Npad % 128 == 0)
   bool active = gid < k.stride && p < npart[env];
@@ -224,39 +225,166 @@ __global__ void __launch_bounds__(GRID_CTA)
   }
 }
 
+// ---- grid_op, parallel over (node, contact frame) --------------------------------------------------------------
+// A "contact frame" is one rigid SDF body: a tool, or one jaw of a gripper (primitives.py:507-511 applies the
+// two jaws sequentially).  The expensive geometry of a contact (signed distance, finite-difference normal,
+// collider velocity) depends on the node and the pose only -- not on the velocity flowing through the chain of
+// tools -- so it is evaluated by one thread per (node, frame); the velocity chain itself is a few dozen flops.
+// Frames whose SDF at the tile centre exceeds the tile radius plus the soft-contact cut-off are culled per tile.
+#define MAX_FRAMES 8
+struct FrameTable {   // built once per CTA
+  int n;              // number of contact frames
+  int tool[MAX_FRAMES];
+  float flag[MAX_FRAMES];   // -1 / +1 gripper jaw, 0 plain tool
+};
+DSK_DEV void build_frame_table(const SimConst& k, const ToolParams* sT, FrameTable& ft) {
+  int n = 0;
+  for (int t = 0; t < k.K; t++) {
+    if (sT[t].type == DSK_TOOL_GRIPPER) {
+      ft.tool[n] = t; ft.flag[n++] = -1.f;
+      ft.tool[n] = t; ft.flag[n++] = 1.f;
+    } else {
+      ft.tool[n] = t; ft.flag[n++] = 0.f;
+    }
+  }
+  ft.n = n;
+}
+DSK_DEV Frame frame_of_pose(const Pose& P, float flag) { return flag == 0.f ? tool_frame(P) : jaw_frame(P, flag); }
+struct ContactGeom {   // per (node, frame), shared memory
+  float influence;     // < 0: contact inactive
+  float3 D, cv;
+};
+struct TileFrames {    // per tile-iteration, shared memory
+  Frame F0[MAX_FRAMES], F1[MAX_FRAMES];
+  int active[MAX_FRAMES];
+};
+// thread (0, y) prepares frame y of the tile's env and decides whether the tile can touch it at all
+DSK_DEV void prepare_tile_frame(const SimConst& k, const ToolParams* sT, const FrameTable& ft, int y,
+                                const float* __restrict__ poses, int env, int j, int tx, int ty, int tz,
+                                TileFrames& tf) {
+  int t = ft.tool[y];
+  const float* a = poses + ((size_t)(env * (k.S + 1) + j) * k.K + t) * 8;
+  Pose P0 = load_pose(a), P1 = load_pose(a + (size_t)k.K * 8);
+  tf.F0[y] = frame_of_pose(P0, ft.flag[y]);
+  tf.F1[y] = frame_of_pose(P1, ft.flag[y]);
+  const ToolParams& T = sT[t];
+  int kind = ft.flag[y] != 0.f ? SDF_BOX : sdf_kind(T.type);
+  float3 c = f3(((float)(tx * 4) + 1.5f) * k.dx, ((float)(ty * 4) + 1.5f) * k.dx, ((float)(tz * 4) + 1.5f) * k.dx);
+  float d = frame_sdf(T, kind, tf.F0[y], c);
+  float reach = 2.6f * k.dx * 1.02f + 1e-4f + (T.softness > 0.f ? 2.302586f / T.softness : 0.f);
+  tf.active[y] = d <= reach;   // all SDFs here are 1-Lipschitz: beyond `reach` no node has dist<=0 or influence>0.1
+}
+DSK_DEV void contact_geometry(const ToolParams& T, int kind, const Frame& F0, const Frame& F1, float3 p, float dt,
+                              ContactGeom& g) {
+  float dist = frame_sdf(T, kind, F0, p);
+  float influence;
+  if (contact_active(dist, T.softness, influence)) {
+    g.influence = influence;
+    g.D = frame_normal(T, kind, F0, p);
+    g.cv = frame_collider_v(F0, F1, p, dt);
+  } else {
+    g.influence = -1.f;
+  }
+}
+
+#define GRID_NODES 64
 // grid_op over active tiles.  Gin holds (momentum, mass); Gout receives (velocity, mass) and may alias Gin.
-__global__ void __launch_bounds__(GRID_CTA)
+// blockDim = (64, n_frames).
+__global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
     k_grid(SimConst k, const ToolParams* __restrict__ tools, const float* __restrict__ poses, int j,
            const float4* Gin, float4* Gout, const int* __restrict__ list, const int* __restrict__ count,
            // tiles of the previous substep to zero (clear_grid), may be null
            const int* __restrict__ clr_list, const int* __restrict__ clr_count, float4* clr0, float4* clr1,
-           float4* clr2, int* zero_count) {
+           float4* clr2, int* zero_count, GridTape tape, const int* __restrict__ run_if) {
+  if (run_if && *run_if == 0) return;
   __shared__ ToolParams sT[DSK_MAX_TOOLS];
-  for (int i = threadIdx.x; i < k.K * (int)(sizeof(ToolParams) / 4); i += blockDim.x)
-    ((int*)sT)[i] = ((const int*)tools)[i];
+  __shared__ FrameTable ft;
+  __shared__ TileFrames tf;
+  __shared__ ContactGeom geo[MAX_FRAMES][GRID_NODES];
+  const int l = threadIdx.x, y = threadIdx.y, tid = y * GRID_NODES + l, nthr = GRID_NODES * blockDim.y;
+  for (int i = tid; i < k.K * (int)(sizeof(ToolParams) / 4); i += nthr) ((int*)sT)[i] = ((const int*)tools)[i];
   __syncthreads();
-  if (blockIdx.x == 0 && threadIdx.x == 0 && zero_count) *zero_count = 0;
-  if (clr_list) clear_tiles(k, clr_list, *clr_count, clr0, clr1, clr2);
+  if (tid == 0) build_frame_table(k, sT, ft);
+  if (blockIdx.x == 0 && tid == 0 && zero_count) *zero_count = 0;
+  if (clr_list && y == 0) clear_tiles(k, clr_list, *clr_count, clr0, clr1, clr2);
+  __syncthreads();
   int n_active = *count;
+  // grid tape: (momentum, mass) and velocity of every active tile are kept so that substep_grad need not
+  // recompute p2g + grid_op (mpm_simulator.py:330-333 does); tape.base[j] = first tape slot of substep j
+  int tb = 0;
+  if (tape.base) {
+    tb = j == 0 ? 0 : tape.base[j];
+    if (blockIdx.x == 0 && tid == 0) {
+      tape.base[j + 1] = tb + n_active;
+      bool over = tb + n_active > tape.cap;
+      if (j == 0) *tape.overflow = over ? 1 : 0;
+      else if (over) *tape.overflow = 1;
+    }
+  }
   for (int it = blockIdx.x; it < n_active; it += gridDim.x) {
     int gt = list[it];
     int env = gt / k.ntile, tile = gt - env * k.ntile;
-    size_t o = ((size_t)gt << 6) + threadIdx.x;
+    int tz = tile % k.nt, ty = (tile / k.nt) % k.nt, tx = tile / (k.nt * k.nt);
+    size_t o = ((size_t)gt << 6) + l;
     float4 g = Gin[o];
-    float3 vout = f3(0.f, 0.f, 0.f);
-    if (g.w > k.m_eps) {
-      int tz = tile % k.nt, ty = (tile / k.nt) % k.nt, tx = tile / (k.nt * k.nt);
-      int l = threadIdx.x;
-      int I0 = tx * 4 + (l >> 4), I1 = ty * 4 + ((l >> 2) & 3), I2 = tz * 4 + (l & 3);
-      float inv = 1.f / g.w;
-      float3 v = f3(inv * g.x + k.grav[0], inv * g.y + k.grav[1], inv * g.z + k.grav[2]);
-      float3 gp = f3(mul_rn((float)I0, k.dx), mul_rn((float)I1, k.dx), mul_rn((float)I2, k.dx));
-      const float* a = poses + ((size_t)(env * (k.S + 1) + j) * k.K) * 8;
-      const float* b = a + (size_t)k.K * 8;
-      for (int t = 0; t < k.K; t++) v = tool_collide(sT[t], load_pose(a + t * 8), load_pose(b + t * 8), gp, v, k.dt);
-      vout = grid_boundary(k, I0, I1, I2, v);
+    bool live = g.w > k.m_eps;
+    int I0 = tx * 4 + (l >> 4), I1 = ty * 4 + ((l >> 2) & 3), I2 = tz * 4 + (l & 3);
+    float3 gp = f3(mul_rn((float)I0, k.dx), mul_rn((float)I1, k.dx), mul_rn((float)I2, k.dx));
+    if (l == 0 && y < ft.n) prepare_tile_frame(k, sT, ft, y, poses, env, j, tx, ty, tz, tf);
+    __syncthreads();
+    if (y < ft.n) {
+      if (live && tf.active[y]) {
+        const ToolParams& T = sT[ft.tool[y]];
+        contact_geometry(T, ft.flag[y] != 0.f ? SDF_BOX : sdf_kind(T.type), tf.F0[y], tf.F1[y], gp, k.dt, geo[y][l]);
+      } else {
+        geo[y][l].influence = -1.f;
+      }
     }
-    Gout[o] = make_float4(vout.x, vout.y, vout.z, g.w);
+    __syncthreads();
+    if (y == 0) {
+      float3 vout = f3(0.f, 0.f, 0.f);
+      if (live) {
+        float inv = 1.f / g.w;
+        float3 v = f3(inv * g.x + k.grav[0], inv * g.y + k.grav[1], inv * g.z + k.grav[2]);
+        for (int f = 0; f < ft.n; f++) {
+          const ContactGeom& c = geo[f][l];
+          if (c.influence >= 0.f) v = contact_response(v, c.D, c.cv, c.influence, sT[ft.tool[f]].friction, ft.flag[f] != 0.f);
+        }
+        vout = grid_boundary(k, I0, I1, I2, v);
+      }
+      float4 go = make_float4(vout.x, vout.y, vout.z, g.w);
+      Gout[o] = go;
+      if (tape.base && tb + it < tape.cap) {
+        if (l == 0) tape.list[tb + it] = gt;
+        float4* d = tape.data + ((size_t)(tb + it) << 7);
+        d[l] = g;
+        d[64 + l] = go;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// substep_grad with a valid grid tape: put the taped (momentum, mass) and velocity tiles of substep j back into
+// the dense grids and rebuild the active-tile list -- replaces the p2g + grid_op recompute
+__global__ void __launch_bounds__(GRID_NODES)
+    k_tape_restore(SimConst k, GridTape tape, int j, float4* __restrict__ G0, float4* __restrict__ Gv,
+                   int* __restrict__ list, int* __restrict__ count,
+                   const int* __restrict__ clr_list, const int* __restrict__ clr_count, float4* clr0, float4* clr1,
+                   float4* clr2, int* zero_count) {
+  if (*tape.overflow) return;   // incomplete tape: the recompute kernels that follow take over
+  if (blockIdx.x == 0 && threadIdx.x == 0 && zero_count) *zero_count = 0;
+  if (clr_list) clear_tiles(k, clr_list, *clr_count, clr0, clr1, clr2);
+  int tb = j == 0 ? 0 : tape.base[j];
+  int n = tape.base[j + 1] - tb;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *count = n;
+  for (int it = blockIdx.x; it < n; it += gridDim.x) {
+    int gt = tape.list[tb + it];
+    if (threadIdx.x == 0) list[it] = gt;
+    size_t o = ((size_t)gt << 6) + threadIdx.x;
+    const float4* d = tape.data + ((size_t)(tb + it) << 7);
+    G0[o] = d[threadIdx.x];
+    Gv[o] = d[64 + threadIdx.x];
   }
 }
 

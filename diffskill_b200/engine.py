@@ -30,7 +30,7 @@ class Config(C.Structure):
     _fields_ = [('abi_version', C.c_int32), ('device', C.c_int32), ('n_envs', C.c_int32),
                 ('particle_capacity', C.c_int32), ('n_grid', C.c_int32), ('substeps', C.c_int32),
                 ('max_steps', C.c_int32), ('step_slots', C.c_int32), ('sort_particles', C.c_int32),
-                ('reserved0', C.c_int32),
+                ('grid_tape_mib', C.c_int32),
                 ('dt', C.c_double), ('dx', C.c_double), ('inv_dx', C.c_double), ('p_vol', C.c_double),
                 ('p_mass', C.c_double), ('mu', C.c_double), ('lam', C.c_double), ('yield_stress', C.c_double),
                 ('gravity', C.c_double * 3), ('ground_friction', C.c_double), ('lower_bound', C.c_double),
@@ -90,11 +90,12 @@ def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
-def make_config(scene: SceneSpec, n_envs, capacity, max_steps, step_slots, sort, softness, device):
+def make_config(scene: SceneSpec, n_envs, capacity, max_steps, step_slots, sort, softness, device, grid_tape_mib=0):
     c = Config()
     c.abi_version, c.device, c.n_envs, c.particle_capacity = ABI_VERSION, device, n_envs, capacity
     c.n_grid, c.substeps, c.max_steps, c.step_slots, c.sort_particles = \
         scene.n_grid, scene.substeps, max_steps, step_slots, int(sort)
+    c.grid_tape_mib = int(grid_tape_mib)
     c.dt, c.dx, c.inv_dx, c.p_vol, c.p_mass = scene.dt, scene.dx, scene.inv_dx, scene.p_vol, scene.p_mass
     c.mu, c.lam, c.yield_stress = scene.mu, scene.lam, scene.yield_stress
     c.gravity[:] = scene.gravity
@@ -122,7 +123,7 @@ class Engine:
     """One batched simulation engine (B envs sharing a scene).  Thin, 1:1 over the C ABI."""
 
     def __init__(self, scene: SceneSpec, n_envs=1, capacity=None, max_steps=64, step_slots=1, sort=True,
-                 softness=666., device=0):
+                 softness=666., device=0, grid_tape_mib=256):
         self.L = load_library()
         self.scene = scene
         self.B = int(n_envs)
@@ -133,7 +134,7 @@ class Engine:
         self.A = scene.action_dim
         self.n_grid = scene.n_grid
         self.device = device
-        self.cfg = make_config(scene, self.B, self.capacity, self.H, step_slots, sort, softness, device)
+        self.cfg = make_config(scene, self.B, self.capacity, self.H, step_slots, sort, softness, device, grid_tape_mib)
         h = C.c_void_p()
         self._ck(self.L.dsk_create(C.byref(self.cfg), C.byref(h)))
         self.h = h

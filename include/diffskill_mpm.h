@@ -81,7 +81,8 @@ typedef struct dsk_config {
   int32_t max_steps;         /* env-step horizon H: checkpoints 0..H are kept */
   int32_t step_slots;        /* substep-frame ring size in env steps (1 = pure checkpointing, H = full tape) */
   int32_t sort_particles;    /* 1: counting-sort particles by cell every env step */
-  int32_t reserved0;
+  int32_t grid_tape_mib;     /* device memory budget (MiB, all step slots) for taping the active grid tiles of every substep so
+                              * that the adjoint skips the p2g + grid_op recompute of mpm_simulator.py:330-333; 0 = off */
   double dt, dx, inv_dx, p_vol, p_mass;
   double mu, lam, yield_stress; /* initial per-particle fill, mpm_simulator.py:85-87 */
   double gravity[3];

@@ -163,10 +163,19 @@ def test_substep_backward_parity(name):
             oo.substep_grad(s)
             oo.L.orc_set_velocity_grad(oo.h, s, 1)
             res.append(collect(oo, s))
+        # A particle sitting exactly on the yield surface (|delta_gamma| ~ 1e-8, mpm_simulator.py:176-178) takes the
+        # other branch under a 1-ulp state difference and has a different (equally valid) gradient: exclude them.
+        sig = o64.get_svd()[2]
+        eps_ = np.log(np.maximum(sig, 0.05))
+        eh = eps_ - eps_.mean(1, keepdims=True)
+        dgamma = np.sqrt((eh ** 2).sum(1) + 1e-8) - scene.yield_stress / (2 * scene.mu)
+        keep = np.abs(dgamma) > 1e-5
+        assert keep.mean() > 0.99
         for k_ in mine:
-            worst[k_] = max(worst.get(k_, 0), relerr(mine[k_], res[0][k_]))
-            worst64[k_] = max(worst64.get(k_, 0), relerr(mine[k_], res[1][k_]))
-            floor[k_] = max(floor.get(k_, 0), relerr(res[0][k_], res[1][k_]))
+            sel = keep if k_ in ('gx', 'gv', 'gF', 'gC') else slice(None)
+            worst[k_] = max(worst.get(k_, 0), relerr(mine[k_][sel], res[0][k_][sel]))
+            worst64[k_] = max(worst64.get(k_, 0), relerr(mine[k_][sel], res[1][k_][sel]))
+            floor[k_] = max(floor.get(k_, 0), relerr(res[0][k_][sel], res[1][k_][sel]))
     fmt = lambda d: {k_: '%.1e' % e_ for k_, e_ in d.items()}
     print(name, 'vs_f32', fmt(worst), 'vs_f64', fmt(worst64), 'f32_vs_f64', fmt(floor))
     for k_ in worst:
