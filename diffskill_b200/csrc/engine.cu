@@ -82,7 +82,7 @@ struct dsk_engine {
   std::vector<int> h_npart;
   std::vector<StepSlot> slot;
   // sort scratch
-  int *cell_count = nullptr, *key = nullptr, *rank = nullptr;
+  int *cell_count = nullptr, *key = nullptr, *rank = nullptr, *scan_partial = nullptr;
   // grids: set index = epoch & 1
   float4 *G0[2], *Gv[2], *Ga[2];
   int *tile_epoch[2], *tile_list[2], *tile_count = nullptr;  // tile_count[4] ring
@@ -104,9 +104,9 @@ struct dsk_engine {
   int bwd_cur = 0;  // adjw index holding the adjoint of the current frame
   // sequences / graphs
   struct GraphSet {
-    cudaGraphExec_t fwd = nullptr, recompute = nullptr, bwd = nullptr, bwd_tape = nullptr;
-    int64_t n_launch[4] = {0, 0, 0, 0};
-    int64_t kid[4][KID_COUNT] = {{0}};
+    cudaGraphExec_t ex[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [kind*2 + full_sort]
+    int64_t n_launch[8] = {0};
+    int64_t kid[8][KID_COUNT] = {{0}};
   };
   std::vector<GraphSet> graphs;
   bool use_graphs = true;
@@ -118,6 +118,13 @@ struct dsk_engine {
   int pending_q = -1;  // fine-grained mode: last substep's grids still hold data
   bool pending_bwd = false, grids_valid = false;
   float* loss = nullptr;  // [B]
+  int* perm_cache = nullptr;   // permutation of the last full sort
+  int sort_age = 1 << 30, resort_interval = 1;   // >1 re-uses the last permutation (cheaper sort, more fragmented warps)
+  bool seq_full_sort = true;
+  bool big = false;   // enough particles to fill the machine: prefer occupancy over registers
+  cudaStream_t cap_side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool kin_join = false;
   int tape_cap = 0;       // grid-tape capacity per step slot, in tiles (0: taping off)
   bool tape_flags_stale = true;
   std::vector<int> tape_overflow;  // host copy of the slots' overflow flags
@@ -287,6 +294,7 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
     }
   }
   e->frame_floats = (size_t)FRAME_COMPS * k.stride;
+  e->big = (size_t)c->n_envs * c->particle_capacity >= 65536;
   e->tool_floats = (size_t)e->B * std::max(1, e->K) * 8;
   int rc = [&]() -> int {
     DA(e->ckpt, (size_t)(e->H + 1) * e->frame_floats);
@@ -313,6 +321,7 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
     }
     DA(e->cell_count, (size_t)e->B * k.nnode);
     DA(e->key, k.stride);
+    DA(e->scan_partial, (size_t)e->B * cdiv(k.nnode, SCAN_CHUNK));
     DA(e->rank, k.stride);
     for (int s = 0; s < 2; s++) {
       DA(e->G0[s], (size_t)e->B * k.nnode);
@@ -327,6 +336,11 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
     DA(e->loss, e->B);
     e->graphs.resize(e->slots);
     CK(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&e->cap_side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    DA(e->perm_cache, k.stride);
+    if (getenv("DSK_RESORT_INTERVAL")) e->resort_interval = std::max(1, atoi(getenv("DSK_RESORT_INTERVAL")));
     e->use_graphs = getenv("DSK_NO_GRAPHS") == nullptr;
     DA(e->d_tools, std::max(1, e->K));
     DA(e->tool_ckpt, (size_t)(e->H + 1) * e->tool_floats);
@@ -363,6 +377,9 @@ int dsk_destroy(dsk_engine* e) {
   cudaStreamSynchronize(e->stream);
   drop_graphs(e);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  if (e->cap_side) cudaStreamDestroy(e->cap_side);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
   for (auto& r : e->prof) {
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
@@ -429,10 +446,10 @@ static void invalidate_all(dsk_engine* e) {
 }
 static void drop_graphs(dsk_engine* e) {
   for (auto& g : e->graphs)
-    for (cudaGraphExec_t* x : {&g.fwd, &g.recompute, &g.bwd, &g.bwd_tape})
-      if (*x) {
-        cudaGraphExecDestroy(*x);
-        *x = nullptr;
+    for (auto& x : g.ex)
+      if (x) {
+        cudaGraphExecDestroy(x);
+        x = nullptr;
       }
 }
 
@@ -498,15 +515,37 @@ static int push_args(dsk_engine* e, const StepArgs& a) {
 static int seq_begin_forward(dsk_engine* e, StepSlot& s) {
   SimConst& k = e->k;
   int nb = cdiv(k.stride, 256);
-  if (e->cfg.sort_particles) {
-    CK(cudaMemsetAsync(e->cell_count, 0, (size_t)e->B * k.nnode * 4, e->qs));
-    KL(KID_SORT, k_sort_bin<<<nb, 256, 0, e->qs>>>(k, e->d_args, e->npart, e->cell_count, e->key, e->rank));
-    KL(KID_SORT, k_sort_scan<<<e->B, 1024, 0, e->qs>>>(k, e->cell_count));
+  bool capturing = e->qs == e->cap_stream;
+  // tool kinematics of the whole step depends on the tool state and the action only: in a captured graph it runs
+  // on a parallel branch next to the sort and the first p2g, joined before the first grid_op
+  if (e->K > 0) {
+    if (capturing) {
+      CK(cudaEventRecord(e->ev_fork, e->qs));
+      CK(cudaStreamWaitEvent(e->cap_side, e->ev_fork, 0));
+      KL(KID_KINEMATICS, k_kinematics<<<e->B, KIN_CTA, 0, e->cap_side>>>(k, e->d_tools, e->d_args, e->rand_num, s.poses, s.cidx));
+      CK(cudaEventRecord(e->ev_join, e->cap_side));
+      e->kin_join = true;
+    } else {
+      KL(KID_KINEMATICS, k_kinematics<<<e->B, KIN_CTA, 0, e->qs>>>(k, e->d_tools, e->d_args, e->rand_num, s.poses, s.cidx));
+    }
   }
-  KL(KID_SORT, k_sort_scatter<<<nb, 256, 0, e->qs>>>(k, e->d_args, e->mat, e->npart, e->cell_count, e->key, e->rank,
-                                                     e->cfg.sort_particles, s.frames, s.mat, s.perm));
-  if (e->K > 0)
-    KL(KID_KINEMATICS, k_kinematics<<<e->B, KIN_CTA, 0, e->qs>>>(k, e->d_tools, e->d_args, e->rand_num, s.poses, s.cidx));
+  if (e->cfg.sort_particles && !e->seq_full_sort) {
+    KL(KID_SORT, k_apply_perm<<<nb, 256, 0, e->qs>>>(k, e->d_args, e->mat, e->npart, e->perm_cache, s.frames, s.mat, s.perm));
+  } else {
+    if (e->cfg.sort_particles) {
+      CK(cudaMemsetAsync(e->cell_count, 0, (size_t)e->B * k.nnode * 4, e->qs));
+      KL(KID_SORT, k_sort_bin<<<nb, 256, 0, e->qs>>>(k, e->d_args, e->npart, e->cell_count, e->key, e->rank));
+      {
+        dim3 sg(cdiv(k.nnode, SCAN_CHUNK), e->B);
+        KL(KID_SORT, k_scan_partial<<<sg, SCAN_CTA, 0, e->qs>>>(k, e->cell_count, e->scan_partial));
+        KL(KID_SORT, k_scan_chunks<<<sg, SCAN_CTA, 0, e->qs>>>(k, e->cell_count, e->scan_partial));
+      }
+    }
+    KL(KID_SORT, k_sort_scatter<<<nb, 256, 0, e->qs>>>(k, e->d_args, e->mat, e->npart, e->cell_count, e->key, e->rank,
+                                                       e->cfg.sort_particles, s.frames, s.mat, s.perm));
+    if (e->cfg.sort_particles)
+      CK(cudaMemcpyAsync(e->perm_cache, s.perm, (size_t)k.stride * 4, cudaMemcpyDeviceToDevice, e->qs));
+  }
   LAUNCH_CHECK();
   return 0;
 }
@@ -519,10 +558,17 @@ static int seq_substep(dsk_engine* e, StepSlot& s, int q, int j, bool write_stat
   float* fin = s.frames + (size_t)j * e->frame_floats;
   float* fout = s.frames + (size_t)(j + 1) * e->frame_floats;
   if (write_state)
-    KL(KID_P2G, k_p2g<true><<<nb, 128, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q, nullptr));
+    if (e->big)
+      KL(KID_P2G, k_p2g<true, 3><<<nb, 128, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q, nullptr));
+    else
+      KL(KID_P2G, k_p2g<true, 1><<<nb, 128, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q, nullptr));
   else
-    KL(KID_P2G_RECOMPUTE, k_p2g<false><<<nb, 128, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q, nullptr));
+    KL(KID_P2G_RECOMPUTE, k_p2g<false, 3><<<nb, 128, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q, nullptr));
   bool clr = q > 0;
+  if (e->kin_join) {
+    CK(cudaStreamWaitEvent(e->qs, e->ev_join, 0));
+    e->kin_join = false;
+  }
   KL(KID_GRID, k_grid<<<grid_ctas(e), grid_block(e), 0, e->qs>>>(
                    k, e->d_tools, s.poses, j, e->G0[set], e->G0[set], tt.list, tt.count,
                    clr ? e->tile_list[prev] : nullptr, e->tile_count + (q & 3), clr ? e->G0[prev] : nullptr, nullptr,
@@ -578,13 +624,16 @@ static int seq_substep_grad(dsk_engine* e, StepSlot& s, int q, int j) {
                                clr ? e->Gv[prev] : nullptr, clr ? e->Ga[prev] : nullptr, e->tile_count + ((q + 3) & 3)));
     run_if = s.tape.overflow;
   }
-  KL(KID_P2G_RECOMPUTE, k_p2g<false><<<nb, 128, 0, e->qs>>>(k, fin, nullptr, s.mat, e->npart, e->G0[set], tt, e->d_args, q, run_if));
+  KL(KID_P2G_RECOMPUTE, k_p2g<false, 3><<<nb, 128, 0, e->qs>>>(k, fin, nullptr, s.mat, e->npart, e->G0[set], tt, e->d_args, q, run_if));
   KL(KID_GRID_RECOMPUTE, k_grid<<<grid_ctas(e), grid_block(e), 0, e->qs>>>(
                              k, e->d_tools, s.poses, j, e->G0[set], e->Gv[set], tt.list, tt.count,
                              clr ? e->tile_list[prev] : nullptr, e->tile_count + (q & 3), clr ? e->G0[prev] : nullptr,
                              clr ? e->Gv[prev] : nullptr, clr ? e->Ga[prev] : nullptr, e->tile_count + ((q + 3) & 3),
                              GridTape{nullptr, nullptr, nullptr, nullptr, 0}, run_if));
-  KL(KID_G2P_ADJ, k_g2p_adj<<<nb, 128, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
+  if (e->big)
+    KL(KID_G2P_ADJ, k_g2p_adj<3><<<nb, 128, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
+  else
+    KL(KID_G2P_ADJ, k_g2p_adj<1><<<nb, 128, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
   KL(KID_GRID_ADJ, k_grid_adj<<<grid_ctas(e), grid_block(e), 0, e->qs>>>(k, e->d_tools, s.poses, j, e->G0[set], e->Ga[set],
                                                                       tt.list, tt.count, e->pose_adj));
   KL(KID_P2G_ADJ, k_p2g_adj<<<nb, 128, 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]));
@@ -595,8 +644,12 @@ static int seq_substep_grad(dsk_engine* e, StepSlot& s, int q, int j) {
 static int seq_end_backward(dsk_engine* e, StepSlot& s) {
   SimConst& k = e->k;
   if (e->K > 0) {
-    size_t sh = (size_t)(e->S + 1) * e->K * 8 * 4;
-    KL(KID_KINEMATICS_ADJ, k_kinematics_adj<<<e->B, 32, sh, e->qs>>>(k, e->d_tools, s.poses, s.cidx, e->rand_num, e->d_args, e->pose_adj));
+    size_t sh = ((size_t)(e->S + 1) * e->K * 8 + (size_t)e->S * e->K * 128) * 4;
+    if (sh > 48 * 1024) {
+      if (sh > 200 * 1024) return fail("tool-adjoint kernel needs %zu bytes of shared memory (substeps x tools too large)", sh);
+      CK(cudaFuncSetAttribute(k_kinematics_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    }
+    KL(KID_KINEMATICS_ADJ, k_kinematics_adj<<<e->B, KINADJ_CTA, sh, e->qs>>>(k, e->d_tools, s.poses, s.cidx, e->rand_num, e->d_args, e->pose_adj));
     KL(KID_IO, k_tool_adj_accum<<<cdiv(e->B * e->K * 8, 128), 128, 0, e->qs>>>(k, e->pose_adj, e->d_args));
   }
   KL(KID_REORDER, k_unsort<<<cdiv(k.stride, 256), 256, 0, e->qs>>>(k, e->adjw[e->bwd_cur], e->npart, s.perm, &e->d_args->adj_out, 1));
@@ -625,12 +678,19 @@ static int run_sequence(dsk_engine* e, int slot_idx, SeqKind kind) {
   StepSlot& s = e->slot[slot_idx];
   if (flush_pending_clear(e)) return -1;
   e->grids_valid = false;
+  if (kind == SEQ_FWD || kind == SEQ_RECOMPUTE) {
+    e->seq_full_sort = !e->cfg.sort_particles || e->sort_age >= e->resort_interval;
+    e->sort_age = e->seq_full_sort ? 1 : e->sort_age + 1;
+  } else {
+    e->seq_full_sort = false;
+  }
   if (e->profiling || !e->use_graphs) {
     e->qs = e->stream;
     return enqueue_sequence(e, s, kind);
   }
   dsk_engine::GraphSet& g = e->graphs[slot_idx];
-  cudaGraphExec_t* ex = kind == SEQ_FWD ? &g.fwd : (kind == SEQ_RECOMPUTE ? &g.recompute : (kind == SEQ_BWD ? &g.bwd : &g.bwd_tape));
+  int idx = (int)kind * 2 + (e->seq_full_sort ? 1 : 0);
+  cudaGraphExec_t* ex = &g.ex[idx];
   if (!*ex) {
     int64_t l0 = e->launches;
     int64_t kl0[KID_COUNT];
@@ -650,14 +710,12 @@ static int run_sequence(dsk_engine* e, int slot_idx, SeqKind kind) {
     cudaGraphDestroy(graph);
     if (err != cudaSuccess) return fail("cudaGraphInstantiate: %s", cudaGetErrorString(err));
     // launches counted during capture are the per-replay launch counts of this graph
-    int idx = (int)kind;
     g.n_launch[idx] = e->launches - l0;
     for (int i = 0; i < KID_COUNT; i++) g.kid[idx][i] = e->kid_launches[i] - kl0[i];
     e->launches = l0;
     memcpy(e->kid_launches, kl0, sizeof kl0);
   }
   CK(cudaGraphLaunch(*ex, e->stream));
-  int idx = (int)kind;
   e->launches += g.n_launch[idx];
   for (int i = 0; i < KID_COUNT; i++) e->kid_launches[i] += g.kid[idx][i];
   return 0;
@@ -688,6 +746,7 @@ int dsk_set_particles(dsk_engine* e, int step, int env, int n, const float* x, c
     LAUNCH_CHECK();
   }
   e->h_npart[env] = n;
+  e->sort_age = 1 << 30;
   CK(cudaMemcpyAsync(e->npart + env, &e->h_npart[env], 4, cudaMemcpyHostToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   invalidate_slots(e, step);
@@ -882,6 +941,8 @@ int dsk_substep(dsk_engine* e, int f) {
     if (push_args(e, make_args(e, step, step + 1, step, -1))) return -1;
     s.src_step = -1;
     s.action_step = step;
+    e->seq_full_sort = true;
+    e->sort_age = 1;
     if (seq_begin_forward(e, s)) return -1;
   } else if (e->last_fwd_frame != f - 1) {
     return fail("dsk_substep(%d): substeps of a step must run in ascending order starting at a step boundary (last was %d)", f, e->last_fwd_frame);

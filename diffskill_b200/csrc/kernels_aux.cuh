@@ -23,43 +23,60 @@ __global__ void k_sort_bin(SimConst k, const StepArgs* __restrict__ args, const 
   key[gid] = kk;
   rank[gid] = atomicAdd(&cell_count[(size_t)env * k.nnode + kk], 1);
 }
-// exclusive scan of cell_count per env, in place.  One 1024-thread CTA per env; each warp owns a
-// contiguous segment and walks it in coalesced 32-wide steps.
-__global__ void __launch_bounds__(1024) k_sort_scan(SimConst k, int* __restrict__ cell_count) {
-  __shared__ int wsum[32];
-  int env = blockIdx.x;
+// exclusive scan of cell_count per env, in place, in two multi-CTA passes (a single CTA per env is bound by one
+// SM's bandwidth on the n^3-cell histogram):
+//   k_scan_partial: grid (chunks, B): sum of each SCAN_CHUNK-cell chunk
+//   k_scan_chunks : grid (chunks, B): offset = sum of the preceding chunk sums, then an in-place chunk scan
+#define SCAN_CHUNK 8192
+#define SCAN_CTA 256
+DSK_DEV int block_sum(int v, int* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int t = 0;
+  for (int w = 0; w < SCAN_CTA / 32; w++) t += sh[w];
+  __syncthreads();
+  return t;
+}
+__global__ void __launch_bounds__(SCAN_CTA) k_scan_partial(SimConst k, const int* __restrict__ cell_count, int* __restrict__ partial) {
+  __shared__ int sh[SCAN_CTA / 32];
+  int env = blockIdx.y, chunk = blockIdx.x;
+  const int* c = cell_count + (size_t)env * k.nnode;
+  int lo = chunk * SCAN_CHUNK, hi = min(lo + SCAN_CHUNK, k.nnode);
+  int v = 0;
+  for (int i = lo + threadIdx.x; i < hi; i += SCAN_CTA) v += c[i];
+  int t = block_sum(v, sh);
+  if (threadIdx.x == 0) partial[env * gridDim.x + chunk] = t;
+}
+__global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(SimConst k, int* __restrict__ cell_count, const int* __restrict__ partial) {
+  __shared__ int sh[SCAN_CTA / 32];
+  __shared__ int wtot[SCAN_CTA / 32];
+  int env = blockIdx.y, chunk = blockIdx.x;
   int* c = cell_count + (size_t)env * k.nnode;
+  int v = 0;
+  for (int i = threadIdx.x; i < chunk; i += SCAN_CTA) v += partial[env * gridDim.x + i];
+  int carry = block_sum(v, sh);
+  int lo = chunk * SCAN_CHUNK, hi = min(lo + SCAN_CHUNK, k.nnode);
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int seg = (k.nnode + 31) / 32;
-  seg = (seg + 31) & ~31;
-  int lo = warp * seg, hi = min(lo + seg, k.nnode);
-  int tot = 0;
-  for (int i = lo + lane; i < hi; i += 32) tot += c[i];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-  if (lane == 0) wsum[warp] = tot;
-  __syncthreads();
-  if (warp == 0) {
-    int v = wsum[lane], s = v;
+  for (int i0 = lo; i0 < hi; i0 += SCAN_CTA) {
+    int i = i0 + threadIdx.x;
+    int x = i < hi ? c[i] : 0, sc = x;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, s, o);
-      if (lane >= o) s += t;
+      int t = __shfl_up_sync(0xffffffffu, sc, o);
+      if (lane >= o) sc += t;
     }
-    wsum[lane] = s - v;
-  }
-  __syncthreads();
-  int carry = wsum[warp];
-  for (int i0 = lo; i0 < hi; i0 += 32) {
-    int i = i0 + lane;
-    int v = i < hi ? c[i] : 0, s = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, s, o);
-      if (lane >= o) s += t;
+    if (lane == 31) wtot[warp] = sc;
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int w = 0; w < SCAN_CTA / 32; w++) {
+      if (w < warp) woff += wtot[w];
+      tot += wtot[w];
     }
-    if (i < hi) c[i] = carry + s - v;
-    carry += __shfl_sync(0xffffffffu, s, 31);
+    if (i < hi) c[i] = carry + woff + sc - x;
+    carry += tot;
+    __syncthreads();
   }
 }
 // scatter checkpoint (canonical order) -> work frame 0 (sorted order); also permutes the material arrays
@@ -78,6 +95,24 @@ __global__ void k_sort_scatter(SimConst k, const StepArgs* __restrict__ args, co
   for (int c = 0; c < FRAME_COMPS; c++) w0[c * k.stride + dst] = ck[c * k.stride + gid];
 #pragma unroll
   for (int c = 0; c < 3; c++) mat_sorted[c * k.stride + dst] = mat[c * k.stride + gid];
+}
+// re-use of an earlier sort: gather the checkpoint into sorted order with a stored permutation (particles move a small
+// fraction of a cell per env step, so the cell order stays nearly sorted for a few steps)
+__global__ void k_apply_perm(SimConst k, const StepArgs* __restrict__ args, const float* __restrict__ mat,
+                             const int* __restrict__ npart, const int* __restrict__ perm_cache,
+                             float* __restrict__ w0, float* __restrict__ mat_sorted, int* __restrict__ perm) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= k.stride) return;
+  int env = gid / k.Npad, d = gid - env * k.Npad;
+  if (d >= npart[env]) return;
+  const float* __restrict__ ck = args->ck_src;
+  int p = perm_cache[gid];
+  perm[gid] = p;
+  int src = env * k.Npad + p;
+#pragma unroll
+  for (int c = 0; c < FRAME_COMPS; c++) w0[c * k.stride + gid] = ck[c * k.stride + src];
+#pragma unroll
+  for (int c = 0; c < 3; c++) mat_sorted[c * k.stride + gid] = mat[c * k.stride + src];
 }
 // sorted frame -> canonical checkpoint.  accumulate=1: += (adjoint checkpoints)
 __global__ void k_unsort(SimConst k, const float* __restrict__ w, const int* __restrict__ npart,

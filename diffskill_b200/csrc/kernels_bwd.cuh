@@ -11,7 +11,8 @@
 #include "kernels_fwd.cuh"
 
 // g2p.grad : reads adjoints of (x,v,C)[j+1], scatters adjoint of grid_v_out, writes the g2p part of x.grad[j]
-__global__ void __launch_bounds__(128)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
     k_g2p_adj(SimConst k, const float* __restrict__ fin, const float* __restrict__ fnext,
               const float* __restrict__ adj_in, float* __restrict__ adj_out, const int* __restrict__ npart,
               const float4* __restrict__ Gv, float4* __restrict__ Ga) {
@@ -35,12 +36,18 @@ __global__ void __launch_bounds__(128)
   float4* Gae = Ga + (size_t)env * k.nnode;
   // adjoint of grid_v_out: warp-aggregated scatter
   TileTrack none{nullptr, nullptr, nullptr};
-  warp_scatter27(k, active, s, Gae, none, false, env, 0, [&](int i, int j, int l) {
-    float w = s.wx[i] * s.wy[j] * s.wz[l];
-    float cw = k.c_C * w;
-    float3 Cd = mv(gC, f3((float)i - s.fx, (float)j - s.fy, (float)l - s.fz));
-    return make_float4(w * gvn.x + cw * Cd.x, w * gvn.y + cw * Cd.y, w * gvn.z + cw * Cd.z, 0.f);
-  });
+  {
+    // w * (gvn + c_C gC (offset - fx)) = w * (b0 + i cx + j cy + l cz)
+    float3 b0 = gvn - k.c_C * mv(gC, f3(s.fx, s.fy, s.fz));
+    float3 cx = f3(k.c_C * gC.m[0], k.c_C * gC.m[3], k.c_C * gC.m[6]);
+    float3 cy = f3(k.c_C * gC.m[1], k.c_C * gC.m[4], k.c_C * gC.m[7]);
+    float3 cz = f3(k.c_C * gC.m[2], k.c_C * gC.m[5], k.c_C * gC.m[8]);
+    warp_scatter27(k, active, s, Gae, none, false, env, 0, [&](int i, int j, int l) {
+      float w = s.wx[i] * s.wy[j] * s.wz[l];
+      float3 a = b0 + (float)i * cx + (float)j * cy + (float)l * cz;
+      return make_float4(w * a.x, w * a.y, w * a.z, 0.f);
+    });
+  }
   if (!active) return;
   float gwx[3] = {0, 0, 0}, gwy[3] = {0, 0, 0}, gwz[3] = {0, 0, 0};
   float3 gf = f3(0, 0, 0);  // adjoint of fx (through dpos)
@@ -201,10 +208,20 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
         const ToolParams& T = sT[ft.tool[y]];
         int kind = ft.flag[y] != 0.f ? SDF_BOX : sdf_kind(T.type);
         const ContactGeomAdj& a = gadj[y][l];
+        const ContactGeom& c = geo[y][l];
+        // D = qrot(q0, n/L)
+        float3 Nl = (1.f / c.L) * c.nraw, gNl = f3(0, 0, 0);
+        qrot_adj(tf.F0[y].q, Nl, a.gD, a0.q, gNl);
+        float3 gpl = local_normal_adj_cached(T, kind, c.pl, c.nraw, c.L, gNl);
+        // dist = sdf(pl)
+        gpl += a.gdist * local_sdf_grad(T, kind, c.pl);
+        // cv = (qrot(q1, pl) + o1 - p) / dt
+        float3 gnp = (1.f / k.dt) * a.gcv;
+        a1.o += gnp;
+        qrot_adj(tf.F1[y].q, c.pl, gnp, a1.q, gpl);
+        // pl = inv_trans(F0, p)
         float3 unused = f3(0, 0, 0);
-        frame_normal_adj(T, kind, tf.F0[y], gp, a.gD, a0, unused);
-        frame_collider_v_adj(tf.F0[y], tf.F1[y], gp, k.dt, a.gcv, a0, a1);
-        frame_sdf_adj(T, kind, tf.F0[y], gp, a.gdist, a0, unused);
+        inv_trans_adj(tf.F0[y], gp, gpl, a0, unused);
       }
       float vals[14] = {a0.o.x, a0.o.y, a0.o.z, a0.q.w, a0.q.x, a0.q.y, a0.q.z,
                         a1.o.x, a1.o.y, a1.o.z, a1.q.w, a1.q.x, a1.q.y, a1.q.z};
@@ -381,110 +398,140 @@ __global__ void __launch_bounds__(128)
 
 // Tool adjoints of one env step: for j = S-1..0: apply_collision_projection.grad, set_surface_points.grad,
 // forward_kinematics.grad (tools in reverse order), then set_velocity.grad (primive_base.py:260-268).
-// One warp per env; lane t owns tool t.
-__global__ void __launch_bounds__(32)
+// The kinematics of a substep is a tiny map pose_j, u -> pose_{j+1}; its adjoint is linear in the incoming
+// adjoint, so phase 1 evaluates the 8x8 / 8x7 Jacobian blocks of ALL substeps in parallel (one thread per
+// (substep, tool, output component), unit seeds through tool_fk_adj) and phase 2 walks the chain with 8
+// multiply-adds per thread per substep.  One CTA per env.
+#define KINADJ_CTA 256
+DSK_DEV void projection_adj(const SimConst& k, const ToolParams* sT, const float* P1, const float* __restrict__ rand_num,
+                            int c, int idx, float* a1) {
+  int ti = k.pairs[c][0], tj = k.pairs[c][1];
+  // tool i is evaluated at its POST-projection pose, as Taichi's grad kernel re-evaluates the forward on the
+  // current field values; the obstacle pose is the post-step pose of frame j+1
+  const float* rn = rand_num + ((size_t)c * DSK_NUM_COLLISION_POINTS + idx) * 3;
+  Pose Pj = load_pose(P1 + tj * 8), Pi = load_pose(P1 + ti * 8);
+  float3 pt = surface_point(sT[tj], Pj, rn);
+  float d = tool_sdf(sT[ti], Pi, pt);
+  float3 nr = tool_normal(sT[ti], Pi, pt);
+  float n2 = dot(nr, nr);
+  float inv = 1.f / sqrtf(n2);
+  // new_pos = pos + (inv*nr)*d ; seed = current position.grad
+  float3 gs = f3(a1[ti * 8 + 0], a1[ti * 8 + 1], a1[ti * 8 + 2]);
+  float3 un = inv * nr;
+  float gd = dot(gs, un);
+  float3 gun = d * gs;
+  float ginv = dot(gun, nr);
+  float3 gnr = inv * gun;
+  gnr += (2.f * (-0.5f * ginv * inv / n2)) * nr;
+  PoseAdj gPi = pose_adj_zero();
+  float3 gpt = f3(0, 0, 0);
+  tool_sdf_adj(sT[ti], Pi, pt, gd, gPi, gpt);
+  tool_normal_adj(sT[ti], Pi, pt, gnr, gPi, gpt);
+  a1[ti * 8 + 0] += gPi.p.x; a1[ti * 8 + 1] += gPi.p.y; a1[ti * 8 + 2] += gPi.p.z;
+  a1[ti * 8 + 3] += gPi.q.w; a1[ti * 8 + 4] += gPi.q.x; a1[ti * 8 + 5] += gPi.q.y; a1[ti * 8 + 6] += gPi.q.z;
+  a1[ti * 8 + 7] += gPi.gap;
+  // set_surface_points.grad: pt = qrot(rot_j, proj) + pos_j
+  float3 q;
+  q.x = tmax(tmin(rn[0] * sT[tj].size[0], sT[tj].size[0]), -sT[tj].size[0]);
+  q.y = tmax(tmin(rn[1] * sT[tj].size[1], sT[tj].size[1]), -sT[tj].size[1]);
+  q.z = tmax(tmin(rn[2] * sT[tj].size[2], sT[tj].size[2]), -sT[tj].size[2]);
+  Q4 gq = {0, 0, 0, 0};
+  float3 gdm = f3(0, 0, 0);
+  qrot_adj(Pj.q, q, gpt, gq, gdm);
+  a1[tj * 8 + 0] += gpt.x; a1[tj * 8 + 1] += gpt.y; a1[tj * 8 + 2] += gpt.z;
+  a1[tj * 8 + 3] += gq.w; a1[tj * 8 + 4] += gq.x; a1[tj * 8 + 5] += gq.y; a1[tj * 8 + 6] += gq.z;
+}
+__global__ void __launch_bounds__(KINADJ_CTA)
     k_kinematics_adj(SimConst k, const ToolParams* __restrict__ tools, const float* __restrict__ poses,
                      const int* __restrict__ cidx, const float* __restrict__ rand_num,
                      const StepArgs* __restrict__ args, float* __restrict__ pose_adj) {
   const float* __restrict__ action = args->action;
   float* __restrict__ action_grad = args->action_grad;  // [B][A] of this step, +=
   __shared__ ToolParams sT[DSK_MAX_TOOLS];
-  extern __shared__ float sadj[];  // [(S+1)][K][8]
-  int env = blockIdx.x, lane = threadIdx.x;
-  for (int i = lane; i < k.K * (int)(sizeof(ToolParams) / 4); i += 32) ((int*)sT)[i] = ((const int*)tools)[i];
+  __shared__ float s_gu[DSK_MAX_TOOLS][8];
+  extern __shared__ float dyn[];
+  int env = blockIdx.x, tid = threadIdx.x;
   int tot = (k.S + 1) * k.K * 8;
+  float* sadj = dyn;                          // [(S+1)][K][8]
+  float* Jp = sadj + tot;                     // [S][K][8 out][8 in]
+  float* Ju = Jp + (size_t)k.S * k.K * 64;    // [S][K][8 out][8 (7 used)]
+  for (int i = tid; i < k.K * (int)(sizeof(ToolParams) / 4); i += blockDim.x) ((int*)sT)[i] = ((const int*)tools)[i];
   float* gadj = pose_adj + (size_t)env * tot;
   const float* P = poses + (size_t)env * tot;
-  for (int i = lane; i < tot; i += 32) sadj[i] = gadj[i];
-  __syncwarp();
-  int A = 0, off = 0;
-  for (int t = 0; t < k.K; t++) {
-    if (t == lane) off = A;
-    A += sT[t].action_dim;
-  }
-  ToolVel u, gu;
-  gu.v = f3(0, 0, 0);
-  gu.w = f3(0, 0, 0);
-  gu.gap_vel = 0.f;
+  for (int i = tid; i < tot; i += blockDim.x) sadj[i] = gadj[i];
+  if (tid < DSK_MAX_TOOLS * 8) s_gu[tid / 8][tid % 8] = 0.f;
+  __syncthreads();
+  int A = 0;
+  for (int t = 0; t < k.K; t++) A += sT[t].action_dim;
   float zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (lane < k.K) u = action_to_vel(sT[lane], action ? action + (size_t)env * A + off : zero, k.S);
+  // phase 1: Jacobian blocks of every (substep, tool), one output component per thread
+  for (int w = tid; w < k.S * k.K * 8; w += blockDim.x) {
+    int r = w & 7, t = (w >> 3) % k.K, j = (w >> 3) / k.K;
+    int off = 0;
+    for (int q = 0; q < t; q++) off += sT[q].action_dim;
+    ToolVel u = action_to_vel(sT[t], action ? action + (size_t)env * A + off : zero, k.S), gu;
+    gu.v = f3(0, 0, 0);
+    gu.w = f3(0, 0, 0);
+    gu.gap_vel = 0.f;
+    PoseAdj gN = pose_adj_zero(), gP = pose_adj_zero();
+    float* gn = (float*)&gN;   // PoseAdj is 8 packed floats: p3, q4, gap
+    gn[r] = 1.f;
+    tool_fk_adj(sT[t], load_pose(P + ((size_t)j * k.K + t) * 8), u, gN, gP, gu);
+    float* o = Jp + (size_t)w * 8;
+    o[0] = gP.p.x; o[1] = gP.p.y; o[2] = gP.p.z; o[3] = gP.q.w; o[4] = gP.q.x; o[5] = gP.q.y; o[6] = gP.q.z; o[7] = gP.gap;
+    float* ou = Ju + (size_t)w * 8;
+    ou[0] = gu.v.x; ou[1] = gu.v.y; ou[2] = gu.v.z; ou[3] = gu.w.x; ou[4] = gu.w.y; ou[5] = gu.w.z; ou[6] = gu.gap_vel; ou[7] = 0.f;
+  }
+  __syncthreads();
+  // phase 2: walk the chain
+  int t = tid >> 3, c = tid & 7;
+  float gu_acc = 0.f;
   for (int j = k.S - 1; j >= 0; j--) {
     float* a1 = sadj + (size_t)(j + 1) * k.K * 8;
     float* a0 = sadj + (size_t)j * k.K * 8;
-    const float* P1 = P + (size_t)(j + 1) * k.K * 8;
-    const float* P0 = P + (size_t)j * k.K * 8;
-    if (k.npairs > 0 && lane == 0) {
-      for (int c = k.npairs - 1; c >= 0; c--) {
-        int idx = cidx[((size_t)env * (k.S + 1) + (j + 1)) * k.npairs + c];
-        if (idx < 0) continue;
-        int ti = k.pairs[c][0], tj = k.pairs[c][1];
-        // NOTE: obstacle pose is the post-step pose of frame j+1 (obstacles are never projected in the
-        // reference's scenes); tool i is evaluated at its POST-projection pose, as Taichi's grad kernel does.
-        const float* rn = rand_num + ((size_t)c * DSK_NUM_COLLISION_POINTS + idx) * 3;
-        Pose Pj = load_pose(P1 + tj * 8), Pi = load_pose(P1 + ti * 8);
-        float3 pt = surface_point(sT[tj], Pj, rn);
-        float d = tool_sdf(sT[ti], Pi, pt);
-        float3 nr = tool_normal(sT[ti], Pi, pt);
-        float n2 = dot(nr, nr);
-        float inv = 1.f / sqrtf(n2);
-        // new_pos = pos + (inv*nr)*d ; seed = current position.grad
-        float3 gs = f3(a1[ti * 8 + 0], a1[ti * 8 + 1], a1[ti * 8 + 2]);
-        float3 un = inv * nr;
-        float gd = dot(gs, un);
-        float3 gun = d * gs;
-        float ginv = dot(gun, nr);
-        float3 gnr = inv * gun;
-        // inv = n2^-1/2
-        gnr += (2.f * (-0.5f * ginv * inv / n2)) * nr;
-        PoseAdj gPi = pose_adj_zero();
-        float3 gpt = f3(0, 0, 0);
-        tool_sdf_adj(sT[ti], Pi, pt, gd, gPi, gpt);
-        tool_normal_adj(sT[ti], Pi, pt, gnr, gPi, gpt);
-        a1[ti * 8 + 0] += gPi.p.x; a1[ti * 8 + 1] += gPi.p.y; a1[ti * 8 + 2] += gPi.p.z;
-        a1[ti * 8 + 3] += gPi.q.w; a1[ti * 8 + 4] += gPi.q.x; a1[ti * 8 + 5] += gPi.q.y; a1[ti * 8 + 6] += gPi.q.z;
-        a1[ti * 8 + 7] += gPi.gap;
-        // set_surface_points.grad: pt = qrot(rot_j, proj) + pos_j
-        float3 q;
-        q.x = tmax(tmin(rn[0] * sT[tj].size[0], sT[tj].size[0]), -sT[tj].size[0]);
-        q.y = tmax(tmin(rn[1] * sT[tj].size[1], sT[tj].size[1]), -sT[tj].size[1]);
-        q.z = tmax(tmin(rn[2] * sT[tj].size[2], sT[tj].size[2]), -sT[tj].size[2]);
-        Q4 gq = {0, 0, 0, 0};
-        float3 gdm = f3(0, 0, 0);
-        qrot_adj(Pj.q, q, gpt, gq, gdm);
-        a1[tj * 8 + 0] += gpt.x; a1[tj * 8 + 1] += gpt.y; a1[tj * 8 + 2] += gpt.z;
-        a1[tj * 8 + 3] += gq.w; a1[tj * 8 + 4] += gq.x; a1[tj * 8 + 5] += gq.y; a1[tj * 8 + 6] += gq.z;
+    if (k.npairs > 0) {
+      if (tid == 0) {
+        for (int cc = k.npairs - 1; cc >= 0; cc--) {
+          int idx = cidx[((size_t)env * (k.S + 1) + (j + 1)) * k.npairs + cc];
+          if (idx >= 0) projection_adj(k, sT, P + (size_t)(j + 1) * k.K * 8, rand_num, cc, idx, a1);
+        }
       }
+      __syncthreads();
     }
-    __syncwarp();
-    if (lane < k.K) {
-      PoseAdj gN;
-      const float* g = a1 + lane * 8;
-      gN.p = f3(g[0], g[1], g[2]);
-      gN.q.w = g[3]; gN.q.x = g[4]; gN.q.y = g[5]; gN.q.z = g[6];
-      gN.gap = g[7];
-      PoseAdj gP = pose_adj_zero();
-      tool_fk_adj(sT[lane], load_pose(P0 + lane * 8), u, gN, gP, gu);
-      float* o = a0 + lane * 8;
-      o[0] += gP.p.x; o[1] += gP.p.y; o[2] += gP.p.z;
-      o[3] += gP.q.w; o[4] += gP.q.x; o[5] += gP.q.y; o[6] += gP.q.z;
-      o[7] += gP.gap;
+    if (t < k.K) {
+      const float* jp = Jp + ((size_t)j * k.K + t) * 64;
+      const float* ju = Ju + ((size_t)j * k.K + t) * 64;
+      const float* g = a1 + t * 8;
+      float sp = 0.f, su = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        sp += jp[r * 8 + c] * g[r];
+        su += ju[r * 8 + c] * g[r];
+      }
+      a0[t * 8 + c] += sp;
+      gu_acc += su;
     }
-    __syncwarp();
+    __syncthreads();
   }
-  for (int i = lane; i < tot; i += 32) gadj[i] = sadj[i];
-  if (lane < k.K && sT[lane].action_dim > 0 && action_grad) {
-    const ToolParams& T = sT[lane];
+  for (int i = tid; i < tot; i += blockDim.x) gadj[i] = sadj[i];
+  if (t < k.K) s_gu[t][c] = gu_acc;
+  __syncthreads();
+  if (tid < k.K && sT[tid].action_dim > 0 && action_grad) {
+    const ToolParams& T = sT[tid];
+    int off = 0;
+    for (int q = 0; q < tid; q++) off += sT[q].action_dim;
     float fs = (float)k.S;
     float* ga = action_grad + (size_t)env * A + off;
-    ga[0] += gu.v.x * (T.action_scale[0] / fs);
-    ga[1] += gu.v.y * (T.action_scale[1] / fs);
-    ga[2] += gu.v.z * (T.action_scale[2] / fs);
+    const float* gu = s_gu[tid];
+    ga[0] += gu[0] * (T.action_scale[0] / fs);
+    ga[1] += gu[1] * (T.action_scale[1] / fs);
+    ga[2] += gu[2] * (T.action_scale[2] / fs);
     if (T.action_dim > 3) {
-      ga[3] += gu.w.x * (T.action_scale[3] / fs);
-      ga[4] += gu.w.y * (T.action_scale[4] / fs);
-      ga[5] += gu.w.z * (T.action_scale[5] / fs);
+      ga[3] += gu[3] * (T.action_scale[3] / fs);
+      ga[4] += gu[4] * (T.action_scale[4] / fs);
+      ga[5] += gu[5] * (T.action_scale[5] / fs);
     }
-    if (T.type == DSK_TOOL_GRIPPER) ga[6] += gu.gap_vel * (T.action_scale[6] / fs);
+    if (T.type == DSK_TOOL_GRIPPER) ga[6] += gu[6] * (T.action_scale[6] / fs);
   }
 }
 

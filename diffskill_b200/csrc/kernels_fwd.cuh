@@ -20,7 +20,7 @@ struct ReturnMap {
 };
 DSK_DEV M3 von_mises(const M3& Ftmp, const M3& U, float3 sig, const M3& V, float ys, float mu, ReturnMap& r) {
   r.sc = f3(tmax(sig.x, 0.05f), tmax(sig.y, 0.05f), tmax(sig.z, 0.05f));
-  r.eps = f3(logf(r.sc.x), logf(r.sc.y), logf(r.sc.z));
+  r.eps = f3(__logf(r.sc.x), __logf(r.sc.y), __logf(r.sc.z));   // MUFU log/exp: the reference runs fast_math=True
   float mean = (r.eps.x + r.eps.y + r.eps.z) / 3.f;
   r.eh = f3(r.eps.x - mean, r.eps.y - mean, r.eps.z - mean);
   r.ehn = sqrtf(dot(r.eh, r.eh) + 1e-8f);
@@ -28,7 +28,7 @@ DSK_DEV M3 von_mises(const M3& Ftmp, const M3& U, float3 sig, const M3& V, float
   r.yields = r.dg > 0.f;
   if (r.yields) {
     float kf = r.dg / r.ehn;
-    r.e = f3(expf(r.eps.x - kf * r.eh.x), expf(r.eps.y - kf * r.eh.y), expf(r.eps.z - kf * r.eh.z));
+    r.e = f3(__expf(r.eps.x - kf * r.eh.x), __expf(r.eps.y - kf * r.eh.y), __expf(r.eps.z - kf * r.eh.z));
     M3 US;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
@@ -69,8 +69,10 @@ DSK_DEV void p2g_particle(const SimConst& k, const M3& C, const M3& F, float mu,
   for (int i = 0; i < 9; i++) o.affine.m[i] = k.c_stress * st.m[i] + k.p_mass * C.m[i];
 }
 
-template <bool WRITE_F>
-__global__ void __launch_bounds__(128)
+// MINB = min CTAs/SM the register allocation must allow: 1 for small (latency-bound) problems -- all registers, no
+// spills; 3 for large batches where occupancy hides the scatter latency
+template <bool WRITE_F, int MINB>
+__global__ void __launch_bounds__(128, MINB)
     k_p2g(SimConst k, const float* __restrict__ fin, float* __restrict__ fout, const float* __restrict__ mat,
           const int* __restrict__ npart, float4* __restrict__ G, TileTrack tt, const StepArgs* __restrict__ args,
           int q, const int* __restrict__ run_if) {
@@ -90,11 +92,15 @@ __global__ void __launch_bounds__(128)
   Stencil s;
   make_stencil(k, x.x, x.y, x.z, s);
   float4* Ge = G + (size_t)env * k.nnode;
-  float3 pmv = k.p_mass * v;
+  // w * (p_mass v + affine (offset - fx) dx) = w * (a0 + i ax + j ay + l az)
+  float3 fxv = f3(s.fx, s.fy, s.fz);
+  float3 a0 = k.p_mass * v - k.dx * mv(o.affine, fxv);
+  float3 ax = f3(k.dx * o.affine.m[0], k.dx * o.affine.m[3], k.dx * o.affine.m[6]);
+  float3 ay = f3(k.dx * o.affine.m[1], k.dx * o.affine.m[4], k.dx * o.affine.m[7]);
+  float3 az = f3(k.dx * o.affine.m[2], k.dx * o.affine.m[5], k.dx * o.affine.m[8]);
   warp_scatter27(k, active, s, Ge, tt, true, env, args->epoch_base + q + 1, [&](int i, int j, int l) {
-    float3 dpos = f3(((float)i - s.fx) * k.dx, ((float)j - s.fy) * k.dx, ((float)l - s.fz) * k.dx);
     float w = s.wx[i] * s.wy[j] * s.wz[l];
-    float3 a = pmv + mv(o.affine, dpos);
+    float3 a = a0 + (float)i * ax + (float)j * ay + (float)l * az;
     return make_float4(w * a.x, w * a.y, w * a.z, w * k.p_mass);
   });
 }
@@ -253,6 +259,8 @@ DSK_DEV Frame frame_of_pose(const Pose& P, float flag) { return flag == 0.f ? to
 struct ContactGeom {   // per (node, frame), shared memory
   float influence;     // < 0: contact inactive
   float3 D, cv;
+  float3 pl, nraw;     // tool-local node position, un-normalised local normal and its length: re-used by the adjoint
+  float L;
 };
 struct TileFrames {    // per tile-iteration, shared memory
   Frame F0[MAX_FRAMES], F1[MAX_FRAMES];
@@ -276,12 +284,20 @@ DSK_DEV void prepare_tile_frame(const SimConst& k, const ToolParams* sT, const F
 }
 DSK_DEV void contact_geometry(const ToolParams& T, int kind, const Frame& F0, const Frame& F1, float3 p, float dt,
                               ContactGeom& g) {
-  float dist = frame_sdf(T, kind, F0, p);
+  float3 pl = inv_trans(F0, p);
+  float dist = local_sdf(T, kind, pl);
   float influence;
   if (contact_active(dist, T.softness, influence)) {
     g.influence = influence;
-    g.D = frame_normal(T, kind, F0, p);
-    g.cv = frame_collider_v(F0, F1, p, dt);
+    float L;
+    float3 n = local_normal_raw(T, kind, pl, L);
+    g.D = qrot_rn(F0.q, f3(__fdiv_rn(n.x, L), __fdiv_rn(n.y, L), __fdiv_rn(n.z, L)));   // primive_base.py:80-85
+    // collider_v (primive_base.py:87-94): the relative position IS the local point
+    float3 np = add3_rn(qrot_rn(F1.q, pl), F1.o);
+    g.cv = f3(__fdiv_rn(sub_rn(np.x, p.x), dt), __fdiv_rn(sub_rn(np.y, p.y), dt), __fdiv_rn(sub_rn(np.z, p.z), dt));
+    g.pl = pl;
+    g.nraw = n;
+    g.L = L;
   } else {
     g.influence = -1.f;
   }

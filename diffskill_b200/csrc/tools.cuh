@@ -203,6 +203,24 @@ DSK_DEV float3 local_normal_adj(const ToolParams& T, int kind, float3 p, float3 
   return gp;
 }
 
+// the same with the un-normalised normal n and its length L already known (cached by the forward geometry pass)
+DSK_DEV float3 local_normal_adj_cached(const ToolParams& T, int kind, float3 p, float3 n, float L, float3 gN) {
+  float3 gn = (1.f / L) * gN - (dot(n, gN) / (L * L * L)) * n;
+  if (kind == SDF_CAPSULE) {
+    float y = p.y + T.half_h;
+    float t = tmax(y, 0.f);
+    float dyy = 1.f - (((0.f < y) && (t < T.h)) ? 1.f : 0.f);
+    return f3(gn.x, dyy * gn.y, gn.z);
+  }
+  const float d = DSK_FD_D;
+  const float c = 0.5f / d;
+  float3 gp = f3(0, 0, 0);
+  gp += (c * gn.x) * (local_sdf_grad(T, kind, f3(p.x + d, p.y, p.z)) - local_sdf_grad(T, kind, f3(p.x - d, p.y, p.z)));
+  gp += (c * gn.y) * (local_sdf_grad(T, kind, f3(p.x, p.y + d, p.z)) - local_sdf_grad(T, kind, f3(p.x, p.y - d, p.z)));
+  gp += (c * gn.z) * (local_sdf_grad(T, kind, f3(p.x, p.y, p.z + d)) - local_sdf_grad(T, kind, f3(p.x, p.y, p.z - d)));
+  return gp;
+}
+
 // ---- world <-> tool frame -----------------------------------------------------------------------
 DSK_DEV float3 inv_trans(const Frame& F, float3 p) {  // utils.py:50-54
   return qrot_rn(qconj_normalized_rn(F.q), sub3_rn(p, F.o));
