@@ -104,9 +104,9 @@ struct dsk_engine {
   int bwd_cur = 0;  // adjw index holding the adjoint of the current frame
   // sequences / graphs
   struct GraphSet {
-    cudaGraphExec_t ex[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [kind*2 + full_sort]
-    int64_t n_launch[8] = {0};
-    int64_t kid[8][KID_COUNT] = {{0}};
+    cudaGraphExec_t ex[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [kind*2 + full_sort]
+    int64_t n_launch[10] = {0};
+    int64_t kid[10][KID_COUNT] = {{0}};
   };
   std::vector<GraphSet> graphs;
   bool use_graphs = true;
@@ -115,6 +115,7 @@ struct dsk_engine {
   int epoch_base = 0;
   int* done = nullptr;
   bool seq_use_tape = false;  // the backward sequence being enqueued restores grids from the slot's tape
+  bool seq_tape_trusted = false;  // ... and the host has verified that the tape did not overflow (no fallback kernels)
   int pending_q = -1;  // fine-grained mode: last substep's grids still hold data
   bool pending_bwd = false, grids_valid = false;
   float* loss = nullptr;  // [B]
@@ -127,6 +128,7 @@ struct dsk_engine {
   bool kin_join = false;
   int tape_cap = 0;       // grid-tape capacity per step slot, in tiles (0: taping off)
   bool tape_flags_stale = true;
+  int* tape_flags = nullptr;   // [slots] device overflow flags
   std::vector<int> tape_overflow;  // host copy of the slots' overflow flags
 
   float* frame_of(float* base, int i) { return base + (size_t)i * frame_floats; }
@@ -305,7 +307,9 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
     DA(e->npart, e->B);
     e->h_npart.assign(e->B, 0);
     e->slot.resize(e->slots);
+    if (e->tape_cap > 0) DA(e->tape_flags, e->slots);
     for (auto& s : e->slot) {
+      if (e->tape_cap > 0) s.tape.overflow = e->tape_flags + (&s - e->slot.data());
       DA(s.frames, (size_t)(e->S + 1) * e->frame_floats);
       DA(s.mat, (size_t)3 * k.stride);
       DA(s.perm, k.stride);
@@ -316,7 +320,6 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
         DA(s.tape.base, e->S + 1);
         DA(s.tape.list, e->tape_cap);
         DA(s.tape.data, (size_t)e->tape_cap * 128);
-        DA(s.tape.overflow, 1);
       }
     }
     DA(e->cell_count, (size_t)e->B * k.nnode);
@@ -624,12 +627,14 @@ static int seq_substep_grad(dsk_engine* e, StepSlot& s, int q, int j) {
                                clr ? e->Gv[prev] : nullptr, clr ? e->Ga[prev] : nullptr, e->tile_count + ((q + 3) & 3)));
     run_if = s.tape.overflow;
   }
-  KL(KID_P2G_RECOMPUTE, k_p2g<false, 3><<<nb, 128, 0, e->qs>>>(k, fin, nullptr, s.mat, e->npart, e->G0[set], tt, e->d_args, q, run_if));
-  KL(KID_GRID_RECOMPUTE, k_grid<<<grid_ctas(e), grid_block(e), 0, e->qs>>>(
-                             k, e->d_tools, s.poses, j, e->G0[set], e->Gv[set], tt.list, tt.count,
-                             clr ? e->tile_list[prev] : nullptr, e->tile_count + (q & 3), clr ? e->G0[prev] : nullptr,
-                             clr ? e->Gv[prev] : nullptr, clr ? e->Ga[prev] : nullptr, e->tile_count + ((q + 3) & 3),
-                             GridTape{nullptr, nullptr, nullptr, nullptr, 0}, run_if));
+  if (!(e->seq_use_tape && e->seq_tape_trusted)) {
+    KL(KID_P2G_RECOMPUTE, k_p2g<false, 3><<<nb, 128, 0, e->qs>>>(k, fin, nullptr, s.mat, e->npart, e->G0[set], tt, e->d_args, q, run_if));
+    KL(KID_GRID_RECOMPUTE, k_grid<<<grid_ctas(e), grid_block(e), 0, e->qs>>>(
+                               k, e->d_tools, s.poses, j, e->G0[set], e->Gv[set], tt.list, tt.count,
+                               clr ? e->tile_list[prev] : nullptr, e->tile_count + (q & 3), clr ? e->G0[prev] : nullptr,
+                               clr ? e->Gv[prev] : nullptr, clr ? e->Ga[prev] : nullptr, e->tile_count + ((q + 3) & 3),
+                               GridTape{nullptr, nullptr, nullptr, nullptr, 0}, run_if));
+  }
   if (e->big)
     KL(KID_G2P_ADJ, k_g2p_adj<3><<<nb, 128, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
   else
@@ -658,10 +663,11 @@ static int seq_end_backward(dsk_engine* e, StepSlot& s) {
 }
 
 // ---- whole sequences, eager or as a replayed graph ---------------------------------------------------------------
-enum SeqKind { SEQ_FWD, SEQ_RECOMPUTE, SEQ_BWD, SEQ_BWD_TAPE };
+enum SeqKind { SEQ_FWD, SEQ_RECOMPUTE, SEQ_BWD, SEQ_BWD_TAPE, SEQ_BWD_TAPE_TRUSTED };
 static int enqueue_sequence(dsk_engine* e, StepSlot& s, SeqKind kind) {
-  if (kind == SEQ_BWD || kind == SEQ_BWD_TAPE) {
-    e->seq_use_tape = kind == SEQ_BWD_TAPE;
+  if (kind == SEQ_BWD || kind == SEQ_BWD_TAPE || kind == SEQ_BWD_TAPE_TRUSTED) {
+    e->seq_use_tape = kind != SEQ_BWD;
+    e->seq_tape_trusted = kind == SEQ_BWD_TAPE_TRUSTED;
     if (seq_begin_backward(e, s)) return -1;
     for (int q = 0; q < e->S; q++)
       if (seq_substep_grad(e, s, q, e->S - 1 - q)) return -1;
@@ -903,6 +909,7 @@ int dsk_forward_step(dsk_engine* e, int src_step, int dst_step, int action_step)
   s.action_step = action_step;
   if (run_sequence(e, si, SEQ_FWD)) return -1;
   s.tape_written = true;
+  e->tape_flags_stale = true;
   invalidate_slots(e, dst_step);
   // the slot's substep frames can serve backward_step(src_step) iff the step was (src, src+?, src) shaped
   s.src_step = (dst_step != src_step && action_step == src_step) ? src_step : -1;
@@ -915,6 +922,7 @@ int dsk_backward_step(dsk_engine* e, int step) {
   if (step < 0 || step >= e->H) return fail("dsk_backward_step: step %d outside [0,%d)", step, e->H);
   int si = step % e->slots;
   StepSlot& s = e->slot[si];
+  bool recomputed = false;
   if (s.src_step != step) {
     // per-step checkpointing: recompute the substep frames of this step from its checkpoint
     if (push_args(e, make_args(e, step, step, step, -1))) return -1;
@@ -922,9 +930,24 @@ int dsk_backward_step(dsk_engine* e, int step) {
     if (run_sequence(e, si, SEQ_RECOMPUTE)) return -1;
     s.src_step = step;
     s.tape_written = true;
+    recomputed = true;
   }
   if (push_args(e, make_args(e, step, step, step, step))) return -1;
-  if (run_sequence(e, si, (e->tape_cap > 0 && s.tape_written) ? SEQ_BWD_TAPE : SEQ_BWD)) return -1;
+  SeqKind bk = SEQ_BWD;
+  if (e->tape_cap > 0 && s.tape_written) {
+    bk = SEQ_BWD_TAPE;
+    if (!recomputed) {
+      // full-tape mode: one host check of the overflow flags per backward pass lets the sequence drop its two
+      // (normally empty) fallback recompute launches per substep
+      if (e->tape_flags_stale) {
+        CK(cudaMemcpyAsync(e->tape_overflow.data(), e->tape_flags, (size_t)e->slots * 4, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        e->tape_flags_stale = false;
+      }
+      if (e->tape_overflow[si] == 0) bk = SEQ_BWD_TAPE_TRUSTED;
+    }
+  }
+  if (run_sequence(e, si, bk)) return -1;
   e->last_bwd_frame = -1;
   e->last_substep_slot = si;
   return 0;

@@ -14,7 +14,7 @@ def f32(a):
     return np.asarray(a, dtype=np.float32)
 
 
-def make_pair(name, n=1500, substeps=None, max_steps=4, seed=0, sort=True, step_slots=1, twin=False):
+def make_pair(name, n=1500, substeps=None, max_steps=4, seed=0, sort=True, step_slots=1, twin=False, grid_tape_mib=256):
     """Engine + fp32 oracle (+ fp64 twin if twin=True) on the same fp32-representable inputs.
     substeps=1 turns every env step into one substep."""
     scene, cfg, x0 = small_dough(name, n, seed)
@@ -24,7 +24,8 @@ def make_pair(name, n=1500, substeps=None, max_steps=4, seed=0, sort=True, step_
     v0, F0, C0 = perturbed_state(x0, seed + 1)
     x0, v0, F0, C0 = f32(x0), f32(v0), f32(F0), f32(C0)
     st0 = [f32(s) for s in tool_start(name, scene)]
-    eng = Engine(scene, n_envs=1, capacity=n, max_steps=max_steps, step_slots=step_slots, sort=sort)
+    eng = Engine(scene, n_envs=1, capacity=n, max_steps=max_steps, step_slots=step_slots, sort=sort,
+                 grid_tape_mib=grid_tape_mib)
     eng.set_particles(0, 0, x0, v0, F0, C0)
     oracles = []
     for f64 in ([False, True] if twin else [False]):

@@ -184,12 +184,13 @@ def test_substep_backward_parity(name):
 
 
 @pytest.mark.parametrize('name', ENVS)
-@pytest.mark.parametrize('slots', [1, 3])
-def test_multi_step_action_gradient(name, slots):
+@pytest.mark.parametrize('slots,tape_mib', [(1, 256), (3, 256), (3, 1), (3, 0)])
+def test_multi_step_action_gradient(name, slots, tape_mib):
     """3 env steps of the real substep count: checkpoint + recompute (slots=1) and full tape (slots=3)
-    must both match the oracle's taped gradient (the reference's own property test, long_term_gradient.ipynb)."""
+    must both match the oracle's taped gradient (the reference's own property test, long_term_gradient.ipynb).
+    tape_mib: grid tape on (256), overflowing -> device-side fallback to recompute (1), off (0)."""
     H = 3
-    scene, eng, o = make_pair(name, n=800, max_steps=H, step_slots=slots)
+    scene, eng, o = make_pair(name, n=800, max_steps=H, step_slots=slots, grid_tape_mib=tape_mib)
     acts = actions_for(scene, H, scale=0.7)
     n = eng.n_particles()
     S = scene.substeps
