@@ -45,6 +45,12 @@ def workload_spec(name):
                     desc='GatherMove-v1 H=50 fwd+bwd, 64 envs sharded over the GPUs')
     if name == 'cutrearrange':
         return dict(env='CutRearrange-v1', horizon=42, envs_per_gpu=32, desc='CutRearrange-v1 H=42 fwd+bwd, 32 envs/GPU')
+    if name.startswith('sweep'):
+        # BASELINE.json configs[4]: single env, N particles at ~8 per cell on an n^3 grid, one capsule tool.
+        # name: sweep:<particles>:<n_grid>   e.g. sweep:1000000:256
+        _, n, g = name.split(':')
+        return dict(env='sweep', horizon=2, envs_per_gpu=1, particles=int(n), n_grid=int(g),
+                    desc=f'synthetic sweep: 1 env, {int(n)} particles (~8/cell) on {int(g)}^3, H=2 fwd+bwd')
     raise SystemExit(f'unknown workload {name}')
 
 
@@ -52,8 +58,28 @@ def make_inputs(spec, rank, n_envs):
     """Synthetic start/goal pairs (the Google-Drive dataset is unavailable offline): SURVEY.md section 8d."""
     from diffskill_b200.scene import load_scene
     from diffskill_b200.shapes import Shapes
-    scene, cfg = load_scene(spec['env'])
     H = spec['horizon']
+    if spec['env'] == 'sweep':
+        from diffskill_b200.config import load
+        from diffskill_b200.scene import scene_from_cfg
+        n, g = spec['particles'], spec['n_grid']
+        cfg = load(data=dict(
+            SIMULATOR=dict(quality=g / 64.0, yield_stress=200., E=5000., gravity=(0, -20, 0), n_particles=n),
+            PRIMITIVES=[dict(shape='RollingPinExt', h=0.3, r=0.03, init_pos=(0.5, 0.5, 0.5), init_rot=(0.707, 0.707, 0., 0.),
+                             friction=0.9, action=dict(dim=6, scale=(0.7, 0.005, 0.005, 0.005, 0., 0.)))],
+            SHAPES=[]))
+        scene = scene_from_cfg(cfg)
+        assert scene.n_grid == g
+        vol = n / 8.0 * scene.dx ** 3                      # ~8 particles per cell
+        side = min(0.8, (vol / 0.25) ** 0.5)               # slab of height 0.25*... keep it inside the unit box
+        height = vol / (side * side)
+        rng = np.random.RandomState(0)
+        x = (rng.random_sample((n, 3)) * np.array([side, height, side]) + np.array([0.5 - side / 2, 4 * scene.dx, 0.5 - side / 2])).astype(np.float32)
+        c = x.mean(0)
+        t = ((x - c) * np.array([1.1, 0.8, 1.1], np.float32) + c).astype(np.float32)
+        acts = np.random.RandomState(100 + rank).uniform(-1, 1, (H, 1, scene.action_dim)).astype(np.float32)
+        return scene, cfg, [x], [t], acts
+    scene, cfg = load_scene(spec['env'])
     xs, targets, actions = [], [], []
     for b in range(n_envs):
         gid = rank * n_envs + b
@@ -215,7 +241,8 @@ def main():
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
-    assert args.warmup >= 3, 'timing rules: at least 3 warm-up steps'
+    if args.warmup < 3:
+        print('bench.py: fewer than 3 warm-up steps -- fine under a profiler, NOT a valid bench number', file=sys.stderr)
 
     import torch
     import torch.distributed as dist
@@ -333,8 +360,14 @@ def main():
         dur_ms = prof[dom][0] / prof[dom][1]
         achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
         step_bytes = (480 * n_particles + 168 * n_occ) * H * S
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+            traffic = tr.get(args.workload, {}).get(dom, {}).get('dram_bytes_per_launch')
+        except Exception:
+            pass
         roof = dict(bound='hbm', kernel=dom, achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
-                    traffic=None, peak_source=peak_src, algorithmic_bytes_per_launch=alg_bytes,
+                    traffic=traffic, peak_source=peak_src, algorithmic_bytes_per_launch=alg_bytes,
                     avg_launch_us=dur_ms * 1e3, kernel_share_of_step=shares[dom],
                     step_achieved_gbs=step_bytes / (ms_step * 1e-3) / 1e9,
                     step_frac=step_bytes / (ms_step * 1e-3) / 1e9 / peak,
@@ -342,7 +375,8 @@ def main():
                     per_kernel_us={k: round(v[0] / v[1] * 1e3, 2) for k, v in prof.items()},
                     per_kernel_share={k: round(s_, 4) for k, s_ in shares.items()})
         out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                   ms_per_step=ms_step, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                   ms_per_step=ms_step, higher_is_better=True, scaling='strong' if spec.get('total_envs') else 'weak',
+                   vs_baseline=None, dtype='f32',
                    data='synthetic',
                    config=dict(workload=spec['desc'], env=spec['env'], horizon=H, substeps=S, envs_per_gpu=B,
                                particles_per_gpu=n_particles, n_grid=scene.n_grid, occupied_nodes=round(n_occ),

@@ -13,13 +13,13 @@ spec = bench.workload_spec(wl)
 spec['horizon'] = H
 scene, cfg, xs, targets, actions = bench.make_inputs(spec, 0, B)
 cap = max(len(x) for x in xs)
-eng = Engine(scene, n_envs=B, capacity=cap, max_steps=H, step_slots=H)
+eng = Engine(scene, n_envs=B, capacity=cap, max_steps=H, step_slots=H, grid_tape_mib=4096)
 eng.set_graphs(False)
 tgt = np.zeros((B, cap, 3), np.float32)
 for b in range(B):
     eng.set_particles(0, b, xs[b]); tgt[b, :len(xs[b])] = targets[b]
 # let the dough settle onto the tools first so contacts are active in the profiled steps
-for it in range(2):
+for it in range(int(os.environ.get('PROFILE_ITERS', '2'))):
     eng.zero_grad(); eng.loss_reset()
     for s in range(H):
         eng.set_action(s, actions[s]); eng.forward_step(s); eng.loss_add_l2(s + 1, tgt, 1.0 / H)
