@@ -472,7 +472,7 @@ static int stage_in(dsk_engine* e, const float* src, size_t n, int on_device, si
   return 0;
 }
 
-static int grid_ctas(dsk_engine* e) { return 148 * 4; }
+static int grid_ctas(dsk_engine* e) { return e->big ? 148 * 8 : 148 * 2; }
 static dim3 grid_block(dsk_engine* e) { return dim3(GRID_NODES, std::min(e->n_frames, MAX_FRAMES)); }
 
 // zero the grids of the last substep of a fine-grained (dsk_substep / dsk_substep_grad) sequence

@@ -36,21 +36,21 @@ __global__ void __launch_bounds__(128, MINB)
   float4* Gae = Ga + (size_t)env * k.nnode;
   // adjoint of grid_v_out: warp-aggregated scatter
   TileTrack none{nullptr, nullptr, nullptr};
-  {
-    // w * (gvn + c_C gC (offset - fx)) = w * (b0 + i cx + j cy + l cz)
-    float3 b0 = gvn - k.c_C * mv(gC, f3(s.fx, s.fy, s.fz));
-    float3 cx = f3(k.c_C * gC.m[0], k.c_C * gC.m[3], k.c_C * gC.m[6]);
-    float3 cy = f3(k.c_C * gC.m[1], k.c_C * gC.m[4], k.c_C * gC.m[7]);
-    float3 cz = f3(k.c_C * gC.m[2], k.c_C * gC.m[5], k.c_C * gC.m[8]);
-    warp_scatter27(k, active, s, Gae, none, false, env, 0, [&](int i, int j, int l) {
-      float w = s.wx[i] * s.wy[j] * s.wz[l];
-      float3 a = b0 + (float)i * cx + (float)j * cy + (float)l * cz;
-      return make_float4(w * a.x, w * a.y, w * a.z, 0.f);
-    });
-  }
+  // adjoint of grid_v_out[node] = w * (gvn + c_C gC (offset - fx)) = w * (b0 + i cx + j cy + l cz)
+  float3 b0 = gvn - k.c_C * mv(gC, f3(s.fx, s.fy, s.fz));
+  float3 cx = f3(k.c_C * gC.m[0], k.c_C * gC.m[3], k.c_C * gC.m[6]);
+  float3 cy = f3(k.c_C * gC.m[1], k.c_C * gC.m[4], k.c_C * gC.m[7]);
+  float3 cz = f3(k.c_C * gC.m[2], k.c_C * gC.m[5], k.c_C * gC.m[8]);
+  warp_scatter27(k, active, s, Gae, none, false, env, 0, [&](int i, int j, int l) {
+    float w = s.wx[i] * s.wy[j] * s.wz[l];
+    float3 a = b0 + (float)i * cx + (float)j * cy + (float)l * cz;
+    return make_float4(w * a.x, w * a.y, w * a.z, 0.f);
+  });
   if (!active) return;
+  // adjoint of the weights: d/dw [ g . (gvn + c_C gC dpos) ] = g . (b0 + i cx + j cy + l cz);
+  // adjoint of fx through dpos: -c_C gC^T (sum w g)
   float gwx[3] = {0, 0, 0}, gwy[3] = {0, 0, 0}, gwz[3] = {0, 0, 0};
-  float3 gf = f3(0, 0, 0);  // adjoint of fx (through dpos)
+  float3 sg = f3(0, 0, 0);
 #pragma unroll
   for (int i = 0; i < 3; i++)
 #pragma unroll
@@ -59,17 +59,14 @@ __global__ void __launch_bounds__(128, MINB)
       for (int l = 0; l < 3; l++) {
         float4 g4 = Gve[s.ox[i] + s.oy[j] + s.oz[l]];
         float3 g = f3(g4.x, g4.y, g4.z);
-        float w = s.wx[i] * s.wy[j] * s.wz[l];
-        float cw = k.c_C * w;
-        float3 dpos = f3((float)i - s.fx, (float)j - s.fy, (float)l - s.fz);
-        float3 Cd = mv(gC, dpos);   // sum_b gC_ab dpos_b
-        float3 Ctg = mTv(gC, g);    // sum_a gC_ab g_a
-        float gw = dot(g, gvn) + k.c_C * dot(g, Cd);
-        gf -= cw * Ctg;
+        float3 a = b0 + (float)i * cx + (float)j * cy + (float)l * cz;
+        float gw = dot(g, a);
+        sg += (s.wx[i] * s.wy[j] * s.wz[l]) * g;
         gwx[i] += gw * s.wy[j] * s.wz[l];
         gwy[j] += gw * s.wx[i] * s.wz[l];
         gwz[l] += gw * s.wx[i] * s.wy[j];
       }
+  float3 gf = (-k.c_C) * mTv(gC, sg);
   float dw[3];
   bspline1_grad(s.fx, dw);
   gf.x += gwx[0] * dw[0] + gwx[1] * dw[1] + gwx[2] * dw[2];
@@ -263,7 +260,7 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
 
 // p2g.grad + svd_grad + compute_F_tmp.grad fused: gathers adjoints of (grid_v_in, grid_m), reads F.grad[j+1],
 // writes x.grad (adding the g2p part already stored), v.grad, C.grad, F.grad of frame j.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
     k_p2g_adj(SimConst k, const float* __restrict__ fin, const float* __restrict__ adj_in, float* __restrict__ adj_out,
               const float* __restrict__ mat, const int* __restrict__ npart, const float4* __restrict__ Ga) {
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -280,12 +277,15 @@ __global__ void __launch_bounds__(128)
   Stencil s;
   make_stencil(k, x.x, x.y, x.z, s);
   const float4* Gae = Ga + (size_t)env * k.nnode;
-  float3 pmv = k.p_mass * v;
+  // contribution(node) = w * (a0 + i ax + j ay + l az, p_mass)  (see k_p2g); with S0 = sum w G and M = sum w G (x) offset:
+  //   g(v) = p_mass S0 ; g(affine) = dx (M - S0 (x) fx) ; g(fx) through dpos = -dx affine^T S0 ; g(w) = G . a + gm p_mass
+  float3 fxv = f3(s.fx, s.fy, s.fz);
+  float3 a0 = k.p_mass * v - k.dx * mv(o.affine, fxv);
+  float3 ax = f3(k.dx * o.affine.m[0], k.dx * o.affine.m[3], k.dx * o.affine.m[6]);
+  float3 ay = f3(k.dx * o.affine.m[1], k.dx * o.affine.m[4], k.dx * o.affine.m[7]);
+  float3 az = f3(k.dx * o.affine.m[2], k.dx * o.affine.m[5], k.dx * o.affine.m[8]);
   float gwx[3] = {0, 0, 0}, gwy[3] = {0, 0, 0}, gwz[3] = {0, 0, 0};
-  float3 gf = f3(0, 0, 0), gv = f3(0, 0, 0);
-  M3 gA;  // adjoint of affine
-#pragma unroll
-  for (int i = 0; i < 9; i++) gA.m[i] = 0.f;
+  float3 S0 = f3(0, 0, 0), m0 = f3(0, 0, 0), m1 = f3(0, 0, 0), m2 = f3(0, 0, 0);
 #pragma unroll
   for (int i = 0; i < 3; i++)
 #pragma unroll
@@ -294,20 +294,23 @@ __global__ void __launch_bounds__(128)
       for (int l = 0; l < 3; l++) {
         float4 g4 = Gae[s.ox[i] + s.oy[j] + s.oz[l]];
         float3 G = f3(g4.x, g4.y, g4.z);
-        float w = s.wx[i] * s.wy[j] * s.wz[l];
-        float3 dpos = f3(((float)i - s.fx) * k.dx, ((float)j - s.fy) * k.dx, ((float)l - s.fz) * k.dx);
-        float3 a = pmv + mv(o.affine, dpos);
+        float3 a = a0 + (float)i * ax + (float)j * ay + (float)l * az;
         float gw = dot(G, a) + g4.w * k.p_mass;
-        gv += (w * k.p_mass) * G;
-        float3 wG = w * G;
-        gA.m[0] += wG.x * dpos.x; gA.m[1] += wG.x * dpos.y; gA.m[2] += wG.x * dpos.z;
-        gA.m[3] += wG.y * dpos.x; gA.m[4] += wG.y * dpos.y; gA.m[5] += wG.y * dpos.z;
-        gA.m[6] += wG.z * dpos.x; gA.m[7] += wG.z * dpos.y; gA.m[8] += wG.z * dpos.z;
-        gf -= k.dx * mTv(o.affine, wG);
+        float3 wG = (s.wx[i] * s.wy[j] * s.wz[l]) * G;
+        S0 += wG;
+        if (i) m0 += (float)i * wG;
+        if (j) m1 += (float)j * wG;
+        if (l) m2 += (float)l * wG;
         gwx[i] += gw * s.wy[j] * s.wz[l];
         gwy[j] += gw * s.wx[i] * s.wz[l];
         gwz[l] += gw * s.wx[i] * s.wy[j];
       }
+  float3 gv = k.p_mass * S0;
+  float3 gf = (-k.dx) * mTv(o.affine, S0);
+  M3 gA;  // adjoint of affine
+  gA.m[0] = k.dx * (m0.x - S0.x * s.fx); gA.m[1] = k.dx * (m1.x - S0.x * s.fy); gA.m[2] = k.dx * (m2.x - S0.x * s.fz);
+  gA.m[3] = k.dx * (m0.y - S0.y * s.fx); gA.m[4] = k.dx * (m1.y - S0.y * s.fy); gA.m[5] = k.dx * (m2.y - S0.y * s.fz);
+  gA.m[6] = k.dx * (m0.z - S0.z * s.fx); gA.m[7] = k.dx * (m1.z - S0.z * s.fy); gA.m[8] = k.dx * (m2.z - S0.z * s.fz);
   float dw[3];
   bspline1_grad(s.fx, dw);
   gf.x += gwx[0] * dw[0] + gwx[1] * dw[1] + gwx[2] * dw[2];
@@ -449,6 +452,7 @@ __global__ void __launch_bounds__(KINADJ_CTA)
   float* __restrict__ action_grad = args->action_grad;  // [B][A] of this step, +=
   __shared__ ToolParams sT[DSK_MAX_TOOLS];
   __shared__ float s_gu[DSK_MAX_TOOLS][8];
+  __shared__ int s_any_hit;
   extern __shared__ float dyn[];
   int env = blockIdx.x, tid = threadIdx.x;
   int tot = (k.S + 1) * k.K * 8;
@@ -460,7 +464,13 @@ __global__ void __launch_bounds__(KINADJ_CTA)
   const float* P = poses + (size_t)env * tot;
   for (int i = tid; i < tot; i += blockDim.x) sadj[i] = gadj[i];
   if (tid < DSK_MAX_TOOLS * 8) s_gu[tid / 8][tid % 8] = 0.f;
+  if (tid == 0) s_any_hit = 0;
   __syncthreads();
+  // did any tool-tool projection fire in this step?  (almost never: then the chain below needs no projection adjoint)
+  for (int i = tid; i < k.S * k.npairs; i += blockDim.x)
+    if (cidx[((size_t)env * (k.S + 1) + 1) * k.npairs + i] >= 0) s_any_hit = 1;
+  __syncthreads();
+  const bool any_hit = s_any_hit != 0;
   int A = 0;
   for (int t = 0; t < k.K; t++) A += sT[t].action_dim;
   float zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -489,7 +499,7 @@ __global__ void __launch_bounds__(KINADJ_CTA)
   for (int j = k.S - 1; j >= 0; j--) {
     float* a1 = sadj + (size_t)(j + 1) * k.K * 8;
     float* a0 = sadj + (size_t)j * k.K * 8;
-    if (k.npairs > 0) {
+    if (any_hit) {
       if (tid == 0) {
         for (int cc = k.npairs - 1; cc >= 0; cc--) {
           int idx = cidx[((size_t)env * (k.S + 1) + (j + 1)) * k.npairs + cc];

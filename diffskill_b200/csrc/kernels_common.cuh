@@ -189,19 +189,25 @@ DSK_DEV void warp_scatter27(const SimConst& k, bool active, const Stencil& s, fl
     int next_head = above ? (__ffs(above) - 1) : 32;
     int end = min(next_head - 1, 31 - __clz(act));   // last lane of my run
     int maxlen = __reduce_max_sync(0xffffffffu, head ? end - lane + 1 : 0);
+    // nine stencil nodes (one x-slab) at a time: 36 independent shuffle chains per reduction step
 #pragma unroll
-    for (int i = 0; i < 3; i++)
+    for (int i = 0; i < 3; i++) {
+      float4 v[9];
 #pragma unroll
-      for (int j = 0; j < 3; j++)
+      for (int q = 0; q < 9; q++) v[q] = active ? val(i, q / 3, q % 3) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int d = 1; d < maxlen; d <<= 1) {
+        bool take = lane + d <= end;
 #pragma unroll
-        for (int l = 0; l < 3; l++) {
-          float4 v = active ? val(i, j, l) : make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int d = 1; d < maxlen; d <<= 1) {
-            float4 t = f4shfl_down(v, d);
-            if (lane + d <= end) v = f4add(v, t);
-          }
-          if (head) red_add4(&Ge[s.ox[i] + s.oy[j] + s.oz[l]], v);
+        for (int q = 0; q < 9; q++) {
+          float4 t = f4shfl_down(v[q], d);
+          if (take) v[q] = f4add(v[q], t);
         }
+      }
+      if (head) {
+#pragma unroll
+        for (int q = 0; q < 9; q++) red_add4(&Ge[s.ox[i] + s.oy[q / 3] + s.oz[q % 3]], v[q]);
+      }
+    }
     return;
   }
   unsigned todo = act;

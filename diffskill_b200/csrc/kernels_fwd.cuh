@@ -415,10 +415,9 @@ __global__ void __launch_bounds__(128)
   Stencil s;
   make_stencil(k, x.x, x.y, x.z, s);
   const float4* Ge = G + (size_t)env * k.nnode;
+  // new_v = sum w g ; new_C = 4 inv_dx sum w g (x) (offset - fx) = c_C (M - new_v (x) fx),  M = sum w g (x) offset
   float3 nv = f3(0.f, 0.f, 0.f);
-  M3 nC;
-#pragma unroll
-  for (int i = 0; i < 9; i++) nC.m[i] = 0.f;
+  float3 m0 = f3(0.f, 0.f, 0.f), m1 = f3(0.f, 0.f, 0.f), m2 = f3(0.f, 0.f, 0.f);   // columns of M
 #pragma unroll
   for (int i = 0; i < 3; i++)
 #pragma unroll
@@ -427,15 +426,16 @@ __global__ void __launch_bounds__(128)
       for (int l = 0; l < 3; l++) {
         float4 g = Ge[s.ox[i] + s.oy[j] + s.oz[l]];
         float w = s.wx[i] * s.wy[j] * s.wz[l];
-        float3 dpos = f3((float)i - s.fx, (float)j - s.fy, (float)l - s.fz);
-        float cw = k.c_C * w;
-        nv.x += w * g.x;
-        nv.y += w * g.y;
-        nv.z += w * g.z;
-        nC.m[0] += cw * (g.x * dpos.x); nC.m[1] += cw * (g.x * dpos.y); nC.m[2] += cw * (g.x * dpos.z);
-        nC.m[3] += cw * (g.y * dpos.x); nC.m[4] += cw * (g.y * dpos.y); nC.m[5] += cw * (g.y * dpos.z);
-        nC.m[6] += cw * (g.z * dpos.x); nC.m[7] += cw * (g.z * dpos.y); nC.m[8] += cw * (g.z * dpos.z);
+        float3 wg = f3(w * g.x, w * g.y, w * g.z);
+        nv += wg;
+        if (i) m0 += (float)i * wg;
+        if (j) m1 += (float)j * wg;
+        if (l) m2 += (float)l * wg;
       }
+  M3 nC;
+  nC.m[0] = k.c_C * (m0.x - nv.x * s.fx); nC.m[1] = k.c_C * (m1.x - nv.x * s.fy); nC.m[2] = k.c_C * (m2.x - nv.x * s.fz);
+  nC.m[3] = k.c_C * (m0.y - nv.y * s.fx); nC.m[4] = k.c_C * (m1.y - nv.y * s.fy); nC.m[5] = k.c_C * (m2.y - nv.y * s.fz);
+  nC.m[6] = k.c_C * (m0.z - nv.z * s.fx); nC.m[7] = k.c_C * (m1.z - nv.z * s.fy); nC.m[8] = k.c_C * (m2.z - nv.z * s.fz);
   float3 nx = f3(tmax(tmin(x.x + k.dt * nv.x, k.x_hi), k.x_lo), tmax(tmin(x.y + k.dt * nv.y, k.x_hi), k.x_lo),
                  tmax(tmin(x.z + k.dt * nv.z, k.x_hi), k.x_lo));
   store_v3(fout, CX, k.stride, gid, nx);
