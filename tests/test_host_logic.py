@@ -70,3 +70,21 @@ def test_shard_envs_partitions_exactly():
         assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
         sizes = [b[1] - b[0] for b in blocks]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_sinkhorn_stand_in_behaves_like_an_emd():
+    """The plain-torch Sinkhorn used when geomloss is absent (taichi_env.py:23-26 stand-in)."""
+    import torch
+    from diffskill_b200.sim.taichi_env import sinkhorn_emd
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(120, 3, generator=g) * 0.1 + 0.4
+    y = (x + torch.tensor([0.05, 0.0, 0.0])).clone()
+    assert abs(float(sinkhorn_emd(x, x.clone()))) < 1e-4
+    d = float(sinkhorn_emd(x, y))
+    assert 0.04 < d < 0.06                                          # p=1: translation by 0.05 costs ~0.05
+    assert abs(float(sinkhorn_emd(y, x)) - d) < 1e-3
+    xr = x.clone().requires_grad_(True)
+    sinkhorn_emd(xr, y).backward()
+    gx = xr.grad
+    assert torch.isfinite(gx).all()
+    assert float(gx[:, 0].mean()) < 0                                # moving x towards +x lowers the loss
