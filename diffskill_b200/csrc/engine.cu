@@ -525,11 +525,11 @@ static int seq_begin_forward(dsk_engine* e, StepSlot& s) {
     if (capturing) {
       CK(cudaEventRecord(e->ev_fork, e->qs));
       CK(cudaStreamWaitEvent(e->cap_side, e->ev_fork, 0));
-      KL(KID_KINEMATICS, k_kinematics<<<e->B, KIN_CTA, 0, e->cap_side>>>(k, e->d_tools, e->d_args, e->rand_num, s.poses, s.cidx));
+      KL(KID_KINEMATICS, k_kinematics<<<e->B, KIN_CTA, (size_t)(e->S + 1) * e->K * 32, e->cap_side>>>(k, e->d_tools, e->d_args, e->rand_num, s.poses, s.cidx));
       CK(cudaEventRecord(e->ev_join, e->cap_side));
       e->kin_join = true;
     } else {
-      KL(KID_KINEMATICS, k_kinematics<<<e->B, KIN_CTA, 0, e->qs>>>(k, e->d_tools, e->d_args, e->rand_num, s.poses, s.cidx));
+      KL(KID_KINEMATICS, k_kinematics<<<e->B, KIN_CTA, (size_t)(e->S + 1) * e->K * 32, e->qs>>>(k, e->d_tools, e->d_args, e->rand_num, s.poses, s.cidx));
     }
   }
   if (e->cfg.sort_particles && !e->seq_full_sort) {

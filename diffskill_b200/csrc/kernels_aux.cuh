@@ -208,6 +208,43 @@ struct ToolVel {
   float3 v, w;
   float gap_vel;
 };
+// the axis-angle increments of a tool are the same for every substep of an env step (set_velocity,
+// primive_base.py:260-268): their quaternions are built once per step
+struct ToolRotInc {
+  Q4 a, b;   // RollingPinExt: a = w2quat(0,-dth,0), b = w2quat(0,dw,0); others: a = w2quat(w)
+};
+DSK_DEV ToolRotInc tool_rot_inc(const ToolParams& T, const ToolVel& u) {
+  ToolRotInc r;
+  if (T.type == DSK_TOOL_ROLLINGPIN_EXT) {
+    r.a = w2quat(f3(0.f, -u.v.y, 0.f));
+    r.b = w2quat(f3(0.f, u.v.x, 0.f));
+  } else {
+    r.a = w2quat(u.w);
+    r.b = r.a;
+  }
+  return r;
+}
+DSK_DEV Pose tool_fk_inc(const ToolParams& T, const Pose& P, const ToolVel& u, const ToolRotInc& r) {
+  Pose N;
+  N.gap = P.gap;
+  float3 step = u.v;
+  if (T.type == DSK_TOOL_ROLLINGPIN_EXT) {
+    float dw = u.v.x, dy = u.v.z;
+    float3 y_dir = qrot_rn(P.q, f3(0.f, -1.f, 0.f));
+    float3 x_dir = (dw * 0.03f + u.w.x) * cross(f3(0.f, 1.f, 0.f), y_dir);
+    x_dir.y = dy;
+    N.q = qmul(r.a, qmul(P.q, r.b));
+    step = x_dir;
+  } else if (T.type == DSK_TOOL_GRIPPER) {
+    N.gap = tmin(tmax(P.gap - u.gap_vel, T.min_gap), T.max_gap);
+    N.q = qmul(P.q, r.a);
+  } else {
+    N.q = qmul(r.a, P.q);
+  }
+  N.p = f3(tmax(tmin(P.p.x + step.x, T.hi[0]), T.lo[0]), tmax(tmin(P.p.y + step.y, T.hi[1]), T.lo[1]),
+           tmax(tmin(P.p.z + step.z, T.hi[2]), T.lo[2]));
+  return N;
+}
 DSK_DEV Pose tool_fk(const ToolParams& T, const Pose& P, const ToolVel& u) {
   Pose N;
   N.gap = P.gap;
@@ -371,9 +408,12 @@ __global__ void k_loss_l2(SimConst k, const float* __restrict__ frame, float* __
   if ((threadIdx.x & 31) == 0 && l != 0.f && gid < k.stride) atomicAdd(&loss[env], l);
 }
 
-#define KIN_CTA 128
+#define KIN_CTA 256
 // One CTA per env: S substeps of forward_kinematics for every tool, then (if any pair) set_surface_points,
 // set_collision_idx (deterministic first minimum) and apply_collision_projection (mpm_simulator.py:286-305).
+// Tool-tool projections are rare, so the kernel is optimistic: (1) the kinematics chain of all S substeps without
+// projections, one thread per tool; (2) the collision query of every (substep, pair) in parallel, one warp per query;
+// (3) only from the first substep that actually hit, the reference's sequential per-substep procedure.
 __global__ void __launch_bounds__(KIN_CTA)
     k_kinematics(SimConst k, const ToolParams* __restrict__ tools, const StepArgs* __restrict__ args,
                  const float* __restrict__ rand_num, float* __restrict__ poses /*[B][S+1][K][8]*/,
@@ -386,15 +426,75 @@ __global__ void __launch_bounds__(KIN_CTA)
   __shared__ float red_d[KIN_CTA / 32];
   __shared__ int red_i[KIN_CTA / 32];
   __shared__ int s_idx[DSK_MAX_PAIRS];
+  __shared__ int s_first;
+  extern __shared__ float sAll[];           // [(S+1)][K][8] projection-free chain
   int env = blockIdx.x, tid = threadIdx.x;
+  const int per = k.K * 8;
   for (int i = tid; i < k.K * (int)(sizeof(ToolParams) / 4); i += blockDim.x) ((int*)sT)[i] = ((const int*)tools)[i];
-  for (int i = tid; i < k.K * 8; i += blockDim.x) sP[i / 8][i % 8] = state0[(size_t)env * k.K * 8 + i];
+  for (int i = tid; i < per; i += blockDim.x) sAll[i] = state0[(size_t)env * per + i];
+  if (tid == 0) s_first = k.S;
   __syncthreads();
-  float* out = poses + (size_t)env * (k.S + 1) * k.K * 8;
-  for (int i = tid; i < k.K * 8; i += blockDim.x) out[i] = sP[i / 8][i % 8];
   int A = 0;
   for (int t = 0; t < k.K; t++) A += sT[t].action_dim;
-  for (int j = 0; j < k.S; j++) {
+  if (tid < k.K) {   // (1) projection-free chain
+    int off = 0;
+    for (int t = 0; t < tid; t++) off += sT[t].action_dim;
+    float zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    ToolVel u = action_to_vel(sT[tid], action ? action + (size_t)env * A + off : zero, k.S);
+    ToolRotInc ri = tool_rot_inc(sT[tid], u);
+    Pose Pc = load_pose(sAll + tid * 8);
+    for (int j = 0; j < k.S; j++) {
+      Pc = tool_fk_inc(sT[tid], Pc, u, ri);
+      store_pose(sAll + (size_t)(j + 1) * per + tid * 8, Pc);
+    }
+  }
+  __syncthreads();
+  if (k.npairs > 0) {   // (2) all collision queries at once, one warp per (substep, pair)
+    int warp = tid >> 5, lane = tid & 31;
+    for (int it = warp; it < k.S * k.npairs; it += KIN_CTA / 32) {
+      int j = it / k.npairs, c = it - j * k.npairs;
+      int ti = k.pairs[c][0], tj = k.pairs[c][1];
+      Pose Pi = load_pose(sAll + (size_t)(j + 1) * per + ti * 8), Pj = load_pose(sAll + (size_t)(j + 1) * per + tj * 8);
+      // the frames of tool i and their normalised inverse rotations are shared by the 600 points of the query
+      const ToolParams& Ti = sT[ti];
+      bool grip = Ti.type == DSK_TOOL_GRIPPER;
+      Frame Fa = grip ? jaw_frame(Pi, -1.f) : tool_frame(Pi), Fb = grip ? jaw_frame(Pi, 1.f) : Fa;
+      Q4 qa = qconj_normalized_rn(Fa.q);
+      int kind = grip ? SDF_BOX : sdf_kind(Ti.type);
+      float best = 0.f;
+      int bi = -1;
+      for (int q = lane; q < DSK_NUM_COLLISION_POINTS; q += 32) {
+        float3 pt = surface_point(sT[tj], Pj, rand_num + ((size_t)c * DSK_NUM_COLLISION_POINTS + q) * 3);
+        float d = local_sdf(Ti, kind, qrot_rn(qa, sub3_rn(pt, Fa.o)));
+        if (grip) d = tmin(d, local_sdf(Ti, kind, qrot_rn(qa, sub3_rn(pt, Fb.o))));
+        if (d < best) {
+          best = d;
+          bi = q;
+        }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        float od = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi >= 0 && (bi < 0 || od < best || (od == best && oi < bi))) {
+          best = od;
+          bi = oi;
+        }
+      }
+      if (lane == 0) {
+        cidx[((size_t)env * (k.S + 1) + (j + 1)) * k.npairs + c] = bi;
+        if (bi >= 0) atomicMin(&s_first, j);
+      }
+    }
+    __syncthreads();
+  }
+  const int j0 = s_first;   // first substep whose frame needs a projection (S: none)
+  float* out = poses + (size_t)env * (k.S + 1) * k.K * 8;
+  for (int i = tid; i < (j0 + 1) * per && i < (k.S + 1) * per; i += blockDim.x) out[i] = sAll[i];
+  if (j0 >= k.S) return;
+  for (int i = tid; i < per; i += blockDim.x) sP[i / 8][i % 8] = sAll[(size_t)j0 * per + i];
+  __syncthreads();
+  // (3) the reference's sequential procedure from substep j0 on
+  for (int j = j0; j < k.S; j++) {
     if (tid < k.K) {
       int off = 0;
       for (int t = 0; t < tid; t++) off += sT[t].action_dim;

@@ -88,3 +88,20 @@ def test_sinkhorn_stand_in_behaves_like_an_emd():
     gx = xr.grad
     assert torch.isfinite(gx).all()
     assert float(gx[:, 0].mean()) < 0                                # moving x towards +x lowers the loss
+
+
+def test_dataset_format_round_trip(tmp_path):
+    """init/state_i.xz (lzma pickle of TaichiEnv.get_state()) + target/target_i.npy, multitask_env.py:24-32,85-89."""
+    from diffskill_b200.envs import dataset
+    rng = np.random.RandomState(0)
+    n = 50
+    state = {'state': [rng.rand(n, 3), rng.rand(n, 3), rng.rand(n, 3, 3), rng.rand(n, 3, 3), rng.rand(7), rng.rand(8)],
+             'softness': 666., 'is_copy': True}
+    root = str(tmp_path / 'ds')
+    dataset.save_pair(root, 3, state, rng.rand(n, 3))
+    dataset.save_pair(root, 1, state, rng.rand(n, 3))
+    assert dataset.list_pairs(root) == [1, 3]
+    st, tgt = dataset.load_pair(root, 3)
+    assert st['softness'] == 666. and st['is_copy'] is True and len(st['state']) == 6
+    assert all(np.array_equal(a, b) for a, b in zip(st['state'], state['state']))
+    assert tgt.shape == (n, 3) and tgt.dtype == np.float64
