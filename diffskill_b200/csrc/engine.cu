@@ -125,6 +125,7 @@ struct dsk_engine {
   bool big = false;   // enough particles to fill the machine: prefer occupancy over registers
   cudaStream_t cap_side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  std::vector<cudaEvent_t> ev_restored, ev_main;   // per backward position, used while capturing the pipelined adjoint
   bool kin_join = false;
   int tape_cap = 0;       // grid-tape capacity per step slot, in tiles (0: taping off)
   bool tape_flags_stale = true;
@@ -342,6 +343,12 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
     CK(cudaStreamCreateWithFlags(&e->cap_side, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    e->ev_restored.resize(e->S);
+    e->ev_main.resize(e->S);
+    for (int i = 0; i < e->S; i++) {
+      CK(cudaEventCreateWithFlags(&e->ev_restored[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&e->ev_main[i], cudaEventDisableTiming));
+    }
     DA(e->perm_cache, k.stride);
     if (getenv("DSK_RESORT_INTERVAL")) e->resort_interval = std::max(1, atoi(getenv("DSK_RESORT_INTERVAL")));
     e->use_graphs = getenv("DSK_NO_GRAPHS") == nullptr;
@@ -383,6 +390,8 @@ int dsk_destroy(dsk_engine* e) {
   if (e->cap_side) cudaStreamDestroy(e->cap_side);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
+  for (auto ev : e->ev_restored) cudaEventDestroy(ev);
+  for (auto ev : e->ev_main) cudaEventDestroy(ev);
   for (auto& r : e->prof) {
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
@@ -662,12 +671,61 @@ static int seq_end_backward(dsk_engine* e, StepSlot& s) {
   return 0;
 }
 
+// Adjoint sequence with a verified grid tape, captured as a two-branch graph: the side branch restores the grids of
+// substep q (and clears the set position q-2 used) while the main branch still works on position q-1, so the
+// restore leaves the critical path:   main:  g2p_adj(q) -> grid_op_adj(q) -> p2g_adj(q)
+//                                     side:  clear(set of q-2) -> restore(q)      [waits for main(q-2)]
+static int enqueue_backward_pipelined(dsk_engine* e, StepSlot& s) {
+  SimConst& k = e->k;
+  cudaStream_t mainq = e->qs, side = e->cap_side;
+  if (seq_begin_backward(e, s)) return -1;
+  CK(cudaEventRecord(e->ev_fork, mainq));
+  CK(cudaStreamWaitEvent(side, e->ev_fork, 0));
+  int nb = cdiv(k.stride, 128);
+  for (int q = 0; q < e->S; q++) {
+    int j = e->S - 1 - q, set = (q + 1) & 1;
+    TileTrack tt{e->tile_epoch[set], e->tile_list[set], e->tile_count + ((q + 1) & 3)};
+    if (q >= 2) {
+      CK(cudaStreamWaitEvent(side, e->ev_main[q - 2], 0));
+      KL(KID_GRID_RECOMPUTE, k_clear_set<<<grid_ctas(e), GRID_CTA, 0, side>>>(k, e->tile_list[set], e->tile_count + ((q - 1) & 3),
+                                                                              e->G0[set], e->Gv[set], e->Ga[set]));
+    }
+    KL(KID_GRID_RECOMPUTE, k_tape_restore<<<grid_ctas(e), GRID_NODES, 0, side>>>(k, s.tape, j, e->G0[set], e->Gv[set], tt.list, tt.count,
+                                                                                 nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+    CK(cudaEventRecord(e->ev_restored[q], side));
+    CK(cudaStreamWaitEvent(mainq, e->ev_restored[q], 0));
+    float* fin = s.frames + (size_t)j * e->frame_floats;
+    float* fnext = s.frames + (size_t)(j + 1) * e->frame_floats;
+    float* ain = e->adjw[e->bwd_cur];
+    float* aout = e->adjw[e->bwd_cur ^ 1];
+    if (e->big)
+      KL(KID_G2P_ADJ, k_g2p_adj<3><<<nb, 128, 0, mainq>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
+    else
+      KL(KID_G2P_ADJ, k_g2p_adj<1><<<nb, 128, 0, mainq>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
+    KL(KID_GRID_ADJ, k_grid_adj<<<grid_ctas(e), grid_block(e), 0, mainq>>>(k, e->d_tools, s.poses, j, e->G0[set], e->Ga[set],
+                                                                          tt.list, tt.count, e->pose_adj));
+    KL(KID_P2G_ADJ, k_p2g_adj<<<nb, 128, 0, mainq>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]));
+    CK(cudaEventRecord(e->ev_main[q], mainq));
+    e->bwd_cur ^= 1;
+  }
+  LAUNCH_CHECK();
+  if (seq_end_backward(e, s)) return -1;
+  // both sets still hold data: positions S-2 and S-1
+  if (e->S >= 2) {
+    int q = e->S - 2, set = (q + 1) & 1;
+    KL(KID_GRID, k_clear_set<<<grid_ctas(e), GRID_CTA, 0, mainq>>>(k, e->tile_list[set], e->tile_count + ((q + 1) & 3), e->G0[set],
+                                                                   e->Gv[set], e->Ga[set]));
+  }
+  return seq_clear(e, e->S - 1, true);
+}
+
 // ---- whole sequences, eager or as a replayed graph ---------------------------------------------------------------
 enum SeqKind { SEQ_FWD, SEQ_RECOMPUTE, SEQ_BWD, SEQ_BWD_TAPE, SEQ_BWD_TAPE_TRUSTED };
 static int enqueue_sequence(dsk_engine* e, StepSlot& s, SeqKind kind) {
   if (kind == SEQ_BWD || kind == SEQ_BWD_TAPE || kind == SEQ_BWD_TAPE_TRUSTED) {
     e->seq_use_tape = kind != SEQ_BWD;
     e->seq_tape_trusted = kind == SEQ_BWD_TAPE_TRUSTED;
+    if (e->seq_tape_trusted && e->qs == e->cap_stream && !getenv("DSK_NO_PIPELINE")) return enqueue_backward_pipelined(e, s);
     if (seq_begin_backward(e, s)) return -1;
     for (int q = 0; q < e->S; q++)
       if (seq_substep_grad(e, s, q, e->S - 1 - q)) return -1;

@@ -304,6 +304,11 @@ DSK_DEV void contact_geometry(const ToolParams& T, int kind, const Frame& F0, co
 }
 
 #define GRID_NODES 64
+__global__ void __launch_bounds__(GRID_CTA)
+    k_clear_set(SimConst k, const int* __restrict__ list, const int* __restrict__ count, float4* c0, float4* c1, float4* c2) {
+  clear_tiles(k, list, *count, c0, c1, c2);
+}
+
 // grid_op over active tiles.  Gin holds (momentum, mass); Gout receives (velocity, mass) and may alias Gin.
 // blockDim = (64, n_frames).
 __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
