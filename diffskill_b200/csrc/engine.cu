@@ -589,6 +589,52 @@ static int seq_substep(dsk_engine* e, StepSlot& s, int q, int j, bool write_stat
   LAUNCH_CHECK();
   return 0;
 }
+// grid_op of substep q (position q == substep index in forward sequences), with taping
+static int seq_grid_fwd(dsk_engine* e, StepSlot& s, int q) {
+  SimConst& k = e->k;
+  int set = (q + 1) & 1, prev = set ^ 1;
+  bool clr = q > 0;
+  if (e->kin_join) {
+    CK(cudaStreamWaitEvent(e->qs, e->ev_join, 0));
+    e->kin_join = false;
+  }
+  KL(KID_GRID, k_grid<<<grid_ctas(e), grid_block(e), 0, e->qs>>>(
+                   k, e->d_tools, s.poses, q, e->G0[set], e->G0[set], e->tile_list[set], e->tile_count + ((q + 1) & 3),
+                   clr ? e->tile_list[prev] : nullptr, e->tile_count + (q & 3), clr ? e->G0[prev] : nullptr, nullptr,
+                   nullptr, e->tile_count + ((q + 3) & 3), s.tape, nullptr));
+  LAUNCH_CHECK();
+  return 0;
+}
+// forward substeps of a whole step with g2p(q) fused into p2g(q+1)
+static int seq_forward_fused(dsk_engine* e, StepSlot& s) {
+  SimConst& k = e->k;
+  int nb = cdiv(k.stride, 128);
+  auto frame = [&](int j) { return s.frames + (size_t)j * e->frame_floats; };
+  {
+    TileTrack tt{e->tile_epoch[1], e->tile_list[1], e->tile_count + 1};
+    if (e->big)
+      KL(KID_P2G, k_p2g<true, 3><<<nb, 128, 0, e->qs>>>(k, frame(0), frame(1), s.mat, e->npart, e->G0[1], tt, e->d_args, 0, nullptr));
+    else
+      KL(KID_P2G, k_p2g<true, 1><<<nb, 128, 0, e->qs>>>(k, frame(0), frame(1), s.mat, e->npart, e->G0[1], tt, e->d_args, 0, nullptr));
+  }
+  for (int q = 0; q < e->S; q++) {
+    if (seq_grid_fwd(e, s, q)) return -1;
+    int set = (q + 1) & 1, nset = set ^ 1;
+    if (q + 1 < e->S) {
+      TileTrack tt{e->tile_epoch[nset], e->tile_list[nset], e->tile_count + ((q + 2) & 3)};
+      if (e->big)
+        KL(KID_P2G, k_g2p2g<3><<<nb, 128, 0, e->qs>>>(k, frame(q), frame(q + 1), frame(q + 2), s.mat, e->npart, e->G0[set],
+                                                     e->G0[nset], tt, e->d_args, q + 1));
+      else
+        KL(KID_P2G, k_g2p2g<1><<<nb, 128, 0, e->qs>>>(k, frame(q), frame(q + 1), frame(q + 2), s.mat, e->npart, e->G0[set],
+                                                     e->G0[nset], tt, e->d_args, q + 1));
+    } else {
+      KL(KID_G2P, k_g2p<<<nb, 128, 0, e->qs>>>(k, frame(q), frame(q + 1), e->npart, e->G0[set]));
+    }
+  }
+  LAUNCH_CHECK();
+  return 0;
+}
 static int seq_end_forward(dsk_engine* e, StepSlot& s, bool store) {
   SimConst& k = e->k;
   if (store) {
@@ -733,8 +779,12 @@ static int enqueue_sequence(dsk_engine* e, StepSlot& s, SeqKind kind) {
     return seq_clear(e, e->S - 1, true);
   }
   if (seq_begin_forward(e, s)) return -1;
-  for (int q = 0; q < e->S; q++)
-    if (seq_substep(e, s, q, q, true)) return -1;
+  if (getenv("DSK_NO_G2P2G")) {
+    for (int q = 0; q < e->S; q++)
+      if (seq_substep(e, s, q, q, true)) return -1;
+  } else if (seq_forward_fused(e, s)) {
+    return -1;
+  }
   if (seq_end_forward(e, s, kind == SEQ_FWD)) return -1;
   return seq_clear(e, e->S - 1, false);
 }

@@ -409,19 +409,11 @@ __global__ void __launch_bounds__(GRID_NODES)
   }
 }
 
-__global__ void __launch_bounds__(128)
-    k_g2p(SimConst k, const float* __restrict__ fin, float* __restrict__ fout, const int* __restrict__ npart,
-          const float4* __restrict__ G) {
-  int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= k.stride) return;
-  int env = gid / k.Npad, p = gid - env * k.Npad;
-  if (p >= npart[env]) return;
-  float3 x = load_v3(fin, CX, k.stride, gid);
-  Stencil s;
-  make_stencil(k, x.x, x.y, x.z, s);
-  const float4* Ge = G + (size_t)env * k.nnode;
-  // new_v = sum w g ; new_C = 4 inv_dx sum w g (x) (offset - fx) = c_C (M - new_v (x) fx),  M = sum w g (x) offset
-  float3 nv = f3(0.f, 0.f, 0.f);
+// g2p of one particle (mpm_simulator.py:264-283): new_v = sum w g ; new_C = 4 inv_dx sum w g (x) (offset - fx)
+//   = c_C (M - new_v (x) fx),  M = sum w g (x) offset
+DSK_DEV void g2p_particle(const SimConst& k, const Stencil& s, const float4* __restrict__ Ge, float3 x, float3& nx,
+                          float3& nv, M3& nC) {
+  nv = f3(0.f, 0.f, 0.f);
   float3 m0 = f3(0.f, 0.f, 0.f), m1 = f3(0.f, 0.f, 0.f), m2 = f3(0.f, 0.f, 0.f);   // columns of M
 #pragma unroll
   for (int i = 0; i < 3; i++)
@@ -437,13 +429,69 @@ __global__ void __launch_bounds__(128)
         if (j) m1 += (float)j * wg;
         if (l) m2 += (float)l * wg;
       }
-  M3 nC;
   nC.m[0] = k.c_C * (m0.x - nv.x * s.fx); nC.m[1] = k.c_C * (m1.x - nv.x * s.fy); nC.m[2] = k.c_C * (m2.x - nv.x * s.fz);
   nC.m[3] = k.c_C * (m0.y - nv.y * s.fx); nC.m[4] = k.c_C * (m1.y - nv.y * s.fy); nC.m[5] = k.c_C * (m2.y - nv.y * s.fz);
   nC.m[6] = k.c_C * (m0.z - nv.z * s.fx); nC.m[7] = k.c_C * (m1.z - nv.z * s.fy); nC.m[8] = k.c_C * (m2.z - nv.z * s.fz);
-  float3 nx = f3(tmax(tmin(x.x + k.dt * nv.x, k.x_hi), k.x_lo), tmax(tmin(x.y + k.dt * nv.y, k.x_hi), k.x_lo),
-                 tmax(tmin(x.z + k.dt * nv.z, k.x_hi), k.x_lo));
+  nx = f3(tmax(tmin(x.x + k.dt * nv.x, k.x_hi), k.x_lo), tmax(tmin(x.y + k.dt * nv.y, k.x_hi), k.x_lo),
+          tmax(tmin(x.z + k.dt * nv.z, k.x_hi), k.x_lo));
+}
+
+__global__ void __launch_bounds__(128)
+    k_g2p(SimConst k, const float* __restrict__ fin, float* __restrict__ fout, const int* __restrict__ npart,
+          const float4* __restrict__ G) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= k.stride) return;
+  int env = gid / k.Npad, p = gid - env * k.Npad;
+  if (p >= npart[env]) return;
+  float3 x = load_v3(fin, CX, k.stride, gid);
+  Stencil s;
+  make_stencil(k, x.x, x.y, x.z, s);
+  float3 nx, nv;
+  M3 nC;
+  g2p_particle(k, s, G + (size_t)env * k.nnode, x, nx, nv, nC);
   store_v3(fout, CX, k.stride, gid, nx);
   store_v3(fout, CV, k.stride, gid, nv);
   store_m3(fout, CC, k.stride, gid, nC);
+}
+
+// Fused g2p of substep q and p2g of substep q+1 ("G2P2G"): the particle state of frame q+1 is produced and consumed
+// in registers (it is still stored: the adjoint needs the frame), one launch fewer per substep.  Gprev = grid set of
+// substep q (velocities), Gnext = the other set (scatter target, tiles tracked for substep q+1).
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
+    k_g2p2g(SimConst k, const float* __restrict__ fprev, float* __restrict__ fcur, float* __restrict__ fnext,
+            const float* __restrict__ mat, const int* __restrict__ npart, const float4* __restrict__ Gprev,
+            float4* __restrict__ Gnext, TileTrack tt, const StepArgs* __restrict__ args, int qnext) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  int env = min(gid / k.Npad, k.B - 1), p = gid - env * k.Npad;
+  bool active = gid < k.stride && p < npart[env];
+  int g = active ? gid : env * k.Npad;
+  float3 x = load_v3(fprev, CX, k.stride, g);
+  Stencil s;
+  make_stencil(k, x.x, x.y, x.z, s);
+  float3 nx, nv;
+  M3 C;
+  g2p_particle(k, s, Gprev + (size_t)env * k.nnode, x, nx, nv, C);
+  M3 F = load_m3(fcur, CF, k.stride, g);   // written by the p2g of substep q
+  if (active) {
+    store_v3(fcur, CX, k.stride, gid, nx);
+    store_v3(fcur, CV, k.stride, gid, nv);
+    store_m3(fcur, CC, k.stride, gid, C);
+  }
+  float mu = mat[g], lam = mat[k.stride + g], ys = mat[2 * k.stride + g];
+  P2GParticle o;
+  p2g_particle(k, C, F, mu, lam, ys, o);
+  if (active) store_m3(fnext, CF, k.stride, gid, o.newF);
+  make_stencil(k, nx.x, nx.y, nx.z, s);
+  float3 fxv = f3(s.fx, s.fy, s.fz);
+  float3 a0 = k.p_mass * nv - k.dx * mv(o.affine, fxv);
+  float3 ax = f3(k.dx * o.affine.m[0], k.dx * o.affine.m[3], k.dx * o.affine.m[6]);
+  float3 ay = f3(k.dx * o.affine.m[1], k.dx * o.affine.m[4], k.dx * o.affine.m[7]);
+  float3 az = f3(k.dx * o.affine.m[2], k.dx * o.affine.m[5], k.dx * o.affine.m[8]);
+  warp_scatter27(k, active, s, Gnext + (size_t)env * k.nnode, tt, true, env, args->epoch_base + qnext + 1,
+                 [&](int i, int j, int l) {
+                   float w = s.wx[i] * s.wy[j] * s.wz[l];
+                   float3 a = a0 + (float)i * ax + (float)j * ay + (float)l * az;
+                   return make_float4(w * a.x, w * a.y, w * a.z, w * k.p_mass);
+                 });
 }
