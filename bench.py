@@ -34,6 +34,7 @@ KERNEL_BYTES = {
     'p2g': (132, 16), 'grid_op': (0, 28), 'g2p': (60, 12),                                     # fwd: 192 / 56
     'p2g_recompute': (96, 16), 'grid_op_recompute': (0, 28), 'g2p_adj': (60, 24),               # bwd: 288 / 112
     'grid_op_adj': (0, 28), 'p2g_adj': (132, 16),
+    'g2p2g': (192, 28),                                                                          # fused g2p(q) + p2g(q+1)
 }
 
 

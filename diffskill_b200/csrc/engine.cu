@@ -50,11 +50,11 @@ struct StepSlot {
 
 enum KernelId {
   KID_SORT = 0, KID_KINEMATICS, KID_P2G, KID_GRID, KID_G2P, KID_P2G_RECOMPUTE, KID_GRID_RECOMPUTE, KID_G2P_ADJ,
-  KID_GRID_ADJ, KID_P2G_ADJ, KID_KINEMATICS_ADJ, KID_REORDER, KID_IO, KID_LOSS, KID_COUNT
+  KID_GRID_ADJ, KID_P2G_ADJ, KID_KINEMATICS_ADJ, KID_REORDER, KID_IO, KID_LOSS, KID_G2P2G, KID_COUNT
 };
 static const char* kKernelNames[KID_COUNT] = {
     "sort", "kinematics", "p2g", "grid_op", "g2p", "p2g_recompute", "grid_op_recompute", "g2p_adj",
-    "grid_op_adj", "p2g_adj", "kinematics_adj", "reorder", "io", "loss"};
+    "grid_op_adj", "p2g_adj", "kinematics_adj", "reorder", "io", "loss", "g2p2g"};
 
 struct ProfRec {
   int kid;
@@ -623,10 +623,10 @@ static int seq_forward_fused(dsk_engine* e, StepSlot& s) {
     if (q + 1 < e->S) {
       TileTrack tt{e->tile_epoch[nset], e->tile_list[nset], e->tile_count + ((q + 2) & 3)};
       if (e->big)
-        KL(KID_P2G, k_g2p2g<3><<<nb, 128, 0, e->qs>>>(k, frame(q), frame(q + 1), frame(q + 2), s.mat, e->npart, e->G0[set],
+        KL(KID_G2P2G, k_g2p2g<3><<<nb, 128, 0, e->qs>>>(k, frame(q), frame(q + 1), frame(q + 2), s.mat, e->npart, e->G0[set],
                                                      e->G0[nset], tt, e->d_args, q + 1));
       else
-        KL(KID_P2G, k_g2p2g<1><<<nb, 128, 0, e->qs>>>(k, frame(q), frame(q + 1), frame(q + 2), s.mat, e->npart, e->G0[set],
+        KL(KID_G2P2G, k_g2p2g<1><<<nb, 128, 0, e->qs>>>(k, frame(q), frame(q + 1), frame(q + 2), s.mat, e->npart, e->G0[set],
                                                      e->G0[nset], tt, e->d_args, q + 1));
     } else {
       KL(KID_G2P, k_g2p<<<nb, 128, 0, e->qs>>>(k, frame(q), frame(q + 1), e->npart, e->G0[set]));
