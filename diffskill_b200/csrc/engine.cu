@@ -123,6 +123,7 @@ struct dsk_engine {
   int sort_age = 1 << 30, resort_interval = 1;   // >1 re-uses the last permutation (cheaper sort, more fragmented warps)
   bool seq_full_sort = true;
   bool big = false;   // enough particles to fill the machine: prefer occupancy over registers
+  bool flat_grid = false;   // many active tiles: throughput layout of the grid kernels
   cudaStream_t cap_side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<cudaEvent_t> ev_restored, ev_main;   // per backward position, used while capturing the pipelined adjoint
@@ -212,6 +213,11 @@ static void fill_tool(ToolParams& T, const dsk_tool_desc& d) {
   T.prot_inv = Q4{inv * w, inv * -x, inv * -y, inv * -z};
   T.min_gap = (float)d.minimal_gap;
   T.max_gap = (float)d.maximal_gap;
+  if (d.type == DSK_TOOL_CAPSULE || d.type == DSK_TOOL_ROLLINGPIN_EXT)
+    T.bound_r = (float)(d.h / 2 + d.r);
+  else
+    T.bound_r = (float)std::sqrt(d.size[0] * d.size[0] + d.size[1] * d.size[1] + d.size[2] * d.size[2]);
+  T.bound_r *= 1.001f;
 }
 
 extern "C" {
@@ -298,6 +304,9 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
   }
   e->frame_floats = (size_t)FRAME_COMPS * k.stride;
   e->big = (size_t)c->n_envs * c->particle_capacity >= 65536;
+  if (const char* v = getenv("DSK_FORCE_BIG")) e->big = atoi(v) != 0;
+  e->flat_grid = e->big;
+  if (const char* v = getenv("DSK_FLAT_GRID")) e->flat_grid = atoi(v) != 0;
   e->tool_floats = (size_t)e->B * std::max(1, e->K) * 8;
   int rc = [&]() -> int {
     DA(e->ckpt, (size_t)(e->H + 1) * e->frame_floats);
@@ -483,6 +492,18 @@ static int stage_in(dsk_engine* e, const float* src, size_t n, int on_device, si
 
 static int grid_ctas(dsk_engine* e) { return e->big ? 148 * 8 : 148 * 2; }
 static dim3 grid_block(dsk_engine* e) { return dim3(GRID_NODES, std::min(e->n_frames, MAX_FRAMES)); }
+// batched engines use the throughput layout of the grid kernels (k_grid_flat / k_grid_adj_flat), single scenes the
+// latency layout (node x frame)
+#define GRID_FWD_LAUNCH(e, stream, ...)                                            \
+  do {                                                                             \
+    if ((e)->flat_grid) k_grid_flat<<<148 * 4, FLAT_THREADS, 0, stream>>>(__VA_ARGS__); \
+    else k_grid<<<grid_ctas(e), grid_block(e), 0, stream>>>(__VA_ARGS__);          \
+  } while (0)
+#define GRID_ADJ_LAUNCH(e, stream, ...)                                                \
+  do {                                                                                 \
+    if ((e)->flat_grid) k_grid_adj_flat<<<148 * 4, FLAT_THREADS, 0, stream>>>(__VA_ARGS__); \
+    else k_grid_adj<<<grid_ctas(e), grid_block(e), 0, stream>>>(__VA_ARGS__);          \
+  } while (0)
 
 // zero the grids of the last substep of a fine-grained (dsk_substep / dsk_substep_grad) sequence
 static int flush_pending_clear(dsk_engine* e) {
@@ -581,7 +602,7 @@ static int seq_substep(dsk_engine* e, StepSlot& s, int q, int j, bool write_stat
     CK(cudaStreamWaitEvent(e->qs, e->ev_join, 0));
     e->kin_join = false;
   }
-  KL(KID_GRID, k_grid<<<grid_ctas(e), grid_block(e), 0, e->qs>>>(
+  KL(KID_GRID, GRID_FWD_LAUNCH(e, e->qs,
                    k, e->d_tools, s.poses, j, e->G0[set], e->G0[set], tt.list, tt.count,
                    clr ? e->tile_list[prev] : nullptr, e->tile_count + (q & 3), clr ? e->G0[prev] : nullptr, nullptr,
                    nullptr, e->tile_count + ((q + 3) & 3), write_state ? s.tape : GridTape{nullptr, nullptr, nullptr, nullptr, 0}, nullptr));
@@ -598,7 +619,7 @@ static int seq_grid_fwd(dsk_engine* e, StepSlot& s, int q) {
     CK(cudaStreamWaitEvent(e->qs, e->ev_join, 0));
     e->kin_join = false;
   }
-  KL(KID_GRID, k_grid<<<grid_ctas(e), grid_block(e), 0, e->qs>>>(
+  KL(KID_GRID, GRID_FWD_LAUNCH(e, e->qs,
                    k, e->d_tools, s.poses, q, e->G0[set], e->G0[set], e->tile_list[set], e->tile_count + ((q + 1) & 3),
                    clr ? e->tile_list[prev] : nullptr, e->tile_count + (q & 3), clr ? e->G0[prev] : nullptr, nullptr,
                    nullptr, e->tile_count + ((q + 3) & 3), s.tape, nullptr));
@@ -684,7 +705,7 @@ static int seq_substep_grad(dsk_engine* e, StepSlot& s, int q, int j) {
   }
   if (!(e->seq_use_tape && e->seq_tape_trusted)) {
     KL(KID_P2G_RECOMPUTE, k_p2g<false, 3><<<nb, 128, 0, e->qs>>>(k, fin, nullptr, s.mat, e->npart, e->G0[set], tt, e->d_args, q, run_if));
-    KL(KID_GRID_RECOMPUTE, k_grid<<<grid_ctas(e), grid_block(e), 0, e->qs>>>(
+    KL(KID_GRID_RECOMPUTE, GRID_FWD_LAUNCH(e, e->qs,
                                k, e->d_tools, s.poses, j, e->G0[set], e->Gv[set], tt.list, tt.count,
                                clr ? e->tile_list[prev] : nullptr, e->tile_count + (q & 3), clr ? e->G0[prev] : nullptr,
                                clr ? e->Gv[prev] : nullptr, clr ? e->Ga[prev] : nullptr, e->tile_count + ((q + 3) & 3),
@@ -694,7 +715,7 @@ static int seq_substep_grad(dsk_engine* e, StepSlot& s, int q, int j) {
     KL(KID_G2P_ADJ, k_g2p_adj<3><<<nb, 128, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
   else
     KL(KID_G2P_ADJ, k_g2p_adj<1><<<nb, 128, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
-  KL(KID_GRID_ADJ, k_grid_adj<<<grid_ctas(e), grid_block(e), 0, e->qs>>>(k, e->d_tools, s.poses, j, e->G0[set], e->Ga[set],
+  KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, e->qs, k, e->d_tools, s.poses, j, e->G0[set], e->Ga[set],
                                                                       tt.list, tt.count, e->pose_adj));
   KL(KID_P2G_ADJ, k_p2g_adj<<<nb, 128, 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]));
   LAUNCH_CHECK();
@@ -748,7 +769,7 @@ static int enqueue_backward_pipelined(dsk_engine* e, StepSlot& s) {
       KL(KID_G2P_ADJ, k_g2p_adj<3><<<nb, 128, 0, mainq>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
     else
       KL(KID_G2P_ADJ, k_g2p_adj<1><<<nb, 128, 0, mainq>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
-    KL(KID_GRID_ADJ, k_grid_adj<<<grid_ctas(e), grid_block(e), 0, mainq>>>(k, e->d_tools, s.poses, j, e->G0[set], e->Ga[set],
+    KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, mainq, k, e->d_tools, s.poses, j, e->G0[set], e->Ga[set],
                                                                           tt.list, tt.count, e->pose_adj));
     KL(KID_P2G_ADJ, k_p2g_adj<<<nb, 128, 0, mainq>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]));
     CK(cudaEventRecord(e->ev_main[q], mainq));

@@ -142,12 +142,16 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
   if (tid == 0) build_frame_table(k, sT, ft);
   __syncthreads();
   int n_active = *count;
+  int gt_next = blockIdx.x < n_active ? list[blockIdx.x] : 0;
   for (int it = blockIdx.x; it < n_active; it += gridDim.x) {
-    int gt = list[it];
+    int gt = gt_next;
+    if (it + (int)gridDim.x < n_active) gt_next = list[it + gridDim.x];   // prefetch: shortens the dependent-load chain
     int env = gt / k.ntile, tile = gt - env * k.ntile;
     int tz = tile % k.nt, ty = (tile / k.nt) % k.nt, tx = tile / (k.nt * k.nt);
     size_t o = ((size_t)gt << 6) + l;
     float4 gin = G0[o];
+    float4 ga4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y == 0) ga4 = Ga[o];
     bool live = gin.w > k.m_eps;
     int I0 = tx * 4 + (l >> 4), I1 = ty * 4 + ((l >> 2) & 3), I2 = tz * 4 + (l & 3);
     float3 gp = f3(mul_rn((float)I0, k.dx), mul_rn((float)I1, k.dx), mul_rn((float)I2, k.dx));
@@ -156,32 +160,34 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
       any_contact[y] = 0;
     }
     __syncthreads();
+    const bool any = tile_any_active(tf, ft.n);
     // phase A: contact geometry per (node, frame)
-    if (y < ft.n) {
-      if (live && tf.active[y]) {
-        const ToolParams& T = sT[ft.tool[y]];
-        contact_geometry(T, ft.flag[y] != 0.f ? SDF_BOX : sdf_kind(T.type), tf.F0[y], tf.F1[y], gp, k.dt, geo[y][l]);
-        if (geo[y][l].influence >= 0.f) any_contact[y] = 1;
-      } else {
-        geo[y][l].influence = -1.f;
+    if (any) {
+      if (y < ft.n) {
+        if (live && tf.active[y]) {
+          const ToolParams& T = sT[ft.tool[y]];
+          contact_geometry(T, ft.flag[y] != 0.f ? SDF_BOX : sdf_kind(T.type), tf.F0[y], tf.F1[y], gp, k.dt, geo[y][l]);
+          if (geo[y][l].influence >= 0.f) any_contact[y] = 1;
+        } else {
+          geo[y][l].influence = -1.f;
+        }
       }
+      __syncthreads();
     }
-    __syncthreads();
     // phase B: velocity chain forward and backward (one thread per node)
     if (y == 0) {
       float4 outv = make_float4(0.f, 0.f, 0.f, 0.f);
       if (live) {
-        float4 ga4 = Ga[o];
         float inv = 1.f / gin.w;
         float3 vs[MAX_FRAMES];
         float3 v = f3(inv * gin.x + k.grav[0], inv * gin.y + k.grav[1], inv * gin.z + k.grav[2]);
-        for (int f = 0; f < ft.n; f++) {
+        for (int f = 0; any && f < ft.n; f++) {
           vs[f] = v;
           const ContactGeom& c = geo[f][l];
           if (c.influence >= 0.f) v = contact_response(v, c.D, c.cv, c.influence, sT[ft.tool[f]].friction, ft.flag[f] != 0.f);
         }
         float3 g = grid_boundary_adj(k, I0, I1, I2, v, f3(ga4.x, ga4.y, ga4.z));
-        for (int f = ft.n - 1; f >= 0; f--) {
+        for (int f = ft.n - 1; any && f >= 0; f--) {
           const ContactGeom& c = geo[f][l];
           if (c.influence >= 0.f) {
             float ginfl;
@@ -196,6 +202,10 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
         outv = make_float4(inv * g.x, inv * g.y, inv * g.z, -(inv * inv) * (gin.x * g.x + gin.y * g.y + gin.z * g.z));
       }
       Ga[o] = outv;
+    }
+    if (!any) {   // no tool near this tile: nothing to differentiate through (uniform branch)
+      __syncthreads();
+      continue;
     }
     __syncthreads();
     // phase C: geometry adjoints per (node, frame), reduced over the tile's nodes
@@ -255,6 +265,117 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
       }
     }
     __syncthreads();
+  }
+}
+
+// grid_op.grad in the throughput layout of k_grid_flat: one thread per node keeps the geometry of its active frames
+// in local memory, walks the velocity chain forward and backward, and the pose adjoints of a frame are reduced over
+// the warp (half tile) before the atomics.
+__global__ void __launch_bounds__(FLAT_THREADS, 4)
+    k_grid_adj_flat(SimConst k, const ToolParams* __restrict__ tools, const float* __restrict__ poses, int j,
+                    const float4* __restrict__ G0, float4* __restrict__ Ga, const int* __restrict__ list,
+                    const int* __restrict__ count, float* __restrict__ pose_adj) {
+  __shared__ ToolParams sT[DSK_MAX_TOOLS];
+  __shared__ FrameTable ft;
+  __shared__ WarpFrames wf[FLAT_THREADS / 32];
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < k.K * (int)(sizeof(ToolParams) / 4); i += FLAT_THREADS) ((int*)sT)[i] = ((const int*)tools)[i];
+  __syncthreads();
+  if (tid == 0) build_frame_table(k, sT, ft);
+  __syncthreads();
+  int n_active = *count;
+  const int l = tid & 63;
+  for (int it = blockIdx.x * FLAT_TILES + (w >> 1); it < n_active; it += gridDim.x * FLAT_TILES) {
+    int gt = list[it];
+    int env = gt / k.ntile, tile = gt - env * k.ntile;
+    int tz = tile % k.nt, ty = (tile / k.nt) % k.nt, tx = tile / (k.nt * k.nt);
+    size_t o = ((size_t)gt << 6) + l;
+    float4 gin = G0[o];
+    float4 ga4 = Ga[o];
+    bool live = gin.w > k.m_eps;
+    int I0 = tx * 4 + (l >> 4), I1 = ty * 4 + ((l >> 2) & 3), I2 = tz * 4 + (l & 3);
+    float3 gp = f3(mul_rn((float)I0, k.dx), mul_rn((float)I1, k.dx), mul_rn((float)I2, k.dx));
+    unsigned mask = warp_prepare_frames(k, sT, ft, poses, env, j, tx, ty, tz, wf[w], lane);
+    ContactGeom geo[MAX_FRAMES];
+    float3 vs[MAX_FRAMES];
+    float inv = live ? 1.f / gin.w : 0.f;
+    float3 v = f3(inv * gin.x + k.grav[0], inv * gin.y + k.grav[1], inv * gin.z + k.grav[2]);
+    int na = 0;
+    for (unsigned m = mask; m; m &= m - 1, na++) {
+      int f = __ffs(m) - 1;
+      const ToolParams& T = sT[ft.tool[f]];
+      geo[na].influence = -1.f;
+      if (live) {
+        contact_geometry(T, ft.flag[f] != 0.f ? SDF_BOX : sdf_kind(T.type), wf[w].F0[f], wf[w].F1[f], gp, k.dt, geo[na]);
+        vs[na] = v;
+        if (geo[na].influence >= 0.f)
+          v = contact_response(v, geo[na].D, geo[na].cv, geo[na].influence, T.friction, ft.flag[f] != 0.f);
+      }
+    }
+    float3 g = f3(0.f, 0.f, 0.f);
+    if (live) g = grid_boundary_adj(k, I0, I1, I2, v, f3(ga4.x, ga4.y, ga4.z));
+    // frames in reverse order; every lane of the warp walks the same frames
+    for (int a = na - 1; a >= 0; a--) {
+      unsigned rest = mask;
+      for (int q = 0; q < a; q++) rest &= rest - 1;
+      int f = __ffs(rest) - 1;
+      const ContactGeom& c = geo[a];
+      bool hit = c.influence >= 0.f;
+      if (!__any_sync(0xffffffffu, hit)) continue;
+      const ToolParams& T = sT[ft.tool[f]];
+      FrameAdj a0 = frame_adj_zero(), a1 = frame_adj_zero();
+      if (hit) {
+        float ginfl;
+        float3 gD, gcv;
+        g = contact_response_adj(vs[a], c.D, c.cv, c.influence, T.friction, ft.flag[f] != 0.f, g, gD, gcv, ginfl);
+        // influence = min(exp(-dist*softness), 1): exp(..) = influence when it is < 1
+        float gdist = (c.influence < 1.f) ? (-T.softness * c.influence * ginfl) : 0.f;
+        int kind = ft.flag[f] != 0.f ? SDF_BOX : sdf_kind(T.type);
+        // D = qrot(q0, n/L)
+        float3 Nl = (1.f / c.L) * c.nraw, gNl = f3(0, 0, 0);
+        qrot_adj(wf[w].F0[f].q, Nl, gD, a0.q, gNl);
+        float3 gpl = local_normal_adj_cached(T, kind, c.pl, c.nraw, c.L, gNl);
+        // dist = sdf(pl)
+        gpl += gdist * local_sdf_grad(T, kind, c.pl);
+        // cv = (qrot(q1, pl) + o1 - p) / dt
+        float3 gnp = (1.f / k.dt) * gcv;
+        a1.o += gnp;
+        qrot_adj(wf[w].F1[f].q, c.pl, gnp, a1.q, gpl);
+        // pl = inv_trans(F0, p)
+        float3 unused = f3(0, 0, 0);
+        inv_trans_adj(wf[w].F0[f], gp, gpl, a0, unused);
+      }
+      float vals[14] = {a0.o.x, a0.o.y, a0.o.z, a0.q.w, a0.q.x, a0.q.y, a0.q.z,
+                        a1.o.x, a1.o.y, a1.o.z, a1.q.w, a1.q.x, a1.q.y, a1.q.z};
+#pragma unroll
+      for (int q = 0; q < 14; q++) vals[q] = warp_sum(vals[q]);
+      if (lane == 0) {
+        a0.o = f3(vals[0], vals[1], vals[2]); a0.q.w = vals[3]; a0.q.x = vals[4]; a0.q.y = vals[5]; a0.q.z = vals[6];
+        a1.o = f3(vals[7], vals[8], vals[9]); a1.q.w = vals[10]; a1.q.x = vals[11]; a1.q.y = vals[12]; a1.q.z = vals[13];
+        int t = ft.tool[f];
+        const float* pa = poses + ((size_t)(env * (k.S + 1) + j) * k.K + t) * 8;
+        PoseAdj g0 = pose_adj_zero(), g1 = pose_adj_zero();
+        if (ft.flag[f] != 0.f) {   // jaw_frame_adj is linear in the frame adjoint: apply it after the reduction
+          jaw_frame_adj(load_pose(pa), ft.flag[f], a0, g0);
+          jaw_frame_adj(load_pose(pa + (size_t)k.K * 8), ft.flag[f], a1, g1);
+        } else {
+          tool_frame_adj(a0, g0);
+          tool_frame_adj(a1, g1);
+        }
+        float* adj0 = pose_adj + ((size_t)(env * (k.S + 1) + j) * k.K + t) * 8;
+        float* adj1 = adj0 + (size_t)k.K * 8;
+        float v0[8] = {g0.p.x, g0.p.y, g0.p.z, g0.q.w, g0.q.x, g0.q.y, g0.q.z, g0.gap};
+        float v1[8] = {g1.p.x, g1.p.y, g1.p.z, g1.q.w, g1.q.x, g1.q.y, g1.q.z, g1.gap};
+        for (int q = 0; q < 8; q++) {
+          if (v0[q] != 0.f) atomicAdd(adj0 + q, v0[q]);
+          if (v1[q] != 0.f) atomicAdd(adj1 + q, v1[q]);
+        }
+      }
+    }
+    float4 outv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) outv = make_float4(inv * g.x, inv * g.y, inv * g.z, -(inv * inv) * (gin.x * g.x + gin.y * g.y + gin.z * g.z));
+    Ga[o] = outv;
+    __syncwarp();   // wf[w] is rewritten by the next tile
   }
 }
 

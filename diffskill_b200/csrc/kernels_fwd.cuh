@@ -266,21 +266,38 @@ struct TileFrames {    // per tile-iteration, shared memory
   Frame F0[MAX_FRAMES], F1[MAX_FRAMES];
   int active[MAX_FRAMES];
 };
-// thread (0, y) prepares frame y of the tile's env and decides whether the tile can touch it at all
-DSK_DEV void prepare_tile_frame(const SimConst& k, const ToolParams* sT, const FrameTable& ft, int y,
-                                const float* __restrict__ poses, int env, int j, int tx, int ty, int tz,
-                                TileFrames& tf) {
+
+DSK_DEV bool tile_any_active(const TileFrames& tf, int n) {   // uniform over the CTA
+  int a = 0;
+  for (int f = 0; f < n; f++) a |= tf.active[f];
+  return a != 0;
+}
+// prepares contact frame y of the tile's env (poses at substeps j and j+1) and decides whether the tile can touch
+// it at all
+DSK_DEV int prepare_frame(const SimConst& k, const ToolParams* sT, const FrameTable& ft, int y,
+                          const float* __restrict__ poses, int env, int j, int tx, int ty, int tz, Frame& F0, Frame& F1) {
   int t = ft.tool[y];
   const float* a = poses + ((size_t)(env * (k.S + 1) + j) * k.K + t) * 8;
   Pose P0 = load_pose(a), P1 = load_pose(a + (size_t)k.K * 8);
-  tf.F0[y] = frame_of_pose(P0, ft.flag[y]);
-  tf.F1[y] = frame_of_pose(P1, ft.flag[y]);
+  F0 = frame_of_pose(P0, ft.flag[y]);
+  F1 = frame_of_pose(P1, ft.flag[y]);
   const ToolParams& T = sT[t];
   int kind = ft.flag[y] != 0.f ? SDF_BOX : sdf_kind(T.type);
   float3 c = f3(((float)(tx * 4) + 1.5f) * k.dx, ((float)(ty * 4) + 1.5f) * k.dx, ((float)(tz * 4) + 1.5f) * k.dx);
-  float d = frame_sdf(T, kind, tf.F0[y], c);
   float reach = 2.6f * k.dx * 1.02f + 1e-4f + (T.softness > 0.f ? 2.302586f / T.softness : 0.f);
-  tf.active[y] = d <= reach;   // all SDFs here are 1-Lipschitz: beyond `reach` no node has dist<=0 or influence>0.1
+  // cheap bounding-sphere test first, exact SDF only for tiles near the tool.  All SDFs here are 1-Lipschitz:
+  // beyond `reach` no node of the tile has dist <= 0 or influence > 0.1
+  float3 dc = c - F0.o;
+  float far = T.bound_r + reach;
+  int act = dot(dc, dc) <= far * far;
+  if (act) act = frame_sdf(T, kind, F0, c) <= reach;
+  return act;
+}
+// thread (0, y) of the (node x frame) kernels
+DSK_DEV void prepare_tile_frame(const SimConst& k, const ToolParams* sT, const FrameTable& ft, int y,
+                                const float* __restrict__ poses, int env, int j, int tx, int ty, int tz,
+                                TileFrames& tf) {
+  tf.active[y] = prepare_frame(k, sT, ft, y, poses, env, j, tx, ty, tz, tf.F0[y], tf.F1[y]);
 }
 DSK_DEV void contact_geometry(const ToolParams& T, int kind, const Frame& F0, const Frame& F1, float3 p, float dt,
                               ContactGeom& g) {
@@ -342,8 +359,10 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
       else if (over) *tape.overflow = 1;
     }
   }
+  int gt_next = blockIdx.x < n_active ? list[blockIdx.x] : 0;
   for (int it = blockIdx.x; it < n_active; it += gridDim.x) {
-    int gt = list[it];
+    int gt = gt_next;
+    if (it + (int)gridDim.x < n_active) gt_next = list[it + gridDim.x];   // prefetch: shortens the dependent-load chain
     int env = gt / k.ntile, tile = gt - env * k.ntile;
     int tz = tile % k.nt, ty = (tile / k.nt) % k.nt, tx = tile / (k.nt * k.nt);
     size_t o = ((size_t)gt << 6) + l;
@@ -353,21 +372,24 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
     float3 gp = f3(mul_rn((float)I0, k.dx), mul_rn((float)I1, k.dx), mul_rn((float)I2, k.dx));
     if (l == 0 && y < ft.n) prepare_tile_frame(k, sT, ft, y, poses, env, j, tx, ty, tz, tf);
     __syncthreads();
-    if (y < ft.n) {
-      if (live && tf.active[y]) {
-        const ToolParams& T = sT[ft.tool[y]];
-        contact_geometry(T, ft.flag[y] != 0.f ? SDF_BOX : sdf_kind(T.type), tf.F0[y], tf.F1[y], gp, k.dt, geo[y][l]);
-      } else {
-        geo[y][l].influence = -1.f;
+    const bool any = tile_any_active(tf, ft.n);
+    if (any) {
+      if (y < ft.n) {
+        if (live && tf.active[y]) {
+          const ToolParams& T = sT[ft.tool[y]];
+          contact_geometry(T, ft.flag[y] != 0.f ? SDF_BOX : sdf_kind(T.type), tf.F0[y], tf.F1[y], gp, k.dt, geo[y][l]);
+        } else {
+          geo[y][l].influence = -1.f;
+        }
       }
+      __syncthreads();
     }
-    __syncthreads();
     if (y == 0) {
       float3 vout = f3(0.f, 0.f, 0.f);
       if (live) {
         float inv = 1.f / g.w;
         float3 v = f3(inv * g.x + k.grav[0], inv * g.y + k.grav[1], inv * g.z + k.grav[2]);
-        for (int f = 0; f < ft.n; f++) {
+        for (int f = 0; any && f < ft.n; f++) {
           const ContactGeom& c = geo[f][l];
           if (c.influence >= 0.f) v = contact_response(v, c.D, c.cv, c.influence, sT[ft.tool[f]].friction, ft.flag[f] != 0.f);
         }
@@ -383,6 +405,99 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
       }
     }
     __syncthreads();
+  }
+}
+
+// ---- grid_op, throughput layout for batched engines ------------------------------------------------------------------
+// One thread per node, one warp per half tile, four tiles per CTA and no CTA-wide barrier inside the tile loop: with
+// thousands of active tiles the (node x frame) layout above leaves most of its warps idle (few tiles touch a tool), so
+// tiles in flight per SM -- not threads per tile -- is what hides the dependent-load latency.  Lanes < n_frames
+// prepare and cull the frames of the warp's tile; the surviving frames are applied in order by every lane.
+#define FLAT_THREADS 256
+#define FLAT_TILES (FLAT_THREADS / GRID_NODES)
+struct WarpFrames {   // per warp, shared memory
+  Frame F0[MAX_FRAMES], F1[MAX_FRAMES];
+};
+DSK_DEV void clear_tiles_flat(const int* __restrict__ list, int count, float4* c0, float4* c1, float4* c2) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = blockIdx.x * FLAT_TILES + (threadIdx.x >> 6); i < count; i += gridDim.x * FLAT_TILES) {
+    size_t o = ((size_t)list[i] << 6) + (threadIdx.x & 63);
+    if (c0) c0[o] = z;
+    if (c1) c1[o] = z;
+    if (c2) c2[o] = z;
+  }
+}
+// returns the warp-uniform mask of frames that may touch the tile
+DSK_DEV unsigned warp_prepare_frames(const SimConst& k, const ToolParams* sT, const FrameTable& ft,
+                                     const float* __restrict__ poses, int env, int j, int tx, int ty, int tz,
+                                     WarpFrames& wf, int lane) {
+  int act = 0;
+  if (lane < ft.n) act = prepare_frame(k, sT, ft, lane, poses, env, j, tx, ty, tz, wf.F0[lane], wf.F1[lane]);
+  unsigned mask = __ballot_sync(0xffffffffu, act);   // also orders the shared-memory writes before the reads below
+  __syncwarp();
+  return mask;
+}
+
+__global__ void __launch_bounds__(FLAT_THREADS, 4)
+    k_grid_flat(SimConst k, const ToolParams* __restrict__ tools, const float* __restrict__ poses, int j,
+                const float4* Gin, float4* Gout, const int* __restrict__ list, const int* __restrict__ count,
+                const int* __restrict__ clr_list, const int* __restrict__ clr_count, float4* clr0, float4* clr1,
+                float4* clr2, int* zero_count, GridTape tape, const int* __restrict__ run_if) {
+  if (run_if && *run_if == 0) return;
+  __shared__ ToolParams sT[DSK_MAX_TOOLS];
+  __shared__ FrameTable ft;
+  __shared__ WarpFrames wf[FLAT_THREADS / 32];
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < k.K * (int)(sizeof(ToolParams) / 4); i += FLAT_THREADS) ((int*)sT)[i] = ((const int*)tools)[i];
+  __syncthreads();
+  if (tid == 0) build_frame_table(k, sT, ft);
+  if (blockIdx.x == 0 && tid == 0 && zero_count) *zero_count = 0;
+  if (clr_list) clear_tiles_flat(clr_list, *clr_count, clr0, clr1, clr2);
+  __syncthreads();
+  int n_active = *count;
+  int tb = 0;
+  if (tape.base) {   // as in k_grid
+    tb = j == 0 ? 0 : tape.base[j];
+    if (blockIdx.x == 0 && tid == 0) {
+      tape.base[j + 1] = tb + n_active;
+      bool over = tb + n_active > tape.cap;
+      if (j == 0) *tape.overflow = over ? 1 : 0;
+      else if (over) *tape.overflow = 1;
+    }
+  }
+  const int l = tid & 63;   // node within the tile
+  for (int it = blockIdx.x * FLAT_TILES + (w >> 1); it < n_active; it += gridDim.x * FLAT_TILES) {
+    int gt = list[it];
+    int env = gt / k.ntile, tile = gt - env * k.ntile;
+    int tz = tile % k.nt, ty = (tile / k.nt) % k.nt, tx = tile / (k.nt * k.nt);
+    size_t o = ((size_t)gt << 6) + l;
+    float4 g = Gin[o];
+    bool live = g.w > k.m_eps;
+    int I0 = tx * 4 + (l >> 4), I1 = ty * 4 + ((l >> 2) & 3), I2 = tz * 4 + (l & 3);
+    unsigned mask = warp_prepare_frames(k, sT, ft, poses, env, j, tx, ty, tz, wf[w], lane);
+    float3 vout = f3(0.f, 0.f, 0.f);
+    if (live) {
+      float3 gp = f3(mul_rn((float)I0, k.dx), mul_rn((float)I1, k.dx), mul_rn((float)I2, k.dx));
+      float inv = 1.f / g.w;
+      float3 v = f3(inv * g.x + k.grav[0], inv * g.y + k.grav[1], inv * g.z + k.grav[2]);
+      for (unsigned m = mask; m; m &= m - 1) {
+        int f = __ffs(m) - 1;
+        const ToolParams& T = sT[ft.tool[f]];
+        ContactGeom c;
+        contact_geometry(T, ft.flag[f] != 0.f ? SDF_BOX : sdf_kind(T.type), wf[w].F0[f], wf[w].F1[f], gp, k.dt, c);
+        if (c.influence >= 0.f) v = contact_response(v, c.D, c.cv, c.influence, T.friction, ft.flag[f] != 0.f);
+      }
+      vout = grid_boundary(k, I0, I1, I2, v);
+    }
+    float4 go = make_float4(vout.x, vout.y, vout.z, g.w);
+    Gout[o] = go;
+    if (tape.base && tb + it < tape.cap) {
+      if (l == 0) tape.list[tb + it] = gt;
+      float4* d = tape.data + ((size_t)(tb + it) << 7);
+      d[l] = g;
+      d[64 + l] = go;
+    }
+    __syncwarp();   // wf[w] is rewritten by the next tile
   }
 }
 

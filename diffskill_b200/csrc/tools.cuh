@@ -25,6 +25,7 @@ struct ToolParams {
   Q4 prot_inv;  // normalised conjugate of prot (computed on device in fp32 like the reference)
   Q4 prot;
   float min_gap, max_gap;
+  float bound_r;  // radius of a sphere around the frame origin that contains the shape (tile culling)
 };
 
 struct Pose {  // position[f], rotation[f], gap[f]

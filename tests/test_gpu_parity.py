@@ -186,6 +186,20 @@ def test_substep_backward_parity(name):
 @pytest.mark.parametrize('name', ENVS)
 @pytest.mark.parametrize('slots,tape_mib', [(1, 256), (3, 256), (3, 1), (3, 0)])
 def test_multi_step_action_gradient(name, slots, tape_mib):
+    _multi_step_action_gradient(name, slots, tape_mib)
+
+
+@pytest.mark.parametrize('name', ENVS)
+@pytest.mark.parametrize('slots,tape_mib', [(3, 256), (1, 0)])
+def test_multi_step_action_gradient_batched_layout(name, slots, tape_mib, monkeypatch):
+    """Same property with the kernel variants batched engines select (>= 65536 particle slots): throughput layout
+    of the grid kernels and the high-occupancy particle kernels."""
+    monkeypatch.setenv('DSK_FLAT_GRID', '1')
+    monkeypatch.setenv('DSK_FORCE_BIG', '1')
+    _multi_step_action_gradient(name, slots, tape_mib)
+
+
+def _multi_step_action_gradient(name, slots, tape_mib):
     """3 env steps of the real substep count: checkpoint + recompute (slots=1) and full tape (slots=3)
     must both match the oracle's taped gradient (the reference's own property test, long_term_gradient.ipynb).
     tape_mib: grid tape on (256), overflowing -> device-side fallback to recompute (1), off (0)."""
