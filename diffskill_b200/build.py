@@ -10,6 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 SO = os.path.join(HERE, 'libdiffskill_mpm.so')
+SO_TIMELINE = os.path.join(HERE, 'libdiffskill_mpm_tl.so')   # profiling build, see dsk_timeline_* in the header
 SOURCES = ['engine.cu']
 HEADERS = ['mpm_math.cuh', 'svd3.cuh', 'tools.cuh', 'kernels_common.cuh', 'kernels_aux.cuh', 'kernels_fwd.cuh',
            'kernels_bwd.cuh', os.path.join('..', '..', 'include', 'diffskill_mpm.h')]
@@ -35,7 +36,15 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False, extra=()):
+def build(force=False, verbose=False, extra=(), timeline=False):
+    """timeline=True builds the profiling variant (kernels stamp %globaltimer) next to the product library."""
+    if timeline:
+        cmd = [_nvcc(), '-ccbin', _host_cxx()] + NVCC_FLAGS + ['-DDSK_TIMELINE'] + list(extra) + ['-o', SO_TIMELINE] + \
+            [os.path.join(CSRC, s) for s in SOURCES]
+        if verbose:
+            print(' '.join(cmd))
+        subprocess.check_call(cmd)
+        return SO_TIMELINE
     if not force and not needs_build():
         return SO
     cmd = [_nvcc(), '-ccbin', _host_cxx()] + NVCC_FLAGS + list(extra) + ['-o', SO] + [os.path.join(CSRC, s) for s in SOURCES]
@@ -46,4 +55,5 @@ def build(force=False, verbose=False, extra=()):
 
 
 if __name__ == '__main__':
-    build(force='--force' in sys.argv, verbose=True, extra=['-Xptxas', '-v'] if '--ptxas' in sys.argv else [])
+    build(force='--force' in sys.argv, verbose=True, extra=['-Xptxas', '-v'] if '--ptxas' in sys.argv else [],
+          timeline='--timeline' in sys.argv)

@@ -122,6 +122,12 @@ struct dsk_engine {
   int* perm_cache = nullptr;   // permutation of the last full sort
   int sort_age = 1 << 30, resort_interval = 1;   // >1 re-uses the last permutation (cheaper sort, more fragmented warps)
   bool seq_full_sort = true;
+#ifdef DSK_TIMELINE
+  TlRec* d_tl = nullptr;
+  int tl_cap = 16384, tl_next = 0;
+  bool tl_on = false;
+  std::vector<int> tl_kid;
+#endif
   bool big = false;   // enough particles to fill the machine: prefer occupancy over registers
   bool flat_grid = false;   // many active tiles: throughput layout of the grid kernels
   cudaStream_t cap_side = nullptr;
@@ -148,6 +154,19 @@ static cudaEvent_t prof_event(dsk_engine* e) {
   return ev;
 }
 // every kernel launch of the engine goes through KL: counts it and, when profiling, brackets it with events
+#ifdef DSK_TIMELINE
+#define TL_ASSIGN(kid_)                                                  \
+  do {                                                                   \
+    if (e->tl_on && e->tl_next < e->tl_cap) {                            \
+      e->k.tl_slot = e->tl_next++;                                       \
+      e->tl_kid.push_back(kid_);                                         \
+    } else {                                                             \
+      e->k.tl_slot = -1;                                                 \
+    }                                                                    \
+  } while (0)
+#else
+#define TL_ASSIGN(kid_) do { } while (0)
+#endif
 #define KL(kid_, ...)                                          \
   do {                                                         \
     ProfRec pr__;                                              \
@@ -157,6 +176,7 @@ static cudaEvent_t prof_event(dsk_engine* e) {
       pr__.b = prof_event(e);                                  \
       cudaEventRecord(pr__.a, e->qs);                      \
     }                                                          \
+    TL_ASSIGN(kid_);                                           \
     __VA_ARGS__;                                               \
     if (e->profiling) {                                        \
       cudaEventRecord(pr__.b, e->qs);                      \
@@ -303,6 +323,10 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
     }
   }
   e->frame_floats = (size_t)FRAME_COMPS * k.stride;
+#ifdef DSK_TIMELINE
+  e->k.tl = nullptr;
+  e->k.tl_slot = -1;
+#endif
   e->big = (size_t)c->n_envs * c->particle_capacity >= 65536;
   if (const char* v = getenv("DSK_FORCE_BIG")) e->big = atoi(v) != 0;
   e->flat_grid = e->big;
@@ -395,6 +419,9 @@ int dsk_destroy(dsk_engine* e) {
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);
   drop_graphs(e);
+#ifdef DSK_TIMELINE
+  if (e->d_tl) cudaFree(e->d_tl);
+#endif
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   if (e->cap_side) cudaStreamDestroy(e->cap_side);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
@@ -714,7 +741,7 @@ static int seq_substep_grad(dsk_engine* e, StepSlot& s, int q, int j) {
   if (e->big)
     KL(KID_G2P_ADJ, k_g2p_adj<3><<<nb, 128, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
   else
-    KL(KID_G2P_ADJ, k_g2p_adj<1><<<nb, 128, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
+    KL(KID_G2P_ADJ, k_g2p_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
   KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, e->qs, k, e->d_tools, s.poses, j, e->G0[set], e->Ga[set],
                                                                       tt.list, tt.count, e->pose_adj));
   KL(KID_P2G_ADJ, k_p2g_adj<<<nb, 128, 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]));
@@ -768,7 +795,7 @@ static int enqueue_backward_pipelined(dsk_engine* e, StepSlot& s) {
     if (e->big)
       KL(KID_G2P_ADJ, k_g2p_adj<3><<<nb, 128, 0, mainq>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
     else
-      KL(KID_G2P_ADJ, k_g2p_adj<1><<<nb, 128, 0, mainq>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
+      KL(KID_G2P_ADJ, k_g2p_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, mainq>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
     KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, mainq, k, e->d_tools, s.poses, j, e->G0[set], e->Ga[set],
                                                                           tt.list, tt.count, e->pose_adj));
     KL(KID_P2G_ADJ, k_p2g_adj<<<nb, 128, 0, mainq>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]));
@@ -1508,6 +1535,56 @@ int dsk_profile_enable(dsk_engine* e, int on) {
   CK(cudaStreamSynchronize(e->stream));
   e->profiling = on != 0;
   return 0;
+}
+// In-graph timeline (profiling build only; the product library reports "unavailable").
+// enable: drops the cached graphs so that the next capture assigns one record per launch; reset: clears the
+// stamps but keeps the assignment, so a following graph replay fills exactly its own records.
+int dsk_timeline_enable(dsk_engine* e, int on) {
+  CKE(e);
+#ifdef DSK_TIMELINE
+  CK(cudaStreamSynchronize(e->stream));
+  if (!e->d_tl) CK(cudaMalloc(&e->d_tl, sizeof(TlRec) * e->tl_cap));
+  e->tl_on = on != 0;
+  e->tl_next = 0;
+  e->tl_kid.clear();
+  e->k.tl = e->d_tl;
+  e->k.tl_slot = -1;
+  drop_graphs(e);
+  return dsk_timeline_reset(e);
+#else
+  (void)on;
+  return fail("timeline: this library was built without -DDSK_TIMELINE");
+#endif
+}
+int dsk_timeline_reset(dsk_engine* e) {
+  CKE(e);
+#ifdef DSK_TIMELINE
+  CK(cudaStreamSynchronize(e->stream));
+  std::vector<TlRec> z(e->tl_cap, TlRec{~0ull, 0ull});
+  CK(cudaMemcpy(e->d_tl, z.data(), sizeof(TlRec) * e->tl_cap, cudaMemcpyHostToDevice));
+  return 0;
+#else
+  return fail("timeline: this library was built without -DDSK_TIMELINE");
+#endif
+}
+// returns the number of records written to (kid, t0_ns, t1_ns); records never stamped have t1 == 0
+int dsk_timeline_read(dsk_engine* e, int* kid, unsigned long long* t0, unsigned long long* t1, int cap) {
+  CKE(e);
+#ifdef DSK_TIMELINE
+  CK(cudaStreamSynchronize(e->stream));
+  int n = std::min(cap, e->tl_next);
+  std::vector<TlRec> r(n);
+  if (n) CK(cudaMemcpy(r.data(), e->d_tl, sizeof(TlRec) * n, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; i++) {
+    kid[i] = e->tl_kid[i];
+    t0[i] = r[i].t0;
+    t1[i] = r[i].t1;
+  }
+  return n;
+#else
+  (void)kid; (void)t0; (void)t1; (void)cap;
+  return fail("timeline: this library was built without -DDSK_TIMELINE");
+#endif
 }
 int dsk_kernel_class_count(void) { return KID_COUNT; }
 const char* dsk_kernel_class_name(int i) { return (i >= 0 && i < KID_COUNT) ? kKernelNames[i] : ""; }

@@ -13,6 +13,7 @@ DSK_DEV int cell_key(const SimConst& k, float x, float y, float z, int& bx, int&
 }
 __global__ void k_sort_bin(SimConst k, const StepArgs* __restrict__ args, const int* __restrict__ npart,
                            int* __restrict__ cell_count, int* __restrict__ key, int* __restrict__ rank) {
+  DSK_TL(k);
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= k.stride) return;
   const float* __restrict__ ck = args->ck_src;
@@ -40,6 +41,7 @@ DSK_DEV int block_sum(int v, int* sh) {
   return t;
 }
 __global__ void __launch_bounds__(SCAN_CTA) k_scan_partial(SimConst k, const int* __restrict__ cell_count, int* __restrict__ partial) {
+  DSK_TL(k);
   __shared__ int sh[SCAN_CTA / 32];
   int env = blockIdx.y, chunk = blockIdx.x;
   const int* c = cell_count + (size_t)env * k.nnode;
@@ -50,6 +52,7 @@ __global__ void __launch_bounds__(SCAN_CTA) k_scan_partial(SimConst k, const int
   if (threadIdx.x == 0) partial[env * gridDim.x + chunk] = t;
 }
 __global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(SimConst k, int* __restrict__ cell_count, const int* __restrict__ partial) {
+  DSK_TL(k);
   __shared__ int sh[SCAN_CTA / 32];
   __shared__ int wtot[SCAN_CTA / 32];
   int env = blockIdx.y, chunk = blockIdx.x;
@@ -84,6 +87,7 @@ __global__ void k_sort_scatter(SimConst k, const StepArgs* __restrict__ args, co
                                const int* __restrict__ npart, const int* __restrict__ cell_start,
                                const int* __restrict__ key, const int* __restrict__ rank, int use_sort,
                                float* __restrict__ w0, float* __restrict__ mat_sorted, int* __restrict__ perm) {
+  DSK_TL(k);
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= k.stride) return;
   const float* __restrict__ ck = args->ck_src;
@@ -101,6 +105,7 @@ __global__ void k_sort_scatter(SimConst k, const StepArgs* __restrict__ args, co
 __global__ void k_apply_perm(SimConst k, const StepArgs* __restrict__ args, const float* __restrict__ mat,
                              const int* __restrict__ npart, const int* __restrict__ perm_cache,
                              float* __restrict__ w0, float* __restrict__ mat_sorted, int* __restrict__ perm) {
+  DSK_TL(k);
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= k.stride) return;
   int env = gid / k.Npad, d = gid - env * k.Npad;
@@ -117,6 +122,7 @@ __global__ void k_apply_perm(SimConst k, const StepArgs* __restrict__ args, cons
 // sorted frame -> canonical checkpoint.  accumulate=1: += (adjoint checkpoints)
 __global__ void k_unsort(SimConst k, const float* __restrict__ w, const int* __restrict__ npart,
                          const int* __restrict__ perm, float* const* __restrict__ pck, int accumulate) {
+  DSK_TL(k);
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= k.stride) return;
   float* __restrict__ ck = *pck;
@@ -134,6 +140,7 @@ __global__ void k_unsort(SimConst k, const float* __restrict__ w, const int* __r
 // canonical (adjoint) checkpoint -> sorted frame
 __global__ void k_gather_sorted(SimConst k, float* const* __restrict__ pck, const int* __restrict__ npart,
                                 const int* __restrict__ perm, float* __restrict__ w) {
+  DSK_TL(k);
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= k.stride) return;
   const float* __restrict__ ck = *pck;
@@ -148,6 +155,7 @@ __global__ void k_gather_sorted(SimConst k, float* const* __restrict__ pck, cons
 // aos: x[n,3] v[n,3] F[n,9] C[n,9] (reference layout); direction 0: aos -> frame, 1: frame -> aos, 2: frame += aos
 __global__ void k_particles_io(SimConst k, float* __restrict__ frame, int env, int n, float* x, float* v, float* F,
                                float* C, int direction) {
+  DSK_TL(k);
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   int gid = env * k.Npad + p;
@@ -168,6 +176,7 @@ __global__ void k_particles_io(SimConst k, float* __restrict__ frame, int env, i
 // batched [B,cap,3]-style adjoint injection (function.py:130-135): gx,gv [B,cap_in,3]; gF,gC [B,cap_in,9]
 __global__ void k_add_particle_grad(SimConst k, float* __restrict__ frame, const int* __restrict__ npart, int cap_in,
                                     const float* gx, const float* gv, const float* gF, const float* gC) {
+  DSK_TL(k);
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= k.stride) return;
   int env = gid / k.Npad, p = gid - env * k.Npad;
@@ -181,6 +190,7 @@ __global__ void k_add_particle_grad(SimConst k, float* __restrict__ frame, const
 // observation: xv [B,cap,6] (function.py:90-95)
 __global__ void k_get_obs(SimConst k, const float* __restrict__ frame, const int* __restrict__ npart, int cap_out,
                           float* __restrict__ xv) {
+  DSK_TL(k);
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= k.stride) return;
   int env = gid / k.Npad, p = gid - env * k.Npad;
@@ -363,6 +373,7 @@ DSK_DEV ToolVel action_to_vel(const ToolParams& T, const float* a, int S) {  // 
 
 // tool states of the last substep frame -> destination checkpoint
 __global__ void k_tool_store(SimConst k, const float* __restrict__ poses, const StepArgs* __restrict__ args) {
+  DSK_TL(k);
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int per = k.K * 8;
   if (i >= k.B * per) return;
@@ -371,6 +382,7 @@ __global__ void k_tool_store(SimConst k, const float* __restrict__ poses, const 
 }
 // pose_adj[B][S+1][K][8] = 0 except frame S = adjoint checkpoint step+1
 __global__ void k_pose_adj_init(SimConst k, float* __restrict__ pose_adj, const StepArgs* __restrict__ args) {
+  DSK_TL(k);
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int per = k.K * 8;
   if (i >= k.B * (k.S + 1) * per) return;
@@ -380,6 +392,7 @@ __global__ void k_pose_adj_init(SimConst k, float* __restrict__ pose_adj, const 
 }
 // adjoint checkpoint step += pose_adj frame 0
 __global__ void k_tool_adj_accum(SimConst k, const float* __restrict__ pose_adj, const StepArgs* __restrict__ args) {
+  DSK_TL(k);
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int per = k.K * 8;
   if (i >= k.B * per) return;
@@ -391,6 +404,7 @@ __global__ void k_tool_adj_accum(SimConst k, const float* __restrict__ pose_adj,
 __global__ void k_loss_l2(SimConst k, const float* __restrict__ frame, float* __restrict__ adj,
                           const int* __restrict__ npart, const float* __restrict__ target, int cap, float weight,
                           float* __restrict__ loss) {
+  DSK_TL(k);
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   int env = gid < k.stride ? gid / k.Npad : 0, p = gid - env * k.Npad;
   int n = npart[env];
@@ -418,6 +432,7 @@ __global__ void __launch_bounds__(KIN_CTA)
     k_kinematics(SimConst k, const ToolParams* __restrict__ tools, const StepArgs* __restrict__ args,
                  const float* __restrict__ rand_num, float* __restrict__ poses /*[B][S+1][K][8]*/,
                  int* __restrict__ cidx /*[B][S+1][npairs]*/) {
+  DSK_TL(k);
   const float* __restrict__ state0 = args->tool_src;  // [B][K][8]
   const float* __restrict__ action = args->action;    // [B][A] or null
   __shared__ ToolParams sT[DSK_MAX_TOOLS];

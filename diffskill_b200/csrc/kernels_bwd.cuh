@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(128, MINB)
     k_g2p_adj(SimConst k, const float* __restrict__ fin, const float* __restrict__ fnext,
               const float* __restrict__ adj_in, float* __restrict__ adj_out, const int* __restrict__ npart,
               const float4* __restrict__ Gv, float4* __restrict__ Ga) {
+  DSK_TL(k);
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   int env = min(gid / k.Npad, k.B - 1), p = gid - env * k.Npad;
   bool active = gid < k.stride && p < npart[env];
@@ -78,6 +79,80 @@ __global__ void __launch_bounds__(128, MINB)
   store_v3(adj_out, CX, k.stride, gid, gx);
 }
 
+// plane-split g2p.grad for small engines (see warp_scatter9): blockDim = (PL_PARTICLES, 3)
+__global__ void __launch_bounds__(PL_PARTICLES * 3)
+    k_g2p_adj_pl(SimConst k, const float* __restrict__ fin, const float* __restrict__ fnext,
+                 const float* __restrict__ adj_in, float* __restrict__ adj_out, const int* __restrict__ npart,
+                 const float4* __restrict__ Gv, float4* __restrict__ Ga) {
+  DSK_TL(k);
+  __shared__ float ex[3][10][PL_PARTICLES];
+  const int tx = threadIdx.x, pl = threadIdx.y;
+  int gid = blockIdx.x * PL_PARTICLES + tx;
+  int env = min(gid / k.Npad, k.B - 1), p = gid - env * k.Npad;
+  bool active = gid < k.stride && p < npart[env];
+  int gi = active ? gid : env * k.Npad;
+  float3 x = load_v3(fin, CX, k.stride, gi);
+  float3 xn = load_v3(fnext, CX, k.stride, gi);
+  float3 gxn = load_v3(adj_in, CX, k.stride, gi);
+  float3 gvn = load_v3(adj_in, CV, k.stride, gi);
+  M3 gC = load_m3(adj_in, CC, k.stride, gi);
+  float3 gt = f3((k.x_lo < xn.x && xn.x < k.x_hi) ? gxn.x : 0.f, (k.x_lo < xn.y && xn.y < k.x_hi) ? gxn.y : 0.f,
+                 (k.x_lo < xn.z && xn.z < k.x_hi) ? gxn.z : 0.f);
+  gvn += k.dt * gt;
+  Stencil s;
+  make_stencil(k, x.x, x.y, x.z, s);
+  const float4* Gve = Gv + (size_t)env * k.nnode;
+  float4* Gae = Ga + (size_t)env * k.nnode;
+  TileTrack none{nullptr, nullptr, nullptr};
+  const float wxp = pick3(s.wx, pl);
+  const int oxp = pick3(s.ox, pl);
+  float3 cx = f3(k.c_C * gC.m[0], k.c_C * gC.m[3], k.c_C * gC.m[6]);
+  float3 cy = f3(k.c_C * gC.m[1], k.c_C * gC.m[4], k.c_C * gC.m[7]);
+  float3 cz = f3(k.c_C * gC.m[2], k.c_C * gC.m[5], k.c_C * gC.m[8]);
+  float3 b0 = gvn - k.c_C * mv(gC, f3(s.fx, s.fy, s.fz)) + (float)pl * cx;   // plane term folded in
+  warp_scatter9(k, active, s, pl, oxp, Gae, none, false, env, 0, [&](int j, int l) {
+    float w = wxp * s.wy[j] * s.wz[l];
+    float3 a = b0 + (float)j * cy + (float)l * cz;
+    return make_float4(w * a.x, w * a.y, w * a.z, 0.f);
+  });
+  // this plane's part of the weight / fx adjoints
+  float gwxp = 0.f, gwy[3] = {0, 0, 0}, gwz[3] = {0, 0, 0};
+  float3 sg = f3(0, 0, 0);
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+#pragma unroll
+    for (int l = 0; l < 3; l++) {
+      float4 g4 = Gve[oxp + s.oy[j] + s.oz[l]];
+      float3 g = f3(g4.x, g4.y, g4.z);
+      float3 a = b0 + (float)j * cy + (float)l * cz;
+      float gw = dot(g, a);
+      sg += (wxp * s.wy[j] * s.wz[l]) * g;
+      gwxp += gw * s.wy[j] * s.wz[l];
+      gwy[j] += gw * wxp * s.wz[l];
+      gwz[l] += gw * wxp * s.wy[j];
+    }
+  float part[10] = {sg.x, sg.y, sg.z, gwxp, gwy[0], gwy[1], gwy[2], gwz[0], gwz[1], gwz[2]};
+#pragma unroll
+  for (int q = 0; q < 10; q++) ex[pl][q][tx] = part[q];
+  __syncthreads();
+  if (pl != 0 || !active) return;
+  float t[3][10];
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int q = 0; q < 10; q++) t[a][q] = ex[a][q][tx];
+  sg = f3(t[0][0] + t[1][0] + t[2][0], t[0][1] + t[1][1] + t[2][1], t[0][2] + t[1][2] + t[2][2]);
+  float3 gf = (-k.c_C) * mTv(gC, sg);
+  float dw[3];
+  bspline1_grad(s.fx, dw);
+  gf.x += t[0][3] * dw[0] + t[1][3] * dw[1] + t[2][3] * dw[2];
+  bspline1_grad(s.fy, dw);
+  gf.y += (t[0][4] + t[1][4] + t[2][4]) * dw[0] + (t[0][5] + t[1][5] + t[2][5]) * dw[1] + (t[0][6] + t[1][6] + t[2][6]) * dw[2];
+  bspline1_grad(s.fz, dw);
+  gf.z += (t[0][7] + t[1][7] + t[2][7]) * dw[0] + (t[0][8] + t[1][8] + t[2][8]) * dw[1] + (t[0][9] + t[1][9] + t[2][9]) * dw[2];
+  store_v3(adj_out, CX, k.stride, gid, gt + k.inv_dx * gf);
+}
+
 // adjoint of contact_response given the geometry (D, cv, influence): returns g(v_in), outputs g(D), g(cv), g(influence)
 DSK_DEV float3 contact_response_adj(float3 v, float3 D, float3 cv, float influence, float friction, bool eps14,
                                     float3 gout, float3& gD, float3& gcv, float& ginfl) {
@@ -129,6 +204,7 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
     k_grid_adj(SimConst k, const ToolParams* __restrict__ tools, const float* __restrict__ poses, int j,
                const float4* __restrict__ G0, float4* __restrict__ Ga, const int* __restrict__ list,
                const int* __restrict__ count, float* __restrict__ pose_adj) {
+  DSK_TL(k);
   __shared__ ToolParams sT[DSK_MAX_TOOLS];
   __shared__ FrameTable ft;
   __shared__ TileFrames tf;
@@ -275,6 +351,7 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4)
     k_grid_adj_flat(SimConst k, const ToolParams* __restrict__ tools, const float* __restrict__ poses, int j,
                     const float4* __restrict__ G0, float4* __restrict__ Ga, const int* __restrict__ list,
                     const int* __restrict__ count, float* __restrict__ pose_adj) {
+  DSK_TL(k);
   __shared__ ToolParams sT[DSK_MAX_TOOLS];
   __shared__ FrameTable ft;
   __shared__ WarpFrames wf[FLAT_THREADS / 32];
@@ -384,6 +461,7 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4)
 __global__ void __launch_bounds__(128, 3)
     k_p2g_adj(SimConst k, const float* __restrict__ fin, const float* __restrict__ adj_in, float* __restrict__ adj_out,
               const float* __restrict__ mat, const int* __restrict__ npart, const float4* __restrict__ Ga) {
+  DSK_TL(k);
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= k.stride) return;
   int env = gid / k.Npad, p = gid - env * k.Npad;
@@ -569,6 +647,7 @@ __global__ void __launch_bounds__(KINADJ_CTA)
     k_kinematics_adj(SimConst k, const ToolParams* __restrict__ tools, const float* __restrict__ poses,
                      const int* __restrict__ cidx, const float* __restrict__ rand_num,
                      const StepArgs* __restrict__ args, float* __restrict__ pose_adj) {
+  DSK_TL(k);
   const float* __restrict__ action = args->action;
   float* __restrict__ action_grad = args->action_grad;  // [B][A] of this step, +=
   __shared__ ToolParams sT[DSK_MAX_TOOLS];
@@ -671,6 +750,7 @@ __global__ void __launch_bounds__(KINADJ_CTA)
 __global__ void k_min_dist(SimConst k, const ToolParams* __restrict__ tools, const float* __restrict__ frame,
                            const int* __restrict__ npart, const float* __restrict__ tool_state /*[B][K][8]*/,
                            int cap_out, int ncols, float* __restrict__ out) {
+  DSK_TL(k);
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= k.stride) return;
   int env = gid / k.Npad, p = gid - env * k.Npad;
@@ -697,6 +777,7 @@ __global__ void k_min_dist_adj(SimConst k, const ToolParams* __restrict__ tools,
                                const int* __restrict__ npart, const float* __restrict__ tool_state, int cap_in,
                                int ncols, const float* __restrict__ gout, float* __restrict__ adj_frame,
                                float* __restrict__ tool_adj /*[B][K][8]*/) {
+  DSK_TL(k);
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   int env = gid < k.stride ? gid / k.Npad : 0, p = gid - env * k.Npad;
   bool live = gid < k.stride && p < npart[env] && p < cap_in;
@@ -739,6 +820,7 @@ __global__ void k_min_dist_adj(SimConst k, const ToolParams* __restrict__ tools,
 // compute_grid_m_kernel (+grad), mpm_simulator.py:456-466.  dense [B,n,n,n] output (row-major x,y,z)
 __global__ void k_grid_m(SimConst k, const float* __restrict__ frame, const int* __restrict__ npart,
                          float* __restrict__ out) {
+  DSK_TL(k);
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= k.stride) return;
   int env = gid / k.Npad, p = gid - env * k.Npad;
@@ -755,6 +837,7 @@ __global__ void k_grid_m(SimConst k, const float* __restrict__ frame, const int*
 }
 __global__ void k_grid_m_adj(SimConst k, const float* __restrict__ frame, const int* __restrict__ npart,
                              const float* __restrict__ gm, float* __restrict__ adj_frame) {
+  DSK_TL(k);
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= k.stride) return;
   int env = gid / k.Npad, p = gid - env * k.Npad;
@@ -788,6 +871,7 @@ __global__ void k_grid_m_adj(SimConst k, const float* __restrict__ frame, const 
 // tile-major grid -> dense [n,n,n,*] for the debug getters
 __global__ void k_grid_to_dense(SimConst k, const float4* __restrict__ G, int env, float* v3, float* m,
                                 unsigned char* occ, const int* __restrict__ tile_epoch, int epoch) {
+  DSK_TL(k);
   int node = blockIdx.x * blockDim.x + threadIdx.x;
   if (node >= k.nnode) return;
   int Z = node % k.n, Y = (node / k.n) % k.n, X = node / (k.n * k.n);

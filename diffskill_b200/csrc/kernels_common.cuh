@@ -22,7 +22,41 @@ struct SimConst {
   float dt, dx, inv_dx, p_mass, c_stress, c_C, x_hi, x_lo, m_eps, ground_friction;
   float grav[3];            // (dt * g) * 30, mpm_simulator.py:235
   int pairs[DSK_MAX_PAIRS][2];
+#ifdef DSK_TIMELINE
+  struct TlRec* tl;         // device timeline records (profiling build only)
+  int tl_slot;              // record of this launch, < 0: none
+#endif
 };
+
+// Profiling build (-DDSK_TIMELINE, libdiffskill_mpm_tl.so): every kernel stamps %globaltimer at its first and last
+// warp into the record of its launch, which gives per-kernel start/end times INSIDE replayed CUDA graphs -- where
+// CUDA events cannot be placed and ncu serialises the launches.  Compiled out of the product library.
+#ifdef DSK_TIMELINE
+struct TlRec {
+  unsigned long long t0, t1;
+};
+struct TlScope {
+  TlRec* r;
+  __device__ TlScope(const SimConst& k) {
+    r = (k.tl && k.tl_slot >= 0) ? k.tl + k.tl_slot : nullptr;
+    if (r && threadIdx.x == 0 && threadIdx.y == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      atomicMin(&r->t0, t);
+    }
+  }
+  __device__ ~TlScope() {
+    if (r && (threadIdx.x & 31) == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      atomicMax(&r->t1, t);
+    }
+  }
+};
+#define DSK_TL(k) TlScope tl_scope__(k)
+#else
+#define DSK_TL(k)
+#endif
 
 DSK_DEV int node_offset(int X, int Y, int Z, int nt) {
   int tile = ((X >> 2) * nt + (Y >> 2)) * nt + (Z >> 2);
@@ -169,22 +203,30 @@ DSK_DEV float4 f4shfl_down(float4 v, int d) {
                      __shfl_down_sync(0xffffffffu, v.z, d), __shfl_down_sync(0xffffffffu, v.w, d));
 }
 // val(i,j,l) -> float4 contribution of this lane to stencil node (i,j,l); must be callable by every lane.
-// Three regimes, chosen per warp from the number of runs of equal cell keys:
-//   <= 2 runs : recursive-halving butterfly per run (dense dough: a whole warp shares one cell)
-//   > 2 runs  : ONE segmented shuffle-down reduction over all runs at once (log2(longest run) steps per node),
-//               run heads issue the vector reductions
+// Regimes, chosen per warp from the groups of lanes with equal cell keys (match.any -- adjacent or not, because the
+// particles are sorted once per env step and a few lanes per warp have strayed into a neighbour cell by the last
+// substeps):
+//   <= 2 groups of >= SCATTER_MIN_GROUP lanes : recursive-halving butterfly per group (dense dough: a whole warp
+//               shares one cell); lanes in smaller groups issue their own reductions
+//   > 2 such groups : ONE segmented shuffle-down reduction over all runs of adjacent equal keys at once
+//               (log2(longest run) steps per node), run heads issue the vector reductions
 template <class F>
 DSK_DEV void warp_scatter27(const SimConst& k, bool active, const Stencil& s, float4* __restrict__ Ge,
                             const TileTrack& tt, bool mark, int env, int epoch, F val) {
   const int lane = threadIdx.x & 31;
-  int key = active ? node_offset(s.bx, s.by, s.bz, k.nt) : -1;
+  int key = active ? node_offset(s.bx, s.by, s.bz, k.nt) : -1 - lane;
   unsigned act = __ballot_sync(0xffffffffu, active);
   if (!act) return;
-  int prev = __shfl_up_sync(0xffffffffu, key, 1);
-  bool head = active && (lane == 0 || prev != key);
-  unsigned heads = __ballot_sync(0xffffffffu, head);
-  if (mark && head) mark_stencil_tiles(k, tt, env, s, epoch);
-  if (__popc(heads) > 2) {
+  // groups of equal keys, adjacent or not: the sort is per env step, so late substeps see a few strays per warp
+  unsigned same = __match_any_sync(0xffffffffu, key);
+  bool first = active && lane == __ffs(same) - 1;
+  bool small = active && __popc(same) < SCATTER_MIN_GROUP;
+  unsigned leaders = __ballot_sync(0xffffffffu, first && !small);
+  if (mark && first) mark_stencil_tiles(k, tt, env, s, epoch);
+  if (__popc(leaders) > 2) {
+    int prev = __shfl_up_sync(0xffffffffu, key, 1);
+    bool head = active && (lane == 0 || prev != key);
+    unsigned heads = __ballot_sync(0xffffffffu, head);
     unsigned above = lane == 31 ? 0u : (heads & (0xffffffffu << (lane + 1)));
     int next_head = above ? (__ffs(above) - 1) : 32;
     int end = min(next_head - 1, 31 - __clz(act));   // last lane of my run
@@ -210,24 +252,21 @@ DSK_DEV void warp_scatter27(const SimConst& k, bool active, const Stencil& s, fl
     }
     return;
   }
-  unsigned todo = act;
+  // strays (groups of fewer than SCATTER_MIN_GROUP lanes): per-lane reductions, all of them in one pass
+  if (small) {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int l = 0; l < 3; l++) red_add4(&Ge[s.ox[i] + s.oy[j] + s.oz[l]], val(i, j, l));
+  }
+  unsigned todo = leaders;
   while (todo) {
     int leader = __ffs(todo) - 1;
-    int lkey = __shfl_sync(0xffffffffu, key, leader);
-    bool mine = active && key == lkey;
-    unsigned grp = __ballot_sync(0xffffffffu, mine);
-    todo &= ~grp;
-    if (__popc(grp) < SCATTER_MIN_GROUP) {
-      if (mine) {
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-          for (int j = 0; j < 3; j++)
-#pragma unroll
-            for (int l = 0; l < 3; l++) red_add4(&Ge[s.ox[i] + s.oy[j] + s.oz[l]], val(i, j, l));
-      }
-      continue;
-    }
+    todo &= todo - 1;
+    unsigned grp = __shfl_sync(0xffffffffu, same, leader);
+    bool mine = (grp >> lane) & 1u;
     float4 acc[16];
     {
       bool hi = lane & 16;
@@ -256,3 +295,94 @@ DSK_DEV void warp_scatter27(const SimConst& k, bool active, const Stencil& s, fl
     }
   }
 }
+
+// ---- plane-split variant for small engines ------------------------------------------------------------------------
+// A single scene has fewer particle warps than the GPU has warp schedulers, so its particle kernels are bound by
+// the instruction chain of ONE thread.  The *_pl kernels use three threads per particle -- one per x-plane of the
+// stencil -- in three different warps with the same lane <-> particle mapping: each gathers / scatters 9 nodes, and
+// partial sums are exchanged through shared memory.  warp_scatter9 is warp_scatter27 for one plane (16-slot
+// butterfly: 64 shuffles).  oxp = s.ox[plane]; val(j, l) is the contribution to node (plane, j, l).
+#define PL_PARTICLES 64   // particles per CTA of a plane-split kernel: blockDim = (64, 3)
+template <int Q, class F>
+DSK_DEV float4 slot_value9(bool mine, F& val) {
+  if (Q >= 9) return make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 v = val(Q / 3, Q % 3);
+  return mine ? v : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+template <int Q, class F>
+DSK_DEV void butterfly9_first(bool mine, bool hi, F& val, float4* acc) {
+  float4 a = slot_value9<Q>(mine, val), b = slot_value9<Q + 8>(mine, val);
+  acc[Q] = f4add(f4sel(hi, b, a), f4shfl_xor(f4sel(hi, a, b), 16));
+}
+template <class F>
+DSK_DEV void warp_scatter9(const SimConst& k, bool active, const Stencil& s, int plane, int oxp,
+                           float4* __restrict__ Ge, const TileTrack& tt, bool mark, int env, int epoch, F val) {
+  const int lane = threadIdx.x & 31;
+  int key = active ? node_offset(s.bx, s.by, s.bz, k.nt) : -1 - lane;
+  unsigned act = __ballot_sync(0xffffffffu, active);
+  if (!act) return;
+  unsigned same = __match_any_sync(0xffffffffu, key);
+  bool first = active && lane == __ffs(same) - 1;
+  bool small = active && __popc(same) < SCATTER_MIN_GROUP;
+  unsigned leaders = __ballot_sync(0xffffffffu, first && !small);
+  if (mark && first) mark_stencil_tiles(k, tt, env, s, epoch);
+  if (__popc(leaders) > 2) {
+    int prev = __shfl_up_sync(0xffffffffu, key, 1);
+    bool head = active && (lane == 0 || prev != key);
+    unsigned heads = __ballot_sync(0xffffffffu, head);
+    unsigned above = lane == 31 ? 0u : (heads & (0xffffffffu << (lane + 1)));
+    int next_head = above ? (__ffs(above) - 1) : 32;
+    int end = min(next_head - 1, 31 - __clz(act));   // last lane of my run
+    int maxlen = __reduce_max_sync(0xffffffffu, head ? end - lane + 1 : 0);
+    float4 v[9];
+#pragma unroll
+    for (int q = 0; q < 9; q++) v[q] = active ? val(q / 3, q % 3) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int d = 1; d < maxlen; d <<= 1) {
+      bool take = lane + d <= end;
+#pragma unroll
+      for (int q = 0; q < 9; q++) {
+        float4 t = f4shfl_down(v[q], d);
+        if (take) v[q] = f4add(v[q], t);
+      }
+    }
+    if (head) {
+#pragma unroll
+      for (int q = 0; q < 9; q++) red_add4(&Ge[oxp + s.oy[q / 3] + s.oz[q % 3]], v[q]);
+    }
+    return;
+  }
+  if (small) {
+#pragma unroll
+    for (int q = 0; q < 9; q++) red_add4(&Ge[oxp + s.oy[q / 3] + s.oz[q % 3]], val(q / 3, q % 3));
+  }
+  unsigned todo = leaders;
+  while (todo) {
+    int leader = __ffs(todo) - 1;
+    todo &= todo - 1;
+    unsigned grp = __shfl_sync(0xffffffffu, same, leader);
+    bool mine = (grp >> lane) & 1u;
+    float4 acc[8];
+    {
+      bool hi = lane & 16;
+      butterfly9_first<0>(mine, hi, val, acc); butterfly9_first<1>(mine, hi, val, acc);
+      butterfly9_first<2>(mine, hi, val, acc); butterfly9_first<3>(mine, hi, val, acc);
+      butterfly9_first<4>(mine, hi, val, acc); butterfly9_first<5>(mine, hi, val, acc);
+      butterfly9_first<6>(mine, hi, val, acc); butterfly9_first<7>(mine, hi, val, acc);
+    }
+#pragma unroll
+    for (int half = 4; half >= 1; half >>= 1) {
+      bool hi = lane & (half << 1);
+#pragma unroll
+      for (int q = 0; q < half; q++)
+        acc[q] = f4add(f4sel(hi, acc[q + half], acc[q]), f4shfl_xor(f4sel(hi, acc[q], acc[q + half]), half << 1));
+    }
+    acc[0] = f4add(acc[0], f4shfl_xor(acc[0], 1));
+    // lanes 2m and 2m+1 now hold the complete sum for node m of the plane
+    int bx = __shfl_sync(0xffffffffu, s.bx, leader), by = __shfl_sync(0xffffffffu, s.by, leader),
+        bz = __shfl_sync(0xffffffffu, s.bz, leader);
+    int m = lane >> 1;
+    if (!(lane & 1) && m < 9) red_add4(&Ge[node_offset(bx + plane, by + m / 3, bz + m % 3, k.nt)], acc[0]);
+  }
+}
+DSK_DEV float pick3(const float* a, int i) { return i == 0 ? a[0] : (i == 1 ? a[1] : a[2]); }
+DSK_DEV int pick3(const int* a, int i) { return i == 0 ? a[0] : (i == 1 ? a[1] : a[2]); }

@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(128, MINB)
     k_p2g(SimConst k, const float* __restrict__ fin, float* __restrict__ fout, const float* __restrict__ mat,
           const int* __restrict__ npart, float4* __restrict__ G, TileTrack tt, const StepArgs* __restrict__ args,
           int q, const int* __restrict__ run_if) {
+  DSK_TL(k);
   if (run_if && *run_if == 0) return;   // adjoint recompute is skipped when the grid tape of the step is complete
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   int env = min(gid / k.Npad, k.B - 1), p = gid - env * k.Npad;   // a warp never straddles envs (Npad % 128 == 0)
@@ -220,6 +221,7 @@ DSK_DEV void clear_tiles(const SimConst& k, const int* __restrict__ list, int co
 __global__ void __launch_bounds__(GRID_CTA)
     k_end_clear(SimConst k, const int* __restrict__ list, const int* __restrict__ count, float4* c0, float4* c1,
                 float4* c2, int* counts4, int* done) {
+  DSK_TL(k);
   clear_tiles(k, list, *count, c0, c1, c2);
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -323,6 +325,7 @@ DSK_DEV void contact_geometry(const ToolParams& T, int kind, const Frame& F0, co
 #define GRID_NODES 64
 __global__ void __launch_bounds__(GRID_CTA)
     k_clear_set(SimConst k, const int* __restrict__ list, const int* __restrict__ count, float4* c0, float4* c1, float4* c2) {
+  DSK_TL(k);
   clear_tiles(k, list, *count, c0, c1, c2);
 }
 
@@ -334,6 +337,7 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
            // tiles of the previous substep to zero (clear_grid), may be null
            const int* __restrict__ clr_list, const int* __restrict__ clr_count, float4* clr0, float4* clr1,
            float4* clr2, int* zero_count, GridTape tape, const int* __restrict__ run_if) {
+  DSK_TL(k);
   if (run_if && *run_if == 0) return;
   __shared__ ToolParams sT[DSK_MAX_TOOLS];
   __shared__ FrameTable ft;
@@ -443,6 +447,7 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4)
                 const float4* Gin, float4* Gout, const int* __restrict__ list, const int* __restrict__ count,
                 const int* __restrict__ clr_list, const int* __restrict__ clr_count, float4* clr0, float4* clr1,
                 float4* clr2, int* zero_count, GridTape tape, const int* __restrict__ run_if) {
+  DSK_TL(k);
   if (run_if && *run_if == 0) return;
   __shared__ ToolParams sT[DSK_MAX_TOOLS];
   __shared__ FrameTable ft;
@@ -508,6 +513,7 @@ __global__ void __launch_bounds__(GRID_NODES)
                    int* __restrict__ list, int* __restrict__ count,
                    const int* __restrict__ clr_list, const int* __restrict__ clr_count, float4* clr0, float4* clr1,
                    float4* clr2, int* zero_count) {
+  DSK_TL(k);
   if (*tape.overflow) return;   // incomplete tape: the recompute kernels that follow take over
   if (blockIdx.x == 0 && threadIdx.x == 0 && zero_count) *zero_count = 0;
   if (clr_list) clear_tiles(k, clr_list, *clr_count, clr0, clr1, clr2);
@@ -554,6 +560,7 @@ DSK_DEV void g2p_particle(const SimConst& k, const Stencil& s, const float4* __r
 __global__ void __launch_bounds__(128)
     k_g2p(SimConst k, const float* __restrict__ fin, float* __restrict__ fout, const int* __restrict__ npart,
           const float4* __restrict__ G) {
+  DSK_TL(k);
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= k.stride) return;
   int env = gid / k.Npad, p = gid - env * k.Npad;
@@ -577,6 +584,7 @@ __global__ void __launch_bounds__(128, MINB)
     k_g2p2g(SimConst k, const float* __restrict__ fprev, float* __restrict__ fcur, float* __restrict__ fnext,
             const float* __restrict__ mat, const int* __restrict__ npart, const float4* __restrict__ Gprev,
             float4* __restrict__ Gnext, TileTrack tt, const StepArgs* __restrict__ args, int qnext) {
+  DSK_TL(k);
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   int env = min(gid / k.Npad, k.B - 1), p = gid - env * k.Npad;
   bool active = gid < k.stride && p < npart[env];

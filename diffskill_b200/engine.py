@@ -13,6 +13,8 @@ from .scene import NUM_COLLISION_POINTS, SceneSpec
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libdiffskill_mpm.so')
+if os.environ.get('DSK_LIB') == 'timeline':   # profiling build with in-graph kernel timestamps (build.py --timeline)
+    LIB_PATH = os.path.join(_HERE, 'libdiffskill_mpm_tl.so')
 MAX_TOOLS, MAX_PAIRS, ABI_VERSION = 8, 8, 1
 
 PARAM_FRICTION, PARAM_SOFTNESS, PARAM_LOWER, PARAM_UPPER = 0, 1, 2, 5
@@ -57,6 +59,7 @@ SYMBOLS = [
     'dsk_debug_tool_frame_grad', 'dsk_debug_svd', 'dsk_launch_count', 'dsk_memory_bytes', 'dsk_set_graphs',
     'dsk_profile_enable', 'dsk_kernel_class_count', 'dsk_kernel_class_name', 'dsk_profile_report',
     'dsk_launch_counts', 'dsk_loss_reset', 'dsk_loss_add_l2', 'dsk_loss_get',
+    'dsk_timeline_enable', 'dsk_timeline_reset', 'dsk_timeline_read',
 ]
 
 
@@ -426,6 +429,23 @@ class Engine:
         cnt = (C.c_int64 * n)()
         self._ck(self.L.dsk_profile_report(self.h, ms, cnt, n, int(reset)))
         return {name: (ms[i], cnt[i]) for i, name in enumerate(self.kernel_classes()) if cnt[i]}
+
+    def timeline_enable(self, on=True):
+        self._ck(self.L.dsk_timeline_enable(self.h, int(on)))
+
+    def timeline_reset(self):
+        self._ck(self.L.dsk_timeline_reset(self.h))
+
+    def timeline_read(self, cap=16384):
+        """[(kernel class, t0_ns, t1_ns)] of the launches stamped since the last reset, in launch order."""
+        kid = (C.c_int * cap)()
+        t0 = (C.c_ulonglong * cap)()
+        t1 = (C.c_ulonglong * cap)()
+        n = self.L.dsk_timeline_read(self.h, kid, t0, t1, cap)
+        if n < 0:
+            self._ck(n)
+        names = self.kernel_classes()
+        return [(names[kid[i]], int(t0[i]), int(t1[i])) for i in range(n) if t1[i] != 0]
 
     def launch_counts(self):
         n = self.L.dsk_kernel_class_count()

@@ -202,6 +202,13 @@ int dsk_kernel_class_count(void);
 const char* dsk_kernel_class_name(int i);
 int dsk_profile_report(dsk_engine* e, double* ms, int64_t* launches, int n, int reset);
 int dsk_launch_counts(dsk_engine* e, int64_t* per_class, int n);
+/* In-graph timeline: per-launch first/last %globaltimer stamps (ns), also inside replayed CUDA graphs.  Only the
+ * profiling build (python -m diffskill_b200.build --timeline -> libdiffskill_mpm_tl.so, selected with
+ * DSK_LIB=timeline) implements it; the product library returns an error.  enable drops the cached graphs so the
+ * next capture assigns one record per launch; reset clears the stamps; read returns the number of records. */
+int dsk_timeline_enable(dsk_engine* e, int on);
+int dsk_timeline_reset(dsk_engine* e);
+int dsk_timeline_read(dsk_engine* e, int* kid, unsigned long long* t0_ns, unsigned long long* t1_ns, int cap);
 /* Deterministic stand-in for the reference's torch-side losses (taichi_env.py:246-275 needs geomloss):
  * loss[env] += weight * mean_p |x_p - target_p|^2 at checkpoint `step`; its gradient is added to the adjoint
  * checkpoint.  target: [n_envs, particle_capacity, 3]; dsk_loss_get: [n_envs]. */
