@@ -50,11 +50,11 @@ struct StepSlot {
 
 enum KernelId {
   KID_SORT = 0, KID_KINEMATICS, KID_P2G, KID_GRID, KID_G2P, KID_P2G_RECOMPUTE, KID_GRID_RECOMPUTE, KID_G2P_ADJ,
-  KID_GRID_ADJ, KID_P2G_ADJ, KID_KINEMATICS_ADJ, KID_REORDER, KID_IO, KID_LOSS, KID_G2P2G, KID_COUNT
+  KID_GRID_ADJ, KID_P2G_ADJ, KID_KINEMATICS_ADJ, KID_REORDER, KID_IO, KID_LOSS, KID_G2P2G, KID_GRID_ADJ_TOOLS, KID_COUNT
 };
 static const char* kKernelNames[KID_COUNT] = {
     "sort", "kinematics", "p2g", "grid_op", "g2p", "p2g_recompute", "grid_op_recompute", "g2p_adj",
-    "grid_op_adj", "p2g_adj", "kinematics_adj", "reorder", "io", "loss", "g2p2g"};
+    "grid_op_adj", "p2g_adj", "kinematics_adj", "reorder", "io", "loss", "g2p2g", "grid_op_adj_tools"};
 
 struct ProfRec {
   int kid;
@@ -129,6 +129,9 @@ struct dsk_engine {
   std::vector<int> tl_kid;
 #endif
   bool big = false;   // enough particles to fill the machine: prefer occupancy over registers
+  float* gadj_scratch[2] = {nullptr, nullptr};   // parked contact adjoints of k_grid_adj (latency layout only)
+  int* gadj_flags[2] = {nullptr, nullptr};
+  int gadj_cap = 0;
   bool flat_grid = false;   // many active tiles: throughput layout of the grid kernels
   cudaStream_t cap_side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -367,6 +370,14 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
       DA(e->tile_epoch[s], (size_t)e->B * k.ntile);
       DA(e->tile_list[s], (size_t)e->B * k.ntile);
     }
+    if (!e->flat_grid && !getenv("DSK_NO_GRID_ADJ_SPLIT")) {
+      e->gadj_cap = (int)std::min<size_t>((size_t)e->B * k.ntile, 4096);
+      int nf = std::min(e->n_frames, MAX_FRAMES);
+      for (int s = 0; s < 2; s++) {
+        DA(e->gadj_scratch[s], (size_t)e->gadj_cap * nf * 7 * GRID_NODES);
+        DA(e->gadj_flags[s], (size_t)e->gadj_cap * MAX_FRAMES);
+      }
+    }
     DA(e->tile_count, 4);
     DA(e->done, 1);
     DA(e->d_args, 1);
@@ -526,10 +537,10 @@ static dim3 grid_block(dsk_engine* e) { return dim3(GRID_NODES, std::min(e->n_fr
     if ((e)->flat_grid) k_grid_flat<<<148 * 4, FLAT_THREADS, 0, stream>>>(__VA_ARGS__); \
     else k_grid<<<grid_ctas(e), grid_block(e), 0, stream>>>(__VA_ARGS__);          \
   } while (0)
-#define GRID_ADJ_LAUNCH(e, stream, ...)                                                \
+#define GRID_ADJ_LAUNCH(e, stream, sc, ...)                                            \
   do {                                                                                 \
     if ((e)->flat_grid) k_grid_adj_flat<<<148 * 4, FLAT_THREADS, 0, stream>>>(__VA_ARGS__); \
-    else k_grid_adj<<<grid_ctas(e), grid_block(e), 0, stream>>>(__VA_ARGS__);          \
+    else k_grid_adj<<<grid_ctas(e), grid_block(e), 0, stream>>>(__VA_ARGS__, sc);      \
   } while (0)
 
 // zero the grids of the last substep of a fine-grained (dsk_substep / dsk_substep_grad) sequence
@@ -742,7 +753,7 @@ static int seq_substep_grad(dsk_engine* e, StepSlot& s, int q, int j) {
     KL(KID_G2P_ADJ, k_g2p_adj<3><<<nb, 128, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
   else
     KL(KID_G2P_ADJ, k_g2p_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
-  KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, e->qs, k, e->d_tools, s.poses, j, e->G0[set], e->Ga[set],
+  KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, e->qs, (GridAdjScratch{nullptr, nullptr, 0}), k, e->d_tools, s.poses, j, e->G0[set], e->Ga[set],
                                                                       tt.list, tt.count, e->pose_adj));
   KL(KID_P2G_ADJ, k_p2g_adj<<<nb, 128, 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]));
   LAUNCH_CHECK();
@@ -781,6 +792,12 @@ static int enqueue_backward_pipelined(dsk_engine* e, StepSlot& s) {
     TileTrack tt{e->tile_epoch[set], e->tile_list[set], e->tile_count + ((q + 1) & 3)};
     if (q >= 2) {
       CK(cudaStreamWaitEvent(side, e->ev_main[q - 2], 0));
+      if (!e->flat_grid && e->gadj_scratch[0]) {   // position q-2 used this set and parked its contact adjoints
+        GridAdjScratch sc{e->gadj_scratch[q & 1], e->gadj_flags[q & 1], e->gadj_cap};
+        KL(KID_GRID_ADJ_TOOLS, k_grid_adj_tools<<<grid_ctas(e), grid_block(e), 0, side>>>(
+                                   k, e->d_tools, s.poses, e->S - 1 - (q - 2), e->G0[set], e->tile_list[set],
+                                   e->tile_count + ((q - 1) & 3), e->pose_adj, sc));
+      }
       KL(KID_GRID_RECOMPUTE, k_clear_set<<<grid_ctas(e), GRID_CTA, 0, side>>>(k, e->tile_list[set], e->tile_count + ((q - 1) & 3),
                                                                               e->G0[set], e->Gv[set], e->Ga[set]));
     }
@@ -796,7 +813,11 @@ static int enqueue_backward_pipelined(dsk_engine* e, StepSlot& s) {
       KL(KID_G2P_ADJ, k_g2p_adj<3><<<nb, 128, 0, mainq>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
     else
       KL(KID_G2P_ADJ, k_g2p_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, mainq>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
-    KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, mainq, k, e->d_tools, s.poses, j, e->G0[set], e->Ga[set],
+    // the pose adjoints of the contacts leave the critical path: parked here, reduced on the side branch two
+    // positions later (before this grid set is cleared); the last two positions do them inline
+    bool park = !e->flat_grid && e->gadj_scratch[0] && q + 2 < e->S;
+    GridAdjScratch sc{park ? e->gadj_scratch[q & 1] : nullptr, park ? e->gadj_flags[q & 1] : nullptr, park ? e->gadj_cap : 0};
+    KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, mainq, sc, k, e->d_tools, s.poses, j, e->G0[set], e->Ga[set],
                                                                           tt.list, tt.count, e->pose_adj));
     KL(KID_P2G_ADJ, k_p2g_adj<<<nb, 128, 0, mainq>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]));
     CK(cudaEventRecord(e->ev_main[q], mainq));

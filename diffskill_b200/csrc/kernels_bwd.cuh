@@ -197,13 +197,82 @@ struct ContactGeomAdj {   // per (node, frame), shared memory
   float gdist;
 };
 
+// phase C of grid_op.grad: geometry adjoints of one (node, frame), reduced over the tile's 64 nodes, then the pose
+// adjoints of the frame's tool at substeps j and j+1.  Called by every thread of the CTA (one barrier inside).
+DSK_DEV void frame_pose_adjoint(const SimConst& k, const ToolParams* sT, const FrameTable& ft, const TileFrames& tf, int y,
+                                int l, float3 gp, const ContactGeom& c, bool contact_frame, float3 gD, float3 gcv,
+                                float gdist, float (*red)[2][14], const float* __restrict__ poses, int env, int j,
+                                float* __restrict__ pose_adj) {
+  if (contact_frame) {
+    FrameAdj a0 = frame_adj_zero(), a1 = frame_adj_zero();
+    if (c.influence >= 0.f) {
+      const ToolParams& T = sT[ft.tool[y]];
+      int kind = ft.flag[y] != 0.f ? SDF_BOX : sdf_kind(T.type);
+      // D = qrot(q0, n/L)
+      float3 Nl = (1.f / c.L) * c.nraw, gNl = f3(0, 0, 0);
+      qrot_adj(tf.F0[y].q, Nl, gD, a0.q, gNl);
+      float3 gpl = local_normal_adj_cached(T, kind, c.pl, c.nraw, c.L, gNl);
+      // dist = sdf(pl)
+      gpl += gdist * local_sdf_grad(T, kind, c.pl);
+      // cv = (qrot(q1, pl) + o1 - p) / dt
+      float3 gnp = (1.f / k.dt) * gcv;
+      a1.o += gnp;
+      qrot_adj(tf.F1[y].q, c.pl, gnp, a1.q, gpl);
+      // pl = inv_trans(F0, p)
+      float3 unused = f3(0, 0, 0);
+      inv_trans_adj(tf.F0[y], gp, gpl, a0, unused);
+    }
+    float vals[14] = {a0.o.x, a0.o.y, a0.o.z, a0.q.w, a0.q.x, a0.q.y, a0.q.z,
+                      a1.o.x, a1.o.y, a1.o.z, a1.q.w, a1.q.x, a1.q.y, a1.q.z};
+#pragma unroll
+    for (int q = 0; q < 14; q++) {
+      float s = warp_sum(vals[q]);
+      if ((l & 31) == 0) red[y][l >> 5][q] = s;
+    }
+  }
+  __syncthreads();
+  if (l == 0 && contact_frame) {
+    FrameAdj a0, a1;
+    float r[14];
+    for (int q = 0; q < 14; q++) r[q] = red[y][0][q] + red[y][1][q];
+    a0.o = f3(r[0], r[1], r[2]); a0.q.w = r[3]; a0.q.x = r[4]; a0.q.y = r[5]; a0.q.z = r[6];
+    a1.o = f3(r[7], r[8], r[9]); a1.q.w = r[10]; a1.q.x = r[11]; a1.q.y = r[12]; a1.q.z = r[13];
+    int t = ft.tool[y];
+    const float* pa = poses + ((size_t)(env * (k.S + 1) + j) * k.K + t) * 8;
+    PoseAdj g0 = pose_adj_zero(), g1 = pose_adj_zero();
+    if (ft.flag[y] != 0.f) {   // jaw_frame_adj is linear in the frame adjoint: apply it after the reduction
+      jaw_frame_adj(load_pose(pa), ft.flag[y], a0, g0);
+      jaw_frame_adj(load_pose(pa + (size_t)k.K * 8), ft.flag[y], a1, g1);
+    } else {
+      tool_frame_adj(a0, g0);
+      tool_frame_adj(a1, g1);
+    }
+    float* adj0 = pose_adj + ((size_t)(env * (k.S + 1) + j) * k.K + t) * 8;
+    float* adj1 = adj0 + (size_t)k.K * 8;
+    float v0[8] = {g0.p.x, g0.p.y, g0.p.z, g0.q.w, g0.q.x, g0.q.y, g0.q.z, g0.gap};
+    float v1[8] = {g1.p.x, g1.p.y, g1.p.z, g1.q.w, g1.q.x, g1.q.y, g1.q.z, g1.gap};
+    for (int q = 0; q < 8; q++) {
+      if (v0[q] != 0.f) atomicAdd(adj0 + q, v0[q]);
+      if (v1[q] != 0.f) atomicAdd(adj1 + q, v1[q]);
+    }
+  }
+}
+
+// Only the adjoint of (grid_v_in, grid_m) is on the critical path of substep_grad; the tool-pose adjoints are needed
+// once per env step (k_kinematics_adj).  With a scratch buffer k_grid_adj parks the per-(node, frame) adjoints of
+// the contact geometry (gD, gcv, gdist) there and k_grid_adj_tools turns them into pose adjoints on a side branch.
+struct GridAdjScratch {
+  float* data;   // [cap][n_frames][7][64], indexed by position in the active-tile list (null: inline pose adjoints)
+  int* flags;    // [cap][MAX_FRAMES] frame had a contact in the tile
+  int cap;
+};
 // grid_op.grad over the active tiles, blockDim = (64, n_frames).  G0: (momentum, mass) of the recomputed p2g.
 // Ga: in = adjoint of grid_v_out (xyz), out = adjoint of (grid_v_in, grid_m), in place.
 // pose_adj: [B][S+1][K][8] accumulators.
 __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
     k_grid_adj(SimConst k, const ToolParams* __restrict__ tools, const float* __restrict__ poses, int j,
                const float4* __restrict__ G0, float4* __restrict__ Ga, const int* __restrict__ list,
-               const int* __restrict__ count, float* __restrict__ pose_adj) {
+               const int* __restrict__ count, float* __restrict__ pose_adj, GridAdjScratch sc) {
   DSK_TL(k);
   __shared__ ToolParams sT[DSK_MAX_TOOLS];
   __shared__ FrameTable ft;
@@ -279,67 +348,80 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
       }
       Ga[o] = outv;
     }
+    const bool park = sc.data != nullptr && it < sc.cap;   // uniform
+    if (park && l == 0 && y < ft.n && !any) sc.flags[it * MAX_FRAMES + y] = 0;
     if (!any) {   // no tool near this tile: nothing to differentiate through (uniform branch)
       __syncthreads();
       continue;
     }
     __syncthreads();
-    // phase C: geometry adjoints per (node, frame), reduced over the tile's nodes
-    if (y < ft.n && any_contact[y]) {
-      FrameAdj a0 = frame_adj_zero(), a1 = frame_adj_zero();
-      if (geo[y][l].influence >= 0.f) {
-        const ToolParams& T = sT[ft.tool[y]];
-        int kind = ft.flag[y] != 0.f ? SDF_BOX : sdf_kind(T.type);
-        const ContactGeomAdj& a = gadj[y][l];
-        const ContactGeom& c = geo[y][l];
-        // D = qrot(q0, n/L)
-        float3 Nl = (1.f / c.L) * c.nraw, gNl = f3(0, 0, 0);
-        qrot_adj(tf.F0[y].q, Nl, a.gD, a0.q, gNl);
-        float3 gpl = local_normal_adj_cached(T, kind, c.pl, c.nraw, c.L, gNl);
-        // dist = sdf(pl)
-        gpl += a.gdist * local_sdf_grad(T, kind, c.pl);
-        // cv = (qrot(q1, pl) + o1 - p) / dt
-        float3 gnp = (1.f / k.dt) * a.gcv;
-        a1.o += gnp;
-        qrot_adj(tf.F1[y].q, c.pl, gnp, a1.q, gpl);
-        // pl = inv_trans(F0, p)
-        float3 unused = f3(0, 0, 0);
-        inv_trans_adj(tf.F0[y], gp, gpl, a0, unused);
+    if (park) {
+      if (y < ft.n) {
+        if (l == 0) sc.flags[it * MAX_FRAMES + y] = any_contact[y];
+        if (any_contact[y]) {
+          const ContactGeomAdj& a = gadj[y][l];
+          bool hit = geo[y][l].influence >= 0.f;
+          float* d = sc.data + ((size_t)(it * ft.n + y) * 7) * GRID_NODES + l;
+          d[0 * GRID_NODES] = hit ? a.gD.x : 0.f;  d[1 * GRID_NODES] = hit ? a.gD.y : 0.f;  d[2 * GRID_NODES] = hit ? a.gD.z : 0.f;
+          d[3 * GRID_NODES] = hit ? a.gcv.x : 0.f; d[4 * GRID_NODES] = hit ? a.gcv.y : 0.f; d[5 * GRID_NODES] = hit ? a.gcv.z : 0.f;
+          d[6 * GRID_NODES] = hit ? a.gdist : 0.f;
+        }
       }
-      float vals[14] = {a0.o.x, a0.o.y, a0.o.z, a0.q.w, a0.q.x, a0.q.y, a0.q.z,
-                        a1.o.x, a1.o.y, a1.o.z, a1.q.w, a1.q.x, a1.q.y, a1.q.z};
-#pragma unroll
-      for (int q = 0; q < 14; q++) {
-        float s = warp_sum(vals[q]);
-        if ((l & 31) == 0) red[y][l >> 5][q] = s;
-      }
+      __syncthreads();
+      continue;
     }
+    frame_pose_adjoint(k, sT, ft, tf, y, l, gp, geo[y][l], y < ft.n && any_contact[y], gadj[y][l].gD, gadj[y][l].gcv,
+                       gadj[y][l].gdist, red, poses, env, j, pose_adj);
     __syncthreads();
-    if (l == 0 && y < ft.n && any_contact[y]) {
-      FrameAdj a0, a1;
-      float r[14];
-      for (int q = 0; q < 14; q++) r[q] = red[y][0][q] + red[y][1][q];
-      a0.o = f3(r[0], r[1], r[2]); a0.q.w = r[3]; a0.q.x = r[4]; a0.q.y = r[5]; a0.q.z = r[6];
-      a1.o = f3(r[7], r[8], r[9]); a1.q.w = r[10]; a1.q.x = r[11]; a1.q.y = r[12]; a1.q.z = r[13];
-      int t = ft.tool[y];
-      const float* pa = poses + ((size_t)(env * (k.S + 1) + j) * k.K + t) * 8;
-      PoseAdj g0 = pose_adj_zero(), g1 = pose_adj_zero();
-      if (ft.flag[y] != 0.f) {   // jaw_frame_adj is linear in the frame adjoint: apply it after the reduction
-        jaw_frame_adj(load_pose(pa), ft.flag[y], a0, g0);
-        jaw_frame_adj(load_pose(pa + (size_t)k.K * 8), ft.flag[y], a1, g1);
-      } else {
-        tool_frame_adj(a0, g0);
-        tool_frame_adj(a1, g1);
+  }
+}
+
+// second half of the split k_grid_adj (side branch): pose adjoints from the parked (gD, gcv, gdist); the contact
+// geometry is recomputed, which is free off the critical path
+__global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
+    k_grid_adj_tools(SimConst k, const ToolParams* __restrict__ tools, const float* __restrict__ poses, int j,
+                     const float4* __restrict__ G0, const int* __restrict__ list, const int* __restrict__ count,
+                     float* __restrict__ pose_adj, GridAdjScratch sc) {
+  DSK_TL(k);
+  __shared__ ToolParams sT[DSK_MAX_TOOLS];
+  __shared__ FrameTable ft;
+  __shared__ TileFrames tf;
+  __shared__ float red[MAX_FRAMES][2][14];
+  const int l = threadIdx.x, y = threadIdx.y, tid = y * GRID_NODES + l, nthr = GRID_NODES * blockDim.y;
+  for (int i = tid; i < k.K * (int)(sizeof(ToolParams) / 4); i += nthr) ((int*)sT)[i] = ((const int*)tools)[i];
+  __syncthreads();
+  if (tid == 0) build_frame_table(k, sT, ft);
+  __syncthreads();
+  int n_active = min(*count, sc.cap);
+  for (int it = blockIdx.x; it < n_active; it += gridDim.x) {
+    int anyf = 0;
+    for (int f = 0; f < ft.n; f++) anyf |= sc.flags[it * MAX_FRAMES + f];
+    if (!anyf) continue;   // uniform
+    const bool fl = y < ft.n && sc.flags[it * MAX_FRAMES + y] != 0;
+    int gt = list[it];
+    int env = gt / k.ntile, tile = gt - env * k.ntile;
+    int tz = tile % k.nt, ty = (tile / k.nt) % k.nt, tx = tile / (k.nt * k.nt);
+    size_t o = ((size_t)gt << 6) + l;
+    bool live = G0[o].w > k.m_eps;
+    int I0 = tx * 4 + (l >> 4), I1 = ty * 4 + ((l >> 2) & 3), I2 = tz * 4 + (l & 3);
+    float3 gp = f3(mul_rn((float)I0, k.dx), mul_rn((float)I1, k.dx), mul_rn((float)I2, k.dx));
+    if (l == 0 && fl) prepare_tile_frame(k, sT, ft, y, poses, env, j, tx, ty, tz, tf);
+    __syncthreads();
+    ContactGeom c;
+    c.influence = -1.f;
+    float3 gD = f3(0, 0, 0), gcv = f3(0, 0, 0);
+    float gdist = 0.f;
+    if (fl) {
+      if (live && tf.active[y]) {
+        const ToolParams& T = sT[ft.tool[y]];
+        contact_geometry(T, ft.flag[y] != 0.f ? SDF_BOX : sdf_kind(T.type), tf.F0[y], tf.F1[y], gp, k.dt, c);
       }
-      float* adj0 = pose_adj + ((size_t)(env * (k.S + 1) + j) * k.K + t) * 8;
-      float* adj1 = adj0 + (size_t)k.K * 8;
-      float v0[8] = {g0.p.x, g0.p.y, g0.p.z, g0.q.w, g0.q.x, g0.q.y, g0.q.z, g0.gap};
-      float v1[8] = {g1.p.x, g1.p.y, g1.p.z, g1.q.w, g1.q.x, g1.q.y, g1.q.z, g1.gap};
-      for (int q = 0; q < 8; q++) {
-        if (v0[q] != 0.f) atomicAdd(adj0 + q, v0[q]);
-        if (v1[q] != 0.f) atomicAdd(adj1 + q, v1[q]);
-      }
+      const float* d = sc.data + ((size_t)(it * ft.n + y) * 7) * GRID_NODES + l;
+      gD = f3(d[0 * GRID_NODES], d[1 * GRID_NODES], d[2 * GRID_NODES]);
+      gcv = f3(d[3 * GRID_NODES], d[4 * GRID_NODES], d[5 * GRID_NODES]);
+      gdist = d[6 * GRID_NODES];
     }
+    frame_pose_adjoint(k, sT, ft, tf, y, l, gp, c, fl, gD, gcv, gdist, red, poses, env, j, pose_adj);
     __syncthreads();
   }
 }
