@@ -685,8 +685,8 @@ static int seq_forward_fused(dsk_engine* e, StepSlot& s) {
         KL(KID_G2P2G, k_g2p2g<3><<<nb, 128, 0, e->qs>>>(k, frame(q), frame(q + 1), frame(q + 2), s.mat, e->npart, e->G0[set],
                                                      e->G0[nset], tt, e->d_args, q + 1));
       else
-        KL(KID_G2P2G, k_g2p2g<1><<<nb, 128, 0, e->qs>>>(k, frame(q), frame(q + 1), frame(q + 2), s.mat, e->npart, e->G0[set],
-                                                     e->G0[nset], tt, e->d_args, q + 1));
+        KL(KID_G2P2G, k_g2p2g_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, e->qs>>>(
+                          k, frame(q), frame(q + 1), frame(q + 2), s.mat, e->npart, e->G0[set], e->G0[nset], tt, e->d_args, q + 1));
     } else {
       KL(KID_G2P, k_g2p<<<nb, 128, 0, e->qs>>>(k, frame(q), frame(q + 1), e->npart, e->G0[set]));
     }
@@ -755,7 +755,10 @@ static int seq_substep_grad(dsk_engine* e, StepSlot& s, int q, int j) {
     KL(KID_G2P_ADJ, k_g2p_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
   KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, e->qs, (GridAdjScratch{nullptr, nullptr, 0}), k, e->d_tools, s.poses, j, e->G0[set], e->Ga[set],
                                                                       tt.list, tt.count, e->pose_adj));
-  KL(KID_P2G_ADJ, k_p2g_adj<<<nb, 128, 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]));
+  if (e->big)
+    KL(KID_P2G_ADJ, k_p2g_adj<<<nb, 128, 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]));
+  else
+    KL(KID_P2G_ADJ, k_p2g_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]));
   LAUNCH_CHECK();
   e->bwd_cur ^= 1;
   return 0;
@@ -819,7 +822,10 @@ static int enqueue_backward_pipelined(dsk_engine* e, StepSlot& s) {
     GridAdjScratch sc{park ? e->gadj_scratch[q & 1] : nullptr, park ? e->gadj_flags[q & 1] : nullptr, park ? e->gadj_cap : 0};
     KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, mainq, sc, k, e->d_tools, s.poses, j, e->G0[set], e->Ga[set],
                                                                           tt.list, tt.count, e->pose_adj));
-    KL(KID_P2G_ADJ, k_p2g_adj<<<nb, 128, 0, mainq>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]));
+    if (e->big)
+      KL(KID_P2G_ADJ, k_p2g_adj<<<nb, 128, 0, mainq>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]));
+    else
+      KL(KID_P2G_ADJ, k_p2g_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, mainq>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]));
     CK(cudaEventRecord(e->ev_main[q], mainq));
     e->bwd_cur ^= 1;
   }

@@ -538,54 +538,12 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4)
   }
 }
 
-// p2g.grad + svd_grad + compute_F_tmp.grad fused: gathers adjoints of (grid_v_in, grid_m), reads F.grad[j+1],
-// writes x.grad (adding the g2p part already stored), v.grad, C.grad, F.grad of frame j.
-__global__ void __launch_bounds__(128, 3)
-    k_p2g_adj(SimConst k, const float* __restrict__ fin, const float* __restrict__ adj_in, float* __restrict__ adj_out,
-              const float* __restrict__ mat, const int* __restrict__ npart, const float4* __restrict__ Ga) {
-  DSK_TL(k);
-  int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= k.stride) return;
-  int env = gid / k.Npad, p = gid - env * k.Npad;
-  if (p >= npart[env]) return;
-  float3 x = load_v3(fin, CX, k.stride, gid);
-  float3 v = load_v3(fin, CV, k.stride, gid);
-  M3 C = load_m3(fin, CC, k.stride, gid);
-  M3 F = load_m3(fin, CF, k.stride, gid);
-  float mu = mat[gid], lam = mat[k.stride + gid], ys = mat[2 * k.stride + gid];
-  P2GParticle o;
-  p2g_particle(k, C, F, mu, lam, ys, o);
-  Stencil s;
-  make_stencil(k, x.x, x.y, x.z, s);
-  const float4* Gae = Ga + (size_t)env * k.nnode;
-  // contribution(node) = w * (a0 + i ax + j ay + l az, p_mass)  (see k_p2g); with S0 = sum w G and M = sum w G (x) offset:
-  //   g(v) = p_mass S0 ; g(affine) = dx (M - S0 (x) fx) ; g(fx) through dpos = -dx affine^T S0 ; g(w) = G . a + gm p_mass
-  float3 fxv = f3(s.fx, s.fy, s.fz);
-  float3 a0 = k.p_mass * v - k.dx * mv(o.affine, fxv);
-  float3 ax = f3(k.dx * o.affine.m[0], k.dx * o.affine.m[3], k.dx * o.affine.m[6]);
-  float3 ay = f3(k.dx * o.affine.m[1], k.dx * o.affine.m[4], k.dx * o.affine.m[7]);
-  float3 az = f3(k.dx * o.affine.m[2], k.dx * o.affine.m[5], k.dx * o.affine.m[8]);
-  float gwx[3] = {0, 0, 0}, gwy[3] = {0, 0, 0}, gwz[3] = {0, 0, 0};
-  float3 S0 = f3(0, 0, 0), m0 = f3(0, 0, 0), m1 = f3(0, 0, 0), m2 = f3(0, 0, 0);
-#pragma unroll
-  for (int i = 0; i < 3; i++)
-#pragma unroll
-    for (int j = 0; j < 3; j++)
-#pragma unroll
-      for (int l = 0; l < 3; l++) {
-        float4 g4 = Gae[s.ox[i] + s.oy[j] + s.oz[l]];
-        float3 G = f3(g4.x, g4.y, g4.z);
-        float3 a = a0 + (float)i * ax + (float)j * ay + (float)l * az;
-        float gw = dot(G, a) + g4.w * k.p_mass;
-        float3 wG = (s.wx[i] * s.wy[j] * s.wz[l]) * G;
-        S0 += wG;
-        if (i) m0 += (float)i * wG;
-        if (j) m1 += (float)j * wG;
-        if (l) m2 += (float)l * wG;
-        gwx[i] += gw * s.wy[j] * s.wz[l];
-        gwy[j] += gw * s.wx[i] * s.wz[l];
-        gwz[l] += gw * s.wx[i] * s.wy[j];
-      }
+// everything of p2g.grad after the 27-node gather: S0 = sum w G, (m0,m1,m2) = columns of sum w G (x) offset,
+// gw* = adjoints of the per-axis weights
+DSK_DEV void p2g_adj_finish(const SimConst& k, int gid, const Stencil& s, const P2GParticle& o, float mu, float lam,
+                            const M3& C, const M3& F, const float* __restrict__ adj_in, float* __restrict__ adj_out,
+                            float3 S0, float3 m0, float3 m1, float3 m2, const float* gwx, const float* gwy,
+                            const float* gwz) {
   float3 gv = k.p_mass * S0;
   float3 gf = (-k.dx) * mTv(o.affine, S0);
   M3 gA;  // adjoint of affine
@@ -678,6 +636,125 @@ __global__ void __launch_bounds__(128, 3)
   store_v3(adj_out, CV, k.stride, gid, gv);
   store_m3(adj_out, CC, k.stride, gid, gCm);
   store_m3(adj_out, CF, k.stride, gid, gF);
+}
+
+// p2g.grad + svd_grad + compute_F_tmp.grad fused: gathers adjoints of (grid_v_in, grid_m), reads F.grad[j+1],
+// writes x.grad (adding the g2p part already stored), v.grad, C.grad, F.grad of frame j.
+__global__ void __launch_bounds__(128, 3)
+    k_p2g_adj(SimConst k, const float* __restrict__ fin, const float* __restrict__ adj_in, float* __restrict__ adj_out,
+              const float* __restrict__ mat, const int* __restrict__ npart, const float4* __restrict__ Ga) {
+  DSK_TL(k);
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= k.stride) return;
+  int env = gid / k.Npad, p = gid - env * k.Npad;
+  if (p >= npart[env]) return;
+  float3 x = load_v3(fin, CX, k.stride, gid);
+  float3 v = load_v3(fin, CV, k.stride, gid);
+  M3 C = load_m3(fin, CC, k.stride, gid);
+  M3 F = load_m3(fin, CF, k.stride, gid);
+  float mu = mat[gid], lam = mat[k.stride + gid], ys = mat[2 * k.stride + gid];
+  P2GParticle o;
+  p2g_particle(k, C, F, mu, lam, ys, o);
+  Stencil s;
+  make_stencil(k, x.x, x.y, x.z, s);
+  const float4* Gae = Ga + (size_t)env * k.nnode;
+  // contribution(node) = w * (a0 + i ax + j ay + l az, p_mass)  (see k_p2g); with S0 = sum w G and M = sum w G (x) offset:
+  //   g(v) = p_mass S0 ; g(affine) = dx (M - S0 (x) fx) ; g(fx) through dpos = -dx affine^T S0 ; g(w) = G . a + gm p_mass
+  float3 fxv = f3(s.fx, s.fy, s.fz);
+  float3 a0 = k.p_mass * v - k.dx * mv(o.affine, fxv);
+  float3 ax = f3(k.dx * o.affine.m[0], k.dx * o.affine.m[3], k.dx * o.affine.m[6]);
+  float3 ay = f3(k.dx * o.affine.m[1], k.dx * o.affine.m[4], k.dx * o.affine.m[7]);
+  float3 az = f3(k.dx * o.affine.m[2], k.dx * o.affine.m[5], k.dx * o.affine.m[8]);
+  float gwx[3] = {0, 0, 0}, gwy[3] = {0, 0, 0}, gwz[3] = {0, 0, 0};
+  float3 S0 = f3(0, 0, 0), m0 = f3(0, 0, 0), m1 = f3(0, 0, 0), m2 = f3(0, 0, 0);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int l = 0; l < 3; l++) {
+        float4 g4 = Gae[s.ox[i] + s.oy[j] + s.oz[l]];
+        float3 G = f3(g4.x, g4.y, g4.z);
+        float3 a = a0 + (float)i * ax + (float)j * ay + (float)l * az;
+        float gw = dot(G, a) + g4.w * k.p_mass;
+        float3 wG = (s.wx[i] * s.wy[j] * s.wz[l]) * G;
+        S0 += wG;
+        if (i) m0 += (float)i * wG;
+        if (j) m1 += (float)j * wG;
+        if (l) m2 += (float)l * wG;
+        gwx[i] += gw * s.wy[j] * s.wz[l];
+        gwy[j] += gw * s.wx[i] * s.wz[l];
+        gwz[l] += gw * s.wx[i] * s.wy[j];
+      }
+  p2g_adj_finish(k, gid, s, o, mu, lam, C, F, adj_in, adj_out, S0, m0, m1, m2, gwx, gwy, gwz);
+}
+
+// plane-split p2g.grad for small engines: three threads per particle gather one x-plane of the stencil each
+__global__ void __launch_bounds__(PL_PARTICLES * 3)
+    k_p2g_adj_pl(SimConst k, const float* __restrict__ fin, const float* __restrict__ adj_in, float* __restrict__ adj_out,
+                 const float* __restrict__ mat, const int* __restrict__ npart, const float4* __restrict__ Ga) {
+  DSK_TL(k);
+  __shared__ float ex[3][16][PL_PARTICLES];
+  const int tx = threadIdx.x, pl = threadIdx.y;
+  int gid = blockIdx.x * PL_PARTICLES + tx;
+  int env = min(gid / k.Npad, k.B - 1), p = gid - env * k.Npad;
+  bool active = gid < k.stride && p < npart[env];
+  int gi = active ? gid : env * k.Npad;
+  float3 x = load_v3(fin, CX, k.stride, gi);
+  float3 v = load_v3(fin, CV, k.stride, gi);
+  M3 C = load_m3(fin, CC, k.stride, gi);
+  M3 F = load_m3(fin, CF, k.stride, gi);
+  float mu = mat[gi], lam = mat[k.stride + gi], ys = mat[2 * k.stride + gi];
+  P2GParticle o;
+  p2g_particle(k, C, F, mu, lam, ys, o);
+  Stencil s;
+  make_stencil(k, x.x, x.y, x.z, s);
+  const float4* Gae = Ga + (size_t)env * k.nnode;
+  {
+    const float wxp = pick3(s.wx, pl);
+    const int oxp = pick3(s.ox, pl);
+    float3 fxv = f3(s.fx, s.fy, s.fz);
+    float3 ax = f3(k.dx * o.affine.m[0], k.dx * o.affine.m[3], k.dx * o.affine.m[6]);
+    float3 ay = f3(k.dx * o.affine.m[1], k.dx * o.affine.m[4], k.dx * o.affine.m[7]);
+    float3 az = f3(k.dx * o.affine.m[2], k.dx * o.affine.m[5], k.dx * o.affine.m[8]);
+    float3 a0 = k.p_mass * v - k.dx * mv(o.affine, fxv) + (float)pl * ax;
+    float gwxp = 0.f, gwy[3] = {0, 0, 0}, gwz[3] = {0, 0, 0};
+    float3 S0 = f3(0, 0, 0), m1 = f3(0, 0, 0), m2 = f3(0, 0, 0);
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int l = 0; l < 3; l++) {
+        float4 g4 = Gae[oxp + s.oy[j] + s.oz[l]];
+        float3 G = f3(g4.x, g4.y, g4.z);
+        float3 a = a0 + (float)j * ay + (float)l * az;
+        float gw = dot(G, a) + g4.w * k.p_mass;
+        float3 wG = (wxp * s.wy[j] * s.wz[l]) * G;
+        S0 += wG;
+        if (j) m1 += (float)j * wG;
+        if (l) m2 += (float)l * wG;
+        gwxp += gw * s.wy[j] * s.wz[l];
+        gwy[j] += gw * wxp * s.wz[l];
+        gwz[l] += gw * wxp * s.wy[j];
+      }
+    float part[16] = {S0.x, S0.y, S0.z, m1.x, m1.y, m1.z, m2.x, m2.y, m2.z, gwxp, gwy[0], gwy[1], gwy[2], gwz[0], gwz[1], gwz[2]};
+#pragma unroll
+    for (int q = 0; q < 16; q++) ex[pl][q][tx] = part[q];
+  }
+  __syncthreads();
+  if (pl != 0 || !active) return;
+  float t[3][16];
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int q = 0; q < 16; q++) t[a][q] = ex[a][q][tx];
+  float3 S0 = f3(t[0][0] + t[1][0] + t[2][0], t[0][1] + t[1][1] + t[2][1], t[0][2] + t[1][2] + t[2][2]);
+  float3 m0 = f3(t[1][0] + 2.f * t[2][0], t[1][1] + 2.f * t[2][1], t[1][2] + 2.f * t[2][2]);
+  float3 m1 = f3(t[0][3] + t[1][3] + t[2][3], t[0][4] + t[1][4] + t[2][4], t[0][5] + t[1][5] + t[2][5]);
+  float3 m2 = f3(t[0][6] + t[1][6] + t[2][6], t[0][7] + t[1][7] + t[2][7], t[0][8] + t[1][8] + t[2][8]);
+  float gwx[3] = {t[0][9], t[1][9], t[2][9]};
+  float gwy[3] = {t[0][10] + t[1][10] + t[2][10], t[0][11] + t[1][11] + t[2][11], t[0][12] + t[1][12] + t[2][12]};
+  float gwz[3] = {t[0][13] + t[1][13] + t[2][13], t[0][14] + t[1][14] + t[2][14], t[0][15] + t[1][15] + t[2][15]};
+  p2g_adj_finish(k, gid, s, o, mu, lam, C, F, adj_in, adj_out, S0, m0, m1, m2, gwx, gwy, gwz);
 }
 
 // Tool adjoints of one env step: for j = S-1..0: apply_collision_projection.grad, set_surface_points.grad,

@@ -530,6 +530,16 @@ __global__ void __launch_bounds__(GRID_NODES)
   }
 }
 
+// tail of g2p: new_C = c_C (M - new_v (x) fx) and the clamped position update
+DSK_DEV void g2p_finish(const SimConst& k, const Stencil& s, float3 x, float3 nv, float3 m0, float3 m1, float3 m2,
+                        float3& nx, M3& nC) {
+  nC.m[0] = k.c_C * (m0.x - nv.x * s.fx); nC.m[1] = k.c_C * (m1.x - nv.x * s.fy); nC.m[2] = k.c_C * (m2.x - nv.x * s.fz);
+  nC.m[3] = k.c_C * (m0.y - nv.y * s.fx); nC.m[4] = k.c_C * (m1.y - nv.y * s.fy); nC.m[5] = k.c_C * (m2.y - nv.y * s.fz);
+  nC.m[6] = k.c_C * (m0.z - nv.z * s.fx); nC.m[7] = k.c_C * (m1.z - nv.z * s.fy); nC.m[8] = k.c_C * (m2.z - nv.z * s.fz);
+  nx = f3(tmax(tmin(x.x + k.dt * nv.x, k.x_hi), k.x_lo), tmax(tmin(x.y + k.dt * nv.y, k.x_hi), k.x_lo),
+          tmax(tmin(x.z + k.dt * nv.z, k.x_hi), k.x_lo));
+}
+
 // g2p of one particle (mpm_simulator.py:264-283): new_v = sum w g ; new_C = 4 inv_dx sum w g (x) (offset - fx)
 //   = c_C (M - new_v (x) fx),  M = sum w g (x) offset
 DSK_DEV void g2p_particle(const SimConst& k, const Stencil& s, const float4* __restrict__ Ge, float3 x, float3& nx,
@@ -550,11 +560,7 @@ DSK_DEV void g2p_particle(const SimConst& k, const Stencil& s, const float4* __r
         if (j) m1 += (float)j * wg;
         if (l) m2 += (float)l * wg;
       }
-  nC.m[0] = k.c_C * (m0.x - nv.x * s.fx); nC.m[1] = k.c_C * (m1.x - nv.x * s.fy); nC.m[2] = k.c_C * (m2.x - nv.x * s.fz);
-  nC.m[3] = k.c_C * (m0.y - nv.y * s.fx); nC.m[4] = k.c_C * (m1.y - nv.y * s.fy); nC.m[5] = k.c_C * (m2.y - nv.y * s.fz);
-  nC.m[6] = k.c_C * (m0.z - nv.z * s.fx); nC.m[7] = k.c_C * (m1.z - nv.z * s.fy); nC.m[8] = k.c_C * (m2.z - nv.z * s.fz);
-  nx = f3(tmax(tmin(x.x + k.dt * nv.x, k.x_hi), k.x_lo), tmax(tmin(x.y + k.dt * nv.y, k.x_hi), k.x_lo),
-          tmax(tmin(x.z + k.dt * nv.z, k.x_hi), k.x_lo));
+  g2p_finish(k, s, x, nv, m0, m1, m2, nx, nC);
 }
 
 __global__ void __launch_bounds__(128)
@@ -617,4 +623,83 @@ __global__ void __launch_bounds__(128, MINB)
                    float3 a = a0 + (float)i * ax + (float)j * ay + (float)l * az;
                    return make_float4(w * a.x, w * a.y, w * a.z, w * k.p_mass);
                  });
+}
+
+// plane-split fused g2p(q) + p2g(q+1) for small engines (see warp_scatter9): blockDim = (PL_PARTICLES, 3).  Each of
+// the three threads of a particle gathers one x-plane of the stencil; the partial sums are exchanged through shared
+// memory and added in a fixed order, so the three threads continue with bit-identical state (SVD, return map --
+// redundantly, the machine is idle anyway) and each scatters one x-plane of the new stencil.
+__global__ void __launch_bounds__(PL_PARTICLES * 3)
+    k_g2p2g_pl(SimConst k, const float* __restrict__ fprev, float* __restrict__ fcur, float* __restrict__ fnext,
+               const float* __restrict__ mat, const int* __restrict__ npart, const float4* __restrict__ Gprev,
+               float4* __restrict__ Gnext, TileTrack tt, const StepArgs* __restrict__ args, int qnext) {
+  DSK_TL(k);
+  __shared__ float ex[3][9][PL_PARTICLES];
+  const int tx = threadIdx.x, pl = threadIdx.y;
+  int gid = blockIdx.x * PL_PARTICLES + tx;
+  int env = min(gid / k.Npad, k.B - 1), p = gid - env * k.Npad;
+  bool active = gid < k.stride && p < npart[env];
+  int g = active ? gid : env * k.Npad;
+  float3 x = load_v3(fprev, CX, k.stride, g);
+  M3 F = load_m3(fcur, CF, k.stride, g);   // written by the p2g of substep q
+  float mu = mat[g], lam = mat[k.stride + g], ys = mat[2 * k.stride + g];
+  Stencil s;
+  make_stencil(k, x.x, x.y, x.z, s);
+  {
+    const float4* Ge = Gprev + (size_t)env * k.nnode;
+    const float wxp = pick3(s.wx, pl);
+    const int oxp = pick3(s.ox, pl);
+    float3 nvp = f3(0.f, 0.f, 0.f), m1 = f3(0.f, 0.f, 0.f), m2 = f3(0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int l = 0; l < 3; l++) {
+        float4 gv = Ge[oxp + s.oy[j] + s.oz[l]];
+        float w = wxp * s.wy[j] * s.wz[l];
+        float3 wg = f3(w * gv.x, w * gv.y, w * gv.z);
+        nvp += wg;
+        if (j) m1 += (float)j * wg;
+        if (l) m2 += (float)l * wg;
+      }
+    float part[9] = {nvp.x, nvp.y, nvp.z, m1.x, m1.y, m1.z, m2.x, m2.y, m2.z};
+#pragma unroll
+    for (int q = 0; q < 9; q++) ex[pl][q][tx] = part[q];
+  }
+  __syncthreads();
+  float3 nx, nv;
+  M3 C;
+  {
+    float t[3][9];
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int q = 0; q < 9; q++) t[a][q] = ex[a][q][tx];
+    nv = f3(t[0][0] + t[1][0] + t[2][0], t[0][1] + t[1][1] + t[2][1], t[0][2] + t[1][2] + t[2][2]);
+    float3 m0 = f3(t[1][0] + 2.f * t[2][0], t[1][1] + 2.f * t[2][1], t[1][2] + 2.f * t[2][2]);
+    float3 m1 = f3(t[0][3] + t[1][3] + t[2][3], t[0][4] + t[1][4] + t[2][4], t[0][5] + t[1][5] + t[2][5]);
+    float3 m2 = f3(t[0][6] + t[1][6] + t[2][6], t[0][7] + t[1][7] + t[2][7], t[0][8] + t[1][8] + t[2][8]);
+    g2p_finish(k, s, x, nv, m0, m1, m2, nx, C);
+  }
+  if (active && pl == 0) {
+    store_v3(fcur, CX, k.stride, gid, nx);
+    store_v3(fcur, CV, k.stride, gid, nv);
+    store_m3(fcur, CC, k.stride, gid, C);
+  }
+  P2GParticle o;
+  p2g_particle(k, C, F, mu, lam, ys, o);
+  if (active && pl == 0) store_m3(fnext, CF, k.stride, gid, o.newF);
+  make_stencil(k, nx.x, nx.y, nx.z, s);
+  const float wxp = pick3(s.wx, pl);
+  const int oxp = pick3(s.ox, pl);
+  float3 fxv = f3(s.fx, s.fy, s.fz);
+  float3 ax = f3(k.dx * o.affine.m[0], k.dx * o.affine.m[3], k.dx * o.affine.m[6]);
+  float3 ay = f3(k.dx * o.affine.m[1], k.dx * o.affine.m[4], k.dx * o.affine.m[7]);
+  float3 az = f3(k.dx * o.affine.m[2], k.dx * o.affine.m[5], k.dx * o.affine.m[8]);
+  float3 a0 = k.p_mass * nv - k.dx * mv(o.affine, fxv) + (float)pl * ax;   // plane term folded in
+  warp_scatter9(k, active, s, pl, oxp, Gnext + (size_t)env * k.nnode, tt, pl == 0, env, args->epoch_base + qnext + 1,
+                [&](int j, int l) {
+                  float w = wxp * s.wy[j] * s.wz[l];
+                  float3 a = a0 + (float)j * ay + (float)l * az;
+                  return make_float4(w * a.x, w * a.y, w * a.z, w * k.p_mass);
+                });
 }
