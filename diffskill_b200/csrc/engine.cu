@@ -132,6 +132,9 @@ struct dsk_engine {
   float* gadj_scratch[2] = {nullptr, nullptr};   // parked contact adjoints of k_grid_adj (latency layout only)
   int* gadj_flags[2] = {nullptr, nullptr};
   int gadj_cap = 0;
+  // resident 128-thread CTAs per SM requested from the particle kernels of batched engines (register cap 65536/(128*n))
+  int big_block = 128;
+  int minb_g2p2g = 4, minb_g2p_adj = 4, minb_p2g_adj = 4;
   bool flat_grid = false;   // many active tiles: throughput layout of the grid kernels
   cudaStream_t cap_side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -332,6 +335,11 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
 #endif
   e->big = (size_t)c->n_envs * c->particle_capacity >= 65536;
   if (const char* v = getenv("DSK_FORCE_BIG")) e->big = atoi(v) != 0;
+  if (const char* v = getenv("DSK_BIG_MINB")) e->minb_g2p2g = e->minb_g2p_adj = e->minb_p2g_adj = atoi(v);
+  if (const char* v = getenv("DSK_BIG_BLOCK")) e->big_block = atoi(v) == 64 ? 64 : 128;
+  if (const char* v = getenv("DSK_MINB_G2P2G")) e->minb_g2p2g = atoi(v);
+  if (const char* v = getenv("DSK_MINB_G2P_ADJ")) e->minb_g2p_adj = atoi(v);
+  if (const char* v = getenv("DSK_MINB_P2G_ADJ")) e->minb_p2g_adj = atoi(v);
   e->flat_grid = e->big;
   if (const char* v = getenv("DSK_FLAT_GRID")) e->flat_grid = atoi(v) != 0;
   e->tool_floats = (size_t)e->B * std::max(1, e->K) * 8;
@@ -625,16 +633,17 @@ static int seq_substep(dsk_engine* e, StepSlot& s, int q, int j, bool write_stat
   SimConst& k = e->k;
   int set = (q + 1) & 1, prev = set ^ 1;
   TileTrack tt{e->tile_epoch[set], e->tile_list[set], e->tile_count + ((q + 1) & 3)};
-  int nb = cdiv(k.stride, 128);
+  const int pb = e->big ? e->big_block : 128;   // threads per CTA of the particle kernels
+  int nb = cdiv(k.stride, pb);
   float* fin = s.frames + (size_t)j * e->frame_floats;
   float* fout = s.frames + (size_t)(j + 1) * e->frame_floats;
   if (write_state)
     if (e->big)
-      KL(KID_P2G, k_p2g<true, 3><<<nb, 128, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q, nullptr));
+      KL(KID_P2G, k_p2g<true, 3><<<nb, pb, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q, nullptr));
     else
-      KL(KID_P2G, k_p2g<true, 1><<<nb, 128, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q, nullptr));
+      KL(KID_P2G, k_p2g<true, 1><<<nb, pb, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q, nullptr));
   else
-    KL(KID_P2G_RECOMPUTE, k_p2g<false, 3><<<nb, 128, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q, nullptr));
+    KL(KID_P2G_RECOMPUTE, k_p2g<false, 3><<<nb, pb, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q, nullptr));
   bool clr = q > 0;
   if (e->kin_join) {
     CK(cudaStreamWaitEvent(e->qs, e->ev_join, 0));
@@ -644,7 +653,7 @@ static int seq_substep(dsk_engine* e, StepSlot& s, int q, int j, bool write_stat
                    k, e->d_tools, s.poses, j, e->G0[set], e->G0[set], tt.list, tt.count,
                    clr ? e->tile_list[prev] : nullptr, e->tile_count + (q & 3), clr ? e->G0[prev] : nullptr, nullptr,
                    nullptr, e->tile_count + ((q + 3) & 3), write_state ? s.tape : GridTape{nullptr, nullptr, nullptr, nullptr, 0}, nullptr));
-  if (write_state) KL(KID_G2P, k_g2p<<<nb, 128, 0, e->qs>>>(k, fin, fout, e->npart, e->G0[set]));
+  if (write_state) KL(KID_G2P, k_g2p<<<nb, pb, 0, e->qs>>>(k, fin, fout, e->npart, e->G0[set]));
   LAUNCH_CHECK();
   return 0;
 }
@@ -667,14 +676,15 @@ static int seq_grid_fwd(dsk_engine* e, StepSlot& s, int q) {
 // forward substeps of a whole step with g2p(q) fused into p2g(q+1)
 static int seq_forward_fused(dsk_engine* e, StepSlot& s) {
   SimConst& k = e->k;
-  int nb = cdiv(k.stride, 128);
+  const int pb = e->big ? e->big_block : 128;   // threads per CTA of the particle kernels
+  int nb = cdiv(k.stride, pb);
   auto frame = [&](int j) { return s.frames + (size_t)j * e->frame_floats; };
   {
     TileTrack tt{e->tile_epoch[1], e->tile_list[1], e->tile_count + 1};
     if (e->big)
-      KL(KID_P2G, k_p2g<true, 3><<<nb, 128, 0, e->qs>>>(k, frame(0), frame(1), s.mat, e->npart, e->G0[1], tt, e->d_args, 0, nullptr));
+      KL(KID_P2G, k_p2g<true, 3><<<nb, pb, 0, e->qs>>>(k, frame(0), frame(1), s.mat, e->npart, e->G0[1], tt, e->d_args, 0, nullptr));
     else
-      KL(KID_P2G, k_p2g<true, 1><<<nb, 128, 0, e->qs>>>(k, frame(0), frame(1), s.mat, e->npart, e->G0[1], tt, e->d_args, 0, nullptr));
+      KL(KID_P2G, k_p2g<true, 1><<<nb, pb, 0, e->qs>>>(k, frame(0), frame(1), s.mat, e->npart, e->G0[1], tt, e->d_args, 0, nullptr));
   }
   for (int q = 0; q < e->S; q++) {
     if (seq_grid_fwd(e, s, q)) return -1;
@@ -682,13 +692,19 @@ static int seq_forward_fused(dsk_engine* e, StepSlot& s) {
     if (q + 1 < e->S) {
       TileTrack tt{e->tile_epoch[nset], e->tile_list[nset], e->tile_count + ((q + 2) & 3)};
       if (e->big)
-        KL(KID_G2P2G, k_g2p2g<3><<<nb, 128, 0, e->qs>>>(k, frame(q), frame(q + 1), frame(q + 2), s.mat, e->npart, e->G0[set],
-                                                     e->G0[nset], tt, e->d_args, q + 1));
+        switch (e->minb_g2p2g) {
+          case 5: KL(KID_G2P2G, k_g2p2g<5><<<nb, pb, 0, e->qs>>>(k, frame(q), frame(q + 1), frame(q + 2), s.mat, e->npart, e->G0[set],
+                                                       e->G0[nset], tt, e->d_args, q + 1)); break;
+          case 4: KL(KID_G2P2G, k_g2p2g<4><<<nb, pb, 0, e->qs>>>(k, frame(q), frame(q + 1), frame(q + 2), s.mat, e->npart, e->G0[set],
+                                                       e->G0[nset], tt, e->d_args, q + 1)); break;
+          default: KL(KID_G2P2G, k_g2p2g<3><<<nb, pb, 0, e->qs>>>(k, frame(q), frame(q + 1), frame(q + 2), s.mat, e->npart, e->G0[set],
+                                                       e->G0[nset], tt, e->d_args, q + 1)); break;
+        }
       else
         KL(KID_G2P2G, k_g2p2g_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, e->qs>>>(
                           k, frame(q), frame(q + 1), frame(q + 2), s.mat, e->npart, e->G0[set], e->G0[nset], tt, e->d_args, q + 1));
     } else {
-      KL(KID_G2P, k_g2p<<<nb, 128, 0, e->qs>>>(k, frame(q), frame(q + 1), e->npart, e->G0[set]));
+      KL(KID_G2P, k_g2p<<<nb, pb, 0, e->qs>>>(k, frame(q), frame(q + 1), e->npart, e->G0[set]));
     }
   }
   LAUNCH_CHECK();
@@ -726,7 +742,8 @@ static int seq_substep_grad(dsk_engine* e, StepSlot& s, int q, int j) {
   SimConst& k = e->k;
   int set = (q + 1) & 1, prev = set ^ 1;
   TileTrack tt{e->tile_epoch[set], e->tile_list[set], e->tile_count + ((q + 1) & 3)};
-  int nb = cdiv(k.stride, 128);
+  const int pb = e->big ? e->big_block : 128;   // threads per CTA of the particle kernels
+  int nb = cdiv(k.stride, pb);
   float* fin = s.frames + (size_t)j * e->frame_floats;
   float* fnext = s.frames + (size_t)(j + 1) * e->frame_floats;
   float* ain = e->adjw[e->bwd_cur];
@@ -742,7 +759,7 @@ static int seq_substep_grad(dsk_engine* e, StepSlot& s, int q, int j) {
     run_if = s.tape.overflow;
   }
   if (!(e->seq_use_tape && e->seq_tape_trusted)) {
-    KL(KID_P2G_RECOMPUTE, k_p2g<false, 3><<<nb, 128, 0, e->qs>>>(k, fin, nullptr, s.mat, e->npart, e->G0[set], tt, e->d_args, q, run_if));
+    KL(KID_P2G_RECOMPUTE, k_p2g<false, 3><<<nb, pb, 0, e->qs>>>(k, fin, nullptr, s.mat, e->npart, e->G0[set], tt, e->d_args, q, run_if));
     KL(KID_GRID_RECOMPUTE, GRID_FWD_LAUNCH(e, e->qs,
                                k, e->d_tools, s.poses, j, e->G0[set], e->Gv[set], tt.list, tt.count,
                                clr ? e->tile_list[prev] : nullptr, e->tile_count + (q & 3), clr ? e->G0[prev] : nullptr,
@@ -750,13 +767,13 @@ static int seq_substep_grad(dsk_engine* e, StepSlot& s, int q, int j) {
                                GridTape{nullptr, nullptr, nullptr, nullptr, 0}, run_if));
   }
   if (e->big)
-    KL(KID_G2P_ADJ, k_g2p_adj<3><<<nb, 128, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
+    KL(KID_G2P_ADJ, k_g2p_adj<3><<<nb, pb, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
   else
     KL(KID_G2P_ADJ, k_g2p_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
   KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, e->qs, (GridAdjScratch{nullptr, nullptr, 0}), k, e->d_tools, s.poses, j, e->G0[set], e->Ga[set],
                                                                       tt.list, tt.count, e->pose_adj));
   if (e->big)
-    KL(KID_P2G_ADJ, k_p2g_adj<<<nb, 128, 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]));
+    KL(KID_P2G_ADJ, k_p2g_adj<3><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]));
   else
     KL(KID_P2G_ADJ, k_p2g_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]));
   LAUNCH_CHECK();
@@ -789,7 +806,8 @@ static int enqueue_backward_pipelined(dsk_engine* e, StepSlot& s) {
   if (seq_begin_backward(e, s)) return -1;
   CK(cudaEventRecord(e->ev_fork, mainq));
   CK(cudaStreamWaitEvent(side, e->ev_fork, 0));
-  int nb = cdiv(k.stride, 128);
+  const int pb = e->big ? e->big_block : 128;   // threads per CTA of the particle kernels
+  int nb = cdiv(k.stride, pb);
   for (int q = 0; q < e->S; q++) {
     int j = e->S - 1 - q, set = (q + 1) & 1;
     TileTrack tt{e->tile_epoch[set], e->tile_list[set], e->tile_count + ((q + 1) & 3)};
@@ -813,7 +831,11 @@ static int enqueue_backward_pipelined(dsk_engine* e, StepSlot& s) {
     float* ain = e->adjw[e->bwd_cur];
     float* aout = e->adjw[e->bwd_cur ^ 1];
     if (e->big)
-      KL(KID_G2P_ADJ, k_g2p_adj<3><<<nb, 128, 0, mainq>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
+      switch (e->minb_g2p_adj) {
+        case 5: KL(KID_G2P_ADJ, k_g2p_adj<5><<<nb, pb, 0, mainq>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set])); break;
+        case 4: KL(KID_G2P_ADJ, k_g2p_adj<4><<<nb, pb, 0, mainq>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set])); break;
+        default: KL(KID_G2P_ADJ, k_g2p_adj<3><<<nb, pb, 0, mainq>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set])); break;
+      }
     else
       KL(KID_G2P_ADJ, k_g2p_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, mainq>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
     // the pose adjoints of the contacts leave the critical path: parked here, reduced on the side branch two
@@ -823,7 +845,11 @@ static int enqueue_backward_pipelined(dsk_engine* e, StepSlot& s) {
     KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, mainq, sc, k, e->d_tools, s.poses, j, e->G0[set], e->Ga[set],
                                                                           tt.list, tt.count, e->pose_adj));
     if (e->big)
-      KL(KID_P2G_ADJ, k_p2g_adj<<<nb, 128, 0, mainq>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]));
+      switch (e->minb_p2g_adj) {
+        case 5: KL(KID_P2G_ADJ, k_p2g_adj<5><<<nb, pb, 0, mainq>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set])); break;
+        case 4: KL(KID_P2G_ADJ, k_p2g_adj<4><<<nb, pb, 0, mainq>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set])); break;
+        default: KL(KID_P2G_ADJ, k_p2g_adj<3><<<nb, pb, 0, mainq>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set])); break;
+      }
     else
       KL(KID_P2G_ADJ, k_p2g_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, mainq>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]));
     CK(cudaEventRecord(e->ev_main[q], mainq));

@@ -640,7 +640,8 @@ DSK_DEV void p2g_adj_finish(const SimConst& k, int gid, const Stencil& s, const 
 
 // p2g.grad + svd_grad + compute_F_tmp.grad fused: gathers adjoints of (grid_v_in, grid_m), reads F.grad[j+1],
 // writes x.grad (adding the g2p part already stored), v.grad, C.grad, F.grad of frame j.
-__global__ void __launch_bounds__(128, 3)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
     k_p2g_adj(SimConst k, const float* __restrict__ fin, const float* __restrict__ adj_in, float* __restrict__ adj_out,
               const float* __restrict__ mat, const int* __restrict__ npart, const float4* __restrict__ Ga) {
   DSK_TL(k);

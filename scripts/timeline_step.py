@@ -50,16 +50,20 @@ for _ in range(3):
     iteration()
 res = iteration(probe=H - 2)
 full = '--full' in sys.argv
+brief = '--brief' in sys.argv
 for name in ('fwd', 'bwd'):
     recs = sorted(res[name], key=lambda r: r[1])
     if not recs:
         continue
     t_begin = min(r[1] for r in recs); t_end = max(r[2] for r in recs)
-    print(f'== {wl} B={B} {name}: {len(recs)} launches, span {(t_end - t_begin) / 1e3:.1f} us')
     tot = {}
     for k, t0, t1 in recs:
         d = tot.setdefault(k, [0, 0.0]); d[0] += 1; d[1] += (t1 - t0) / 1e3
     busy = sum(v[1] for v in tot.values())
+    if brief:
+        print(f'{wl} B={B} {name} span={(t_end - t_begin) / 1e3:.1f} ' + ' '.join(f'{k}={us / n:.2f}' for k, (n, us) in sorted(tot.items(), key=lambda kv: -kv[1][1])[:6]))
+        continue
+    print(f'== {wl} B={B} {name}: {len(recs)} launches, span {(t_end - t_begin) / 1e3:.1f} us')
     for k, (n, us) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
         print(f'   {k:20s} n={n:3d}  total {us:8.1f} us  avg {us / n:6.2f} us  ({100 * us / (t_end - t_begin) * 1e3:5.1f}% of span)')
     print(f'   sum of kernel durations {busy:.1f} us (overlap or gaps: span - sum = {(t_end - t_begin) / 1e3 - busy:.1f} us)')
