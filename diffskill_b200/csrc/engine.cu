@@ -42,6 +42,7 @@ struct StepSlot {
   int* perm;         // sorted slot -> particle id, [stride]
   float* poses;      // [B][S+1][K][8]
   int* cidx;         // [B][S+1][npairs]
+  float* svd = nullptr;  // [S][SVD_COMPS][stride] U, sigma, V of every substep's F_tmp (null: adjoint recomputes the SVD)
   GridTape tape = {nullptr, nullptr, nullptr, nullptr, 0};
   bool tape_written = false;  // the slot's tape belongs to src_step
   int src_step = -1; // checkpoint the frames were simulated from (-1: invalid)
@@ -209,6 +210,7 @@ static int dalloc(dsk_engine* e, T** p, size_t count, bool zero = true) {
   } while (0)
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static float* svd_at(dsk_engine* e, StepSlot& s, int j);
 static void drop_graphs(dsk_engine* e);
 
 static void fill_tool(ToolParams& T, const dsk_tool_desc& d) {
@@ -360,6 +362,7 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
       DA(s.perm, k.stride);
       DA(s.poses, (size_t)(e->S + 1) * e->tool_floats);
       DA(s.cidx, (size_t)e->B * (e->S + 1) * std::max(1, k.npairs));
+      if (!getenv("DSK_NO_SVD_TAPE")) DA(s.svd, (size_t)e->S * SVD_COMPS * k.stride);
       if (e->tape_cap > 0) {
         s.tape.cap = e->tape_cap;
         DA(s.tape.base, e->S + 1);
@@ -537,6 +540,9 @@ static int stage_in(dsk_engine* e, const float* src, size_t n, int on_device, si
 }
 
 static int grid_ctas(dsk_engine* e) { return e->big ? 148 * 8 : 148 * 2; }
+static float* svd_at(dsk_engine* e, StepSlot& s, int j) {
+  return s.svd ? s.svd + (size_t)j * SVD_COMPS * e->k.stride : nullptr;
+}
 static dim3 grid_block(dsk_engine* e) { return dim3(GRID_NODES, std::min(e->n_frames, MAX_FRAMES)); }
 // batched engines use the throughput layout of the grid kernels (k_grid_flat / k_grid_adj_flat), single scenes the
 // latency layout (node x frame)
@@ -639,11 +645,11 @@ static int seq_substep(dsk_engine* e, StepSlot& s, int q, int j, bool write_stat
   float* fout = s.frames + (size_t)(j + 1) * e->frame_floats;
   if (write_state)
     if (e->big)
-      KL(KID_P2G, k_p2g<true, 3><<<nb, pb, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q, nullptr));
+      KL(KID_P2G, k_p2g<true, 3><<<nb, pb, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q, nullptr, svd_at(e, s, j)));
     else
-      KL(KID_P2G, k_p2g<true, 1><<<nb, pb, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q, nullptr));
+      KL(KID_P2G, k_p2g<true, 1><<<nb, pb, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q, nullptr, svd_at(e, s, j)));
   else
-    KL(KID_P2G_RECOMPUTE, k_p2g<false, 3><<<nb, pb, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q, nullptr));
+    KL(KID_P2G_RECOMPUTE, k_p2g<false, 3><<<nb, pb, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q, nullptr, nullptr));
   bool clr = q > 0;
   if (e->kin_join) {
     CK(cudaStreamWaitEvent(e->qs, e->ev_join, 0));
@@ -682,9 +688,9 @@ static int seq_forward_fused(dsk_engine* e, StepSlot& s) {
   {
     TileTrack tt{e->tile_epoch[1], e->tile_list[1], e->tile_count + 1};
     if (e->big)
-      KL(KID_P2G, k_p2g<true, 3><<<nb, pb, 0, e->qs>>>(k, frame(0), frame(1), s.mat, e->npart, e->G0[1], tt, e->d_args, 0, nullptr));
+      KL(KID_P2G, k_p2g<true, 3><<<nb, pb, 0, e->qs>>>(k, frame(0), frame(1), s.mat, e->npart, e->G0[1], tt, e->d_args, 0, nullptr, svd_at(e, s, 0)));
     else
-      KL(KID_P2G, k_p2g<true, 1><<<nb, pb, 0, e->qs>>>(k, frame(0), frame(1), s.mat, e->npart, e->G0[1], tt, e->d_args, 0, nullptr));
+      KL(KID_P2G, k_p2g<true, 1><<<nb, pb, 0, e->qs>>>(k, frame(0), frame(1), s.mat, e->npart, e->G0[1], tt, e->d_args, 0, nullptr, svd_at(e, s, 0)));
   }
   for (int q = 0; q < e->S; q++) {
     if (seq_grid_fwd(e, s, q)) return -1;
@@ -694,15 +700,15 @@ static int seq_forward_fused(dsk_engine* e, StepSlot& s) {
       if (e->big)
         switch (e->minb_g2p2g) {
           case 5: KL(KID_G2P2G, k_g2p2g<5><<<nb, pb, 0, e->qs>>>(k, frame(q), frame(q + 1), frame(q + 2), s.mat, e->npart, e->G0[set],
-                                                       e->G0[nset], tt, e->d_args, q + 1)); break;
+                                                       e->G0[nset], tt, e->d_args, q + 1, svd_at(e, s, q + 1))); break;
           case 4: KL(KID_G2P2G, k_g2p2g<4><<<nb, pb, 0, e->qs>>>(k, frame(q), frame(q + 1), frame(q + 2), s.mat, e->npart, e->G0[set],
-                                                       e->G0[nset], tt, e->d_args, q + 1)); break;
+                                                       e->G0[nset], tt, e->d_args, q + 1, svd_at(e, s, q + 1))); break;
           default: KL(KID_G2P2G, k_g2p2g<3><<<nb, pb, 0, e->qs>>>(k, frame(q), frame(q + 1), frame(q + 2), s.mat, e->npart, e->G0[set],
-                                                       e->G0[nset], tt, e->d_args, q + 1)); break;
+                                                       e->G0[nset], tt, e->d_args, q + 1, svd_at(e, s, q + 1))); break;
         }
       else
         KL(KID_G2P2G, k_g2p2g_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, e->qs>>>(
-                          k, frame(q), frame(q + 1), frame(q + 2), s.mat, e->npart, e->G0[set], e->G0[nset], tt, e->d_args, q + 1));
+                          k, frame(q), frame(q + 1), frame(q + 2), s.mat, e->npart, e->G0[set], e->G0[nset], tt, e->d_args, q + 1, svd_at(e, s, q + 1)));
     } else {
       KL(KID_G2P, k_g2p<<<nb, pb, 0, e->qs>>>(k, frame(q), frame(q + 1), e->npart, e->G0[set]));
     }
@@ -759,7 +765,7 @@ static int seq_substep_grad(dsk_engine* e, StepSlot& s, int q, int j) {
     run_if = s.tape.overflow;
   }
   if (!(e->seq_use_tape && e->seq_tape_trusted)) {
-    KL(KID_P2G_RECOMPUTE, k_p2g<false, 3><<<nb, pb, 0, e->qs>>>(k, fin, nullptr, s.mat, e->npart, e->G0[set], tt, e->d_args, q, run_if));
+    KL(KID_P2G_RECOMPUTE, k_p2g<false, 3><<<nb, pb, 0, e->qs>>>(k, fin, nullptr, s.mat, e->npart, e->G0[set], tt, e->d_args, q, run_if, nullptr));
     KL(KID_GRID_RECOMPUTE, GRID_FWD_LAUNCH(e, e->qs,
                                k, e->d_tools, s.poses, j, e->G0[set], e->Gv[set], tt.list, tt.count,
                                clr ? e->tile_list[prev] : nullptr, e->tile_count + (q & 3), clr ? e->G0[prev] : nullptr,
@@ -773,9 +779,9 @@ static int seq_substep_grad(dsk_engine* e, StepSlot& s, int q, int j) {
   KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, e->qs, (GridAdjScratch{nullptr, nullptr, 0}), k, e->d_tools, s.poses, j, e->G0[set], e->Ga[set],
                                                                       tt.list, tt.count, e->pose_adj));
   if (e->big)
-    KL(KID_P2G_ADJ, k_p2g_adj<3><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]));
+    KL(KID_P2G_ADJ, k_p2g_adj<3><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set], svd_at(e, s, j)));
   else
-    KL(KID_P2G_ADJ, k_p2g_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]));
+    KL(KID_P2G_ADJ, k_p2g_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set], svd_at(e, s, j)));
   LAUNCH_CHECK();
   e->bwd_cur ^= 1;
   return 0;
@@ -846,12 +852,12 @@ static int enqueue_backward_pipelined(dsk_engine* e, StepSlot& s) {
                                                                           tt.list, tt.count, e->pose_adj));
     if (e->big)
       switch (e->minb_p2g_adj) {
-        case 5: KL(KID_P2G_ADJ, k_p2g_adj<5><<<nb, pb, 0, mainq>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set])); break;
-        case 4: KL(KID_P2G_ADJ, k_p2g_adj<4><<<nb, pb, 0, mainq>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set])); break;
-        default: KL(KID_P2G_ADJ, k_p2g_adj<3><<<nb, pb, 0, mainq>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set])); break;
+        case 5: KL(KID_P2G_ADJ, k_p2g_adj<5><<<nb, pb, 0, mainq>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set], svd_at(e, s, j))); break;
+        case 4: KL(KID_P2G_ADJ, k_p2g_adj<4><<<nb, pb, 0, mainq>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set], svd_at(e, s, j))); break;
+        default: KL(KID_P2G_ADJ, k_p2g_adj<3><<<nb, pb, 0, mainq>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set], svd_at(e, s, j))); break;
       }
     else
-      KL(KID_P2G_ADJ, k_p2g_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, mainq>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set]));
+      KL(KID_P2G_ADJ, k_p2g_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, mainq>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set], svd_at(e, s, j)));
     CK(cudaEventRecord(e->ev_main[q], mainq));
     e->bwd_cur ^= 1;
   }

@@ -643,7 +643,8 @@ DSK_DEV void p2g_adj_finish(const SimConst& k, int gid, const Stencil& s, const 
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB)
     k_p2g_adj(SimConst k, const float* __restrict__ fin, const float* __restrict__ adj_in, float* __restrict__ adj_out,
-              const float* __restrict__ mat, const int* __restrict__ npart, const float4* __restrict__ Ga) {
+              const float* __restrict__ mat, const int* __restrict__ npart, const float4* __restrict__ Ga,
+              const float* __restrict__ svd_in) {
   DSK_TL(k);
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= k.stride) return;
@@ -655,7 +656,7 @@ __global__ void __launch_bounds__(128, MINB)
   M3 F = load_m3(fin, CF, k.stride, gid);
   float mu = mat[gid], lam = mat[k.stride + gid], ys = mat[2 * k.stride + gid];
   P2GParticle o;
-  p2g_particle(k, C, F, mu, lam, ys, o);
+  p2g_particle_adj(k, svd_in, gid, C, F, mu, lam, ys, o);
   Stencil s;
   make_stencil(k, x.x, x.y, x.z, s);
   const float4* Gae = Ga + (size_t)env * k.nnode;
@@ -693,7 +694,8 @@ __global__ void __launch_bounds__(128, MINB)
 // plane-split p2g.grad for small engines: three threads per particle gather one x-plane of the stencil each
 __global__ void __launch_bounds__(PL_PARTICLES * 3)
     k_p2g_adj_pl(SimConst k, const float* __restrict__ fin, const float* __restrict__ adj_in, float* __restrict__ adj_out,
-                 const float* __restrict__ mat, const int* __restrict__ npart, const float4* __restrict__ Ga) {
+                 const float* __restrict__ mat, const int* __restrict__ npart, const float4* __restrict__ Ga,
+                 const float* __restrict__ svd_in) {
   DSK_TL(k);
   __shared__ float ex[3][16][PL_PARTICLES];
   const int tx = threadIdx.x, pl = threadIdx.y;
@@ -707,7 +709,7 @@ __global__ void __launch_bounds__(PL_PARTICLES * 3)
   M3 F = load_m3(fin, CF, k.stride, gi);
   float mu = mat[gi], lam = mat[k.stride + gi], ys = mat[2 * k.stride + gi];
   P2GParticle o;
-  p2g_particle(k, C, F, mu, lam, ys, o);
+  p2g_particle_adj(k, svd_in, gi, C, F, mu, lam, ys, o);
   Stencil s;
   make_stencil(k, x.x, x.y, x.z, s);
   const float4* Gae = Ga + (size_t)env * k.nnode;

@@ -48,12 +48,15 @@ struct P2GParticle {
   ReturnMap rm;
   float J;
 };
-DSK_DEV void p2g_particle(const SimConst& k, const M3& C, const M3& F, float mu, float lam, float ys, P2GParticle& o) {
+// HAVE_SVD: o.U, o.sig, o.V were read from the SVD tape of the forward pass (the adjoint's fused recompute,
+// mpm_simulator.py:330-333, then skips the Jacobi sweeps -- a quarter of its instructions)
+template <bool HAVE_SVD>
+DSK_DEV void p2g_particle_impl(const SimConst& k, const M3& C, const M3& F, float mu, float lam, float ys, P2GParticle& o) {
   M3 Mx;
 #pragma unroll
   for (int i = 0; i < 9; i++) Mx.m[i] = ((i % 4 == 0) ? 1.f : 0.f) + k.dt * C.m[i];
   o.Ftmp = mm(Mx, F);  // compute_F_tmp
-  svd3(o.Ftmp, o.U, o.sig, o.V);
+  if (!HAVE_SVD) svd3(o.Ftmp, o.U, o.sig, o.V);
   o.newF = von_mises(o.Ftmp, o.U, o.sig, o.V, ys, mu, o.rm);
   o.J = det3(o.newF);
   M3 R = mmT(o.U, o.V);
@@ -68,6 +71,28 @@ DSK_DEV void p2g_particle(const SimConst& k, const M3& C, const M3& F, float mu,
 #pragma unroll
   for (int i = 0; i < 9; i++) o.affine.m[i] = k.c_stress * st.m[i] + k.p_mass * C.m[i];
 }
+DSK_DEV void p2g_particle(const SimConst& k, const M3& C, const M3& F, float mu, float lam, float ys, P2GParticle& o) {
+  p2g_particle_impl<false>(k, C, F, mu, lam, ys, o);
+}
+// SVD tape: [S][SVD_COMPS][stride] per step slot, U (9), sigma (3), V (9) of substep j's F_tmp
+#define SVD_COMPS 21
+DSK_DEV void store_svd(float* __restrict__ t, int stride, int gid, const P2GParticle& o) {
+  store_m3(t, 0, stride, gid, o.U);
+  store_v3(t, 9, stride, gid, o.sig);
+  store_m3(t, 12, stride, gid, o.V);
+}
+// p2g_particle for the adjoint: from the tape when there is one
+DSK_DEV void p2g_particle_adj(const SimConst& k, const float* __restrict__ svd, int gid, const M3& C, const M3& F, float mu,
+                              float lam, float ys, P2GParticle& o) {
+  if (svd) {
+    o.U = load_m3(svd, 0, k.stride, gid);
+    o.sig = load_v3(svd, 9, k.stride, gid);
+    o.V = load_m3(svd, 12, k.stride, gid);
+    p2g_particle_impl<true>(k, C, F, mu, lam, ys, o);
+  } else {
+    p2g_particle_impl<false>(k, C, F, mu, lam, ys, o);
+  }
+}
 
 // MINB = min CTAs/SM the register allocation must allow: 1 for small (latency-bound) problems -- all registers, no
 // spills; 3 for large batches where occupancy hides the scatter latency
@@ -75,7 +100,7 @@ template <bool WRITE_F, int MINB>
 __global__ void __launch_bounds__(128, MINB)
     k_p2g(SimConst k, const float* __restrict__ fin, float* __restrict__ fout, const float* __restrict__ mat,
           const int* __restrict__ npart, float4* __restrict__ G, TileTrack tt, const StepArgs* __restrict__ args,
-          int q, const int* __restrict__ run_if) {
+          int q, const int* __restrict__ run_if, float* __restrict__ svd_out) {
   DSK_TL(k);
   if (run_if && *run_if == 0) return;   // adjoint recompute is skipped when the grid tape of the step is complete
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -89,7 +114,10 @@ __global__ void __launch_bounds__(128, MINB)
   float mu = mat[g], lam = mat[k.stride + g], ys = mat[2 * k.stride + g];
   P2GParticle o;
   p2g_particle(k, C, F, mu, lam, ys, o);
-  if (WRITE_F && active) store_m3(fout, CF, k.stride, gid, o.newF);
+  if (WRITE_F && active) {
+    store_m3(fout, CF, k.stride, gid, o.newF);
+    if (svd_out) store_svd(svd_out, k.stride, gid, o);
+  }
   Stencil s;
   make_stencil(k, x.x, x.y, x.z, s);
   float4* Ge = G + (size_t)env * k.nnode;
@@ -589,7 +617,8 @@ template <int MINB>
 __global__ void __launch_bounds__(128, MINB)
     k_g2p2g(SimConst k, const float* __restrict__ fprev, float* __restrict__ fcur, float* __restrict__ fnext,
             const float* __restrict__ mat, const int* __restrict__ npart, const float4* __restrict__ Gprev,
-            float4* __restrict__ Gnext, TileTrack tt, const StepArgs* __restrict__ args, int qnext) {
+            float4* __restrict__ Gnext, TileTrack tt, const StepArgs* __restrict__ args, int qnext,
+            float* __restrict__ svd_out) {
   DSK_TL(k);
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   int env = min(gid / k.Npad, k.B - 1), p = gid - env * k.Npad;
@@ -610,7 +639,10 @@ __global__ void __launch_bounds__(128, MINB)
   float mu = mat[g], lam = mat[k.stride + g], ys = mat[2 * k.stride + g];
   P2GParticle o;
   p2g_particle(k, C, F, mu, lam, ys, o);
-  if (active) store_m3(fnext, CF, k.stride, gid, o.newF);
+  if (active) {
+    store_m3(fnext, CF, k.stride, gid, o.newF);
+    if (svd_out) store_svd(svd_out, k.stride, gid, o);
+  }
   make_stencil(k, nx.x, nx.y, nx.z, s);
   float3 fxv = f3(s.fx, s.fy, s.fz);
   float3 a0 = k.p_mass * nv - k.dx * mv(o.affine, fxv);
@@ -632,7 +664,8 @@ __global__ void __launch_bounds__(128, MINB)
 __global__ void __launch_bounds__(PL_PARTICLES * 3)
     k_g2p2g_pl(SimConst k, const float* __restrict__ fprev, float* __restrict__ fcur, float* __restrict__ fnext,
                const float* __restrict__ mat, const int* __restrict__ npart, const float4* __restrict__ Gprev,
-               float4* __restrict__ Gnext, TileTrack tt, const StepArgs* __restrict__ args, int qnext) {
+               float4* __restrict__ Gnext, TileTrack tt, const StepArgs* __restrict__ args, int qnext,
+               float* __restrict__ svd_out) {
   DSK_TL(k);
   __shared__ float ex[3][9][PL_PARTICLES];
   const int tx = threadIdx.x, pl = threadIdx.y;
@@ -687,7 +720,10 @@ __global__ void __launch_bounds__(PL_PARTICLES * 3)
   }
   P2GParticle o;
   p2g_particle(k, C, F, mu, lam, ys, o);
-  if (active && pl == 0) store_m3(fnext, CF, k.stride, gid, o.newF);
+  if (active && pl == 0) {
+    store_m3(fnext, CF, k.stride, gid, o.newF);
+    if (svd_out) store_svd(svd_out, k.stride, gid, o);
+  }
   make_stencil(k, nx.x, nx.y, nx.z, s);
   const float wxp = pick3(s.wx, pl);
   const int oxp = pick3(s.ox, pl);
