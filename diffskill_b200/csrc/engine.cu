@@ -91,6 +91,7 @@ struct dsk_engine {
   int epoch = 0;
   // tools
   ToolParams* d_tools = nullptr;
+  GridTools grid_tools;   // by-value copy for the grid kernels (refreshed by sync_grid_tools)
   std::vector<ToolParams> h_tools;
   float *tool_ckpt = nullptr, *tool_adj_ckpt = nullptr;  // [H+1][B][K][8]
   float* pose_adj = nullptr;                             // [B][S+1][K][8]
@@ -246,6 +247,24 @@ static void fill_tool(ToolParams& T, const dsk_tool_desc& d) {
   else
     T.bound_r = (float)std::sqrt(d.size[0] * d.size[0] + d.size[1] * d.size[1] + d.size[2] * d.size[2]);
   T.bound_r *= 1.001f;
+}
+// host mirror of build_frame_table: one contact frame per tool, two (the jaws) per gripper
+static void sync_grid_tools(dsk_engine* e) {
+  GridTools& g = e->grid_tools;
+  memset(&g, 0, sizeof g);
+  int n = 0;
+  for (int t = 0; t < e->K; t++) {
+    g.T[t] = e->h_tools[t];
+    if (e->h_tools[t].type == DSK_TOOL_GRIPPER) {
+      if (n + 2 > MAX_FRAMES) break;
+      g.ft.tool[n] = t; g.ft.flag[n++] = -1.f;
+      g.ft.tool[n] = t; g.ft.flag[n++] = 1.f;
+    } else {
+      if (n + 1 > MAX_FRAMES) break;
+      g.ft.tool[n] = t; g.ft.flag[n++] = 0.f;
+    }
+  }
+  g.ft.n = n;
 }
 
 extern "C" {
@@ -417,6 +436,7 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
     e->stage_floats = std::max<size_t>((size_t)k.stride * 24, (size_t)e->B * k.nnode * 4);
     DA(e->stage, e->stage_floats);
     CK(cudaMemcpy(e->d_tools, e->h_tools.data(), sizeof(ToolParams) * std::max(1, e->K), cudaMemcpyHostToDevice));
+    sync_grid_tools(e);
     // material fill, mpm_simulator.py:85-87
     std::vector<float> m((size_t)3 * k.stride);
     for (int i = 0; i < k.stride; i++) {
@@ -656,7 +676,7 @@ static int seq_substep(dsk_engine* e, StepSlot& s, int q, int j, bool write_stat
     e->kin_join = false;
   }
   KL(KID_GRID, GRID_FWD_LAUNCH(e, e->qs,
-                   k, e->d_tools, s.poses, j, e->G0[set], e->G0[set], tt.list, tt.count,
+                   k, e->grid_tools, s.poses, j, e->G0[set], e->G0[set], tt.list, tt.count,
                    clr ? e->tile_list[prev] : nullptr, e->tile_count + (q & 3), clr ? e->G0[prev] : nullptr, nullptr,
                    nullptr, e->tile_count + ((q + 3) & 3), write_state ? s.tape : GridTape{nullptr, nullptr, nullptr, nullptr, 0}, nullptr));
   if (write_state) KL(KID_G2P, k_g2p<<<nb, pb, 0, e->qs>>>(k, fin, fout, e->npart, e->G0[set]));
@@ -673,7 +693,7 @@ static int seq_grid_fwd(dsk_engine* e, StepSlot& s, int q) {
     e->kin_join = false;
   }
   KL(KID_GRID, GRID_FWD_LAUNCH(e, e->qs,
-                   k, e->d_tools, s.poses, q, e->G0[set], e->G0[set], e->tile_list[set], e->tile_count + ((q + 1) & 3),
+                   k, e->grid_tools, s.poses, q, e->G0[set], e->G0[set], e->tile_list[set], e->tile_count + ((q + 1) & 3),
                    clr ? e->tile_list[prev] : nullptr, e->tile_count + (q & 3), clr ? e->G0[prev] : nullptr, nullptr,
                    nullptr, e->tile_count + ((q + 3) & 3), s.tape, nullptr));
   LAUNCH_CHECK();
@@ -767,7 +787,7 @@ static int seq_substep_grad(dsk_engine* e, StepSlot& s, int q, int j) {
   if (!(e->seq_use_tape && e->seq_tape_trusted)) {
     KL(KID_P2G_RECOMPUTE, k_p2g<false, 3><<<nb, pb, 0, e->qs>>>(k, fin, nullptr, s.mat, e->npart, e->G0[set], tt, e->d_args, q, run_if, nullptr));
     KL(KID_GRID_RECOMPUTE, GRID_FWD_LAUNCH(e, e->qs,
-                               k, e->d_tools, s.poses, j, e->G0[set], e->Gv[set], tt.list, tt.count,
+                               k, e->grid_tools, s.poses, j, e->G0[set], e->Gv[set], tt.list, tt.count,
                                clr ? e->tile_list[prev] : nullptr, e->tile_count + (q & 3), clr ? e->G0[prev] : nullptr,
                                clr ? e->Gv[prev] : nullptr, clr ? e->Ga[prev] : nullptr, e->tile_count + ((q + 3) & 3),
                                GridTape{nullptr, nullptr, nullptr, nullptr, 0}, run_if));
@@ -776,7 +796,7 @@ static int seq_substep_grad(dsk_engine* e, StepSlot& s, int q, int j) {
     KL(KID_G2P_ADJ, k_g2p_adj<3><<<nb, pb, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
   else
     KL(KID_G2P_ADJ, k_g2p_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
-  KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, e->qs, (GridAdjScratch{nullptr, nullptr, 0}), k, e->d_tools, s.poses, j, e->G0[set], e->Ga[set],
+  KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, e->qs, (GridAdjScratch{nullptr, nullptr, 0}), k, e->grid_tools, s.poses, j, e->G0[set], e->Ga[set],
                                                                       tt.list, tt.count, e->pose_adj));
   if (e->big)
     KL(KID_P2G_ADJ, k_p2g_adj<3><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set], svd_at(e, s, j)));
@@ -822,7 +842,7 @@ static int enqueue_backward_pipelined(dsk_engine* e, StepSlot& s) {
       if (!e->flat_grid && e->gadj_scratch[0]) {   // position q-2 used this set and parked its contact adjoints
         GridAdjScratch sc{e->gadj_scratch[q & 1], e->gadj_flags[q & 1], e->gadj_cap};
         KL(KID_GRID_ADJ_TOOLS, k_grid_adj_tools<<<grid_ctas(e), grid_block(e), 0, side>>>(
-                                   k, e->d_tools, s.poses, e->S - 1 - (q - 2), e->G0[set], e->tile_list[set],
+                                   k, e->grid_tools, s.poses, e->S - 1 - (q - 2), e->G0[set], e->tile_list[set],
                                    e->tile_count + ((q - 1) & 3), e->pose_adj, sc));
       }
       KL(KID_GRID_RECOMPUTE, k_clear_set<<<grid_ctas(e), GRID_CTA, 0, side>>>(k, e->tile_list[set], e->tile_count + ((q - 1) & 3),
@@ -848,7 +868,7 @@ static int enqueue_backward_pipelined(dsk_engine* e, StepSlot& s) {
     // positions later (before this grid set is cleared); the last two positions do them inline
     bool park = !e->flat_grid && e->gadj_scratch[0] && q + 2 < e->S;
     GridAdjScratch sc{park ? e->gadj_scratch[q & 1] : nullptr, park ? e->gadj_flags[q & 1] : nullptr, park ? e->gadj_cap : 0};
-    KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, mainq, sc, k, e->d_tools, s.poses, j, e->G0[set], e->Ga[set],
+    KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, mainq, sc, k, e->grid_tools, s.poses, j, e->G0[set], e->Ga[set],
                                                                           tt.list, tt.count, e->pose_adj));
     if (e->big)
       switch (e->minb_p2g_adj) {
@@ -1069,6 +1089,8 @@ int dsk_set_tool_param(dsk_engine* e, int tool, int which, double value) {
   }
   CK(cudaStreamSynchronize(e->stream));
   CK(cudaMemcpy(e->d_tools + tool, &T, sizeof T, cudaMemcpyHostToDevice));
+  sync_grid_tools(e);
+  drop_graphs(e);   // the grid kernels take the tool parameters by value
   for (auto& s : e->slot) s.src_step = -1;
   return 0;
 }

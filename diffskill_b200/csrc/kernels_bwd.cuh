@@ -270,22 +270,18 @@ struct GridAdjScratch {
 // Ga: in = adjoint of grid_v_out (xyz), out = adjoint of (grid_v_in, grid_m), in place.
 // pose_adj: [B][S+1][K][8] accumulators.
 __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
-    k_grid_adj(SimConst k, const ToolParams* __restrict__ tools, const float* __restrict__ poses, int j,
+    k_grid_adj(SimConst k, const __grid_constant__ GridTools tp, const float* __restrict__ poses, int j,
                const float4* __restrict__ G0, float4* __restrict__ Ga, const int* __restrict__ list,
                const int* __restrict__ count, float* __restrict__ pose_adj, GridAdjScratch sc) {
   DSK_TL(k);
-  __shared__ ToolParams sT[DSK_MAX_TOOLS];
-  __shared__ FrameTable ft;
+  const ToolParams* sT = tp.T;   // tool parameters and the frame table arrive as kernel parameters: no setup barrier
+  const FrameTable& ft = tp.ft;
   __shared__ TileFrames tf;
   __shared__ ContactGeom geo[MAX_FRAMES][GRID_NODES];
   __shared__ ContactGeomAdj gadj[MAX_FRAMES][GRID_NODES];
   __shared__ float red[MAX_FRAMES][2][14];
   __shared__ int any_contact[MAX_FRAMES];
-  const int l = threadIdx.x, y = threadIdx.y, tid = y * GRID_NODES + l, nthr = GRID_NODES * blockDim.y;
-  for (int i = tid; i < k.K * (int)(sizeof(ToolParams) / 4); i += nthr) ((int*)sT)[i] = ((const int*)tools)[i];
-  __syncthreads();
-  if (tid == 0) build_frame_table(k, sT, ft);
-  __syncthreads();
+  const int l = threadIdx.x, y = threadIdx.y;
   int n_active = *count;
   int gt_next = blockIdx.x < n_active ? list[blockIdx.x] : 0;
   for (int it = blockIdx.x; it < n_active; it += gridDim.x) {
@@ -379,19 +375,15 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
 // second half of the split k_grid_adj (side branch): pose adjoints from the parked (gD, gcv, gdist); the contact
 // geometry is recomputed, which is free off the critical path
 __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
-    k_grid_adj_tools(SimConst k, const ToolParams* __restrict__ tools, const float* __restrict__ poses, int j,
+    k_grid_adj_tools(SimConst k, const __grid_constant__ GridTools tp, const float* __restrict__ poses, int j,
                      const float4* __restrict__ G0, const int* __restrict__ list, const int* __restrict__ count,
                      float* __restrict__ pose_adj, GridAdjScratch sc) {
   DSK_TL(k);
-  __shared__ ToolParams sT[DSK_MAX_TOOLS];
-  __shared__ FrameTable ft;
+  const ToolParams* sT = tp.T;   // tool parameters and the frame table arrive as kernel parameters: no setup barrier
+  const FrameTable& ft = tp.ft;
   __shared__ TileFrames tf;
   __shared__ float red[MAX_FRAMES][2][14];
-  const int l = threadIdx.x, y = threadIdx.y, tid = y * GRID_NODES + l, nthr = GRID_NODES * blockDim.y;
-  for (int i = tid; i < k.K * (int)(sizeof(ToolParams) / 4); i += nthr) ((int*)sT)[i] = ((const int*)tools)[i];
-  __syncthreads();
-  if (tid == 0) build_frame_table(k, sT, ft);
-  __syncthreads();
+  const int l = threadIdx.x, y = threadIdx.y;
   int n_active = min(*count, sc.cap);
   for (int it = blockIdx.x; it < n_active; it += gridDim.x) {
     int anyf = 0;
@@ -430,18 +422,14 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
 // in local memory, walks the velocity chain forward and backward, and the pose adjoints of a frame are reduced over
 // the warp (half tile) before the atomics.
 __global__ void __launch_bounds__(FLAT_THREADS, 4)
-    k_grid_adj_flat(SimConst k, const ToolParams* __restrict__ tools, const float* __restrict__ poses, int j,
+    k_grid_adj_flat(SimConst k, const __grid_constant__ GridTools tp, const float* __restrict__ poses, int j,
                     const float4* __restrict__ G0, float4* __restrict__ Ga, const int* __restrict__ list,
                     const int* __restrict__ count, float* __restrict__ pose_adj) {
   DSK_TL(k);
-  __shared__ ToolParams sT[DSK_MAX_TOOLS];
-  __shared__ FrameTable ft;
+  const ToolParams* sT = tp.T;   // tool parameters and the frame table arrive as kernel parameters: no setup barrier
+  const FrameTable& ft = tp.ft;
   __shared__ WarpFrames wf[FLAT_THREADS / 32];
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < k.K * (int)(sizeof(ToolParams) / 4); i += FLAT_THREADS) ((int*)sT)[i] = ((const int*)tools)[i];
-  __syncthreads();
-  if (tid == 0) build_frame_table(k, sT, ft);
-  __syncthreads();
   int n_active = *count;
   const int l = tid & 63;
   for (int it = blockIdx.x * FLAT_TILES + (w >> 1); it < n_active; it += gridDim.x * FLAT_TILES) {

@@ -285,6 +285,11 @@ DSK_DEV void build_frame_table(const SimConst& k, const ToolParams* sT, FrameTab
   }
   ft.n = n;
 }
+// tool parameters + frame table, passed to the grid kernels by value (constant bank)
+struct GridTools {
+  ToolParams T[DSK_MAX_TOOLS];
+  FrameTable ft;
+};
 DSK_DEV Frame frame_of_pose(const Pose& P, float flag) { return flag == 0.f ? tool_frame(P) : jaw_frame(P, flag); }
 struct ContactGeom {   // per (node, frame), shared memory
   float influence;     // < 0: contact inactive
@@ -360,24 +365,20 @@ __global__ void __launch_bounds__(GRID_CTA)
 // grid_op over active tiles.  Gin holds (momentum, mass); Gout receives (velocity, mass) and may alias Gin.
 // blockDim = (64, n_frames).
 __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
-    k_grid(SimConst k, const ToolParams* __restrict__ tools, const float* __restrict__ poses, int j,
+    k_grid(SimConst k, const __grid_constant__ GridTools tp, const float* __restrict__ poses, int j,
            const float4* Gin, float4* Gout, const int* __restrict__ list, const int* __restrict__ count,
            // tiles of the previous substep to zero (clear_grid), may be null
            const int* __restrict__ clr_list, const int* __restrict__ clr_count, float4* clr0, float4* clr1,
            float4* clr2, int* zero_count, GridTape tape, const int* __restrict__ run_if) {
   DSK_TL(k);
   if (run_if && *run_if == 0) return;
-  __shared__ ToolParams sT[DSK_MAX_TOOLS];
-  __shared__ FrameTable ft;
+  const ToolParams* sT = tp.T;   // tool parameters and the frame table arrive as kernel parameters: no setup barrier
+  const FrameTable& ft = tp.ft;
   __shared__ TileFrames tf;
   __shared__ ContactGeom geo[MAX_FRAMES][GRID_NODES];
-  const int l = threadIdx.x, y = threadIdx.y, tid = y * GRID_NODES + l, nthr = GRID_NODES * blockDim.y;
-  for (int i = tid; i < k.K * (int)(sizeof(ToolParams) / 4); i += nthr) ((int*)sT)[i] = ((const int*)tools)[i];
-  __syncthreads();
-  if (tid == 0) build_frame_table(k, sT, ft);
+  const int l = threadIdx.x, y = threadIdx.y, tid = y * GRID_NODES + l;
   if (blockIdx.x == 0 && tid == 0 && zero_count) *zero_count = 0;
   if (clr_list && y == 0) clear_tiles(k, clr_list, *clr_count, clr0, clr1, clr2);
-  __syncthreads();
   int n_active = *count;
   // grid tape: (momentum, mass) and velocity of every active tile are kept so that substep_grad need not
   // recompute p2g + grid_op (mpm_simulator.py:330-333 does); tape.base[j] = first tape slot of substep j
@@ -471,22 +472,18 @@ DSK_DEV unsigned warp_prepare_frames(const SimConst& k, const ToolParams* sT, co
 }
 
 __global__ void __launch_bounds__(FLAT_THREADS, 4)
-    k_grid_flat(SimConst k, const ToolParams* __restrict__ tools, const float* __restrict__ poses, int j,
+    k_grid_flat(SimConst k, const __grid_constant__ GridTools tp, const float* __restrict__ poses, int j,
                 const float4* Gin, float4* Gout, const int* __restrict__ list, const int* __restrict__ count,
                 const int* __restrict__ clr_list, const int* __restrict__ clr_count, float4* clr0, float4* clr1,
                 float4* clr2, int* zero_count, GridTape tape, const int* __restrict__ run_if) {
   DSK_TL(k);
   if (run_if && *run_if == 0) return;
-  __shared__ ToolParams sT[DSK_MAX_TOOLS];
-  __shared__ FrameTable ft;
+  const ToolParams* sT = tp.T;   // tool parameters and the frame table arrive as kernel parameters: no setup barrier
+  const FrameTable& ft = tp.ft;
   __shared__ WarpFrames wf[FLAT_THREADS / 32];
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < k.K * (int)(sizeof(ToolParams) / 4); i += FLAT_THREADS) ((int*)sT)[i] = ((const int*)tools)[i];
-  __syncthreads();
-  if (tid == 0) build_frame_table(k, sT, ft);
   if (blockIdx.x == 0 && tid == 0 && zero_count) *zero_count = 0;
   if (clr_list) clear_tiles_flat(clr_list, *clr_count, clr0, clr1, clr2);
-  __syncthreads();
   int n_active = *count;
   int tb = 0;
   if (tape.base) {   // as in k_grid
