@@ -237,6 +237,7 @@ def main():
                          '0 = auto: H if the tape fits in 16 GB else 1)')
     ap.add_argument('--grid-tape-mib', type=int, default=8192,
                     help='device memory budget for taping active grid tiles (adjoint skips the p2g/grid_op recompute); 0 = off')
+    ap.add_argument('--envs', type=int, default=0, help='override the envs per GPU of the workload (experiments; the JSON says so)')
     ap.add_argument('--no-sort', action='store_true')
     ap.add_argument('--no-graphs', action='store_true')
     args = ap.parse_args()
@@ -261,6 +262,9 @@ def main():
 
     spec = workload_spec(args.workload)
     B = spec['envs_per_gpu'] or spec['total_envs'] // world
+    if args.envs > 0:
+        B = args.envs
+        spec['desc'] += f' [--envs {B} override]'
     H = spec['horizon']
     scene, cfg, xs, targets, actions = make_inputs(spec, rank, B)
     cap = max(len(x) for x in xs)

@@ -354,7 +354,8 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
   e->k.tl = nullptr;
   e->k.tl_slot = -1;
 #endif
-  e->big = (size_t)c->n_envs * c->particle_capacity >= 65536;
+  // measured crossover (GatherMove 8 vs 16 envs, LiftSpread 2 envs): ~24-32 k particles, i.e. ~1.5 warps per scheduler
+  e->big = (size_t)c->n_envs * c->particle_capacity >= 24576;
   if (const char* v = getenv("DSK_FORCE_BIG")) e->big = atoi(v) != 0;
   if (const char* v = getenv("DSK_BIG_MINB")) e->minb_g2p2g = e->minb_g2p_adj = e->minb_p2g_adj = atoi(v);
   if (const char* v = getenv("DSK_BIG_BLOCK")) e->big_block = atoi(v) == 64 ? 64 : 128;

@@ -192,7 +192,7 @@ def test_multi_step_action_gradient(name, slots, tape_mib):
 @pytest.mark.parametrize('name', ENVS)
 @pytest.mark.parametrize('slots,tape_mib', [(3, 256), (1, 0)])
 def test_multi_step_action_gradient_batched_layout(name, slots, tape_mib, monkeypatch):
-    """Same property with the kernel variants batched engines select (>= 65536 particle slots): throughput layout
+    """Same property with the kernel variants batched engines select (>= 24576 particle slots): throughput layout
     of the grid kernels and the high-occupancy particle kernels."""
     monkeypatch.setenv('DSK_FLAT_GRID', '1')
     monkeypatch.setenv('DSK_FORCE_BIG', '1')
