@@ -212,6 +212,7 @@ static int dalloc(dsk_engine* e, T** p, size_t count, bool zero = true) {
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static float* svd_at(dsk_engine* e, StepSlot& s, int j);
+static size_t kin_smem(dsk_engine* e);
 static void drop_graphs(dsk_engine* e);
 
 static void fill_tool(ToolParams& T, const dsk_tool_desc& d) {
@@ -409,6 +410,10 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
         DA(e->gadj_flags[s], (size_t)e->gadj_cap * MAX_FRAMES);
       }
     }
+    if (kin_smem(e) > 48 * 1024) {
+      if (kin_smem(e) > 200 * 1024) return fail("tool kinematics kernel needs %zu bytes of shared memory", kin_smem(e));
+      CK(cudaFuncSetAttribute(k_kinematics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kin_smem(e)));
+    }
     DA(e->tile_count, 4);
     DA(e->done, 1);
     DA(e->d_args, 1);
@@ -564,6 +569,9 @@ static int grid_ctas(dsk_engine* e) { return e->big ? 148 * 8 : 148 * 2; }
 static float* svd_at(dsk_engine* e, StepSlot& s, int j) {
   return s.svd ? s.svd + (size_t)j * SVD_COMPS * e->k.stride : nullptr;
 }
+static size_t kin_smem(dsk_engine* e) {   // pose chain + the collision samples of every pair
+  return (size_t)(e->S + 1) * e->K * 32 + (size_t)e->k.npairs * DSK_NUM_COLLISION_POINTS * 12;
+}
 static dim3 grid_block(dsk_engine* e) { return dim3(GRID_NODES, std::min(e->n_frames, MAX_FRAMES)); }
 // batched engines use the throughput layout of the grid kernels (k_grid_flat / k_grid_adj_flat), single scenes the
 // latency layout (node x frame)
@@ -628,11 +636,11 @@ static int seq_begin_forward(dsk_engine* e, StepSlot& s) {
     if (capturing) {
       CK(cudaEventRecord(e->ev_fork, e->qs));
       CK(cudaStreamWaitEvent(e->cap_side, e->ev_fork, 0));
-      KL(KID_KINEMATICS, k_kinematics<<<e->B, KIN_CTA, (size_t)(e->S + 1) * e->K * 32, e->cap_side>>>(k, e->d_tools, e->d_args, e->rand_num, s.poses, s.cidx));
+      KL(KID_KINEMATICS, k_kinematics<<<e->B, KIN_CTA, kin_smem(e), e->cap_side>>>(k, e->d_tools, e->d_args, e->rand_num, s.poses, s.cidx));
       CK(cudaEventRecord(e->ev_join, e->cap_side));
       e->kin_join = true;
     } else {
-      KL(KID_KINEMATICS, k_kinematics<<<e->B, KIN_CTA, (size_t)(e->S + 1) * e->K * 32, e->qs>>>(k, e->d_tools, e->d_args, e->rand_num, s.poses, s.cidx));
+      KL(KID_KINEMATICS, k_kinematics<<<e->B, KIN_CTA, kin_smem(e), e->qs>>>(k, e->d_tools, e->d_args, e->rand_num, s.poses, s.cidx));
     }
   }
   if (e->cfg.sort_particles && !e->seq_full_sort) {

@@ -422,7 +422,7 @@ __global__ void k_loss_l2(SimConst k, const float* __restrict__ frame, float* __
   if ((threadIdx.x & 31) == 0 && l != 0.f && gid < k.stride) atomicAdd(&loss[env], l);
 }
 
-#define KIN_CTA 256
+#define KIN_CTA 1024   // one CTA per env: 32 warps share the S*npairs collision queries of the optimistic pass
 // One CTA per env: S substeps of forward_kinematics for every tool, then (if any pair) set_surface_points,
 // set_collision_idx (deterministic first minimum) and apply_collision_projection (mpm_simulator.py:286-305).
 // Tool-tool projections are rare, so the kernel is optimistic: (1) the kinematics chain of all S substeps without
@@ -442,11 +442,13 @@ __global__ void __launch_bounds__(KIN_CTA)
   __shared__ int red_i[KIN_CTA / 32];
   __shared__ int s_idx[DSK_MAX_PAIRS];
   __shared__ int s_first;
-  extern __shared__ float sAll[];           // [(S+1)][K][8] projection-free chain
+  extern __shared__ float sAll[];           // [(S+1)][K][8] projection-free chain, then [npairs][600][3] collision samples
   int env = blockIdx.x, tid = threadIdx.x;
   const int per = k.K * 8;
   for (int i = tid; i < k.K * (int)(sizeof(ToolParams) / 4); i += blockDim.x) ((int*)sT)[i] = ((const int*)tools)[i];
   for (int i = tid; i < per; i += blockDim.x) sAll[i] = state0[(size_t)env * per + i];
+  float* sRand = sAll + (size_t)(k.S + 1) * per;
+  for (int i = tid; i < k.npairs * DSK_NUM_COLLISION_POINTS * 3; i += blockDim.x) sRand[i] = rand_num[i];
   if (tid == 0) s_first = k.S;
   __syncthreads();
   int A = 0;
@@ -479,7 +481,7 @@ __global__ void __launch_bounds__(KIN_CTA)
       float best = 0.f;
       int bi = -1;
       for (int q = lane; q < DSK_NUM_COLLISION_POINTS; q += 32) {
-        float3 pt = surface_point(sT[tj], Pj, rand_num + ((size_t)c * DSK_NUM_COLLISION_POINTS + q) * 3);
+        float3 pt = surface_point(sT[tj], Pj, sRand + ((size_t)c * DSK_NUM_COLLISION_POINTS + q) * 3);
         float d = local_sdf(Ti, kind, qrot_rn(qa, sub3_rn(pt, Fa.o)));
         if (grip) d = tmin(d, local_sdf(Ti, kind, qrot_rn(qa, sub3_rn(pt, Fb.o))));
         if (d < best) {
@@ -509,33 +511,65 @@ __global__ void __launch_bounds__(KIN_CTA)
   for (int i = tid; i < per; i += blockDim.x) sP[i / 8][i % 8] = sAll[(size_t)j0 * per + i];
   __syncthreads();
   // (3) the reference's sequential procedure from substep j0 on
+  ToolVel u3;
+  ToolRotInc ri3;
+  if (tid < k.K) {
+    int off = 0;
+    for (int t = 0; t < tid; t++) off += sT[t].action_dim;
+    float zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    u3 = action_to_vel(sT[tid], action ? action + (size_t)env * A + off : zero, k.S);
+    ri3 = tool_rot_inc(sT[tid], u3);
+  }
   for (int j = j0; j < k.S; j++) {
     if (tid < k.K) {
-      int off = 0;
-      for (int t = 0; t < tid; t++) off += sT[t].action_dim;
-      float zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      const float* a = action ? action + (size_t)env * A + off : zero;
-      ToolVel u = action_to_vel(sT[tid], a, k.S);
-      Pose N = tool_fk(sT[tid], load_pose(sP[tid]), u);
+      Pose N = tool_fk_inc(sT[tid], load_pose(sP[tid]), u3, ri3);   // same arithmetic as the optimistic chain
       store_pose(sP[tid], N);
       store_pose(sPre[tid], N);
     }
     __syncthreads();
     if (k.npairs > 0) {
-      for (int c = 0; c < k.npairs; c++) {
+      // all pairs at once: the warps are split evenly between the pairs (every query reads the pre-projection poses)
+      const int wpp = (KIN_CTA / 32) / k.npairs;           // warps per pair (DSK_MAX_PAIRS <= 8 -> at least 4)
+      const int warp = tid >> 5, lane = tid & 31;
+      const int c = min(warp / wpp, k.npairs - 1), wq = warp - c * wpp;
+      const bool worker = warp < wpp * k.npairs;
+      float best = 0.f;
+      int bi = -1;
+      if (worker) {
         int ti = k.pairs[c][0], tj = k.pairs[c][1];
         Pose Pi = load_pose(sPre[ti]), Pj = load_pose(sPre[tj]);
-        float best = 0.f;
-        int bi = -1;
-        for (int q = tid; q < DSK_NUM_COLLISION_POINTS; q += blockDim.x) {
-          float3 pt = surface_point(sT[tj], Pj, rand_num + ((size_t)c * DSK_NUM_COLLISION_POINTS + q) * 3);
-          float d = tool_sdf(sT[ti], Pi, pt);
+        const ToolParams& Ti = sT[ti];   // tool_sdf with the frames and their inverse rotation hoisted, as in (2)
+        bool grip = Ti.type == DSK_TOOL_GRIPPER;
+        Frame Fa = grip ? jaw_frame(Pi, -1.f) : tool_frame(Pi), Fb = grip ? jaw_frame(Pi, 1.f) : Fa;
+        Q4 qa = qconj_normalized_rn(Fa.q);
+        int kind = grip ? SDF_BOX : sdf_kind(Ti.type);
+        for (int q = wq * 32 + lane; q < DSK_NUM_COLLISION_POINTS; q += wpp * 32) {
+          float3 pt = surface_point(sT[tj], Pj, sRand + ((size_t)c * DSK_NUM_COLLISION_POINTS + q) * 3);
+          float d = local_sdf(Ti, kind, qrot_rn(qa, sub3_rn(pt, Fa.o)));
+          if (grip) d = tmin(d, local_sdf(Ti, kind, qrot_rn(qa, sub3_rn(pt, Fb.o))));
           if (d < best) {
             best = d;
             bi = q;
           }
         }
-        // block arg-min, ties -> smaller index ("first minimum")
+      }
+      // arg-min, ties -> smaller index ("first minimum"): warp, then the first warp of each pair over its warps
+      for (int o = 16; o > 0; o >>= 1) {
+        float od = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi >= 0 && (bi < 0 || od < best || (od == best && oi < bi))) {
+          best = od;
+          bi = oi;
+        }
+      }
+      if (lane == 0) {
+        red_d[warp] = best;
+        red_i[warp] = bi;
+      }
+      __syncthreads();
+      if (worker && wq == 0) {
+        best = lane < wpp ? red_d[c * wpp + lane] : 0.f;
+        bi = lane < wpp ? red_i[c * wpp + lane] : -1;
         for (int o = 16; o > 0; o >>= 1) {
           float od = __shfl_xor_sync(0xffffffffu, best, o);
           int oi = __shfl_xor_sync(0xffffffffu, bi, o);
@@ -544,39 +578,45 @@ __global__ void __launch_bounds__(KIN_CTA)
             bi = oi;
           }
         }
-        if ((tid & 31) == 0) {
-          red_d[tid >> 5] = best;
-          red_i[tid >> 5] = bi;
-        }
-        __syncthreads();
-        if (tid == 0) {
-          for (int w = 1; w < KIN_CTA / 32; w++) {
-            float od = red_d[w];
-            int oi = red_i[w];
-            if (oi >= 0 && (bi < 0 || od < best || (od == best && oi < bi))) {
-              best = od;
-              bi = oi;
-            }
-          }
+        if (lane == 0) {
           s_idx[c] = bi;
+          cidx[((size_t)env * (k.S + 1) + (j + 1)) * k.npairs + c] = bi;
         }
-        __syncthreads();
       }
-      if (tid == 0) {
-        for (int c = 0; c < k.npairs; c++) {
-          int ti = k.pairs[c][0], tj = k.pairs[c][1];
-          cidx[((size_t)env * (k.S + 1) + (j + 1)) * k.npairs + c] = s_idx[c];
-          if (s_idx[c] >= 0) {  // collision_projection, primive_base.py:145-150
-            float3 pt = surface_point(sT[tj], load_pose(sPre[tj]),
-                                      rand_num + ((size_t)c * DSK_NUM_COLLISION_POINTS + s_idx[c]) * 3);
-            Pose Pi = load_pose(sP[ti]);
-            float d = tool_sdf(sT[ti], Pi, pt);
-            float3 nr = tool_normal(sT[ti], Pi, pt);
-            float inv = __fdiv_rn(1.f, __fsqrt_rn(dot_rn(nr, nr)));
-            sP[ti][0] = add_rn(Pi.p.x, mul_rn(mul_rn(inv, nr.x), d));
-            sP[ti][1] = add_rn(Pi.p.y, mul_rn(mul_rn(inv, nr.y), d));
-            sP[ti][2] = add_rn(Pi.p.z, mul_rn(mul_rn(inv, nr.z), d));
+      __syncthreads();
+      // collision_projection, primive_base.py:145-150, in pair order for every moved tool: thread t handles the
+      // pairs that move tool t (different tools are independent: a projection changes only its own tool's position)
+      if (tid < k.K) {
+        for (int c2 = 0; c2 < k.npairs; c2++) {
+          int ti = k.pairs[c2][0], tj = k.pairs[c2][1];
+          if (ti != tid || s_idx[c2] < 0) continue;
+          float3 pt = surface_point(sT[tj], load_pose(sPre[tj]),
+                                    sRand + ((size_t)c2 * DSK_NUM_COLLISION_POINTS + s_idx[c2]) * 3);
+          Pose Pi = load_pose(sP[ti]);
+          // d = tool_sdf, nr = tool_normal (primitives.py:489-496 picks the jaw with da <= db), frames built once
+          const ToolParams& Ti = sT[ti];
+          bool grip = Ti.type == DSK_TOOL_GRIPPER;
+          int kind = grip ? SDF_BOX : sdf_kind(Ti.type);
+          Frame Fa = grip ? jaw_frame(Pi, -1.f) : tool_frame(Pi);
+          Q4 qa = qconj_normalized_rn(Fa.q);
+          float3 pl = qrot_rn(qa, sub3_rn(pt, Fa.o));
+          float d = local_sdf(Ti, kind, pl);
+          Q4 qf = Fa.q;
+          if (grip) {
+            Frame Fb = jaw_frame(Pi, 1.f);
+            float3 plb = qrot_rn(qconj_normalized_rn(Fb.q), sub3_rn(pt, Fb.o));
+            float db = local_sdf(Ti, kind, plb);
+            if (!(d <= db)) {
+              pl = plb;
+              qf = Fb.q;
+            }
+            d = tmin(d, db);
           }
+          float3 nr = qrot_rn(qf, local_normal(Ti, kind, pl));
+          float inv = __fdiv_rn(1.f, __fsqrt_rn(dot_rn(nr, nr)));
+          sP[ti][0] = add_rn(Pi.p.x, mul_rn(mul_rn(inv, nr.x), d));
+          sP[ti][1] = add_rn(Pi.p.y, mul_rn(mul_rn(inv, nr.y), d));
+          sP[ti][2] = add_rn(Pi.p.z, mul_rn(mul_rn(inv, nr.z), d));
         }
       }
       __syncthreads();
