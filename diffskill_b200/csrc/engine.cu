@@ -802,13 +802,21 @@ static int seq_substep_grad(dsk_engine* e, StepSlot& s, int q, int j) {
                                GridTape{nullptr, nullptr, nullptr, nullptr, 0}, run_if));
   }
   if (e->big)
-    KL(KID_G2P_ADJ, k_g2p_adj<3><<<nb, pb, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
+    switch (e->minb_g2p_adj) {
+      case 5: KL(KID_G2P_ADJ, k_g2p_adj<5><<<nb, pb, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set])); break;
+      case 4: KL(KID_G2P_ADJ, k_g2p_adj<4><<<nb, pb, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set])); break;
+      default: KL(KID_G2P_ADJ, k_g2p_adj<3><<<nb, pb, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set])); break;
+    }
   else
     KL(KID_G2P_ADJ, k_g2p_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
   KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, e->qs, (GridAdjScratch{nullptr, nullptr, 0}), k, e->grid_tools, s.poses, j, e->G0[set], e->Ga[set],
                                                                       tt.list, tt.count, e->pose_adj));
   if (e->big)
-    KL(KID_P2G_ADJ, k_p2g_adj<3><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set], svd_at(e, s, j)));
+    switch (e->minb_p2g_adj) {
+      case 5: KL(KID_P2G_ADJ, k_p2g_adj<5><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set], svd_at(e, s, j))); break;
+      case 4: KL(KID_P2G_ADJ, k_p2g_adj<4><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set], svd_at(e, s, j))); break;
+      default: KL(KID_P2G_ADJ, k_p2g_adj<3><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set], svd_at(e, s, j))); break;
+    }
   else
     KL(KID_P2G_ADJ, k_p2g_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set], svd_at(e, s, j)));
   LAUNCH_CHECK();
