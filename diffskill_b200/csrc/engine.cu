@@ -245,6 +245,8 @@ static void fill_tool(ToolParams& T, const dsk_tool_desc& d) {
   T.max_gap = (float)d.maximal_gap;
   if (d.type == DSK_TOOL_CAPSULE || d.type == DSK_TOOL_ROLLINGPIN_EXT)
     T.bound_r = (float)(d.h / 2 + d.r);
+  else if (d.type == DSK_TOOL_SPHERE)
+    T.bound_r = (float)d.r;
   else
     T.bound_r = (float)std::sqrt(d.size[0] * d.size[0] + d.size[1] * d.size[1] + d.size[2] * d.size[2]);
   T.bound_r *= 1.001f;
@@ -345,7 +347,7 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
     e->A += c->tools[i].action_dim;
     e->ncols += c->tools[i].type == DSK_TOOL_GRIPPER ? 2 : 1;
     e->n_frames = std::max(1, e->ncols);
-    if (c->tools[i].type < 0 || c->tools[i].type > DSK_TOOL_KNIFE) {
+    if (c->tools[i].type < 0 || c->tools[i].type > DSK_TOOL_SPHERE) {
       delete e;
       return fail("unknown tool type %d", c->tools[i].type);
     }

@@ -73,8 +73,12 @@ DSK_DEV FrameAdj frame_adj_zero() {
   return a;
 }
 
-enum { SDF_CAPSULE = 0, SDF_BOX = 1, SDF_KNIFE = 2 };
+// SDF_SPHERE (primitives.py:23-41): the reference evaluates length(p - position) - radius in WORLD space; here it is
+// |R^-1 (p - position)| - radius in the tool frame like every other shape -- the same number up to an fp32 rounding of
+// the rotation, and the rotation adjoint it produces is zero to the same rounding.
+enum { SDF_CAPSULE = 0, SDF_BOX = 1, SDF_KNIFE = 2, SDF_SPHERE = 3 };
 DSK_DEV int sdf_kind(int tool_type) {
+  if (tool_type == DSK_TOOL_SPHERE) return SDF_SPHERE;
   return (tool_type == DSK_TOOL_CAPSULE || tool_type == DSK_TOOL_ROLLINGPIN_EXT)
              ? SDF_CAPSULE
              : (tool_type == DSK_TOOL_KNIFE ? SDF_KNIFE : SDF_BOX);
@@ -103,6 +107,7 @@ DSK_DEV float prism_sdf(const ToolParams& T, float3 p0) {  // primitives.py:711-
 DSK_DEV float local_sdf(const ToolParams& T, int kind, float3 p) {
   if (kind == SDF_CAPSULE) return sub_rn(len14_rn(capsule_p2(T, p)), T.r);
   if (kind == SDF_BOX) return box_sdf(T, p);
+  if (kind == SDF_SPHERE) return sub_rn(len14_rn(p), T.r);   // primitives.py:28-30
   return tmax(prism_sdf(T, p), box_sdf(T, p));  // primitives.py:769-773
 }
 
@@ -157,6 +162,7 @@ DSK_DEV float3 prism_sdf_grad(const ToolParams& T, float3 p0) {
 DSK_DEV float3 local_sdf_grad(const ToolParams& T, int kind, float3 p) {
   if (kind == SDF_CAPSULE) return capsule_sdf_grad(T, p);
   if (kind == SDF_BOX) return box_sdf_grad(T, p);
+  if (kind == SDF_SPHERE) return (1.f / sqrtf(dot(p, p) + 1e-14f)) * p;
   float a = prism_sdf(T, p), b = box_sdf(T, p);
   return (b < a) ? prism_sdf_grad(T, p) : box_sdf_grad(T, p);
 }
@@ -168,6 +174,8 @@ DSK_DEV float3 local_normal_raw(const ToolParams& T, int kind, float3 p, float& 
   float3 n;
   if (kind == SDF_CAPSULE) {
     n = capsule_p2(T, p);
+  } else if (kind == SDF_SPHERE) {  // primitives.py:32-34: normalize(p)
+    n = p;
   } else {  // primitives.py:382-393 / 796-807
     const float d = DSK_FD_D;
     const float c = __fdiv_rn(0.5f, d);
@@ -195,6 +203,7 @@ DSK_DEV float3 local_normal_adj(const ToolParams& T, int kind, float3 p, float3 
     float dyy = 1.f - (((0.f < y) && (t < T.h)) ? 1.f : 0.f);
     return f3(gn.x, dyy * gn.y, gn.z);
   }
+  if (kind == SDF_SPHERE) return gn;   // n = p
   const float d = DSK_FD_D;
   const float c = 0.5f / d;
   float3 gp = f3(0, 0, 0);
@@ -213,6 +222,7 @@ DSK_DEV float3 local_normal_adj_cached(const ToolParams& T, int kind, float3 p, 
     float dyy = 1.f - (((0.f < y) && (t < T.h)) ? 1.f : 0.f);
     return f3(gn.x, dyy * gn.y, gn.z);
   }
+  if (kind == SDF_SPHERE) return gn;   // n = p
   const float d = DSK_FD_D;
   const float c = 0.5f / d;
   float3 gp = f3(0, 0, 0);

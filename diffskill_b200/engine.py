@@ -9,7 +9,7 @@ import os
 
 import numpy as np
 
-from .scene import NUM_COLLISION_POINTS, SceneSpec
+from .scene import NUM_COLLISION_POINTS, TOOL_SPHERE, SceneSpec
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libdiffskill_mpm.so')
@@ -113,7 +113,7 @@ def make_config(scene: SceneSpec, n_envs, capacity, max_steps, step_slots, sort,
         d.lower_bound[:] = t.lower_bound
         d.upper_bound[:] = t.upper_bound
         d.size[:] = t.size
-        d.h, d.r = t.h, t.r
+        d.h, d.r = t.h, (t.radius if t.type_id == TOOL_SPHERE else t.r)
         d.prism_h[:] = t.prism_h
         d.prot[:] = t.prot
         d.minimal_gap, d.maximal_gap = t.minimal_gap, t.maximal_gap

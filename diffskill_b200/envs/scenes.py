@@ -54,8 +54,24 @@ CUT_REARRANGE = dict(
     ENV=dict(cached_state_path='datasets/1215_cutrearrange', env_name='CutRearrange-v1'),
 )
 
+# PlasticineLab's Move-v1 (plb/envs/move.yml, first variant): two Sphere manipulators around a ball of dough.  Not one
+# of the three DiffSkill envs -- registered to exercise the Sphere tool.
+MOVE = dict(
+    SIMULATOR=dict(E=5000., n_particles=10000, yield_stress=200.),
+    SHAPES=[dict(shape='sphere', radius=0.2049069760770578 / 2,
+                 init_pos=(0.6757143040494873, 0.5619162002773135, 0.7515980438048129), color=127 << 16)],
+    PRIMITIVES=[
+        dict(shape='Sphere', radius=0.03, init_pos=(0.5757143040494873, 0.5619162002773135, 0.7515980438048129),
+             color=(0.7, 0.7, 0.7), friction=0.9, action=dict(dim=3, scale=(0.01, 0.01, 0.01))),
+        dict(shape='Sphere', radius=0.03, init_pos=(0.7757143040494873, 0.5619162002773135, 0.7515980438048129),
+             color=(0.7, 0.7, 0.7), friction=0.9, action=dict(dim=3, scale=(0.01, 0.01, 0.01))),
+    ],
+    ENV=dict(env_name='Move-v1'),
+)
+
 SCENES = {
     'LiftSpread-v1': LIFT_SPREAD,
     'GatherMove-v1': GATHER_MOVE,
     'CutRearrange-v1': CUT_REARRANGE,
+    'Move-v1': MOVE,
 }

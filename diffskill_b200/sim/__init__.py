@@ -1,5 +1,5 @@
 """Drop-in mirrors of the reference's plb.engine classes over the CUDA engine."""
 from .function import GradModel  # noqa: F401
 from .mpm_simulator import MPMSimulator  # noqa: F401
-from .primitives import Box, Capsule, Gripper, Knife, Primitive, Primitives, RollingPinExt  # noqa: F401
+from .primitives import Box, Capsule, Gripper, Knife, Primitive, Primitives, RollingPinExt, Sphere  # noqa: F401
 from .taichi_env import TaichiEnv  # noqa: F401

@@ -190,6 +190,11 @@ class Primitive:
         return _primitive_defaults(cls.shape)
 
 
+class Sphere(Primitive):
+    """primitives.py:23-41 (legacy PlasticineLab tool); the base class's zero init_points."""
+    shape = 'Sphere'
+
+
 class Capsule(Primitive):
     shape = 'Capsule'
 
@@ -291,7 +296,7 @@ class Knife(Primitive):
         return action
 
 
-_SHAPES = {c.shape: c for c in (Capsule, RollingPinExt, Box, Gripper, Knife)}
+_SHAPES = {c.shape: c for c in (Sphere, Capsule, RollingPinExt, Box, Gripper, Knife)}
 
 
 class Primitives:
@@ -303,7 +308,7 @@ class Primitives:
         for i in cfgs:
             cfg = i if isinstance(i, CfgNode) else CfgNode(yaml.safe_load(yaml.safe_dump(dict(i))))
             if cfg.shape not in _SHAPES:
-                raise NotImplementedError(f"primitive {cfg.shape!r}: only the tools of the three DiffSkill envs are built "
+                raise NotImplementedError(f"primitive {cfg.shape!r}: only the tools of the three DiffSkill envs and Sphere are built "
                                           "(SURVEY.md section 8f row 4)")
             p = _SHAPES[cfg.shape](cfg=cfg, max_timesteps=max_timesteps)
             self.primitives.append(p)

@@ -42,7 +42,8 @@ enum dsk_tool_type {
   DSK_TOOL_ROLLINGPIN_EXT = 1, /* primitives.py:120 */
   DSK_TOOL_BOX = 2,            /* primitives.py:359 */
   DSK_TOOL_GRIPPER = 3,        /* primitives.py:428 */
-  DSK_TOOL_KNIFE = 4           /* primitives.py:740 (Prism :700 + Box) */
+  DSK_TOOL_KNIFE = 4,          /* primitives.py:740 (Prism :700 + Box) */
+  DSK_TOOL_SPHERE = 5          /* primitives.py:23 (legacy PlasticineLab tool; radius in `r`) */
 };
 
 enum dsk_tool_param {
@@ -62,7 +63,7 @@ typedef struct dsk_tool_desc {
   double lower_bound[3];   /* cfg.lower_bound -> xyz_limit[0] */
   double upper_bound[3];   /* cfg.upper_bound -> xyz_limit[1] */
   double size[3];          /* Box / Gripper / Knife.box half extents */
-  double h, r;             /* Capsule */
+  double h, r;             /* Capsule; Sphere: r = cfg.radius */
   double prism_h[2];       /* Knife.prism.h */
   double prot[4];          /* Knife.prism.prot */
   double minimal_gap, maximal_gap; /* Gripper */

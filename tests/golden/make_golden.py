@@ -46,5 +46,5 @@ def make(name, n=300, seed=0):
 
 
 if __name__ == '__main__':
-    for nm in ['LiftSpread-v1', 'GatherMove-v1', 'CutRearrange-v1']:
+    for nm in ['LiftSpread-v1', 'GatherMove-v1', 'CutRearrange-v1', 'Move-v1']:
         make(nm)

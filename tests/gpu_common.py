@@ -7,7 +7,7 @@ from helpers import perturbed_state, relerr, small_dough, tool_start
 from diffskill_b200.engine import Engine
 from oracle import oracle as orc
 
-ENVS = ['LiftSpread-v1', 'GatherMove-v1', 'CutRearrange-v1']
+ENVS = ['LiftSpread-v1', 'GatherMove-v1', 'CutRearrange-v1', 'Move-v1']   # Move-v1: the Sphere tool
 
 
 def f32(a):

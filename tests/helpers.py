@@ -23,6 +23,9 @@ def small_dough(name, n, seed=0):
         x = rng.uniform(-1, 1, (n, 3)) * np.array([0.05, 0.012, 0.05]) + np.array([0.70, 0.05, 0.5])
     elif name == 'CutRearrange-v1':
         x = rng.uniform(-1, 1, (n, 3)) * np.array([0.06, 0.03, 0.03]) + np.array([0.5, 0.06, 0.5])
+    elif name == 'Move-v1':
+        # slab between the two sphere manipulators (x = 0.576 and 0.776, radius 0.03), 5 mm into each of them
+        x = rng.uniform(-1, 1, (n, 3)) * np.array([0.075, 0.03, 0.03]) + np.array([0.6757143, 0.5619162, 0.7515980])
     else:
         x = Shapes(cfg.SHAPES, seed=seed).get()[0][:n]
     return scene, cfg, x
