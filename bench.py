@@ -238,6 +238,7 @@ def main():
     ap.add_argument('--grid-tape-mib', type=int, default=8192,
                     help='device memory budget for taping active grid tiles (adjoint skips the p2g/grid_op recompute); 0 = off')
     ap.add_argument('--envs', type=int, default=0, help='override the envs per GPU of the workload (experiments; the JSON says so)')
+    ap.add_argument('--per-step-calls', action='store_true', help='drive the rollout with one host call per env step')
     ap.add_argument('--no-sort', action='store_true')
     ap.add_argument('--no-graphs', action='store_true')
     args = ap.parse_args()
@@ -292,16 +293,26 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     w = 1.0 / H
 
-    def iteration(e2e):
+    def iteration(e2e, mark=None):
+        # the planner's rollout through the multi-step calls of the C ABI (one host call per phase, see
+        # include/diffskill_mpm.h); --per-step-calls uses the reference-shaped per-step entry points instead
         eng.zero_grad()
         eng.loss_reset()
-        for s in range(H):
-            eng.set_action(s, act_host[s].numpy() if e2e else act_dev[s])   # e2e: H2D copy of this step's action
-            eng.forward_step(s)
-            eng.loss_add_l2(s + 1, tgt_dev, w)
-        for s in range(H - 1, -1, -1):
-            eng.backward_step(s)
+        if args.per_step_calls:
+            for s in range(H):
+                eng.set_action(s, act_host[s].numpy() if e2e else act_dev[s])   # e2e: H2D copy of this step's action
+                eng.forward_step(s)
+                eng.loss_add_l2(s + 1, tgt_dev, w)
+            for s in range(H - 1, -1, -1):
+                eng.backward_step(s)
+        else:
+            eng.set_actions(0, act_host.numpy() if e2e else act_dev)            # e2e: H2D copy of the action sequences
+            eng.forward_steps(0, H)
+            eng.loss_add_l2_steps(1, H, tgt_dev, w)
+            eng.backward_steps(H - 1, H)
         if world > 1:   # the planner's exchange step: per-env losses and action gradients of every rank
+            if mark is not None:
+                mark.record()   # end of this rank's own simulation work, before the collective couples the ranks
             eng.get_action_grads(0, H, grads_dev)
             eng.loss_get(loss_dev)
             gather_planner_inputs(loss_dev, grads_dev)
@@ -309,21 +320,30 @@ def main():
             eng.get_action_grads(0, H, grads_host.numpy())
             eng.loss_get(loss_host.numpy())
 
+    per_rank_ms = {}   # mean device time of every rank's own work, up to the exchange step (ranks simulate different envs)
+
     def timed(e2e, iters):
-        ms = []
+        ms, own = [], []
         for _ in range(iters):
             flush.zero_()
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c = torch.cuda.Event(enable_timing=True) if world > 1 else None
             a.record()
-            iteration(e2e)
+            iteration(e2e, c)
             b.record()
             torch.cuda.synchronize()
             ms.append(a.elapsed_time(b))
+            if c is not None:
+                own.append(a.elapsed_time(c))
         t = torch.tensor(ms, device=dev, dtype=torch.float64)
         if world > 1:
+            mine = torch.tensor([sum(own) / len(own)], device=dev, dtype=torch.float64)   # before the exchange step
+            every = torch.zeros(world, device=dev, dtype=torch.float64)
+            dist.all_gather_into_tensor(every, mine)
+            per_rank_ms[bool(e2e)] = [round(float(v), 3) for v in every.cpu()]
             dist.all_reduce(t, op=dist.ReduceOp.MAX)   # max over ranks, per iteration
         return t.cpu().numpy()
 
@@ -394,6 +414,8 @@ def main():
                             d2h_bytes_per_step=int(grads_host.numel() * 4 + loss_host.numel() * 4)),
                    gpu_launches=int(launches), roofline=roof, clocks=clocks,
                    loss=final_loss, finite=finite, engine_bytes=eng.memory_bytes())
+        if per_rank_ms:
+            out['per_rank_ms'] = dict(device=per_rank_ms.get(False), e2e=per_rank_ms.get(True))
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             v, dt, n_, S_ = cpu_oracle_sample(spec, threads, env_steps=1)

@@ -1736,6 +1736,48 @@ int dsk_loss_add_l2(dsk_engine* e, int step, const float* target, double weight,
   if (!on_device) CK(cudaStreamSynchronize(e->stream));
   return 0;
 }
+/* ---- multi-step calls: the planner's fast path -- one host call instead of one per env step ---- */
+int dsk_set_actions(dsk_engine* e, int step0, int nsteps, const float* actions, int on_device) {
+  CKE(e);
+  if (nsteps <= 0) return 0;
+  if (step0 < 0 || step0 + nsteps > e->H) return fail("dsk_set_actions: steps [%d,%d) outside [0,%d)", step0, step0 + nsteps, e->H);
+  if (e->A == 0) return 0;
+  size_t n = (size_t)nsteps * e->B * e->A;
+  const float* src;
+  if (stage_in(e, actions, n, on_device, 0, &src)) return -1;
+  KL(KID_IO, k_clip_actions<<<cdiv((int)n, 256), 256, 0, e->stream>>>(e->actions + (size_t)step0 * e->B * e->A, src, (int)n));
+  LAUNCH_CHECK();
+  if (!on_device) CK(cudaStreamSynchronize(e->stream));  // the staging buffer may be reused by the next call
+  for (auto& s : e->slot)
+    if (s.action_step >= step0 && s.action_step < step0 + nsteps) s.src_step = -1;
+  return 0;
+}
+int dsk_forward_steps(dsk_engine* e, int step0, int nsteps) {
+  CKE(e);
+  for (int s = step0; s < step0 + nsteps; s++)
+    if (dsk_forward_step(e, s, s + 1, s)) return -1;
+  return 0;
+}
+int dsk_backward_steps(dsk_engine* e, int step_hi, int nsteps) {
+  CKE(e);
+  for (int s = step_hi; s > step_hi - nsteps; s--)
+    if (dsk_backward_step(e, s)) return -1;
+  return 0;
+}
+int dsk_loss_add_l2_steps(dsk_engine* e, int step0, int nsteps, const float* target, double weight, int on_device) {
+  CKE(e);
+  if (nsteps <= 0) return 0;
+  if (check_step(e, step0, "dsk_loss_add_l2_steps") || check_step(e, step0 + nsteps - 1, "dsk_loss_add_l2_steps")) return -1;
+  int cap = e->cfg.particle_capacity;
+  const float* d;
+  if (stage_in(e, target, (size_t)e->B * cap * 3, on_device, 0, &d)) return -1;
+  for (int step = step0; step < step0 + nsteps; step++)
+    KL(KID_LOSS, k_loss_l2<<<cdiv(e->k.stride, 128), 128, 0, e->stream>>>(e->k, e->frame_of(e->ckpt, step), e->frame_of(e->adj_ckpt, step),
+                                                                          e->npart, d, cap, (float)weight, e->loss));
+  LAUNCH_CHECK();
+  if (!on_device) CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
 int dsk_loss_get(dsk_engine* e, float* out, int on_device) {
   CKE(e);
   CK(cudaMemcpyAsync(out, e->loss, (size_t)e->B * 4, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));

@@ -60,6 +60,7 @@ SYMBOLS = [
     'dsk_profile_enable', 'dsk_kernel_class_count', 'dsk_kernel_class_name', 'dsk_profile_report',
     'dsk_launch_counts', 'dsk_loss_reset', 'dsk_loss_add_l2', 'dsk_loss_get',
     'dsk_timeline_enable', 'dsk_timeline_reset', 'dsk_timeline_read',
+    'dsk_set_actions', 'dsk_forward_steps', 'dsk_backward_steps', 'dsk_loss_add_l2_steps',
 ]
 
 
@@ -460,6 +461,27 @@ class Engine:
         p, dev = _ptr(_f32(target) if isinstance(target, np.ndarray) else target)
         self._keep_t = target
         self._ck(self.L.dsk_loss_add_l2(self.h, step, p, C.c_double(weight), dev))
+
+    # ---- multi-step fast path (one host call per phase of a rollout) -------------------------------------------
+    def set_actions(self, step0, actions):
+        """actions: [nsteps, B, A] numpy (host) or torch CUDA tensor."""
+        a = _f32(actions) if isinstance(actions, np.ndarray) else actions
+        n = int(a.shape[0])
+        assert tuple(a.shape[1:]) == (self.B, self.A), f"actions must be [nsteps, {self.B}, {self.A}]"
+        p, dev = _ptr(a)
+        self._keep_a = a
+        self._ck(self.L.dsk_set_actions(self.h, step0, n, p, dev))
+
+    def forward_steps(self, step0, nsteps):
+        self._ck(self.L.dsk_forward_steps(self.h, step0, nsteps))
+
+    def backward_steps(self, step_hi, nsteps):
+        self._ck(self.L.dsk_backward_steps(self.h, step_hi, nsteps))
+
+    def loss_add_l2_steps(self, step0, nsteps, target, weight=1.0):
+        p, dev = _ptr(_f32(target) if isinstance(target, np.ndarray) else target)
+        self._keep_t = target
+        self._ck(self.L.dsk_loss_add_l2_steps(self.h, step0, nsteps, p, C.c_double(weight), dev))
 
     def loss_get(self, out=None):
         if out is None:

@@ -23,6 +23,7 @@ class BatchedSolver:
 
         def fn(eng, step):
             eng.loss_add_l2(step, targets, w)
+        fn.steps = lambda eng, step0, n: eng.loss_add_l2_steps(step0, n, targets, w)   # multi-step fast path
         return fn
 
     def rollout_grad(self, actions, loss_fn):
@@ -30,12 +31,18 @@ class BatchedSolver:
         eng = self.eng
         eng.zero_grad()
         eng.loss_reset()
-        for s in range(self.H):
-            eng.set_action(s, actions[s])
-            eng.forward_step(s)
-            loss_fn(eng, s + 1)
-        for s in range(self.H - 1, -1, -1):
-            eng.backward_step(s)
+        if hasattr(loss_fn, 'steps'):   # engine-side loss: the whole rollout in five host calls
+            eng.set_actions(0, actions)
+            eng.forward_steps(0, self.H)
+            loss_fn.steps(eng, 1, self.H)
+            eng.backward_steps(self.H - 1, self.H)
+        else:
+            for s in range(self.H):
+                eng.set_action(s, actions[s])
+                eng.forward_step(s)
+                loss_fn(eng, s + 1)
+            for s in range(self.H - 1, -1, -1):
+                eng.backward_step(s)
         return eng.loss_get(), eng.get_action_grads(0, self.H)
 
     def solve(self, init_actions, loss_fn, max_iter=20, callback=None, distributed=False):

@@ -216,6 +216,14 @@ int dsk_timeline_read(dsk_engine* e, int* kid, unsigned long long* t0_ns, unsign
 int dsk_loss_reset(dsk_engine* e);
 int dsk_loss_add_l2(dsk_engine* e, int step, const float* target, double weight, int on_device);
 int dsk_loss_get(dsk_engine* e, float* out, int on_device);
+/* Multi-step calls -- the batched fast path under the planner loops (Solver.solve_one_plan, plb/optimizer/solver.py:111-127;
+ * plb/cut/solve_func.solve :74-105): the same work as the per-step calls above, issued by ONE host call each, so a whole
+ * rollout is ~6 calls instead of ~5 per env step.  actions: [nsteps, n_envs, action_dim]; the loss is added at checkpoints
+ * step0 .. step0+nsteps-1; backward runs steps step_hi, step_hi-1, ... (nsteps of them). */
+int dsk_set_actions(dsk_engine* e, int step0, int nsteps, const float* actions, int on_device);
+int dsk_forward_steps(dsk_engine* e, int step0, int nsteps);
+int dsk_backward_steps(dsk_engine* e, int step_hi, int nsteps);
+int dsk_loss_add_l2_steps(dsk_engine* e, int step0, int nsteps, const float* target, double weight, int on_device);
 /* launches issued by this engine since creation (bench.py's gpu_launches) */
 int dsk_launch_count(dsk_engine* e, int64_t* n);
 /* bytes of device memory owned by the engine */

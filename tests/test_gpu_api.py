@@ -148,3 +148,37 @@ def test_batched_solver_reduces_loss():
     print('planner loss history', ['%.3e' % v for v in h])
     assert np.isfinite(h).all() and h[-1] < h[0]
     assert res['best_action'].shape == (H, B, scene.action_dim) and np.abs(res['best_action']).max() <= 1.0
+
+
+def test_multi_step_calls_equal_per_step_calls():
+    """dsk_set_actions / forward_steps / loss_add_l2_steps / backward_steps issue exactly the per-step work."""
+    from diffskill_b200.engine import Engine
+    from diffskill_b200.scene import load_scene
+    from helpers import relerr, small_dough, tool_start
+    name, n, H, B = 'GatherMove-v1', 700, 3, 2
+    scene, cfg, x = small_dough(name, n)
+    acts = np.random.RandomState(4).uniform(-0.8, 0.8, (H, B, scene.action_dim)).astype(np.float32)
+    tgt = np.broadcast_to((x + np.array([0.01, 0.0, 0.01]))[None], (B, n, 3)).astype(np.float32).copy()
+    out = []
+    for multi in (False, True):
+        eng = Engine(scene, n_envs=B, capacity=n, max_steps=H, step_slots=H)
+        for b in range(B):
+            eng.set_particles(0, b, x.astype(np.float32))
+            for i, st in enumerate(tool_start(name, scene)):
+                eng.set_tool_state(0, b, i, np.asarray(st, np.float32))
+        eng.zero_grad(); eng.loss_reset()
+        if multi:
+            eng.set_actions(0, acts)
+            eng.forward_steps(0, H)
+            eng.loss_add_l2_steps(1, H, tgt, 1.0 / H)
+            eng.backward_steps(H - 1, H)
+        else:
+            for s in range(H):
+                eng.set_action(s, acts[s]); eng.forward_step(s); eng.loss_add_l2(s + 1, tgt, 1.0 / H)
+            for s in range(H - 1, -1, -1):
+                eng.backward_step(s)
+        out.append((eng.loss_get().copy(), eng.get_action_grads(0, H).copy(), eng.get_particles(H, 1, 'x')[0]))
+    (l0, g0, x0), (l1, g1, x1) = out
+    print('multi-step vs per-step: loss %.2e grads %.2e x %.2e' % (relerr(l1, l0), relerr(g1, g0), relerr(x1, x0)))
+    assert np.abs(g0).max() > 0
+    assert relerr(l1, l0) < 1e-5 and relerr(x1, x0) < 1e-6 and relerr(g1, g0) < 1e-4
