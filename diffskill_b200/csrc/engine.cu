@@ -106,9 +106,9 @@ struct dsk_engine {
   int bwd_cur = 0;  // adjw index holding the adjoint of the current frame
   // sequences / graphs
   struct GraphSet {
-    cudaGraphExec_t ex[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [kind*2 + full_sort]
-    int64_t n_launch[10] = {0};
-    int64_t kid[10][KID_COUNT] = {{0}};
+    cudaGraphExec_t ex[16] = {};  // [kind*2 + full_sort]
+    int64_t n_launch[16] = {0};
+    int64_t kid[16][KID_COUNT] = {{0}};
   };
   std::vector<GraphSet> graphs;
   bool use_graphs = true;
@@ -124,6 +124,11 @@ struct dsk_engine {
   int* perm_cache = nullptr;   // permutation of the last full sort
   int sort_age = 1 << 30, resort_interval = 1;   // >1 re-uses the last permutation (cheaper sort, more fragmented warps)
   bool seq_full_sort = true;
+  bool seq_skip_kin = false;          // sequence being enqueued must not run its own tool kinematics / tool store
+  StepSlot* seq_next_slot = nullptr;  // ... and runs the kinematics of the next step (this slot) on a side branch
+  int seq_next_step = -1;
+  cudaEvent_t ev_join2 = nullptr;
+  StepArgs* d_args_kin = nullptr;     // [H] device-resident args of the lookahead kinematics (pointers only: set once)
 #ifdef DSK_TIMELINE
   TlRec* d_tl = nullptr;
   int tl_cap = 16384, tl_next = 0;
@@ -473,6 +478,7 @@ int dsk_destroy(dsk_engine* e) {
   if (e->d_tl) cudaFree(e->d_tl);
 #endif
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  if (e->ev_join2) cudaEventDestroy(e->ev_join2);
   if (e->cap_side) cudaStreamDestroy(e->cap_side);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
@@ -634,13 +640,24 @@ static int seq_begin_forward(dsk_engine* e, StepSlot& s) {
   bool capturing = e->qs == e->cap_stream;
   // tool kinematics of the whole step depends on the tool state and the action only: in a captured graph it runs
   // on a parallel branch next to the sort and the first p2g, joined before the first grid_op
-  if (e->K > 0) {
+  const bool next_kin = capturing && e->seq_next_slot != nullptr;
+  if (e->K > 0 && (!e->seq_skip_kin || next_kin)) {
     if (capturing) {
       CK(cudaEventRecord(e->ev_fork, e->qs));
       CK(cudaStreamWaitEvent(e->cap_side, e->ev_fork, 0));
-      KL(KID_KINEMATICS, k_kinematics<<<e->B, KIN_CTA, kin_smem(e), e->cap_side>>>(k, e->d_tools, e->d_args, e->rand_num, s.poses, s.cidx));
-      CK(cudaEventRecord(e->ev_join, e->cap_side));
-      e->kin_join = true;
+      if (!e->seq_skip_kin) {
+        KL(KID_KINEMATICS, k_kinematics<<<e->B, KIN_CTA, kin_smem(e), e->cap_side>>>(k, e->d_tools, e->d_args, e->rand_num, s.poses, s.cidx));
+        CK(cudaEventRecord(e->ev_join, e->cap_side));
+        e->kin_join = true;
+      }
+      if (next_kin) {   // lookahead: this step's tool checkpoint first, then the whole kinematics of the next step
+        StepSlot& nx = *e->seq_next_slot;
+        const StepArgs* na = e->d_args_kin + e->seq_next_step;
+        if (!e->seq_skip_kin) KL(KID_IO, k_tool_store<<<cdiv(e->B * e->K * 8, 128), 128, 0, e->cap_side>>>(k, s.poses, e->d_args));
+        KL(KID_KINEMATICS, k_kinematics<<<e->B, KIN_CTA, kin_smem(e), e->cap_side>>>(k, e->d_tools, na, e->rand_num, nx.poses, nx.cidx));
+        KL(KID_IO, k_tool_store<<<cdiv(e->B * e->K * 8, 128), 128, 0, e->cap_side>>>(k, nx.poses, na));
+        CK(cudaEventRecord(e->ev_join2, e->cap_side));
+      }
     } else {
       KL(KID_KINEMATICS, k_kinematics<<<e->B, KIN_CTA, kin_smem(e), e->qs>>>(k, e->d_tools, e->d_args, e->rand_num, s.poses, s.cidx));
     }
@@ -752,7 +769,9 @@ static int seq_end_forward(dsk_engine* e, StepSlot& s, bool store) {
   if (store) {
     KL(KID_REORDER, k_unsort<<<cdiv(k.stride, 256), 256, 0, e->qs>>>(k, s.frames + (size_t)e->S * e->frame_floats,
                                                                     e->npart, s.perm, &e->d_args->ck_dst, 0));
-    if (e->K > 0) KL(KID_IO, k_tool_store<<<cdiv(e->B * e->K * 8, 128), 128, 0, e->qs>>>(k, s.poses, e->d_args));
+    const bool next_kin = e->qs == e->cap_stream && e->seq_next_slot != nullptr && e->K > 0;
+    if (e->K > 0 && !e->seq_skip_kin && !next_kin) KL(KID_IO, k_tool_store<<<cdiv(e->B * e->K * 8, 128), 128, 0, e->qs>>>(k, s.poses, e->d_args));
+    if (next_kin) CK(cudaStreamWaitEvent(e->qs, e->ev_join2, 0));   // join the lookahead branch
   }
   LAUNCH_CHECK();
   return 0;
@@ -912,7 +931,11 @@ static int enqueue_backward_pipelined(dsk_engine* e, StepSlot& s) {
 }
 
 // ---- whole sequences, eager or as a replayed graph ---------------------------------------------------------------
-enum SeqKind { SEQ_FWD, SEQ_RECOMPUTE, SEQ_BWD, SEQ_BWD_TAPE, SEQ_BWD_TAPE_TRUSTED };
+// SEQ_FWD_NOKIN: forward step whose tool kinematics (and tool checkpoint) were produced ahead of time on the lookahead
+// stream by dsk_forward_steps
+// as is, or (LOOK_*) with the kinematics of the NEXT step on a side branch of this step's graph
+enum SeqKind { SEQ_FWD, SEQ_RECOMPUTE, SEQ_BWD, SEQ_BWD_TAPE, SEQ_BWD_TAPE_TRUSTED, SEQ_FWD_NOKIN, SEQ_FWD_LOOK_FIRST, SEQ_FWD_LOOK_MID };
+static bool is_fwd_kind(SeqKind k) { return k == SEQ_FWD || k == SEQ_FWD_NOKIN || k == SEQ_FWD_LOOK_FIRST || k == SEQ_FWD_LOOK_MID; }
 static int enqueue_sequence(dsk_engine* e, StepSlot& s, SeqKind kind) {
   if (kind == SEQ_BWD || kind == SEQ_BWD_TAPE || kind == SEQ_BWD_TAPE_TRUSTED) {
     e->seq_use_tape = kind != SEQ_BWD;
@@ -924,6 +947,8 @@ static int enqueue_sequence(dsk_engine* e, StepSlot& s, SeqKind kind) {
     if (seq_end_backward(e, s)) return -1;
     return seq_clear(e, e->S - 1, true);
   }
+  e->seq_skip_kin = kind == SEQ_FWD_NOKIN || kind == SEQ_FWD_LOOK_MID;
+  if (!(kind == SEQ_FWD_LOOK_FIRST || kind == SEQ_FWD_LOOK_MID)) e->seq_next_slot = nullptr;
   if (seq_begin_forward(e, s)) return -1;
   if (getenv("DSK_NO_G2P2G")) {
     for (int q = 0; q < e->S; q++)
@@ -931,14 +956,16 @@ static int enqueue_sequence(dsk_engine* e, StepSlot& s, SeqKind kind) {
   } else if (seq_forward_fused(e, s)) {
     return -1;
   }
-  if (seq_end_forward(e, s, kind == SEQ_FWD)) return -1;
+  if (seq_end_forward(e, s, is_fwd_kind(kind))) return -1;
+  e->seq_skip_kin = false;
+  e->seq_next_slot = nullptr;
   return seq_clear(e, e->S - 1, false);
 }
 static int run_sequence(dsk_engine* e, int slot_idx, SeqKind kind) {
   StepSlot& s = e->slot[slot_idx];
   if (flush_pending_clear(e)) return -1;
   e->grids_valid = false;
-  if (kind == SEQ_FWD || kind == SEQ_RECOMPUTE) {
+  if (is_fwd_kind(kind) || kind == SEQ_RECOMPUTE) {
     e->seq_full_sort = !e->cfg.sort_particles || e->sort_age >= e->resort_interval;
     e->sort_age = e->seq_full_sort ? 1 : e->sort_age + 1;
   } else {
@@ -1154,8 +1181,7 @@ int dsk_set_action(dsk_engine* e, int step, const float* actions, int on_device)
     if (s.action_step == step) s.src_step = -1;
   return 0;
 }
-int dsk_forward_step(dsk_engine* e, int src_step, int dst_step, int action_step) {
-  CKE(e);
+static int forward_step_impl(dsk_engine* e, int src_step, int dst_step, int action_step, SeqKind kind) {
   if (check_step(e, src_step, "dsk_forward_step") || check_step(e, dst_step, "dsk_forward_step")) return -1;
   if (action_step >= e->H) return fail("action step %d outside [0,%d)", action_step, e->H);
   int si = src_step % e->slots;
@@ -1163,7 +1189,7 @@ int dsk_forward_step(dsk_engine* e, int src_step, int dst_step, int action_step)
   if (push_args(e, make_args(e, src_step, dst_step, action_step, -1))) return -1;
   s.src_step = -1;
   s.action_step = action_step;
-  if (run_sequence(e, si, SEQ_FWD)) return -1;
+  if (run_sequence(e, si, kind)) return -1;
   s.tape_written = true;
   e->tape_flags_stale = true;
   invalidate_slots(e, dst_step);
@@ -1172,6 +1198,10 @@ int dsk_forward_step(dsk_engine* e, int src_step, int dst_step, int action_step)
   e->last_fwd_frame = -1;
   e->last_substep_slot = si;
   return 0;
+}
+int dsk_forward_step(dsk_engine* e, int src_step, int dst_step, int action_step) {
+  CKE(e);
+  return forward_step_impl(e, src_step, dst_step, action_step, SEQ_FWD);
 }
 int dsk_backward_step(dsk_engine* e, int step) {
   CKE(e);
@@ -1752,10 +1782,37 @@ int dsk_set_actions(dsk_engine* e, int step0, int nsteps, const float* actions, 
     if (s.action_step >= step0 && s.action_step < step0 + nsteps) s.src_step = -1;
   return 0;
 }
+// The tool trajectory never depends on the dough, and here the actions of all the steps are known up front: the
+// kinematics of every step (pose chain, tool-tool collision projections, tool checkpoints) runs ahead on its own
+// stream while the main stream simulates earlier steps, so it leaves the critical path even when a collision forces
+// the reference's sequential per-substep procedure.  Needs one step slot per env step (poses live in the slot).
 int dsk_forward_steps(dsk_engine* e, int step0, int nsteps) {
   CKE(e);
-  for (int s = step0; s < step0 + nsteps; s++)
-    if (dsk_forward_step(e, s, s + 1, s)) return -1;
+  if (nsteps <= 0) return 0;
+  if (step0 < 0 || step0 + nsteps > e->H) return fail("dsk_forward_steps: steps [%d,%d) outside [0,%d)", step0, step0 + nsteps, e->H);
+  bool look = e->K > 0 && e->use_graphs && !e->profiling && e->slots >= e->H && nsteps >= 2 && !getenv("DSK_NO_KIN_LOOKAHEAD");
+  if (!look) {
+    for (int s = step0; s < step0 + nsteps; s++)
+      if (forward_step_impl(e, s, s + 1, s, SEQ_FWD)) return -1;
+    return 0;
+  }
+  if (!e->d_args_kin) {   // pointers only, one entry per step: written once
+    DA(e->d_args_kin, e->H);
+    CK(cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming));
+    for (int s = 0; s < e->H; s++) KL(KID_IO, k_set_args<<<1, 1, 0, e->stream>>>(e->d_args_kin + s, make_args(e, s, s + 1, s, -1)));
+    LAUNCH_CHECK();
+  }
+  const int last = step0 + nsteps - 1;
+  for (int s = step0; s <= last; s++) {
+    SeqKind kind = s == last ? SEQ_FWD_NOKIN : (s == step0 ? SEQ_FWD_LOOK_FIRST : SEQ_FWD_LOOK_MID);
+    if (s < last) {
+      e->seq_next_slot = &e->slot[(s + 1) % e->slots];
+      e->seq_next_step = s + 1;
+    }
+    int rc = forward_step_impl(e, s, s + 1, s, kind);
+    e->seq_next_slot = nullptr;
+    if (rc) return -1;
+  }
   return 0;
 }
 int dsk_backward_steps(dsk_engine* e, int step_hi, int nsteps) {
