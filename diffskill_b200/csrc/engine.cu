@@ -248,14 +248,21 @@ static void fill_tool(ToolParams& T, const dsk_tool_desc& d) {
   T.prot_inv = Q4{inv * w, inv * -x, inv * -y, inv * -z};
   T.min_gap = (float)d.minimal_gap;
   T.max_gap = (float)d.maximal_gap;
-  if (d.type == DSK_TOOL_CAPSULE || d.type == DSK_TOOL_ROLLINGPIN_EXT)
+  // radius of a sphere around the contact-frame origin (tool position, or a jaw's position) that contains the shape
+  if (d.type == DSK_TOOL_CAPSULE || d.type == DSK_TOOL_ROLLINGPIN_EXT || d.type == DSK_TOOL_ROLLINGPIN ||
+      d.type == DSK_TOOL_GRIPPER2)
     T.bound_r = (float)(d.h / 2 + d.r);
   else if (d.type == DSK_TOOL_SPHERE)
     T.bound_r = (float)d.r;
+  else if (d.type == DSK_TOOL_CYLINDER)   // radial extent h, axial half extent r
+    T.bound_r = (float)std::sqrt(d.h * d.h + d.r * d.r);
+  else if (d.type == DSK_TOOL_TORUS)      // major + minor radius
+    T.bound_r = (float)(d.h + d.r);
   else
     T.bound_r = (float)std::sqrt(d.size[0] * d.size[0] + d.size[1] * d.size[1] + d.size[2] * d.size[2]);
   T.bound_r *= 1.001f;
 }
+static bool host_is_gripper(int type) { return type == DSK_TOOL_GRIPPER || type == DSK_TOOL_GRIPPER2; }
 // host mirror of build_frame_table: one contact frame per tool, two (the jaws) per gripper
 static void sync_grid_tools(dsk_engine* e) {
   GridTools& g = e->grid_tools;
@@ -263,7 +270,7 @@ static void sync_grid_tools(dsk_engine* e) {
   int n = 0;
   for (int t = 0; t < e->K; t++) {
     g.T[t] = e->h_tools[t];
-    if (e->h_tools[t].type == DSK_TOOL_GRIPPER) {
+    if (host_is_gripper(e->h_tools[t].type)) {
       if (n + 2 > MAX_FRAMES) break;
       g.ft.tool[n] = t; g.ft.flag[n++] = -1.f;
       g.ft.tool[n] = t; g.ft.flag[n++] = 1.f;
@@ -350,9 +357,9 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
   for (int i = 0; i < e->K; i++) {
     fill_tool(e->h_tools[i], c->tools[i]);
     e->A += c->tools[i].action_dim;
-    e->ncols += c->tools[i].type == DSK_TOOL_GRIPPER ? 2 : 1;
+    e->ncols += host_is_gripper(c->tools[i].type) ? 2 : 1;
     e->n_frames = std::max(1, e->ncols);
-    if (c->tools[i].type < 0 || c->tools[i].type > DSK_TOOL_SPHERE) {
+    if (c->tools[i].type < 0 || c->tools[i].type > DSK_TOOL_TORUS) {
       delete e;
       return fail("unknown tool type %d", c->tools[i].type);
     }

@@ -212,138 +212,7 @@ __global__ void k_clip_actions(float* dst, const float* src, int n) {
   if (i < n) dst[i] = fminf(1.f, fmaxf(-1.f, src[i]));
 }
 
-// ---- tool kinematics ---------------------------------------------------------------------------------------
-// forward_kinematics of one tool, primive_base.py:152-156 / primitives.py:120-136 / :456-460
-struct ToolVel {
-  float3 v, w;
-  float gap_vel;
-};
-// the axis-angle increments of a tool are the same for every substep of an env step (set_velocity,
-// primive_base.py:260-268): their quaternions are built once per step
-struct ToolRotInc {
-  Q4 a, b;   // RollingPinExt: a = w2quat(0,-dth,0), b = w2quat(0,dw,0); others: a = w2quat(w)
-};
-DSK_DEV ToolRotInc tool_rot_inc(const ToolParams& T, const ToolVel& u) {
-  ToolRotInc r;
-  if (T.type == DSK_TOOL_ROLLINGPIN_EXT) {
-    r.a = w2quat(f3(0.f, -u.v.y, 0.f));
-    r.b = w2quat(f3(0.f, u.v.x, 0.f));
-  } else {
-    r.a = w2quat(u.w);
-    r.b = r.a;
-  }
-  return r;
-}
-DSK_DEV Pose tool_fk_inc(const ToolParams& T, const Pose& P, const ToolVel& u, const ToolRotInc& r) {
-  Pose N;
-  N.gap = P.gap;
-  float3 step = u.v;
-  if (T.type == DSK_TOOL_ROLLINGPIN_EXT) {
-    float dw = u.v.x, dy = u.v.z;
-    float3 y_dir = qrot_rn(P.q, f3(0.f, -1.f, 0.f));
-    float3 x_dir = (dw * 0.03f + u.w.x) * cross(f3(0.f, 1.f, 0.f), y_dir);
-    x_dir.y = dy;
-    N.q = qmul(r.a, qmul(P.q, r.b));
-    step = x_dir;
-  } else if (T.type == DSK_TOOL_GRIPPER) {
-    N.gap = tmin(tmax(P.gap - u.gap_vel, T.min_gap), T.max_gap);
-    N.q = qmul(P.q, r.a);
-  } else {
-    N.q = qmul(r.a, P.q);
-  }
-  N.p = f3(tmax(tmin(P.p.x + step.x, T.hi[0]), T.lo[0]), tmax(tmin(P.p.y + step.y, T.hi[1]), T.lo[1]),
-           tmax(tmin(P.p.z + step.z, T.hi[2]), T.lo[2]));
-  return N;
-}
-DSK_DEV Pose tool_fk(const ToolParams& T, const Pose& P, const ToolVel& u) {
-  Pose N;
-  N.gap = P.gap;
-  float3 step = u.v;
-  if (T.type == DSK_TOOL_ROLLINGPIN_EXT) {
-    float dw = u.v.x, dth = u.v.y, dy = u.v.z;
-    float3 y_dir = qrot_rn(P.q, f3(0.f, -1.f, 0.f));
-    float3 x_dir = (dw * 0.03f + u.w.x) * cross(f3(0.f, 1.f, 0.f), y_dir);
-    x_dir.y = dy;
-    N.q = qmul(w2quat(f3(0.f, -dth, 0.f)), qmul(P.q, w2quat(f3(0.f, dw, 0.f))));
-    step = x_dir;
-  } else if (T.type == DSK_TOOL_GRIPPER) {
-    N.gap = tmin(tmax(P.gap - u.gap_vel, T.min_gap), T.max_gap);
-    N.q = qmul(P.q, w2quat(u.w));
-  } else {
-    N.q = qmul(w2quat(u.w), P.q);
-  }
-  N.p = f3(tmax(tmin(P.p.x + step.x, T.hi[0]), T.lo[0]), tmax(tmin(P.p.y + step.y, T.hi[1]), T.lo[1]),
-           tmax(tmin(P.p.z + step.z, T.hi[2]), T.lo[2]));
-  return N;
-}
-// adjoint of tool_fk: given g(N) accumulates g(P), g(u)
-DSK_DEV void tool_fk_adj(const ToolParams& T, const Pose& P, const ToolVel& u, const PoseAdj& gN, PoseAdj& gP,
-                         ToolVel& gu) {
-  float3 step = u.v;
-  float3 y_dir = f3(0, 0, 0), cr = f3(0, 0, 0);
-  float sc = 0.f;
-  if (T.type == DSK_TOOL_ROLLINGPIN_EXT) {
-    y_dir = qrot_rn(P.q, f3(0.f, -1.f, 0.f));
-    cr = cross(f3(0.f, 1.f, 0.f), y_dir);
-    sc = u.v.x * 0.03f + u.w.x;
-    step = sc * cr;
-    step.y = u.v.z;
-  }
-  // position clamp: max(min(a, hi), lo)
-  float3 gstep;
-  {
-    float a0 = P.p.x + step.x, a1 = P.p.y + step.y, a2 = P.p.z + step.z;
-    float g0 = (a0 < T.hi[0] && T.lo[0] < tmin(a0, T.hi[0])) ? gN.p.x : 0.f;
-    float g1 = (a1 < T.hi[1] && T.lo[1] < tmin(a1, T.hi[1])) ? gN.p.y : 0.f;
-    float g2 = (a2 < T.hi[2] && T.lo[2] < tmin(a2, T.hi[2])) ? gN.p.z : 0.f;
-    gstep = f3(g0, g1, g2);
-    gP.p += gstep;
-  }
-  if (T.type == DSK_TOOL_ROLLINGPIN_EXT) {
-    float dw = u.v.x, dth = u.v.y;
-    // step = (sc*cr.x, dy, sc*cr.z)
-    gu.v.z += gstep.y;
-    float gsc = gstep.x * cr.x + gstep.z * cr.z;
-    float3 gcr = f3(sc * gstep.x, 0.f, sc * gstep.z);
-    gu.v.x += 0.03f * gsc;
-    gu.w.x += gsc;
-    // cr = e_y x y_dir  -> g(y_dir) = gcr x e_y
-    float3 gy = cross(gcr, f3(0.f, 1.f, 0.f));
-    float3 gdummy = f3(0, 0, 0);
-    qrot_adj(P.q, f3(0.f, -1.f, 0.f), gy, gP.q, gdummy);
-    // N.q = qmul(qa, qmul(P.q, qb)), qa = w2quat(0,-dth,0), qb = w2quat(0,dw,0)
-    Q4 qa = w2quat(f3(0.f, -dth, 0.f)), qb = w2quat(f3(0.f, dw, 0.f));
-    Q4 inner = qmul(P.q, qb);
-    Q4 gqa = {0, 0, 0, 0}, ginner = {0, 0, 0, 0}, gqb = {0, 0, 0, 0};
-    qmul_adj(qa, inner, gN.q, gqa, ginner);
-    qmul_adj(P.q, qb, ginner, gP.q, gqb);
-    float3 ga = f3(0, 0, 0), gb = f3(0, 0, 0);
-    w2quat_adj(f3(0.f, -dth, 0.f), gqa, ga);
-    w2quat_adj(f3(0.f, dw, 0.f), gqb, gb);
-    gu.v.y += -ga.y;
-    gu.v.x += gb.y;
-  } else if (T.type == DSK_TOOL_GRIPPER) {
-    gu.v += gstep;
-    float a = P.gap - u.gap_vel;
-    float m1 = tmax(a, T.min_gap);
-    float g = (m1 < T.max_gap) ? gN.gap : 0.f;     // min(m1, max_gap): m1 gets it iff m1 < max_gap
-    g = (T.min_gap < a) ? g : 0.f;                 // max(a, min_gap): a gets it iff min_gap < a
-    gP.gap += g;
-    gu.gap_vel -= g;
-    Q4 qw = w2quat(u.w);
-    Q4 gqw = {0, 0, 0, 0};
-    qmul_adj(P.q, qw, gN.q, gP.q, gqw);
-    w2quat_adj(u.w, gqw, gu.w);
-  } else {
-    gu.v += gstep;
-    Q4 qw = w2quat(u.w);
-    Q4 gqw = {0, 0, 0, 0};
-    qmul_adj(qw, P.q, gN.q, gqw, gP.q);
-    w2quat_adj(u.w, gqw, gu.w);
-  }
-  if (T.type != DSK_TOOL_GRIPPER) gP.gap += gN.gap;
-}
-
+// ---- tool kinematics: tool_fk / tool_fk_adj / action_to_vel live in tools.cuh ---------------------------------
 DSK_DEV void store_pose(float* s, const Pose& P) {
   s[0] = P.p.x; s[1] = P.p.y; s[2] = P.p.z;
   s[3] = P.q.w; s[4] = P.q.x; s[5] = P.q.y; s[6] = P.q.z;
@@ -357,20 +226,6 @@ DSK_DEV float3 surface_point(const ToolParams& Tj, const Pose& Pj, const float* 
   q.z = tmax(tmin(mul_rn(rn[2], Tj.size[2]), Tj.size[2]), -Tj.size[2]);
   return add3_rn(qrot_rn(Pj.q, q), Pj.p);
 }
-DSK_DEV ToolVel action_to_vel(const ToolParams& T, const float* a, int S) {  // set_velocity, primive_base.py:260-268
-  ToolVel u;
-  u.v = f3(0, 0, 0);
-  u.w = f3(0, 0, 0);
-  u.gap_vel = 0.f;
-  float fs = (float)S;
-  if (T.action_dim > 0) {
-    u.v = f3(a[0] * T.action_scale[0] / fs, a[1] * T.action_scale[1] / fs, a[2] * T.action_scale[2] / fs);
-    if (T.action_dim > 3) u.w = f3(a[3] * T.action_scale[3] / fs, a[4] * T.action_scale[4] / fs, a[5] * T.action_scale[5] / fs);
-    if (T.type == DSK_TOOL_GRIPPER) u.gap_vel = a[6] * T.action_scale[6] / fs;
-  }
-  return u;
-}
-
 // tool states of the last substep frame -> destination checkpoint
 __global__ void k_tool_store(SimConst k, const float* __restrict__ poses, const StepArgs* __restrict__ args) {
   DSK_TL(k);
@@ -474,10 +329,10 @@ __global__ void __launch_bounds__(KIN_CTA)
       Pose Pi = load_pose(sAll + (size_t)(j + 1) * per + ti * 8), Pj = load_pose(sAll + (size_t)(j + 1) * per + tj * 8);
       // the frames of tool i and their normalised inverse rotations are shared by the 600 points of the query
       const ToolParams& Ti = sT[ti];
-      bool grip = Ti.type == DSK_TOOL_GRIPPER;
+      bool grip = is_gripper(Ti.type);
       Frame Fa = grip ? jaw_frame(Pi, -1.f) : tool_frame(Pi), Fb = grip ? jaw_frame(Pi, 1.f) : Fa;
       Q4 qa = qconj_normalized_rn(Fa.q);
-      int kind = grip ? SDF_BOX : sdf_kind(Ti.type);
+      int kind = sdf_kind(Ti.type);
       float best = 0.f;
       int bi = -1;
       for (int q = lane; q < DSK_NUM_COLLISION_POINTS; q += 32) {
@@ -539,10 +394,10 @@ __global__ void __launch_bounds__(KIN_CTA)
         int ti = k.pairs[c][0], tj = k.pairs[c][1];
         Pose Pi = load_pose(sPre[ti]), Pj = load_pose(sPre[tj]);
         const ToolParams& Ti = sT[ti];   // tool_sdf with the frames and their inverse rotation hoisted, as in (2)
-        bool grip = Ti.type == DSK_TOOL_GRIPPER;
+        bool grip = is_gripper(Ti.type);
         Frame Fa = grip ? jaw_frame(Pi, -1.f) : tool_frame(Pi), Fb = grip ? jaw_frame(Pi, 1.f) : Fa;
         Q4 qa = qconj_normalized_rn(Fa.q);
-        int kind = grip ? SDF_BOX : sdf_kind(Ti.type);
+        int kind = sdf_kind(Ti.type);
         for (int q = wq * 32 + lane; q < DSK_NUM_COLLISION_POINTS; q += wpp * 32) {
           float3 pt = surface_point(sT[tj], Pj, sRand + ((size_t)c * DSK_NUM_COLLISION_POINTS + q) * 3);
           float d = local_sdf(Ti, kind, qrot_rn(qa, sub3_rn(pt, Fa.o)));
@@ -595,8 +450,8 @@ __global__ void __launch_bounds__(KIN_CTA)
           Pose Pi = load_pose(sP[ti]);
           // d = tool_sdf, nr = tool_normal (primitives.py:489-496 picks the jaw with da <= db), frames built once
           const ToolParams& Ti = sT[ti];
-          bool grip = Ti.type == DSK_TOOL_GRIPPER;
-          int kind = grip ? SDF_BOX : sdf_kind(Ti.type);
+          bool grip = is_gripper(Ti.type);
+          int kind = sdf_kind(Ti.type);
           Frame Fa = grip ? jaw_frame(Pi, -1.f) : tool_frame(Pi);
           Q4 qa = qconj_normalized_rn(Fa.q);
           float3 pl = qrot_rn(qa, sub3_rn(pt, Fa.o));

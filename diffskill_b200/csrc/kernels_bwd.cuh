@@ -207,7 +207,7 @@ DSK_DEV void frame_pose_adjoint(const SimConst& k, const ToolParams* sT, const F
     FrameAdj a0 = frame_adj_zero(), a1 = frame_adj_zero();
     if (c.influence >= 0.f) {
       const ToolParams& T = sT[ft.tool[y]];
-      int kind = ft.flag[y] != 0.f ? SDF_BOX : sdf_kind(T.type);
+      int kind = sdf_kind(T.type);
       // D = qrot(q0, n/L)
       float3 Nl = (1.f / c.L) * c.nraw, gNl = f3(0, 0, 0);
       qrot_adj(tf.F0[y].q, Nl, gD, a0.q, gNl);
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
       if (y < ft.n) {
         if (live && tf.active[y]) {
           const ToolParams& T = sT[ft.tool[y]];
-          contact_geometry(T, ft.flag[y] != 0.f ? SDF_BOX : sdf_kind(T.type), tf.F0[y], tf.F1[y], gp, k.dt, geo[y][l]);
+          contact_geometry(T, sdf_kind(T.type), tf.F0[y], tf.F1[y], gp, k.dt, geo[y][l]);
           if (geo[y][l].influence >= 0.f) any_contact[y] = 1;
         } else {
           geo[y][l].influence = -1.f;
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
     if (fl) {
       if (live && tf.active[y]) {
         const ToolParams& T = sT[ft.tool[y]];
-        contact_geometry(T, ft.flag[y] != 0.f ? SDF_BOX : sdf_kind(T.type), tf.F0[y], tf.F1[y], gp, k.dt, c);
+        contact_geometry(T, sdf_kind(T.type), tf.F0[y], tf.F1[y], gp, k.dt, c);
       }
       const float* d = sc.data + ((size_t)(it * ft.n + y) * 7) * GRID_NODES + l;
       gD = f3(d[0 * GRID_NODES], d[1 * GRID_NODES], d[2 * GRID_NODES]);
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4)
       const ToolParams& T = sT[ft.tool[f]];
       geo[na].influence = -1.f;
       if (live) {
-        contact_geometry(T, ft.flag[f] != 0.f ? SDF_BOX : sdf_kind(T.type), wf[w].F0[f], wf[w].F1[f], gp, k.dt, geo[na]);
+        contact_geometry(T, sdf_kind(T.type), wf[w].F0[f], wf[w].F1[f], gp, k.dt, geo[na]);
         vs[na] = v;
         if (geo[na].influence >= 0.f)
           v = contact_response(v, geo[na].D, geo[na].cv, geo[na].influence, T.friction, ft.flag[f] != 0.f);
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4)
         g = contact_response_adj(vs[a], c.D, c.cv, c.influence, T.friction, ft.flag[f] != 0.f, g, gD, gcv, ginfl);
         // influence = min(exp(-dist*softness), 1): exp(..) = influence when it is < 1
         float gdist = (c.influence < 1.f) ? (-T.softness * c.influence * ginfl) : 0.f;
-        int kind = ft.flag[f] != 0.f ? SDF_BOX : sdf_kind(T.type);
+        int kind = sdf_kind(T.type);
         // D = qrot(q0, n/L)
         float3 Nl = (1.f / c.L) * c.nraw, gNl = f3(0, 0, 0);
         qrot_adj(wf[w].F0[f].q, Nl, gD, a0.q, gNl);
@@ -891,7 +891,7 @@ __global__ void __launch_bounds__(KINADJ_CTA)
       ga[4] += gu[4] * (T.action_scale[4] / fs);
       ga[5] += gu[5] * (T.action_scale[5] / fs);
     }
-    if (T.type == DSK_TOOL_GRIPPER) ga[6] += gu[6] * (T.action_scale[6] / fs);
+    if (is_gripper(T.type)) ga[6] += gu[6] * (T.action_scale[6] / fs);
   }
 }
 
@@ -915,9 +915,9 @@ __global__ void k_min_dist(SimConst k, const ToolParams* __restrict__ tools, con
   for (int t = 0; t < k.K; t++) {
     ToolParams T = tools[t];
     Pose P = load_pose(tool_state + ((size_t)env * k.K + t) * 8);
-    if (T.type == DSK_TOOL_GRIPPER) {
-      o[col++] = frame_sdf(T, SDF_BOX, jaw_frame(P, -1.f), x);
-      o[col++] = frame_sdf(T, SDF_BOX, jaw_frame(P, 1.f), x);
+    if (is_gripper(T.type)) {
+      o[col++] = frame_sdf(T, sdf_kind(T.type), jaw_frame(P, -1.f), x);
+      o[col++] = frame_sdf(T, sdf_kind(T.type), jaw_frame(P, 1.f), x);
     } else {
       o[col++] = tool_sdf(T, P, x);
     }
@@ -941,18 +941,18 @@ __global__ void k_min_dist_adj(SimConst k, const ToolParams* __restrict__ tools,
     PoseAdj gP = pose_adj_zero();
     if (live) {
       Pose P = load_pose(tool_state + ((size_t)env * k.K + t) * 8);
-      if (T.type == DSK_TOOL_GRIPPER) {
+      if (is_gripper(T.type)) {
         FrameAdj fa = frame_adj_zero();
-        frame_sdf_adj(T, SDF_BOX, jaw_frame(P, -1.f), x, g[col], fa, gx);
+        frame_sdf_adj(T, sdf_kind(T.type), jaw_frame(P, -1.f), x, g[col], fa, gx);
         jaw_frame_adj(P, -1.f, fa, gP);
         fa = frame_adj_zero();
-        frame_sdf_adj(T, SDF_BOX, jaw_frame(P, 1.f), x, g[col + 1], fa, gx);
+        frame_sdf_adj(T, sdf_kind(T.type), jaw_frame(P, 1.f), x, g[col + 1], fa, gx);
         jaw_frame_adj(P, 1.f, fa, gP);
       } else {
         tool_sdf_adj(T, P, x, g[col], gP, gx);
       }
     }
-    col += T.type == DSK_TOOL_GRIPPER ? 2 : 1;
+    col += is_gripper(T.type) ? 2 : 1;
     float vals[8] = {gP.p.x, gP.p.y, gP.p.z, gP.q.w, gP.q.x, gP.q.y, gP.q.z, gP.gap};
 #pragma unroll
     for (int q = 0; q < 8; q++) {

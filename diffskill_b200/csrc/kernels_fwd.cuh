@@ -276,7 +276,7 @@ struct FrameTable {   // built once per CTA
 DSK_DEV void build_frame_table(const SimConst& k, const ToolParams* sT, FrameTable& ft) {
   int n = 0;
   for (int t = 0; t < k.K; t++) {
-    if (sT[t].type == DSK_TOOL_GRIPPER) {
+    if (is_gripper(sT[t].type)) {
       ft.tool[n] = t; ft.flag[n++] = -1.f;
       ft.tool[n] = t; ft.flag[n++] = 1.f;
     } else {
@@ -317,7 +317,7 @@ DSK_DEV int prepare_frame(const SimConst& k, const ToolParams* sT, const FrameTa
   F0 = frame_of_pose(P0, ft.flag[y]);
   F1 = frame_of_pose(P1, ft.flag[y]);
   const ToolParams& T = sT[t];
-  int kind = ft.flag[y] != 0.f ? SDF_BOX : sdf_kind(T.type);
+  int kind = sdf_kind(T.type);
   float3 c = f3(((float)(tx * 4) + 1.5f) * k.dx, ((float)(ty * 4) + 1.5f) * k.dx, ((float)(tz * 4) + 1.5f) * k.dx);
   float reach = 2.6f * k.dx * 1.02f + 1e-4f + (T.softness > 0.f ? 2.302586f / T.softness : 0.f);
   // cheap bounding-sphere test first, exact SDF only for tiles near the tool.  All SDFs here are 1-Lipschitz:
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
       if (y < ft.n) {
         if (live && tf.active[y]) {
           const ToolParams& T = sT[ft.tool[y]];
-          contact_geometry(T, ft.flag[y] != 0.f ? SDF_BOX : sdf_kind(T.type), tf.F0[y], tf.F1[y], gp, k.dt, geo[y][l]);
+          contact_geometry(T, sdf_kind(T.type), tf.F0[y], tf.F1[y], gp, k.dt, geo[y][l]);
         } else {
           geo[y][l].influence = -1.f;
         }
@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4)
         int f = __ffs(m) - 1;
         const ToolParams& T = sT[ft.tool[f]];
         ContactGeom c;
-        contact_geometry(T, ft.flag[f] != 0.f ? SDF_BOX : sdf_kind(T.type), wf[w].F0[f], wf[w].F1[f], gp, k.dt, c);
+        contact_geometry(T, sdf_kind(T.type), wf[w].F0[f], wf[w].F1[f], gp, k.dt, c);
         if (c.influence >= 0.f) v = contact_response(v, c.D, c.cv, c.influence, T.friction, ft.flag[f] != 0.f);
       }
       vout = grid_boundary(k, I0, I1, I2, v);

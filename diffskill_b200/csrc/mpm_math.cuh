@@ -3,9 +3,15 @@
 // arithmetic is ill-conditioned (cell indexing, finite-difference SDF normals), so
 // that the CUDA path and the CPU oracle round identically (DESIGN.md "Numerics").
 #pragma once
+#ifdef DSK_HOST_CHECK
+// tests/host_check: the tool math (this header + tools.cuh) compiled by g++ for the CPU test suite, so that the device
+// functions can be checked against the oracle without a GPU.  Never part of the product library.
+#include "../../tests/host_check/cuda_shim.h"
+#else
 #include <cuda_runtime.h>
 
 #define DSK_DEV __device__ __forceinline__
+#endif
 
 struct Q4 {
   float w, x, y, z;
@@ -233,8 +239,10 @@ DSK_DEV float3 mTv(const M3& A, float3 x) {
 }
 
 // warp helpers
+#ifndef DSK_HOST_CHECK
 DSK_DEV float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+#endif

@@ -76,13 +76,27 @@ DSK_DEV FrameAdj frame_adj_zero() {
 // SDF_SPHERE (primitives.py:23-41): the reference evaluates length(p - position) - radius in WORLD space; here it is
 // |R^-1 (p - position)| - radius in the tool frame like every other shape -- the same number up to an fp32 rounding of
 // the rotation, and the rotation adjoint it produces is zero to the same rounding.
-enum { SDF_CAPSULE = 0, SDF_BOX = 1, SDF_KNIFE = 2, SDF_SPHERE = 3 };
+// SDF_CYLINDER (primitives.py:302-336): T.h = radial, T.r = axial half extent.  SDF_TORUS (primitives.py:337-365):
+// major radius tx in T.h, minor radius ty in T.r.  Both have analytic normals.
+enum { SDF_CAPSULE = 0, SDF_BOX = 1, SDF_KNIFE = 2, SDF_SPHERE = 3, SDF_CYLINDER = 4, SDF_TORUS = 5 };
+// the local shape of a tool's contact frame(s): the tool itself, or one jaw of a Gripper (box jaws, primitives.py:475-483)
+// / Gripper2 (capsule jaws, primitives.py:607-615)
 DSK_DEV int sdf_kind(int tool_type) {
-  if (tool_type == DSK_TOOL_SPHERE) return SDF_SPHERE;
-  return (tool_type == DSK_TOOL_CAPSULE || tool_type == DSK_TOOL_ROLLINGPIN_EXT)
-             ? SDF_CAPSULE
-             : (tool_type == DSK_TOOL_KNIFE ? SDF_KNIFE : SDF_BOX);
+  switch (tool_type) {
+    case DSK_TOOL_CAPSULE:
+    case DSK_TOOL_ROLLINGPIN_EXT:
+    case DSK_TOOL_ROLLINGPIN:
+    case DSK_TOOL_GRIPPER2: return SDF_CAPSULE;
+    case DSK_TOOL_KNIFE: return SDF_KNIFE;
+    case DSK_TOOL_SPHERE: return SDF_SPHERE;
+    case DSK_TOOL_CYLINDER: return SDF_CYLINDER;
+    case DSK_TOOL_TORUS: return SDF_TORUS;
+    default: return SDF_BOX;   // Box, Gripper
+  }
 }
+// tools with two jaws applied sequentially, a gap state and a 7-D action (primitives.py:428, :576)
+DSK_DEV bool is_gripper(int tool_type) { return tool_type == DSK_TOOL_GRIPPER || tool_type == DSK_TOOL_GRIPPER2; }
+DSK_DEV bool is_rollingpin(int tool_type) { return tool_type == DSK_TOOL_ROLLINGPIN_EXT || tool_type == DSK_TOOL_ROLLINGPIN; }
 
 // ---- local SDFs (value) ----------------------------------------------------------------------
 DSK_DEV float len14_rn(float3 v) { return __fsqrt_rn(add_rn(dot_rn(v, v), 1e-14f)); }
@@ -104,10 +118,22 @@ DSK_DEV float prism_sdf(const ToolParams& T, float3 p0) {  // primitives.py:711-
   float a = add_rn(mul_rn(fabsf(p.x), 0.866025f), mul_rn(p.y, 0.5f));
   return tmax(sub_rn(fabsf(p.z), T.prism_h1), sub_rn(tmax(a, -p.y), mul_rn(T.prism_h0, 0.5f)));
 }
+DSK_DEV float len14_2_rn(float a, float b) { return __fsqrt_rn(add_rn(add_rn(mul_rn(a, a), mul_rn(b, b)), 1e-14f)); }
+DSK_DEV float cylinder_sdf(const ToolParams& T, float3 p) {  // primitives.py:309-313
+  float l = len14_2_rn(p.x, p.z);
+  float d0 = sub_rn(fabsf(l), T.h), d1 = sub_rn(fabsf(p.y), T.r);
+  return add_rn(tmin(tmax(d0, d1), 0.f), len14_2_rn(tmax(d0, 0.f), tmax(d1, 0.f)));
+}
+DSK_DEV float torus_sdf(const ToolParams& T, float3 p) {  // primitives.py:344-347
+  float q0 = sub_rn(len14_2_rn(p.x, p.z), T.h);
+  return sub_rn(len14_2_rn(q0, p.y), T.r);
+}
 DSK_DEV float local_sdf(const ToolParams& T, int kind, float3 p) {
   if (kind == SDF_CAPSULE) return sub_rn(len14_rn(capsule_p2(T, p)), T.r);
   if (kind == SDF_BOX) return box_sdf(T, p);
   if (kind == SDF_SPHERE) return sub_rn(len14_rn(p), T.r);   // primitives.py:28-30
+  if (kind == SDF_CYLINDER) return cylinder_sdf(T, p);
+  if (kind == SDF_TORUS) return torus_sdf(T, p);
   return tmax(prism_sdf(T, p), box_sdf(T, p));  // primitives.py:769-773
 }
 
@@ -159,16 +185,92 @@ DSK_DEV float3 prism_sdf_grad(const ToolParams& T, float3 p0) {
   qrot_adj(T.prot_inv, p0, g, gq, gp0);
   return gp0;
 }
+DSK_DEV float3 cylinder_sdf_grad(const ToolParams& T, float3 p) {
+  float l = sqrtf(p.x * p.x + p.z * p.z + 1e-14f);
+  float d0 = l - T.h, d1 = fabsf(p.y) - T.r;   // |l| = l: l > 0
+  float g0 = 0.f, g1 = 0.f;
+  if (tmax(d0, d1) < 0.f) {  // min(max(d0,d1), 0): the max gets it iff it is < 0; max(a,b) -> a iff b < a
+    if (d1 < d0) g0 += 1.f;
+    else g1 += 1.f;
+  }
+  float m0 = tmax(d0, 0.f), m1 = tmax(d1, 0.f);
+  float L = sqrtf(m0 * m0 + m1 * m1 + 1e-14f);
+  if (0.f < d0) g0 += m0 / L;
+  if (0.f < d1) g1 += m1 / L;
+  return f3(g0 * p.x / l, g1 * sgnf(p.y), g0 * p.z / l);
+}
+DSK_DEV float3 torus_sdf_grad(const ToolParams& T, float3 p) {
+  float l = sqrtf(p.x * p.x + p.z * p.z + 1e-14f);
+  float q0 = l - T.h;
+  float lq = sqrtf(q0 * q0 + p.y * p.y + 1e-14f);
+  float gl = q0 / lq;
+  return f3(gl * p.x / l, p.y / lq, gl * p.z / l);
+}
 DSK_DEV float3 local_sdf_grad(const ToolParams& T, int kind, float3 p) {
   if (kind == SDF_CAPSULE) return capsule_sdf_grad(T, p);
   if (kind == SDF_BOX) return box_sdf_grad(T, p);
   if (kind == SDF_SPHERE) return (1.f / sqrtf(dot(p, p) + 1e-14f)) * p;
+  if (kind == SDF_CYLINDER) return cylinder_sdf_grad(T, p);
+  if (kind == SDF_TORUS) return torus_sdf_grad(T, p);
   float a = prism_sdf(T, p), b = box_sdf(T, p);
   return (b < a) ? prism_sdf_grad(T, p) : box_sdf_grad(T, p);
 }
 
 // ---- local normals ---------------------------------------------------------------------------------
 #define DSK_FD_D 1e-4f
+// Cylinder._normal before the final normalize (primitives.py:315-328)
+DSK_DEV float3 cylinder_n3(const ToolParams& T, float3 p) {
+  float l = len14_2_rn(p.x, p.z);
+  float d0 = sub_rn(l, T.h), d1 = sub_rn(fabsf(p.y), T.r);
+  float f = d0 > d1 ? 1.f : 0.f;
+  float inside = tmax(d0, d1) <= 0.f ? 1.f : 0.f;
+  float n20 = add_rn(tmax(d0, 0.f), mul_rn(inside, f)), n21 = add_rn(tmax(d1, 0.f), mul_rn(inside, sub_rn(1.f, f)));
+  float ln = len14_2_rn(n20, n21);
+  float a = __fdiv_rn(n20, ln), b = __fdiv_rn(n21, ln);
+  float sy = p.y >= 0.f ? 1.f : -1.f;
+  return f3(mul_rn(__fdiv_rn(p.x, l), a), mul_rn(b, sy), mul_rn(__fdiv_rn(p.z, l), a));
+}
+// adjoint of n3 = cylinder_n3(p) wrt p; the casts (f, inside, sy) carry no gradient
+DSK_DEV float3 cylinder_n3_adj(const ToolParams& T, float3 p, float3 g) {
+  float l = sqrtf(p.x * p.x + p.z * p.z + 1e-14f);
+  float d0 = l - T.h, d1 = fabsf(p.y) - T.r;
+  float f = d0 > d1 ? 1.f : 0.f;
+  float inside = tmax(d0, d1) <= 0.f ? 1.f : 0.f;
+  float n20 = tmax(d0, 0.f) + inside * f, n21 = tmax(d1, 0.f) + inside * (1.f - f);
+  float ln = sqrtf(n20 * n20 + n21 * n21 + 1e-14f);
+  float a = n20 / ln;
+  float sy = p.y >= 0.f ? 1.f : -1.f;
+  float p20 = p.x / l, p21 = p.z / l;
+  float gp20 = g.x * a, gp21 = g.z * a;
+  float ga = g.x * p20 + g.z * p21, gb = g.y * sy;
+  float gln = -(ga * n20 + gb * n21) / (ln * ln);
+  float gn20 = ga / ln + gln * n20 / ln, gn21 = gb / ln + gln * n21 / ln;
+  float gl = (0.f < d0) ? gn20 : 0.f;          // max(d0, 0): d0 gets it iff 0 < d0
+  float gy = ((0.f < d1) ? gn21 : 0.f) * sgnf(p.y);
+  gl -= (gp20 * p.x + gp21 * p.z) / (l * l);   // p2 = (x, z) / l
+  return f3(gp20 / l + gl * p.x / l, gy, gp21 / l + gl * p.z / l);
+}
+// Torus._normal before the final normalize (primitives.py:349-357)
+DSK_DEV float3 torus_n3(const ToolParams& T, float3 p) {
+  float l = len14_2_rn(p.x, p.z);
+  float q0 = sub_rn(l, T.h);
+  float lq = len14_2_rn(q0, p.y);
+  float n20 = __fdiv_rn(q0, lq), n21 = __fdiv_rn(p.y, lq);
+  return f3(mul_rn(__fdiv_rn(p.x, l), n20), n21, mul_rn(__fdiv_rn(p.z, l), n20));
+}
+DSK_DEV float3 torus_n3_adj(const ToolParams& T, float3 p, float3 g) {
+  float l = sqrtf(p.x * p.x + p.z * p.z + 1e-14f);
+  float q0 = l - T.h, q1 = p.y;
+  float lq = sqrtf(q0 * q0 + q1 * q1 + 1e-14f);
+  float n20 = q0 / lq;
+  float x20 = p.x / l, x21 = p.z / l;
+  float gx20 = g.x * n20, gx21 = g.z * n20;
+  float gn20 = g.x * x20 + g.z * x21, gn21 = g.y;
+  float glq = -(gn20 * q0 + gn21 * q1) / (lq * lq);
+  float gq0 = gn20 / lq + glq * q0 / lq, gq1 = gn21 / lq + glq * q1 / lq;
+  float gl = gq0 - (gx20 * p.x + gx21 * p.z) / (l * l);
+  return f3(gx20 / l + gl * p.x / l, gq1, gx21 / l + gl * p.z / l);
+}
 DSK_DEV float3 local_normal_raw(const ToolParams& T, int kind, float3 p, float& L) {
   // returns the un-normalised n and its length (eps 1e-14)
   float3 n;
@@ -176,6 +278,10 @@ DSK_DEV float3 local_normal_raw(const ToolParams& T, int kind, float3 p, float& 
     n = capsule_p2(T, p);
   } else if (kind == SDF_SPHERE) {  // primitives.py:32-34: normalize(p)
     n = p;
+  } else if (kind == SDF_CYLINDER) {
+    n = cylinder_n3(T, p);
+  } else if (kind == SDF_TORUS) {
+    n = torus_n3(T, p);
   } else {  // primitives.py:382-393 / 796-807
     const float d = DSK_FD_D;
     const float c = __fdiv_rn(0.5f, d);
@@ -204,6 +310,8 @@ DSK_DEV float3 local_normal_adj(const ToolParams& T, int kind, float3 p, float3 
     return f3(gn.x, dyy * gn.y, gn.z);
   }
   if (kind == SDF_SPHERE) return gn;   // n = p
+  if (kind == SDF_CYLINDER) return cylinder_n3_adj(T, p, gn);
+  if (kind == SDF_TORUS) return torus_n3_adj(T, p, gn);
   const float d = DSK_FD_D;
   const float c = 0.5f / d;
   float3 gp = f3(0, 0, 0);
@@ -223,6 +331,8 @@ DSK_DEV float3 local_normal_adj_cached(const ToolParams& T, int kind, float3 p, 
     return f3(gn.x, dyy * gn.y, gn.z);
   }
   if (kind == SDF_SPHERE) return gn;   // n = p
+  if (kind == SDF_CYLINDER) return cylinder_n3_adj(T, p, gn);
+  if (kind == SDF_TORUS) return torus_n3_adj(T, p, gn);
   const float d = DSK_FD_D;
   const float c = 0.5f / d;
   float3 gp = f3(0, 0, 0);
@@ -410,9 +520,10 @@ DSK_DEV void tool_frame_adj(const FrameAdj& gF, PoseAdj& gP) {
 
 // Primitive.collide / Gripper.collide for one tool at one grid node
 DSK_DEV float3 tool_collide(const ToolParams& T, const Pose& P0, const Pose& P1, float3 p, float3 v, float dt) {
-  if (T.type == DSK_TOOL_GRIPPER) {  // primitives.py:507-511: jaws applied sequentially
-    v = contact_forward(T, SDF_BOX, jaw_frame(P0, -1.f), jaw_frame(P1, -1.f), p, v, dt, true);
-    v = contact_forward(T, SDF_BOX, jaw_frame(P0, 1.f), jaw_frame(P1, 1.f), p, v, dt, true);
+  if (is_gripper(T.type)) {  // primitives.py:507-511 / :636-640: jaws applied sequentially
+    const int jk = sdf_kind(T.type);
+    v = contact_forward(T, jk, jaw_frame(P0, -1.f), jaw_frame(P1, -1.f), p, v, dt, true);
+    v = contact_forward(T, jk, jaw_frame(P0, 1.f), jaw_frame(P1, 1.f), p, v, dt, true);
     return v;
   }
   return contact_forward(T, sdf_kind(T.type), tool_frame(P0), tool_frame(P1), p, v, dt, false);
@@ -420,12 +531,13 @@ DSK_DEV float3 tool_collide(const ToolParams& T, const Pose& P0, const Pose& P1,
 // adjoint; v is the velocity ENTERING this tool
 DSK_DEV float3 tool_collide_adj(const ToolParams& T, const Pose& P0, const Pose& P1, float3 p, float3 v, float dt,
                                 float3 gout, PoseAdj& g0, PoseAdj& g1) {
-  if (T.type == DSK_TOOL_GRIPPER) {
+  if (is_gripper(T.type)) {
+    const int jk = sdf_kind(T.type);
     Frame a0 = jaw_frame(P0, -1.f), a1 = jaw_frame(P1, -1.f), b0 = jaw_frame(P0, 1.f), b1 = jaw_frame(P1, 1.f);
-    float3 vmid = contact_forward(T, SDF_BOX, a0, a1, p, v, dt, true);
+    float3 vmid = contact_forward(T, jk, a0, a1, p, v, dt, true);
     FrameAdj ga0 = frame_adj_zero(), ga1 = frame_adj_zero(), gb0 = frame_adj_zero(), gb1 = frame_adj_zero();
-    float3 gmid = contact_adjoint(T, SDF_BOX, b0, b1, p, vmid, dt, true, gout, gb0, gb1);
-    float3 gin = contact_adjoint(T, SDF_BOX, a0, a1, p, v, dt, true, gmid, ga0, ga1);
+    float3 gmid = contact_adjoint(T, jk, b0, b1, p, vmid, dt, true, gout, gb0, gb1);
+    float3 gin = contact_adjoint(T, jk, a0, a1, p, v, dt, true, gmid, ga0, ga1);
     jaw_frame_adj(P0, 1.f, gb0, g0);
     jaw_frame_adj(P1, 1.f, gb1, g1);
     jaw_frame_adj(P0, -1.f, ga0, g0);
@@ -441,20 +553,20 @@ DSK_DEV float3 tool_collide_adj(const ToolParams& T, const Pose& P0, const Pose&
 
 // Primitive.sdf / Gripper.sdf and normals at tool level (collision projection, min-dist observation)
 DSK_DEV float tool_sdf(const ToolParams& T, const Pose& P, float3 p) {
-  if (T.type == DSK_TOOL_GRIPPER)
-    return tmin(frame_sdf(T, SDF_BOX, jaw_frame(P, -1.f), p), frame_sdf(T, SDF_BOX, jaw_frame(P, 1.f), p));
+  if (is_gripper(T.type))
+    return tmin(frame_sdf(T, sdf_kind(T.type), jaw_frame(P, -1.f), p), frame_sdf(T, sdf_kind(T.type), jaw_frame(P, 1.f), p));
   return frame_sdf(T, sdf_kind(T.type), tool_frame(P), p);
 }
 DSK_DEV void tool_sdf_adj(const ToolParams& T, const Pose& P, float3 p, float gd, PoseAdj& gP, float3& gp) {
-  if (T.type == DSK_TOOL_GRIPPER) {
+  if (is_gripper(T.type)) {
     Frame a = jaw_frame(P, -1.f), b = jaw_frame(P, 1.f);
-    float da = frame_sdf(T, SDF_BOX, a, p), db = frame_sdf(T, SDF_BOX, b, p);
+    float da = frame_sdf(T, sdf_kind(T.type), a, p), db = frame_sdf(T, sdf_kind(T.type), b, p);
     FrameAdj g = frame_adj_zero();
     if (da < db) {
-      frame_sdf_adj(T, SDF_BOX, a, p, gd, g, gp);
+      frame_sdf_adj(T, sdf_kind(T.type), a, p, gd, g, gp);
       jaw_frame_adj(P, -1.f, g, gP);
     } else {
-      frame_sdf_adj(T, SDF_BOX, b, p, gd, g, gp);
+      frame_sdf_adj(T, sdf_kind(T.type), b, p, gd, g, gp);
       jaw_frame_adj(P, 1.f, g, gP);
     }
     return;
@@ -464,23 +576,23 @@ DSK_DEV void tool_sdf_adj(const ToolParams& T, const Pose& P, float3 p, float gd
   tool_frame_adj(g, gP);
 }
 DSK_DEV float3 tool_normal(const ToolParams& T, const Pose& P, float3 p) {
-  if (T.type == DSK_TOOL_GRIPPER) {  // primitives.py:489-496
+  if (is_gripper(T.type)) {  // primitives.py:489-496
     Frame a = jaw_frame(P, -1.f), b = jaw_frame(P, 1.f);
-    float da = frame_sdf(T, SDF_BOX, a, p), db = frame_sdf(T, SDF_BOX, b, p);
-    return (da <= db) ? frame_normal(T, SDF_BOX, a, p) : frame_normal(T, SDF_BOX, b, p);
+    float da = frame_sdf(T, sdf_kind(T.type), a, p), db = frame_sdf(T, sdf_kind(T.type), b, p);
+    return (da <= db) ? frame_normal(T, sdf_kind(T.type), a, p) : frame_normal(T, sdf_kind(T.type), b, p);
   }
   return frame_normal(T, sdf_kind(T.type), tool_frame(P), p);
 }
 DSK_DEV void tool_normal_adj(const ToolParams& T, const Pose& P, float3 p, float3 gN, PoseAdj& gP, float3& gp) {
-  if (T.type == DSK_TOOL_GRIPPER) {
+  if (is_gripper(T.type)) {
     Frame a = jaw_frame(P, -1.f), b = jaw_frame(P, 1.f);
-    float da = frame_sdf(T, SDF_BOX, a, p), db = frame_sdf(T, SDF_BOX, b, p);
+    float da = frame_sdf(T, sdf_kind(T.type), a, p), db = frame_sdf(T, sdf_kind(T.type), b, p);
     FrameAdj g = frame_adj_zero();
     if (da <= db) {
-      frame_normal_adj(T, SDF_BOX, a, p, gN, g, gp);
+      frame_normal_adj(T, sdf_kind(T.type), a, p, gN, g, gp);
       jaw_frame_adj(P, -1.f, g, gP);
     } else {
-      frame_normal_adj(T, SDF_BOX, b, p, gN, g, gp);
+      frame_normal_adj(T, sdf_kind(T.type), b, p, gN, g, gp);
       jaw_frame_adj(P, 1.f, g, gP);
     }
     return;
@@ -488,4 +600,156 @@ DSK_DEV void tool_normal_adj(const ToolParams& T, const Pose& P, float3 p, float
   FrameAdj g = frame_adj_zero();
   frame_normal_adj(T, sdf_kind(T.type), tool_frame(P), p, gN, g, gp);
   tool_frame_adj(g, gP);
+}
+
+// ---- tool kinematics ---------------------------------------------------------------------------------------
+// forward_kinematics of one tool, primive_base.py:152-156 / primitives.py:120-136 / :456-460
+struct ToolVel {
+  float3 v, w;
+  float gap_vel;
+};
+// the axis-angle increments of a tool are the same for every substep of an env step (set_velocity,
+// primive_base.py:260-268): their quaternions are built once per step
+struct ToolRotInc {
+  Q4 a, b;   // RollingPinExt: a = w2quat(0,-dth,0), b = w2quat(0,dw,0); others: a = w2quat(w)
+};
+// RollingPinExt slides along its rolling direction by w[0] on top of the roll dw * 0.03 (primitives.py:129); the plain
+// RollingPin only rolls (primitives.py:110)
+DSK_DEV float rollingpin_slide(const ToolParams& T, const ToolVel& u) { return T.type == DSK_TOOL_ROLLINGPIN_EXT ? u.w.x : 0.f; }
+DSK_DEV ToolRotInc tool_rot_inc(const ToolParams& T, const ToolVel& u) {
+  ToolRotInc r;
+  if (is_rollingpin(T.type)) {
+    r.a = w2quat(f3(0.f, -u.v.y, 0.f));
+    r.b = w2quat(f3(0.f, u.v.x, 0.f));
+  } else {
+    r.a = w2quat(u.w);
+    r.b = r.a;
+  }
+  return r;
+}
+DSK_DEV Pose tool_fk_inc(const ToolParams& T, const Pose& P, const ToolVel& u, const ToolRotInc& r) {
+  Pose N;
+  N.gap = P.gap;
+  float3 step = u.v;
+  if (is_rollingpin(T.type)) {
+    float dw = u.v.x, dy = u.v.z;
+    float3 y_dir = qrot_rn(P.q, f3(0.f, -1.f, 0.f));
+    float3 cr = cross(f3(0.f, 1.f, 0.f), y_dir);
+    float3 x_dir = T.type == DSK_TOOL_ROLLINGPIN_EXT ? (dw * 0.03f + u.w.x) * cr      // primitives.py:129
+                                                     : 0.03f * (dw * cr);              // primitives.py:110
+    x_dir.y = dy;
+    N.q = qmul(r.a, qmul(P.q, r.b));
+    step = x_dir;
+  } else if (is_gripper(T.type)) {
+    N.gap = tmin(tmax(P.gap - u.gap_vel, T.min_gap), T.max_gap);
+    N.q = qmul(P.q, r.a);
+  } else {
+    N.q = qmul(r.a, P.q);
+  }
+  N.p = f3(tmax(tmin(P.p.x + step.x, T.hi[0]), T.lo[0]), tmax(tmin(P.p.y + step.y, T.hi[1]), T.lo[1]),
+           tmax(tmin(P.p.z + step.z, T.hi[2]), T.lo[2]));
+  return N;
+}
+DSK_DEV Pose tool_fk(const ToolParams& T, const Pose& P, const ToolVel& u) {
+  Pose N;
+  N.gap = P.gap;
+  float3 step = u.v;
+  if (is_rollingpin(T.type)) {
+    float dw = u.v.x, dth = u.v.y, dy = u.v.z;
+    float3 y_dir = qrot_rn(P.q, f3(0.f, -1.f, 0.f));
+    float3 cr = cross(f3(0.f, 1.f, 0.f), y_dir);
+    float3 x_dir = T.type == DSK_TOOL_ROLLINGPIN_EXT ? (dw * 0.03f + u.w.x) * cr      // primitives.py:129
+                                                     : 0.03f * (dw * cr);              // primitives.py:110
+    x_dir.y = dy;
+    N.q = qmul(w2quat(f3(0.f, -dth, 0.f)), qmul(P.q, w2quat(f3(0.f, dw, 0.f))));
+    step = x_dir;
+  } else if (is_gripper(T.type)) {
+    N.gap = tmin(tmax(P.gap - u.gap_vel, T.min_gap), T.max_gap);
+    N.q = qmul(P.q, w2quat(u.w));
+  } else {
+    N.q = qmul(w2quat(u.w), P.q);
+  }
+  N.p = f3(tmax(tmin(P.p.x + step.x, T.hi[0]), T.lo[0]), tmax(tmin(P.p.y + step.y, T.hi[1]), T.lo[1]),
+           tmax(tmin(P.p.z + step.z, T.hi[2]), T.lo[2]));
+  return N;
+}
+// adjoint of tool_fk: given g(N) accumulates g(P), g(u)
+DSK_DEV void tool_fk_adj(const ToolParams& T, const Pose& P, const ToolVel& u, const PoseAdj& gN, PoseAdj& gP,
+                         ToolVel& gu) {
+  float3 step = u.v;
+  float3 y_dir = f3(0, 0, 0), cr = f3(0, 0, 0);
+  float sc = 0.f;
+  if (is_rollingpin(T.type)) {
+    y_dir = qrot_rn(P.q, f3(0.f, -1.f, 0.f));
+    cr = cross(f3(0.f, 1.f, 0.f), y_dir);
+    sc = u.v.x * 0.03f + rollingpin_slide(T, u);
+    step = sc * cr;
+    step.y = u.v.z;
+  }
+  // position clamp: max(min(a, hi), lo)
+  float3 gstep;
+  {
+    float a0 = P.p.x + step.x, a1 = P.p.y + step.y, a2 = P.p.z + step.z;
+    float g0 = (a0 < T.hi[0] && T.lo[0] < tmin(a0, T.hi[0])) ? gN.p.x : 0.f;
+    float g1 = (a1 < T.hi[1] && T.lo[1] < tmin(a1, T.hi[1])) ? gN.p.y : 0.f;
+    float g2 = (a2 < T.hi[2] && T.lo[2] < tmin(a2, T.hi[2])) ? gN.p.z : 0.f;
+    gstep = f3(g0, g1, g2);
+    gP.p += gstep;
+  }
+  if (is_rollingpin(T.type)) {
+    float dw = u.v.x, dth = u.v.y;
+    // step = (sc*cr.x, dy, sc*cr.z)
+    gu.v.z += gstep.y;
+    float gsc = gstep.x * cr.x + gstep.z * cr.z;
+    float3 gcr = f3(sc * gstep.x, 0.f, sc * gstep.z);
+    gu.v.x += 0.03f * gsc;
+    if (T.type == DSK_TOOL_ROLLINGPIN_EXT) gu.w.x += gsc;
+    // cr = e_y x y_dir  -> g(y_dir) = gcr x e_y
+    float3 gy = cross(gcr, f3(0.f, 1.f, 0.f));
+    float3 gdummy = f3(0, 0, 0);
+    qrot_adj(P.q, f3(0.f, -1.f, 0.f), gy, gP.q, gdummy);
+    // N.q = qmul(qa, qmul(P.q, qb)), qa = w2quat(0,-dth,0), qb = w2quat(0,dw,0)
+    Q4 qa = w2quat(f3(0.f, -dth, 0.f)), qb = w2quat(f3(0.f, dw, 0.f));
+    Q4 inner = qmul(P.q, qb);
+    Q4 gqa = {0, 0, 0, 0}, ginner = {0, 0, 0, 0}, gqb = {0, 0, 0, 0};
+    qmul_adj(qa, inner, gN.q, gqa, ginner);
+    qmul_adj(P.q, qb, ginner, gP.q, gqb);
+    float3 ga = f3(0, 0, 0), gb = f3(0, 0, 0);
+    w2quat_adj(f3(0.f, -dth, 0.f), gqa, ga);
+    w2quat_adj(f3(0.f, dw, 0.f), gqb, gb);
+    gu.v.y += -ga.y;
+    gu.v.x += gb.y;
+  } else if (is_gripper(T.type)) {
+    gu.v += gstep;
+    float a = P.gap - u.gap_vel;
+    float m1 = tmax(a, T.min_gap);
+    float g = (m1 < T.max_gap) ? gN.gap : 0.f;     // min(m1, max_gap): m1 gets it iff m1 < max_gap
+    g = (T.min_gap < a) ? g : 0.f;                 // max(a, min_gap): a gets it iff min_gap < a
+    gP.gap += g;
+    gu.gap_vel -= g;
+    Q4 qw = w2quat(u.w);
+    Q4 gqw = {0, 0, 0, 0};
+    qmul_adj(P.q, qw, gN.q, gP.q, gqw);
+    w2quat_adj(u.w, gqw, gu.w);
+  } else {
+    gu.v += gstep;
+    Q4 qw = w2quat(u.w);
+    Q4 gqw = {0, 0, 0, 0};
+    qmul_adj(qw, P.q, gN.q, gqw, gP.q);
+    w2quat_adj(u.w, gqw, gu.w);
+  }
+  if (!is_gripper(T.type)) gP.gap += gN.gap;
+}
+DSK_DEV ToolVel action_to_vel(const ToolParams& T, const float* a, int S) {  // set_velocity, primive_base.py:260-268
+  ToolVel u;
+  u.v = f3(0, 0, 0);
+  u.w = f3(0, 0, 0);
+  u.gap_vel = 0.f;
+  float fs = (float)S;
+  if (T.action_dim > 0) {
+    u.v = f3(a[0] * T.action_scale[0] / fs, a[1] * T.action_scale[1] / fs, a[2] * T.action_scale[2] / fs);
+    if (T.action_dim > 3) u.w = f3(a[3] * T.action_scale[3] / fs, a[4] * T.action_scale[4] / fs, a[5] * T.action_scale[5] / fs);
+    if (is_gripper(T.type)) u.gap_vel = a[6] * T.action_scale[6] / fs;
+  }
+  return u;
 }

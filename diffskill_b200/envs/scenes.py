@@ -69,9 +69,59 @@ MOVE = dict(
     ENV=dict(env_name='Move-v1'),
 )
 
+# Legacy PlasticineLab scenes that exercise the remaining tools: first variants of
+# plb/envs/rollingpin.yml (RollingPin), torus.yml (Torus) and rope.yml (two Spheres + a static Cylinder pillar).
+ROLLINGPIN = dict(
+    SIMULATOR=dict(E=5000., n_particles=10000, yield_stress=50., ground_friction=1.5),
+    SHAPES=[dict(shape='box', width=(0.3, 0.1, 0.3), init_pos=(0.5, 0.05, 0.5), color=100)],
+    PRIMITIVES=[
+        dict(shape='RollingPin', h=0.3, r=0.03, init_pos=(0.5, 0.123, 0.5), init_rot=_TILT, color=(0.8, 0.8, 0.8),
+             friction=0.9, action=dict(dim=3, scale=(0.6666666666666667, 0.06666666666666668, 0.001))),
+    ],
+    ENV=dict(env_name='Rollingpin-v1'),
+)
+TORUS = dict(
+    SIMULATOR=dict(yield_stress=50., ground_friction=100.),
+    SHAPES=[dict(shape='box', width=(0.3, 0.1, 0.3), init_pos=(0.5, 0.05, 0.5), color=(((200 << 8) + 200) << 8))],
+    PRIMITIVES=[
+        dict(shape='Torus', tx=0.05, ty=0.03, init_pos=(0.5, 0.2, 0.5), init_rot=(0., 0., 0., 1.), friction=0.9,
+             color=(0.8, 0.8, 0.8), lower_bound=(0., 0.05, 0.), action=dict(dim=3, scale=(0.004, 0.004, 0.004))),
+    ],
+    ENV=dict(env_name='Torus-v1'),
+)
+ROPE = dict(
+    SIMULATOR=dict(yield_stress=50., ground_friction=0.3),
+    SHAPES=[dict(shape='box', width=(0.6, 0.06, 0.06), init_pos=(0.5, 0.03, 0.73), color=(((0 << 8) + 150) << 8))],
+    PRIMITIVES=[
+        dict(shape='Sphere', radius=0.03, init_pos=(0.22, 0.015, 0.82), color=(0.8, 0.8, 0.8), friction=0.9,
+             action=dict(dim=3, scale=(0.01, 0.01, 0.01))),
+        dict(shape='Sphere', radius=0.03, init_pos=(0.78, 0.015, 0.82), color=(0.8, 0.8, 0.8), friction=0.9,
+             action=dict(dim=3, scale=(0.01, 0.01, 0.01))),
+        dict(shape='Cylinder', h=0.1, r=0.2, init_pos=(0.3919300650726247, 0., 0.4990770359432596),
+             color=(0.3, 0.3, 0.3), friction=0.9),
+    ],
+    ENV=dict(env_name='Rope-v1'),
+)
+# No reference YAML instantiates Gripper2 (primitives.py:576-697, capsule jaws); this scene is the CutRearrange gripper
+# pose and action scales with capsule jaws, so that the tool is exercised by the same parity tests.
+GRIPPER2_SYNTHETIC = dict(
+    SIMULATOR=dict(E=5000., n_particles=10000, yield_stress=150., ground_friction=0.5, gravity=(0, -10, 0)),
+    SHAPES=[dict(shape='box', init_pos=(0.5, 0.06, 0.5), width=(0.12, 0.08, 0.08), color=100, n_particles=5000)],
+    PRIMITIVES=[
+        dict(shape='Gripper2', h=0.12, r=0.02, init_pos=(0.5, 0.08, 0.5), init_gap=0.18, minimal_gap=0.08,
+             maximal_gap=0.2, init_rot=(0.707, 0.0, 0.707, 0.0), color=_WOOD, friction=10.,
+             action=dict(dim=7, scale=(0.015, 0.015, 0.015, 0.02, 0.02, 0.02, 0.015))),
+    ],
+    ENV=dict(env_name='Gripper2-synthetic'),
+)
+
 SCENES = {
     'LiftSpread-v1': LIFT_SPREAD,
     'GatherMove-v1': GATHER_MOVE,
     'CutRearrange-v1': CUT_REARRANGE,
     'Move-v1': MOVE,
+    'Rollingpin-v1': ROLLINGPIN,
+    'Torus-v1': TORUS,
+    'Rope-v1': ROPE,
+    'Gripper2-synthetic': GRIPPER2_SYNTHETIC,
 }

@@ -13,9 +13,12 @@ import numpy as np
 
 from .config import CfgNode, load
 
-TOOL_CAPSULE, TOOL_ROLLINGPIN_EXT, TOOL_BOX, TOOL_GRIPPER, TOOL_KNIFE, TOOL_SPHERE = range(6)
+(TOOL_CAPSULE, TOOL_ROLLINGPIN_EXT, TOOL_BOX, TOOL_GRIPPER, TOOL_KNIFE, TOOL_SPHERE, TOOL_ROLLINGPIN, TOOL_GRIPPER2,
+ TOOL_CYLINDER, TOOL_TORUS) = range(10)
 TOOL_TYPE = {'Capsule': TOOL_CAPSULE, 'RollingPinExt': TOOL_ROLLINGPIN_EXT, 'Box': TOOL_BOX,
-             'Gripper': TOOL_GRIPPER, 'Knife': TOOL_KNIFE, 'Sphere': TOOL_SPHERE}
+             'Gripper': TOOL_GRIPPER, 'Knife': TOOL_KNIFE, 'Sphere': TOOL_SPHERE, 'RollingPin': TOOL_ROLLINGPIN,
+             'Gripper2': TOOL_GRIPPER2, 'Cylinder': TOOL_CYLINDER, 'Torus': TOOL_TORUS}
+GRIPPER_LIKE = (TOOL_GRIPPER, TOOL_GRIPPER2)      # two jaws, gap state, 8-float state (primitives.py:428, :576)
 NUM_COLLISION_POINTS = 600  # mpm_simulator.py:59
 
 
@@ -31,10 +34,18 @@ def _primitive_defaults(shape):
         d.update(size=(0.1, 0.1, 0.1))
     elif shape == 'Gripper':
         d.update(size=(0.03, 0.06, 0.03), minimal_gap=0.06, maximal_gap=1., init_gap=0.06, round=0)
+    elif shape == 'Gripper2':                                  # primitives.py:685-696
+        d.update(h=0.06, r=0.015, minimal_gap=0.06, maximal_gap=1., init_gap=0.06, round=0)
+    elif shape == 'Cylinder':                                  # primitives.py:331-336
+        d.update(h=0.2, r=0.1)
+    elif shape == 'Torus':                                     # primitives.py:360-365
+        d.update(tx=0.2, ty=0.1)
     elif shape == 'Knife':
         d.update(h=(0.1, 0.1), size=(0.1, 0.1, 0.1), prot=(1.0, 0.0, 0.0, 0.0))
     else:
-        raise NotImplementedError(f"tool shape {shape!r} is not on the DiffSkill hot path (SURVEY.md section 8f row 4)")
+        # Chopsticks (primitives.py:218-300): its SDF depends on gap[f] inside the tool frame while collider_v ignores the
+        # gap -- it does not fit the (frame, local shape) contact model of the grid kernels and no DiffSkill env uses it
+        raise NotImplementedError(f"tool shape {shape!r} is not built (SURVEY.md section 8f row 4)")
     return CfgNode(d)
 
 
@@ -61,7 +72,7 @@ class ToolSpec:
 
     @property
     def state_dim(self):
-        return 8 if self.type_id == TOOL_GRIPPER else 7
+        return 8 if self.type_id in GRIPPER_LIKE else 7
 
 
 def tool_from_cfg(c) -> ToolSpec:
@@ -77,8 +88,15 @@ def tool_from_cfg(c) -> ToolSpec:
                     upper_bound=tuple(map(float, cfg.upper_bound)),
                     collision_group=tuple(float(v) for v in cfg.collision_group))
     init = tuple(map(float, cfg.init_pos)) + tuple(map(float, cfg.init_rot))
-    if t in (TOOL_CAPSULE, TOOL_ROLLINGPIN_EXT):
+    if t in (TOOL_CAPSULE, TOOL_ROLLINGPIN_EXT, TOOL_ROLLINGPIN, TOOL_CYLINDER):
         spec.h, spec.r = float(cfg.h), float(cfg.r)
+    elif t == TOOL_TORUS:                                      # major / minor radius travel in (h, r)
+        spec.h, spec.r = float(cfg.tx), float(cfg.ty)
+    elif t == TOOL_GRIPPER2:
+        spec.h, spec.r = float(cfg.h), float(cfg.r)
+        spec.minimal_gap, spec.maximal_gap = float(cfg.minimal_gap), float(cfg.maximal_gap)
+        init = init + (float(cfg.init_gap),)
+        assert adim == 7, "Gripper2 needs a 7-D action (primitives.py:594-601)"
     elif t == TOOL_SPHERE:
         spec.radius = float(cfg.radius)
     elif t == TOOL_BOX:

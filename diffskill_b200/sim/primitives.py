@@ -205,6 +205,11 @@ class Capsule(Primitive):
         self.init_points = np.array([[r * np.cos(l2[k]), l1[l], r * np.sin(l2[k])] for k in range(n) for l in range(n)])
 
 
+class RollingPin(Capsule):
+    """primitives.py:101-117: rolls (dw), yaws about the world y (dth) and sinks (dy); 3-D action."""
+    shape = 'RollingPin'
+
+
 class RollingPinExt(Capsule):
     shape = 'RollingPinExt'
 
@@ -271,6 +276,37 @@ class Gripper(Box):
         return action
 
 
+class Gripper2(Capsule):
+    """primitives.py:576-697: the Gripper's kinematics and two-jaw contact with capsule jaws (h, r)."""
+    shape = 'Gripper2'
+    state_dim = 8
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        zero = self._zero_grads
+        self.gap = ToolFrameField(self, slice(7, 8), zero)
+        self.gap_vel = type('F', (), {'grad': ZeroOnFillGrad(zero)})()
+        self.minimal_gap, self.maximal_gap = self.cfg.minimal_gap, self.cfg.maximal_gap
+
+    @property
+    def init_state(self):
+        return tuple(self.cfg.init_pos) + tuple(self.cfg.init_rot) + (self.cfg.init_gap,)
+
+    def set_state(self, f, state, env=None):
+        assert len(state) == 8                                  # primitives.py:679
+        super().set_state(f, state, env)
+
+
+class Cylinder(Primitive):
+    """primitives.py:302-336 (cfg.h = radial, cfg.r = axial half extent); the base class's zero init_points."""
+    shape = 'Cylinder'
+
+
+class Torus(Primitive):
+    """primitives.py:337-365 (cfg.tx major, cfg.ty minor radius)."""
+    shape = 'Torus'
+
+
 class Knife(Primitive):
     shape = 'Knife'
 
@@ -296,7 +332,7 @@ class Knife(Primitive):
         return action
 
 
-_SHAPES = {c.shape: c for c in (Sphere, Capsule, RollingPinExt, Box, Gripper, Knife)}
+_SHAPES = {c.shape: c for c in (Sphere, Capsule, RollingPin, RollingPinExt, Box, Gripper, Gripper2, Cylinder, Torus, Knife)}
 
 
 class Primitives:
@@ -308,8 +344,8 @@ class Primitives:
         for i in cfgs:
             cfg = i if isinstance(i, CfgNode) else CfgNode(yaml.safe_load(yaml.safe_dump(dict(i))))
             if cfg.shape not in _SHAPES:
-                raise NotImplementedError(f"primitive {cfg.shape!r}: only the tools of the three DiffSkill envs and Sphere are built "
-                                          "(SURVEY.md section 8f row 4)")
+                raise NotImplementedError(f"primitive {cfg.shape!r} is not built: every tool of primitives.py except "
+                                          "Chopsticks is (SURVEY.md section 8f row 4)")
             p = _SHAPES[cfg.shape](cfg=cfg, max_timesteps=max_timesteps)
             self.primitives.append(p)
             self.action_dims.append(self.action_dims[-1] + p.action_dim)

@@ -43,7 +43,11 @@ enum dsk_tool_type {
   DSK_TOOL_BOX = 2,            /* primitives.py:359 */
   DSK_TOOL_GRIPPER = 3,        /* primitives.py:428 */
   DSK_TOOL_KNIFE = 4,          /* primitives.py:740 (Prism :700 + Box) */
-  DSK_TOOL_SPHERE = 5          /* primitives.py:23 (legacy PlasticineLab tool; radius in `r`) */
+  DSK_TOOL_SPHERE = 5,         /* primitives.py:23 (legacy PlasticineLab tool; radius in `r`) */
+  DSK_TOOL_ROLLINGPIN = 6,     /* primitives.py:101 (capsule; RollingPinExt kinematics without the w[0] slide) */
+  DSK_TOOL_GRIPPER2 = 7,       /* primitives.py:576 (Gripper with capsule jaws `h`, `r`) */
+  DSK_TOOL_CYLINDER = 8,       /* primitives.py:302 (`h` = radial, `r` = axial half extent, as the reference names them) */
+  DSK_TOOL_TORUS = 9           /* primitives.py:337 (major radius cfg.tx in `h`, minor radius cfg.ty in `r`) */
 };
 
 enum dsk_tool_param {
@@ -63,10 +67,10 @@ typedef struct dsk_tool_desc {
   double lower_bound[3];   /* cfg.lower_bound -> xyz_limit[0] */
   double upper_bound[3];   /* cfg.upper_bound -> xyz_limit[1] */
   double size[3];          /* Box / Gripper / Knife.box half extents */
-  double h, r;             /* Capsule; Sphere: r = cfg.radius */
+  double h, r;             /* Capsule / RollingPin(Ext) / Gripper2 jaws; Sphere: r = cfg.radius; Cylinder; Torus: (tx, ty) */
   double prism_h[2];       /* Knife.prism.h */
   double prot[4];          /* Knife.prism.prot */
-  double minimal_gap, maximal_gap; /* Gripper */
+  double minimal_gap, maximal_gap; /* Gripper, Gripper2 */
 } dsk_tool_desc;
 
 /* Scene + capacity.  Derived constants are passed as the python doubles the

@@ -180,6 +180,9 @@ inline S length14(const V3<S>& x) {  // primitives.py:13-15
 // ----------------------------------------------------------------------------
 // tools
 // ----------------------------------------------------------------------------
+inline bool is_gripper(int type) {  // tools with two jaws, a gap state and an 8-float state (primitives.py:428, :576)
+  return type == ORC_TOOL_GRIPPER || type == ORC_TOOL_GRIPPER2;
+}
 template <class T>
 struct ToolC {  // constants rounded to T as Taichi rounds python floats into fields/constants
   int type, action_dim;
@@ -221,12 +224,60 @@ inline S prism_sdf(const ToolC<T>& c, const V3<S>& p0) {  // primitives.py:711-7
   S q0 = s_abs(p[0]), q2 = s_abs(p[2]);
   return s_max(q2 - c.prism_h[1], s_max(q0 * T(0.866025) + p[1] * T(0.5), -p[1]) - c.prism_h[0] * T(0.5));
 }
+template <class S>
+inline S length14_2(const S& a, const S& b) {  // primitives.py:13-15 on a 2-vector
+  typedef typename real_of<S>::type T;
+  return s_sqrt(a * a + b * b + T(1e-14));
+}
+template <class S, class T>
+inline S cylinder_sdf(const ToolC<T>& c, const V3<S>& p) {  // primitives.py:309-313 (h = radial, r = axial half extent)
+  S l = length14_2(p[0], p[2]);
+  S d0 = s_abs(l) - c.h, d1 = s_abs(p[1]) - c.r;
+  return s_min(s_max(d0, d1), T(0)) + length14_2(s_max(d0, T(0)), s_max(d1, T(0)));
+}
+template <class S, class T>
+inline V3<S> cylinder_normal(const ToolC<T>& c, const V3<S>& p) {  // primitives.py:315-329
+  S l = length14_2(p[0], p[2]);
+  S d0 = l - c.h, d1 = s_abs(p[1]) - c.r;
+  T f = val(d0) > val(d1) ? T(1) : T(0);                       // casts: no gradient
+  T inside = val(s_max(d0, d1)) <= T(0) ? T(1) : T(0);
+  S n20 = s_max(d0, T(0)) + inside * f, n21 = s_max(d1, T(0)) + inside * (T(1) - f);
+  S ln = length14_2(n20, n21);
+  S a = n20 / ln, b = n21 / ln;
+  S p20 = p[0] / l, p21 = p[2] / l;
+  T sy = (val(p[1]) >= T(0) ? T(1) : T(0)) * T(2) - T(1);
+  V3<S> n3{{p20 * a, b * sy, p21 * a}};
+  S l3 = length14(n3);
+  return V3<S>{{n3[0] / l3, n3[1] / l3, n3[2] / l3}};
+}
+template <class S, class T>
+inline S torus_sdf(const ToolC<T>& c, const V3<S>& p) {  // primitives.py:344-347 (tx in h, ty in r)
+  S q0 = length14_2(p[0], p[2]) - c.h;
+  return length14_2(q0, p[1]) - c.r;
+}
+template <class S, class T>
+inline V3<S> torus_normal(const ToolC<T>& c, const V3<S>& p) {  // primitives.py:349-358
+  S l = length14_2(p[0], p[2]);
+  S q0 = length14_2(p[0], p[2]) - c.h, q1 = p[1];
+  S lq = length14_2(q0, q1);
+  S n20 = q0 / lq, n21 = q1 / lq;
+  S x20 = p[0] / l, x21 = p[2] / l;
+  V3<S> n3{{x20 * n20, n21, x21 * n20}};
+  S l3 = length14(n3);
+  return V3<S>{{n3[0] / l3, n3[1] / l3, n3[2] / l3}};
+}
 template <class S, class T>
 inline S local_sdf(const ToolC<T>& c, const V3<S>& p) {
   switch (c.type) {
     case ORC_TOOL_CAPSULE:
     case ORC_TOOL_ROLLINGPIN_EXT:
+    case ORC_TOOL_ROLLINGPIN:
+    case ORC_TOOL_GRIPPER2:
       return length14(capsule_p2(c, p)) - c.r;  // primitives.py:59
+    case ORC_TOOL_CYLINDER:
+      return cylinder_sdf(c, p);
+    case ORC_TOOL_TORUS:
+      return torus_sdf(c, p);
     case ORC_TOOL_BOX:
     case ORC_TOOL_GRIPPER:
       return box_sdf<S, T>(c.size, p);
@@ -238,7 +289,10 @@ inline S local_sdf(const ToolC<T>& c, const V3<S>& p) {
 }
 template <class S, class T>
 inline V3<S> local_normal(const ToolC<T>& c, const V3<S>& p) {
-  if (c.type == ORC_TOOL_CAPSULE || c.type == ORC_TOOL_ROLLINGPIN_EXT) {  // primitives.py:61-66
+  if (c.type == ORC_TOOL_CYLINDER) return cylinder_normal(c, p);
+  if (c.type == ORC_TOOL_TORUS) return torus_normal(c, p);
+  if (c.type == ORC_TOOL_CAPSULE || c.type == ORC_TOOL_ROLLINGPIN_EXT || c.type == ORC_TOOL_ROLLINGPIN ||
+      c.type == ORC_TOOL_GRIPPER2) {  // primitives.py:61-66
     V3<S> p2 = capsule_p2(c, p);
     S l = length14(p2);
     return V3<S>{{p2[0] / l, p2[1] / l, p2[2] / l}};
@@ -263,23 +317,25 @@ inline V3<S> gripper_pos(const Pose<S>& P, int flag) {  // primitives.py:471-473
 }
 template <class S, class T>
 inline S sdf2(const ToolC<T>& c, const Pose<S>& P, const V3<S>& p, int flag) {  // primitives.py:475-478
+  if (c.type == ORC_TOOL_GRIPPER2)  // primitives.py:607-610: Capsule._sdf
+    return length14(capsule_p2(c, inv_trans(p, gripper_pos(P, flag), P.rot))) - c.r;
   return box_sdf<S, T>(c.size, inv_trans(p, gripper_pos(P, flag), P.rot));
 }
 template <class S, class T>
 inline V3<S> normal2(const ToolC<T>& c, const Pose<S>& P, const V3<S>& p, int flag) {  // primitives.py:480-483
   ToolC<T> b = c;
-  b.type = ORC_TOOL_BOX;
+  b.type = c.type == ORC_TOOL_GRIPPER2 ? ORC_TOOL_CAPSULE : ORC_TOOL_BOX;  // primitives.py:612-615: Capsule._normal
   return qrot(P.rot, local_normal(b, inv_trans(p, gripper_pos(P, flag), P.rot)));
 }
 template <class S, class T>
 inline S tool_sdf(const ToolC<T>& c, const Pose<S>& P, const V3<S>& p) {
-  if (c.type == ORC_TOOL_GRIPPER) return s_min(sdf2(c, P, p, -1), sdf2(c, P, p, 1));  // primitives.py:485-487
+  if (is_gripper(c.type)) return s_min(sdf2(c, P, p, -1), sdf2(c, P, p, 1));  // primitives.py:485-487
   if (c.type == ORC_TOOL_SPHERE) return length14(p - P.pos) - c.radius;               // primitives.py:28-30
   return local_sdf(c, inv_trans(p, P.pos, P.rot));                                      // primive_base.py:75-78
 }
 template <class S, class T>
 inline V3<S> tool_normal(const ToolC<T>& c, const Pose<S>& P, const V3<S>& p) {
-  if (c.type == ORC_TOOL_GRIPPER) {  // primitives.py:489-496
+  if (is_gripper(c.type)) {  // primitives.py:489-496
     S a = sdf2(c, P, p, -1), b = sdf2(c, P, p, 1);
     V3<S> an = normal2(c, P, p, -1), bn = normal2(c, P, p, 1);
     T m = val(a) <= val(b) ? T(1) : T(0);
@@ -318,7 +374,7 @@ inline V3<S> contact_response(const V3<S>& v_out, const V3<S>& D, const V3<S>& c
 
 template <class S, class T>
 inline V3<S> tool_collide(const ToolC<T>& c, const Pose<S>& P0, const Pose<S>& P1, const V3<S>& p, V3<S> v_out, T dt) {
-  if (c.type == ORC_TOOL_GRIPPER) {  // primitives.py:507-536
+  if (is_gripper(c.type)) {  // primitives.py:507-536
     for (int flag = -1; flag <= 1; flag += 2) {
       S dist = sdf2(c, P0, p, flag);
       S influence = s_min(s_exp(-dist * c.softness), T(1));
@@ -353,17 +409,18 @@ inline Pose<S> tool_fk(const ToolC<T>& c, const Pose<S>& P, const V3<S>& v, cons
   Pose<S> N;
   N.gap = P.gap;
   V3<S> step = v;
-  if (c.type == ORC_TOOL_ROLLINGPIN_EXT) {  // primitives.py:120-136
+  if (c.type == ORC_TOOL_ROLLINGPIN_EXT || c.type == ORC_TOOL_ROLLINGPIN) {  // primitives.py:120-136 / :101-117
     S dw = v[0], dth = v[1], dy = v[2];
     V3<S> down{{S(T(0)), S(T(-1)), S(T(0))}};
     V3<S> y_dir = qrot(P.rot, down);
     V3<S> up{{S(T(0)), S(T(1)), S(T(0))}};
-    V3<S> x_dir = scale(cross(up, y_dir), dw * T(0.03) + w[0]);
+    V3<S> x_dir = c.type == ORC_TOOL_ROLLINGPIN ? scale(scale(cross(up, y_dir), dw), T(0.03))  // :110
+                                                : scale(cross(up, y_dir), dw * T(0.03) + w[0]);
     x_dir[1] = dy;
     V3<S> a1{{S(T(0)), -dth, S(T(0))}}, a2{{S(T(0)), dw, S(T(0))}};
     N.rot = qmul(w2quat(a1), qmul(P.rot, w2quat(a2)));
     step = x_dir;
-  } else if (c.type == ORC_TOOL_GRIPPER) {  // primitives.py:456-460
+  } else if (is_gripper(c.type)) {  // primitives.py:456-460
     N.gap = s_min(s_max(P.gap - gap_vel, c.min_gap), c.max_gap);
     N.rot = qmul(P.rot, w2quat(w));
   } else {  // primive_base.py:152-156
@@ -723,7 +780,7 @@ struct Sim {
       collision_idx.assign((size_t)frames * npairs, -1);
     }
     int ncols = 0;
-    for (int i = 0; i < K; i++) ncols += tools[i].c.type == ORC_TOOL_GRIPPER ? 2 : 1;
+    for (int i = 0; i < K; i++) ncols += is_gripper(tools[i].c.type) ? 2 : 1;
     dists.assign(ncols, std::vector<T>(cap, 0));
     g_dists = dists;
   }
@@ -1253,7 +1310,7 @@ struct Sim {
       for (int d = 0; d < 3; d++) t.vel[j * 3 + d] = a[d] * t.c.action_scale[d] / T(nsub);
       if (ad > 3)
         for (int d = 0; d < 3; d++) t.w[j * 3 + d] = a[d + 3] * t.c.action_scale[d + 3] / T(nsub);
-      if (t.c.type == ORC_TOOL_GRIPPER) t.gap_vel[j] = a[6] * t.c.action_scale[6] / T(nsub);
+      if (is_gripper(t.c.type)) t.gap_vel[j] = a[6] * t.c.action_scale[6] / T(nsub);
     }
   }
   void set_velocity_grad(int s, int nsub) {
@@ -1266,7 +1323,7 @@ struct Sim {
         for (int d = 0; d < 3; d++) ga[d] += t.g_vel[j * 3 + d] * (t.c.action_scale[d] / T(nsub));
         if (ad > 3)
           for (int d = 0; d < 3; d++) ga[d + 3] += t.g_w[j * 3 + d] * (t.c.action_scale[d + 3] / T(nsub));
-        if (t.c.type == ORC_TOOL_GRIPPER) ga[6] += t.g_gap_vel[j] * (t.c.action_scale[6] / T(nsub));
+        if (is_gripper(t.c.type)) ga[6] += t.g_gap_vel[j] * (t.c.action_scale[6] / T(nsub));
       }
     }
   }
@@ -1285,21 +1342,21 @@ struct Sim {
       Pose<T> P = load_pose<T>(j, f, false);
       for (int p = 0; p < n; p++) {
         V3<T> xx = load_v3<T>(x, (size_t)f * cap + p, false);
-        if (tools[j].c.type != ORC_TOOL_GRIPPER) {
+        if (!is_gripper(tools[j].c.type)) {
           dists[col][p] = tool_sdf<T, T>(tools[j].c, P, xx);
         } else {
           dists[col][p] = sdf2<T, T>(tools[j].c, P, xx, -1);
           dists[col + 1][p] = sdf2<T, T>(tools[j].c, P, xx, 1);
         }
       }
-      col += tools[j].c.type == ORC_TOOL_GRIPPER ? 2 : 1;
+      col += is_gripper(tools[j].c.type) ? 2 : 1;
     }
   }
   void compute_min_dist_grad(int f) {
     typedef Var<T> S;
     int col = 0;
     for (int j = 0; j < K; j++) {
-      bool grip = tools[j].c.type == ORC_TOOL_GRIPPER;
+      bool grip = is_gripper(tools[j].c.type);
       for (int p = 0; p < n; p++) {
         Tape<T>& tp = tape<T>();
         tp.clear();
@@ -1400,6 +1457,75 @@ static void add_in(std::vector<T>& dst, size_t off, const double* src, size_t cn
   for (size_t i = 0; i < cnt; i++) dst[off + i] += (T)src[i];
 }
 
+/* adjoint probes (tape AD of the same templates the .grad kernels use): out = [g(p) 3 | g(v_in) 3 | g(pose f) 8 | g(pose f+1) 8] */
+static const int PROBE_OUT = 22;
+template <class SimT>
+static void probe_grad(SimT& S, int tool, int f, int what, const double* p, const double* v_in, const double* gout,
+                       double* out) {
+  typedef decltype(S.k.dt) TT;
+  typedef Var<TT> VS;
+  Tape<TT>& tp = tape<TT>();
+  tp.clear();
+  V3<VS> pp{{VS::input((TT)p[0]), VS::input((TT)p[1]), VS::input((TT)p[2])}};
+  V3<VS> vv{{VS::input((TT)v_in[0]), VS::input((TT)v_in[1]), VS::input((TT)v_in[2])}};
+  Pose<VS> P0 = S.template load_pose<VS>(tool, f, true), P1 = S.template load_pose<VS>(tool, f + 1, true);
+  V3<VS> r3;
+  VS r1;
+  int nout = 3;
+  if (what == 0) {
+    r1 = tool_sdf<VS, TT>(S.tools[tool].c, P0, pp);
+    nout = 1;
+  } else if (what == 1) {
+    r3 = tool_normal<VS, TT>(S.tools[tool].c, P0, pp);
+  } else {
+    r3 = tool_collide<VS, TT>(S.tools[tool].c, P0, P1, pp, vv, S.k.dt);
+  }
+  tp.begin_reverse();
+  if (nout == 1) r1.seed((TT)gout[0]);
+  else for (int d = 0; d < 3; d++) r3[d].seed((TT)gout[d]);
+  tp.reverse();
+  for (int d = 0; d < 3; d++) out[d] = (double)pp[d].grad();
+  for (int d = 0; d < 3; d++) out[3 + d] = (double)vv[d].grad();
+  const Pose<VS>* Ps[2] = {&P0, &P1};
+  for (int q = 0; q < 2; q++) {
+    for (int d = 0; d < 3; d++) out[6 + q * 8 + d] = (double)Ps[q]->pos[d].grad();
+    for (int d = 0; d < 4; d++) out[6 + q * 8 + 3 + d] = (double)Ps[q]->rot[d].grad();
+    out[6 + q * 8 + 7] = (double)Ps[q]->gap.grad();
+  }
+}
+/* forward kinematics of one tool from an explicit (state8, vel7 = v3 w3 gap_vel); with gnext8 != NULL also the adjoint
+ * [g(state) 8 | g(vel) 7] */
+template <class SimT>
+static void probe_fk(SimT& S, int tool, const double* st, const double* vel, double* next8, const double* gnext8,
+                     double* gout15) {
+  typedef decltype(S.k.dt) TT;
+  typedef Var<TT> VS;
+  Tape<TT>& tp = tape<TT>();
+  tp.clear();
+  Pose<VS> P;
+  for (int d = 0; d < 3; d++) P.pos[d] = VS::input((TT)st[d]);
+  for (int d = 0; d < 4; d++) P.rot[d] = VS::input((TT)st[3 + d]);
+  P.gap = VS::input((TT)st[7]);
+  V3<VS> v{{VS::input((TT)vel[0]), VS::input((TT)vel[1]), VS::input((TT)vel[2])}};
+  V3<VS> w{{VS::input((TT)vel[3]), VS::input((TT)vel[4]), VS::input((TT)vel[5])}};
+  VS gv = VS::input((TT)vel[6]);
+  Pose<VS> N = tool_fk<VS, TT>(S.tools[tool].c, P, v, w, gv);
+  for (int d = 0; d < 3; d++) next8[d] = (double)val(N.pos[d]);
+  for (int d = 0; d < 4; d++) next8[3 + d] = (double)val(N.rot[d]);
+  next8[7] = (double)val(N.gap);
+  if (!gnext8) return;
+  tp.begin_reverse();
+  for (int d = 0; d < 3; d++) N.pos[d].seed((TT)gnext8[d]);
+  for (int d = 0; d < 4; d++) N.rot[d].seed((TT)gnext8[3 + d]);
+  N.gap.seed((TT)gnext8[7]);
+  tp.reverse();
+  for (int d = 0; d < 3; d++) gout15[d] = (double)P.pos[d].grad();
+  for (int d = 0; d < 4; d++) gout15[3 + d] = (double)P.rot[d].grad();
+  gout15[7] = (double)P.gap.grad();
+  for (int d = 0; d < 3; d++) gout15[8 + d] = (double)v[d].grad();
+  for (int d = 0; d < 3; d++) gout15[11 + d] = (double)w[d].grad();
+  gout15[14] = (double)gv.grad();
+}
 extern "C" {
 
 void* orc_create(const orc_config* cfg, int use_f64) {
@@ -1492,7 +1618,7 @@ void orc_copyframe(void* h, int src, int dst) {
     for (auto& t : S.tools) {
       for (int d = 0; d < 3; d++) t.pos[dst * 3 + d] = t.pos[src * 3 + d];
       for (int d = 0; d < 4; d++) t.rot[dst * 4 + d] = t.rot[src * 4 + d];
-      if (t.c.type == ORC_TOOL_GRIPPER) t.gap[dst] = t.gap[src];
+      if (is_gripper(t.c.type)) t.gap[dst] = t.gap[src];
     }
   });
 }
@@ -1560,7 +1686,7 @@ void orc_add_tool_grad(void* h, int f, int tool, const double* g8) {
     auto& t = S.tools[tool];
     add_in(t.g_pos, (size_t)f * 3, g8, 3);
     add_in(t.g_rot, (size_t)f * 4, g8 + 3, 4);
-    if (t.c.type == ORC_TOOL_GRIPPER) add_in(t.g_gap, (size_t)f, g8 + 7, 1);
+    if (is_gripper(t.c.type)) add_in(t.g_gap, (size_t)f, g8 + 7, 1);
   });
 }
 void orc_get_tool_vel_grad(void* h, int f, int tool, double* g7) {
@@ -1696,5 +1822,13 @@ void orc_tool_collide(void* h, int tool, int f, const double* p, const double* v
                                     S.template load_pose<TT>(tool, f + 1, false), pp, vv, S.k.dt);
     for (int d = 0; d < 3; d++) v_out[d] = (double)r[d];
   });
+}
+void orc_tool_probe_grad(void* h, int tool, int f, int what, const double* p, const double* v_in, const double* gout,
+                         double* out22) {
+  DISPATCH(h, { probe_grad(S, tool, f, what, p, v_in, gout, out22); });
+}
+void orc_tool_probe_fk(void* h, int tool, const double* state8, const double* vel7, double* next8,
+                       const double* gnext8, double* gout15) {
+  DISPATCH(h, { probe_fk(S, tool, state8, vel7, next8, gnext8, gout15); });
 }
 }

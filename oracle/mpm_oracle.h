@@ -31,7 +31,11 @@ enum orc_tool_type {
   ORC_TOOL_BOX = 2,            /* primitives.py:359 */
   ORC_TOOL_GRIPPER = 3,        /* primitives.py:428 */
   ORC_TOOL_KNIFE = 4,          /* primitives.py:740 */
-  ORC_TOOL_SPHERE = 5          /* primitives.py:23  */
+  ORC_TOOL_SPHERE = 5,         /* primitives.py:23  */
+  ORC_TOOL_ROLLINGPIN = 6,     /* primitives.py:101 */
+  ORC_TOOL_GRIPPER2 = 7,       /* primitives.py:576 (capsule jaws) */
+  ORC_TOOL_CYLINDER = 8,       /* primitives.py:302 (h = radial, r = axial half extent) */
+  ORC_TOOL_TORUS = 9           /* primitives.py:337 (tx in h, ty in r) */
 };
 
 typedef struct orc_tool_cfg {
@@ -42,7 +46,7 @@ typedef struct orc_tool_cfg {
   double softness;
   double lower_bound[3], upper_bound[3]; /* xyz_limit */
   double size[3];                        /* Box / Gripper / Knife.box half extents */
-  double h, r;                           /* Capsule */
+  double h, r;                           /* Capsule, RollingPin, Gripper2 jaws; Cylinder (h, r); Torus (tx, ty) */
   double radius;                         /* Sphere */
   double prism_h[2];                     /* Knife.prism.h */
   double prot[4];                        /* Knife.prism.prot */
@@ -115,6 +119,13 @@ void orc_svd3(int use_f64, const double* F, double* U, double* sig, double* V);
 double orc_tool_sdf(void* h, int tool, int f, const double* p);
 void orc_tool_normal(void* h, int tool, int f, const double* p, double* n);
 void orc_tool_collide(void* h, int tool, int f, const double* p, const double* v_in, double* v_out);
+/* tape-AD adjoint of tool_sdf (what = 0, gout[1]), tool_normal (1, gout[3]) or tool_collide (2, gout[3]) at poses f, f+1:
+ * out22 = [g(p) 3 | g(v_in) 3 | g(pose f) 8 | g(pose f+1) 8] */
+void orc_tool_probe_grad(void* h, int tool, int f, int what, const double* p, const double* v_in, const double* gout,
+                         double* out22);
+/* forward_kinematics of one tool from (state8, vel7 = v3 w3 gap_vel); gnext8 != NULL: also [g(state) 8 | g(vel) 7] */
+void orc_tool_probe_fk(void* h, int tool, const double* state8, const double* vel7, double* next8,
+                       const double* gnext8, double* gout15);
 
 #ifdef __cplusplus
 }

@@ -284,6 +284,32 @@ class Oracle:
         self.L.orc_tool_normal(self.h, i, f, _d(p)[1], _d(n)[1])
         return n
 
+    def tool_probe_grad(self, i, f, what, p, v, gout):
+        """Tape-AD adjoint of tool_sdf ('sdf'), tool_normal ('normal') or tool_collide ('collide') of tool i at poses
+        f, f+1 -> (g_p[3], g_v_in[3], g_pose_f[8], g_pose_f1[8])."""
+        out = np.zeros(22)
+        g = np.zeros(3)
+        g[:np.size(gout)] = np.ravel(gout)
+        pa, pp = _d(p)
+        va, vp = _d(v)
+        ga, gp = _d(g)
+        self.L.orc_tool_probe_grad(self.h, int(i), int(f), {'sdf': 0, 'normal': 1, 'collide': 2}[what], pp, vp, gp,
+                                   out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out[0:3], out[3:6], out[6:14], out[14:22]
+
+    def tool_probe_fk(self, i, state8, vel7, gnext8=None):
+        """forward_kinematics of tool i from an explicit state -> next8 (and (g_state[8], g_vel[7]) with gnext8)."""
+        sa, sp = _d(state8)
+        va, vp = _d(vel7)
+        nxt, g = np.zeros(8), np.zeros(15)
+        if gnext8 is None:
+            self.L.orc_tool_probe_fk(self.h, int(i), sp, vp, nxt.ctypes.data_as(C.POINTER(C.c_double)), None, None)
+            return nxt
+        ga, gp = _d(gnext8)
+        self.L.orc_tool_probe_fk(self.h, int(i), sp, vp, nxt.ctypes.data_as(C.POINTER(C.c_double)), gp,
+                                 g.ctypes.data_as(C.POINTER(C.c_double)))
+        return nxt, g[:8], g[8:]
+
     def tool_collide(self, i, f, p, v):
         o = np.zeros(3)
         self.L.orc_tool_collide(self.h, i, f, _d(p)[1], _d(v)[1], _d(o)[1])

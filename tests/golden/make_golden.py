@@ -12,7 +12,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
-from helpers import perturbed_state, small_dough, tool_start  # noqa: E402
+from helpers import ENVS, perturbed_state, small_dough, tool_start  # noqa: E402
 from oracle import oracle as orc  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -46,5 +46,5 @@ def make(name, n=300, seed=0):
 
 
 if __name__ == '__main__':
-    for nm in ['LiftSpread-v1', 'GatherMove-v1', 'CutRearrange-v1', 'Move-v1']:
+    for nm in (sys.argv[1:] or ENVS):
         make(nm)

@@ -3,11 +3,10 @@ import copy
 
 import numpy as np
 
-from helpers import perturbed_state, relerr, small_dough, tool_start
+from helpers import ENVS, perturbed_state, relerr, small_dough, tool_start
 from diffskill_b200.engine import Engine
 from oracle import oracle as orc
 
-ENVS = ['LiftSpread-v1', 'GatherMove-v1', 'CutRearrange-v1', 'Move-v1']   # Move-v1: the Sphere tool
 
 
 def f32(a):

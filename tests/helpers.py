@@ -12,6 +12,12 @@ from diffskill_b200.scene import load_scene  # noqa: E402
 from diffskill_b200.shapes import Shapes  # noqa: E402
 
 
+# the three DiffSkill envs, then legacy PlasticineLab scenes that exercise the remaining tools:
+# Move-v1 Sphere, Rollingpin-v1 RollingPin, Torus-v1 Torus, Rope-v1 Sphere + Cylinder, Gripper2-synthetic Gripper2
+ENVS = ['LiftSpread-v1', 'GatherMove-v1', 'CutRearrange-v1', 'Move-v1', 'Rollingpin-v1', 'Torus-v1', 'Rope-v1',
+        'Gripper2-synthetic']
+
+
 def small_dough(name, n, seed=0):
     """n particles of the env's synthetic dough, squeezed next to the tools so contacts are active."""
     scene, cfg = load_scene(name)
@@ -26,6 +32,19 @@ def small_dough(name, n, seed=0):
     elif name == 'Move-v1':
         # slab between the two sphere manipulators (x = 0.576 and 0.776, radius 0.03), 5 mm into each of them
         x = rng.uniform(-1, 1, (n, 3)) * np.array([0.075, 0.03, 0.03]) + np.array([0.6757143, 0.5619162, 0.7515980])
+    elif name == 'Rollingpin-v1':
+        # slab under the pin (capsule r = 0.03 at y = 0.123, axis along world z): top face 7 mm inside it
+        x = rng.uniform(-1, 1, (n, 3)) * np.array([0.04, 0.015, 0.06]) + np.array([0.5, 0.085, 0.5])
+    elif name == 'Torus-v1':
+        # slab under the ring (major 0.05, minor 0.03, axis = world y), which tool_start lowers to y = 0.12
+        x = rng.uniform(-1, 1, (n, 3)) * np.array([0.09, 0.02, 0.09]) + np.array([0.5, 0.08, 0.5])
+    elif name == 'Rope-v1':
+        # piece of rope pressed 9 mm into the side of the pillar (Cylinder radius 0.1 at z = 0.499), the two spheres
+        # (moved by tool_start) touching it from the other side
+        x = rng.uniform(-1, 1, (n, 3)) * np.array([0.05, 0.03, 0.02]) + np.array([0.392, 0.04, 0.61])
+    elif name == 'Gripper2-synthetic':
+        # slab between the two capsule jaws (axis = world y, separated along world z), 5 mm into each
+        x = rng.uniform(-1, 1, (n, 3)) * np.array([0.04, 0.03, 0.035]) + np.array([0.5, 0.06, 0.5])
     else:
         x = Shapes(cfg.SHAPES, seed=seed).get()[0][:n]
     return scene, cfg, x
@@ -53,6 +72,13 @@ def tool_start(name, scene):
         st[0][:3] = (0.5, 0.24, 0.5)      # knife tip inside the slab
         st[1][:3] = (0.5, 0.09, 0.5)
         st[1][7] = 0.10
+    elif name == 'Torus-v1':
+        st[0][:3] = (0.5, 0.12, 0.5)
+    elif name == 'Rope-v1':
+        st[0][:3] = (0.36, 0.04, 0.655)
+        st[1][:3] = (0.42, 0.04, 0.655)
+    elif name == 'Gripper2-synthetic':
+        st[0][7] = 0.10
     return st
 
 

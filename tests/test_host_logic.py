@@ -60,7 +60,15 @@ def test_primitive_mirrors_unbound():
     assert a[0] == 0. and a[1] == pytest.approx(8.0)
     assert P[0].inv_action(np.zeros(7), np.zeros(7)) is None
     with pytest.raises(NotImplementedError):
-        Primitives([CfgNode(dict(shape='Torus'))])
+        Primitives([CfgNode(dict(shape='Chopsticks'))])
+    # the legacy PlasticineLab tools with the defaults of their default_config()
+    L = Primitives([CfgNode(dict(shape=s)) for s in ('Sphere', 'RollingPin', 'Cylinder', 'Torus')]
+                   + [CfgNode(dict(shape='Gripper2', action=dict(dim=7, scale=(0.01,) * 7)))])
+    assert L.state_dims == [7, 7, 7, 7, 8] and L.action_dim == 7
+    assert (L[2].spec.h, L[2].spec.r) == (0.2, 0.1) and (L[3].spec.h, L[3].spec.r) == (0.2, 0.1)   # Torus: (tx, ty)
+    assert L[4].init_state[-1] == 0.06 and L[4].spec.r == 0.015
+    with pytest.raises(AssertionError):
+        L[4].set_state(0, np.zeros(7))
 
 
 def test_shard_envs_partitions_exactly():

@@ -5,10 +5,9 @@ import os
 import numpy as np
 import pytest
 
-from helpers import perturbed_state, relerr, small_dough, tool_start
+from helpers import ENVS, perturbed_state, relerr, small_dough, tool_start
 from oracle import oracle as orc
 
-ENVS = ['LiftSpread-v1', 'GatherMove-v1', 'CutRearrange-v1', 'Move-v1']   # Move-v1: the Sphere tool
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 
