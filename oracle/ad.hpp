@@ -14,6 +14,7 @@
 // the min/max tie-breaking hold by construction rather than by hand derivation.
 #pragma once
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 namespace ad {
@@ -133,18 +134,51 @@ inline Var<T> s_sqrt(const Var<T>& x) {
   T r = std::sqrt(x.v);
   return mk<T>(r, x.id, T(0.5) / r, -1, T(0));
 }
-inline float s_exp(float x) { return std::exp(x); }
-inline double s_exp(double x) { return std::exp(x); }
+// Emulation of fast-math transcendentals (test infrastructure).  The reference runs ti.init(fast_math=True)
+// (plb/engine/taichi_env.py:20): on its CUDA backend log/exp are the hardware approximations (absolute error of log up to
+// 2^-21.4 on [0.5, 2], exp about 2 ulp).  With amplitude a > 0 the oracle's log carries a deterministic pseudo-random
+// absolute error in [-a, a] and exp a relative one in [-a/2, a/2] (hash of the argument, so a recompute sees the same
+// value); the spread over a few amplitudes / salts is the formulation's sensitivity to that freedom.  0 = exact (default).
+inline double& fast_math_noise() {
+  static double a = 0.0;
+  return a;
+}
+inline int& fast_math_salt() {
+  static int s = 0;
+  return s;
+}
+inline double fm_hash(double x) {   // in [-1, 1], deterministic in (x, salt)
+  float xf = (float)x;
+  unsigned h;
+  std::memcpy(&h, &xf, 4);
+  h ^= (unsigned)fast_math_salt() * 0x9E3779B1u;
+  h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+  return (double)(h & 0xFFFFFF) / (double)0x7FFFFF - 1.0;
+}
+template <class T>
+inline T fm_exp(T x) {
+  T r = std::exp(x);
+  double a = fast_math_noise();
+  return a > 0.0 ? (T)((double)r * (1.0 + 0.5 * a * fm_hash((double)x))) : r;
+}
+template <class T>
+inline T fm_log(T x) {
+  T r = std::log(x);
+  double a = fast_math_noise();
+  return a > 0.0 ? (T)((double)r + a * fm_hash((double)x)) : r;
+}
+inline float s_exp(float x) { return fm_exp(x); }
+inline double s_exp(double x) { return fm_exp(x); }
 template <class T>
 inline Var<T> s_exp(const Var<T>& x) {
-  T r = std::exp(x.v);
+  T r = fm_exp(x.v);
   return mk<T>(r, x.id, r, -1, T(0));
 }
-inline float s_log(float x) { return std::log(x); }
-inline double s_log(double x) { return std::log(x); }
+inline float s_log(float x) { return fm_log(x); }
+inline double s_log(double x) { return fm_log(x); }
 template <class T>
 inline Var<T> s_log(const Var<T>& x) {
-  return mk<T>(std::log(x.v), x.id, T(1) / x.v, -1, T(0));
+  return mk<T>(fm_log(x.v), x.id, T(1) / x.v, -1, T(0));
 }
 inline float s_sin(float x) { return std::sin(x); }
 inline double s_sin(double x) { return std::sin(x); }

@@ -669,6 +669,27 @@ inline V3<S> grid_op_body(const Consts<T>& k, const int I[3], const V3<S>& v_in,
 // ----------------------------------------------------------------------------
 // simulator state (fields as in MPMSimulator.__init__ / Primitive.__init__)
 // ----------------------------------------------------------------------------
+// ---- emulation of the reference's unspecified float-atomic order (test infrastructure) -------------------------------
+// The reference accumulates p2g and the g2p adjoint with float atomics whose order changes from run to run, so every
+// grid sum carries about an ulp of run-to-run noise.  With a non-zero seed the oracle multiplies each rounded grid sum
+// by (1 + s * ulp), s in {-1, 0, +1} a hash of (seed, frame, node, component): the spread of the results over a few
+// seeds is the reference formulation's own reproducibility floor for a scene (tests use it as the parity floor where it
+// exceeds the north-star tolerance).  Deterministic in (seed, frame, node), so substep_grad's recompute sees the same grid.
+static int g_scatter_noise_seed = 0;
+static double g_scatter_noise_ulps = 1.0;
+static inline double scatter_noise(int f, int g, int d, double ulp) {
+  if (g_scatter_noise_seed == 0) return 1.0;
+  uint32_t h = (uint32_t)g_scatter_noise_seed * 0x9E3779B1u;
+  h ^= (uint32_t)f + 0x7F4A7C15u + (h << 6) + (h >> 2);
+  h ^= (uint32_t)g * 0x85EBCA6Bu + (h << 6) + (h >> 2);
+  h ^= (uint32_t)d * 0xC2B2AE35u + (h << 6) + (h >> 2);
+  h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+  return 1.0 + ((int)(h % 3u) - 1) * ulp * g_scatter_noise_ulps;
+}
+template <class T> inline double ulp_of();
+template <> inline double ulp_of<float>() { return 1.1920928955078125e-7; }
+template <> inline double ulp_of<double>() { return 2.220446049250313e-16; }
+
 template <class T>
 struct ToolState {
   ToolC<T> c;
@@ -878,8 +899,9 @@ struct Sim {
     }
 #pragma omp parallel for schedule(static)
     for (int g = 0; g < G; g++) {
-      for (int d = 0; d < 3; d++) grid_v_in[(size_t)g * 3 + d] = (T)acc4[(size_t)g * 4 + d];
-      grid_m[g] = (T)acc4[(size_t)g * 4 + 3];
+      for (int d = 0; d < 3; d++)
+        grid_v_in[(size_t)g * 3 + d] = (T)((double)(T)acc4[(size_t)g * 4 + d] * scatter_noise(f, g, d, ulp_of<T>()));
+      grid_m[g] = (T)((double)(T)acc4[(size_t)g * 4 + 3] * scatter_noise(f, g, 3, ulp_of<T>()));
     }
   }
   void forward_kinematics(int i, int f) {
@@ -1056,7 +1078,8 @@ struct Sim {
     }
 #pragma omp parallel for schedule(static)
     for (int g = 0; g < G; g++)
-      for (int d = 0; d < 3; d++) g_grid_v_out[(size_t)g * 3 + d] += (T)acc3[(size_t)g * 3 + d];
+      for (int d = 0; d < 3; d++)
+        g_grid_v_out[(size_t)g * 3 + d] += (T)((double)(T)acc3[(size_t)g * 3 + d] * scatter_noise(f, g, 4 + d, ulp_of<T>()));
   }
   void grid_op_grad(int f) {
     int nn = k.n;
@@ -1541,6 +1564,14 @@ void orc_destroy(void* h) {
   delete H->f;
   delete H->d;
   delete H;
+}
+void orc_set_scatter_noise(int seed, double ulps) {
+  orc::g_scatter_noise_seed = seed;
+  orc::g_scatter_noise_ulps = ulps;
+}
+void orc_set_fast_math_noise(double amplitude, int salt) {
+  ad::fast_math_noise() = amplitude;
+  ad::fast_math_salt() = salt;
 }
 void orc_set_threads(int n) { omp_set_num_threads(n); }
 int orc_is_f64(void* h) { return ((Handle*)h)->f64; }

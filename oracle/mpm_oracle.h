@@ -72,6 +72,12 @@ typedef struct orc_config {
 void* orc_create(const orc_config* cfg, int use_f64);
 void orc_destroy(void* h);
 void orc_set_threads(int n);
+/* seed != 0: every grid sum of p2g / g2p.grad is perturbed by -ulps/0/+ulps units in the last place (hash of seed, frame, node): emulates the
+ * run-to-run noise of the reference's unordered float atomics (mpm_simulator.py:224-225); 0 = exact (default) */
+void orc_set_scatter_noise(int seed, double ulps);
+/* amplitude > 0: log carries a pseudo-random absolute error in [-a, a], exp a relative one in [-a/2, a/2] (the reference
+ * runs fast_math=True, taichi_env.py:20: hardware log/exp, |err(log)| <= 2^-21.4 = 3.7e-7); 0 = exact (default) */
+void orc_set_fast_math_noise(double amplitude, int salt);
 int orc_is_f64(void* h);
 
 void orc_initialize(void* h, int n_particles);            /* mpm_simulator.py:82-97 */

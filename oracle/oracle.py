@@ -55,6 +55,19 @@ def lib():
     return _LIB
 
 
+def set_scatter_noise(seed, ulps=1.0):
+    """Process-wide: perturb every grid sum of p2g / g2p.grad by -ulps/0/+ulps units in the last place (hash of seed,
+    frame, node) -- the run-to-run noise of the reference's unordered float atomics.  The spread of a result over a few
+    seeds is the reference formulation's own reproducibility floor on a scene.  seed 0 switches it off."""
+    lib().orc_set_scatter_noise(int(seed), C.c_double(ulps))
+
+
+def set_fast_math_noise(amplitude, salt=1):
+    """Process-wide: log gets a pseudo-random absolute error in [-a, a], exp a relative one in [-a/2, a/2] (the reference
+    runs ti.init(fast_math=True): hardware log/exp, |err(log)| <= 2^-21.4).  amplitude 0 switches it off."""
+    lib().orc_set_fast_math_noise(C.c_double(amplitude), int(salt))
+
+
 def _d(a):
     a = np.ascontiguousarray(a, dtype=np.float64)
     return a, a.ctypes.data_as(C.POINTER(C.c_double))
