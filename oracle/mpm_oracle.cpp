@@ -677,6 +677,7 @@ inline V3<S> grid_op_body(const Consts<T>& k, const int I[3], const V3<S>& v_in,
 // exceeds the north-star tolerance).  Deterministic in (seed, frame, node), so substep_grad's recompute sees the same grid.
 static int g_scatter_noise_seed = 0;
 static double g_scatter_noise_ulps = 1.0;
+static int g_pose_atomics_seed = 0;   // != 0: tool-pose adjoints of grid_op.grad accumulate like the reference's atomics
 static inline double scatter_noise(int f, int g, int d, double ulp) {
   if (g_scatter_noise_seed == 0) return 1.0;
   uint32_t h = (uint32_t)g_scatter_noise_seed * 0x9E3779B1u;
@@ -1085,16 +1086,18 @@ struct Sim {
     int nn = k.n;
     std::vector<ToolC<T>> tc(K);
     for (int i = 0; i < K; i++) tc[i] = tools[i].c;
-    int nth = omp_get_max_threads();
-    std::vector<std::vector<double>> acc(nth, std::vector<double>((size_t)K * 16, 0.0));
+    std::vector<int> live;
+    for (int g = 0; g < G; g++)
+      if (grid_m[g] > k.m_eps) live.push_back(g);
+    const size_t W = (size_t)K * 16;
+    std::vector<T> contrib(live.size() * W, T(0));   // per-node adjoints of (pose f, pose f+1) of every tool
 #pragma omp parallel
     {
       typedef Var<T> S;
-      std::vector<double>& my = acc[omp_get_thread_num()];
       std::vector<Pose<S>> P0(K), P1(K);
 #pragma omp for schedule(static)
-      for (int g = 0; g < G; g++) {
-        if (!(grid_m[g] > k.m_eps)) continue;
+      for (int li = 0; li < (int)live.size(); li++) {
+        int g = live[li];
         Tape<T>& tp = tape<T>();
         tp.clear();
         int I[3] = {g / (nn * nn), (g / nn) % nn, g % nn};
@@ -1112,28 +1115,44 @@ struct Sim {
         for (int d = 0; d < 3; d++) g_grid_v_in[(size_t)g * 3 + d] += vin[d].grad();
         g_grid_m[g] += m.grad();
         for (int i = 0; i < K; i++) {
-          double* a = &my[(size_t)i * 16];
-          for (int d = 0; d < 3; d++) a[d] += P0[i].pos[d].grad();
-          for (int d = 0; d < 4; d++) a[3 + d] += P0[i].rot[d].grad();
-          a[7] += P0[i].gap.grad();
-          for (int d = 0; d < 3; d++) a[8 + d] += P1[i].pos[d].grad();
-          for (int d = 0; d < 4; d++) a[11 + d] += P1[i].rot[d].grad();
-          a[15] += P1[i].gap.grad();
+          T* a = &contrib[(size_t)li * W + (size_t)i * 16];
+          for (int d = 0; d < 3; d++) a[d] = P0[i].pos[d].grad();
+          for (int d = 0; d < 4; d++) a[3 + d] = P0[i].rot[d].grad();
+          a[7] = P0[i].gap.grad();
+          for (int d = 0; d < 3; d++) a[8 + d] = P1[i].pos[d].grad();
+          for (int d = 0; d < 4; d++) a[11 + d] = P1[i].rot[d].grad();
+          a[15] = P1[i].gap.grad();
         }
       }
     }
-    for (int t = 1; t < nth; t++)
-      for (size_t q = 0; q < (size_t)K * 16; q++) acc[0][q] += acc[t][q];
-    for (int t = 0; t < 1; t++)
-      for (int i = 0; i < K; i++) {
-        const double* a = &acc[t][(size_t)i * 16];
-        ToolState<T>& ts = tools[i];
-        for (int d = 0; d < 3; d++) ts.g_pos[f * 3 + d] += (T)a[d];
-        for (int d = 0; d < 4; d++) ts.g_rot[f * 4 + d] += (T)a[3 + d];
-        ts.g_gap[f] += (T)a[7];
-        for (int d = 0; d < 3; d++) ts.g_pos[(f + 1) * 3 + d] += (T)a[8 + d];
-        for (int d = 0; d < 4; d++) ts.g_rot[(f + 1) * 4 + d] += (T)a[11 + d];
-        ts.g_gap[f + 1] += (T)a[15];
+    auto field = [&](ToolState<T>& ts, int q) -> T& {   // slot q of (pose f | pose f+1) in the tool's .grad fields
+      int ff = q < 8 ? f : f + 1, c = q & 7;
+      return c < 3 ? ts.g_pos[ff * 3 + c] : (c < 7 ? ts.g_rot[ff * 4 + c - 3] : ts.g_gap[ff]);
+    };
+    if (g_pose_atomics_seed != 0) {
+      // the reference: every node thread atomically adds its term to position.grad / rotation.grad in T precision, in an
+      // unspecified order (the terms are O(1/dt) and cancel, so the order matters): seeded shuffle of the node order
+      std::vector<int> order(live.size());
+      for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+      uint32_t st = (uint32_t)g_pose_atomics_seed * 2654435761u + (uint32_t)f * 40503u + 1u;
+      for (size_t i = order.size(); i > 1; i--) {
+        st ^= st << 13; st ^= st >> 17; st ^= st << 5;
+        std::swap(order[i - 1], order[st % i]);
+      }
+      for (int li : order)
+        for (int i = 0; i < K; i++)
+          for (int q = 0; q < 16; q++) {
+            T& dst = field(tools[i], q);
+            dst = dst + contrib[(size_t)li * W + (size_t)i * 16 + q];
+          }
+      return;
+    }
+    // default: order-independent (sum in double, round once)
+    for (int i = 0; i < K; i++)
+      for (int q = 0; q < 16; q++) {
+        double a = 0.0;
+        for (size_t li = 0; li < live.size(); li++) a += (double)contrib[li * W + (size_t)i * 16 + q];
+        field(tools[i], q) += (T)a;
       }
   }
   void apply_collision_projection_grad(int s) {
@@ -1569,6 +1588,7 @@ void orc_set_scatter_noise(int seed, double ulps) {
   orc::g_scatter_noise_seed = seed;
   orc::g_scatter_noise_ulps = ulps;
 }
+void orc_set_pose_adjoint_atomics(int seed) { orc::g_pose_atomics_seed = seed; }
 void orc_set_fast_math_noise(double amplitude, int salt) {
   ad::fast_math_noise() = amplitude;
   ad::fast_math_salt() = salt;

@@ -78,6 +78,10 @@ void orc_set_scatter_noise(int seed, double ulps);
 /* amplitude > 0: log carries a pseudo-random absolute error in [-a, a], exp a relative one in [-a/2, a/2] (the reference
  * runs fast_math=True, taichi_env.py:20: hardware log/exp, |err(log)| <= 2^-21.4 = 3.7e-7); 0 = exact (default) */
 void orc_set_fast_math_noise(double amplitude, int salt);
+/* seed != 0: grid_op.grad adds every node's tool-pose adjoint terms to position.grad / rotation.grad one by one in the
+ * simulation precision, in a seeded random node order -- what the reference's float atomics do (the terms are O(1/dt) and
+ * cancel); 0 (default): order-independent sum in double, rounded once */
+void orc_set_pose_adjoint_atomics(int seed);
 int orc_is_f64(void* h);
 
 void orc_initialize(void* h, int n_particles);            /* mpm_simulator.py:82-97 */

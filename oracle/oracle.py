@@ -62,6 +62,12 @@ def set_scatter_noise(seed, ulps=1.0):
     lib().orc_set_scatter_noise(int(seed), C.c_double(ulps))
 
 
+def set_pose_adjoint_atomics(seed):
+    """Process-wide: grid_op.grad adds every node's tool-pose adjoint terms one by one in the simulation precision, in a
+    seeded random node order (what the reference's float atomics do); 0 = order-independent double sum (default)."""
+    lib().orc_set_pose_adjoint_atomics(int(seed))
+
+
 def set_fast_math_noise(amplitude, salt=1):
     """Process-wide: log gets a pseudo-random absolute error in [-a, a], exp a relative one in [-a/2, a/2] (the reference
     runs ti.init(fast_math=True): hardware log/exp, |err(log)| <= 2^-21.4).  amplitude 0 switches it off."""
