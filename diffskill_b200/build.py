@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, 'csrc')
 SO = os.path.join(HERE, 'libdiffskill_mpm.so')
 SO_TIMELINE = os.path.join(HERE, 'libdiffskill_mpm_tl.so')   # profiling build, see dsk_timeline_* in the header
 SOURCES = ['engine.cu']
-HEADERS = ['mpm_math.cuh', 'svd3.cuh', 'tools.cuh', 'kernels_common.cuh', 'kernels_aux.cuh', 'kernels_fwd.cuh',
+HEADERS = ['mpm_math.cuh', 'svd3.cuh', 'tools.cuh', 'particle_math.cuh', 'kernels_common.cuh', 'kernels_aux.cuh', 'kernels_fwd.cuh',
            'kernels_bwd.cuh', os.path.join('..', '..', 'include', 'diffskill_mpm.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC', '-shared']

@@ -26,56 +26,16 @@ __global__ void __launch_bounds__(128, MINB)
   float3 gxn = load_v3(adj_in, CX, k.stride, gi);
   float3 gvn = load_v3(adj_in, CV, k.stride, gi);
   M3 gC = load_m3(adj_in, CC, k.stride, gi);
-  // x' = max(min(x + dt v', hi), lo): the adjoint passes iff lo < x' < hi
-  float3 gt = f3((k.x_lo < xn.x && xn.x < k.x_hi) ? gxn.x : 0.f, (k.x_lo < xn.y && xn.y < k.x_hi) ? gxn.y : 0.f,
-                 (k.x_lo < xn.z && xn.z < k.x_hi) ? gxn.z : 0.f);
-  gvn += k.dt * gt;
-  float3 gx = gt;
   Stencil s;
-  make_stencil(k, x.x, x.y, x.z, s);
+  G2PAdj c;
+  g2p_adj_begin(k, x, xn, gxn, gvn, gC, s, c);
   const float4* Gve = Gv + (size_t)env * k.nnode;
   float4* Gae = Ga + (size_t)env * k.nnode;
   // adjoint of grid_v_out: warp-aggregated scatter
   TileTrack none{nullptr, nullptr, nullptr};
-  // adjoint of grid_v_out[node] = w * (gvn + c_C gC (offset - fx)) = w * (b0 + i cx + j cy + l cz)
-  float3 b0 = gvn - k.c_C * mv(gC, f3(s.fx, s.fy, s.fz));
-  float3 cx = f3(k.c_C * gC.m[0], k.c_C * gC.m[3], k.c_C * gC.m[6]);
-  float3 cy = f3(k.c_C * gC.m[1], k.c_C * gC.m[4], k.c_C * gC.m[7]);
-  float3 cz = f3(k.c_C * gC.m[2], k.c_C * gC.m[5], k.c_C * gC.m[8]);
-  warp_scatter27(k, active, s, Gae, none, false, env, 0, [&](int i, int j, int l) {
-    float w = s.wx[i] * s.wy[j] * s.wz[l];
-    float3 a = b0 + (float)i * cx + (float)j * cy + (float)l * cz;
-    return make_float4(w * a.x, w * a.y, w * a.z, 0.f);
-  });
+  warp_scatter27(k, active, s, Gae, none, false, env, 0, [&](int i, int j, int l) { return g2p_adj_node(s, c, i, j, l); });
   if (!active) return;
-  // adjoint of the weights: d/dw [ g . (gvn + c_C gC dpos) ] = g . (b0 + i cx + j cy + l cz);
-  // adjoint of fx through dpos: -c_C gC^T (sum w g)
-  float gwx[3] = {0, 0, 0}, gwy[3] = {0, 0, 0}, gwz[3] = {0, 0, 0};
-  float3 sg = f3(0, 0, 0);
-#pragma unroll
-  for (int i = 0; i < 3; i++)
-#pragma unroll
-    for (int j = 0; j < 3; j++)
-#pragma unroll
-      for (int l = 0; l < 3; l++) {
-        float4 g4 = Gve[s.ox[i] + s.oy[j] + s.oz[l]];
-        float3 g = f3(g4.x, g4.y, g4.z);
-        float3 a = b0 + (float)i * cx + (float)j * cy + (float)l * cz;
-        float gw = dot(g, a);
-        sg += (s.wx[i] * s.wy[j] * s.wz[l]) * g;
-        gwx[i] += gw * s.wy[j] * s.wz[l];
-        gwy[j] += gw * s.wx[i] * s.wz[l];
-        gwz[l] += gw * s.wx[i] * s.wy[j];
-      }
-  float3 gf = (-k.c_C) * mTv(gC, sg);
-  float dw[3];
-  bspline1_grad(s.fx, dw);
-  gf.x += gwx[0] * dw[0] + gwx[1] * dw[1] + gwx[2] * dw[2];
-  bspline1_grad(s.fy, dw);
-  gf.y += gwy[0] * dw[0] + gwy[1] * dw[1] + gwy[2] * dw[2];
-  bspline1_grad(s.fz, dw);
-  gf.z += gwz[0] * dw[0] + gwz[1] * dw[1] + gwz[2] * dw[2];
-  gx += k.inv_dx * gf;
+  float3 gx = g2p_adj_finish(k, s, Gve, gC, c);
   store_v3(adj_out, CX, k.stride, gid, gx);
 }
 
@@ -153,45 +113,6 @@ __global__ void __launch_bounds__(PL_PARTICLES * 3)
   store_v3(adj_out, CX, k.stride, gid, gt + k.inv_dx * gf);
 }
 
-// adjoint of contact_response given the geometry (D, cv, influence): returns g(v_in), outputs g(D), g(cv), g(influence)
-DSK_DEV float3 contact_response_adj(float3 v, float3 D, float3 cv, float influence, float friction, bool eps14,
-                                    float3 gout, float3& gD, float3& gcv, float& ginfl) {
-  float3 u = v - cv;
-  float nc = dot(u, D);
-  float mn = tmin(nc, 0.f);
-  float3 t = u - mn * D;
-  float tn = sqrtf(dot(t, t) + (eps14 ? 1e-14f : 1e-8f));
-  float a2 = tn + nc * friction;
-  float mx = tmax(0.f, a2);
-  bool flag = (nc < 0.f) && (sqrtf(dot(t, t)) > 1e-30f);
-  float3 q = (1.f / tn) * t;
-  float3 t2 = flag ? mx * q : t;
-  gcv = gout;
-  float3 gu = (1.f - influence) * gout;
-  ginfl = dot(gout, t2 - u);
-  float3 gt2 = influence * gout;
-  float3 gt = f3(0, 0, 0);
-  float gnc = 0.f;
-  if (flag) {
-    float3 gq = mx * gt2;
-    float gmx = dot(gt2, q);
-    float ga2 = (a2 < 0.f) ? 0.f : gmx;
-    float gtn = ga2 - dot(gq, t) / (tn * tn);
-    gt += (1.f / tn) * gq;
-    gnc += ga2 * friction;
-    gt += (gtn / tn) * t;
-  } else {
-    gt += gt2;
-  }
-  gu += gt;
-  float gmn = -dot(gt, D);
-  gD = (-mn) * gt;
-  if (nc < 0.f) gnc += gmn;
-  gu += gnc * D;
-  gD += gnc * u;
-  gcv -= gu;
-  return gu;
-}
 struct ContactGeomAdj {   // per (node, frame), shared memory
   float3 gD, gcv;
   float gdist;
@@ -526,106 +447,6 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4)
   }
 }
 
-// everything of p2g.grad after the 27-node gather: S0 = sum w G, (m0,m1,m2) = columns of sum w G (x) offset,
-// gw* = adjoints of the per-axis weights
-DSK_DEV void p2g_adj_finish(const SimConst& k, int gid, const Stencil& s, const P2GParticle& o, float mu, float lam,
-                            const M3& C, const M3& F, const float* __restrict__ adj_in, float* __restrict__ adj_out,
-                            float3 S0, float3 m0, float3 m1, float3 m2, const float* gwx, const float* gwy,
-                            const float* gwz) {
-  float3 gv = k.p_mass * S0;
-  float3 gf = (-k.dx) * mTv(o.affine, S0);
-  M3 gA;  // adjoint of affine
-  gA.m[0] = k.dx * (m0.x - S0.x * s.fx); gA.m[1] = k.dx * (m1.x - S0.x * s.fy); gA.m[2] = k.dx * (m2.x - S0.x * s.fz);
-  gA.m[3] = k.dx * (m0.y - S0.y * s.fx); gA.m[4] = k.dx * (m1.y - S0.y * s.fy); gA.m[5] = k.dx * (m2.y - S0.y * s.fz);
-  gA.m[6] = k.dx * (m0.z - S0.z * s.fx); gA.m[7] = k.dx * (m1.z - S0.z * s.fy); gA.m[8] = k.dx * (m2.z - S0.z * s.fz);
-  float dw[3];
-  bspline1_grad(s.fx, dw);
-  gf.x += gwx[0] * dw[0] + gwx[1] * dw[1] + gwx[2] * dw[2];
-  bspline1_grad(s.fy, dw);
-  gf.y += gwy[0] * dw[0] + gwy[1] * dw[1] + gwy[2] * dw[2];
-  bspline1_grad(s.fz, dw);
-  gf.z += gwz[0] * dw[0] + gwz[1] * dw[1] + gwz[2] * dw[2];
-  float3 gx = load_v3(adj_out, CX, k.stride, gid) + k.inv_dx * gf;
-
-  // affine = c_stress * stress + p_mass * C
-  M3 gCm, gS;
-#pragma unroll
-  for (int i = 0; i < 9; i++) {
-    gCm.m[i] = k.p_mass * gA.m[i];
-    gS.m[i] = k.c_stress * gA.m[i];
-  }
-  // stress = A N^T + vol I,  A = 2mu (N - R),  vol = (lam J)(J - 1)
-  M3 R = mmT(o.U, o.V);
-  M3 A;
-#pragma unroll
-  for (int i = 0; i < 9; i++) A.m[i] = (2.f * mu) * (o.newF.m[i] - R.m[i]);
-  M3 gAm = mm(gS, o.newF);   // g(A) = gS N
-  M3 gN = mTm(gS, A);        // g(N) = gS^T A
-  M3 gR;
-#pragma unroll
-  for (int i = 0; i < 9; i++) {
-    gN.m[i] += (2.f * mu) * gAm.m[i];
-    gR.m[i] = -(2.f * mu) * gAm.m[i];
-  }
-  float gJ = lam * (2.f * o.J - 1.f) * (gS.m[0] + gS.m[4] + gS.m[8]);
-  M3 cf = cof3(o.newF);
-  M3 gFn = load_m3(adj_in, CF, k.stride, gid);  // F.grad[j+1]
-#pragma unroll
-  for (int i = 0; i < 9; i++) gN.m[i] += gJ * cf.m[i] + gFn.m[i];
-  // R = U V^T
-  M3 gU = mm(gR, o.V);
-  M3 gV = mTm(gR, o.U);
-  float3 gsig = f3(0, 0, 0);
-  M3 gFt;
-  if (!o.rm.yields) {
-    gFt = gN;
-  } else {
-    const ReturnMap& r = o.rm;
-    float e[3] = {r.e.x, r.e.y, r.e.z};
-    // N = U diag(e) V^T
-    M3 NV = mm(gN, o.V);     // gN V
-    M3 NtU = mTm(gN, o.U);   // gN^T U
-    M3 UtNV = mTm(o.U, NV);  // U^T gN V
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-      for (int q = 0; q < 3; q++) {
-        gU.m[i * 3 + q] += NV.m[i * 3 + q] * e[q];
-        gV.m[i * 3 + q] += NtU.m[i * 3 + q] * e[q];
-      }
-    float3 ge = f3(UtNV.m[0], UtNV.m[4], UtNV.m[8]);
-    float3 gep = f3(ge.x * r.e.x, ge.y * r.e.y, ge.z * r.e.z);  // adjoint of the returned log strain
-    float kf = r.dg / r.ehn;
-    float3 geps = gep;
-    float gk = -dot(gep, r.eh);
-    float3 geh = (-kf) * gep;
-    float gdg = gk / r.ehn;
-    float gehn = -gk * r.dg / (r.ehn * r.ehn) + gdg;
-    geh += (gehn / r.ehn) * r.eh;
-    float gm = (geh.x + geh.y + geh.z) / 3.f;
-    geps += f3(geh.x - gm, geh.y - gm, geh.z - gm);
-    gsig = f3((0.05f < o.sig.x) ? geps.x / r.sc.x : 0.f, (0.05f < o.sig.y) ? geps.y / r.sc.y : 0.f,
-              (0.05f < o.sig.z) ? geps.z / r.sc.z : 0.f);
-#pragma unroll
-    for (int i = 0; i < 9; i++) gFt.m[i] = 0.f;
-  }
-  M3 gsv = svd3_backward(gU, gsig, gV, o.U, o.sig, o.V);
-#pragma unroll
-  for (int i = 0; i < 9; i++) gFt.m[i] += gsv.m[i];
-  // F_tmp = (I + dt C) F
-  M3 Mx;
-#pragma unroll
-  for (int i = 0; i < 9; i++) Mx.m[i] = ((i % 4 == 0) ? 1.f : 0.f) + k.dt * C.m[i];
-  M3 gM = mmT(gFt, F);
-  M3 gF = mTm(Mx, gFt);
-#pragma unroll
-  for (int i = 0; i < 9; i++) gCm.m[i] += k.dt * gM.m[i];
-  store_v3(adj_out, CX, k.stride, gid, gx);
-  store_v3(adj_out, CV, k.stride, gid, gv);
-  store_m3(adj_out, CC, k.stride, gid, gCm);
-  store_m3(adj_out, CF, k.stride, gid, gF);
-}
-
 // p2g.grad + svd_grad + compute_F_tmp.grad fused: gathers adjoints of (grid_v_in, grid_m), reads F.grad[j+1],
 // writes x.grad (adding the g2p part already stored), v.grad, C.grad, F.grad of frame j.
 template <int MINB>
@@ -638,45 +459,7 @@ __global__ void __launch_bounds__(128, MINB)
   if (gid >= k.stride) return;
   int env = gid / k.Npad, p = gid - env * k.Npad;
   if (p >= npart[env]) return;
-  float3 x = load_v3(fin, CX, k.stride, gid);
-  float3 v = load_v3(fin, CV, k.stride, gid);
-  M3 C = load_m3(fin, CC, k.stride, gid);
-  M3 F = load_m3(fin, CF, k.stride, gid);
-  float mu = mat[gid], lam = mat[k.stride + gid], ys = mat[2 * k.stride + gid];
-  P2GParticle o;
-  p2g_particle_adj(k, svd_in, gid, C, F, mu, lam, ys, o);
-  Stencil s;
-  make_stencil(k, x.x, x.y, x.z, s);
-  const float4* Gae = Ga + (size_t)env * k.nnode;
-  // contribution(node) = w * (a0 + i ax + j ay + l az, p_mass)  (see k_p2g); with S0 = sum w G and M = sum w G (x) offset:
-  //   g(v) = p_mass S0 ; g(affine) = dx (M - S0 (x) fx) ; g(fx) through dpos = -dx affine^T S0 ; g(w) = G . a + gm p_mass
-  float3 fxv = f3(s.fx, s.fy, s.fz);
-  float3 a0 = k.p_mass * v - k.dx * mv(o.affine, fxv);
-  float3 ax = f3(k.dx * o.affine.m[0], k.dx * o.affine.m[3], k.dx * o.affine.m[6]);
-  float3 ay = f3(k.dx * o.affine.m[1], k.dx * o.affine.m[4], k.dx * o.affine.m[7]);
-  float3 az = f3(k.dx * o.affine.m[2], k.dx * o.affine.m[5], k.dx * o.affine.m[8]);
-  float gwx[3] = {0, 0, 0}, gwy[3] = {0, 0, 0}, gwz[3] = {0, 0, 0};
-  float3 S0 = f3(0, 0, 0), m0 = f3(0, 0, 0), m1 = f3(0, 0, 0), m2 = f3(0, 0, 0);
-#pragma unroll
-  for (int i = 0; i < 3; i++)
-#pragma unroll
-    for (int j = 0; j < 3; j++)
-#pragma unroll
-      for (int l = 0; l < 3; l++) {
-        float4 g4 = Gae[s.ox[i] + s.oy[j] + s.oz[l]];
-        float3 G = f3(g4.x, g4.y, g4.z);
-        float3 a = a0 + (float)i * ax + (float)j * ay + (float)l * az;
-        float gw = dot(G, a) + g4.w * k.p_mass;
-        float3 wG = (s.wx[i] * s.wy[j] * s.wz[l]) * G;
-        S0 += wG;
-        if (i) m0 += (float)i * wG;
-        if (j) m1 += (float)j * wG;
-        if (l) m2 += (float)l * wG;
-        gwx[i] += gw * s.wy[j] * s.wz[l];
-        gwy[j] += gw * s.wx[i] * s.wz[l];
-        gwz[l] += gw * s.wx[i] * s.wy[j];
-      }
-  p2g_adj_finish(k, gid, s, o, mu, lam, C, F, adj_in, adj_out, S0, m0, m1, m2, gwx, gwy, gwz);
+  p2g_adj_particle(k, gid, env, fin, adj_in, adj_out, mat, Ga, svd_in);
 }
 
 // plane-split p2g.grad for small engines: three threads per particle gather one x-plane of the stencil each

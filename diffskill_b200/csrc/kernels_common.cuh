@@ -11,22 +11,7 @@
 #include "mpm_math.cuh"
 #include "tools.cuh"
 
-#define FRAME_COMPS 24
-enum { CX = 0, CV = 3, CC = 6, CF = 15 };
-
-struct SimConst {
-  int n, nt, ntile, nnode;  // grid nodes per axis, tiles per axis, tiles, nodes (per env)
-  int B, Npad, stride;      // envs, padded capacity, B*Npad
-  int S, K, npairs;         // substeps, tools, tool-tool pairs
-  int gf_mode;              // ground friction: 0 zero-normal, 1 Coulomb, 2 stick (mpm_simulator.py:245-258)
-  float dt, dx, inv_dx, p_mass, c_stress, c_C, x_hi, x_lo, m_eps, ground_friction;
-  float grav[3];            // (dt * g) * 30, mpm_simulator.py:235
-  int pairs[DSK_MAX_PAIRS][2];
-#ifdef DSK_TIMELINE
-  struct TlRec* tl;         // device timeline records (profiling build only)
-  int tl_slot;              // record of this launch, < 0: none
-#endif
-};
+#include "particle_math.cuh"
 
 // Profiling build (-DDSK_TIMELINE, libdiffskill_mpm_tl.so): every kernel stamps %globaltimer at its first and last
 // warp into the record of its launch, which gives per-kernel start/end times INSIDE replayed CUDA graphs -- where
@@ -61,64 +46,6 @@ struct TlScope {
 DSK_DEV int node_offset(int X, int Y, int Z, int nt) {
   int tile = ((X >> 2) * nt + (Y >> 2)) * nt + (Z >> 2);
   return (tile << 6) | ((X & 3) << 4) | ((Y & 3) << 2) | (Z & 3);
-}
-
-// Quadratic B-spline stencil of one coordinate, mpm_simulator.py:201-204.  The cell index is
-// integer work and must be bit-exact: separate roundings, truncation toward zero.
-DSK_DEV void bspline1(float x, float inv_dx, int n, int& base, float& fx, float w[3]) {
-  float xg = __fmul_rn(x, inv_dx);
-  int b = (int)__fsub_rn(xg, 0.5f);
-  b = max(0, min(b, n - 3));  // no-op for any state the reference can represent; keeps NaN/blown-up states in bounds
-  base = b;
-  fx = __fsub_rn(xg, (float)b);
-  float a = 1.5f - fx, c = fx - 1.f, d = fx - 0.5f;
-  w[0] = 0.5f * (a * a);
-  w[1] = 0.75f - c * c;
-  w[2] = 0.5f * (d * d);
-}
-// d w / d fx
-DSK_DEV void bspline1_grad(float fx, float dw[3]) {
-  dw[0] = -(1.5f - fx);
-  dw[1] = -2.f * (fx - 1.f);
-  dw[2] = fx - 0.5f;
-}
-
-struct Stencil {
-  int ox[3], oy[3], oz[3];  // per-axis partial node offsets (tile-major)
-  float wx[3], wy[3], wz[3];
-  float fx, fy, fz;
-  int bx, by, bz;
-};
-DSK_DEV void make_stencil(const SimConst& k, float x, float y, float z, Stencil& s) {
-  bspline1(x, k.inv_dx, k.n, s.bx, s.fx, s.wx);
-  bspline1(y, k.inv_dx, k.n, s.by, s.fy, s.wy);
-  bspline1(z, k.inv_dx, k.n, s.bz, s.fz, s.wz);
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    int X = s.bx + i, Y = s.by + i, Z = s.bz + i;
-    s.ox[i] = ((X >> 2) * k.nt * k.nt << 6) | ((X & 3) << 4);
-    s.oy[i] = ((Y >> 2) * k.nt << 6) | ((Y & 3) << 2);
-    s.oz[i] = ((Z >> 2) << 6) | (Z & 3);
-  }
-}
-
-DSK_DEV M3 load_m3(const float* __restrict__ f, int comp0, int stride, int gid) {
-  M3 A;
-#pragma unroll
-  for (int i = 0; i < 9; i++) A.m[i] = f[(comp0 + i) * stride + gid];
-  return A;
-}
-DSK_DEV void store_m3(float* __restrict__ f, int comp0, int stride, int gid, const M3& A) {
-#pragma unroll
-  for (int i = 0; i < 9; i++) f[(comp0 + i) * stride + gid] = A.m[i];
-}
-DSK_DEV float3 load_v3(const float* __restrict__ f, int comp0, int stride, int gid) {
-  return f3(f[comp0 * stride + gid], f[(comp0 + 1) * stride + gid], f[(comp0 + 2) * stride + gid]);
-}
-DSK_DEV void store_v3(float* __restrict__ f, int comp0, int stride, int gid, float3 v) {
-  f[comp0 * stride + gid] = v.x;
-  f[(comp0 + 1) * stride + gid] = v.y;
-  f[(comp0 + 2) * stride + gid] = v.z;
 }
 
 // vector reduction to global memory: one RED.E.ADD.F32x4 (sm_90+) instead of four scalar REDs

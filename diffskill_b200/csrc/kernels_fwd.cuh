@@ -8,92 +8,6 @@
 #include "kernels_common.cuh"
 #include "svd3.cuh"
 
-// ---- plasticity: compute_von_mises, mpm_simulator.py:165-182 ---------------------------------------
-struct ReturnMap {
-  bool yields;
-  float3 sc;   // clamped sigma
-  float3 eps;  // log sc
-  float3 eh;   // deviatoric part
-  float ehn;   // its eps-norm
-  float dg;    // delta_gamma
-  float3 e;    // exp of the returned log-strain
-};
-DSK_DEV M3 von_mises(const M3& Ftmp, const M3& U, float3 sig, const M3& V, float ys, float mu, ReturnMap& r) {
-  r.sc = f3(tmax(sig.x, 0.05f), tmax(sig.y, 0.05f), tmax(sig.z, 0.05f));
-  r.eps = f3(__logf(r.sc.x), __logf(r.sc.y), __logf(r.sc.z));   // MUFU log/exp: the reference runs fast_math=True
-  float mean = (r.eps.x + r.eps.y + r.eps.z) / 3.f;
-  r.eh = f3(r.eps.x - mean, r.eps.y - mean, r.eps.z - mean);
-  r.ehn = sqrtf(dot(r.eh, r.eh) + 1e-8f);
-  r.dg = r.ehn - ys / (2.f * mu);
-  r.yields = r.dg > 0.f;
-  if (r.yields) {
-    float kf = r.dg / r.ehn;
-    r.e = f3(__expf(r.eps.x - kf * r.eh.x), __expf(r.eps.y - kf * r.eh.y), __expf(r.eps.z - kf * r.eh.z));
-    M3 US;
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-      US.m[i * 3 + 0] = U.m[i * 3 + 0] * r.e.x;
-      US.m[i * 3 + 1] = U.m[i * 3 + 1] * r.e.y;
-      US.m[i * 3 + 2] = U.m[i * 3 + 2] * r.e.z;
-    }
-    return mmT(US, V);
-  }
-  return Ftmp;
-}
-
-// everything p2g computes per particle before the scatter
-struct P2GParticle {
-  M3 Ftmp, U, V, newF, affine;
-  float3 sig;
-  ReturnMap rm;
-  float J;
-};
-// HAVE_SVD: o.U, o.sig, o.V were read from the SVD tape of the forward pass (the adjoint's fused recompute,
-// mpm_simulator.py:330-333, then skips the Jacobi sweeps -- a quarter of its instructions)
-template <bool HAVE_SVD>
-DSK_DEV void p2g_particle_impl(const SimConst& k, const M3& C, const M3& F, float mu, float lam, float ys, P2GParticle& o) {
-  M3 Mx;
-#pragma unroll
-  for (int i = 0; i < 9; i++) Mx.m[i] = ((i % 4 == 0) ? 1.f : 0.f) + k.dt * C.m[i];
-  o.Ftmp = mm(Mx, F);  // compute_F_tmp
-  if (!HAVE_SVD) svd3(o.Ftmp, o.U, o.sig, o.V);
-  o.newF = von_mises(o.Ftmp, o.U, o.sig, o.V, ys, mu, o.rm);
-  o.J = det3(o.newF);
-  M3 R = mmT(o.U, o.V);
-  M3 A;
-#pragma unroll
-  for (int i = 0; i < 9; i++) A.m[i] = (2.f * mu) * (o.newF.m[i] - R.m[i]);
-  M3 st = mmT(A, o.newF);
-  float vol = (lam * o.J) * (o.J - 1.f);
-  st.m[0] += vol;
-  st.m[4] += vol;
-  st.m[8] += vol;
-#pragma unroll
-  for (int i = 0; i < 9; i++) o.affine.m[i] = k.c_stress * st.m[i] + k.p_mass * C.m[i];
-}
-DSK_DEV void p2g_particle(const SimConst& k, const M3& C, const M3& F, float mu, float lam, float ys, P2GParticle& o) {
-  p2g_particle_impl<false>(k, C, F, mu, lam, ys, o);
-}
-// SVD tape: [S][SVD_COMPS][stride] per step slot, U (9), sigma (3), V (9) of substep j's F_tmp
-#define SVD_COMPS 21
-DSK_DEV void store_svd(float* __restrict__ t, int stride, int gid, const P2GParticle& o) {
-  store_m3(t, 0, stride, gid, o.U);
-  store_v3(t, 9, stride, gid, o.sig);
-  store_m3(t, 12, stride, gid, o.V);
-}
-// p2g_particle for the adjoint: from the tape when there is one
-DSK_DEV void p2g_particle_adj(const SimConst& k, const float* __restrict__ svd, int gid, const M3& C, const M3& F, float mu,
-                              float lam, float ys, P2GParticle& o) {
-  if (svd) {
-    o.U = load_m3(svd, 0, k.stride, gid);
-    o.sig = load_v3(svd, 9, k.stride, gid);
-    o.V = load_m3(svd, 12, k.stride, gid);
-    p2g_particle_impl<true>(k, C, F, mu, lam, ys, o);
-  } else {
-    p2g_particle_impl<false>(k, C, F, mu, lam, ys, o);
-  }
-}
-
 // MINB = min CTAs/SM the register allocation must allow: 1 for small (latency-bound) problems -- all registers, no
 // spills; 3 for large batches where occupancy hides the scatter latency
 template <bool WRITE_F, int MINB>
@@ -132,103 +46,6 @@ __global__ void __launch_bounds__(128, MINB)
     float3 a = a0 + (float)i * ax + (float)j * ay + (float)l * az;
     return make_float4(w * a.x, w * a.y, w * a.z, w * k.p_mass);
   });
-}
-
-// ---- grid_op for one node ---------------------------------------------------------------------------
-// boundary conditions of mpm_simulator.py:241-260; returns the post-boundary velocity
-DSK_DEV float3 grid_boundary(const SimConst& k, int I0, int I1, int I2, float3 v) {
-  const int bound = 3;
-  int I[3] = {I0, I1, I2};
-#pragma unroll
-  for (int d = 0; d < 3; d++) {
-    if (I[d] < bound && comp(v, d) < 0.f) {
-      if (d != 1 || k.gf_mode == 0) {
-        setcomp(v, d, 0.f);
-      } else if (k.gf_mode == 1) {
-        float lin = v.y + 1e-30f;
-        float3 off = f3((float)I0 * 1e-30f, (float)I1 * 1e-30f, (float)I2 * 1e-30f);
-        float3 vit = f3(v.x - off.x, v.y - lin - off.y, v.z - off.z);
-        float lit = sqrtf(dot(vit, vit) + 1e-8f);
-        float sc = tmax(1.f + k.ground_friction * lin / lit, 0.f);
-        v = f3(sc * (vit.x + off.x), 0.f, sc * (vit.z + off.z));
-      } else {
-        v = f3(0.f, 0.f, 0.f);
-      }
-    }
-    if (I[d] > k.n - bound && comp(v, d) > 0.f) setcomp(v, d, 0.f);
-  }
-  return v;
-}
-DSK_DEV float3 grid_boundary_adj(const SimConst& k, int I0, int I1, int I2, float3 v, float3 g) {
-  // replay forward, remember the inputs of the three stages, then reverse
-  const int bound = 3;
-  int I[3] = {I0, I1, I2};
-  float3 vin[3];
-#pragma unroll
-  for (int d = 0; d < 3; d++) {
-    vin[d] = v;
-    if (I[d] < bound && comp(v, d) < 0.f) {
-      if (d != 1 || k.gf_mode == 0) {
-        setcomp(v, d, 0.f);
-      } else if (k.gf_mode == 1) {
-        float lin = v.y + 1e-30f;
-        float3 off = f3((float)I0 * 1e-30f, (float)I1 * 1e-30f, (float)I2 * 1e-30f);
-        float3 vit = f3(v.x - off.x, v.y - lin - off.y, v.z - off.z);
-        float lit = sqrtf(dot(vit, vit) + 1e-8f);
-        float sc = tmax(1.f + k.ground_friction * lin / lit, 0.f);
-        v = f3(sc * (vit.x + off.x), 0.f, sc * (vit.z + off.z));
-      } else {
-        v = f3(0.f, 0.f, 0.f);
-      }
-    }
-    if (I[d] > k.n - bound && comp(v, d) > 0.f) setcomp(v, d, 0.f);
-  }
-#pragma unroll
-  for (int d = 2; d >= 0; d--) {
-    float3 u = vin[d];
-    // state after the first `if` of stage d
-    float3 mid = u;
-    bool lower = I[d] < bound && comp(u, d) < 0.f;
-    float lin = 0.f, lit = 1.f, a = 0.f, sc = 0.f;
-    float3 vit = f3(0, 0, 0), off = f3(0, 0, 0);
-    if (lower) {
-      if (d != 1 || k.gf_mode == 0) {
-        setcomp(mid, d, 0.f);
-      } else if (k.gf_mode == 1) {
-        lin = u.y + 1e-30f;
-        off = f3((float)I0 * 1e-30f, (float)I1 * 1e-30f, (float)I2 * 1e-30f);
-        vit = f3(u.x - off.x, u.y - lin - off.y, u.z - off.z);
-        lit = sqrtf(dot(vit, vit) + 1e-8f);
-        a = 1.f + k.ground_friction * lin / lit;
-        sc = tmax(a, 0.f);
-        mid = f3(sc * (vit.x + off.x), 0.f, sc * (vit.z + off.z));
-      } else {
-        mid = f3(0.f, 0.f, 0.f);
-      }
-    }
-    if (I[d] > k.n - bound && comp(mid, d) > 0.f) setcomp(g, d, 0.f);
-    if (lower) {
-      if (d != 1 || k.gf_mode == 0) {
-        setcomp(g, d, 0.f);
-      } else if (k.gf_mode == 1) {
-        g.y = 0.f;  // v_out[1] = 0
-        float3 w = f3(vit.x + off.x, vit.y + off.y, vit.z + off.z);
-        float gsc = dot(g, w);
-        float3 gvit = sc * g;
-        float ga = (0.f < a) ? gsc : 0.f;  // max(a, 0): a gets it iff 0 < a
-        float glin = ga * k.ground_friction / lit;
-        float glit = -ga * k.ground_friction * lin / (lit * lit);
-        gvit += (glit / lit) * vit;
-        // vit = u - lin*e_y - off ; lin = u.y + 1e-30
-        glin -= gvit.y;
-        g = gvit;
-        g.y += glin;
-      } else {
-        g = f3(0.f, 0.f, 0.f);
-      }
-    }
-  }
-  return g;
 }
 
 #define GRID_CTA 64
@@ -291,12 +108,6 @@ struct GridTools {
   FrameTable ft;
 };
 DSK_DEV Frame frame_of_pose(const Pose& P, float flag) { return flag == 0.f ? tool_frame(P) : jaw_frame(P, flag); }
-struct ContactGeom {   // per (node, frame), shared memory
-  float influence;     // < 0: contact inactive
-  float3 D, cv;
-  float3 pl, nraw;     // tool-local node position, un-normalised local normal and its length: re-used by the adjoint
-  float L;
-};
 struct TileFrames {    // per tile-iteration, shared memory
   Frame F0[MAX_FRAMES], F1[MAX_FRAMES];
   int active[MAX_FRAMES];
@@ -334,27 +145,6 @@ DSK_DEV void prepare_tile_frame(const SimConst& k, const ToolParams* sT, const F
                                 TileFrames& tf) {
   tf.active[y] = prepare_frame(k, sT, ft, y, poses, env, j, tx, ty, tz, tf.F0[y], tf.F1[y]);
 }
-DSK_DEV void contact_geometry(const ToolParams& T, int kind, const Frame& F0, const Frame& F1, float3 p, float dt,
-                              ContactGeom& g) {
-  float3 pl = inv_trans(F0, p);
-  float dist = local_sdf(T, kind, pl);
-  float influence;
-  if (contact_active(dist, T.softness, influence)) {
-    g.influence = influence;
-    float L;
-    float3 n = local_normal_raw(T, kind, pl, L);
-    g.D = qrot_rn(F0.q, f3(__fdiv_rn(n.x, L), __fdiv_rn(n.y, L), __fdiv_rn(n.z, L)));   // primive_base.py:80-85
-    // collider_v (primive_base.py:87-94): the relative position IS the local point
-    float3 np = add3_rn(qrot_rn(F1.q, pl), F1.o);
-    g.cv = f3(__fdiv_rn(sub_rn(np.x, p.x), dt), __fdiv_rn(sub_rn(np.y, p.y), dt), __fdiv_rn(sub_rn(np.z, p.z), dt));
-    g.pl = pl;
-    g.nraw = n;
-    g.L = L;
-  } else {
-    g.influence = -1.f;
-  }
-}
-
 #define GRID_NODES 64
 __global__ void __launch_bounds__(GRID_CTA)
     k_clear_set(SimConst k, const int* __restrict__ list, const int* __restrict__ count, float4* c0, float4* c1, float4* c2) {
@@ -553,16 +343,6 @@ __global__ void __launch_bounds__(GRID_NODES)
     G0[o] = d[threadIdx.x];
     Gv[o] = d[64 + threadIdx.x];
   }
-}
-
-// tail of g2p: new_C = c_C (M - new_v (x) fx) and the clamped position update
-DSK_DEV void g2p_finish(const SimConst& k, const Stencil& s, float3 x, float3 nv, float3 m0, float3 m1, float3 m2,
-                        float3& nx, M3& nC) {
-  nC.m[0] = k.c_C * (m0.x - nv.x * s.fx); nC.m[1] = k.c_C * (m1.x - nv.x * s.fy); nC.m[2] = k.c_C * (m2.x - nv.x * s.fz);
-  nC.m[3] = k.c_C * (m0.y - nv.y * s.fx); nC.m[4] = k.c_C * (m1.y - nv.y * s.fy); nC.m[5] = k.c_C * (m2.y - nv.y * s.fz);
-  nC.m[6] = k.c_C * (m0.z - nv.z * s.fx); nC.m[7] = k.c_C * (m1.z - nv.z * s.fy); nC.m[8] = k.c_C * (m2.z - nv.z * s.fz);
-  nx = f3(tmax(tmin(x.x + k.dt * nv.x, k.x_hi), k.x_lo), tmax(tmin(x.y + k.dt * nv.y, k.x_hi), k.x_lo),
-          tmax(tmin(x.z + k.dt * nv.z, k.x_hi), k.x_lo));
 }
 
 // g2p of one particle (mpm_simulator.py:264-283): new_v = sum w g ; new_C = 4 inv_dx sum w g (x) (offset - fx)

@@ -1,0 +1,120 @@
+"""CPU twin of one adjoint substep of the CUDA engine against the oracle (no GPU).
+
+`tests/host_check/host_twin.cpp` strings the product's own device functions (diffskill_b200/csrc/particle_math.cuh and
+tools.cuh, compiled by g++) into g2p.grad -> grid_op.grad -> p2g.grad for a dense grid: the arithmetic of the plain
+kernel family without its launch geometry (warp scatters, tile culling, shared memory, graphs).  It is fed the oracle's
+state of a substep deep inside a multi-step rollout -- regimes the small per-substep GPU cases do not reach -- and must
+reproduce the oracle's substep_grad (mpm_simulator.py:325-345) under the parity rule of the GPU tests.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import perturbed_state, relerr, small_dough, tool_start
+from diffskill_b200.engine import make_config
+from oracle import oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HC_DIR = os.path.join(HERE, 'host_check')
+CSRC = os.path.join(os.path.dirname(HERE), 'diffskill_b200', 'csrc')
+FP = C.POINTER(C.c_float)
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a):
+    return a.ctypes.data_as(FP)
+
+
+@pytest.fixture(scope='module')
+def twin():
+    so = os.path.join(HC_DIR, 'libhost_twin.so')
+    srcs = [os.path.join(HC_DIR, 'host_twin.cpp'), os.path.join(HC_DIR, 'cuda_shim.h')] + \
+           [os.path.join(CSRC, f) for f in ('particle_math.cuh', 'tools.cuh', 'mpm_math.cuh', 'svd3.cuh')]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(['g++', '-O1', '-std=c++17', '-ffp-contract=off', '-fPIC', '-shared', '-w', '-o', so, srcs[0]])
+    return C.CDLL(so)
+
+
+def _rollout(name, n, steps, f64):
+    scene, cfg, x0 = small_dough(name, n, 0)
+    v0, F0, C0 = perturbed_state(x0, 1)
+    S = scene.substeps
+    o = orc.Oracle(scene, n, steps * S + 2, f64=f64, threads=4)
+    o.set_frame(0, f32(x0), f32(v0), f32(F0), f32(C0))
+    for i, s in enumerate(tool_start(name, scene)):
+        o.set_tool_state(0, i, f32(s))
+    acts = f32(np.random.RandomState(3).uniform(-1, 1, (steps, scene.action_dim)) * 0.7)
+    for s in range(steps):
+        o.forward_step(s, acts[s])
+    return scene, o
+
+
+# (scene, env steps rolled out, frames inside the LAST step whose adjoint substep is checked)
+CASES = [('LiftSpread-v1', 1, (3, 17)), ('GatherMove-v1', 2, (25,)), ('CutRearrange-v1', 2, (40,)),
+         ('Rope-v1', 3, (40, 47, 55)), ('Torus-v1', 2, (30,)), ('Gripper2-synthetic', 2, (33,)), ('Move-v1', 2, (28,))]
+
+
+@pytest.mark.parametrize('name,steps,frames', CASES)
+def test_adjoint_substep_twin_matches_oracle(name, steps, frames, twin):
+    n = 400
+    scene, o32 = _rollout(name, n, steps, False)
+    _, o64 = _rollout(name, n, steps, True)
+    cfgc = make_config(scene, 1, n, 1, 1, True, 666., 0)
+    K, G = len(scene.tools), scene.n_grid ** 3
+    rng = np.random.RandomState(5)
+    for f in frames:
+        # identical fp32 state at frame f in both oracles, then the forward substep f (grids, frame f+1)
+        x, v, F, Cm = [f32(a) for a in o32.get_frame(f)]
+        o64.set_frame(f, x, v, F, Cm)
+        for i in range(K):
+            for ff in (f, f + 1):
+                o64.set_tool_state(ff, i, f32(o32.get_tool_state(ff, i)))
+        gxn, gvn = f32(rng.normal(size=(n, 3))), f32(rng.normal(size=(n, 3)) * 0.01)
+        gFn, gCn = f32(rng.normal(size=(n, 3, 3)) * 0.1), f32(rng.normal(size=(n, 3, 3)) * 1e-3)
+        ref = []
+        for o in (o32, o64):
+            # forward_kinematics of substep f would overwrite the synced pose f+1 with the oracle's own: same values
+            o.substep(f)
+            o.zero_grad()
+            o.add_frame_grad(f + 1, gxn, gvn, gFn, gCn)
+            o.substep_grad(f)
+            g = o.get_frame_grad(f)
+            gin, _, gm = o.get_grid_grad()
+            t1 = np.stack([o.get_tool_grad(f + 1, i) for i in range(K)])
+            ref.append(dict(gx=g[0], gv=g[1], gF=g[2], gC=g[3], grid_gv=gin, grid_gm=gm, tool_f1=t1))
+        xn = f32(o32.get_frame(f + 1)[0])
+        vin, vout, m = o32.get_grid()
+        g0 = f32(np.concatenate([vin.reshape(G, 3), m.reshape(G, 1)], axis=1))
+        gvo = f32(vout.reshape(G, 3))
+        poses = f32(np.stack([[o32.get_tool_state(ff, i) for i in range(K)] for ff in (f, f + 1)]))
+        mat = f32(np.stack([np.full(n, scene.mu), np.full(n, scene.lam), np.full(n, scene.yield_stress)]))
+        gx, gv, gC, gF = (np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32), np.zeros((n, 9), np.float32),
+                          np.zeros((n, 9), np.float32))
+        ga, padj = np.zeros((G, 4), np.float32), np.zeros((2, max(K, 1), 8), np.float32)
+        twin.hc_substep_grad(C.byref(cfgc), n, _p(x), _p(v), _p(f32(Cm.reshape(n, 9))), _p(f32(F.reshape(n, 9))), _p(xn),
+                             _p(mat), _p(g0), _p(gvo), _p(poses), _p(gxn), _p(gvn), _p(f32(gCn.reshape(n, 9))),
+                             _p(f32(gFn.reshape(n, 9))), _p(gx), _p(gv), _p(gC), _p(gF), _p(ga), _p(padj))
+        mine = dict(gx=gx, gv=gv, gF=gF.reshape(n, 3, 3), gC=gC.reshape(n, 3, 3), grid_gv=ga[:, :3], grid_gm=ga[:, 3],
+                    tool_f1=padj[1, :K])
+        # particles on the yield surface take either branch under a 1-ulp difference (as in the GPU parity test)
+        sig = o64.get_svd()[2]
+        eps_ = np.log(np.maximum(sig, 0.05))
+        eh = eps_ - eps_.mean(1, keepdims=True)
+        dgamma = np.sqrt((eh ** 2).sum(1) + 1e-8) - scene.yield_stress / (2 * scene.mu)
+        keep = np.abs(dgamma) > 1e-5
+        assert keep.mean() > 0.95
+        report = {}
+        for k_ in mine:
+            a, r32, r64 = [np.asarray(z, np.float64).reshape(np.asarray(mine[k_]).shape) for z in (mine[k_], ref[0][k_], ref[1][k_])]
+            if k_ in ('gx', 'gv', 'gF', 'gC'):
+                a, r32, r64 = a[keep], r32[keep], r64[keep]
+            e32, e64, fl = relerr(a, r32), relerr(a, r64), relerr(r32, r64)
+            report[k_] = '%.1e/%.1e (floor %.1e)' % (e32, e64, fl)
+            assert e32 < 2e-4 or e64 <= max(2e-4, 3 * fl), (name, f, k_, e32, e64, fl)
+        print(name, 'frame', f, report)
