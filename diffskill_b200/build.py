@@ -11,6 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 SO = os.path.join(HERE, 'libdiffskill_mpm.so')
 SO_TIMELINE = os.path.join(HERE, 'libdiffskill_mpm_tl.so')   # profiling build, see dsk_timeline_* in the header
+SO_PRECISE = os.path.join(HERE, 'libdiffskill_mpm_pm.so')    # diagnostic build: correctly rounded log/exp/div/rsqrt (DSK_PRECISE_MATH)
 SOURCES = ['engine.cu']
 HEADERS = ['mpm_math.cuh', 'svd3.cuh', 'tools.cuh', 'particle_math.cuh', 'kernels_common.cuh', 'kernels_aux.cuh', 'kernels_fwd.cuh',
            'kernels_bwd.cuh', os.path.join('..', '..', 'include', 'diffskill_mpm.h')]
@@ -36,8 +37,16 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False, extra=(), timeline=False):
-    """timeline=True builds the profiling variant (kernels stamp %globaltimer) next to the product library."""
+def build(force=False, verbose=False, extra=(), timeline=False, precise=False):
+    """timeline=True builds the profiling variant (kernels stamp %globaltimer) next to the product library;
+    precise=True the diagnostic variant without fast-math transcendentals."""
+    if precise:
+        cmd = [_nvcc(), '-ccbin', _host_cxx()] + NVCC_FLAGS + ['-DDSK_PRECISE_MATH'] + list(extra) + ['-o', SO_PRECISE] + \
+            [os.path.join(CSRC, s) for s in SOURCES]
+        if verbose:
+            print(' '.join(cmd))
+        subprocess.check_call(cmd)
+        return SO_PRECISE
     if timeline:
         cmd = [_nvcc(), '-ccbin', _host_cxx()] + NVCC_FLAGS + ['-DDSK_TIMELINE'] + list(extra) + ['-o', SO_TIMELINE] + \
             [os.path.join(CSRC, s) for s in SOURCES]
@@ -56,4 +65,4 @@ def build(force=False, verbose=False, extra=(), timeline=False):
 
 if __name__ == '__main__':
     build(force='--force' in sys.argv, verbose=True, extra=['-Xptxas', '-v'] if '--ptxas' in sys.argv else [],
-          timeline='--timeline' in sys.argv)
+          timeline='--timeline' in sys.argv, precise='--precise' in sys.argv)

@@ -13,6 +13,22 @@
 #define DSK_DEV __device__ __forceinline__
 #endif
 
+// Transcendentals of the return map and the reciprocals of the Jacobi SVD.  Product build: the hardware approximations
+// (the reference runs ti.init(fast_math=True), plb/engine/taichi_env.py:20).  -DDSK_PRECISE_MATH (diagnostic library
+// libdiffskill_mpm_pm.so, DSK_LIB=precise) swaps in the correctly rounded ones, to separate fast-math sensitivity of a
+// scene's gradients (yield-surface branch flips) from defects.
+#ifdef DSK_PRECISE_MATH
+#define DSK_LOG(x) logf(x)
+#define DSK_EXP(x) expf(x)
+#define DSK_FDIV(a, b) ((a) / (b))
+#define DSK_RSQRT(x) (1.f / sqrtf(x))
+#else
+#define DSK_LOG(x) __logf(x)
+#define DSK_EXP(x) __expf(x)
+#define DSK_FDIV(a, b) __fdividef(a, b)
+#define DSK_RSQRT(x) rsqrtf(x)
+#endif
+
 struct Q4 {
   float w, x, y, z;
 };

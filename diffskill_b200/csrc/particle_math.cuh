@@ -95,7 +95,7 @@ struct ReturnMap {
 };
 DSK_DEV M3 von_mises(const M3& Ftmp, const M3& U, float3 sig, const M3& V, float ys, float mu, ReturnMap& r) {
   r.sc = f3(tmax(sig.x, 0.05f), tmax(sig.y, 0.05f), tmax(sig.z, 0.05f));
-  r.eps = f3(__logf(r.sc.x), __logf(r.sc.y), __logf(r.sc.z));   // MUFU log/exp: the reference runs fast_math=True
+  r.eps = f3(DSK_LOG(r.sc.x), DSK_LOG(r.sc.y), DSK_LOG(r.sc.z));   // MUFU log/exp: the reference runs fast_math=True
   float mean = (r.eps.x + r.eps.y + r.eps.z) / 3.f;
   r.eh = f3(r.eps.x - mean, r.eps.y - mean, r.eps.z - mean);
   r.ehn = sqrtf(dot(r.eh, r.eh) + 1e-8f);
@@ -103,7 +103,7 @@ DSK_DEV M3 von_mises(const M3& Ftmp, const M3& U, float3 sig, const M3& V, float
   r.yields = r.dg > 0.f;
   if (r.yields) {
     float kf = r.dg / r.ehn;
-    r.e = f3(__expf(r.eps.x - kf * r.eh.x), __expf(r.eps.y - kf * r.eh.y), __expf(r.eps.z - kf * r.eh.z));
+    r.e = f3(DSK_EXP(r.eps.x - kf * r.eh.x), DSK_EXP(r.eps.y - kf * r.eh.y), DSK_EXP(r.eps.z - kf * r.eh.z));
     M3 US;
 #pragma unroll
     for (int i = 0; i < 3; i++) {

@@ -17,9 +17,9 @@ DSK_DEV void jacobi_pair(float& b0p, float& b1p, float& b2p, float& b0q, float& 
   if (ga != 0.f) {
     // approximate reciprocals / rsqrt (MUFU, <= 2 ulp): the rotation stays orthonormal to ~2e-7 per step, far below
     // the fp32 noise of the return map; zeta -> inf gives t -> 0
-    float zeta = __fdividef(be - al, 2.f * ga);
-    float t = copysignf(1.f, zeta) * __fdividef(1.f, fabsf(zeta) + sqrtf(1.f + zeta * zeta));
-    float c = rsqrtf(1.f + t * t), s = c * t;
+    float zeta = DSK_FDIV(be - al, 2.f * ga);
+    float t = copysignf(1.f, zeta) * DSK_FDIV(1.f, fabsf(zeta) + sqrtf(1.f + zeta * zeta));
+    float c = DSK_RSQRT(1.f + t * t), s = c * t;
     float a, b;
     a = b0p; b = b0q; b0p = c * a - s * b; b0q = s * a + c * b;
     a = b1p; b = b1q; b1p = c * a - s * b; b1q = s * a + c * b;

@@ -214,6 +214,25 @@ def test_multi_step_action_gradient_batched_layout(name, slots, tape_mib, monkey
     _multi_step_action_gradient(name, slots, tape_mib)
 
 
+@pytest.mark.xfail(reason='hypothesis check for the open Rope-v1 issue (DESIGN.md section 10), reports either way', strict=False)
+def test_rope_multi_step_gradient_without_fast_math():
+    """Diagnostic: the failing Rope-v1 case on the DSK_PRECISE_MATH build (correctly rounded log / exp / div / rsqrt in the
+    return map and the SVD, libdiffskill_mpm_pm.so).  If it passes there, the open issue is the scene's sensitivity to the
+    fast-math freedom the reference itself takes (fast_math=True) -- yield-surface branch flips -- and not a defect."""
+    import os
+    import subprocess
+    import sys
+    from diffskill_b200 import build as b
+    if not os.path.exists(b.SO_PRECISE):
+        pytest.skip('libdiffskill_mpm_pm.so not built (python -m diffskill_b200.build --precise)')
+    env = dict(os.environ, DSK_LIB='precise')
+    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.abspath(__file__), '-q', '-s', '--runxfail', '-p', 'no:cacheprovider',
+                        '-k', 'test_multi_step_action_gradient and 1-256-Rope'], env=env, capture_output=True, text=True,
+                       timeout=600)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0
+
+
 def _multi_step_action_gradient(name, slots, tape_mib):
     """3 env steps of the real substep count: checkpoint + recompute (slots=1) and full tape (slots=3)
     must both match the oracle's taped gradient (the reference's own property test, long_term_gradient.ipynb).
