@@ -84,61 +84,6 @@ __global__ void __launch_bounds__(GRID_CTA)
 // collider velocity) depends on the node and the pose only -- not on the velocity flowing through the chain of
 // tools -- so it is evaluated by one thread per (node, frame); the velocity chain itself is a few dozen flops.
 // Frames whose SDF at the tile centre exceeds the tile radius plus the soft-contact cut-off are culled per tile.
-#define MAX_FRAMES 8
-struct FrameTable {   // built once per CTA
-  int n;              // number of contact frames
-  int tool[MAX_FRAMES];
-  float flag[MAX_FRAMES];   // -1 / +1 gripper jaw, 0 plain tool
-};
-DSK_DEV void build_frame_table(const SimConst& k, const ToolParams* sT, FrameTable& ft) {
-  int n = 0;
-  for (int t = 0; t < k.K; t++) {
-    if (is_gripper(sT[t].type)) {
-      ft.tool[n] = t; ft.flag[n++] = -1.f;
-      ft.tool[n] = t; ft.flag[n++] = 1.f;
-    } else {
-      ft.tool[n] = t; ft.flag[n++] = 0.f;
-    }
-  }
-  ft.n = n;
-}
-// tool parameters + frame table, passed to the grid kernels by value (constant bank)
-struct GridTools {
-  ToolParams T[DSK_MAX_TOOLS];
-  FrameTable ft;
-};
-DSK_DEV Frame frame_of_pose(const Pose& P, float flag) { return flag == 0.f ? tool_frame(P) : jaw_frame(P, flag); }
-struct TileFrames {    // per tile-iteration, shared memory
-  Frame F0[MAX_FRAMES], F1[MAX_FRAMES];
-  int active[MAX_FRAMES];
-};
-
-DSK_DEV bool tile_any_active(const TileFrames& tf, int n) {   // uniform over the CTA
-  int a = 0;
-  for (int f = 0; f < n; f++) a |= tf.active[f];
-  return a != 0;
-}
-// prepares contact frame y of the tile's env (poses at substeps j and j+1) and decides whether the tile can touch
-// it at all
-DSK_DEV int prepare_frame(const SimConst& k, const ToolParams* sT, const FrameTable& ft, int y,
-                          const float* __restrict__ poses, int env, int j, int tx, int ty, int tz, Frame& F0, Frame& F1) {
-  int t = ft.tool[y];
-  const float* a = poses + ((size_t)(env * (k.S + 1) + j) * k.K + t) * 8;
-  Pose P0 = load_pose(a), P1 = load_pose(a + (size_t)k.K * 8);
-  F0 = frame_of_pose(P0, ft.flag[y]);
-  F1 = frame_of_pose(P1, ft.flag[y]);
-  const ToolParams& T = sT[t];
-  int kind = sdf_kind(T.type);
-  float3 c = f3(((float)(tx * 4) + 1.5f) * k.dx, ((float)(ty * 4) + 1.5f) * k.dx, ((float)(tz * 4) + 1.5f) * k.dx);
-  float reach = 2.6f * k.dx * 1.02f + 1e-4f + (T.softness > 0.f ? 2.302586f / T.softness : 0.f);
-  // cheap bounding-sphere test first, exact SDF only for tiles near the tool.  All SDFs here are 1-Lipschitz:
-  // beyond `reach` no node of the tile has dist <= 0 or influence > 0.1
-  float3 dc = c - F0.o;
-  float far = T.bound_r + reach;
-  int act = dot(dc, dc) <= far * far;
-  if (act) act = frame_sdf(T, kind, F0, c) <= reach;
-  return act;
-}
 // thread (0, y) of the (node x frame) kernels
 DSK_DEV void prepare_tile_frame(const SimConst& k, const ToolParams* sT, const FrameTable& ft, int y,
                                 const float* __restrict__ poses, int env, int j, int tx, int ty, int tz,
@@ -343,29 +288,6 @@ __global__ void __launch_bounds__(GRID_NODES)
     G0[o] = d[threadIdx.x];
     Gv[o] = d[64 + threadIdx.x];
   }
-}
-
-// g2p of one particle (mpm_simulator.py:264-283): new_v = sum w g ; new_C = 4 inv_dx sum w g (x) (offset - fx)
-//   = c_C (M - new_v (x) fx),  M = sum w g (x) offset
-DSK_DEV void g2p_particle(const SimConst& k, const Stencil& s, const float4* __restrict__ Ge, float3 x, float3& nx,
-                          float3& nv, M3& nC) {
-  nv = f3(0.f, 0.f, 0.f);
-  float3 m0 = f3(0.f, 0.f, 0.f), m1 = f3(0.f, 0.f, 0.f), m2 = f3(0.f, 0.f, 0.f);   // columns of M
-#pragma unroll
-  for (int i = 0; i < 3; i++)
-#pragma unroll
-    for (int j = 0; j < 3; j++)
-#pragma unroll
-      for (int l = 0; l < 3; l++) {
-        float4 g = Ge[s.ox[i] + s.oy[j] + s.oz[l]];
-        float w = s.wx[i] * s.wy[j] * s.wz[l];
-        float3 wg = f3(w * g.x, w * g.y, w * g.z);
-        nv += wg;
-        if (i) m0 += (float)i * wg;
-        if (j) m1 += (float)j * wg;
-        if (l) m2 += (float)l * wg;
-      }
-  g2p_finish(k, s, x, nv, m0, m1, m2, nx, nC);
 }
 
 __global__ void __launch_bounds__(128)

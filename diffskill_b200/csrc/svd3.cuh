@@ -15,11 +15,25 @@ DSK_DEV void jacobi_pair(float& b0p, float& b1p, float& b2p, float& b0q, float& 
   float be = b0q * b0q + b1q * b1q + b2q * b2q;
   float ga = b0p * b0q + b1p * b1q + b2p * b2q;
   if (ga != 0.f) {
-    // approximate reciprocals / rsqrt (MUFU, <= 2 ulp): the rotation stays orthonormal to ~2e-7 per step, far below
-    // the fp32 noise of the return map; zeta -> inf gives t -> 0
+    // approximate reciprocals (MUFU, <= 2 ulp): for the rotation ANGLE an error only changes how fast the sweeps converge;
+    // zeta -> inf gives t -> 0
     float zeta = DSK_FDIV(be - al, 2.f * ga);
     float t = copysignf(1.f, zeta) * DSK_FDIV(1.f, fabsf(zeta) + sqrtf(1.f + zeta * zeta));
+#ifdef DSK_UNBIASED_COSINE
+    // The cosine is different: unless c^2 (1 + t^2) = 1 every rotation rescales the columns of V and B, and a BIAS of the
+    // approximation (MUFU.RSQ; a plain fp32 Newton step has -1.4e-8 on average) makes sigma, R = U V^T and U f(S) V^T
+    // drift the same way for every particle in every substep.  scripts/fastmath_sensitivity.py (CPU twin of the engine):
+    // with 2-ulp errors in this cosine x.grad[0] of a 3-step rollout moves by 2.8e-3 (LiftSpread-v1) / 1.9e-2 (Rope-v1),
+    // with the FMA-residual (Markstein) step below -- unbiased to 3e-10 whatever the bias of its input, 4 instructions --
+    // by 3e-5 / 2e-4.  Compiled into the diagnostic library (DSK_PRECISE_MATH) and the CPU twin study only: the product
+    // keeps the cosine that was validated on the B200 until the refined one has been.
+    float w = fmaf(t, t, 1.f);
+    float y = DSK_RSQRT(w);
+    float r = fmaf(-(w * y), 0.5f * y, 0.5f);   // 0.5 - (w y)(y / 2): the residual, one rounding
+    float c = fmaf(y, r, y), s = c * t;
+#else
     float c = DSK_RSQRT(1.f + t * t), s = c * t;
+#endif
     float a, b;
     a = b0p; b = b0q; b0p = c * a - s * b; b0q = s * a + c * b;
     a = b1p; b = b1q; b1p = c * a - s * b; b1q = s * a + c * b;

@@ -17,13 +17,36 @@ struct float4 {
   float x, y, z, w;
 };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
-// fast-math intrinsics of the return map / SVD: exact host versions (the device ones are a few ulp off, which the tests'
-// tolerances cover)
-static inline float hc_logf(float a) { return std::log(a); }
-static inline float hc_expf(float a) { return std::exp(a); }
+// fast-math intrinsics of the return map / SVD.  Default: exact host versions (the device ones are a few ulp off, which
+// the tests' tolerances cover).  -DHC_APPROX: each carries a deterministic pseudo-random error of the size the hardware
+// approximations are allowed (log: 2^-21.4 absolute; exp, div, rsqrt: 2 ulp) -- used to study how far a scene's gradients
+// move under the fast-math freedom (scripts/fastmath_sensitivity.py), never by the tests.
+#include <cstdint>
+#include <cstring>
+static inline float hc_noise(float x) {   // in [-1, 1], deterministic in the bits of x
+  uint32_t h;
+  std::memcpy(&h, &x, 4);
+  h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+  return (float)(h & 0xFFFFFF) / (float)0x7FFFFF - 1.0f;
+}
+#ifdef HC_APPROX   /* bit mask: 1 log, 2 exp, 4 div + rsqrt (the Jacobi SVD) */
+#define HC_APPROX_ON(bit) ((HC_APPROX) & (bit))
+#else
+#define HC_APPROX_ON(bit) 0
+#endif
+static inline float hc_logf(float a) {
+  return HC_APPROX_ON(1) ? (float)(std::log((double)a) + 3.7e-7 * hc_noise(a)) : std::log(a);
+}
+static inline float hc_expf(float a) {
+  return HC_APPROX_ON(2) ? (float)(std::exp((double)a) * (1.0 + 2.4e-7 * hc_noise(a))) : std::exp(a);
+}
+static inline float rsqrtf(float a) {
+  return HC_APPROX_ON(4) ? (float)(1.0 / std::sqrt((double)a) * (1.0 + 2.4e-7 * hc_noise(a))) : 1.0f / std::sqrt(a);
+}
+static inline float __fdividef(float a, float b) {
+  return HC_APPROX_ON(4) ? (float)((double)a / (double)b * (1.0 + 2.4e-7 * hc_noise(a + b))) : a / b;
+}
 #define __logf hc_logf   /* glibc declares its own __logf / __expf */
 #define __expf hc_expf
-static inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }
-static inline float __fdividef(float a, float b) { return a / b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline int min(int a, int b) { return a < b ? a : b; }

@@ -1,4 +1,4 @@
-"""CPU twin of one adjoint substep of the CUDA engine against the oracle (no GPU).
+"""CPU twin of one substep and one adjoint substep of the CUDA engine against the oracle (no GPU).
 
 `tests/host_check/host_twin.cpp` strings the product's own device functions (diffskill_b200/csrc/particle_math.cuh and
 tools.cuh, compiled by g++) into g2p.grad -> grid_op.grad -> p2g.grad for a dense grid: the arithmetic of the plain
@@ -13,7 +13,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from helpers import perturbed_state, relerr, small_dough, tool_start
+from helpers import ENVS, perturbed_state, relerr, small_dough, tool_start
 from diffskill_b200.engine import make_config
 from oracle import oracle as orc
 
@@ -118,3 +118,74 @@ def test_adjoint_substep_twin_matches_oracle(name, steps, frames, twin):
             report[k_] = '%.1e/%.1e (floor %.1e)' % (e32, e64, fl)
             assert e32 < 2e-4 or e64 <= max(2e-4, 3 * fl), (name, f, k_, e32, e64, fl)
         print(name, 'frame', f, report)
+
+
+@pytest.mark.parametrize('name,steps,frames', CASES)
+def test_forward_substep_twin_matches_oracle(name, steps, frames, twin):
+    """k_p2g -> k_grid (contact chain, boundary; with and without the kernels' per-tile frame culling) -> k_g2p from the
+    product's device functions, on the oracle's state at the same deep frames: one substep of state within the per-substep
+    parity tolerances of the GPU tests, and culling must not change a single bit."""
+    n = 400
+    scene, o32 = _rollout(name, n, steps, False)
+    _, o64 = _rollout(name, n, steps, True)
+    cfgc = make_config(scene, 1, n, 1, 1, True, 666., 0)
+    K, G = len(scene.tools), scene.n_grid ** 3
+    mat = f32(np.stack([np.full(n, scene.mu), np.full(n, scene.lam), np.full(n, scene.yield_stress)]))
+    for f in frames:
+        x, v, F, Cm = [f32(a) for a in o32.get_frame(f)]
+        o64.set_frame(f, x, v, F, Cm)
+        for i in range(K):
+            for ff in (f, f + 1):
+                o64.set_tool_state(ff, i, f32(o32.get_tool_state(ff, i)))
+        poses = f32(np.stack([[o32.get_tool_state(ff, i) for i in range(K)] for ff in (f, f + 1)]))
+        outs = []
+        for cull in (1, 0):
+            xn, vn = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+            Cn, Fn = np.zeros((n, 9), np.float32), np.zeros((n, 9), np.float32)
+            g0, gvo = np.zeros((G, 4), np.float32), np.zeros((G, 3), np.float32)
+            twin.hc_substep(C.byref(cfgc), n, _p(x), _p(v), _p(f32(Cm.reshape(n, 9))), _p(f32(F.reshape(n, 9))), _p(mat),
+                            _p(poses), cull, _p(xn), _p(vn), _p(Cn), _p(Fn), _p(g0), _p(gvo))
+            outs.append((xn, vn, Cn, Fn, g0, gvo))
+        for a, b in zip(*outs):
+            assert np.array_equal(a, b), 'tile culling changed the result'
+        xn, vn, Cn, Fn, g0, gvo = outs[0]
+        refs = []
+        for o in (o32, o64):
+            o.substep(f)
+            fr = o.get_frame(f + 1)
+            vin, vout, m = o.get_grid()
+            refs.append(dict(x=fr[0], v=fr[1], F=fr[2].reshape(n, 9), C=fr[3].reshape(n, 9), grid_m=m.reshape(G),
+                             grid_p=vin.reshape(G, 3), grid_v=vout.reshape(G, 3)))
+        mine = dict(x=xn, v=vn, F=Fn, C=Cn, grid_m=g0[:, 3], grid_p=g0[:, :3], grid_v=gvo)
+        report = {}
+        for k_, tol in (('x', 1e-6), ('v', 2e-5), ('F', 2e-6), ('C', 5e-5), ('grid_m', 1e-6), ('grid_p', 2e-6), ('grid_v', 5e-5)):
+            e32, e64, fl = relerr(mine[k_], refs[0][k_]), relerr(mine[k_], refs[1][k_]), relerr(refs[0][k_], refs[1][k_])
+            report[k_] = '%.1e/%.1e (floor %.1e)' % (e32, e64, fl)
+            assert e32 < tol or e64 <= max(tol, 3 * fl), (name, f, k_, e32, e64, fl)
+        # integer work: occupancy (mass > 0) identical to the oracle's
+        assert np.array_equal(g0[:, 3] > 0, refs[0]['grid_m'] > 0)
+        print(name, 'frame', f, report)
+
+
+@pytest.mark.parametrize('name', ENVS)
+def test_tile_culling_is_conservative(name, twin):
+    """The grid kernels skip a contact frame for a whole 4x4x4 tile when a bounding sphere and the SDF at the tile centre
+    say no node of it can be in contact (prepare_frame).  Exhaustively over every node of the grid and a few generic tool
+    poses: no (node, frame) pair with an active contact is ever culled."""
+    scene, cfg, _ = small_dough(name, 8)
+    cfgc = make_config(scene, 1, 8, 1, 1, True, 666., 0)
+    rng = np.random.RandomState(23)
+    total = 0
+    for trial in range(4):
+        st = [np.array(s_, dtype=np.float64) for s_ in tool_start(name, scene)]
+        if trial:
+            for s_ in st:
+                s_[:3] += rng.uniform(-0.03, 0.03, 3)
+                s_[3:7] += rng.normal(size=4) * 0.3
+                s_[3:7] /= np.linalg.norm(s_[3:7])
+        poses = f32(np.stack([st, st]))
+        out = np.zeros(16, np.float32)
+        bad = twin.hc_culling_check(C.byref(cfgc), _p(poses), _p(out))
+        assert bad == 0, (name, trial, out[:9])
+        total += int(out[1])
+    assert total > 50     # the poses do touch the grid
