@@ -72,6 +72,7 @@ def run(name, twins, H=3, n=800):
     d32 = np.abs(refs[0][0] - refs[1][0]).max(1)
     print(f'{name}: fp32 oracle vs fp64: x.grad[0] %.1e (%d of %d particles above 1e-4 of the max), v %.1e' %
           (relerr(refs[0][0], refs[1][0]), (d32 > 1e-4 * sc).sum(), n, relerr(refs[0][1][1], refs[1][1][1])))
+    results = {}
     for tag, tw in twins:
         fr = [(f32(x0), f32(v0), f32(np.reshape(C0, (n, 9))), f32(np.reshape(F0, (n, 9))))]
         grids = []
@@ -99,6 +100,10 @@ def run(name, twins, H=3, n=800):
               'state after %d substeps: v %.1e F %.1e vs fp32 oracle' %
               (relerr(a[0], refs[0][0]), relerr(a[0], refs[1][0]), (d > 1e-4 * sc).sum(), H * S,
                relerr(fr[-1][1], refs[0][1][1]), relerr(fr[-1][3].reshape(n, 3, 3), refs[0][1][2])))
+        results[tag] = dict(gx_vs_f32=relerr(a[0], refs[0][0]), gx_vs_f64=relerr(a[0], refs[1][0]),
+                            floor=relerr(refs[0][0], refs[1][0]), particles_off=int((d > 1e-4 * sc).sum()),
+                            v_vs_f32=relerr(fr[-1][1], refs[0][1][1]), x_vs_f32=relerr(fr[-1][0], refs[0][1][0]))
+    return results
 
 
 if __name__ == '__main__':

@@ -189,3 +189,19 @@ def test_tile_culling_is_conservative(name, twin):
         assert bad == 0, (name, trial, out[:9])
         total += int(out[1])
     assert total > 50     # the poses do touch the grid
+
+
+@pytest.mark.parametrize('name', ['LiftSpread-v1', 'GatherMove-v1', 'Move-v1'])
+def test_chained_twin_rollout_matches_oracle(name):
+    """The twin's forward substep chained over a whole 3-step rollout (57 substeps), then its adjoint substep chained all
+    the way back: the final state and x.grad[0] must match the oracle's rollout and backward pass -- the engine's arithmetic
+    end to end, on the CPU (scripts/fastmath_sensitivity.py holds the loop; its other builds study hardware approximations).
+    Scenes whose 3-step gradient sits on a discrete branch (Rope-v1, Torus-v1, CutRearrange-v1: DESIGN.md section 10) are
+    left to that study -- there even this twin and the oracle, 1e-7 apart per substep, can land 3e-3 apart."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), 'scripts'))
+    import fastmath_sensitivity as fs
+    tw = fs.build('exact_test', ['-O1', '-ffp-contract=off'])
+    r = fs.run(name, [('exact', tw)], H=3, n=400)['exact']
+    assert r['x_vs_f32'] < 2e-6 and r['v_vs_f32'] < 2e-4, r
+    assert r['gx_vs_f32'] < 5e-4 or r['gx_vs_f64'] <= max(5e-4, 3 * r['floor']), r
