@@ -215,10 +215,7 @@ def test_multi_step_action_gradient_batched_layout(name, slots, tape_mib, monkey
     _multi_step_action_gradient(name, slots, tape_mib)
 
 
-@pytest.mark.xfail(reason='GPU check of the staged SVD-cosine fix (DESIGN.md section 10), reports either way', strict=False)
-def test_rope_multi_step_gradient_without_fast_math():
-    """Diagnostic: the Rope-v1 case on the DSK_PRECISE_MATH build (correctly rounded log / exp / div, unbiased cosine in the
-    Jacobi SVD; libdiffskill_mpm_pm.so).  The CPU study (scripts/fastmath_sensitivity.py) predicts that it passes there."""
+def _run_on_precise_library(selector):
     import os
     import subprocess
     import sys
@@ -227,10 +224,23 @@ def test_rope_multi_step_gradient_without_fast_math():
         pytest.skip('libdiffskill_mpm_pm.so not built (python -m diffskill_b200.build --precise)')
     env = dict(os.environ, DSK_LIB='precise')
     r = subprocess.run([sys.executable, '-m', 'pytest', os.path.abspath(__file__), '-q', '-s', '--runxfail', '-p', 'no:cacheprovider',
-                        '-k', 'test_multi_step_action_gradient and 1-256-Rope'], env=env, capture_output=True, text=True,
-                       timeout=600)
-    print(r.stdout[-3000:])
-    assert r.returncode == 0
+                        '-k', selector], env=env, capture_output=True, text=True, timeout=900)
+    print('\n'.join(l for l in r.stdout.splitlines() if 'action grad' in l or 'twin' in l or 'passed' in l or 'failed' in l))
+    return r.returncode
+
+
+@pytest.mark.xfail(reason='GPU check of the staged SVD-cosine fix (DESIGN.md section 10), reports either way', strict=False)
+def test_rope_multi_step_gradient_without_fast_math():
+    """Diagnostic: the Rope-v1 case on the DSK_PRECISE_MATH build (correctly rounded log / exp / div, unbiased cosine in the
+    Jacobi SVD; libdiffskill_mpm_pm.so).  The CPU study (scripts/fastmath_sensitivity.py) predicts that it passes there."""
+    assert _run_on_precise_library('test_multi_step_action_gradient and 1-256-Rope') == 0
+
+
+@pytest.mark.xfail(reason='GPU validation run of the staged SVD-cosine fix on every scene, reports either way', strict=False)
+def test_all_multi_step_gradients_without_fast_math():
+    """Diagnostic: the 3-step gradient property of every scene on the diagnostic library, i.e. the data the decision to
+    move the unbiased cosine into the product build needs (it re-rolls the branch every knife-edge scene takes)."""
+    assert _run_on_precise_library('test_multi_step_action_gradient and 1-256 and not Rope') == 0
 
 
 def _multi_step_action_gradient(name, slots, tape_mib):
