@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(KIN_CTA)
   __shared__ int red_i[KIN_CTA / 32];
   __shared__ int s_idx[DSK_MAX_PAIRS];
   __shared__ int s_first;
-  extern __shared__ float sAll[];           // [(S+1)][K][8] projection-free chain, then [npairs][600][3] collision samples
+  DSK_DYN_SMEM(float, sAll);           // [(S+1)][K][8] projection-free chain, then [npairs][600][3] collision samples
   int env = blockIdx.x, tid = threadIdx.x;
   const int per = k.K * 8;
   for (int i = tid; i < k.K * (int)(sizeof(ToolParams) / 4); i += blockDim.x) ((int*)sT)[i] = ((const int*)tools)[i];

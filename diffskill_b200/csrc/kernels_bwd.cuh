@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(KINADJ_CTA)
   __shared__ ToolParams sT[DSK_MAX_TOOLS];
   __shared__ float s_gu[DSK_MAX_TOOLS][8];
   __shared__ int s_any_hit;
-  extern __shared__ float dyn[];
+  DSK_DYN_SMEM(float, dyn);
   int env = blockIdx.x, tid = threadIdx.x;
   int tot = (k.S + 1) * k.K * 8;
   float* sadj = dyn;                          // [(S+1)][K][8]

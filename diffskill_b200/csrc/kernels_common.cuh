@@ -13,6 +13,13 @@
 
 #include "particle_math.cuh"
 
+// dynamic shared memory of a kernel (the CPU emulation of tests/host_check keeps it in one process-wide buffer)
+#ifdef DSK_HOST_SIMT
+#define DSK_DYN_SMEM(type, name) type* name = (type*)simt_dyn_smem.data()
+#else
+#define DSK_DYN_SMEM(type, name) extern __shared__ type name[]
+#endif
+
 // Profiling build (-DDSK_TIMELINE, libdiffskill_mpm_tl.so): every kernel stamps %globaltimer at its first and last
 // warp into the record of its launch, which gives per-kernel start/end times INSIDE replayed CUDA graphs -- where
 // CUDA events cannot be placed and ncu serialises the launches.  Compiled out of the product library.

@@ -256,7 +256,7 @@ DSK_DEV float3 mTv(const M3& A, float3 x) {
 }
 
 // warp helpers
-#ifndef DSK_HOST_CHECK
+#if !defined(DSK_HOST_CHECK) || defined(DSK_HOST_SIMT)
 DSK_DEV float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -50,3 +50,9 @@ static inline float __fdividef(float a, float b) {
 #define __expf hc_expf
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline int min(int a, int b) { return a < b ? a : b; }
+#ifdef DSK_HOST_SIMT   /* warp / block primitives and the kernel-launch emulation */
+#include "simt_shim.h"
+#endif
+#ifdef DSK_HOST_EMU    /* the CUDA runtime calls of engine.cu */
+#include "cuda_rt_shim.h"
+#endif

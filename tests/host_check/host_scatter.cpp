@@ -2,9 +2,8 @@
 // one-thread-per-particle family, warp_scatter9 of the plane-split family) executed on an emulated warp (simt_shim.h) and
 // compared by the tests with a plain per-particle accumulation, for key patterns that drive each of their regimes.
 #define DSK_HOST_CHECK 1
+#define DSK_HOST_SIMT 1
 #include <cstring>
-#include "../../diffskill_b200/csrc/mpm_math.cuh"
-#include "simt_shim.h"
 #include "../../diffskill_b200/csrc/kernels_common.cuh"
 
 extern "C" {
