@@ -9,6 +9,11 @@ from oracle import oracle as orc
 
 
 
+# torch device of the API-level tests: the engine's CPU emulation (DSK_LIB=emu, tests/host_check) works on host memory
+import os
+DEVICE = 'cpu' if os.environ.get('DSK_LIB') == 'emu' else 'cuda'
+
+
 def f32(a):
     return np.asarray(a, dtype=np.float32)
 

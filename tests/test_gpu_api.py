@@ -3,6 +3,7 @@ checked against the oracle driven through the reference's own call sequences."""
 import numpy as np
 import pytest
 
+from gpu_common import DEVICE
 from helpers import relerr
 
 pytestmark = pytest.mark.gpu
@@ -60,11 +61,11 @@ def test_gradmodel_autograd_matches_oracle(name, return_dist):
     H, S, A = 3, te.simulator.substeps, te.primitives.action_dim
     o = _oracle_for(te, H * S + 1)
     rng = np.random.RandomState(0)
-    acts = torch.tensor(rng.uniform(-1, 1, (H, A)), device='cuda', dtype=torch.float32, requires_grad=True)
+    acts = torch.tensor(rng.uniform(-1, 1, (H, A)), device=DEVICE, dtype=torch.float32, requires_grad=True)
     ncol = 6 + (func.eng.ncols if return_dist else 0)
-    W = torch.tensor(rng.normal(size=(H, n, ncol)), device='cuda', dtype=torch.float32)
-    Wc = torch.tensor(rng.normal(size=(H, len(te.primitives), 8)) * 0.1, device='cuda', dtype=torch.float32)
-    obs = func.reset(device='cuda')
+    W = torch.tensor(rng.normal(size=(H, n, ncol)), device=DEVICE, dtype=torch.float32)
+    Wc = torch.tensor(rng.normal(size=(H, len(te.primitives), 8)) * 0.1, device=DEVICE, dtype=torch.float32)
+    obs = func.reset(device=DEVICE)
     assert obs[0].shape == (n, ncol) and obs[1].shape == (len(te.primitives), 8)
     loss = 0
     for s in range(H):
