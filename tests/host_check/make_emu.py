@@ -64,7 +64,9 @@ def rewrite_launches(src):
     return ''.join(out)
 
 
-def build(verbose=False):
+def build(verbose=False, flags=(), so=None):
+    """flags / so: study variants (e.g. -DHC_APPROX=7 -ffp-contract=fast -mfma: GPU-like arithmetic, see cuda_shim.h)."""
+    so = so or SO
     os.makedirs(GEN, exist_ok=True)
     src = open(os.path.join(CSRC, 'engine.cu')).read()
     src = src.replace('#include <cuda_runtime.h>', '// (cuda_runtime.h: tests/host_check/cuda_rt_shim.h through mpm_math.cuh)')
@@ -78,11 +80,12 @@ def build(verbose=False):
         src = src.replace(old, new)
     gen = os.path.join(GEN, 'engine_emu.cpp')
     open(gen, 'w').write('#define DSK_HOST_CHECK 1\n#define DSK_HOST_SIMT 1\n#define DSK_HOST_EMU 1\n' + rewrite_launches(src))
-    cmd = ['g++', '-O1', '-std=c++17', '-ffp-contract=off', '-fPIC', '-shared', '-pthread', '-w', '-U_FORTIFY_SOURCE', '-D_FORTIFY_SOURCE=0', '-o', SO, gen]
+    cmd = ['g++', '-O1', '-std=c++17', '-fPIC', '-shared', '-pthread', '-w', '-U_FORTIFY_SOURCE', '-D_FORTIFY_SOURCE=0'] + \
+        (list(flags) or ['-ffp-contract=off']) + ['-o', so, gen]
     if verbose:
         print(' '.join(cmd))
     subprocess.check_call(cmd)
-    return SO
+    return so
 
 
 def stale():
