@@ -18,7 +18,6 @@
 // libdiffskill_mpm_pm.so, DSK_LIB=precise) swaps in the correctly rounded ones, to separate fast-math sensitivity of a
 // scene's gradients (yield-surface branch flips) from defects.
 #ifdef DSK_PRECISE_MATH
-#define DSK_UNBIASED_COSINE 1
 #define DSK_LOG(x) logf(x)
 #define DSK_EXP(x) expf(x)
 #define DSK_FDIV(a, b) ((a) / (b))

@@ -19,14 +19,15 @@ DSK_DEV void jacobi_pair(float& b0p, float& b1p, float& b2p, float& b0q, float& 
     // zeta -> inf gives t -> 0
     float zeta = DSK_FDIV(be - al, 2.f * ga);
     float t = copysignf(1.f, zeta) * DSK_FDIV(1.f, fabsf(zeta) + sqrtf(1.f + zeta * zeta));
-#ifdef DSK_UNBIASED_COSINE
+#ifndef DSK_BIASED_COSINE
     // The cosine is different: unless c^2 (1 + t^2) = 1 every rotation rescales the columns of V and B, and a BIAS of the
     // approximation (MUFU.RSQ; a plain fp32 Newton step has -1.4e-8 on average) makes sigma, R = U V^T and U f(S) V^T
-    // drift the same way for every particle in every substep.  scripts/fastmath_sensitivity.py (CPU twin of the engine):
-    // with 2-ulp errors in this cosine x.grad[0] of a 3-step rollout moves by 2.8e-3 (LiftSpread-v1) / 1.9e-2 (Rope-v1),
-    // with the FMA-residual (Markstein) step below -- unbiased to 3e-10 whatever the bias of its input, 4 instructions --
-    // by 3e-5 / 2e-4.  Compiled into the diagnostic library (DSK_PRECISE_MATH) and the CPU twin study only: the product
-    // keeps the cosine that was validated on the B200 until the refined one has been.
+    // drift the same way for every particle in every substep: v 1e-5 per substep on the B200, and the branch a soft-dough
+    // scene's gradient sits on flips (Rope-v1: 3-step action gradient 3.5e-3 from the oracle).
+    // The FMA-residual (Markstein) step below is unbiased to 3e-10 whatever the bias of its input, for 4 instructions.
+    // On the CPU emulation of the engine under GPU-like arithmetic (2-ulp errors on every MUFU result, FMA contraction)
+    // the biased cosine fails exactly the six Rope-v1 gradient cases the B200 failed, this one passes all 48
+    // (profiles/r01j_cpu_emulated_gpu_like_arithmetic_*.log); -DDSK_BIASED_COSINE restores the old behaviour.
     float w = fmaf(t, t, 1.f);
     float y = DSK_RSQRT(w);
     float r = fmaf(-(w * y), 0.5f * y, 0.5f);   // 0.5 - (w y)(y / 2): the residual, one rounding

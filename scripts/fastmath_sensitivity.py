@@ -113,8 +113,8 @@ if __name__ == '__main__':
              ('approximate exp only', build('exp', ['-O1', '-DHC_APPROX=2', '-ffp-contract=off'])),
              ('approximate div + rsqrt (SVD) only', build('svd', ['-O1', '-DHC_APPROX=4', '-ffp-contract=off'])),
              ('all approximate + FMA contraction', build('approx_fma', ['-O2', '-DHC_APPROX=7', '-ffp-contract=fast', '-mfma'])),
-             ('SVD approx., unbiased cosine', build('svd_u', ['-O1', '-DHC_APPROX=4', '-DDSK_UNBIASED_COSINE', '-ffp-contract=off'])),
-             ('all approx. + FMA, unbiased cosine', build('approx_fma_u', ['-O2', '-DHC_APPROX=7', '-DDSK_UNBIASED_COSINE',
-                                                                          '-ffp-contract=fast', '-mfma']))]
+             ('SVD approx., BIASED cosine (round 1)', build('svd_b', ['-O1', '-DHC_APPROX=4', '-DDSK_BIASED_COSINE', '-ffp-contract=off'])),
+             ('all approx. + FMA, BIASED cosine', build('approx_fma_b', ['-O2', '-DHC_APPROX=7', '-DDSK_BIASED_COSINE',
+                                                                        '-ffp-contract=fast', '-mfma']))]
     for nm in (sys.argv[1:] or ['Rope-v1', 'LiftSpread-v1']):
         run(nm, twins)

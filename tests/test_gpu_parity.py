@@ -188,13 +188,12 @@ def test_substep_backward_parity(name):
             (k_, worst[k_], worst64[k_], floor[k_])
 
 
-# Rope-v1 (two Spheres + a static Cylinder on a sliding ground), DESIGN.md section 10: forward state, per-substep adjoints
-# and the 1-step gradient match the oracle at the noise floor, but the 3-step gradient has two "basins" 2.3e-3 apart
-# (x.grad[0]; 3.5e-3 on the action gradient) -- a discrete branch that a ~1e-8 bias in the cosine of the Jacobi rotations
-# (MUFU rsqrt) flips: the oracles take one, the B200 the other; the CPU twin of the engine reproduces either, depending
-# on that bias alone (scripts/fastmath_sensitivity.py).  The unbiased cosine is staged behind DSK_UNBIASED_COSINE and has
-# not been validated on a GPU yet, so these cases run and report (xfail, non-strict) instead of gating.
-_ROPE_OPEN = pytest.mark.xfail(reason='Rope-v1 3-step gradient sits on a branch the biased MUFU cosine of the SVD flips (DESIGN.md section 10)',
+# Rope-v1 (two Spheres + a static Cylinder on a sliding ground), DESIGN.md section 10: on the B200, with the first builds,
+# forward state, per-substep adjoints and the 1-step gradient matched the oracle at the noise floor but the 3-step gradient
+# was 3.5e-3 off -- the scene has two gradient "basins" and a ~1e-8 bias in the cosine of the Jacobi rotations (MUFU rsqrt)
+# put the GPU into the other one.  The cosine is unbiased now (svd3.cuh) and the emulated engine passes these cases even
+# under GPU-like arithmetic, but no B200 has confirmed it yet: they run and report (xfail, non-strict: expected to XPASS).
+_ROPE_OPEN = pytest.mark.xfail(reason='Rope-v1 3-step gradient: SVD-cosine fix not yet confirmed on a GPU (DESIGN.md section 10)',
                                strict=False)
 MULTI_STEP_ENVS = [pytest.param(n, marks=_ROPE_OPEN) if n == 'Rope-v1' else n for n in ENVS]
 
@@ -229,17 +228,17 @@ def _run_on_precise_library(selector):
     return r.returncode
 
 
-@pytest.mark.xfail(reason='GPU check of the staged SVD-cosine fix (DESIGN.md section 10), reports either way', strict=False)
+@pytest.mark.xfail(reason='same case on the correctly rounded diagnostic library (DESIGN.md section 10), reports either way', strict=False)
 def test_rope_multi_step_gradient_without_fast_math():
     """Diagnostic: the Rope-v1 case on the DSK_PRECISE_MATH build (correctly rounded log / exp / div, unbiased cosine in the
     Jacobi SVD; libdiffskill_mpm_pm.so).  The CPU study (scripts/fastmath_sensitivity.py) predicts that it passes there."""
     assert _run_on_precise_library('test_multi_step_action_gradient and 1-256-Rope') == 0
 
 
-@pytest.mark.xfail(reason='GPU validation run of the staged SVD-cosine fix on every scene, reports either way', strict=False)
+@pytest.mark.xfail(reason='every scene on the correctly rounded diagnostic library, reports either way', strict=False)
 def test_all_multi_step_gradients_without_fast_math():
-    """Diagnostic: the 3-step gradient property of every scene on the diagnostic library, i.e. the data the decision to
-    move the unbiased cosine into the product build needs (it re-rolls the branch every knife-edge scene takes)."""
+    """Diagnostic: the 3-step gradient property of every scene on the diagnostic library (correctly rounded log / exp /
+    div instead of the hardware approximations): how much of the remaining distance to the oracle is fast-math."""
     assert _run_on_precise_library('test_multi_step_action_gradient and 1-256 and not Rope') == 0
 
 
