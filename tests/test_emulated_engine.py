@@ -53,7 +53,8 @@ def test_emulated_library_exports_the_whole_abi(emu_library):
 def test_gpu_parity_cases_on_the_emulated_engine(emu_library):
     env = dict(os.environ, DSK_LIB='emu')
     r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(HERE, 'test_gpu_parity.py'), os.path.join(HERE, 'test_gpu_aux.py'),
-                        '-m', 'gpu', '-q', '-x', '-p', 'no:cacheprovider', '-k', f'({SUBSET}) or test_gpu_aux'],
+                        os.path.join(HERE, 'test_legacy_loss.py'),
+                        '-m', 'gpu', '-q', '-x', '-p', 'no:cacheprovider', '-k', f'({SUBSET}) or test_gpu_aux or test_legacy_loss'],
                        env=env, capture_output=True, text=True, timeout=1500)
     tail = '\n'.join(r.stdout.splitlines()[-15:])
     print(tail)
