@@ -105,8 +105,8 @@ class Loss:
 
     # ---- target ----------------------------------------------------------------------------------------------------
     def load_target_density(self, path=None, grids=None):         # loss.py:57-74
-        if path is None and grids is None:
-            return
+        if grids is None and (path is None or len(path) == 0):
+            return              # the reference's empty default `target_path: ''` has no grid to load (default_config.py:70)
         if path is not None and len(path) > 0:
             grids = np.load(path if os.path.isabs(path) else os.path.join(os.path.dirname(os.path.abspath(__file__)), '../../', path))
         else:

@@ -161,3 +161,49 @@ def test_legacy_loss_terms_and_adjoints_match_the_oracle(name, soft):
     assert relerr(eng.get_particle_grad(0)[0], o.get_frame_grad(0)[0]) < 2e-4
     if np.abs(gc).max() > 0:
         assert relerr(eng.get_tool_grads(0), o.get_tool_grads(0)) < 2e-3
+
+
+@pytest.mark.gpu
+def test_grid_loss_on_the_env_classes():
+    """Loss(cfg.ENV.loss, env.simulator) as the reference builds it (taichi_env.py:58; plb/envs/env.py in PlasticineLab):
+    target SDF from a density grid, reward bookkeeping over env steps, and the loss adjoint reaching x.grad of the frame."""
+    from diffskill_b200.config import load
+    from diffskill_b200.envs.scenes import SCENES
+    from diffskill_b200.sim import Loss as L2, TaichiEnv
+    assert L2 is Loss
+    cfg = load(data=SCENES['GatherMove-v1'])
+    te = TaichiEnv(cfg, loss=False, max_env_steps=2)
+    te.initialize()
+    sim = te.simulator
+    loss = Loss(cfg.ENV.loss, sim)
+    loss.initialize()                                              # weights 10 / 10 / 1, hard contact, no target file
+    assert loss.sdf_weight[None] == 10 and loss.contact_weight[0] == 1 and not loss.soft_contact_loss
+    assert [p.action_dim for p in loss.primitives] == [7, 6] and loss._cols == [(0, 2), (2, 3)]
+    n = sim.n_grid
+    ax = np.arange(n) / n
+    X, Y, Z = np.meshgrid(ax, ax, ax, indexing='ij')
+    blob = (np.sqrt((X - 0.5) ** 2 + (Y - 0.1) ** 2 + (Z - 0.5) ** 2) < 0.07).astype(np.float32) * float(sim.p_mass) * 8
+    loss.load_target_density(grids=blob)
+    assert 0 < loss.sweeps < 2 * n and loss._target_iou == pytest.approx(1.0, rel=1e-5)
+    tsdf = loss.target_sdf.cpu().numpy()
+    assert (tsdf[blob > 1e-4] == 0).all() and tsdf.max() < loss.inf
+    far = tsdf[int(0.9 * n), int(0.1 * n), int(0.5 * n)]          # a node 0.4 from the blob centre
+    assert far == pytest.approx(0.4 - 0.07, abs=1.5 / n)
+    loss.reset()
+    assert loss._start_loss > 0 and 0 <= loss._init_iou < 1
+    te.step(np.zeros(13))
+    sim.cur = 0                                                    # copy mode keeps the state at frame 0
+    info = loss.compute_loss(0)
+    assert set(info) >= {'loss', 'reward', 'incremental_iou', 'iou', 'target_iou', 'sdf_loss', 'density_loss', 'contact_loss'}
+    assert np.isfinite(info['loss']) and info['reward'] == pytest.approx(loss._start_loss - info['loss'], rel=1e-6)
+    sim.engine.zero_grad()
+    loss.compute_loss_kernel_grad(0)
+    g = sim.engine.get_particle_grad(0)[0]
+    assert np.isfinite(g).all() and np.abs(g).max() > 0
+    # the density + SDF pull: moving every particle along -grad lowers the loss (first order)
+    x = sim.get_x(0)
+    before = loss.density_loss * 10 + loss.sdf_loss * 10 + loss.contact_loss
+    sim.reset(x - 2e-4 * g[:len(x), :3] / np.abs(g).max())
+    loss.clear()
+    after = loss.compute_loss(0)['loss']
+    assert after < before
