@@ -76,3 +76,107 @@ class BatchedSolver:
             if callback:
                 callback(it, loss)
         return dict(best_action=best_a, best_loss=best_loss, history=history, last_action=a)
+
+
+FUNCS = {}          # one GradModel per env, as plb/optimizer/solver.py:10,19-21
+
+
+class Solver:
+    """The reference's single-env trajectory optimiser with its own signatures (plb/optimizer/solver.py:13-165): torch Adam on
+    an action sequence [H, A], each iteration = GradModel.reset -> H x GradModel.forward (autograd Function over the engine's
+    forward_step / backward_step) -> loss_fn(idxes, observations, vel_loss_weight, loss_type=...) -> backward -> clamp to
+    [-1, 1] -> mask, keeping the best-so-far plan.  `args` needs adam_loss_type, stop_action_n, vel_loss_weight, energy_weight,
+    component_matching, enumerate_contact (debug plotting is not carried over).  BatchedSolver above is the fast path for many
+    envs with an engine-side loss; this class is the drop-in for callers written against the reference."""
+
+    def __init__(self, args, env, ouput_grid=(), device=None, **kwargs):
+        import torch
+        from .sim.function import GradModel
+        self.args, self.env = args, env
+        self.device = device or ('cuda' if torch.cuda.is_available() else 'cpu')
+        self.env.update_loss_fn(self.args.adam_loss_type)
+        if env not in FUNCS:
+            FUNCS[env] = GradModel(env, output_grid=ouput_grid, **kwargs)
+        self.func = FUNCS[env]
+        self.buffer = []
+
+    def solve(self, initial_actions, loss_fn, action_mask=None, lr=0.01, max_iter=200, verbose=True, scheduler=None):
+        import torch
+        from functools import partial
+        if action_mask is not None:
+            initial_actions = initial_actions * action_mask[None]
+            action_mask = torch.as_tensor(np.asarray(action_mask)[None], dtype=torch.float32, device=self.device)
+        self.initial_state = self.env.get_state()
+        kw = dict(action_mask=action_mask, lr=lr, max_iter=max_iter, verbose=verbose, scheduler=scheduler)
+        if getattr(self.args, 'component_matching', False):
+            raise NotImplementedError("component_matching needs core.diffskill.utils.get_component_masks, which the reference "
+                                      "tree does not contain (solver.py:3,30)")
+        if getattr(self.args, 'enumerate_contact', False):
+            # DBSCAN the initial dough; one optimisation per component with the contact loss restricted to it; keep the plan
+            # with the largest relative improvement (solver.py:54-90)
+            from sklearn.cluster import DBSCAN
+            labels = DBSCAN(eps=0.01, min_samples=5).fit(self.initial_state['state'][0].reshape(-1, 3)).labels_
+            infos, buffers = [], []
+            for label in range(labels.max() + 1):
+                self.env.set_state(**self.initial_state)
+                mask = torch.as_tensor(labels == label, dtype=torch.bool, device=self.device)
+                buffer, info = self.solve_one_plan(initial_actions, partial(loss_fn, state_mask=mask), **kw)
+                buffers.append(buffer)
+                infos.append(info)
+            gain = np.array([(b[0]['loss'] - i['best_loss']) / b[0]['loss'] for b, i in zip(buffers, infos)])
+            k = int(np.argmax(gain))
+            self.buffer.append(buffers[k])
+            return infos[k], buffers[k]
+        buffer, info = self.solve_one_plan(initial_actions, loss_fn, **kw)
+        self.buffer.append(buffer)
+        return info, buffer
+
+    def solve_one_plan(self, initial_actions, loss_fn, action_mask=None, lr=0.01, max_iter=200, verbose=True, scheduler=None):
+        import torch
+        action = torch.nn.Parameter(torch.as_tensor(np.array(initial_actions), dtype=torch.float32, device=self.device))
+        optim = torch.optim.Adam([action], lr=lr)
+        sched = None if scheduler is None else scheduler(optim)
+        buffer, best_action, best_loss = [], initial_actions, np.inf
+        loss, last, H = np.inf, initial_actions, action.shape[0]
+        for iter_id in range(max_iter):
+            optim.zero_grad()
+            observations = self.func.reset(self.initial_state['state'], device=self.device)
+            cached_obs = []
+            for idx, a in enumerate(action):
+                a = a.detach() if H - idx <= self.args.stop_action_n else a       # the last stop_action_n actions get no gradient
+                observations = self.func.forward(idx, a, *observations)
+                cached_obs.append(observations)
+            loss = loss_fn(list(range(H)), cached_obs, self.args.vel_loss_weight, loss_type=self.args.adam_loss_type)
+            assert self.args.energy_weight == 0.
+            loss.backward()
+            optim.step()
+            if sched is not None:
+                sched.step()
+            with torch.no_grad():
+                action.data.copy_(torch.clamp(action.data, -1, 1))
+                if action_mask is not None:
+                    action.data.copy_(action.data * action_mask)
+                loss = loss.item()
+                last = action.data.detach().cpu().numpy()
+                if loss < best_loss:
+                    best_loss, best_action = loss, last
+            buffer.append({'action': last, 'loss': loss})
+            if verbose:
+                print(f"{iter_id}:  {loss}")
+        self.env.set_state(**self.initial_state)
+        return buffer, {'best_loss': best_loss, 'best_action': best_action, 'last_loss': loss, 'last_action': last}
+
+    def eval(self, action, render_fn):
+        self.env.simulator.cur = 0
+        self.env.set_state(**self.initial_state)
+        outs = []
+        for a in action:
+            self.env.step(a)
+            outs.append(render_fn())
+        self.env.set_state(**self.initial_state)
+        return outs
+
+    def dump_buffer(self, path='/tmp/buffer.pkl'):
+        import pickle
+        with open(path, 'wb') as f:
+            pickle.dump(self.buffer, f)

@@ -183,3 +183,42 @@ def test_multi_step_calls_equal_per_step_calls():
     print('multi-step vs per-step: loss %.2e grads %.2e x %.2e' % (relerr(l1, l0), relerr(g1, g0), relerr(x1, x0)))
     assert np.abs(g0).max() > 0
     assert relerr(l1, l0) < 1e-5 and relerr(x1, x0) < 1e-6 and relerr(g1, g0) < 1e-4
+
+
+def test_reference_solver_api():
+    """plb/optimizer/solver.py: Solver(args, env).solve(init_actions, env.compute_loss, action_mask, lr, max_iter) -- torch Adam
+    through GradModel's autograd Function, EMD + contact + velocity loss, clamp / mask / best-so-far, state restored."""
+    import types
+    import torch
+    from diffskill_b200.config import load
+    from diffskill_b200.envs.scenes import SCENES
+    from diffskill_b200.planner import FUNCS, Solver
+    from diffskill_b200.sim import TaichiEnv
+    cfg = load(data=SCENES['GatherMove-v1'])
+    te = TaichiEnv(cfg, loss=True, return_dist=True, max_env_steps=2)
+    te.initialize()
+    te.device = DEVICE
+    x0 = te.simulator.get_x(0)
+    te.target_x = (x0 + np.array([0.03, 0.0, 0.0])).astype(np.float32)
+    te.tensor_target_x = torch.as_tensor(te.target_x, device=DEVICE)
+    te.set_contact_loss_mask(torch.ones(len(te.primitives), device=DEVICE))
+    args = types.SimpleNamespace(adam_loss_type='emd', stop_action_n=0, vel_loss_weight=0.02, energy_weight=0.,
+                                 component_matching=False, enumerate_contact=False, debug=False)
+    solver = Solver(args, te, return_dist=True, device=DEVICE)
+    assert FUNCS[te] is solver.func
+    H, A = 2, te.primitives.action_dim
+    mask = np.ones(A, np.float32)
+    mask[-1] = 0.                                   # freeze one action dimension
+    np.random.seed(0)                               # compute_loss subsamples 500 particles (taichi_env.py:261)
+    before = te.get_state()
+    info, buffer = solver.solve(np.full((H, A), 0.2, np.float32), te.compute_loss, action_mask=mask, lr=0.05, max_iter=3,
+                                verbose=False)
+    assert len(buffer) == 3 and all(np.isfinite(b['loss']) for b in buffer)
+    assert info['best_loss'] == min(b['loss'] for b in buffer) and info['last_loss'] == buffer[-1]['loss']
+    assert info['best_action'].shape == (H, A) and np.abs(info['last_action']).max() <= 1.0
+    assert (info['last_action'][:, -1] == 0).all()
+    assert not np.allclose(info['last_action'][:, :-1], 0.2)            # Adam moved the free dimensions
+    after = te.get_state()
+    assert te.simulator.cur == 0 and np.array_equal(after['state'][0], before['state'][0])
+    outs = solver.eval(info['best_action'], lambda: te.simulator.get_x(0).mean(0))
+    assert len(outs) == H and np.isfinite(outs).all()
