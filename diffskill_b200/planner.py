@@ -180,3 +180,91 @@ class Solver:
         import pickle
         with open(path, 'wb') as f:
             pickle.dump(self.buffer, f)
+
+
+def solve(env, func, initial_actions, loss_fn, lr=0.01, max_iter=200, verbose=True, scheduler=None, action_dims=None,
+          state=None, early_stop=None, compute_loss_in_end=False, device=None):
+    """plb/cut/solve_func.solve (:32-166), the CutRearrange optimiser: resumable Adam on [H, A] actions with a per-step loss
+    `loss_fn(idx, *observations)` (a tensor, or (tensor, dict of logged terms)), summed while stepping or after the rollout
+    (`compute_loss_in_end`); after each update the actions are clamped to [-1, 1] and projected -- `action_dims` a tuple:
+    only those columns stay non-zero; 'gripper': two 6-D tools move as one in y / z and keep their own x (:110-119) --
+    NaN stops, a loss < -10000 is skipped as a bug guard, `early_stop` = patience in non-improving iterations.  Returns the
+    plan and the optimiser state to pass back as `state=` for another `max_iter` iterations."""
+    import torch
+    dev = device or ('cuda' if torch.cuda.is_available() else 'cpu')
+    if state is None:
+        assert initial_actions is not None
+        iter_id, optim_buffer = 0, []
+        action = torch.nn.Parameter(torch.as_tensor(np.array(initial_actions), dtype=torch.float32, device=dev))
+        optim = torch.optim.Adam([action], lr=lr)
+        initial_state = env.get_state()
+        scheduler = scheduler if scheduler is None else scheduler(optim)
+        last_action, last_loss = best_action, best_loss = initial_actions, np.inf
+    else:
+        iter_id, optim_buffer, action, optim = state['iter_id'], state['optim_buffer'], state['action'], state['optim']
+        initial_state, scheduler = state['initial_state'], state['scheduler']
+        best_action, best_loss = state['best_action'], state['best_loss']
+        last_action, last_loss = state['last_action'], state['last_loss']
+    zero_masks = None
+    if isinstance(action_dims, tuple):
+        zero_masks = torch.ones(action.shape[-1], dtype=torch.bool, device=action.device)
+        zero_masks[list(action_dims)] = False
+    non_decrease_iters = 0
+    for iter_id in range(iter_id, iter_id + max_iter):
+        optim.zero_grad()
+        loss, outputs = 0, []
+        observations = func.reset(initial_state['state'], device=dev)
+
+        def calc_loss(idx, observations):
+            l = loss_fn(idx, *observations)
+            if isinstance(l, tuple):
+                outputs.append(l[1])
+                return l[0]
+            return l
+
+        obs_array = []
+        for idx, a in enumerate(action):
+            observations = func.forward(idx, a, *observations)
+            if compute_loss_in_end:
+                obs_array.append(observations)
+            else:
+                loss = loss + calc_loss(idx, observations)
+        for idx, observations in enumerate(obs_array):
+            loss = loss + calc_loss(idx, observations)
+        loss.backward()
+        optim.step()
+        if scheduler is not None:
+            scheduler.step()
+        with torch.no_grad():
+            a = torch.clamp(action, -1, 1)
+            if zero_masks is not None:
+                a[:, zero_masks] = 0
+            elif action_dims == 'gripper':
+                a1, a2 = a[:, 0:3], a[:, 6:9]
+                a = torch.zeros_like(a)
+                a[:, [1, 2]] = a[:, [7, 8]] = (a1[:, 1:] + a2[:, 1:]) / 2
+                a[:, 0], a[:, 6] = a1[:, 0], a2[:, 0]
+            action.data[:] = a
+            last_loss = loss.item()
+            if np.isnan(last_loss):
+                print("MEET NAN!!")
+                break
+            if last_loss < -10000:
+                continue
+            last_action = action.data.detach().cpu().numpy()
+            if last_loss < best_loss:
+                best_loss, best_action, non_decrease_iters = last_loss, last_action, 0
+            else:
+                non_decrease_iters += 1
+        optim_buffer.append({'action': last_action, 'loss': last_loss})
+        if verbose:
+            word = f"{iter_id}: {last_loss:.4f}  {best_loss:.3f}"
+            for k in (outputs[0] if outputs else ()):
+                word += f', {k}: {sum(float(o[k]) for o in outputs):.3f}'
+            print(word)
+        if early_stop is not None and non_decrease_iters >= early_stop:
+            break
+    env.set_state(initial_state)
+    return {'best_loss': best_loss, 'best_action': best_action, 'last_loss': last_loss, 'last_action': last_action,
+            'iter_id': iter_id, 'optim_buffer': optim_buffer, 'action': action, 'optim': optim,
+            'initial_state': initial_state, 'scheduler': scheduler}

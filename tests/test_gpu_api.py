@@ -222,3 +222,40 @@ def test_reference_solver_api():
     assert te.simulator.cur == 0 and np.array_equal(after['state'][0], before['state'][0])
     outs = solver.eval(info['best_action'], lambda: te.simulator.get_x(0).mean(0))
     assert len(outs) == H and np.isfinite(outs).all()
+
+
+def test_cut_solve_func_api():
+    """plb/cut/solve_func.solve: per-step loss with logged terms, action_dims projection, resumable optimiser state."""
+    import torch
+    from diffskill_b200.config import load
+    from diffskill_b200.envs.scenes import SCENES
+    from diffskill_b200.planner import solve
+    from diffskill_b200.sim import GradModel, TaichiEnv
+    cfg = load(data=SCENES['CutRearrange-v1'])
+    cfg.SHAPES[0]['n_particles'] = 700
+    te = TaichiEnv(cfg, loss=False, max_env_steps=2)
+    te.initialize()
+    func = GradModel(te, softness=666.)
+    x0 = torch.as_tensor(te.simulator.get_x(0), dtype=torch.float32, device=DEVICE)
+    target = x0 + torch.tensor([0.0, -0.01, 0.02], device=DEVICE)
+
+    def loss_fn(idx, x, c):
+        d = ((x[:, :3] - target) ** 2).mean()
+        knife = ((c[0, :3] - x[:, :3].mean(0)) ** 2).sum()
+        return d + 0.1 * knife, {'dist': d.item(), 'knife': knife.item()}
+
+    H, A = 2, te.primitives.action_dim
+    init = np.zeros((H, A), np.float32)
+    init[:, 1] = -0.3                                                   # knife goes down (solve_utils.py:166-168)
+    before = te.get_state()
+    st = solve(te, func, init, loss_fn, lr=0.05, max_iter=2, verbose=False, action_dims=(0, 1, 2), device=DEVICE)
+    assert st['iter_id'] == 1 and len(st['optim_buffer']) == 2 and np.isfinite(st['best_loss'])
+    assert (st['last_action'][:, 3:] == 0).all() and np.abs(st['last_action']).max() <= 1.0
+    assert not np.allclose(st['last_action'][:, :3], init[:, :3])
+    assert np.array_equal(te.get_state()['state'][0], before['state'][0])
+    st2 = solve(te, func, None, loss_fn, max_iter=1, verbose=False, action_dims=(0, 1, 2), state=st, early_stop=5,
+                compute_loss_in_end=True, device=DEVICE)
+    assert len(st2['optim_buffer']) == 3 and st2['optim'] is st['optim'] and st2['best_loss'] <= st['best_loss']
+    g = solve(te, func, np.full((H, A), 0.5, np.float32), lambda i, x, c: (x[:, :3] ** 2).mean(), max_iter=1, verbose=False,
+              action_dims='gripper', device=DEVICE)['last_action']       # two 6-D tools tied in y / z (solve_func.py:110-119)
+    assert np.allclose(g[:, [1, 2]], g[:, [7, 8]]) and (g[:, 3:6] == 0).all() and (g[:, 9:] == 0).all()
