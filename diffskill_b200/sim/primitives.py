@@ -117,9 +117,9 @@ class Primitive:
         for b in envs:
             self._engine.set_tool_state(self._step_of(f), b, self._index, ss)
 
-    def get_state_tensor(self, f):
+    def get_state_tensor(self, f, device='cuda'):
         import torch
-        return torch.tensor(self.get_state(f)[:7], dtype=torch.float32, device='cuda')
+        return torch.tensor(self.get_state(f)[:7], dtype=torch.float32, device=device)
 
     @property
     def init_state(self):

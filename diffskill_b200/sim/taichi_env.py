@@ -225,7 +225,7 @@ class TaichiEnv:
         sampled_idx = np.random.choice(curr_x.shape[0], min(500, curr_x.shape[0]), replace=False)
         curr_x, target_x = curr_x[sampled_idx], self.tensor_target_x[sampled_idx]
         emd = self.emd_loss_fn(curr_x, target_x)
-        prim = torch.cat([i.get_state_tensor(0)[None, :3] for i in self.primitives], dim=0)
+        prim = torch.cat([i.get_state_tensor(0, self.device)[None, :3] for i in self.primitives], dim=0)
         dists = torch.min(torch.cdist(prim[None], curr_x[None])[0], dim=1)[0]
         contact_loss = (self.contact_loss_mask * dists).sum() * 1e-3
         reward, emd = -emd - contact_loss, emd.item()

@@ -259,3 +259,37 @@ def test_cut_solve_func_api():
     g = solve(te, func, np.full((H, A), 0.5, np.float32), lambda i, x, c: (x[:, :3] ** 2).mean(), max_iter=1, verbose=False,
               action_dims='gripper', device=DEVICE)['last_action']       # two 6-D tools tied in y / z (solve_func.py:110-119)
     assert np.allclose(g[:, [1, 2]], g[:, [7, 8]]) and (g[:, 3:6] == 0).all() and (g[:, 9:] == 0).all()
+
+
+def test_multitask_env_over_a_cached_dataset(tmp_path):
+    """plb/envs/multitask_env.py: init/state_<i>.xz + target/target_<i>.npy -> reset(init_v, target_v, contact_loss_mask) ->
+    step -> reward / info; the dataset is written by envs.dataset.generate_synthetic in the reference's on-disk layout."""
+    import torch
+    from diffskill_b200.envs import MultitaskPlasticineEnv, make
+    from diffskill_b200.envs.dataset import generate_synthetic, load_pair
+    root = str(tmp_path / 'gathermove')
+    gen = make('GatherMove-v1', max_env_steps=2)
+    assert generate_synthetic(gen, root, 2, settle_steps=1) == [0, 1]
+    st0, goal1 = load_pair(root, 0)[0], load_pair(root, 1)[1]
+    del gen
+    np.random.seed(0)
+    env = MultitaskPlasticineEnv('GatherMove-v1', cached_state_path=root, device=DEVICE, max_env_steps=2)
+    assert env.num_inits == 2 and env.num_targets == 2 and len(env.target_pcs) == 2 and env.action_dim == 13
+    obs = env.reset(init_v=0, target_v=1, contact_loss_mask=[1., 0., 0.])
+    te = env.taichi_env
+    assert (env.init_v, env.target_v) == (0, 1) and np.array_equal(env.target_pc, goal1)
+    assert np.allclose(te.simulator.get_x(0), st0['state'][0], atol=1e-7)           # the cached state, through fp32
+    assert te.contact_loss_mask.tolist() == [1., 0., 0.] and te.init_emd > 0
+    assert obs.ndim == 1 and np.isfinite(obs).all()
+    a = np.zeros(13)
+    a[1] = -2.0                                                                      # clipped to -1
+    obs2, r, done, info = env.step(a)
+    assert obs2.shape == obs.shape and np.isfinite(r) and done is False
+    assert set(info) == {'info_emd', 'info_normalized_performance', 'info_contact_loss'}
+    assert np.array_equal(env._recorded_actions[0], np.clip(a, -1, 1))
+    s = env.get_state()
+    env.step(np.zeros(13))
+    env.set_state(s)
+    assert np.array_equal(env.get_state()['state'][0], s['state'][0]) and len(env.get_primitive_state()) == 3
+    env.reset(contact_loss_mask=0)                                                   # random pair, mask by tool index
+    assert te.contact_loss_mask.tolist() == [1., 0., 0.] and env.init_v in (0, 1) and isinstance(te.tensor_target_x, torch.Tensor)
