@@ -207,3 +207,37 @@ def test_grid_loss_on_the_env_classes():
     loss.clear()
     after = loss.compute_loss(0)['loss']
     assert after < before
+
+
+@pytest.mark.gpu
+def test_grid_loss_of_one_env_of_a_batch():
+    """A Loss bound to env 1 of a two-env engine sees that env's particles only, and its adjoint touches that env only."""
+    from diffskill_b200.engine import Engine
+    from diffskill_b200.scene import load_scene
+    from diffskill_b200.shapes import make_box
+    scene, _ = load_scene('CutRearrange-v1')
+    n = 500
+    xs = [make_box((0.45 + 0.1 * b, 0.07, 0.5), (0.1, 0.06, 0.08), n, np.random.RandomState(b)).astype(np.float32) for b in range(2)]
+    both = Engine(scene, n_envs=2, capacity=n, max_steps=1)
+    single = Engine(scene, n_envs=1, capacity=n, max_steps=1)
+    for b in range(2):
+        both.set_particles(0, b, xs[b])
+    single.set_particles(0, 0, xs[1])
+    ng = scene.n_grid
+    mk = lambda eng, env: Loss(None, types.SimpleNamespace(engine=eng, n_grid=ng, dx=scene.dx, primitives=scene.tools,
+                                                            _frame_to_step=lambda f: f // scene.substeps), env=env)
+    La, Lb = mk(both, 1), mk(single, 0)
+    rng = np.random.RandomState(0)
+    tdens = torch.from_numpy((rng.uniform(size=(ng, ng, ng)) < 0.01).astype(np.float32) * scene.p_mass)
+    tsdf = torch.from_numpy(rng.uniform(0, 0.3, size=(ng, ng, ng)).astype(np.float32))
+    for L in (La, Lb):
+        L.set_weights_only(10., 10., 1., True, 0.)
+        L.target_density, L.target_sdf = tdens.to(L.device), tsdf.to(L.device)
+        L.compute_loss_kernel(0)
+    assert La.loss == pytest.approx(Lb.loss, rel=1e-6) and La.min_dist == pytest.approx(Lb.min_dist, rel=1e-5)
+    both.zero_grad()
+    single.zero_grad()
+    La.compute_loss_kernel_grad(0)
+    Lb.compute_loss_kernel_grad(0)
+    assert np.allclose(both.get_particle_grad(0, 1)[0], single.get_particle_grad(0, 0)[0], rtol=1e-5, atol=1e-9)
+    assert np.abs(both.get_particle_grad(0, 0)[0]).max() == 0
