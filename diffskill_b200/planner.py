@@ -176,6 +176,15 @@ class Solver:
         self.env.set_state(**self.initial_state)
         return outs
 
+    def save_plot_buffer(self, path, buffer=None):          # solver.py:181-193 (matplotlib only when asked for)
+        import matplotlib.pyplot as plt
+        for buf in (self.buffer if buffer is None else buffer):
+            plt.plot(range(len(buf)), [b['loss'] for b in buf])
+        plt.xlabel('Steps')
+        plt.ylabel('Loss')
+        plt.savefig(path)
+        plt.close()
+
     def dump_buffer(self, path='/tmp/buffer.pkl'):
         import pickle
         with open(path, 'wb') as f:
