@@ -1133,6 +1133,12 @@ int dsk_set_tool_param(dsk_engine* e, int tool, int which, double value) {
   if (tool < 0 || tool >= e->K) return fail("tool %d outside [0,%d)", tool, e->K);
   ToolParams& T = e->h_tools[tool];
   float v = (float)value;
+  {   // unchanged value: keep the captured graphs and the resident substep tapes (TaichiEnv.set_state sets the softness
+      // on every call, i.e. once per planner iteration)
+    double cur = 0;
+    if (dsk_get_tool_param(e, tool, which, &cur)) return -1;
+    if ((float)cur == v) return 0;
+  }
   switch (which) {
     case DSK_PARAM_FRICTION: T.friction = v; break;
     case DSK_PARAM_SOFTNESS: T.softness = v; break;
@@ -1262,6 +1268,10 @@ int dsk_substep(dsk_engine* e, int f) {
     if (seq_begin_forward(e, s)) return -1;
   } else if (e->last_fwd_frame != f - 1) {
     return fail("dsk_substep(%d): substeps of a step must run in ascending order starting at a step boundary (last was %d)", f, e->last_fwd_frame);
+  } else {
+    // every fine-grained substep runs at sequence position q = 0: it needs its own tile epoch (with the epoch of the
+    // previous substep mark_tile would skip the tiles that one tagged and grid_op would miss them)
+    if (push_args(e, make_args(e, step, step + 1, step, -1))) return -1;
   }
   // every fine-grained substep is its own one-substep sequence (q = 0) so its grids stay inspectable
   if (seq_substep(e, s, 0, j, true)) return -1;
@@ -1299,8 +1309,9 @@ int dsk_substep_grad(dsk_engine* e, int f) {
     if (seq_begin_backward(e, s)) return -1;
   } else if (e->last_bwd_frame != f + 1) {
     return fail("dsk_substep_grad(%d): adjoint substeps of a step must run in descending order from the step's last substep (last was %d)", f, e->last_bwd_frame);
-  } else if (flush_pending_clear(e)) {
-    return -1;
+  } else {
+    if (flush_pending_clear(e)) return -1;
+    if (push_args(e, make_args(e, step, step, step, step))) return -1;   // fresh tile epoch, see dsk_substep
   }
   e->seq_use_tape = false;   // fine-grained adjoint substeps always recompute (their grids stay inspectable)
   if (seq_substep_grad(e, s, 0, j)) return -1;

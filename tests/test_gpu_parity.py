@@ -296,6 +296,51 @@ def _multi_step_action_gradient(name, slots, tape_mib):
     assert within_noise_floor(ex64, fx64, 5 * TOL_ACTION_GRAD), (ex, ex64, fx64)
 
 
+@pytest.mark.parametrize('name', ['LiftSpread-v1', 'GatherMove-v1', 'CutRearrange-v1'])
+def test_fine_grained_substeps_equal_whole_step(name):
+    """MPMSimulator.substep / substep_grad called substep by substep (mpm_simulator.py:307-345, the reference's own entry
+    points) must reproduce forward_step / backward_step with substeps > 1: states, particle adjoints, action gradients.
+    (Round 1 ran every fine-grained substep of a step under one tile epoch: grid_op skipped most tiles.)"""
+    S = 4
+    H = 2
+    res = []
+    for fine in (False, True):
+        scene, eng, o = make_pair(name, n=900, substeps=S, max_steps=H)
+        acts = actions_for(scene, H, scale=0.7)
+        n = eng.n_particles()
+        for s in range(H):
+            eng.set_action(s, acts[s][None])
+            if fine:
+                for j in range(S):
+                    eng.substep(s * S + j)
+            else:
+                eng.forward_step(s)
+        state = eng.get_particles(H)
+        rng = np.random.RandomState(5)
+        gx, gv = f32(rng.normal(size=(n, 3))), f32(rng.normal(size=(n, 3)) * 0.01)
+        eng.zero_grad()
+        eng.add_particle_grad(H, gx[None], gv[None])
+        for s in range(H - 1, -1, -1):
+            if fine:
+                for j in range(S - 1, -1, -1):
+                    eng.substep_grad(s * S + j)
+            else:
+                eng.backward_step(s)
+        res.append((state, eng.get_particle_grad(0), eng.get_action_grads(0, H)[:, 0]))
+        if not fine:   # and the whole-step path against the oracle, so "equal" is not "equally wrong"
+            for s in range(H):
+                o.forward_step(s, acts[s])
+            ox, ov, _, _ = o.get_frame(H * S)
+            assert relerr(state[0], ox) < 1e-5 and relerr(state[1], ov) < 2e-3
+    (sa, ga, aa), (sb, gb, ab) = res
+    errs = dict(x=relerr(sb[0], sa[0]), v=relerr(sb[1], sa[1]), F=relerr(sb[2], sa[2]), C=relerr(sb[3], sa[3]),
+                gx=relerr(gb[0], ga[0]), gv=relerr(gb[1], ga[1]), gF=relerr(gb[2], ga[2]), action=relerr(ab, aa))
+    print(name, 'fine-grained vs whole-step', {k_: '%.1e' % e_ for k_, e_ in errs.items()})
+    # different scatter orders (float atomics) and recompute vs tape only
+    for k_, e_ in errs.items():
+        assert e_ < (1e-3 if k_ in ('gx', 'gv', 'gF', 'action') else 2e-5), (k_, e_)
+
+
 @pytest.mark.parametrize('name', ENVS)
 def test_against_committed_golden_fixture(name):
     """CUDA path vs tests/golden/*.npz (oracle fp64, generated by tests/golden/make_golden.py): one env step of
