@@ -7,8 +7,13 @@ Metric (BASELINE.json): particle-substeps/sec fwd+bwd.  One *step* of this bench
 trajectory-optimisation iteration of the workload: H env steps forward (H*S substeps), the loss at
 every step boundary, H env steps backward (H*S adjoint substeps), action gradients out.
 
-Default workload = BASELINE.json configs[1]: LiftSpread-v1, 50-step forward+backward action-gradient
-iteration, single env (15 707-particle synthetic dough), one env per GPU (weak scaling over GPUs).
+Default workload = BASELINE.json configs[2], the config the metric's "1/2/4/8 B200" wording is quoted on:
+GatherMove-v1, batch of 64 envs (scatter doughs settled by 10 zero-action steps, sphere-blob goals), H=50
+forward+backward, the 64 envs sharded 64/N per GPU (strong scaling).  Other workloads (--workload):
+  liftspread      configs[1]  LiftSpread-v1 H=50 fwd+bwd, 1 env per GPU (weak)
+  random_rollout  configs[0]  LiftSpread-v1 forward-only rollout with random actions (scripts/random_env.py)
+  cutrearrange    configs[3]  CutRearrange-v1, 32 start/goal pairs per GPU (256 on 8 GPUs, weak), H=42
+  sweep:<N>:<n>   configs[4]  single env, N particles at ~8 per cell on an n^3 grid
 
 JSON keys follow the driver contract; see DESIGN.md "Measurement" for the byte accounting.
 """
@@ -41,11 +46,17 @@ KERNEL_BYTES = {
 def workload_spec(name):
     if name == 'liftspread':
         return dict(env='LiftSpread-v1', horizon=50, envs_per_gpu=1, desc='LiftSpread-v1 H=50 fwd+bwd, 1 env/GPU')
+    if name == 'random_rollout':
+        return dict(env='LiftSpread-v1', horizon=50, envs_per_gpu=1, forward_only=True,
+                    desc='LiftSpread-v1 forward-only rollout, 50 random actions (scripts/random_env.py), 1 env/GPU')
     if name == 'gathermove':
         return dict(env='GatherMove-v1', horizon=50, envs_per_gpu=None, total_envs=64,
-                    desc='GatherMove-v1 H=50 fwd+bwd, 64 envs sharded over the GPUs')
+                    desc='GatherMove-v1 H=50 fwd+bwd, 64 settled scatter doughs + sphere goals '
+                         '(gathermove_generator_V2.py), sharded 64/N per GPU')
     if name == 'cutrearrange':
-        return dict(env='CutRearrange-v1', horizon=42, envs_per_gpu=32, desc='CutRearrange-v1 H=42 fwd+bwd, 32 envs/GPU')
+        return dict(env='CutRearrange-v1', horizon=42, envs_per_gpu=32,
+                    desc='CutRearrange-v1 H=42 fwd+bwd, 32 start/goal pairs per GPU (cutrearrange_generator_0528.py; '
+                         '256 pairs on 8 GPUs), knife push init')
     if name.startswith('sweep'):
         # BASELINE.json configs[4]: single env, N particles at ~8 per cell on an n^3 grid, one capsule tool.
         # name: sweep:<particles>:<n_grid>   e.g. sweep:1000000:256
@@ -82,6 +93,27 @@ def make_inputs(spec, rank, n_envs):
         return scene, cfg, [x], [t], acts
     scene, cfg = load_scene(spec['env'])
     xs, targets, actions = [], [], []
+    if spec['env'] == 'GatherMove-v1':
+        from diffskill_b200.envs import generators as gen
+        for b in range(n_envs):
+            gid = rank * n_envs + b
+            x = gen.gathermove_start(cfg, gid)              # settled on the device by main() (10 zero-action steps)
+            xs.append(x)
+            targets.append(gen.gathermove_goal(gid, len(x)))
+            actions.append(np.random.RandomState(100 + gid).uniform(-1, 1, (H, scene.action_dim)).astype(np.float32))
+        return scene, cfg, xs, targets, np.stack(actions, 1)
+    if spec['env'] == 'CutRearrange-v1':
+        from diffskill_b200.envs import generators as gen
+        rng = np.random.RandomState(0)                      # the reference: np.random.seed(0), pairs drawn in sequence
+        pairs = [gen.cutrearrange_pair(rng) for _ in range((rank + 1) * n_envs)][rank * n_envs:]
+        for b, (x, cut, _, _) in enumerate(pairs):
+            xs.append(x)
+            targets.append(cut)
+            a = gen.knife_init_actions(H, scene.action_dim)
+            # the optimiser's first iterations perturb the initial guess; keep the envs' action sequences distinct
+            a += np.random.RandomState(100 + rank * n_envs + b).uniform(-0.05, 0.05, a.shape).astype(np.float32)
+            actions.append(a)
+        return scene, cfg, xs, targets, np.stack(actions, 1)
     for b in range(n_envs):
         gid = rank * n_envs + b
         shapes = [dict(s) for s in cfg.SHAPES]
@@ -172,28 +204,45 @@ def measured_peak():
 
 def cpu_oracle_sample(spec, threads, env_steps=1, repeats=1):
     """Times the CPU oracle (a port of the reference; Taichi is not installable offline) on a bounded sample:
-    `env_steps` env steps forward + backward of env 0 of the workload.  Returns particle-substeps/s."""
+    `env_steps` env steps forward (+ backward) of the workload's first env(s).  Batched workloads run one env per host
+    thread concurrently (each oracle single-threaded) -- the layout a CPU user of the reference would pick (one process per
+    env, mp_wrapper.py:148-167); single-env workloads give all threads to the one env.  Returns particle-substeps/s."""
+    from concurrent.futures import ThreadPoolExecutor
     from oracle import oracle as orc
-    scene, cfg, xs, targets, actions = make_inputs(spec, 0, 1)
-    x0 = xs[0]
-    n = len(x0)
+    batched = (spec.get('total_envs') or spec.get('envs_per_gpu') or 1) > 1
+    n_envs = threads if batched else 1
+    scene, cfg, xs, targets, actions = make_inputs(spec, 0, n_envs)
     S = scene.substeps
-    o = orc.Oracle(scene, n, env_steps * S + 1, f64=False, threads=threads)
-    best = None
-    for _ in range(repeats):
+    fwd_only = bool(spec.get('forward_only'))
+    oracles = [orc.Oracle(scene, len(x), env_steps * S + 1, f64=False, threads=1 if batched else threads) for x in xs]
+
+    def run(b):
+        o, x0, n = oracles[b], xs[b], len(xs[b])
         o.reset(x0.astype(np.float64))
         for i, t in enumerate(scene.tools):
             o.set_tool_state(0, i, t.init_state)
         o.zero_grad()
-        t0 = time.perf_counter()
         for s in range(env_steps):
-            o.forward_step(s, actions[s, 0])
+            o.forward_step(s, actions[s, b])
+            if fwd_only:
+                continue
             x = o.get_frame((s + 1) * S)[0]
-            o.add_frame_grad((s + 1) * S, gx=2.0 * (x - targets[0]) / n)
+            o.add_frame_grad((s + 1) * S, gx=2.0 * (x - targets[b]) / n)
         for s in range(env_steps - 1, -1, -1):
-            o.backward_step(s)
+            if not fwd_only:
+                o.backward_step(s)
+
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        if n_envs == 1:
+            run(0)
+        else:
+            with ThreadPoolExecutor(n_envs) as ex:
+                list(ex.map(run, range(n_envs)))
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
+    n = sum(len(x) for x in xs)
     return n * S * env_steps / best, best, n, S
 
 
@@ -205,7 +254,7 @@ def run_reference(args):
         return
     spec = workload_spec(args.workload)
     threads = os.cpu_count() or 1
-    env_steps = 1
+    env_steps = 3 if spec.get('forward_only') else 1
     vals = []
     for i in range(args.warmup + args.steps):
         v, dt, n, S = cpu_oracle_sample(spec, threads, env_steps)
@@ -213,11 +262,12 @@ def run_reference(args):
             vals.append((v, dt))
     v = float(np.mean([a for a, _ in vals]))
     ms = float(np.mean([b for _, b in vals]) * 1e3)
-    sample = (f'{env_steps} env step ({S} substeps fwd + {S} adjoint substeps) of env 0 ({n} particles) per step; '
+    sample = (f'{env_steps} env step(s) ({env_steps * S} substeps fwd' + ('' if spec.get('forward_only') else f' + {env_steps * S} adjoint substeps')
+              + f') of the first env(s) ({n} particles in total; batched workloads: one env per host thread) per step; '
               'adjoints via the oracle tape AD (about 10x the arithmetic of a hand-written reverse pass)')
     out = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-               ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-               impl='reference',
+               ms_per_step=ms, higher_is_better=True, scaling='strong' if spec.get('total_envs') else 'weak',
+               vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
                config=dict(workload=spec['desc'], horizon=spec['horizon'], l2='n/a (CPU)'),
                cpu_baseline=dict(value=v, unit=UNIT, cores=threads, kind='port', sample=sample),
                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
@@ -230,7 +280,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='liftspread')
+    ap.add_argument('--workload', default='gathermove')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--step-slots', type=int, default=0,
                     help='substep-frame ring in env steps (1 = pure per-step checkpointing + recompute, H = full tape; '
@@ -283,11 +333,16 @@ def main():
         eng.set_particles(0, b, xs[b])
         tgt[b, :len(xs[b])] = targets[b]
     n_particles = sum(len(x) for x in xs)
+    if spec['env'] == 'GatherMove-v1':   # "wait for dough to drop": 10 zero-action env steps (gathermove_generator_V2.py:30-32)
+        from diffskill_b200.envs import generators as gen
+        gen.settle(eng)
+    fwd_only = bool(spec.get('forward_only'))
     tgt_dev = torch.from_numpy(tgt).to(dev)
     act_host = torch.from_numpy(actions).pin_memory()           # [H,B,A] pinned host
     act_dev = act_host.to(dev)
     grads_host = torch.zeros((H, B, A)).pin_memory()
     loss_host = torch.zeros(B).pin_memory()
+    obs_host_xv = np.zeros((B, cap, 6), np.float32)
     grads_dev = torch.zeros((H, B, A), device=dev)
     loss_dev = torch.zeros(B, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -296,6 +351,16 @@ def main():
     def iteration(e2e, mark=None):
         # the planner's rollout through the multi-step calls of the C ABI (one host call per phase, see
         # include/diffskill_mpm.h); --per-step-calls uses the reference-shaped per-step entry points instead
+        if fwd_only:
+            # configs[0], scripts/random_env.py:19-24: env.step(action) x H in copy mode -- checkpoint s -> s+1 here so
+            # that the rollout stays readable; no loss, no adjoint
+            eng.set_actions(0, act_host.numpy() if e2e else act_dev)
+            eng.forward_steps(0, H)
+            if world > 1 and mark is not None:
+                mark.record()
+            if e2e:     # D2H read of the step's result: the final particle positions of env 0
+                eng.get_obs(H, obs_host_xv, None)
+            return
         eng.zero_grad()
         eng.loss_reset()
         if args.per_step_calls:
@@ -367,8 +432,8 @@ def main():
     prof = eng.profile_report(reset=True)
     eng.profile_enable(False)
     n_occ = occupied_nodes(eng, range(0, H + 1, max(1, H // 10)), B) * B   # per launch, all envs
-    final_loss = float(eng.loss_get().sum())
-    g = eng.get_action_grads(0, H)
+    final_loss = float(eng.loss_get().sum()) if not fwd_only else 0.0
+    g = eng.get_action_grads(0, H) if not fwd_only else eng.get_obs(H)[0]
     finite = bool(np.isfinite(g).all() and np.isfinite(final_loss))
 
     if rank == 0:
@@ -384,11 +449,11 @@ def main():
         alg_bytes = bp * n_particles + bn * n_occ
         dur_ms = prof[dom][0] / prof[dom][1]
         achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
-        step_bytes = (480 * n_particles + 168 * n_occ) * H * S
+        step_bytes = ((192 if fwd_only else 480) * n_particles + (56 if fwd_only else 168) * n_occ) * H * S
         traffic = None
         try:
             tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
-            traffic = tr.get(args.workload, {}).get(dom, {}).get('dram_bytes_per_launch')
+            traffic = tr.get('liftspread' if fwd_only else args.workload, {}).get(dom, {}).get('dram_bytes_per_launch')
         except Exception:
             pass
         roof = dict(bound='hbm', kernel=dom, achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
@@ -399,7 +464,7 @@ def main():
                     method='CUDA events around every launch of one eager (graph-free) iteration on the engine stream',
                     per_kernel_us={k: round(v[0] / v[1] * 1e3, 2) for k, v in prof.items()},
                     per_kernel_share={k: round(s_, 4) for k, s_ in shares.items()})
-        out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+        out = dict(metric=METRIC if not fwd_only else 'particle-substeps/sec fwd (forward-only rollout)', value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                    ms_per_step=ms_step, higher_is_better=True, scaling='strong' if spec.get('total_envs') else 'weak',
                    vs_baseline=None, dtype='f32',
                    data='synthetic',
@@ -411,18 +476,20 @@ def main():
                                parallelism=f'env-sharded x{world}' if world > 1 else 'single GPU'),
                    e2e=dict(value=e2e_value, unit=UNIT, ms_per_step=float(ms_e2e.mean()),
                             h2d_bytes_per_step=int(act_host.numel() * 4),
-                            d2h_bytes_per_step=int(grads_host.numel() * 4 + loss_host.numel() * 4)),
+                            d2h_bytes_per_step=int(obs_host_xv.size * 4 if fwd_only else grads_host.numel() * 4 + loss_host.numel() * 4)),
                    gpu_launches=int(launches), roofline=roof, clocks=clocks,
                    loss=final_loss, finite=finite, engine_bytes=eng.memory_bytes())
-        if per_rank_ms:
-            out['per_rank_ms'] = dict(device=per_rank_ms.get(False), e2e=per_rank_ms.get(True))
+        out['per_rank_ms'] = (dict(device=per_rank_ms.get(False), e2e=per_rank_ms.get(True)) if per_rank_ms else
+                              dict(device=[round(ms_step, 3)], e2e=[round(float(ms_e2e.mean()), 3)]))
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, dt, n_, S_ = cpu_oracle_sample(spec, threads, env_steps=1)
+            v, dt, n_, S_ = cpu_oracle_sample(spec, threads, env_steps=3 if fwd_only else 1)
+            what = (f'3 env steps ({3 * S_} substeps forward only)' if fwd_only else
+                    f'1 env step ({S_} substeps fwd + {S_} adjoint substeps)')
             out['cpu_baseline'] = dict(value=v, unit=UNIT, cores=threads, kind='port',
-                                       sample=f'1 env step ({S_} substeps fwd + {S_} adjoint substeps) of env 0 ({n_} particles), '
-                                              f'{dt:.1f} s; oracle port of the reference (taichi is not installable offline), '
-                                              'adjoints via tape AD')
+                                       sample=f'{what} of the first env(s) ({n_} particles in total; batched workloads: one env per host thread), '
+                                              f'{dt:.1f} s; oracle port of the reference (taichi is not installable offline)'
+                                              + ('' if fwd_only else ', adjoints via tape AD'))
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

@@ -15,9 +15,6 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libdiffskill_mpm.so')
 if os.environ.get('DSK_LIB') == 'timeline':   # profiling build with in-graph kernel timestamps (build.py --timeline)
     LIB_PATH = os.path.join(_HERE, 'libdiffskill_mpm_tl.so')
-if os.environ.get('DSK_LIB') == 'emu':        # CPU emulation of the engine (tests/host_check/make_emu.py): test infrastructure
-    LIB_PATH = os.environ.get('DSK_EMU_LIB') or os.path.join(os.path.dirname(_HERE), 'tests', 'host_check', 'libdiffskill_mpm_emu.so')
-    os.environ['DSK_NO_GRAPHS'] = '1'
 if os.environ.get('DSK_LIB') == 'precise':    # diagnostic build without fast-math log/exp/div/rsqrt (build.py --precise)
     LIB_PATH = os.path.join(_HERE, 'libdiffskill_mpm_pm.so')
 MAX_TOOLS, MAX_PAIRS, ABI_VERSION = 8, 8, 1

@@ -11,6 +11,12 @@ for p in (ROOT, os.path.join(ROOT, 'tests')):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+    if os.environ.get('DSK_LIB') == 'emu':
+        # TEST INFRASTRUCTURE ONLY: point the binding at the CPU emulation of the engine (tests/host_check/make_emu.py).  The
+        # product loader (diffskill_b200/engine.py) knows nothing about it -- the switch lives here, in the test harness.
+        os.environ['DSK_NO_GRAPHS'] = '1'
+        from diffskill_b200 import engine
+        engine.LIB_PATH = os.environ.get('DSK_EMU_LIB') or os.path.join(ROOT, 'tests', 'host_check', 'libdiffskill_mpm_emu.so')
 
 
 def _has_gpu():
