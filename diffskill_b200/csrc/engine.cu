@@ -143,6 +143,7 @@ struct dsk_engine {
   int big_block = 128;
   int minb_g2p2g = 4, minb_g2p_adj = 4, minb_p2g_adj = 4;
   bool flat_grid = false;   // many active tiles: throughput layout of the grid kernels
+  bool ts = true;           // transposed shared-memory scatter (warp_scatter27_ts) instead of the shuffle butterfly
   cudaStream_t cap_side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<cudaEvent_t> ev_restored, ev_main;   // per backward position, used while capturing the pipelined adjoint
@@ -219,6 +220,7 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static float* svd_at(dsk_engine* e, StepSlot& s, int j);
 static size_t kin_smem(dsk_engine* e);
 static void drop_graphs(dsk_engine* e);
+static int ts_opt_in(dsk_engine* e);
 
 static void fill_tool(ToolParams& T, const dsk_tool_desc& d) {
   memset(&T, 0, sizeof T);
@@ -378,6 +380,7 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
   if (const char* v = getenv("DSK_MINB_G2P_ADJ")) e->minb_g2p_adj = atoi(v);
   if (const char* v = getenv("DSK_MINB_P2G_ADJ")) e->minb_p2g_adj = atoi(v);
   e->flat_grid = e->big;
+  if (const char* v = getenv("DSK_TS")) e->ts = atoi(v) != 0;
   if (const char* v = getenv("DSK_FLAT_GRID")) e->flat_grid = atoi(v) != 0;
   e->tool_floats = (size_t)e->B * std::max(1, e->K) * 8;
   int rc = [&]() -> int {
@@ -428,6 +431,7 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
       if (kin_smem(e) > 200 * 1024) return fail("tool kinematics kernel needs %zu bytes of shared memory", kin_smem(e));
       CK(cudaFuncSetAttribute(k_kinematics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kin_smem(e)));
     }
+    if (ts_opt_in(e)) return -1;
     DA(e->tile_count, 4);
     DA(e->done, 1);
     DA(e->d_args, 1);
@@ -601,6 +605,97 @@ static dim3 grid_block(dsk_engine* e) { return dim3(GRID_NODES, std::min(e->n_fr
     else k_grid_adj<<<grid_ctas(e), grid_block(e), 0, stream>>>(__VA_ARGS__, sc);      \
   } while (0)
 
+
+// ---- launchers of the particle kernels: pick the kernel family (latency: plane-split, 3 threads per particle; throughput:
+// one thread per particle), the register cap and the scatter variant (TS: transposed shared-memory scatter) -------------
+static size_t ts_smem(dsk_engine* e, int threads) { return e->ts ? (size_t)(threads / 32) * TS_WARP_FLOAT4 * sizeof(float4) : 0; }
+static size_t ts9_smem(dsk_engine* e) { return e->ts ? (size_t)(PL_PARTICLES * 3 / 32) * TS9_WARP_FLOAT4 * sizeof(float4) : 0; }
+static int launch_p2g(dsk_engine* e, bool write_f, const float* fin, float* fout, const float* mat, float4* G, TileTrack tt,
+                      int q, const int* run_if, float* svd) {
+  const SimConst& k = e->k;
+  const int pb = e->big ? e->big_block : 128;
+  const int nb = cdiv(k.stride, pb);
+  const size_t sm = ts_smem(e, pb);
+  if (!write_f) {
+    if (e->ts) KL(KID_P2G_RECOMPUTE, k_p2g<false, 3, true><<<nb, pb, sm, e->qs>>>(k, fin, fout, mat, e->npart, G, tt, e->d_args, q, run_if, nullptr));
+    else KL(KID_P2G_RECOMPUTE, k_p2g<false, 3, false><<<nb, pb, 0, e->qs>>>(k, fin, fout, mat, e->npart, G, tt, e->d_args, q, run_if, nullptr));
+  } else if (e->big) {
+    if (e->ts) KL(KID_P2G, k_p2g<true, 3, true><<<nb, pb, sm, e->qs>>>(k, fin, fout, mat, e->npart, G, tt, e->d_args, q, run_if, svd));
+    else KL(KID_P2G, k_p2g<true, 3, false><<<nb, pb, 0, e->qs>>>(k, fin, fout, mat, e->npart, G, tt, e->d_args, q, run_if, svd));
+  } else {
+    if (e->ts) KL(KID_P2G, k_p2g<true, 1, true><<<nb, pb, sm, e->qs>>>(k, fin, fout, mat, e->npart, G, tt, e->d_args, q, run_if, svd));
+    else KL(KID_P2G, k_p2g<true, 1, false><<<nb, pb, 0, e->qs>>>(k, fin, fout, mat, e->npart, G, tt, e->d_args, q, run_if, svd));
+  }
+  LAUNCH_CHECK();
+  return 0;
+}
+static int launch_g2p2g(dsk_engine* e, const float* fprev, float* fcur, float* fnext, const float* mat, const float4* Gprev,
+                        float4* Gnext, TileTrack tt, int qnext, float* svd) {
+  const SimConst& k = e->k;
+  if (!e->big) {
+    const int nb = cdiv(k.stride, PL_PARTICLES);
+    if (e->ts) KL(KID_G2P2G, k_g2p2g_pl<true><<<nb, dim3(PL_PARTICLES, 3), ts9_smem(e), e->qs>>>(k, fprev, fcur, fnext, mat, e->npart, Gprev, Gnext, tt, e->d_args, qnext, svd));
+    else KL(KID_G2P2G, k_g2p2g_pl<false><<<nb, dim3(PL_PARTICLES, 3), 0, e->qs>>>(k, fprev, fcur, fnext, mat, e->npart, Gprev, Gnext, tt, e->d_args, qnext, svd));
+  } else {
+    const int pb = e->big_block, nb = cdiv(k.stride, pb);
+    const size_t sm = ts_smem(e, pb);
+    switch ((e->minb_g2p2g >= 4 ? 2 : 0) + (e->ts ? 1 : 0)) {
+      case 3: KL(KID_G2P2G, k_g2p2g<4, true><<<nb, pb, sm, e->qs>>>(k, fprev, fcur, fnext, mat, e->npart, Gprev, Gnext, tt, e->d_args, qnext, svd)); break;
+      case 2: KL(KID_G2P2G, k_g2p2g<4, false><<<nb, pb, 0, e->qs>>>(k, fprev, fcur, fnext, mat, e->npart, Gprev, Gnext, tt, e->d_args, qnext, svd)); break;
+      case 1: KL(KID_G2P2G, k_g2p2g<3, true><<<nb, pb, sm, e->qs>>>(k, fprev, fcur, fnext, mat, e->npart, Gprev, Gnext, tt, e->d_args, qnext, svd)); break;
+      default: KL(KID_G2P2G, k_g2p2g<3, false><<<nb, pb, 0, e->qs>>>(k, fprev, fcur, fnext, mat, e->npart, Gprev, Gnext, tt, e->d_args, qnext, svd)); break;
+    }
+  }
+  LAUNCH_CHECK();
+  return 0;
+}
+static int launch_g2p_adj(dsk_engine* e, const float* fin, const float* fnext, const float* ain, float* aout, const float4* Gv,
+                          float4* Ga) {
+  const SimConst& k = e->k;
+  if (!e->big) {
+    const int nb = cdiv(k.stride, PL_PARTICLES);
+    if (e->ts) KL(KID_G2P_ADJ, k_g2p_adj_pl<true><<<nb, dim3(PL_PARTICLES, 3), ts9_smem(e), e->qs>>>(k, fin, fnext, ain, aout, e->npart, Gv, Ga));
+    else KL(KID_G2P_ADJ, k_g2p_adj_pl<false><<<nb, dim3(PL_PARTICLES, 3), 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, Gv, Ga));
+  } else {
+    const int pb = e->big_block, nb = cdiv(k.stride, pb);
+    const size_t sm = ts_smem(e, pb);
+    switch ((e->minb_g2p_adj >= 4 ? 2 : 0) + (e->ts ? 1 : 0)) {
+      case 3: KL(KID_G2P_ADJ, k_g2p_adj<4, true><<<nb, pb, sm, e->qs>>>(k, fin, fnext, ain, aout, e->npart, Gv, Ga)); break;
+      case 2: KL(KID_G2P_ADJ, k_g2p_adj<4, false><<<nb, pb, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, Gv, Ga)); break;
+      case 1: KL(KID_G2P_ADJ, k_g2p_adj<3, true><<<nb, pb, sm, e->qs>>>(k, fin, fnext, ain, aout, e->npart, Gv, Ga)); break;
+      default: KL(KID_G2P_ADJ, k_g2p_adj<3, false><<<nb, pb, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, Gv, Ga)); break;
+    }
+  }
+  LAUNCH_CHECK();
+  return 0;
+}
+static int launch_p2g_adj(dsk_engine* e, const float* fin, const float* ain, float* aout, const float* mat, const float4* Ga,
+                          const float* svd) {
+  const SimConst& k = e->k;
+  if (!e->big) {
+    KL(KID_P2G_ADJ, k_p2g_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, e->qs>>>(k, fin, ain, aout, mat, e->npart, Ga, svd));
+  } else {
+    const int pb = e->big_block, nb = cdiv(k.stride, pb);
+    if (e->minb_p2g_adj >= 4) KL(KID_P2G_ADJ, k_p2g_adj<4><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, mat, e->npart, Ga, svd));
+    else KL(KID_P2G_ADJ, k_p2g_adj<3><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, mat, e->npart, Ga, svd));
+  }
+  LAUNCH_CHECK();
+  return 0;
+}
+// shared-memory opt-in of the TS kernel instantiations (57 KB for a 128-thread CTA)
+static int ts_opt_in(dsk_engine* e) {
+  const int sm = (int)(4 * TS_WARP_FLOAT4 * sizeof(float4));
+  CK(cudaFuncSetAttribute(k_p2g<false, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_p2g<true, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_p2g<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_g2p2g<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_g2p2g<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_g2p_adj<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_g2p_adj<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  (void)e;
+  return 0;
+}
+
 // zero the grids of the last substep of a fine-grained (dsk_substep / dsk_substep_grad) sequence
 static int flush_pending_clear(dsk_engine* e) {
   if (e->pending_q < 0) return 0;
@@ -698,13 +793,7 @@ static int seq_substep(dsk_engine* e, StepSlot& s, int q, int j, bool write_stat
   int nb = cdiv(k.stride, pb);
   float* fin = s.frames + (size_t)j * e->frame_floats;
   float* fout = s.frames + (size_t)(j + 1) * e->frame_floats;
-  if (write_state)
-    if (e->big)
-      KL(KID_P2G, k_p2g<true, 3><<<nb, pb, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q, nullptr, svd_at(e, s, j)));
-    else
-      KL(KID_P2G, k_p2g<true, 1><<<nb, pb, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q, nullptr, svd_at(e, s, j)));
-  else
-    KL(KID_P2G_RECOMPUTE, k_p2g<false, 3><<<nb, pb, 0, e->qs>>>(k, fin, fout, s.mat, e->npart, e->G0[set], tt, e->d_args, q, nullptr, nullptr));
+  if (launch_p2g(e, write_state, fin, fout, s.mat, e->G0[set], tt, q, nullptr, write_state ? svd_at(e, s, j) : nullptr)) return -1;
   bool clr = q > 0;
   if (e->kin_join) {
     CK(cudaStreamWaitEvent(e->qs, e->ev_join, 0));
@@ -742,28 +831,14 @@ static int seq_forward_fused(dsk_engine* e, StepSlot& s) {
   auto frame = [&](int j) { return s.frames + (size_t)j * e->frame_floats; };
   {
     TileTrack tt{e->tile_epoch[1], e->tile_list[1], e->tile_count + 1};
-    if (e->big)
-      KL(KID_P2G, k_p2g<true, 3><<<nb, pb, 0, e->qs>>>(k, frame(0), frame(1), s.mat, e->npart, e->G0[1], tt, e->d_args, 0, nullptr, svd_at(e, s, 0)));
-    else
-      KL(KID_P2G, k_p2g<true, 1><<<nb, pb, 0, e->qs>>>(k, frame(0), frame(1), s.mat, e->npart, e->G0[1], tt, e->d_args, 0, nullptr, svd_at(e, s, 0)));
+    if (launch_p2g(e, true, frame(0), frame(1), s.mat, e->G0[1], tt, 0, nullptr, svd_at(e, s, 0))) return -1;
   }
   for (int q = 0; q < e->S; q++) {
     if (seq_grid_fwd(e, s, q)) return -1;
     int set = (q + 1) & 1, nset = set ^ 1;
     if (q + 1 < e->S) {
       TileTrack tt{e->tile_epoch[nset], e->tile_list[nset], e->tile_count + ((q + 2) & 3)};
-      if (e->big)
-        switch (e->minb_g2p2g) {
-          case 5: KL(KID_G2P2G, k_g2p2g<5><<<nb, pb, 0, e->qs>>>(k, frame(q), frame(q + 1), frame(q + 2), s.mat, e->npart, e->G0[set],
-                                                       e->G0[nset], tt, e->d_args, q + 1, svd_at(e, s, q + 1))); break;
-          case 4: KL(KID_G2P2G, k_g2p2g<4><<<nb, pb, 0, e->qs>>>(k, frame(q), frame(q + 1), frame(q + 2), s.mat, e->npart, e->G0[set],
-                                                       e->G0[nset], tt, e->d_args, q + 1, svd_at(e, s, q + 1))); break;
-          default: KL(KID_G2P2G, k_g2p2g<3><<<nb, pb, 0, e->qs>>>(k, frame(q), frame(q + 1), frame(q + 2), s.mat, e->npart, e->G0[set],
-                                                       e->G0[nset], tt, e->d_args, q + 1, svd_at(e, s, q + 1))); break;
-        }
-      else
-        KL(KID_G2P2G, k_g2p2g_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, e->qs>>>(
-                          k, frame(q), frame(q + 1), frame(q + 2), s.mat, e->npart, e->G0[set], e->G0[nset], tt, e->d_args, q + 1, svd_at(e, s, q + 1)));
+      if (launch_g2p2g(e, frame(q), frame(q + 1), frame(q + 2), s.mat, e->G0[set], e->G0[nset], tt, q + 1, svd_at(e, s, q + 1))) return -1;
     } else {
       KL(KID_G2P, k_g2p<<<nb, pb, 0, e->qs>>>(k, frame(q), frame(q + 1), e->npart, e->G0[set]));
     }
@@ -822,31 +897,17 @@ static int seq_substep_grad(dsk_engine* e, StepSlot& s, int q, int j) {
     run_if = s.tape.overflow;
   }
   if (!(e->seq_use_tape && e->seq_tape_trusted)) {
-    KL(KID_P2G_RECOMPUTE, k_p2g<false, 3><<<nb, pb, 0, e->qs>>>(k, fin, nullptr, s.mat, e->npart, e->G0[set], tt, e->d_args, q, run_if, nullptr));
+    if (launch_p2g(e, false, fin, nullptr, s.mat, e->G0[set], tt, q, run_if, nullptr)) return -1;
     KL(KID_GRID_RECOMPUTE, GRID_FWD_LAUNCH(e, e->qs,
                                k, e->grid_tools, s.poses, j, e->G0[set], e->Gv[set], tt.list, tt.count,
                                clr ? e->tile_list[prev] : nullptr, e->tile_count + (q & 3), clr ? e->G0[prev] : nullptr,
                                clr ? e->Gv[prev] : nullptr, clr ? e->Ga[prev] : nullptr, e->tile_count + ((q + 3) & 3),
                                GridTape{nullptr, nullptr, nullptr, nullptr, 0}, run_if));
   }
-  if (e->big)
-    switch (e->minb_g2p_adj) {
-      case 5: KL(KID_G2P_ADJ, k_g2p_adj<5><<<nb, pb, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set])); break;
-      case 4: KL(KID_G2P_ADJ, k_g2p_adj<4><<<nb, pb, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set])); break;
-      default: KL(KID_G2P_ADJ, k_g2p_adj<3><<<nb, pb, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set])); break;
-    }
-  else
-    KL(KID_G2P_ADJ, k_g2p_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
+  if (launch_g2p_adj(e, fin, fnext, ain, aout, e->Gv[set], e->Ga[set])) return -1;
   KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, e->qs, (GridAdjScratch{nullptr, nullptr, 0}), k, e->grid_tools, s.poses, j, e->G0[set], e->Ga[set],
                                                                       tt.list, tt.count, e->pose_adj));
-  if (e->big)
-    switch (e->minb_p2g_adj) {
-      case 5: KL(KID_P2G_ADJ, k_p2g_adj<5><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set], svd_at(e, s, j))); break;
-      case 4: KL(KID_P2G_ADJ, k_p2g_adj<4><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set], svd_at(e, s, j))); break;
-      default: KL(KID_P2G_ADJ, k_p2g_adj<3><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set], svd_at(e, s, j))); break;
-    }
-  else
-    KL(KID_P2G_ADJ, k_p2g_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, e->qs>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set], svd_at(e, s, j)));
+  if (launch_p2g_adj(e, fin, ain, aout, s.mat, e->Ga[set], svd_at(e, s, j))) return -1;
   LAUNCH_CHECK();
   e->bwd_cur ^= 1;
   return 0;
@@ -901,28 +962,14 @@ static int enqueue_backward_pipelined(dsk_engine* e, StepSlot& s) {
     float* fnext = s.frames + (size_t)(j + 1) * e->frame_floats;
     float* ain = e->adjw[e->bwd_cur];
     float* aout = e->adjw[e->bwd_cur ^ 1];
-    if (e->big)
-      switch (e->minb_g2p_adj) {
-        case 5: KL(KID_G2P_ADJ, k_g2p_adj<5><<<nb, pb, 0, mainq>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set])); break;
-        case 4: KL(KID_G2P_ADJ, k_g2p_adj<4><<<nb, pb, 0, mainq>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set])); break;
-        default: KL(KID_G2P_ADJ, k_g2p_adj<3><<<nb, pb, 0, mainq>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set])); break;
-      }
-    else
-      KL(KID_G2P_ADJ, k_g2p_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, mainq>>>(k, fin, fnext, ain, aout, e->npart, e->Gv[set], e->Ga[set]));
+    if (launch_g2p_adj(e, fin, fnext, ain, aout, e->Gv[set], e->Ga[set])) return -1;   // on e->qs == mainq
     // the pose adjoints of the contacts leave the critical path: parked here, reduced on the side branch two
     // positions later (before this grid set is cleared); the last two positions do them inline
     bool park = !e->flat_grid && e->gadj_scratch[0] && q + 2 < e->S;
     GridAdjScratch sc{park ? e->gadj_scratch[q & 1] : nullptr, park ? e->gadj_flags[q & 1] : nullptr, park ? e->gadj_cap : 0};
     KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, mainq, sc, k, e->grid_tools, s.poses, j, e->G0[set], e->Ga[set],
                                                                           tt.list, tt.count, e->pose_adj));
-    if (e->big)
-      switch (e->minb_p2g_adj) {
-        case 5: KL(KID_P2G_ADJ, k_p2g_adj<5><<<nb, pb, 0, mainq>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set], svd_at(e, s, j))); break;
-        case 4: KL(KID_P2G_ADJ, k_p2g_adj<4><<<nb, pb, 0, mainq>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set], svd_at(e, s, j))); break;
-        default: KL(KID_P2G_ADJ, k_p2g_adj<3><<<nb, pb, 0, mainq>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set], svd_at(e, s, j))); break;
-      }
-    else
-      KL(KID_P2G_ADJ, k_p2g_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, mainq>>>(k, fin, ain, aout, s.mat, e->npart, e->Ga[set], svd_at(e, s, j)));
+    if (launch_p2g_adj(e, fin, ain, aout, s.mat, e->Ga[set], svd_at(e, s, j))) return -1;
     CK(cudaEventRecord(e->ev_main[q], mainq));
     e->bwd_cur ^= 1;
   }

@@ -11,7 +11,7 @@
 #include "kernels_fwd.cuh"
 
 // g2p.grad : reads adjoints of (x,v,C)[j+1], scatters adjoint of grid_v_out, writes the g2p part of x.grad[j]
-template <int MINB>
+template <int MINB, bool TS>
 __global__ void __launch_bounds__(128, MINB)
     k_g2p_adj(SimConst k, const float* __restrict__ fin, const float* __restrict__ fnext,
               const float* __restrict__ adj_in, float* __restrict__ adj_out, const int* __restrict__ npart,
@@ -33,13 +33,14 @@ __global__ void __launch_bounds__(128, MINB)
   float4* Gae = Ga + (size_t)env * k.nnode;
   // adjoint of grid_v_out: warp-aggregated scatter
   TileTrack none{nullptr, nullptr, nullptr};
-  warp_scatter27(k, active, s, Gae, none, false, env, 0, [&](int i, int j, int l) { return g2p_adj_node(s, c, i, j, l); });
+  scatter27_affine<TS>(k, active, s, Gae, none, false, env, 0, make_float4(c.b0.x, c.b0.y, c.b0.z, 0.f), c.cx, c.cy, c.cz);
   if (!active) return;
   float3 gx = g2p_adj_finish(k, s, Gve, gC, c);
   store_v3(adj_out, CX, k.stride, gid, gx);
 }
 
 // plane-split g2p.grad for small engines (see warp_scatter9): blockDim = (PL_PARTICLES, 3)
+template <bool TS>
 __global__ void __launch_bounds__(PL_PARTICLES * 3)
     k_g2p_adj_pl(SimConst k, const float* __restrict__ fin, const float* __restrict__ fnext,
                  const float* __restrict__ adj_in, float* __restrict__ adj_out, const int* __restrict__ npart,
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(PL_PARTICLES * 3)
   float3 cy = f3(k.c_C * gC.m[1], k.c_C * gC.m[4], k.c_C * gC.m[7]);
   float3 cz = f3(k.c_C * gC.m[2], k.c_C * gC.m[5], k.c_C * gC.m[8]);
   float3 b0 = gvn - k.c_C * mv(gC, f3(s.fx, s.fy, s.fz)) + (float)pl * cx;   // plane term folded in
-  warp_scatter9(k, active, s, pl, oxp, Gae, none, false, env, 0, [&](int j, int l) {
+  scatter9<TS>(k, active, s, pl, oxp, Gae, none, false, env, 0, [&](int j, int l) {
     float w = wxp * s.wy[j] * s.wz[l];
     float3 a = b0 + (float)j * cy + (float)l * cz;
     return make_float4(w * a.x, w * a.y, w * a.z, 0.f);

@@ -318,5 +318,179 @@ DSK_DEV void warp_scatter9(const SimConst& k, bool active, const Stencil& s, int
     if (!(lane & 1) && m < 9) red_add4(&Ge[node_offset(bx + plane, by + m / 3, bz + m % 3, k.nt)], acc[0]);
   }
 }
+// ---- transposed shared-memory scatter (round 2) -------------------------------------------------------------------------
+// The butterfly above costs ~900 instructions per lane and group (124 shuffles, 248 selects, the 27 values re-evaluated
+// for every group) and its segmented fallback ~1 300.  Here every lane writes its 27 float4 contributions ONCE into a
+// per-warp shared-memory tile laid out [node][lane] (row stride 33 float4: the STS.128 of a warp and the LDS.128 of 27
+// lanes walking 27 different rows are both conflict-free), and for every RUN of adjacent lanes with equal cell keys
+// lanes 0..26 add up their node's row segment and issue one RED.128: 27 STS + 32 LDS + 128 FADD per lane whatever the
+// number of runs.  Strays (the sort is per env step) simply form runs of length one; inactive lanes store zeros.
+#define TS_ROW 33
+#define TS_WARP_FLOAT4 (27 * TS_ROW)      // 14 256 bytes per warp
+#define TS9_WARP_FLOAT4 (9 * TS_ROW)      //  4 752 bytes per warp (plane-split kernels)
+// run bookkeeping shared by the transposed scatters: heads of the runs of adjacent equal keys (an inactive lane is a dead
+// run of its own, so that no live run ever covers a row element an inactive lane wrote), the stencil tiles marked once per
+// live run; returns the ballot of run heads (0: no active lane) and the ballot of active lanes
+DSK_DEV unsigned ts_run_heads(const SimConst& k, bool active, const Stencil& s, const TileTrack& tt, bool mark, int env,
+                              int epoch, unsigned& act) {
+  const int lane = threadIdx.x & 31;
+  int key = active ? node_offset(s.bx, s.by, s.bz, k.nt) : -1 - lane;
+  act = __ballot_sync(0xffffffffu, active);
+  int prev = __shfl_up_sync(0xffffffffu, key, 1);
+  bool head = lane == 0 || prev != key;
+  unsigned heads = __ballot_sync(0xffffffffu, head);
+  if (mark && head && active) mark_stencil_tiles(k, tt, env, s, epoch);   // idempotent per (tile, epoch)
+  return act ? heads : 0u;
+}
+// second half: for every run lanes 0..26 add up their node's row segment and issue one RED.128
+DSK_DEV void ts_reduce_runs27(const SimConst& k, const Stencil& s, float4* __restrict__ Ge, const float4* wbuf, unsigned todo,
+                              unsigned act) {
+  const int lane = threadIdx.x & 31;
+  const int i = lane / 9, j = (lane / 3) % 3, l = lane % 3;   // stencil node owned by lanes 0..26
+  const float4* row = wbuf + (lane < 27 ? lane : 0) * TS_ROW;
+  while (todo) {
+    int h = __ffs(todo) - 1;
+    todo &= todo - 1;
+    int e = todo ? __ffs(todo) - 1 : 32;   // the run is [h, e)
+    if (!((act >> h) & 1u)) continue;      // dead run (inactive lane)
+    int bx = __shfl_sync(0xffffffffu, s.bx, h), by = __shfl_sync(0xffffffffu, s.by, h),
+        bz = __shfl_sync(0xffffffffu, s.bz, h);
+    if (lane < 27) {
+      float4 acc = row[h];
+#pragma unroll 4
+      for (int t = h + 1; t < e; t++) acc = f4add(acc, row[t]);
+      red_add4(&Ge[node_offset(bx + i, by + j, bz + l, k.nt)], acc);
+    }
+  }
+}
+template <class F>
+DSK_DEV void warp_scatter27_ts(const SimConst& k, bool active, const Stencil& s, float4* __restrict__ Ge,
+                               const TileTrack& tt, bool mark, int env, int epoch, float4* wbuf, F val) {
+  const int lane = threadIdx.x & 31;
+  unsigned act;
+  unsigned todo = ts_run_heads(k, active, s, tt, mark, env, epoch, act);
+  if (!todo) return;
+#pragma unroll
+  for (int q = 0; q < 27; q++) wbuf[q * TS_ROW + lane] = val(q / 9, (q / 3) % 3, q % 3);
+  __syncwarp();
+  ts_reduce_runs27(k, s, Ge, wbuf, todo, act);
+  __syncwarp();   // the tile is rewritten by the warp's next scatter
+}
+// Both scatters of a substep have AFFINE contributions: node (i, j, l) receives w_ijl * (A0 + i AX + j AY + l AZ) with
+// float4 coefficients (p2g: A0 = (p_mass v - dx affine fx, p_mass), AX.. = dx * columns of affine; g2p.grad: A0 = (b0, 0),
+// AX.. = (c_C * columns of gC, 0)).  The 27 values are built incrementally, (x, y) and (z, w) as packed pairs: ~150
+// instructions instead of 27 x 15.
+DSK_DEV void warp_scatter27_ts_affine(const SimConst& k, bool active, const Stencil& s, float4* __restrict__ Ge,
+                                      const TileTrack& tt, bool mark, int env, int epoch, float4* wbuf, float4 A0, float3 AX,
+                                      float3 AY, float3 AZ) {
+  const int lane = threadIdx.x & 31;
+  unsigned act;
+  unsigned todo = ts_run_heads(k, active, s, tt, mark, env, epoch, act);
+  if (!todo) return;
+  {
+    const float2 axl = f2(AX.x, AX.y), axh = f2(AX.z, 0.f), ayl = f2(AY.x, AY.y), ayh = f2(AY.z, 0.f);
+    const float2 azl = f2(AZ.x, AZ.y), azh = f2(AZ.z, 0.f);
+    float2 lo_i = f2(A0.x, A0.y), hi_i = f2(A0.z, A0.w);
+    float4* col = wbuf + lane;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      float2 lo_ij = lo_i, hi_ij = hi_i;
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const float wxy = s.wx[i] * s.wy[j];
+        float2 lo = lo_ij, hi = hi_ij;
+#pragma unroll
+        for (int l = 0; l < 3; l++) {
+          const float2 w2 = bc2(wxy * s.wz[l]);
+          float2 vlo = mul2(w2, lo), vhi = mul2(w2, hi);
+          col[((i * 3 + j) * 3 + l) * TS_ROW] = make_float4(vlo.x, vlo.y, vhi.x, vhi.y);
+          if (l < 2) {
+            lo = add2(lo, azl);
+            hi = add2(hi, azh);
+          }
+        }
+        if (j < 2) {
+          lo_ij = add2(lo_ij, ayl);
+          hi_ij = add2(hi_ij, ayh);
+        }
+      }
+      if (i < 2) {
+        lo_i = add2(lo_i, axl);
+        hi_i = add2(hi_i, axh);
+      }
+    }
+  }
+  __syncwarp();
+  ts_reduce_runs27(k, s, Ge, wbuf, todo, act);
+  __syncwarp();
+}
+// one x-plane (9 nodes) per thread, for the plane-split kernels: lanes (part, node) = (lane / 9, lane % 9) add every third
+// element of the run's row segment, two shuffle-downs combine the three parts
+template <class F>
+DSK_DEV void warp_scatter9_ts(const SimConst& k, bool active, const Stencil& s, int plane, float4* __restrict__ Ge,
+                              const TileTrack& tt, bool mark, int env, int epoch, float4* wbuf, F val) {
+  const int lane = threadIdx.x & 31;
+  unsigned act;
+  unsigned todo = ts_run_heads(k, active, s, tt, mark, env, epoch, act);
+  if (!todo) return;
+#pragma unroll
+  for (int q = 0; q < 9; q++) wbuf[q * TS_ROW + lane] = val(q / 3, q % 3);
+  __syncwarp();
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int part = lane / 9, q = lane - part * 9;
+  const float4* row = wbuf + (lane < 27 ? q : 0) * TS_ROW;
+  while (todo) {
+    int h = __ffs(todo) - 1;
+    todo &= todo - 1;
+    int e = todo ? __ffs(todo) - 1 : 32;
+    if (!((act >> h) & 1u)) continue;      // dead run (inactive lane)
+    int bx = __shfl_sync(0xffffffffu, s.bx, h), by = __shfl_sync(0xffffffffu, s.by, h),
+        bz = __shfl_sync(0xffffffffu, s.bz, h);
+    float4 acc = z4;
+    if (lane < 27)
+      for (int t = h + part; t < e; t += 3) acc = f4add(acc, row[t]);
+    float4 a1 = f4shfl_down(acc, 9), a2 = f4shfl_down(acc, 18);
+    if (lane < 9) red_add4(&Ge[node_offset(bx + plane, by + q / 3, bz + q % 3, k.nt)], f4add(f4add(acc, a1), a2));
+  }
+  __syncwarp();
+}
+// scatter front ends of the kernels: TS selects the transposed shared-memory version (dynamic shared memory:
+// TS_WARP_FLOAT4 / TS9_WARP_FLOAT4 float4 per warp of the CTA)
+template <bool TS, class F>
+DSK_DEV void scatter27(const SimConst& k, bool active, const Stencil& s, float4* __restrict__ Ge, const TileTrack& tt,
+                       bool mark, int env, int epoch, F val) {
+  if (TS) {
+    DSK_DYN_SMEM(float4, ts_buf);
+    warp_scatter27_ts(k, active, s, Ge, tt, mark, env, epoch, ts_buf + (threadIdx.x >> 5) * TS_WARP_FLOAT4, val);
+  } else {
+    warp_scatter27(k, active, s, Ge, tt, mark, env, epoch, val);
+  }
+}
+// affine contributions (see warp_scatter27_ts_affine); the butterfly path evaluates the same values through a lambda
+template <bool TS>
+DSK_DEV void scatter27_affine(const SimConst& k, bool active, const Stencil& s, float4* __restrict__ Ge, const TileTrack& tt,
+                              bool mark, int env, int epoch, float4 A0, float3 AX, float3 AY, float3 AZ) {
+  if (TS) {
+    DSK_DYN_SMEM(float4, ts_buf);
+    warp_scatter27_ts_affine(k, active, s, Ge, tt, mark, env, epoch, ts_buf + (threadIdx.x >> 5) * TS_WARP_FLOAT4, A0, AX, AY, AZ);
+  } else {
+    warp_scatter27(k, active, s, Ge, tt, mark, env, epoch, [&](int i, int j, int l) {
+      float w = s.wx[i] * s.wy[j] * s.wz[l];
+      float3 a = f3(A0.x, A0.y, A0.z) + (float)i * AX + (float)j * AY + (float)l * AZ;
+      return make_float4(w * a.x, w * a.y, w * a.z, w * A0.w);
+    });
+  }
+}
+template <bool TS, class F>
+DSK_DEV void scatter9(const SimConst& k, bool active, const Stencil& s, int plane, int oxp, float4* __restrict__ Ge,
+                      const TileTrack& tt, bool mark, int env, int epoch, F val) {
+  if (TS) {
+    DSK_DYN_SMEM(float4, ts_buf);
+    int warp = (threadIdx.y * blockDim.x + threadIdx.x) >> 5;
+    warp_scatter9_ts(k, active, s, plane, Ge, tt, mark, env, epoch, ts_buf + warp * TS9_WARP_FLOAT4, val);
+  } else {
+    warp_scatter9(k, active, s, plane, oxp, Ge, tt, mark, env, epoch, val);
+  }
+}
 DSK_DEV float pick3(const float* a, int i) { return i == 0 ? a[0] : (i == 1 ? a[1] : a[2]); }
 DSK_DEV int pick3(const int* a, int i) { return i == 0 ? a[0] : (i == 1 ? a[1] : a[2]); }

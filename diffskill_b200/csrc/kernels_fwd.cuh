@@ -10,7 +10,7 @@
 
 // MINB = min CTAs/SM the register allocation must allow: 1 for small (latency-bound) problems -- all registers, no
 // spills; 3 for large batches where occupancy hides the scatter latency
-template <bool WRITE_F, int MINB>
+template <bool WRITE_F, int MINB, bool TS>
 __global__ void __launch_bounds__(128, MINB)
     k_p2g(SimConst k, const float* __restrict__ fin, float* __restrict__ fout, const float* __restrict__ mat,
           const int* __restrict__ npart, float4* __restrict__ G, TileTrack tt, const StepArgs* __restrict__ args,
@@ -41,11 +41,7 @@ __global__ void __launch_bounds__(128, MINB)
   float3 ax = f3(k.dx * o.affine.m[0], k.dx * o.affine.m[3], k.dx * o.affine.m[6]);
   float3 ay = f3(k.dx * o.affine.m[1], k.dx * o.affine.m[4], k.dx * o.affine.m[7]);
   float3 az = f3(k.dx * o.affine.m[2], k.dx * o.affine.m[5], k.dx * o.affine.m[8]);
-  warp_scatter27(k, active, s, Ge, tt, true, env, args->epoch_base + q + 1, [&](int i, int j, int l) {
-    float w = s.wx[i] * s.wy[j] * s.wz[l];
-    float3 a = a0 + (float)i * ax + (float)j * ay + (float)l * az;
-    return make_float4(w * a.x, w * a.y, w * a.z, w * k.p_mass);
-  });
+  scatter27_affine<TS>(k, active, s, Ge, tt, true, env, args->epoch_base + q + 1, make_float4(a0.x, a0.y, a0.z, k.p_mass), ax, ay, az);
 }
 
 #define GRID_CTA 64
@@ -312,7 +308,7 @@ __global__ void __launch_bounds__(128)
 // Fused g2p of substep q and p2g of substep q+1 ("G2P2G"): the particle state of frame q+1 is produced and consumed
 // in registers (it is still stored: the adjoint needs the frame), one launch fewer per substep.  Gprev = grid set of
 // substep q (velocities), Gnext = the other set (scatter target, tiles tracked for substep q+1).
-template <int MINB>
+template <int MINB, bool TS>
 __global__ void __launch_bounds__(128, MINB)
     k_g2p2g(SimConst k, const float* __restrict__ fprev, float* __restrict__ fcur, float* __restrict__ fnext,
             const float* __restrict__ mat, const int* __restrict__ npart, const float4* __restrict__ Gprev,
@@ -348,18 +344,15 @@ __global__ void __launch_bounds__(128, MINB)
   float3 ax = f3(k.dx * o.affine.m[0], k.dx * o.affine.m[3], k.dx * o.affine.m[6]);
   float3 ay = f3(k.dx * o.affine.m[1], k.dx * o.affine.m[4], k.dx * o.affine.m[7]);
   float3 az = f3(k.dx * o.affine.m[2], k.dx * o.affine.m[5], k.dx * o.affine.m[8]);
-  warp_scatter27(k, active, s, Gnext + (size_t)env * k.nnode, tt, true, env, args->epoch_base + qnext + 1,
-                 [&](int i, int j, int l) {
-                   float w = s.wx[i] * s.wy[j] * s.wz[l];
-                   float3 a = a0 + (float)i * ax + (float)j * ay + (float)l * az;
-                   return make_float4(w * a.x, w * a.y, w * a.z, w * k.p_mass);
-                 });
+  scatter27_affine<TS>(k, active, s, Gnext + (size_t)env * k.nnode, tt, true, env, args->epoch_base + qnext + 1,
+                       make_float4(a0.x, a0.y, a0.z, k.p_mass), ax, ay, az);
 }
 
 // plane-split fused g2p(q) + p2g(q+1) for small engines (see warp_scatter9): blockDim = (PL_PARTICLES, 3).  Each of
 // the three threads of a particle gathers one x-plane of the stencil; the partial sums are exchanged through shared
 // memory and added in a fixed order, so the three threads continue with bit-identical state (SVD, return map --
 // redundantly, the machine is idle anyway) and each scatters one x-plane of the new stencil.
+template <bool TS>
 __global__ void __launch_bounds__(PL_PARTICLES * 3)
     k_g2p2g_pl(SimConst k, const float* __restrict__ fprev, float* __restrict__ fcur, float* __restrict__ fnext,
                const float* __restrict__ mat, const int* __restrict__ npart, const float4* __restrict__ Gprev,
@@ -431,7 +424,7 @@ __global__ void __launch_bounds__(PL_PARTICLES * 3)
   float3 ay = f3(k.dx * o.affine.m[1], k.dx * o.affine.m[4], k.dx * o.affine.m[7]);
   float3 az = f3(k.dx * o.affine.m[2], k.dx * o.affine.m[5], k.dx * o.affine.m[8]);
   float3 a0 = k.p_mass * nv - k.dx * mv(o.affine, fxv) + (float)pl * ax;   // plane term folded in
-  warp_scatter9(k, active, s, pl, oxp, Gnext + (size_t)env * k.nnode, tt, pl == 0, env, args->epoch_base + qnext + 1,
+  scatter9<TS>(k, active, s, pl, oxp, Gnext + (size_t)env * k.nnode, tt, pl == 0, env, args->epoch_base + qnext + 1,
                 [&](int j, int l) {
                   float w = wxp * s.wy[j] * s.wz[l];
                   float3 a = a0 + (float)j * ay + (float)l * az;

@@ -82,6 +82,40 @@ DSK_DEV float3 cross_rn(float3 a, float3 b) {
             sub_rn(mul_rn(a.x, b.y), mul_rn(a.y, b.x)));
 }
 
+// ---- packed fp32x2 arithmetic: Blackwell FFMA2 / FMUL2 / FADD2 (PTX fma/mul/add.rn.f32x2, sm_100+) -------------------------
+// One instruction, two IEEE fp32 results (each rounded exactly like its scalar counterpart): the stencil loops and the
+// Jacobi rotations work on (x, y) / (z, w) pairs, which halves their issue slots.  Host builds (tests/host_check) use the
+// scalar operations.
+#if defined(__CUDA_ARCH__)
+DSK_DEV float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+DSK_DEV float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+DSK_DEV float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+#else
+DSK_DEV float2 fma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+DSK_DEV float2 mul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+DSK_DEV float2 add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+#endif
+DSK_DEV float2 f2(float x, float y) { return make_float2(x, y); }
+DSK_DEV float2 bc2(float s) { return make_float2(s, s); }   // broadcast
+
 // ---- quaternions (w,x,y,z), plb/engine/primitive/utils.py ------------------------------------
 // qrot, utils.py:9-15
 DSK_DEV float3 qrot_rn(Q4 q, float3 v) {

@@ -468,26 +468,73 @@ DSK_DEV void p2g_adj_particle(const SimConst& k, int gid, int env, const float* 
   float3 ay = f3(k.dx * o.affine.m[1], k.dx * o.affine.m[4], k.dx * o.affine.m[7]);
   float3 az = f3(k.dx * o.affine.m[2], k.dx * o.affine.m[5], k.dx * o.affine.m[8]);
   float gwx[3] = {0, 0, 0}, gwy[3] = {0, 0, 0}, gwz[3] = {0, 0, 0};
-  float3 S0 = f3(0, 0, 0), m0 = f3(0, 0, 0), m1 = f3(0, 0, 0), m2 = f3(0, 0, 0);
+  float3 S0, m0, m1, m2;
+  {
+    // moments of the grid adjoint (S0 = sum w G, M = sum w G (x) offset) by sum factorisation along l, j, i as in
+    // g2p_particle; the weight adjoints gw = G . (a, p_mass) per node with the affine value a(i, j, l) built
+    // incrementally, (x, y) and (z, mass) as packed pairs
+    const float2 wz0 = bc2(s.wz[0]), wz1 = bc2(s.wz[1]), wz2 = bc2(s.wz[2]), wz22 = bc2(2.f * s.wz[2]);
+    const float2 axl = f2(ax.x, ax.y), ayl = f2(ay.x, ay.y), azl = f2(az.x, az.y);
+    float2 S0p = f2(0.f, 0.f), m0p = f2(0.f, 0.f), m1p = f2(0.f, 0.f), m2p = f2(0.f, 0.f);
+    float S0z = 0.f, m0z = 0.f, m1z = 0.f, m2z = 0.f;
+    float2 ai_lo = f2(a0.x, a0.y);
+    float ai_z = a0.z;
 #pragma unroll
-  for (int i = 0; i < 3; i++)
+    for (int i = 0; i < 3; i++) {
+      float2 Q = f2(0.f, 0.f), Qy = f2(0.f, 0.f), Ql = f2(0.f, 0.f);
+      float Qz = 0.f, Qyz = 0.f, Qlz = 0.f;
+      float2 aij_lo = ai_lo;
+      float aij_z = ai_z;
 #pragma unroll
-    for (int j = 0; j < 3; j++)
-#pragma unroll
-      for (int l = 0; l < 3; l++) {
-        float4 g4 = Gae[s.ox[i] + s.oy[j] + s.oz[l]];
-        float3 G = f3(g4.x, g4.y, g4.z);
-        float3 a = a0 + (float)i * ax + (float)j * ay + (float)l * az;
-        float gw = dot(G, a) + g4.w * k.p_mass;
-        float3 wG = (s.wx[i] * s.wy[j] * s.wz[l]) * G;
-        S0 += wG;
-        if (i) m0 += (float)i * wG;
-        if (j) m1 += (float)j * wG;
-        if (l) m2 += (float)l * wG;
-        gwx[i] += gw * s.wy[j] * s.wz[l];
-        gwy[j] += gw * s.wx[i] * s.wz[l];
-        gwz[l] += gw * s.wx[i] * s.wy[j];
+      for (int j = 0; j < 3; j++) {
+        const int ob = s.ox[i] + s.oy[j];
+        float4 g0 = Gae[ob + s.oz[0]], g1 = Gae[ob + s.oz[1]], g2 = Gae[ob + s.oz[2]];
+        float2 R = fma2(wz2, f2(g2.x, g2.y), fma2(wz1, f2(g1.x, g1.y), mul2(wz0, f2(g0.x, g0.y))));
+        float Rz = fmaf(s.wz[2], g2.z, fmaf(s.wz[1], g1.z, s.wz[0] * g0.z));
+        float2 R1 = fma2(wz22, f2(g2.x, g2.y), mul2(wz1, f2(g1.x, g1.y)));
+        float R1z = fmaf(wz22.x, g2.z, s.wz[1] * g1.z);
+        const float wy = s.wy[j];
+        Q = fma2(bc2(wy), R, Q);
+        Qz = fmaf(wy, Rz, Qz);
+        Ql = fma2(bc2(wy), R1, Ql);
+        Qlz = fmaf(wy, R1z, Qlz);
+        if (j) {
+          Qy = fma2(bc2((float)j * wy), R, Qy);
+          Qyz = fmaf((float)j * wy, Rz, Qyz);
+        }
+        // gw(i,j,l) = G . a(i,j,l) + gm p_mass
+        const float wxy = s.wx[i] * wy;
+        float2 t0 = fma2(f2(g0.z, g0.w), f2(aij_z, k.p_mass), mul2(f2(g0.x, g0.y), aij_lo));
+        float2 a1 = add2(aij_lo, azl);
+        float2 t1 = fma2(f2(g1.z, g1.w), f2(aij_z + az.z, k.p_mass), mul2(f2(g1.x, g1.y), a1));
+        float2 a2 = add2(a1, azl);
+        float2 t2 = fma2(f2(g2.z, g2.w), f2(aij_z + 2.f * az.z, k.p_mass), mul2(f2(g2.x, g2.y), a2));
+        float gw0 = t0.x + t0.y, gw1 = t1.x + t1.y, gw2 = t2.x + t2.y;
+        gwz[0] = fmaf(gw0, wxy, gwz[0]);
+        gwz[1] = fmaf(gw1, wxy, gwz[1]);
+        gwz[2] = fmaf(gw2, wxy, gwz[2]);
+        float h = fmaf(gw2, s.wz[2], fmaf(gw1, s.wz[1], gw0 * s.wz[0]));
+        gwx[i] = fmaf(h, wy, gwx[i]);
+        gwy[j] = fmaf(h, s.wx[i], gwy[j]);
+        aij_lo = add2(aij_lo, ayl);
+        aij_z += ay.z;
       }
+      const float wx = s.wx[i];
+      S0p = fma2(bc2(wx), Q, S0p);   S0z = fmaf(wx, Qz, S0z);
+      m1p = fma2(bc2(wx), Qy, m1p);  m1z = fmaf(wx, Qyz, m1z);
+      m2p = fma2(bc2(wx), Ql, m2p);  m2z = fmaf(wx, Qlz, m2z);
+      if (i) {
+        m0p = fma2(bc2((float)i * wx), Q, m0p);
+        m0z = fmaf((float)i * wx, Qz, m0z);
+      }
+      ai_lo = add2(ai_lo, axl);
+      ai_z += ax.z;
+    }
+    S0 = f3(S0p.x, S0p.y, S0z);
+    m0 = f3(m0p.x, m0p.y, m0z);
+    m1 = f3(m1p.x, m1p.y, m1z);
+    m2 = f3(m2p.x, m2p.y, m2z);
+  }
   p2g_adj_finish(k, gid, s, o, mu, lam, C, F, adj_in, adj_out, S0, m0, m1, m2, gwx, gwy, gwz);
 }
 
@@ -520,22 +567,49 @@ DSK_DEV float4 g2p_adj_node(const Stencil& s, const G2PAdj& c, int i, int j, int
 DSK_DEV float3 g2p_adj_finish(const SimConst& k, const Stencil& s, const float4* __restrict__ Gve, const M3& gC,
                               const G2PAdj& c) {
   float gwx[3] = {0, 0, 0}, gwy[3] = {0, 0, 0}, gwz[3] = {0, 0, 0};
-  float3 sg = f3(0, 0, 0);
+  float3 sg;
+  {
+    // sg = sum w g per node; gw = g . a(i,j,l) with the affine value built incrementally ((x, y) packed, z scalar)
+    const float2 cxl = f2(c.cx.x, c.cx.y), cyl = f2(c.cy.x, c.cy.y), czl = f2(c.cz.x, c.cz.y);
+    float2 sgp = f2(0.f, 0.f);
+    float sgz = 0.f;
+    float2 ai_lo = f2(c.b0.x, c.b0.y);
+    float ai_z = c.b0.z;
 #pragma unroll
-  for (int i = 0; i < 3; i++)
+    for (int i = 0; i < 3; i++) {
+      float2 aij_lo = ai_lo;
+      float aij_z = ai_z;
 #pragma unroll
-    for (int j = 0; j < 3; j++)
-#pragma unroll
-      for (int l = 0; l < 3; l++) {
-        float4 g4 = Gve[s.ox[i] + s.oy[j] + s.oz[l]];
-        float3 g = f3(g4.x, g4.y, g4.z);
-        float3 a = c.b0 + (float)i * c.cx + (float)j * c.cy + (float)l * c.cz;
-        float gw = dot(g, a);
-        sg += (s.wx[i] * s.wy[j] * s.wz[l]) * g;
-        gwx[i] += gw * s.wy[j] * s.wz[l];
-        gwy[j] += gw * s.wx[i] * s.wz[l];
-        gwz[l] += gw * s.wx[i] * s.wy[j];
+      for (int j = 0; j < 3; j++) {
+        const int ob = s.ox[i] + s.oy[j];
+        float4 g0 = Gve[ob + s.oz[0]], g1 = Gve[ob + s.oz[1]], g2 = Gve[ob + s.oz[2]];
+        const float wy = s.wy[j], wxy = s.wx[i] * wy;
+        float2 R = fma2(bc2(s.wz[2]), f2(g2.x, g2.y), fma2(bc2(s.wz[1]), f2(g1.x, g1.y), mul2(bc2(s.wz[0]), f2(g0.x, g0.y))));
+        float Rz = fmaf(s.wz[2], g2.z, fmaf(s.wz[1], g1.z, s.wz[0] * g0.z));
+        sgp = fma2(bc2(wxy), R, sgp);
+        sgz = fmaf(wxy, Rz, sgz);
+        float2 t0 = mul2(f2(g0.x, g0.y), aij_lo);
+        float2 a1 = add2(aij_lo, czl);
+        float2 t1 = mul2(f2(g1.x, g1.y), a1);
+        float2 a2 = add2(a1, czl);
+        float2 t2 = mul2(f2(g2.x, g2.y), a2);
+        float gw0 = fmaf(g0.z, aij_z, t0.x + t0.y);
+        float gw1 = fmaf(g1.z, aij_z + c.cz.z, t1.x + t1.y);
+        float gw2 = fmaf(g2.z, aij_z + 2.f * c.cz.z, t2.x + t2.y);
+        gwz[0] = fmaf(gw0, wxy, gwz[0]);
+        gwz[1] = fmaf(gw1, wxy, gwz[1]);
+        gwz[2] = fmaf(gw2, wxy, gwz[2]);
+        float h = fmaf(gw2, s.wz[2], fmaf(gw1, s.wz[1], gw0 * s.wz[0]));
+        gwx[i] = fmaf(h, wy, gwx[i]);
+        gwy[j] = fmaf(h, s.wx[i], gwy[j]);
+        aij_lo = add2(aij_lo, cyl);
+        aij_z += c.cy.z;
       }
+      ai_lo = add2(ai_lo, cxl);
+      ai_z += c.cx.z;
+    }
+    sg = f3(sgp.x, sgp.y, sgz);
+  }
   float3 gf = (-k.c_C) * mTv(gC, sg);
   float dw[3];
   bspline1_grad(s.fx, dw);
@@ -608,21 +682,43 @@ DSK_DEV int prepare_frame(const SimConst& k, const ToolParams* sT, const FrameTa
 //   = c_C (M - new_v (x) fx),  M = sum w g (x) offset
 DSK_DEV void g2p_particle(const SimConst& k, const Stencil& s, const float4* __restrict__ Ge, float3 x, float3& nx,
                           float3& nv, M3& nC) {
-  nv = f3(0.f, 0.f, 0.f);
-  float3 m0 = f3(0.f, 0.f, 0.f), m1 = f3(0.f, 0.f, 0.f), m2 = f3(0.f, 0.f, 0.f);   // columns of M
+  // Sum factorisation over the tensor-product weights (round 2): first along l (R = sum_l wz_l g, R1 = sum_l l wz_l g per
+  // (i, j)), then along j, then along i -- 160 packed / scalar multiply-adds instead of 27 x 12.  (x, y) travel as one
+  // packed pair (FFMA2), z as a scalar.
+  const float2 wz0 = bc2(s.wz[0]), wz1 = bc2(s.wz[1]), wz2 = bc2(s.wz[2]), wz22 = bc2(2.f * s.wz[2]);
+  float2 nvp = f2(0.f, 0.f), m0p = f2(0.f, 0.f), m1p = f2(0.f, 0.f), m2p = f2(0.f, 0.f);
+  float nvz = 0.f, m0z = 0.f, m1z = 0.f, m2z = 0.f;
 #pragma unroll
-  for (int i = 0; i < 3; i++)
+  for (int i = 0; i < 3; i++) {
+    float2 Q = f2(0.f, 0.f), Qy = f2(0.f, 0.f), Ql = f2(0.f, 0.f);
+    float Qz = 0.f, Qyz = 0.f, Qlz = 0.f;
 #pragma unroll
-    for (int j = 0; j < 3; j++)
-#pragma unroll
-      for (int l = 0; l < 3; l++) {
-        float4 g = Ge[s.ox[i] + s.oy[j] + s.oz[l]];
-        float w = s.wx[i] * s.wy[j] * s.wz[l];
-        float3 wg = f3(w * g.x, w * g.y, w * g.z);
-        nv += wg;
-        if (i) m0 += (float)i * wg;
-        if (j) m1 += (float)j * wg;
-        if (l) m2 += (float)l * wg;
+    for (int j = 0; j < 3; j++) {
+      const int o = s.ox[i] + s.oy[j];
+      float4 g0 = Ge[o + s.oz[0]], g1 = Ge[o + s.oz[1]], g2 = Ge[o + s.oz[2]];
+      float2 R = fma2(wz2, f2(g2.x, g2.y), fma2(wz1, f2(g1.x, g1.y), mul2(wz0, f2(g0.x, g0.y))));
+      float Rz = fmaf(s.wz[2], g2.z, fmaf(s.wz[1], g1.z, s.wz[0] * g0.z));
+      float2 R1 = fma2(wz22, f2(g2.x, g2.y), mul2(wz1, f2(g1.x, g1.y)));
+      float R1z = fmaf(wz22.x, g2.z, s.wz[1] * g1.z);
+      const float wy = s.wy[j];
+      Q = fma2(bc2(wy), R, Q);
+      Qz = fmaf(wy, Rz, Qz);
+      Ql = fma2(bc2(wy), R1, Ql);
+      Qlz = fmaf(wy, R1z, Qlz);
+      if (j) {
+        Qy = fma2(bc2((float)j * wy), R, Qy);
+        Qyz = fmaf((float)j * wy, Rz, Qyz);
       }
-  g2p_finish(k, s, x, nv, m0, m1, m2, nx, nC);
+    }
+    const float wx = s.wx[i];
+    nvp = fma2(bc2(wx), Q, nvp);   nvz = fmaf(wx, Qz, nvz);
+    m1p = fma2(bc2(wx), Qy, m1p);  m1z = fmaf(wx, Qyz, m1z);
+    m2p = fma2(bc2(wx), Ql, m2p);  m2z = fmaf(wx, Qlz, m2z);
+    if (i) {
+      m0p = fma2(bc2((float)i * wx), Q, m0p);
+      m0z = fmaf((float)i * wx, Qz, m0z);
+    }
+  }
+  nv = f3(nvp.x, nvp.y, nvz);
+  g2p_finish(k, s, x, nv, f3(m0p.x, m0p.y, m0z), f3(m1p.x, m1p.y, m1z), f3(m2p.x, m2p.y, m2z), nx, nC);
 }

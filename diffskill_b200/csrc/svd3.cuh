@@ -5,84 +5,95 @@
 // rotations, singular values ordered by decreasing magnitude, sign carried by the last one.
 // Algorithm: 4 cyclic sweeps of one-sided (Hestenes) Jacobi on the columns of F, column
 // sort, U from the normalised columns with u2 = u0 x u1.  Everything is fully unrolled
-// so the 3x3s stay in registers.
+// so the 3x3s stay in registers.  Round 2: the rotation costs two MUFU.RSQ instead of two
+// reciprocals, a square root and a reciprocal square root, and the column updates are packed
+// (FFMA2): 1 071 -> ~500 thread-instructions per particle (profiles/r02*_ncu_sections_*.md).
 #pragma once
 #include "mpm_math.cuh"
 
-DSK_DEV void jacobi_pair(float& b0p, float& b1p, float& b2p, float& b0q, float& b1q, float& b2q, float& v0p,
-                         float& v1p, float& v2p, float& v0q, float& v1q, float& v2q) {
-  float al = b0p * b0p + b1p * b1p + b2p * b2p;
-  float be = b0q * b0q + b1q * b1q + b2q * b2q;
-  float ga = b0p * b0q + b1p * b1q + b2p * b2q;
-  if (ga != 0.f) {
-    // approximate reciprocals (MUFU, <= 2 ulp): for the rotation ANGLE an error only changes how fast the sweeps converge;
-    // zeta -> inf gives t -> 0
-    float zeta = DSK_FDIV(be - al, 2.f * ga);
-    float t = copysignf(1.f, zeta) * DSK_FDIV(1.f, fabsf(zeta) + sqrtf(1.f + zeta * zeta));
+// unbiased reciprocal square root: MUFU.RSQ plus one FMA-residual (Markstein) step.  A BIAS of ~1e-8 in the cosine of the
+// rotations rescales the columns of V and B the same way for every particle in every substep, sigma, R = U V^T and
+// U f(S) V^T drift coherently (v 1e-5 per substep on the B200) and the branch a soft-dough scene's gradient sits on flips
+// (Rope-v1: 3-step action gradient 3.5e-3 from the oracle).  The refined value is unbiased to 3e-10
+// whatever the bias of the MUFU result.  -DDSK_BIASED_COSINE restores the raw MUFU value.
+DSK_DEV float rsqrt_unbiased(float w) {
+  float y = DSK_RSQRT(w);
 #ifndef DSK_BIASED_COSINE
-    // The cosine is different: unless c^2 (1 + t^2) = 1 every rotation rescales the columns of V and B, and a BIAS of the
-    // approximation (MUFU.RSQ; a plain fp32 Newton step has -1.4e-8 on average) makes sigma, R = U V^T and U f(S) V^T
-    // drift the same way for every particle in every substep: v 1e-5 per substep on the B200, and the branch a soft-dough
-    // scene's gradient sits on flips (Rope-v1: 3-step action gradient 3.5e-3 from the oracle).
-    // The FMA-residual (Markstein) step below is unbiased to 3e-10 whatever the bias of its input, for 4 instructions.
-    // On the CPU emulation of the engine under GPU-like arithmetic (2-ulp errors on every MUFU result, FMA contraction)
-    // the biased cosine fails exactly the six Rope-v1 gradient cases the B200 failed, this one passes all 48
-    // (profiles/r01j_cpu_emulated_gpu_like_arithmetic_*.log); -DDSK_BIASED_COSINE restores the old behaviour.
-    float w = fmaf(t, t, 1.f);
-    float y = DSK_RSQRT(w);
-    float r = fmaf(-(w * y), 0.5f * y, 0.5f);   // 0.5 - (w y)(y / 2): the residual, one rounding
-    float c = fmaf(y, r, y), s = c * t;
-#else
-    float c = DSK_RSQRT(1.f + t * t), s = c * t;
+  float r = fmaf(-(w * y), 0.5f * y, 0.5f);   // 0.5 - (w y)(y / 2): the residual, one rounding
+  y = fmaf(y, r, y);
 #endif
-    float a, b;
-    a = b0p; b = b0q; b0p = c * a - s * b; b0q = s * a + c * b;
-    a = b1p; b = b1q; b1p = c * a - s * b; b1q = s * a + c * b;
-    a = b2p; b = b2q; b2p = c * a - s * b; b2q = s * a + c * b;
-    a = v0p; b = v0q; v0p = c * a - s * b; v0q = s * a + c * b;
-    a = v1p; b = v1q; v1p = c * a - s * b; v1q = s * a + c * b;
-    a = v2p; b = v2q; v2p = c * a - s * b; v2q = s * a + c * b;
-  }
+  return y;
 }
 
-DSK_DEV void swapneg(bool doit, float& n2p, float& n2q, float& b0p, float& b1p, float& b2p, float& b0q, float& b1q,
-                     float& b2q, float& v0p, float& v1p, float& v2p, float& v0q, float& v1q, float& v2q) {
+// One Hestenes rotation of columns p, q of B (and V).  A column lives in three packed pairs (b0, b1), (b2, v0), (v1, v2),
+// so that the six 2x2 rotations are 12 packed instructions (FMUL2 / FFMA2).
+// Rotation angle: tan(2 theta) = 2 ga / (be - al), |theta| <= pi/4, from two reciprocal square roots and no division:
+//   h = sqrt(d^2 + (2 ga)^2),  cos^2(theta) = (1 + |d| / h) / 2,  sin(theta) = sign(d) (2 ga / h) / (2 cos(theta))
+// (the same angle as t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = d / (2 ga), c = 1 / sqrt(1 + t^2), s = c t of the
+// textbook form: tan(2 theta) = 2 t / (1 - t^2) = 1 / zeta).  c^2 + s^2 = 1 needs (d^2 + 4 ga^2) / h^2 = 1 and
+// cos^2 / cos^2 = 1 without bias: both reciprocal square roots are the unbiased ones.
+struct SvdCol {
+  float2 a, b, c;   // (b0, b1), (b2, v0), (v1, v2)
+};
+DSK_DEV float col_dot(const SvdCol& p, const SvdCol& q) {
+  float2 t = mul2(p.a, q.a);
+  return fmaf(p.b.x, q.b.x, t.x + t.y);
+}
+DSK_DEV void jacobi_pair(SvdCol& p, SvdCol& q) {
+  float al = col_dot(p, p), be = col_dot(q, q), ga = col_dot(p, q);
+  if (ga != 0.f) {
+    float g2 = ga + ga, d = be - al;
+    float rh = rsqrt_unbiased(fmaf(d, d, g2 * g2));
+    float u = fmaf(0.5f * fabsf(d), rh, 0.5f);     // cos^2(theta), in [0.5, 1]
+    float y = rsqrt_unbiased(u);
+    float c = u * y;
+    float s = (copysignf(0.5f, d) * y) * (g2 * rh);
+    float2 c2 = bc2(c), s2 = bc2(s), n2 = bc2(-s);
+    float2 t;
+    t = fma2(c2, p.a, mul2(n2, q.a)); q.a = fma2(s2, p.a, mul2(c2, q.a)); p.a = t;
+    t = fma2(c2, p.b, mul2(n2, q.b)); q.b = fma2(s2, p.b, mul2(c2, q.b)); p.b = t;
+    t = fma2(c2, p.c, mul2(n2, q.c)); q.c = fma2(s2, p.c, mul2(c2, q.c)); p.c = t;
+  }
+}
+// order two columns by decreasing norm; the swap (p, q) <- (q, -p) keeps V a proper rotation
+DSK_DEV void swapneg(bool doit, float& n2p, float& n2q, SvdCol& p, SvdCol& q) {
   if (doit) {
-    float t;
-    t = b0p; b0p = b0q; b0q = -t;
-    t = b1p; b1p = b1q; b1q = -t;
-    t = b2p; b2p = b2q; b2q = -t;
-    t = v0p; v0p = v0q; v0q = -t;
-    t = v1p; v1p = v1q; v1q = -t;
-    t = v2p; v2p = v2q; v2q = -t;
-    t = n2p; n2p = n2q; n2q = t;
+    SvdCol t = p;
+    p = q;
+    q.a = f2(-t.a.x, -t.a.y);
+    q.b = f2(-t.b.x, -t.b.y);
+    q.c = f2(-t.c.x, -t.c.y);
+    float n = n2p;
+    n2p = n2q;
+    n2q = n;
   }
 }
 
 // A = U diag(sig) V^T
 DSK_DEV void svd3(const M3& A, M3& U, float3& sig, M3& V) {
-  float b00 = A.m[0], b01 = A.m[1], b02 = A.m[2];
-  float b10 = A.m[3], b11 = A.m[4], b12 = A.m[5];
-  float b20 = A.m[6], b21 = A.m[7], b22 = A.m[8];
-  float v00 = 1.f, v01 = 0.f, v02 = 0.f, v10 = 0.f, v11 = 1.f, v12 = 0.f, v20 = 0.f, v21 = 0.f, v22 = 1.f;
+  SvdCol c0 = {f2(A.m[0], A.m[3]), f2(A.m[6], 1.f), f2(0.f, 0.f)};
+  SvdCol c1 = {f2(A.m[1], A.m[4]), f2(A.m[7], 0.f), f2(1.f, 0.f)};
+  SvdCol c2 = {f2(A.m[2], A.m[5]), f2(A.m[8], 0.f), f2(0.f, 1.f)};
 #pragma unroll
   for (int sw = 0; sw < 4; sw++) {
-    jacobi_pair(b00, b10, b20, b01, b11, b21, v00, v10, v20, v01, v11, v21);  // (0,1)
-    jacobi_pair(b00, b10, b20, b02, b12, b22, v00, v10, v20, v02, v12, v22);  // (0,2)
-    jacobi_pair(b01, b11, b21, b02, b12, b22, v01, v11, v21, v02, v12, v22);  // (1,2)
+    jacobi_pair(c0, c1);  // (0,1)
+    jacobi_pair(c0, c2);  // (0,2)
+    jacobi_pair(c1, c2);  // (1,2)
   }
-  float n0 = b00 * b00 + b10 * b10 + b20 * b20;
-  float n1 = b01 * b01 + b11 * b11 + b21 * b21;
-  float n2 = b02 * b02 + b12 * b12 + b22 * b22;
-  swapneg(n0 < n1, n0, n1, b00, b10, b20, b01, b11, b21, v00, v10, v20, v01, v11, v21);
-  swapneg(n0 < n2, n0, n2, b00, b10, b20, b02, b12, b22, v00, v10, v20, v02, v12, v22);
-  swapneg(n1 < n2, n1, n2, b01, b11, b21, b02, b12, b22, v01, v11, v21, v02, v12, v22);
-  float s0 = sqrtf(n0), s1 = sqrtf(n1);
+  float n0 = col_dot(c0, c0), n1 = col_dot(c1, c1), n2 = col_dot(c2, c2);
+  swapneg(n0 < n1, n0, n1, c0, c1);
+  swapneg(n0 < n2, n0, n2, c0, c2);
+  swapneg(n1 < n2, n1, n2, c1, c2);
+  float b00 = c0.a.x, b10 = c0.a.y, b20 = c0.b.x, b01 = c1.a.x, b11 = c1.a.y, b21 = c1.b.x;
+  float b02 = c2.a.x, b12 = c2.a.y, b22 = c2.b.x;
+  // sigma_i = |b_i| and u_i = b_i / |b_i| from one (unbiased) reciprocal square root each
+  float r0 = n0 > 0.f ? rsqrt_unbiased(n0) : 0.f, r1 = n1 > 1e-36f ? rsqrt_unbiased(n1) : 0.f;
+  float s0 = n0 * r0, s1 = fminf(n1 * r1, s0);   // n0 >= n1 after the sort; keep the order through the two roundings
   float3 u0, u1;
-  if (s0 > 0.f) u0 = f3(b00 / s0, b10 / s0, b20 / s0);
+  if (n0 > 0.f) u0 = f3(b00 * r0, b10 * r0, b20 * r0);
   else u0 = f3(1.f, 0.f, 0.f);
-  if (s1 > 1e-18f) {
-    u1 = f3(b01 / s1, b11 / s1, b21 / s1);
+  if (n1 > 1e-36f) {
+    u1 = f3(b01 * r1, b11 * r1, b21 * r1);
   } else {  // rank <= 1: any unit vector orthogonal to u0
     float ax = fabsf(u0.x), ay = fabsf(u0.y), az = fabsf(u0.z);
     int k = ax < ay ? (ax < az ? 0 : 2) : (ay < az ? 1 : 2);
@@ -96,9 +107,9 @@ DSK_DEV void svd3(const M3& A, M3& U, float3& sig, M3& V) {
   U.m[0] = u0.x; U.m[1] = u1.x; U.m[2] = u2.x;
   U.m[3] = u0.y; U.m[4] = u1.y; U.m[5] = u2.y;
   U.m[6] = u0.z; U.m[7] = u1.z; U.m[8] = u2.z;
-  V.m[0] = v00; V.m[1] = v01; V.m[2] = v02;
-  V.m[3] = v10; V.m[4] = v11; V.m[5] = v12;
-  V.m[6] = v20; V.m[7] = v21; V.m[8] = v22;
+  V.m[0] = c0.b.y; V.m[1] = c1.b.y; V.m[2] = c2.b.y;
+  V.m[3] = c0.c.x; V.m[4] = c1.c.x; V.m[5] = c2.c.x;
+  V.m[6] = c0.c.y; V.m[7] = c1.c.y; V.m[8] = c2.c.y;
 }
 
 DSK_DEV float clamp_gap(float a) {  // mpm_simulator.py:184-192

@@ -7,6 +7,10 @@ struct float3 {
   float x, y, z;
 };
 static inline float3 make_float3(float x, float y, float z) { return float3{x, y, z}; }
+struct float2 {
+  float x, y;
+};
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }

@@ -27,7 +27,12 @@ def _inputs(workload, B, H):
     import bench
     spec = bench.workload_spec(workload)
     spec['horizon'] = H
-    return bench.make_inputs(spec, 0, B)
+    scene, cfg, xs, targets, actions = bench.make_inputs(spec, 0, B)
+    if workload == 'cutrearrange':
+        # the bench's knife-push initial guess (solve_utils.py:166-168) reaches the dough after ~10 env steps; these
+        # properties are checked on 2-4 steps, so drive the tools hard from the start instead
+        actions = np.random.RandomState(100).uniform(-1, 1, actions.shape).astype(np.float32)
+    return scene, cfg, xs, targets, actions
 
 
 def _engine(scene, xs, H, **kw):

@@ -1,5 +1,9 @@
 """The warp-aggregated scatters of the particle kernels on an emulated warp (no GPU).
 
+Round 2 added the transposed shared-memory scatters (`warp_scatter27_ts`, `warp_scatter27_ts_affine`, `warp_scatter9_ts`: every
+lane stores its contributions to a [node][lane] tile, lanes 0..26 add up the row segment of every run of equal cell keys);
+they run here on the same patterns (modes 127 / 227 / 109).
+
 `warp_scatter27` / `warp_scatter9` (diffskill_b200/csrc/kernels_common.cuh) choose between three regimes per warp from
 the pattern of cell keys: a recursive-halving butterfly per group of lanes that share a cell, one segmented shuffle-down
 reduction over all runs when there are more than two such groups, and per-lane reductions for strays.  `tests/host_check`
@@ -89,7 +93,7 @@ def _patterns(rng):
     yield 'three warps, random runs of random cells', [cells[i] for i in np.sort(rng.randint(0, 6, 96))], rng.rand(96) > 0.1
 
 
-@pytest.mark.parametrize('mode', [27, 9])
+@pytest.mark.parametrize('mode', [27, 9, 127, 227, 109])
 def test_warp_scatter_equals_per_particle_accumulation(mode, lib):
     rng = np.random.RandomState(3)
     FP, IP = C.POINTER(C.c_float), C.POINTER(C.c_int)
