@@ -143,7 +143,8 @@ struct dsk_engine {
   int big_block = 128;
   int minb_g2p2g = 4, minb_g2p_adj = 4, minb_p2g_adj = 4;
   bool flat_grid = false;   // many active tiles: throughput layout of the grid kernels
-  bool ts = true;           // transposed shared-memory scatter (warp_scatter27_ts) instead of the shuffle butterfly
+  bool ts = true;           // batched engines: transposed shared-memory scatter (warp_scatter27_ts_affine) instead of the shuffle butterfly
+  bool ts_pl = false;       // ... in the plane-split kernels of single scenes (slower there: r02b liftspread 46.3 vs 42.3 ms)
   cudaStream_t cap_side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<cudaEvent_t> ev_restored, ev_main;   // per backward position, used while capturing the pipelined adjoint
@@ -381,6 +382,7 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
   if (const char* v = getenv("DSK_MINB_P2G_ADJ")) e->minb_p2g_adj = atoi(v);
   e->flat_grid = e->big;
   if (const char* v = getenv("DSK_TS")) e->ts = atoi(v) != 0;
+  if (const char* v = getenv("DSK_TS_PL")) e->ts_pl = atoi(v) != 0;
   if (const char* v = getenv("DSK_FLAT_GRID")) e->flat_grid = atoi(v) != 0;
   e->tool_floats = (size_t)e->B * std::max(1, e->K) * 8;
   int rc = [&]() -> int {
@@ -608,8 +610,8 @@ static dim3 grid_block(dsk_engine* e) { return dim3(GRID_NODES, std::min(e->n_fr
 
 // ---- launchers of the particle kernels: pick the kernel family (latency: plane-split, 3 threads per particle; throughput:
 // one thread per particle), the register cap and the scatter variant (TS: transposed shared-memory scatter) -------------
-static size_t ts_smem(dsk_engine* e, int threads) { return e->ts ? (size_t)(threads / 32) * TS_WARP_FLOAT4 * sizeof(float4) : 0; }
-static size_t ts9_smem(dsk_engine* e) { return e->ts ? (size_t)(PL_PARTICLES * 3 / 32) * TS9_WARP_FLOAT4 * sizeof(float4) : 0; }
+static size_t ts_smem(dsk_engine* e, int threads) { return e->ts ? (size_t)(threads / 32) * TS9_WARP_FLOAT4 * sizeof(float4) : 0; }
+static size_t ts9_smem(dsk_engine* e) { return e->ts_pl ? (size_t)(PL_PARTICLES * 3 / 32) * TS9_WARP_FLOAT4 * sizeof(float4) : 0; }
 static int launch_p2g(dsk_engine* e, bool write_f, const float* fin, float* fout, const float* mat, float4* G, TileTrack tt,
                       int q, const int* run_if, float* svd) {
   const SimConst& k = e->k;
@@ -629,21 +631,22 @@ static int launch_p2g(dsk_engine* e, bool write_f, const float* fin, float* fout
   LAUNCH_CHECK();
   return 0;
 }
+static int minb_class(int minb) { return minb >= 7 ? 8 : (minb >= 5 ? 6 : 4); }
 static int launch_g2p2g(dsk_engine* e, const float* fprev, float* fcur, float* fnext, const float* mat, const float4* Gprev,
                         float4* Gnext, TileTrack tt, int qnext, float* svd) {
   const SimConst& k = e->k;
   if (!e->big) {
     const int nb = cdiv(k.stride, PL_PARTICLES);
-    if (e->ts) KL(KID_G2P2G, k_g2p2g_pl<true><<<nb, dim3(PL_PARTICLES, 3), ts9_smem(e), e->qs>>>(k, fprev, fcur, fnext, mat, e->npart, Gprev, Gnext, tt, e->d_args, qnext, svd));
+    if (e->ts_pl) KL(KID_G2P2G, k_g2p2g_pl<true><<<nb, dim3(PL_PARTICLES, 3), ts9_smem(e), e->qs>>>(k, fprev, fcur, fnext, mat, e->npart, Gprev, Gnext, tt, e->d_args, qnext, svd));
     else KL(KID_G2P2G, k_g2p2g_pl<false><<<nb, dim3(PL_PARTICLES, 3), 0, e->qs>>>(k, fprev, fcur, fnext, mat, e->npart, Gprev, Gnext, tt, e->d_args, qnext, svd));
   } else {
     const int pb = e->big_block, nb = cdiv(k.stride, pb);
     const size_t sm = ts_smem(e, pb);
-    switch ((e->minb_g2p2g >= 4 ? 2 : 0) + (e->ts ? 1 : 0)) {
-      case 3: KL(KID_G2P2G, k_g2p2g<4, true><<<nb, pb, sm, e->qs>>>(k, fprev, fcur, fnext, mat, e->npart, Gprev, Gnext, tt, e->d_args, qnext, svd)); break;
-      case 2: KL(KID_G2P2G, k_g2p2g<4, false><<<nb, pb, 0, e->qs>>>(k, fprev, fcur, fnext, mat, e->npart, Gprev, Gnext, tt, e->d_args, qnext, svd)); break;
-      case 1: KL(KID_G2P2G, k_g2p2g<3, true><<<nb, pb, sm, e->qs>>>(k, fprev, fcur, fnext, mat, e->npart, Gprev, Gnext, tt, e->d_args, qnext, svd)); break;
-      default: KL(KID_G2P2G, k_g2p2g<3, false><<<nb, pb, 0, e->qs>>>(k, fprev, fcur, fnext, mat, e->npart, Gprev, Gnext, tt, e->d_args, qnext, svd)); break;
+    if (!e->ts) KL(KID_G2P2G, k_g2p2g<4, false><<<nb, pb, 0, e->qs>>>(k, fprev, fcur, fnext, mat, e->npart, Gprev, Gnext, tt, e->d_args, qnext, svd));
+    else switch (minb_class(e->minb_g2p2g)) {
+      case 8: KL(KID_G2P2G, k_g2p2g<8, true><<<nb, pb, sm, e->qs>>>(k, fprev, fcur, fnext, mat, e->npart, Gprev, Gnext, tt, e->d_args, qnext, svd)); break;
+      case 6: KL(KID_G2P2G, k_g2p2g<6, true><<<nb, pb, sm, e->qs>>>(k, fprev, fcur, fnext, mat, e->npart, Gprev, Gnext, tt, e->d_args, qnext, svd)); break;
+      default: KL(KID_G2P2G, k_g2p2g<4, true><<<nb, pb, sm, e->qs>>>(k, fprev, fcur, fnext, mat, e->npart, Gprev, Gnext, tt, e->d_args, qnext, svd)); break;
     }
   }
   LAUNCH_CHECK();
@@ -654,16 +657,16 @@ static int launch_g2p_adj(dsk_engine* e, const float* fin, const float* fnext, c
   const SimConst& k = e->k;
   if (!e->big) {
     const int nb = cdiv(k.stride, PL_PARTICLES);
-    if (e->ts) KL(KID_G2P_ADJ, k_g2p_adj_pl<true><<<nb, dim3(PL_PARTICLES, 3), ts9_smem(e), e->qs>>>(k, fin, fnext, ain, aout, e->npart, Gv, Ga));
+    if (e->ts_pl) KL(KID_G2P_ADJ, k_g2p_adj_pl<true><<<nb, dim3(PL_PARTICLES, 3), ts9_smem(e), e->qs>>>(k, fin, fnext, ain, aout, e->npart, Gv, Ga));
     else KL(KID_G2P_ADJ, k_g2p_adj_pl<false><<<nb, dim3(PL_PARTICLES, 3), 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, Gv, Ga));
   } else {
     const int pb = e->big_block, nb = cdiv(k.stride, pb);
     const size_t sm = ts_smem(e, pb);
-    switch ((e->minb_g2p_adj >= 4 ? 2 : 0) + (e->ts ? 1 : 0)) {
-      case 3: KL(KID_G2P_ADJ, k_g2p_adj<4, true><<<nb, pb, sm, e->qs>>>(k, fin, fnext, ain, aout, e->npart, Gv, Ga)); break;
-      case 2: KL(KID_G2P_ADJ, k_g2p_adj<4, false><<<nb, pb, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, Gv, Ga)); break;
-      case 1: KL(KID_G2P_ADJ, k_g2p_adj<3, true><<<nb, pb, sm, e->qs>>>(k, fin, fnext, ain, aout, e->npart, Gv, Ga)); break;
-      default: KL(KID_G2P_ADJ, k_g2p_adj<3, false><<<nb, pb, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, Gv, Ga)); break;
+    if (!e->ts) KL(KID_G2P_ADJ, k_g2p_adj<4, false><<<nb, pb, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, Gv, Ga));
+    else switch (minb_class(e->minb_g2p_adj)) {
+      case 8: KL(KID_G2P_ADJ, k_g2p_adj<8, true><<<nb, pb, sm, e->qs>>>(k, fin, fnext, ain, aout, e->npart, Gv, Ga)); break;
+      case 6: KL(KID_G2P_ADJ, k_g2p_adj<6, true><<<nb, pb, sm, e->qs>>>(k, fin, fnext, ain, aout, e->npart, Gv, Ga)); break;
+      default: KL(KID_G2P_ADJ, k_g2p_adj<4, true><<<nb, pb, sm, e->qs>>>(k, fin, fnext, ain, aout, e->npart, Gv, Ga)); break;
     }
   }
   LAUNCH_CHECK();
@@ -676,22 +679,16 @@ static int launch_p2g_adj(dsk_engine* e, const float* fin, const float* ain, flo
     KL(KID_P2G_ADJ, k_p2g_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, e->qs>>>(k, fin, ain, aout, mat, e->npart, Ga, svd));
   } else {
     const int pb = e->big_block, nb = cdiv(k.stride, pb);
-    if (e->minb_p2g_adj >= 4) KL(KID_P2G_ADJ, k_p2g_adj<4><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, mat, e->npart, Ga, svd));
-    else KL(KID_P2G_ADJ, k_p2g_adj<3><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, mat, e->npart, Ga, svd));
+    switch (minb_class(e->minb_p2g_adj)) {
+      case 8: KL(KID_P2G_ADJ, k_p2g_adj<8><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, mat, e->npart, Ga, svd)); break;
+      case 6: KL(KID_P2G_ADJ, k_p2g_adj<6><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, mat, e->npart, Ga, svd)); break;
+      default: KL(KID_P2G_ADJ, k_p2g_adj<4><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, mat, e->npart, Ga, svd)); break;
+    }
   }
   LAUNCH_CHECK();
   return 0;
 }
-// shared-memory opt-in of the TS kernel instantiations (57 KB for a 128-thread CTA)
-static int ts_opt_in(dsk_engine* e) {
-  const int sm = (int)(4 * TS_WARP_FLOAT4 * sizeof(float4));
-  CK(cudaFuncSetAttribute(k_p2g<false, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  CK(cudaFuncSetAttribute(k_p2g<true, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  CK(cudaFuncSetAttribute(k_p2g<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  CK(cudaFuncSetAttribute(k_g2p2g<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  CK(cudaFuncSetAttribute(k_g2p2g<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  CK(cudaFuncSetAttribute(k_g2p_adj<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  CK(cudaFuncSetAttribute(k_g2p_adj<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+static int ts_opt_in(dsk_engine* e) {   // the plane-pass tile is 19 KB per 128-thread CTA: no shared-memory opt-in needed
   (void)e;
   return 0;
 }

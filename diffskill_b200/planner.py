@@ -20,10 +20,17 @@ class BatchedSolver:
     def l2_target_loss(self, targets, weight=None):
         """loss_fn: sum_t w * mean_p |x_t - target|^2 (deterministic stand-in for the EMD loss), engine-side."""
         w = 1.0 / self.H if weight is None else weight
+        box = [targets]
 
         def fn(eng, step):
-            eng.loss_add_l2(step, targets, w)
-        fn.steps = lambda eng, step0, n: eng.loss_add_l2_steps(step0, n, targets, w)   # multi-step fast path
+            eng.loss_add_l2(step, box[0], w)
+        fn.steps = lambda eng, step0, n: eng.loss_add_l2_steps(step0, n, box[0], w)   # multi-step fast path
+
+        def to_device(device):   # keep the targets resident next to the engine (no per-iteration staging copy)
+            import torch
+            if isinstance(box[0], np.ndarray):
+                box[0] = torch.as_tensor(np.ascontiguousarray(box[0], dtype=np.float32), device=device)
+        fn.to_device = to_device
         return fn
 
     def rollout_grad(self, actions, loss_fn):
@@ -45,37 +52,77 @@ class BatchedSolver:
                 eng.backward_step(s)
         return eng.loss_get(), eng.get_action_grads(0, self.H)
 
-    def solve(self, init_actions, loss_fn, max_iter=20, callback=None, distributed=False):
-        """Adam on the action sequences; keeps the best-so-far plan per env (solver.py:135-141)."""
-        a = np.array(init_actions, dtype=np.float32).reshape(self.H, self.eng.B, self.eng.A)
-        m, v = np.zeros_like(a), np.zeros_like(a)
-        best_loss = np.full(self.eng.B, np.inf, np.float32)
-        best_a = a.copy()
+    def rollout_grad_device(self, actions, loss_fn, loss_out, grad_out):
+        """rollout_grad with everything resident on the device: `actions` [H,B,A], `loss_out` [B], `grad_out` [H,B,A] are
+        torch tensors on the engine's GPU; no host synchronisation."""
+        eng = self.eng
+        eng.zero_grad()
+        eng.loss_reset()
+        eng.set_actions(0, actions)
+        eng.forward_steps(0, self.H)
+        if hasattr(loss_fn, 'steps'):
+            loss_fn.steps(eng, 1, self.H)
+        else:
+            for s in range(1, self.H + 1):
+                loss_fn(eng, s)
+        eng.backward_steps(self.H - 1, self.H)
+        eng.loss_get(loss_out)
+        eng.get_action_grads(0, self.H, grad_out)
+
+    def solve(self, init_actions, loss_fn, max_iter=20, callback=None, distributed=False, device=None):
+        """Adam on the action sequences; keeps the best-so-far plan per env (solver.py:135-141).  The optimiser state, the
+        clamp / mask and the best-so-far bookkeeping live in torch tensors on the engine's device (plb/optimizer/solver.py
+        keeps them in torch too); one iteration makes no device->host copy unless a callback asks for the loss.  The NaN
+        guard ("MEET NAN", plb/cut/solve_func.py:124-129) freezes the update on the device and is polled every 10th
+        iteration."""
+        import torch
+        H, B, A = self.H, self.eng.B, self.eng.A
+        if device is None:
+            device = 'cuda' if torch.cuda.is_available() else 'cpu'
+        on_gpu = str(device).startswith('cuda')
+        if on_gpu and hasattr(loss_fn, 'to_device'):
+            loss_fn.to_device(device)
+        a = torch.as_tensor(np.array(init_actions, dtype=np.float32).reshape(H, B, A), device=device).contiguous()
+        m, v = torch.zeros_like(a), torch.zeros_like(a)
+        mask = None if self.mask is None else torch.as_tensor(self.mask, device=device)
+        best_loss = torch.full((B,), float('inf'), device=device)
+        best_a = a.clone()
+        loss, g = torch.zeros(B, device=device), torch.zeros((H, B, A), device=device)
         history = []
+        alive = torch.ones((), dtype=torch.bool, device=device)
         for it in range(1, max_iter + 1):
-            loss, g = self.rollout_grad(a, loss_fn)
+            if on_gpu:
+                self.rollout_grad_device(a, loss_fn, loss, g)
+            else:   # host engine (the CPU emulation of the test-suite): same arithmetic on CPU tensors
+                l_, g_ = self.rollout_grad(a.numpy(), loss_fn)
+                loss, g = torch.from_numpy(np.asarray(l_)), torch.from_numpy(np.asarray(g_))
             if distributed:
-                import torch
-                gl, gg = gather_planner_inputs(torch.from_numpy(loss), torch.from_numpy(g))
-                history.append(float(gl.mean()))
+                gl, gg = gather_planner_inputs(loss, g)
+                history.append(gl.mean())
             else:
-                history.append(float(loss.mean()))
-            if not np.isfinite(loss).all():          # "MEET NAN" (plb/cut/solve_func.py:124-129)
-                break
-            better = loss < best_loss
-            best_loss = np.where(better, loss, best_loss)
-            best_a[:, better] = a[:, better]
-            if self.mask is not None:
-                g = g * self.mask
-            m = self.b1 * m + (1 - self.b1) * g
-            v = self.b2 * v + (1 - self.b2) * g * g
-            a = a - self.lr * (m / (1 - self.b1 ** it)) / (np.sqrt(v / (1 - self.b2 ** it)) + self.eps)
-            a = np.clip(a, -1, 1)
-            if self.mask is not None:
-                a = a * self.mask
+                history.append(loss.mean())
+            alive = alive & torch.isfinite(loss).all()
+            better = (loss < best_loss) & alive
+            best_loss = torch.where(better, loss, best_loss)
+            best_a = torch.where(better.view(1, B, 1), a, best_a)
+            gm = g if mask is None else g * mask
+            m = self.b1 * m + (1 - self.b1) * gm
+            v = self.b2 * v + (1 - self.b2) * gm * gm
+            step = self.lr * (m / (1 - self.b1 ** it)) / (torch.sqrt(v / (1 - self.b2 ** it)) + self.eps)
+            a_new = torch.clamp(a - step, -1, 1)
+            if mask is not None:
+                a_new = a_new * mask
+            a = torch.where(alive, a_new, a).contiguous()
             if callback:
-                callback(it, loss)
-        return dict(best_action=best_a, best_loss=best_loss, history=history, last_action=a)
+                callback(it, loss.detach().cpu().numpy())
+            if it % 10 == 0 and not bool(alive):
+                break
+        hist = [float(h) for h in torch.stack(history).cpu()] if history else []
+        if not bool(alive):   # history up to and including the first non-finite loss, as the reference's early break
+            bad = next((i for i, h in enumerate(hist) if not np.isfinite(h)), len(hist) - 1)
+            hist = hist[:bad + 1]
+        return dict(best_action=best_a.cpu().numpy(), best_loss=best_loss.cpu().numpy(), history=hist,
+                    last_action=a.cpu().numpy())
 
 
 FUNCS = {}          # one GradModel per env, as plb/optimizer/solver.py:10,19-21

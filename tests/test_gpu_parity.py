@@ -3,10 +3,12 @@
 Tolerances are the north-star's: integer work bit-exact; fp32 state within 1e-5 (normwise
 relative) per substep; action gradients within 1e-3.
 """
+import os
+
 import numpy as np
 import pytest
 
-from gpu_common import ENVS, actions_for, f32, make_pair, sync_oracle_to_engine, within_noise_floor
+from gpu_common import ENVS, actions_for, f32, make_pair, record_parity, sync_oracle_to_engine, within_noise_floor
 from helpers import relerr
 
 pytestmark = pytest.mark.gpu
@@ -113,6 +115,7 @@ def test_substep_forward_parity(name, sort):
     print(name, 'sort' if sort else 'nosort', 'vs_f32', fmt(worst), 'vs_f64', fmt(worst64), 'f32_vs_f64', fmt(floor))
     for k_ in worst:
         tol = TOL_STATE_C if k_ in ('C', 'grid_v') else TOL_STATE
+        record_parity('substep_forward', name, k_, worst[k_], worst64[k_], floor[k_], tol, config='sort' if sort else 'nosort')
         assert worst[k_] < tol or within_noise_floor(worst64[k_], floor[k_], tol), (k_, worst[k_], worst64[k_], floor[k_])
 
 
@@ -184,6 +187,7 @@ def test_substep_backward_parity(name):
     fmt = lambda d: {k_: '%.1e' % e_ for k_, e_ in d.items()}
     print(name, 'vs_f32', fmt(worst), 'vs_f64', fmt(worst64), 'f32_vs_f64', fmt(floor))
     for k_ in worst:
+        record_parity('substep_backward', name, k_, worst[k_], worst64[k_], floor[k_], TOL_GRAD_SUBSTEP)
         assert worst[k_] < TOL_GRAD_SUBSTEP or within_noise_floor(worst64[k_], floor[k_], TOL_GRAD_SUBSTEP), \
             (k_, worst[k_], worst64[k_], floor[k_])
 
@@ -277,7 +281,10 @@ def _multi_step_action_gradient(name, slots, tape_mib):
     b = o.get_frame_grad(0)
     ex = relerr(a[0], b[0])
     print(name, 'slots', slots, 'action grad err %.2e' % e, 'x.grad[0] err %.2e' % ex)
+    cfg_ = f'H=3 slots={slots} tape_mib={tape_mib}' + (' batched-layout' if os.environ.get('DSK_FORCE_BIG') == '1' else '')
     if e < TOL_ACTION_GRAD and ex < 5 * TOL_ACTION_GRAD:
+        record_parity('multi_step_gradient', name, 'action_grad', e, tol=TOL_ACTION_GRAD, config=cfg_)
+        record_parity('multi_step_gradient', name, 'x_grad0', ex, tol=5 * TOL_ACTION_GRAD, config=cfg_)
         return
     # Out of the north-star tolerance against the fp32 oracle: acceptable only where the reference's own fp32 formulation
     # is that far from its fp64 twin on this scene (Torus-v1: fp32 oracle 1.5e-3 from fp64, CUDA 7e-5 from fp64).
@@ -292,6 +299,8 @@ def _multi_step_action_gradient(name, slots, tape_mib):
     e64, f64_ = relerr(ga, oga64), relerr(oga, oga64)
     ex64, fx64 = relerr(a[0], b64[0]), relerr(b[0], b64[0])
     print(name, 'vs fp64 twin: action grad %.2e (fp32 oracle %.2e), x.grad[0] %.2e (fp32 oracle %.2e)' % (e64, f64_, ex64, fx64))
+    record_parity('multi_step_gradient', name, 'action_grad', e, e64, f64_, TOL_ACTION_GRAD, config=cfg_)
+    record_parity('multi_step_gradient', name, 'x_grad0', ex, ex64, fx64, 5 * TOL_ACTION_GRAD, config=cfg_)
     assert within_noise_floor(e64, f64_, TOL_ACTION_GRAD), (e, e64, f64_)
     assert within_noise_floor(ex64, fx64, 5 * TOL_ACTION_GRAD), (ex, ex64, fx64)
 
