@@ -610,7 +610,7 @@ static dim3 grid_block(dsk_engine* e) { return dim3(GRID_NODES, std::min(e->n_fr
 
 // ---- launchers of the particle kernels: pick the kernel family (latency: plane-split, 3 threads per particle; throughput:
 // one thread per particle), the register cap and the scatter variant (TS: transposed shared-memory scatter) -------------
-static size_t ts_smem(dsk_engine* e, int threads) { return e->ts ? (size_t)(threads / 32) * TS9_WARP_FLOAT4 * sizeof(float4) : 0; }
+static size_t ts_smem(dsk_engine* e, int threads) { return e->ts ? (size_t)(threads / 32) * TS_WARP_FLOAT4 * sizeof(float4) : 0; }
 static size_t ts9_smem(dsk_engine* e) { return e->ts_pl ? (size_t)(PL_PARTICLES * 3 / 32) * TS9_WARP_FLOAT4 * sizeof(float4) : 0; }
 static int launch_p2g(dsk_engine* e, bool write_f, const float* fin, float* fout, const float* mat, float4* G, TileTrack tt,
                       int q, const int* run_if, float* svd) {
@@ -631,7 +631,7 @@ static int launch_p2g(dsk_engine* e, bool write_f, const float* fin, float* fout
   LAUNCH_CHECK();
   return 0;
 }
-static int minb_class(int minb) { return minb >= 7 ? 8 : (minb >= 5 ? 6 : 4); }
+static int minb_class(int minb) { return minb >= 5 ? 6 : 4; }
 static int launch_g2p2g(dsk_engine* e, const float* fprev, float* fcur, float* fnext, const float* mat, const float4* Gprev,
                         float4* Gnext, TileTrack tt, int qnext, float* svd) {
   const SimConst& k = e->k;
@@ -644,7 +644,6 @@ static int launch_g2p2g(dsk_engine* e, const float* fprev, float* fcur, float* f
     const size_t sm = ts_smem(e, pb);
     if (!e->ts) KL(KID_G2P2G, k_g2p2g<4, false><<<nb, pb, 0, e->qs>>>(k, fprev, fcur, fnext, mat, e->npart, Gprev, Gnext, tt, e->d_args, qnext, svd));
     else switch (minb_class(e->minb_g2p2g)) {
-      case 8: KL(KID_G2P2G, k_g2p2g<8, true><<<nb, pb, sm, e->qs>>>(k, fprev, fcur, fnext, mat, e->npart, Gprev, Gnext, tt, e->d_args, qnext, svd)); break;
       case 6: KL(KID_G2P2G, k_g2p2g<6, true><<<nb, pb, sm, e->qs>>>(k, fprev, fcur, fnext, mat, e->npart, Gprev, Gnext, tt, e->d_args, qnext, svd)); break;
       default: KL(KID_G2P2G, k_g2p2g<4, true><<<nb, pb, sm, e->qs>>>(k, fprev, fcur, fnext, mat, e->npart, Gprev, Gnext, tt, e->d_args, qnext, svd)); break;
     }
@@ -664,7 +663,6 @@ static int launch_g2p_adj(dsk_engine* e, const float* fin, const float* fnext, c
     const size_t sm = ts_smem(e, pb);
     if (!e->ts) KL(KID_G2P_ADJ, k_g2p_adj<4, false><<<nb, pb, 0, e->qs>>>(k, fin, fnext, ain, aout, e->npart, Gv, Ga));
     else switch (minb_class(e->minb_g2p_adj)) {
-      case 8: KL(KID_G2P_ADJ, k_g2p_adj<8, true><<<nb, pb, sm, e->qs>>>(k, fin, fnext, ain, aout, e->npart, Gv, Ga)); break;
       case 6: KL(KID_G2P_ADJ, k_g2p_adj<6, true><<<nb, pb, sm, e->qs>>>(k, fin, fnext, ain, aout, e->npart, Gv, Ga)); break;
       default: KL(KID_G2P_ADJ, k_g2p_adj<4, true><<<nb, pb, sm, e->qs>>>(k, fin, fnext, ain, aout, e->npart, Gv, Ga)); break;
     }
@@ -680,7 +678,6 @@ static int launch_p2g_adj(dsk_engine* e, const float* fin, const float* ain, flo
   } else {
     const int pb = e->big_block, nb = cdiv(k.stride, pb);
     switch (minb_class(e->minb_p2g_adj)) {
-      case 8: KL(KID_P2G_ADJ, k_p2g_adj<8><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, mat, e->npart, Ga, svd)); break;
       case 6: KL(KID_P2G_ADJ, k_p2g_adj<6><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, mat, e->npart, Ga, svd)); break;
       default: KL(KID_P2G_ADJ, k_p2g_adj<4><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, mat, e->npart, Ga, svd)); break;
     }
@@ -688,7 +685,16 @@ static int launch_p2g_adj(dsk_engine* e, const float* fin, const float* ain, flo
   LAUNCH_CHECK();
   return 0;
 }
-static int ts_opt_in(dsk_engine* e) {   // the plane-pass tile is 19 KB per 128-thread CTA: no shared-memory opt-in needed
+// shared-memory opt-in of the TS kernel instantiations (57 KB for a 128-thread CTA)
+static int ts_opt_in(dsk_engine* e) {
+  const int sm = (int)(4 * TS_WARP_FLOAT4 * sizeof(float4));
+  CK(cudaFuncSetAttribute(k_p2g<false, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_p2g<true, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_p2g<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_g2p2g<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_g2p2g<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_g2p_adj<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  CK(cudaFuncSetAttribute(k_g2p_adj<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   (void)e;
   return 0;
 }

@@ -389,73 +389,56 @@ DSK_DEV void warp_scatter27_ts(const SimConst& k, bool active, const Stencil& s,
 }
 // Both scatters of a substep have AFFINE contributions: node (i, j, l) receives w_ijl * (A0 + i AX + j AY + l AZ) with
 // float4 coefficients (p2g: A0 = (p_mass v - dx affine fx, p_mass), AX.. = dx * columns of affine; g2p.grad: A0 = (b0, 0),
-// AX.. = (c_C * columns of gC, 0)).  The values are built incrementally, (x, y) and (z, w) as packed pairs: ~150
-// instructions instead of 27 x 15.  The 27 nodes go through the shared-memory tile in three passes of one x-plane (9
-// nodes) each, so the tile is 9 x 33 float4 = 4 752 bytes per warp and does not limit the occupancy (a 27-row tile is
-// 14 KB per warp: 3 CTAs of 128 threads per SM); in the reduction lanes (part, node) = (lane / 9, lane % 9) add every
-// third element of the run's row segment and two shuffle-downs combine the three parts.
+// AX.. = (c_C * columns of gC, 0)).  The 27 values are built incrementally, (x, y) and (z, w) as packed pairs: ~150
+// instructions instead of 27 x 15.  (A three-pass variant with a 9-row tile -- 4.75 KB per warp, no occupancy limit from shared
+// memory -- was measured in r02c: the run loop executed three times costs far more than the occupancy returns, 1 M-particle
+// k_g2p2g 165 -> 257 us at 8 CTAs/SM; profiles/r02c_*.json.)
 DSK_DEV void warp_scatter27_ts_affine(const SimConst& k, bool active, const Stencil& s, float4* __restrict__ Ge,
                                       const TileTrack& tt, bool mark, int env, int epoch, float4* wbuf, float4 A0, float3 AX,
                                       float3 AY, float3 AZ) {
   const int lane = threadIdx.x & 31;
   unsigned act;
-  const unsigned heads = ts_run_heads(k, active, s, tt, mark, env, epoch, act);
-  if (!heads) return;
-  const float2 axl = f2(AX.x, AX.y), axh = f2(AX.z, 0.f), ayl = f2(AY.x, AY.y), ayh = f2(AY.z, 0.f);
-  const float2 azl = f2(AZ.x, AZ.y), azh = f2(AZ.z, 0.f);
-  float2 lo_i = f2(A0.x, A0.y), hi_i = f2(A0.z, A0.w);
-  float4* col = wbuf + lane;
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int part = lane / 9, q = lane - part * 9;
-  const float4* row = wbuf + (lane < 27 ? q : 0) * TS_ROW;
-  const int qj = q / 3, ql = q - qj * 3;
+  unsigned todo = ts_run_heads(k, active, s, tt, mark, env, epoch, act);
+  if (!todo) return;
+  {
+    const float2 axl = f2(AX.x, AX.y), axh = f2(AX.z, 0.f), ayl = f2(AY.x, AY.y), ayh = f2(AY.z, 0.f);
+    const float2 azl = f2(AZ.x, AZ.y), azh = f2(AZ.z, 0.f);
+    float2 lo_i = f2(A0.x, A0.y), hi_i = f2(A0.z, A0.w);
+    float4* col = wbuf + lane;
 #pragma unroll
-  for (int i = 0; i < 3; i++) {
-    float2 lo_ij = lo_i, hi_ij = hi_i;
+    for (int i = 0; i < 3; i++) {
+      float2 lo_ij = lo_i, hi_ij = hi_i;
 #pragma unroll
-    for (int j = 0; j < 3; j++) {
-      const float wxy = s.wx[i] * s.wy[j];
-      float2 lo = lo_ij, hi = hi_ij;
+      for (int j = 0; j < 3; j++) {
+        const float wxy = s.wx[i] * s.wy[j];
+        float2 lo = lo_ij, hi = hi_ij;
 #pragma unroll
-      for (int l = 0; l < 3; l++) {
-        const float2 w2 = bc2(wxy * s.wz[l]);
-        float2 vlo = mul2(w2, lo), vhi = mul2(w2, hi);
-        col[(j * 3 + l) * TS_ROW] = make_float4(vlo.x, vlo.y, vhi.x, vhi.y);
-        if (l < 2) {
-          lo = add2(lo, azl);
-          hi = add2(hi, azh);
+        for (int l = 0; l < 3; l++) {
+          const float2 w2 = bc2(wxy * s.wz[l]);
+          float2 vlo = mul2(w2, lo), vhi = mul2(w2, hi);
+          col[((i * 3 + j) * 3 + l) * TS_ROW] = make_float4(vlo.x, vlo.y, vhi.x, vhi.y);
+          if (l < 2) {
+            lo = add2(lo, azl);
+            hi = add2(hi, azh);
+          }
+        }
+        if (j < 2) {
+          lo_ij = add2(lo_ij, ayl);
+          hi_ij = add2(hi_ij, ayh);
         }
       }
-      if (j < 2) {
-        lo_ij = add2(lo_ij, ayl);
-        hi_ij = add2(hi_ij, ayh);
+      if (i < 2) {
+        lo_i = add2(lo_i, axl);
+        hi_i = add2(hi_i, axh);
       }
     }
-    if (i < 2) {
-      lo_i = add2(lo_i, axl);
-      hi_i = add2(hi_i, axh);
-    }
-    __syncwarp();
-    unsigned todo = heads;
-    while (todo) {
-      int h = __ffs(todo) - 1;
-      todo &= todo - 1;
-      int e = todo ? __ffs(todo) - 1 : 32;   // the run is [h, e)
-      if (!((act >> h) & 1u)) continue;      // dead run (inactive lane)
-      int bx = __shfl_sync(0xffffffffu, s.bx, h), by = __shfl_sync(0xffffffffu, s.by, h),
-          bz = __shfl_sync(0xffffffffu, s.bz, h);
-      float4 acc = z4;
-      if (lane < 27)
-        for (int t = h + part; t < e; t += 3) acc = f4add(acc, row[t]);
-      if (e - h > 1) {   // uniform: single-lane runs (strays, sparse dough) have nothing to combine
-        float4 a1 = f4shfl_down(acc, 9), a2 = f4shfl_down(acc, 18);
-        acc = f4add(f4add(acc, a1), a2);
-      }
-      if (lane < 9) red_add4(&Ge[node_offset(bx + i, by + qj, bz + ql, k.nt)], acc);
-    }
-    __syncwarp();   // the tile is rewritten by the next plane / the warp's next scatter
   }
+  __syncwarp();
+  ts_reduce_runs27(k, s, Ge, wbuf, todo, act);
+  __syncwarp();
 }
+// one x-plane (9 nodes) per thread, for the plane-split kernels: lanes (part, node) = (lane / 9, lane % 9) add every third
+// element of the run's row segment, two shuffle-downs combine the three parts
 template <class F>
 DSK_DEV void warp_scatter9_ts(const SimConst& k, bool active, const Stencil& s, int plane, float4* __restrict__ Ge,
                               const TileTrack& tt, bool mark, int env, int epoch, float4* wbuf, F val) {
@@ -502,7 +485,7 @@ DSK_DEV void scatter27_affine(const SimConst& k, bool active, const Stencil& s, 
                               bool mark, int env, int epoch, float4 A0, float3 AX, float3 AY, float3 AZ) {
   if (TS) {
     DSK_DYN_SMEM(float4, ts_buf);
-    warp_scatter27_ts_affine(k, active, s, Ge, tt, mark, env, epoch, ts_buf + (threadIdx.x >> 5) * TS9_WARP_FLOAT4, A0, AX, AY, AZ);
+    warp_scatter27_ts_affine(k, active, s, Ge, tt, mark, env, epoch, ts_buf + (threadIdx.x >> 5) * TS_WARP_FLOAT4, A0, AX, AY, AZ);
   } else {
     warp_scatter27(k, active, s, Ge, tt, mark, env, epoch, [&](int i, int j, int l) {
       float w = s.wx[i] * s.wy[j] * s.wz[l];

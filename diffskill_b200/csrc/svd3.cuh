@@ -41,9 +41,15 @@ DSK_DEV float col_dot(const SvdCol& p, const SvdCol& q) {
 }
 DSK_DEV void jacobi_pair(SvdCol& p, SvdCol& q) {
   float al = col_dot(p, p), be = col_dot(q, q), ga = col_dot(p, q);
-  if (ga != 0.f) {
-    float g2 = ga + ga, d = be - al;
-    float rh = rsqrt_unbiased(fmaf(d, d, g2 * g2));
+  float g2 = ga + ga, d = be - al;
+  float n2 = fmaf(d, d, g2 * g2);
+  if (n2 < 1e-30f) {   // al == be and a tiny ga: the squares underflow -- rescale (only the ratio d : g2 matters)
+    d *= 1.8446744e19f;
+    g2 *= 1.8446744e19f;
+    n2 = fmaf(d, d, g2 * g2);
+  }
+  if (ga != 0.f && n2 > 0.f) {
+    float rh = rsqrt_unbiased(n2);
     float u = fmaf(0.5f * fabsf(d), rh, 0.5f);     // cos^2(theta), in [0.5, 1]
     float y = rsqrt_unbiased(u);
     float c = u * y;

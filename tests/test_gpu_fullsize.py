@@ -35,12 +35,20 @@ def _inputs(workload, B, H):
     return scene, cfg, xs, targets, actions
 
 
-def _engine(scene, xs, H, **kw):
+def _engine(scene, xs, H, contact_tools=False, **kw):
     from diffskill_b200.engine import Engine
+    from helpers import tool_start
     cap = max(len(x) for x in xs)
     eng = Engine(scene, n_envs=len(xs), capacity=cap, max_steps=H, **kw)
     for b, x in enumerate(xs):
         eng.set_particles(0, b, x)
+    if contact_tools:
+        # the generator's slab (cutrearrange_generator_0528.py) is lower than the scene's default box: start the knife and
+        # the gripper in contact with it (as tests/helpers.tool_start does for the small doughs), these properties are
+        # checked on 2-4 env steps
+        for b in range(len(xs)):
+            for i, st in enumerate(tool_start('CutRearrange-v1', scene)):
+                eng.set_tool_state(0, b, i, np.asarray(st, np.float32))
     return eng, cap
 
 
@@ -65,7 +73,7 @@ def test_checkpointed_gradient_equals_taped_gradient_full_size(workload):
     grads = {}
     for name, kw in dict(tape=dict(step_slots=H, grid_tape_mib=1024), checkpoint=dict(step_slots=1, grid_tape_mib=1024),
                          recompute_grid=dict(step_slots=H, grid_tape_mib=0)).items():
-        eng, cap = _engine(scene, xs, H, **kw)
+        eng, cap = _engine(scene, xs, H, contact_tools=workload == 'cutrearrange', **kw)
         grads[name] = _rollout_grads(eng, actions, H, gx)
         del eng
     ref = grads['tape']

@@ -29,8 +29,15 @@ def test_svd_matches_oracle():
     rng = np.random.RandomState(0)
     F = np.eye(3)[None] + rng.normal(size=(4096, 3, 3)) * rng.choice([1e-7, 1e-3, 0.1, 1.0], size=(4096, 1, 1))
     F[0] = np.eye(3)
+    # equal column norms with off-diagonals whose squares underflow: the rotation angle is 45 degrees however tiny the
+    # coupling is (round 2 regression: 1/sqrt(d^2 + 4 ga^2) = inf gave NaN velocities two substeps into a rollout)
+    for i, eps in enumerate((1e-25, 1e-30, 1e-38, 3e-20), start=1):
+        F[i] = np.eye(3)
+        F[i][0, 1] = eps
+        F[i][2, 1] = -eps
     F = f32(F)
     U, s, V = eng.debug_svd(F)
+    assert np.isfinite(U).all() and np.isfinite(s).all() and np.isfinite(V).all()
     rec = np.einsum('nij,nj,nkj->nik', U, s, V)
     assert np.abs(rec - F).max() < 5e-6 * max(1.0, np.abs(F).max())
     assert np.abs(np.einsum('nji,njk->nik', U, U) - np.eye(3)).max() < 5e-6
