@@ -274,8 +274,76 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+def run_gradmodel(args):
+    """--api gradmodel: the reference-API path.  One step = one iteration of `Solver.solve_one_plan`
+    (plb/optimizer/solver.py:111-127) on a single env: GradModel.reset -> H x GradModel.forward (one torch autograd node per
+    env step, observations handed back to torch) -> a torch loss on every observation -> loss.backward() (H x
+    set_obs_grad + backward_step) -> torch Adam step, clamp to [-1, 1].  Same metric as the C-ABI path."""
+    import torch
+    from diffskill_b200.config import load
+    from diffskill_b200.envs.scenes import SCENES
+    from diffskill_b200.sim import GradModel, TaichiEnv
+    spec = workload_spec(args.workload)
+    assert spec['env'] in SCENES and not spec.get('forward_only'), '--api gradmodel runs the single-env fwd+bwd workloads'
+    H = spec['horizon']
+    dev = torch.device('cuda', 0)
+    torch.cuda.set_device(0)
+    cfg = load(data=SCENES[spec['env']])
+    te = TaichiEnv(cfg, loss=False, max_env_steps=H, step_slots=H)
+    te.initialize()
+    n, S, A = te.n_particles, te.simulator.substeps, te.primitives.action_dim
+    func = GradModel(te, softness=666.)
+    x0 = torch.as_tensor(te.simulator.get_x(0), dtype=torch.float32, device=dev)
+    c = x0.mean(0)
+    tgt = (x0 - c) * torch.tensor([1.414, 0.5, 1.414], device=dev) + c + torch.tensor([-0.1, 0., 0.], device=dev)
+    action = torch.nn.Parameter(torch.as_tensor(np.random.RandomState(100).uniform(-1, 1, (H, A)), dtype=torch.float32, device=dev))
+    optim = torch.optim.Adam([action], lr=0.01)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def iteration():
+        obs = func.reset(device=dev)
+        loss = 0
+        for s in range(H):
+            obs = func.forward(s, action[s], *obs)
+            loss = loss + ((obs[0][:, :3] - tgt) ** 2).mean() / H
+        optim.zero_grad()
+        loss.backward()
+        optim.step()
+        with torch.no_grad():
+            action.clamp_(-1, 1)
+        return loss
+
+    for _ in range(args.warmup):
+        iteration()
+    ms = []
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        loss = iteration()
+        lv = float(loss)        # the planner reads the loss every iteration (solver.py:128-141): D2H inside the timed region
+        b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    ms_step = float(np.mean(ms))
+    units = n * H * S
+    out = dict(metric=METRIC, value=units / (ms_step * 1e-3), unit=UNIT, n_gpus=1, steps=args.steps, warmup=args.warmup,
+               ms_per_step=ms_step, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+               api='gradmodel',
+               config=dict(workload=spec['desc'] + ' through GradModel.forward (torch autograd, one node per env step) + torch Adam',
+                           env=spec['env'], horizon=H, substeps=S, envs_per_gpu=1, particles_per_gpu=n,
+                           l2='flushed between timed iterations (256 MiB write)'),
+               e2e=dict(value=units / (ms_step * 1e-3), unit=UNIT, ms_per_step=ms_step, h2d_bytes_per_step=0,
+                        d2h_bytes_per_step=4),
+               gpu_launches=int(func.eng.launch_count()), loss=lv, finite=bool(np.isfinite(lv)))
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument('--api', default='cabi', choices=['cabi', 'gradmodel'],
+                    help='cabi: the multi-step C-ABI calls (default); gradmodel: the reference-shaped torch autograd loop')
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
@@ -294,6 +362,8 @@ def main():
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
+    if args.api == 'gradmodel':
+        return run_gradmodel(args)
     if args.warmup < 3:
         print('bench.py: fewer than 3 warm-up steps -- fine under a profiler, NOT a valid bench number', file=sys.stderr)
 

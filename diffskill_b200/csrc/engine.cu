@@ -94,7 +94,14 @@ struct dsk_engine {
   GridTools grid_tools;   // by-value copy for the grid kernels (refreshed by sync_grid_tools)
   std::vector<ToolParams> h_tools;
   float *tool_ckpt = nullptr, *tool_adj_ckpt = nullptr;  // [H+1][B][K][8]
-  float* pose_adj = nullptr;                             // [B][S+1][K][8]
+  float* pose_adj = nullptr;                             // [B][S+1][K][8] (the buffer the sequence being enqueued uses)
+  float* pose_adj_buf[2] = {nullptr, nullptr};           // two of them: the tool adjoints of step s run on tool_stream while
+                                                         // the main stream already simulates step s-1 (dsk_backward_steps)
+  cudaStream_t tool_stream = nullptr;
+  cudaEvent_t ev_bwd_main[2] = {nullptr, nullptr}, ev_bwd_tools[2] = {nullptr, nullptr};
+  bool tools_pending[2] = {false, false};
+  StepArgs* d_args_bwd = nullptr;                        // [H] per-step args of the deferred tool adjoints (written once)
+  bool seq_defer_tools = false;                          // backward sequence being enqueued leaves the tool adjoints out
   float *actions = nullptr, *action_grad = nullptr;      // [H][B][A]
   float* rand_num = nullptr;
   // io staging
@@ -106,9 +113,9 @@ struct dsk_engine {
   int bwd_cur = 0;  // adjw index holding the adjoint of the current frame
   // sequences / graphs
   struct GraphSet {
-    cudaGraphExec_t ex[16] = {};  // [kind*2 + full_sort]
-    int64_t n_launch[16] = {0};
-    int64_t kid[16][KID_COUNT] = {{0}};
+    cudaGraphExec_t ex[24] = {};  // [kind*2 + full_sort]
+    int64_t n_launch[24] = {0};
+    int64_t kid[24][KID_COUNT] = {{0}};
   };
   std::vector<GraphSet> graphs;
   bool use_graphs = true;
@@ -455,7 +462,14 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
     DA(e->d_tools, std::max(1, e->K));
     DA(e->tool_ckpt, (size_t)(e->H + 1) * e->tool_floats);
     DA(e->tool_adj_ckpt, (size_t)(e->H + 1) * e->tool_floats);
-    DA(e->pose_adj, (size_t)(e->S + 1) * e->tool_floats);
+    DA(e->pose_adj_buf[0], (size_t)(e->S + 1) * e->tool_floats);
+    DA(e->pose_adj_buf[1], (size_t)(e->S + 1) * e->tool_floats);
+    e->pose_adj = e->pose_adj_buf[0];
+    CK(cudaStreamCreateWithFlags(&e->tool_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      CK(cudaEventCreateWithFlags(&e->ev_bwd_main[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&e->ev_bwd_tools[i], cudaEventDisableTiming));
+    }
     DA(e->actions, (size_t)e->H * e->B * std::max(1, e->A));
     DA(e->action_grad, (size_t)e->H * e->B * std::max(1, e->A));
     DA(e->rand_num, (size_t)std::max(1, k.npairs) * DSK_NUM_COLLISION_POINTS * 3);
@@ -493,6 +507,11 @@ int dsk_destroy(dsk_engine* e) {
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   if (e->ev_join2) cudaEventDestroy(e->ev_join2);
   if (e->cap_side) cudaStreamDestroy(e->cap_side);
+  if (e->tool_stream) cudaStreamDestroy(e->tool_stream);
+  for (int i = 0; i < 2; i++) {
+    if (e->ev_bwd_main[i]) cudaEventDestroy(e->ev_bwd_main[i]);
+    if (e->ev_bwd_tools[i]) cudaEventDestroy(e->ev_bwd_tools[i]);
+  }
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   for (auto ev : e->ev_restored) cudaEventDestroy(ev);
@@ -874,7 +893,7 @@ static int seq_begin_backward(dsk_engine* e, StepSlot& s) {
   e->bwd_cur = 0;
   KL(KID_REORDER, k_gather_sorted<<<cdiv(k.stride, 256), 256, 0, e->qs>>>(k, &e->d_args->adj_in, e->npart, s.perm, e->adjw[0]));
   if (e->K > 0)
-    KL(KID_IO, k_pose_adj_init<<<cdiv(e->B * (e->S + 1) * e->K * 8, 128), 128, 0, e->qs>>>(k, e->pose_adj, e->d_args));
+    KL(KID_IO, k_pose_adj_init<<<cdiv(e->B * (e->S + 1) * e->K * 8, 128), 128, 0, e->qs>>>(k, e->pose_adj, e->seq_defer_tools ? nullptr : e->d_args));
   LAUNCH_CHECK();
   return 0;
 }
@@ -915,17 +934,24 @@ static int seq_substep_grad(dsk_engine* e, StepSlot& s, int q, int j) {
   e->bwd_cur ^= 1;
   return 0;
 }
+static size_t kin_adj_smem(dsk_engine* e) { return ((size_t)(e->S + 1) * e->K * 8 + (size_t)e->S * e->K * 128) * 4; }
+// tool adjoints of one env step from the pose adjoints the grid kernels accumulated: on e->qs with `args`
+static int enqueue_tool_adjoints(dsk_engine* e, StepSlot& s, const StepArgs* args, bool seed) {
+  SimConst& k = e->k;
+  size_t sh = kin_adj_smem(e);
+  if (sh > 48 * 1024) {
+    if (sh > 200 * 1024) return fail("tool-adjoint kernel needs %zu bytes of shared memory (substeps x tools too large)", sh);
+    CK(cudaFuncSetAttribute(k_kinematics_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+  }
+  if (seed) KL(KID_IO, k_pose_adj_seed<<<cdiv(e->B * e->K * 8, 128), 128, 0, e->qs>>>(k, e->pose_adj, args));
+  KL(KID_KINEMATICS_ADJ, k_kinematics_adj<<<e->B, KINADJ_CTA, sh, e->qs>>>(k, e->d_tools, s.poses, s.cidx, e->rand_num, args, e->pose_adj));
+  KL(KID_IO, k_tool_adj_accum<<<cdiv(e->B * e->K * 8, 128), 128, 0, e->qs>>>(k, e->pose_adj, args));
+  LAUNCH_CHECK();
+  return 0;
+}
 static int seq_end_backward(dsk_engine* e, StepSlot& s) {
   SimConst& k = e->k;
-  if (e->K > 0) {
-    size_t sh = ((size_t)(e->S + 1) * e->K * 8 + (size_t)e->S * e->K * 128) * 4;
-    if (sh > 48 * 1024) {
-      if (sh > 200 * 1024) return fail("tool-adjoint kernel needs %zu bytes of shared memory (substeps x tools too large)", sh);
-      CK(cudaFuncSetAttribute(k_kinematics_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-    }
-    KL(KID_KINEMATICS_ADJ, k_kinematics_adj<<<e->B, KINADJ_CTA, sh, e->qs>>>(k, e->d_tools, s.poses, s.cidx, e->rand_num, e->d_args, e->pose_adj));
-    KL(KID_IO, k_tool_adj_accum<<<cdiv(e->B * e->K * 8, 128), 128, 0, e->qs>>>(k, e->pose_adj, e->d_args));
-  }
+  if (e->K > 0 && !e->seq_defer_tools && enqueue_tool_adjoints(e, s, e->d_args, false)) return -1;
   KL(KID_REORDER, k_unsort<<<cdiv(k.stride, 256), 256, 0, e->qs>>>(k, e->adjw[e->bwd_cur], e->npart, s.perm, &e->d_args->adj_out, 1));
   LAUNCH_CHECK();
   return 0;
@@ -991,18 +1017,28 @@ static int enqueue_backward_pipelined(dsk_engine* e, StepSlot& s) {
 // SEQ_FWD_NOKIN: forward step whose tool kinematics (and tool checkpoint) were produced ahead of time on the lookahead
 // stream by dsk_forward_steps
 // as is, or (LOOK_*) with the kinematics of the NEXT step on a side branch of this step's graph
-enum SeqKind { SEQ_FWD, SEQ_RECOMPUTE, SEQ_BWD, SEQ_BWD_TAPE, SEQ_BWD_TAPE_TRUSTED, SEQ_FWD_NOKIN, SEQ_FWD_LOOK_FIRST, SEQ_FWD_LOOK_MID };
+enum SeqKind { SEQ_FWD, SEQ_RECOMPUTE, SEQ_BWD, SEQ_BWD_TAPE, SEQ_BWD_TAPE_TRUSTED, SEQ_FWD_NOKIN, SEQ_FWD_LOOK_FIRST, SEQ_FWD_LOOK_MID,
+               SEQ_BWD_TRUSTED_DEFER_A, SEQ_BWD_TRUSTED_DEFER_B /* tool adjoints left to tool_stream; pose_adj buffer 0 / 1 */, SEQ_KIND_COUNT };
 static bool is_fwd_kind(SeqKind k) { return k == SEQ_FWD || k == SEQ_FWD_NOKIN || k == SEQ_FWD_LOOK_FIRST || k == SEQ_FWD_LOOK_MID; }
 static int enqueue_sequence(dsk_engine* e, StepSlot& s, SeqKind kind) {
-  if (kind == SEQ_BWD || kind == SEQ_BWD_TAPE || kind == SEQ_BWD_TAPE_TRUSTED) {
+  if (kind == SEQ_BWD || kind == SEQ_BWD_TAPE || kind == SEQ_BWD_TAPE_TRUSTED || kind == SEQ_BWD_TRUSTED_DEFER_A ||
+      kind == SEQ_BWD_TRUSTED_DEFER_B) {
+    const bool defer = kind == SEQ_BWD_TRUSTED_DEFER_A || kind == SEQ_BWD_TRUSTED_DEFER_B;
     e->seq_use_tape = kind != SEQ_BWD;
-    e->seq_tape_trusted = kind == SEQ_BWD_TAPE_TRUSTED;
-    if (e->seq_tape_trusted && e->qs == e->cap_stream && !getenv("DSK_NO_PIPELINE")) return enqueue_backward_pipelined(e, s);
-    if (seq_begin_backward(e, s)) return -1;
-    for (int q = 0; q < e->S; q++)
-      if (seq_substep_grad(e, s, q, e->S - 1 - q)) return -1;
-    if (seq_end_backward(e, s)) return -1;
-    return seq_clear(e, e->S - 1, true);
+    e->seq_tape_trusted = kind == SEQ_BWD_TAPE_TRUSTED || defer;
+    e->seq_defer_tools = defer;
+    e->pose_adj = e->pose_adj_buf[kind == SEQ_BWD_TRUSTED_DEFER_B ? 1 : 0];
+    int rc;
+    if (e->seq_tape_trusted && e->qs == e->cap_stream && !getenv("DSK_NO_PIPELINE")) {
+      rc = enqueue_backward_pipelined(e, s);
+    } else {
+      rc = seq_begin_backward(e, s);
+      for (int q = 0; !rc && q < e->S; q++) rc = seq_substep_grad(e, s, q, e->S - 1 - q);
+      if (!rc) rc = seq_end_backward(e, s);
+      if (!rc) rc = seq_clear(e, e->S - 1, true);
+    }
+    e->seq_defer_tools = false;
+    return rc;
   }
   e->seq_skip_kin = kind == SEQ_FWD_NOKIN || kind == SEQ_FWD_LOOK_MID;
   if (!(kind == SEQ_FWD_LOOK_FIRST || kind == SEQ_FWD_LOOK_MID)) e->seq_next_slot = nullptr;
@@ -1266,8 +1302,19 @@ int dsk_forward_step(dsk_engine* e, int src_step, int dst_step, int action_step)
   CKE(e);
   return forward_step_impl(e, src_step, dst_step, action_step, SEQ_FWD);
 }
-int dsk_backward_step(dsk_engine* e, int step) {
-  CKE(e);
+// join the deferred tool adjoints (dsk_backward_steps) back into the main stream
+static int join_tool_stream(dsk_engine* e) {
+  for (int b = 0; b < 2; b++)
+    if (e->tools_pending[b]) {
+      CK(cudaStreamWaitEvent(e->stream, e->ev_bwd_tools[b], 0));
+      e->tools_pending[b] = false;
+    }
+  return 0;
+}
+// allow_defer: the caller (dsk_backward_steps) lets the tool adjoints of this step run on tool_stream, concurrently with
+// the particle / grid adjoints of the NEXT (earlier) step: they are needed once per env step only (the pose-adjoint chain
+// k_kinematics_adj, 30-210 us on one SM per env) and nothing on the particle chain depends on them
+static int backward_step_impl(dsk_engine* e, int step, bool allow_defer) {
   if (step < 0 || step >= e->H) return fail("dsk_backward_step: step %d outside [0,%d)", step, e->H);
   int si = step % e->slots;
   StepSlot& s = e->slot[si];
@@ -1296,10 +1343,42 @@ int dsk_backward_step(dsk_engine* e, int step) {
       if (e->tape_overflow[si] == 0) bk = SEQ_BWD_TAPE_TRUSTED;
     }
   }
-  if (run_sequence(e, si, bk)) return -1;
+  const bool defer = allow_defer && bk == SEQ_BWD_TAPE_TRUSTED && e->K > 0 && e->use_graphs && !e->profiling && e->slots >= e->H;
+  if (!defer) {
+    if (join_tool_stream(e)) return -1;   // this step's own tool adjoints need the checkpoint an earlier deferred step writes
+    if (run_sequence(e, si, bk)) return -1;
+  } else {
+    const int b = si & 1;
+    if (e->tools_pending[b]) {   // the buffer's previous user (two steps ago) must be done with it
+      CK(cudaStreamWaitEvent(e->stream, e->ev_bwd_tools[b], 0));
+      e->tools_pending[b] = false;
+    }
+    if (!e->d_args_bwd) {   // pointers only, one entry per step: written once
+      DA(e->d_args_bwd, e->H);
+      int eb = e->epoch_base;
+      for (int t = 0; t < e->H; t++) KL(KID_IO, k_set_args<<<1, 1, 0, e->stream>>>(e->d_args_bwd + t, make_args(e, t, t, t, t)));
+      e->epoch_base = eb;   // these entries never reach a grid kernel: do not burn tile epochs
+      LAUNCH_CHECK();
+    }
+    if (run_sequence(e, si, b ? SEQ_BWD_TRUSTED_DEFER_B : SEQ_BWD_TRUSTED_DEFER_A)) return -1;
+    CK(cudaEventRecord(e->ev_bwd_main[b], e->stream));
+    CK(cudaStreamWaitEvent(e->tool_stream, e->ev_bwd_main[b], 0));
+    cudaStream_t keep = e->qs;
+    e->qs = e->tool_stream;
+    e->pose_adj = e->pose_adj_buf[b];
+    int rc = enqueue_tool_adjoints(e, s, e->d_args_bwd + step, true);
+    e->qs = keep;
+    if (rc) return -1;
+    CK(cudaEventRecord(e->ev_bwd_tools[b], e->tool_stream));
+    e->tools_pending[b] = true;
+  }
   e->last_bwd_frame = -1;
   e->last_substep_slot = si;
   return 0;
+}
+int dsk_backward_step(dsk_engine* e, int step) {
+  CKE(e);
+  return backward_step_impl(e, step, false);
 }
 int dsk_substep(dsk_engine* e, int f) {
   CKE(e);
@@ -1885,9 +1964,13 @@ int dsk_forward_steps(dsk_engine* e, int step0, int nsteps) {
 }
 int dsk_backward_steps(dsk_engine* e, int step_hi, int nsteps) {
   CKE(e);
+  const bool defer = nsteps >= 2 && !getenv("DSK_NO_TOOL_DEFER");
   for (int s = step_hi; s > step_hi - nsteps; s--)
-    if (dsk_backward_step(e, s)) return -1;
-  return 0;
+    if (backward_step_impl(e, s, defer)) {
+      join_tool_stream(e);
+      return -1;
+    }
+  return join_tool_stream(e);   // action gradients and tool adjoints are complete when the call returns (stream order)
 }
 int dsk_loss_add_l2_steps(dsk_engine* e, int step0, int nsteps, const float* target, double weight, int on_device) {
   CKE(e);

@@ -243,7 +243,16 @@ __global__ void k_pose_adj_init(SimConst k, float* __restrict__ pose_adj, const 
   if (i >= k.B * (k.S + 1) * per) return;
   int env = i / ((k.S + 1) * per), r = i - env * (k.S + 1) * per;
   int f = r / per, q = r - f * per;
-  pose_adj[i] = (f == k.S) ? args->tool_adj_in[env * per + q] : 0.f;
+  pose_adj[i] = (f == k.S && args) ? args->tool_adj_in[env * per + q] : 0.f;   // args == null: all zero, seeded later
+}
+// deferred tool adjoints (dsk_backward_steps): frame S of a zero-initialised pose_adj += adjoint checkpoint step+1
+__global__ void k_pose_adj_seed(SimConst k, float* __restrict__ pose_adj, const StepArgs* __restrict__ args) {
+  DSK_TL(k);
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int per = k.K * 8;
+  if (i >= k.B * per) return;
+  int env = i / per, q = i - env * per;
+  pose_adj[((size_t)env * (k.S + 1) + k.S) * per + q] += args->tool_adj_in[i];
 }
 // adjoint checkpoint step += pose_adj frame 0
 __global__ void k_tool_adj_accum(SimConst k, const float* __restrict__ pose_adj, const StepArgs* __restrict__ args) {

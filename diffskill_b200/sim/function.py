@@ -38,12 +38,28 @@ class GradModel:
     def decay_kernel(self, f, alpha):             # function.py:66-77
         self.eng.scale_grad(self.sim._frame_to_step(f), float(alpha))
 
+    def _bufs(self, device):
+        """Device-resident staging tensors, allocated once per device: the per-step entry points below neither allocate
+        nor synchronise (the reference's get_obs / set_obs_grad go through Taichi's to_torch / from_torch copies)."""
+        import torch
+        key = str(device)
+        if getattr(self, '_buf_key', None) != key:
+            eng = self.eng
+            z = lambda *shape: torch.zeros(shape, device=device)
+            self._buf = dict(xv=z(eng.B, eng.capacity, 6), c=z(eng.B, eng.K, 8), d=z(eng.B, eng.capacity, max(eng.ncols, 1)),
+                             gx=z(eng.B, eng.capacity, 3), gv=z(eng.B, eng.capacity, 3), gt=z(eng.B, eng.K, 8),
+                             gd=z(eng.B, eng.capacity, max(eng.ncols, 1)), ga=z(eng.B, max(eng.A, 1)))
+            self._buf_key = key
+            # gap.grad only exists for 8-dof tools (function.py:141-142)
+            self._gap_mask = torch.tensor([1. if p.state_dim == 8 else 0. for p in self.primitives], device=device)
+        return self._buf
+
     def get_obs(self, s, device):
         import torch
         eng, b = self.eng, self.env_index
         n = eng.n_particles(b)
-        xv = torch.zeros((eng.B, eng.capacity, 6), device=device)
-        c = torch.zeros((eng.B, eng.K, 8), device=device)
+        buf = self._bufs(device)
+        xv, c = buf['xv'], buf['c']
         if xv.is_cuda:
             eng.get_obs(s, xv, c)
         else:
@@ -51,16 +67,18 @@ class GradModel:
             xv, c = torch.from_numpy(a), torch.from_numpy(bb)
         x = xv[b, :n]
         if self.return_dist:
-            d = torch.zeros((eng.B, eng.capacity, eng.ncols), device=device)
+            d = buf['d']
             if d.is_cuda:
                 eng.compute_min_dist(s, d)
             else:
                 d = torch.from_numpy(eng.compute_min_dist(s))
             x = torch.cat((x, d[b, :n]), 1)
-        outputs = x.clone(), c[b].clone()
+        else:
+            x = x.clone()
+        outputs = x, c[b].clone()
         for _ in self.output_grid:
             self.sim.clear_and_compute_grid_m(s * self.substeps)
-            outputs = outputs + (self.sim.grid_m.to_torch(device),)
+            outputs = outputs + (self.sim.grid_m.to_torch(device, env=b),)
         return outputs
 
     def set_obs_grad(self, s, obs_grad, manipulator_grad, *args):
@@ -68,23 +86,20 @@ class GradModel:
         eng, b = self.eng, self.env_index
         n = eng.n_particles(b)
         if len(self.output_grid) > 0:
-            self.sim.grid_m.grad.from_torch(args[0])
+            self.sim.grid_m.grad.from_torch(args[0], env=b)
             self.sim.compute_grid_m_kernel.grad(s * self.substeps)
         dev = obs_grad.device
+        buf = self._bufs(dev)
         if self.return_dist:
-            gd = torch.zeros((eng.B, eng.capacity, eng.ncols), device=dev)
+            gd = buf['gd']
             gd[b, :n] = obs_grad[:, -eng.ncols:]
             eng.compute_min_dist_grad(s, gd if gd.is_cuda else gd.numpy())
             obs_grad = obs_grad[..., :-eng.ncols]
         obs_grad = obs_grad.reshape(-1, self.dim * 2)
-        gx = torch.zeros((eng.B, eng.capacity, 3), device=dev)
-        gv = torch.zeros((eng.B, eng.capacity, 3), device=dev)
+        gx, gv, gt = buf['gx'], buf['gv'], buf['gt']     # rows of other envs / beyond n stay zero
         gx[b, :n], gv[b, :n] = obs_grad[:, :3], obs_grad[:, 3:6]
-        gt = torch.zeros((eng.B, eng.K, 8), device=dev)
         gt[b] = manipulator_grad.reshape(eng.K, 8)
-        for i, p in enumerate(self.primitives):
-            if p.state_dim != 8:
-                gt[b, i, 7] = 0.                  # gap.grad only exists for 8-dof tools (function.py:141-142)
+        gt[b, :, 7] *= self._gap_mask
         if gx.is_cuda:
             eng.add_particle_grad(s, gx, gv)
             eng.add_tool_grad(s, gt)
@@ -104,6 +119,10 @@ class GradModel:
     def backward_step(self, s):
         import torch
         self.eng.backward_step(s)
+        if str(self.device).startswith('cuda'):
+            ga = self._bufs(self.device)['ga']
+            self.eng.get_action_grad(s, ga)                     # device -> device, no host round trip
+            return ga[self.env_index, :self.eng.A].double()
         g = self.eng.get_action_grad(s)[self.env_index]
         return torch.tensor(g.astype(np.float64), device=self.device)
 

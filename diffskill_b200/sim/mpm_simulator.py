@@ -42,16 +42,17 @@ class _GridMassField:
     def _set(self, value):
         self._value = value
 
-    def to_numpy(self):
+    def to_numpy(self, env=0):
         n = self._sim.n_grid
-        return np.zeros((n, n, n), np.float32) if self._value is None else self._value[0].copy()
+        return np.zeros((n, n, n), np.float32) if self._value is None else self._value[env].copy()
 
-    def to_torch(self, device='cuda'):
+    def to_torch(self, device='cuda', env=0):
         import torch
-        return torch.from_numpy(self.to_numpy()).to(device)
+        return torch.from_numpy(self.to_numpy(env)).to(device)
 
-    def from_torch(self, t):      # grid_m.grad.from_torch(...)
+    def from_torch(self, t, env=None):      # grid_m.grad.from_torch(...); env: the env of a batched engine the gradient is for
         self._sim._grid_m_grad = t.detach().to(dtype=t.dtype).contiguous()
+        self._sim._grid_m_grad_env = env
 
 
 class MPMSimulator:
@@ -85,6 +86,7 @@ class MPMSimulator:
         self.cur = 0
         self._actions = np.zeros((self.horizon, n_envs, max(1, scene.action_dim)), np.float32)
         self._grid_m_grad = None
+        self._grid_m_grad_env = None
         zero = self.engine.zero_grad
         self.x, self.v = FrameField(self, 'x', zero), FrameField(self, 'v', zero)
         self.F, self.C = FrameField(self, 'F', zero), FrameField(self, 'C', zero)
@@ -215,9 +217,15 @@ class MPMSimulator:
             raise RuntimeError("grid_m.grad.from_torch(...) must be called before compute_grid_m_kernel.grad")
         n = self.n_grid
         if hasattr(g, 'is_cuda'):
+            import torch
             g = g.reshape(-1, n, n, n).float().contiguous()
             if g.shape[0] != self.n_envs:
-                g = g.expand(self.n_envs, n, n, n).contiguous()
+                # a single-env gradient on a batched engine goes to ITS env only (the other envs get zeros)
+                full = torch.zeros((self.n_envs, n, n, n), dtype=g.dtype, device=g.device)
+                full[getattr(self, '_grid_m_grad_env', None) or 0] = g[0]
+                g = full
+            if not g.is_cuda:
+                g = g.numpy()
         self.engine.compute_grid_m_grad(self._frame_to_step(f), g)
 
     def clear_and_compute_grid_m(self, f):

@@ -74,3 +74,18 @@ def test_decay_copy_and_material_fields():
     x, v, F, C = eng.get_particles(1)
     ox, ov, oF, oC = o.get_frame(scene.substeps)
     assert relerr(x, ox) < 1e-5 and relerr(F, oF) < 1e-4          # ... and match the oracle given the same field
+
+
+def test_reference_backend_probe_reports():
+    """The run-time `import taichi` probe BASELINE.md section 3 / SURVEY.md section 8c promise: reports (and records in the
+    parity log) whether the reference's own backend exists on the GPU box.  It never has; if it ever does, this line in the
+    log is the cue to diff against plb/engine directly."""
+    import sys
+    sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
+    from __graft_entry__ import probe_reference_backend
+    from gpu_common import parity_log_path
+    verdict = probe_reference_backend()
+    print(verdict)
+    with open(parity_log_path(), 'a') as f:
+        f.write(__import__('json').dumps(dict(test='reference_backend_probe', verdict=verdict)) + '\n')
+    assert 'taichi' in verdict

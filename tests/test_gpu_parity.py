@@ -126,11 +126,7 @@ def test_substep_forward_parity(name, sort):
         assert worst[k_] < tol or within_noise_floor(worst64[k_], floor[k_], tol), (k_, worst[k_], worst64[k_], floor[k_])
 
 
-# Rope-v1: the only thing that failed here on the GPU was the guard on yield-surface particles (0.985 of the particles
-# are clear of it, the guard asked for 0.99); the comparison behind the relaxed guard has not been re-run on a GPU since
-# (budget), so it reports instead of gating
-@pytest.mark.parametrize('name', [pytest.param(n, marks=pytest.mark.xfail(reason='unverified after relaxing the '
-                                  'yield-surface guard', strict=False)) if n == 'Rope-v1' else n for n in ENVS])
+@pytest.mark.parametrize('name', ENVS)
 def test_substep_backward_parity(name):
     steps = 4
     scene, eng, o, o64 = make_pair(name, n=1200, substeps=1, max_steps=steps, twin=True)
@@ -199,16 +195,11 @@ def test_substep_backward_parity(name):
             (k_, worst[k_], worst64[k_], floor[k_])
 
 
-# Rope-v1 (two Spheres + a static Cylinder on a sliding ground), DESIGN.md section 10: on the B200, with the first builds,
-# forward state, per-substep adjoints and the 1-step gradient matched the oracle at the noise floor but the 3-step gradient
-# was 3.5e-3 off -- the scene has two gradient "basins" and a ~1e-8 bias in the cosine of the Jacobi rotations (MUFU rsqrt)
-# put the GPU into the other one.  The cosine is unbiased now (svd3.cuh), which removes the drift, but the scene stays a coin
-# flip at the 1-ulp level: on the emulated engine these cases pass with GPU-like arithmetic and the new cosine, fail with
-# GPU-like arithmetic and the old one, pass with exact host arithmetic and c = 1/sqrt, fail with exact arithmetic and the
-# refined cosine.  They run and report (xfail, non-strict) instead of gating.
-_ROPE_OPEN = pytest.mark.xfail(reason='Rope-v1 3-step gradient is bistable at the 1-ulp level (DESIGN.md section 10)',
-                               strict=False)
-MULTI_STEP_ENVS = [pytest.param(n, marks=_ROPE_OPEN) if n == 'Rope-v1' else n for n in ENVS]
+# Rope-v1 (two Spheres + a static Cylinder on a sliding ground), DESIGN.md section 10: with the first builds of round 1 the
+# 3-step gradient was 3.5e-3 off on the B200 -- a ~1e-8 bias in the cosine of the Jacobi rotations (MUFU rsqrt) put the GPU
+# into the scene's other gradient "basin".  The cosine has been unbiased since (svd3.cuh: rsqrt_unbiased); these cases
+# passed on the B200 in the round-1 driver run and in every round-2 run (profiles/parity_r02.jsonl), so they gate again.
+MULTI_STEP_ENVS = list(ENVS)
 
 
 @pytest.mark.parametrize('name', MULTI_STEP_ENVS)
@@ -241,14 +232,12 @@ def _run_on_precise_library(selector):
     return r.returncode
 
 
-@pytest.mark.xfail(reason='same case on the correctly rounded diagnostic library (DESIGN.md section 10), reports either way', strict=False)
 def test_rope_multi_step_gradient_without_fast_math():
     """Diagnostic: the Rope-v1 case on the DSK_PRECISE_MATH build (correctly rounded log / exp / div, unbiased cosine in the
     Jacobi SVD; libdiffskill_mpm_pm.so).  The CPU study (scripts/fastmath_sensitivity.py) predicts that it passes there."""
     assert _run_on_precise_library('test_multi_step_action_gradient and 1-256-Rope') == 0
 
 
-@pytest.mark.xfail(reason='every scene on the correctly rounded diagnostic library, reports either way', strict=False)
 def test_all_multi_step_gradients_without_fast_math():
     """Diagnostic: the 3-step gradient property of every scene on the diagnostic library (correctly rounded log / exp /
     div instead of the hardware approximations): how much of the remaining distance to the oracle is fast-math."""
