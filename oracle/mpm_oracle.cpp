@@ -517,6 +517,101 @@ void svd3(const T A[9], T U[9], T sig[3], T V[9]) {
   }
 }
 
+// Second, independent SVD algorithm (test infrastructure for the parity policy): the construction of the
+// McAdams-Selle-Tamstorf-Teran-Sifakis 3x3 SVD that `ti.svd` is recalled to use -- cyclic Jacobi
+// EIGEN-decomposition of the symmetric S = A^T A (exact Givens angles here, the original approximates them), columns of
+// B = A V sorted by decreasing norm, then a Givens QR of B: U = Q, sigma = diag(R), sign carried by the last value.
+// It shares no code with svd3 above: different iteration (two-sided on S instead of one-sided on B), different U
+// (QR instead of normalised columns).  orc_set_svd_algorithm(1) makes every substep use it, so that forward states and
+// -- through backward_svd's 1/clamp(sigma_j^2 - sigma_i^2) -- gradients can be compared ACROSS algorithms, in particular
+// in degenerate singular subspaces (F = I at rest) where U and V are a choice.
+int g_svd_algorithm = 0;
+template <class T>
+void svd3_eig_qr(const T A[9], T U[9], T sig[3], T V[9]) {
+  T S[3][3], W[3][3];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      S[i][j] = A[0 * 3 + i] * A[0 * 3 + j] + A[1 * 3 + i] * A[1 * 3 + j] + A[2 * 3 + i] * A[2 * 3 + j];
+      W[i][j] = i == j ? T(1) : T(0);
+    }
+  const int sweeps = sizeof(T) == 4 ? 5 : 10;
+  const int PQ[3][2] = {{0, 1}, {0, 2}, {1, 2}};
+  for (int sw = 0; sw < sweeps; sw++)
+    for (int k = 0; k < 3; k++) {
+      int p = PQ[k][0], q = PQ[k][1];
+      T apq = S[p][q];
+      if (apq == T(0)) continue;
+      T theta = (S[q][q] - S[p][p]) / (T(2) * apq);
+      T t = (theta >= T(0) ? T(1) : T(-1)) / (std::fabs(theta) + std::sqrt(T(1) + theta * theta));
+      T c = T(1) / std::sqrt(T(1) + t * t), s = c * t;
+      // S <- J^T S J, W <- W J with J = [[c, s], [-s, c]] on (p, q)
+      for (int i = 0; i < 3; i++) {
+        T sp = S[i][p], sq = S[i][q];
+        S[i][p] = c * sp - s * sq;
+        S[i][q] = s * sp + c * sq;
+      }
+      for (int j = 0; j < 3; j++) {
+        T sp = S[p][j], sq = S[q][j];
+        S[p][j] = c * sp - s * sq;
+        S[q][j] = s * sp + c * sq;
+      }
+      for (int i = 0; i < 3; i++) {
+        T wp = W[i][p], wq = W[i][q];
+        W[i][p] = c * wp - s * wq;
+        W[i][q] = s * wp + c * wq;
+      }
+    }
+  T B[3][3];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) B[i][j] = A[i * 3 + 0] * W[0][j] + A[i * 3 + 1] * W[1][j] + A[i * 3 + 2] * W[2][j];
+  T n2[3];
+  for (int j = 0; j < 3; j++) n2[j] = B[0][j] * B[0][j] + B[1][j] * B[1][j] + B[2][j] * B[2][j];
+  auto swapneg = [&](int p, int q) {
+    for (int i = 0; i < 3; i++) {
+      T b = B[i][p];
+      B[i][p] = B[i][q];
+      B[i][q] = -b;
+      T w = W[i][p];
+      W[i][p] = W[i][q];
+      W[i][q] = -w;
+    }
+    std::swap(n2[p], n2[q]);
+  };
+  if (n2[0] < n2[1]) swapneg(0, 1);
+  if (n2[0] < n2[2]) swapneg(0, 2);
+  if (n2[1] < n2[2]) swapneg(1, 2);
+  // Givens QR of B: Q accumulates the rotations, R = Q^T B ends upper triangular (diagonal up to round-off)
+  T Q[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  auto givens = [&](int a, int b, int col) {   // zero B[b][col] against B[a][col]
+    T x = B[a][col], y = B[b][col];
+    T r = std::sqrt(x * x + y * y);
+    if (r == T(0)) return;
+    T c = x / r, s = y / r;
+    for (int j = 0; j < 3; j++) {
+      T ba = B[a][j], bb = B[b][j];
+      B[a][j] = c * ba + s * bb;
+      B[b][j] = -s * ba + c * bb;
+    }
+    for (int i = 0; i < 3; i++) {
+      T qa = Q[i][a], qb = Q[i][b];
+      Q[i][a] = c * qa + s * qb;
+      Q[i][b] = -s * qa + c * qb;
+    }
+  };
+  givens(0, 1, 0);
+  givens(0, 2, 0);
+  givens(1, 2, 1);
+  // r00, r11 >= 0 by construction; the sign of det(A) ends up in r22
+  sig[0] = B[0][0];
+  sig[1] = B[1][1];
+  sig[2] = B[2][2];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      U[i * 3 + j] = Q[i][j];
+      V[i * 3 + j] = W[i][j];
+    }
+}
+
 // ----------------------------------------------------------------------------
 // per-element forward bodies, templated on S
 // ----------------------------------------------------------------------------
@@ -876,7 +971,10 @@ struct Sim {
   }
   void svd() {  // :126-129
 #pragma omp parallel for schedule(static)
-    for (int p = 0; p < n; p++) svd3<T>(&Ftmp[(size_t)p * 9], &U[(size_t)p * 9], &sig[(size_t)p * 3], &V[(size_t)p * 9]);
+    for (int p = 0; p < n; p++) {
+      if (g_svd_algorithm == 1) svd3_eig_qr<T>(&Ftmp[(size_t)p * 9], &U[(size_t)p * 9], &sig[(size_t)p * 3], &V[(size_t)p * 9]);
+      else svd3<T>(&Ftmp[(size_t)p * 9], &U[(size_t)p * 9], &sig[(size_t)p * 3], &V[(size_t)p * 9]);
+    }
   }
   void p2g(int f) {
     std::fill(acc4.begin(), acc4.end(), 0.0);
@@ -1594,6 +1692,7 @@ void orc_set_fast_math_noise(double amplitude, int salt) {
   ad::fast_math_salt() = salt;
 }
 void orc_set_threads(int n) { omp_set_num_threads(n); }
+void orc_set_svd_algorithm(int alg) { orc::g_svd_algorithm = alg; }
 int orc_is_f64(void* h) { return ((Handle*)h)->f64; }
 int orc_n_particles(void* h) {
   int r = 0;
@@ -1836,7 +1935,8 @@ void orc_compute_grid_m_grad(void* h, int f, const double* gin) {
 }
 void orc_svd3(int use_f64, const double* F, double* U, double* sig, double* V) {
   if (use_f64) {
-    svd3<double>(F, U, sig, V);
+    if (orc::g_svd_algorithm == 1) svd3_eig_qr<double>(F, U, sig, V);
+    else svd3<double>(F, U, sig, V);
   } else {
     float f[9], u[9], s[3], v[9];
     for (int i = 0; i < 9; i++) f[i] = (float)F[i];

@@ -72,6 +72,9 @@ typedef struct orc_config {
 void* orc_create(const orc_config* cfg, int use_f64);
 void orc_destroy(void* h);
 void orc_set_threads(int n);
+/* 0: one-sided Jacobi (default); 1: Jacobi eigen-decomposition of A^T A + Givens QR (McAdams et al. construction): a second,
+   independent algorithm to compare degenerate-subspace behaviour of backward_svd across (process-wide switch) */
+void orc_set_svd_algorithm(int alg);
 /* seed != 0: every grid sum of p2g / g2p.grad is perturbed by -ulps/0/+ulps units in the last place (hash of seed, frame, node): emulates the
  * run-to-run noise of the reference's unordered float atomics (mpm_simulator.py:224-225); 0 = exact (default) */
 void orc_set_scatter_noise(int seed, double ulps);

@@ -55,6 +55,11 @@ def lib():
     return _LIB
 
 
+def set_svd_algorithm(alg):
+    """0: one-sided Jacobi (default), 1: eigen-decomposition of A^T A + Givens QR (process-wide)."""
+    lib().orc_set_svd_algorithm(int(alg))
+
+
 def set_scatter_noise(seed, ulps=1.0):
     """Process-wide: perturb every grid sum of p2g / g2p.grad by -ulps/0/+ulps units in the last place (hash of seed,
     frame, node) -- the run-to-run noise of the reference's unordered float atomics.  The spread of a result over a few
