@@ -1964,7 +1964,10 @@ int dsk_forward_steps(dsk_engine* e, int step0, int nsteps) {
 }
 int dsk_backward_steps(dsk_engine* e, int step_hi, int nsteps) {
   CKE(e);
-  const bool defer = nsteps >= 2 && !getenv("DSK_NO_TOOL_DEFER");
+  // worth its two events per step only where the pose-adjoint chain is long: many envs per launch or tool-tool collision
+  // pairs (r02e: GatherMove x64 113.3 -> 105.1 ms, x8 50.1 -> 48.2 ms; LiftSpread, one env and one pair, 42.5 -> 43.4 ms)
+  bool defer = nsteps >= 2 && e->B * std::max(1, e->k.npairs) >= 8;
+  if (const char* v = getenv("DSK_TOOL_DEFER")) defer = nsteps >= 2 && atoi(v) != 0;
   for (int s = step_hi; s > step_hi - nsteps; s--)
     if (backward_step_impl(e, s, defer)) {
       join_tool_stream(e);

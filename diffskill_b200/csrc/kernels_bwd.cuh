@@ -354,13 +354,24 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4)
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   int n_active = *count;
   const int l = tid & 63;
-  for (int it = blockIdx.x * FLAT_TILES + (w >> 1); it < n_active; it += gridDim.x * FLAT_TILES) {
-    int gt = list[it];
+  // software pipeline over the tile loop (see k_grid_flat): next iteration's list entry, (momentum, mass) and adjoint tile
+  // are in flight while the current tile is processed
+  const int it0 = blockIdx.x * FLAT_TILES + (w >> 1), stride = gridDim.x * FLAT_TILES;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  int gt_n = it0 < n_active ? list[it0] : 0;
+  float4 gin_n = it0 < n_active ? G0[((size_t)gt_n << 6) + l] : z4;
+  float4 ga_n = it0 < n_active ? Ga[((size_t)gt_n << 6) + l] : z4;
+  for (int it = it0; it < n_active; it += stride) {
+    const int gt = gt_n;
+    const float4 gin = gin_n, ga4 = ga_n;
+    if (it + stride < n_active) {
+      gt_n = list[it + stride];
+      gin_n = G0[((size_t)gt_n << 6) + l];
+      ga_n = Ga[((size_t)gt_n << 6) + l];
+    }
     int env = gt / k.ntile, tile = gt - env * k.ntile;
     int tz = tile % k.nt, ty = (tile / k.nt) % k.nt, tx = tile / (k.nt * k.nt);
     size_t o = ((size_t)gt << 6) + l;
-    float4 gin = G0[o];
-    float4 ga4 = Ga[o];
     bool live = gin.w > k.m_eps;
     int I0 = tx * 4 + (l >> 4), I1 = ty * 4 + ((l >> 2) & 3), I2 = tz * 4 + (l & 3);
     float3 gp = f3(mul_rn((float)I0, k.dx), mul_rn((float)I1, k.dx), mul_rn((float)I2, k.dx));

@@ -227,12 +227,22 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4)
     }
   }
   const int l = tid & 63;   // node within the tile
-  for (int it = blockIdx.x * FLAT_TILES + (w >> 1); it < n_active; it += gridDim.x * FLAT_TILES) {
-    int gt = list[it];
+  // software pipeline over the tile loop: the list entry and the tile's 1 KB of the NEXT iteration are loaded before the
+  // current tile is processed (list -> grid is a dependent L2 + HBM round trip of ~1 us per iteration otherwise; a batch of
+  // 64 envs has ~4 iterations per warp pair)
+  const int it0 = blockIdx.x * FLAT_TILES + (w >> 1), stride = gridDim.x * FLAT_TILES;
+  int gt_n = it0 < n_active ? list[it0] : 0;
+  float4 g_n = it0 < n_active ? Gin[((size_t)gt_n << 6) + l] : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int it = it0; it < n_active; it += stride) {
+    const int gt = gt_n;
+    const float4 g = g_n;
+    if (it + stride < n_active) {
+      gt_n = list[it + stride];
+      g_n = Gin[((size_t)gt_n << 6) + l];
+    }
     int env = gt / k.ntile, tile = gt - env * k.ntile;
     int tz = tile % k.nt, ty = (tile / k.nt) % k.nt, tx = tile / (k.nt * k.nt);
     size_t o = ((size_t)gt << 6) + l;
-    float4 g = Gin[o];
     bool live = g.w > k.m_eps;
     int I0 = tx * 4 + (l >> 4), I1 = ty * 4 + ((l >> 2) & 3), I2 = tz * 4 + (l & 3);
     unsigned mask = warp_prepare_frames(k, sT, ft, poses, env, j, tx, ty, tz, wf[w], lane);

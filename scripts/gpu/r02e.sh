@@ -10,7 +10,7 @@ python -c "import __graft_entry__ as g; g.smoke()" > $O/r02e_smoke.log 2>&1
 B="python bench.py --steps 5 --warmup 3 --no-cpu-baseline"
 for wl in gathermove liftspread cutrearrange; do
   $B --workload $wl > $O/r02e_bench_${wl}.json 2> $O/r02e_bench_${wl}.err
-  DSK_NO_TOOL_DEFER=1 $B --workload $wl > $O/r02e_bench_${wl}_nodefer.json 2>&1
+  DSK_TOOL_DEFER=0 $B --workload $wl > $O/r02e_bench_${wl}_nodefer.json 2>&1
 done
 $B --workload gathermove --envs 8 > $O/r02e_bench_gathermove_8env.json 2>&1
 $B --workload liftspread --api gradmodel > $O/r02e_bench_liftspread_api_gradmodel.json 2> $O/r02e_bench_liftspread_api_gradmodel.err

@@ -218,32 +218,6 @@ def test_multi_step_action_gradient_batched_layout(name, slots, tape_mib, monkey
     _multi_step_action_gradient(name, slots, tape_mib)
 
 
-def _run_on_precise_library(selector):
-    import os
-    import subprocess
-    import sys
-    from diffskill_b200 import build as b
-    if not os.path.exists(b.SO_PRECISE):
-        pytest.skip('libdiffskill_mpm_pm.so not built (python -m diffskill_b200.build --precise)')
-    env = dict(os.environ, DSK_LIB='precise')
-    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.abspath(__file__), '-q', '-s', '--runxfail', '-p', 'no:cacheprovider',
-                        '-k', selector], env=env, capture_output=True, text=True, timeout=900)
-    print('\n'.join(l for l in r.stdout.splitlines() if 'action grad' in l or 'twin' in l or 'passed' in l or 'failed' in l))
-    return r.returncode
-
-
-def test_rope_multi_step_gradient_without_fast_math():
-    """Diagnostic: the Rope-v1 case on the DSK_PRECISE_MATH build (correctly rounded log / exp / div, unbiased cosine in the
-    Jacobi SVD; libdiffskill_mpm_pm.so).  The CPU study (scripts/fastmath_sensitivity.py) predicts that it passes there."""
-    assert _run_on_precise_library('test_multi_step_action_gradient and 1-256-Rope') == 0
-
-
-def test_all_multi_step_gradients_without_fast_math():
-    """Diagnostic: the 3-step gradient property of every scene on the diagnostic library (correctly rounded log / exp /
-    div instead of the hardware approximations): how much of the remaining distance to the oracle is fast-math."""
-    assert _run_on_precise_library('test_multi_step_action_gradient and 1-256 and not Rope') == 0
-
-
 def _multi_step_action_gradient(name, slots, tape_mib):
     """3 env steps of the real substep count: checkpoint + recompute (slots=1) and full tape (slots=3)
     must both match the oracle's taped gradient (the reference's own property test, long_term_gradient.ipynb).
