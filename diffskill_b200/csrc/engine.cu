@@ -149,6 +149,7 @@ struct dsk_engine {
   // resident 128-thread CTAs per SM requested from the particle kernels of batched engines (register cap 65536/(128*n))
   int big_block = 128;
   int minb_g2p2g = 4, minb_g2p_adj = 4, minb_p2g_adj = 4;
+  bool mat_uniform = true;  // no per-particle material set: the particle kernels take (mu, lam, yield_stress) from SimConst
   bool flat_grid = false;   // many active tiles: throughput layout of the grid kernels
   bool ts = true;           // batched engines: transposed shared-memory scatter (warp_scatter27_ts_affine) instead of the shuffle butterfly
   bool ts_pl = false;       // ... in the plane-split kernels of single scenes (slower there: r02b liftspread 46.3 vs 42.3 ms)
@@ -349,6 +350,9 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
   k.x_lo = (float)(c->lower_bound * c->dx);
   k.m_eps = 1e-12f;
   k.ground_friction = (float)c->ground_friction;
+  k.mu = (float)c->mu;
+  k.lam = (float)c->lam;
+  k.ys = (float)c->yield_stress;
   for (int d = 0; d < 3; d++) {
     volatile float t = k.dt * (float)c->gravity[d];
     k.grav[d] = t * 30.f;
@@ -815,7 +819,7 @@ static int seq_substep(dsk_engine* e, StepSlot& s, int q, int j, bool write_stat
   int nb = cdiv(k.stride, pb);
   float* fin = s.frames + (size_t)j * e->frame_floats;
   float* fout = s.frames + (size_t)(j + 1) * e->frame_floats;
-  if (launch_p2g(e, write_state, fin, fout, s.mat, e->G0[set], tt, q, nullptr, write_state ? svd_at(e, s, j) : nullptr)) return -1;
+  if (launch_p2g(e, write_state, fin, fout, (e->mat_uniform ? nullptr : s.mat), e->G0[set], tt, q, nullptr, write_state ? svd_at(e, s, j) : nullptr)) return -1;
   bool clr = q > 0;
   if (e->kin_join) {
     CK(cudaStreamWaitEvent(e->qs, e->ev_join, 0));
@@ -853,14 +857,14 @@ static int seq_forward_fused(dsk_engine* e, StepSlot& s) {
   auto frame = [&](int j) { return s.frames + (size_t)j * e->frame_floats; };
   {
     TileTrack tt{e->tile_epoch[1], e->tile_list[1], e->tile_count + 1};
-    if (launch_p2g(e, true, frame(0), frame(1), s.mat, e->G0[1], tt, 0, nullptr, svd_at(e, s, 0))) return -1;
+    if (launch_p2g(e, true, frame(0), frame(1), (e->mat_uniform ? nullptr : s.mat), e->G0[1], tt, 0, nullptr, svd_at(e, s, 0))) return -1;
   }
   for (int q = 0; q < e->S; q++) {
     if (seq_grid_fwd(e, s, q)) return -1;
     int set = (q + 1) & 1, nset = set ^ 1;
     if (q + 1 < e->S) {
       TileTrack tt{e->tile_epoch[nset], e->tile_list[nset], e->tile_count + ((q + 2) & 3)};
-      if (launch_g2p2g(e, frame(q), frame(q + 1), frame(q + 2), s.mat, e->G0[set], e->G0[nset], tt, q + 1, svd_at(e, s, q + 1))) return -1;
+      if (launch_g2p2g(e, frame(q), frame(q + 1), frame(q + 2), (e->mat_uniform ? nullptr : s.mat), e->G0[set], e->G0[nset], tt, q + 1, svd_at(e, s, q + 1))) return -1;
     } else {
       KL(KID_G2P, k_g2p<<<nb, pb, 0, e->qs>>>(k, frame(q), frame(q + 1), e->npart, e->G0[set]));
     }
@@ -919,7 +923,7 @@ static int seq_substep_grad(dsk_engine* e, StepSlot& s, int q, int j) {
     run_if = s.tape.overflow;
   }
   if (!(e->seq_use_tape && e->seq_tape_trusted)) {
-    if (launch_p2g(e, false, fin, nullptr, s.mat, e->G0[set], tt, q, run_if, nullptr)) return -1;
+    if (launch_p2g(e, false, fin, nullptr, (e->mat_uniform ? nullptr : s.mat), e->G0[set], tt, q, run_if, nullptr)) return -1;
     KL(KID_GRID_RECOMPUTE, GRID_FWD_LAUNCH(e, e->qs,
                                k, e->grid_tools, s.poses, j, e->G0[set], e->Gv[set], tt.list, tt.count,
                                clr ? e->tile_list[prev] : nullptr, e->tile_count + (q & 3), clr ? e->G0[prev] : nullptr,
@@ -929,7 +933,7 @@ static int seq_substep_grad(dsk_engine* e, StepSlot& s, int q, int j) {
   if (launch_g2p_adj(e, fin, fnext, ain, aout, e->Gv[set], e->Ga[set])) return -1;
   KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, e->qs, (GridAdjScratch{nullptr, nullptr, 0}), k, e->grid_tools, s.poses, j, e->G0[set], e->Ga[set],
                                                                       tt.list, tt.count, e->pose_adj));
-  if (launch_p2g_adj(e, fin, ain, aout, s.mat, e->Ga[set], svd_at(e, s, j))) return -1;
+  if (launch_p2g_adj(e, fin, ain, aout, (e->mat_uniform ? nullptr : s.mat), e->Ga[set], svd_at(e, s, j))) return -1;
   LAUNCH_CHECK();
   e->bwd_cur ^= 1;
   return 0;
@@ -998,7 +1002,7 @@ static int enqueue_backward_pipelined(dsk_engine* e, StepSlot& s) {
     GridAdjScratch sc{park ? e->gadj_scratch[q & 1] : nullptr, park ? e->gadj_flags[q & 1] : nullptr, park ? e->gadj_cap : 0};
     KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, mainq, sc, k, e->grid_tools, s.poses, j, e->G0[set], e->Ga[set],
                                                                           tt.list, tt.count, e->pose_adj));
-    if (launch_p2g_adj(e, fin, ain, aout, s.mat, e->Ga[set], svd_at(e, s, j))) return -1;
+    if (launch_p2g_adj(e, fin, ain, aout, (e->mat_uniform ? nullptr : s.mat), e->Ga[set], svd_at(e, s, j))) return -1;
     CK(cudaEventRecord(e->ev_main[q], mainq));
     e->bwd_cur ^= 1;
   }
@@ -1212,6 +1216,10 @@ int dsk_set_material(dsk_engine* e, int env, const float* mu, const float* lam, 
                          cudaMemcpyHostToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   invalidate_all(e);
+  if (e->mat_uniform) {   // from now on the kernels read the per-particle arrays (the pointer is baked into the graphs)
+    e->mat_uniform = false;
+    drop_graphs(e);
+  }
   return 0;
 }
 int dsk_set_tool_param(dsk_engine* e, int tool, int which, double value) {

@@ -490,7 +490,8 @@ __global__ void __launch_bounds__(PL_PARTICLES * 3)
   float3 v = load_v3(fin, CV, k.stride, gi);
   M3 C = load_m3(fin, CC, k.stride, gi);
   M3 F = load_m3(fin, CF, k.stride, gi);
-  float mu = mat[gi], lam = mat[k.stride + gi], ys = mat[2 * k.stride + gi];
+  float mu, lam, ys;
+  load_mat(k, mat, gi, mu, lam, ys);
   P2GParticle o;
   p2g_particle_adj(k, svd_in, gi, C, F, mu, lam, ys, o);
   Stencil s;

@@ -25,7 +25,8 @@ __global__ void __launch_bounds__(128, MINB)
   float3 v = load_v3(fin, CV, k.stride, g);
   M3 C = load_m3(fin, CC, k.stride, g);
   M3 F = load_m3(fin, CF, k.stride, g);
-  float mu = mat[g], lam = mat[k.stride + g], ys = mat[2 * k.stride + g];
+  float mu, lam, ys;
+  load_mat(k, mat, g, mu, lam, ys);
   P2GParticle o;
   p2g_particle(k, C, F, mu, lam, ys, o);
   if (WRITE_F && active) {
@@ -341,7 +342,8 @@ __global__ void __launch_bounds__(128, MINB)
     store_v3(fcur, CV, k.stride, gid, nv);
     store_m3(fcur, CC, k.stride, gid, C);
   }
-  float mu = mat[g], lam = mat[k.stride + g], ys = mat[2 * k.stride + g];
+  float mu, lam, ys;
+  load_mat(k, mat, g, mu, lam, ys);
   P2GParticle o;
   p2g_particle(k, C, F, mu, lam, ys, o);
   if (active) {
@@ -377,7 +379,8 @@ __global__ void __launch_bounds__(PL_PARTICLES * 3)
   int g = active ? gid : env * k.Npad;
   float3 x = load_v3(fprev, CX, k.stride, g);
   M3 F = load_m3(fcur, CF, k.stride, g);   // written by the p2g of substep q
-  float mu = mat[g], lam = mat[k.stride + g], ys = mat[2 * k.stride + g];
+  float mu, lam, ys;
+  load_mat(k, mat, g, mu, lam, ys);
   Stencil s;
   make_stencil(k, x.x, x.y, x.z, s);
   {

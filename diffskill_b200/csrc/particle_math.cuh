@@ -18,6 +18,7 @@ struct SimConst {
   int gf_mode;              // ground friction: 0 zero-normal, 1 Coulomb, 2 stick (mpm_simulator.py:245-258)
   float dt, dx, inv_dx, p_mass, c_stress, c_C, x_hi, x_lo, m_eps, ground_friction;
   float grav[3];            // (dt * g) * 30, mpm_simulator.py:235
+  float mu, lam, ys;        // the scene's material; the kernels read these while no per-particle material was set (mat == null)
   int pairs[DSK_MAX_PAIRS][2];
 #ifdef DSK_TIMELINE
   struct TlRec* tl;         // device timeline records (profiling build only)
@@ -64,6 +65,19 @@ DSK_DEV void make_stencil(const SimConst& k, float x, float y, float z, Stencil&
   }
 }
 
+// per-particle material (mu, lam, yield_stress): the sorted arrays, or the scene's constants while nobody called
+// dsk_set_material (12 bytes per particle and kernel less)
+DSK_DEV void load_mat(const SimConst& k, const float* __restrict__ mat, int g, float& mu, float& lam, float& ys) {
+  if (mat) {
+    mu = mat[g];
+    lam = mat[k.stride + g];
+    ys = mat[2 * k.stride + g];
+  } else {
+    mu = k.mu;
+    lam = k.lam;
+    ys = k.ys;
+  }
+}
 DSK_DEV M3 load_m3(const float* __restrict__ f, int comp0, int stride, int gid) {
   M3 A;
 #pragma unroll
@@ -454,7 +468,8 @@ DSK_DEV void p2g_adj_particle(const SimConst& k, int gid, int env, const float* 
   float3 v = load_v3(fin, CV, k.stride, gid);
   M3 C = load_m3(fin, CC, k.stride, gid);
   M3 F = load_m3(fin, CF, k.stride, gid);
-  float mu = mat[gid], lam = mat[k.stride + gid], ys = mat[2 * k.stride + gid];
+  float mu, lam, ys;
+  load_mat(k, mat, gid, mu, lam, ys);
   P2GParticle o;
   p2g_particle_adj(k, svd_in, gid, C, F, mu, lam, ys, o);
   Stencil s;
