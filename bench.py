@@ -356,6 +356,7 @@ def main():
     ap.add_argument('--grid-tape-mib', type=int, default=8192,
                     help='device memory budget for taping active grid tiles (adjoint skips the p2g/grid_op recompute); 0 = off')
     ap.add_argument('--envs', type=int, default=0, help='override the envs per GPU of the workload (experiments; the JSON says so)')
+    ap.add_argument('--env-offset', type=int, default=0, help='simulate the envs a later rank would get (experiments: per-rank spread)')
     ap.add_argument('--per-step-calls', action='store_true', help='drive the rollout with one host call per env step')
     ap.add_argument('--no-sort', action='store_true')
     ap.add_argument('--no-graphs', action='store_true')
@@ -387,7 +388,9 @@ def main():
         B = args.envs
         spec['desc'] += f' [--envs {B} override]'
     H = spec['horizon']
-    scene, cfg, xs, targets, actions = make_inputs(spec, rank, B)
+    if args.env_offset:
+        spec['desc'] += f' [--env-offset {args.env_offset}]'
+    scene, cfg, xs, targets, actions = make_inputs(spec, rank + args.env_offset, B)
     cap = max(len(x) for x in xs)
     if args.step_slots <= 0:
         tape_bytes = H * (scene.substeps + 1) * 24 * B * ((cap + 127) // 128 * 128) * 4
