@@ -149,6 +149,7 @@ struct dsk_engine {
   // resident 128-thread CTAs per SM requested from the particle kernels of batched engines (register cap 65536/(128*n))
   int big_block = 128;
   int minb_g2p2g = 4, minb_g2p_adj = 4, minb_p2g_adj = 4;
+  int grid_ctas_per_sm = 2;  // latency layout of the grid kernels: CTAs per SM walking the active-tile list
   bool mat_uniform = true;  // no per-particle material set: the particle kernels take (mu, lam, yield_stress) from SimConst
   bool flat_grid = false;   // many active tiles: throughput layout of the grid kernels
   bool ts = true;           // batched engines: transposed shared-memory scatter (warp_scatter27_ts_affine) instead of the shuffle butterfly
@@ -392,6 +393,7 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
   if (const char* v = getenv("DSK_MINB_G2P_ADJ")) e->minb_g2p_adj = atoi(v);
   if (const char* v = getenv("DSK_MINB_P2G_ADJ")) e->minb_p2g_adj = atoi(v);
   e->flat_grid = e->big;
+  if (const char* v = getenv("DSK_GRID_CTAS_PER_SM")) e->grid_ctas_per_sm = std::max(1, atoi(v));
   if (const char* v = getenv("DSK_TS")) e->ts = atoi(v) != 0;
   if (const char* v = getenv("DSK_TS_PL")) e->ts_pl = atoi(v) != 0;
   if (const char* v = getenv("DSK_FLAT_GRID")) e->flat_grid = atoi(v) != 0;
@@ -609,7 +611,7 @@ static int stage_in(dsk_engine* e, const float* src, size_t n, int on_device, si
   return 0;
 }
 
-static int grid_ctas(dsk_engine* e) { return e->big ? 148 * 8 : 148 * 2; }
+static int grid_ctas(dsk_engine* e) { return e->big ? 148 * 8 : 148 * e->grid_ctas_per_sm; }
 static float* svd_at(dsk_engine* e, StepSlot& s, int j) {
   return s.svd ? s.svd + (size_t)j * SVD_COMPS * e->k.stride : nullptr;
 }
