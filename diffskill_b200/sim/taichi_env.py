@@ -42,9 +42,12 @@ def sinkhorn_emd(x, y, blur=0.001, p=1, scaling=0.5, iters_cap=200):
                 f = -e * torch.logsumexp(lb[None, :] + (g[None, :] - Cd) / e, dim=1)
                 g = -e * torch.logsumexp(la[None, :] + (f[None, :] - Cd.t()) / e, dim=1)
         e = eps_list[-1]
-        # one differentiable half-step at the final temperature (envelope theorem: gradients w.r.t. the points)
+        # One differentiable half-step at the final temperature.  Envelope theorem: d OT / d points = sum_ij pi_ij dC_ij; the
+        # f half-step alone already carries exactly that (its softmin weights are the rows of the plan), for both clouds.
+        # Differentiating the g half-step as well counts every pair twice (round 2: tests/test_losses_known_answers.py found
+        # the gradient of the first version to be 2x a finite difference of its own value), so g contributes its VALUE only.
         f2 = -e * torch.logsumexp(lb[None, :] + (g[None, :] - C) / e, dim=1)
-        g2 = -e * torch.logsumexp(la[None, :] + (f[None, :] - C.t()) / e, dim=1)
+        g2 = -e * torch.logsumexp(la[None, :] + (f[None, :] - Cd.t()) / e, dim=1)
         return f2.mean() + g2.mean()
 
     return ot(x, y) - 0.5 * (ot(x, x) + ot(y, y))
