@@ -76,8 +76,7 @@ def chamfer_loss(bidirectional):
 class TaichiEnv:
     def __init__(self, cfg, nn=False, loss=True, return_dist=False, n_envs=1, device_index=0, step_slots=None,
                  max_env_steps=None):
-        if nn:
-            raise NotImplementedError("the Taichi MLP policy (plb/engine/nn) is out of scope (SURVEY.md section 2 row 9)")
+        self._want_nn = bool(nn)           # taichi_env.py:81-82: self.nn = MLP(simulator, primitives, (256, 256)), built below
         self.has_loss = loss
         self.full_cfg = cfg
         self.cfg = cfg.ENV
@@ -118,6 +117,9 @@ class TaichiEnv:
         self.primitives.initialize(self.cfg.cached_state_path)
         self.simulator.initialize(self.n_particles)
         self.simulator.reset(self.init_particles)
+        if self._want_nn and not hasattr(self, 'nn'):
+            from .mlp import MLP
+            self.nn = MLP(self.simulator, self.primitives, (256, 256), n_particles=self.n_particles)   # taichi_env.py:81-82
 
     def load_target_x(self, path):
         import torch

@@ -293,3 +293,66 @@ def test_multitask_env_over_a_cached_dataset(tmp_path):
     assert np.array_equal(env.get_state()['state'][0], s['state'][0]) and len(env.get_primitive_state()) == 3
     env.reset(contact_loss_mask=0)                                                   # random pair, mask by tool index
     assert te.contact_loss_mask.tolist() == [1., 0., 0.] and env.init_v in (0, 1) and isinstance(te.tensor_target_x, torch.Tensor)
+
+
+def test_mlp_policy_gradients_through_the_engine():
+    """plb/engine/nn/mlp.py over the engine: TaichiEnv(nn=True).nn is the closed-loop policy (observation -> layers -> clamp ->
+    action); its parameter gradients flow through GradModel's autograd nodes.  One env step: the flat get_grad() must equal
+    (d action / d params)^T applied to the engine's own action gradient; two env steps: a directional finite difference
+    through the whole closed loop."""
+    import torch
+    from diffskill_b200.config import load
+    from diffskill_b200.envs.scenes import SCENES
+    from diffskill_b200.sim import GradModel, MLP, TaichiEnv
+    cfg = load(data=SCENES['LiftSpread-v1'])
+    cfg.SHAPES[0]['radius'] = 0.02
+    te = TaichiEnv(cfg, nn=True, loss=False, max_env_steps=3)
+    te.initialize()
+    assert isinstance(te.nn, MLP) and te.nn.dims[0] == te.nn.obs_num * 6 + 7 * len(te.primitives) and te.nn.dims[-1] == te.primitives.action_dim
+    # dough in contact with the rolling pin and the lifter (tests/helpers.py), so that actions matter from the first step
+    from helpers import small_dough, tool_start
+    scene_, _, x0 = small_dough('LiftSpread-v1', te.n_particles, 0)
+    te.simulator.reset(x0)
+    for p, st in zip(te.primitives, tool_start('LiftSpread-v1', scene_)):
+        p.set_state(0, list(st[:p.state_dim]))
+    nn = MLP(te.simulator, te.primitives, (16,), activation='tanh', n_observed_particles=50, n_particles=te.n_particles, device=DEVICE, seed=1)
+    flat = nn.get_params()
+    nn.set_params(flat * 0.5)
+    assert np.allclose(nn.get_params(), flat * 0.5) and len(flat) == sum(a * b + a for a, b in zip(nn.dims[1:], nn.dims[:-1]))
+    func = GradModel(te, softness=666.)
+    rng = np.random.RandomState(0)
+    n = te.n_particles
+    Wt = torch.tensor(rng.normal(size=(n, 6)), device=DEVICE, dtype=torch.float32)
+
+    def loss_of(H):
+        nn.zero_grad()
+        return nn.rollout(func, H, lambda s, obs: (obs[0][:, :6] * Wt).sum() / n, device=DEVICE)
+
+    # one step: chain rule by hand
+    loss = loss_of(1)
+    loss.backward()
+    g = nn.get_grad()
+    ga = torch.as_tensor(func.eng.get_action_grad(0)[0], device=DEVICE)
+    obs0 = func.reset(device=DEVICE)
+    nn.zero_grad()
+    (nn.forward(obs0) * ga).sum().backward()
+    g_manual = nn.get_grad()
+    e1 = relerr(g, g_manual)
+    # two steps: directional derivative of the closed loop
+    loss2 = loss_of(2)
+    loss2.backward()
+    g2 = nn.get_grad()
+    d = rng.normal(size=len(flat)) * (np.abs(g2) > 0)
+    d /= np.linalg.norm(d)
+    p0, fds = nn.get_params(), []
+    for h in (1e-3, 2e-3, 4e-3):     # fp32 losses of O(1) differenced at 1e-5: average a few step sizes
+        nn.set_params(p0 + h * d)
+        lp = float(loss_of(2))
+        nn.set_params(p0 - h * d)
+        lm = float(loss_of(2))
+        fds.append((lp - lm) / (2 * h))
+    nn.set_params(p0)
+    fd, an = float(np.mean(fds)), float(g2 @ d)
+    print('MLP policy: 1-step chain err %.2e; 2-step directional derivative autograd %.4e vs FD %.4e' % (e1, an, fd))
+    assert e1 < 1e-4 and np.abs(g).max() > 0
+    assert an * fd > 0 and 1 / 3 < an / fd < 3, (an, fds)   # a consistency check at fp32 finite-difference noise, not a parity bar
