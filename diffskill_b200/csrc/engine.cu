@@ -270,6 +270,11 @@ static void fill_tool(ToolParams& T, const dsk_tool_desc& d) {
     T.bound_r = (float)std::sqrt(d.h * d.h + d.r * d.r);
   else if (d.type == DSK_TOOL_TORUS)      // major + minor radius
     T.bound_r = (float)(d.h + d.r);
+  else if (d.type == DSK_TOOL_CHOPSTICKS) {   // two capsules spanning local y in [-h, 0] at x = -+gap/2; no upper clamp on the gap
+    T.max_gap = 1e30f;
+    double g = std::max(d.maximal_gap > 0 && d.maximal_gap < 1e3 ? d.maximal_gap : 0.0, 1.0);   // a gap never exceeds the unit box
+    T.bound_r = (float)std::sqrt((g / 2 + d.r) * (g / 2 + d.r) + (d.h + d.r) * (d.h + d.r));
+  }
   else
     T.bound_r = (float)std::sqrt(d.size[0] * d.size[0] + d.size[1] * d.size[1] + d.size[2] * d.size[2]);
   T.bound_r *= 1.001f;
@@ -374,7 +379,7 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
     e->A += c->tools[i].action_dim;
     e->ncols += host_is_gripper(c->tools[i].type) ? 2 : 1;
     e->n_frames = std::max(1, e->ncols);
-    if (c->tools[i].type < 0 || c->tools[i].type > DSK_TOOL_TORUS) {
+    if (c->tools[i].type < 0 || c->tools[i].type > DSK_TOOL_CHOPSTICKS) {
       delete e;
       return fail("unknown tool type %d", c->tools[i].type);
     }

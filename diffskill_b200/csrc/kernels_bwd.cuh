@@ -123,7 +123,7 @@ struct ContactGeomAdj {   // per (node, frame), shared memory
 // adjoints of the frame's tool at substeps j and j+1.  Called by every thread of the CTA (one barrier inside).
 DSK_DEV void frame_pose_adjoint(const SimConst& k, const ToolParams* sT, const FrameTable& ft, const TileFrames& tf, int y,
                                 int l, float3 gp, const ContactGeom& c, bool contact_frame, float3 gD, float3 gcv,
-                                float gdist, float (*red)[2][14], const float* __restrict__ poses, int env, int j,
+                                float gdist, float (*red)[2][15], const float* __restrict__ poses, int env, int j,
                                 float* __restrict__ pose_adj) {
   if (contact_frame) {
     FrameAdj a0 = frame_adj_zero(), a1 = frame_adj_zero();
@@ -133,9 +133,7 @@ DSK_DEV void frame_pose_adjoint(const SimConst& k, const ToolParams* sT, const F
       // D = qrot(q0, n/L)
       float3 Nl = (1.f / c.L) * c.nraw, gNl = f3(0, 0, 0);
       qrot_adj(tf.F0[y].q, Nl, gD, a0.q, gNl);
-      float3 gpl = local_normal_adj_cached(T, kind, c.pl, c.nraw, c.L, gNl);
-      // dist = sdf(pl)
-      gpl += gdist * local_sdf_grad(T, kind, c.pl);
+      float3 gpl = contact_local_adj(T, kind, tf.F0[y].aux, c.pl, c.nraw, c.L, gNl, gdist, a0.aux);   // + dist = sdf(pl)
       // cv = (qrot(q1, pl) + o1 - p) / dt
       float3 gnp = (1.f / k.dt) * gcv;
       a1.o += gnp;
@@ -144,10 +142,10 @@ DSK_DEV void frame_pose_adjoint(const SimConst& k, const ToolParams* sT, const F
       float3 unused = f3(0, 0, 0);
       inv_trans_adj(tf.F0[y], gp, gpl, a0, unused);
     }
-    float vals[14] = {a0.o.x, a0.o.y, a0.o.z, a0.q.w, a0.q.x, a0.q.y, a0.q.z,
-                      a1.o.x, a1.o.y, a1.o.z, a1.q.w, a1.q.x, a1.q.y, a1.q.z};
+    float vals[15] = {a0.o.x, a0.o.y, a0.o.z, a0.q.w, a0.q.x, a0.q.y, a0.q.z,
+                      a1.o.x, a1.o.y, a1.o.z, a1.q.w, a1.q.x, a1.q.y, a1.q.z, a0.aux};
 #pragma unroll
-    for (int q = 0; q < 14; q++) {
+    for (int q = 0; q < 15; q++) {
       float s = warp_sum(vals[q]);
       if ((l & 31) == 0) red[y][l >> 5][q] = s;
     }
@@ -155,10 +153,12 @@ DSK_DEV void frame_pose_adjoint(const SimConst& k, const ToolParams* sT, const F
   __syncthreads();
   if (l == 0 && contact_frame) {
     FrameAdj a0, a1;
-    float r[14];
-    for (int q = 0; q < 14; q++) r[q] = red[y][0][q] + red[y][1][q];
+    float r[15];
+    for (int q = 0; q < 15; q++) r[q] = red[y][0][q] + red[y][1][q];
     a0.o = f3(r[0], r[1], r[2]); a0.q.w = r[3]; a0.q.x = r[4]; a0.q.y = r[5]; a0.q.z = r[6];
     a1.o = f3(r[7], r[8], r[9]); a1.q.w = r[10]; a1.q.x = r[11]; a1.q.y = r[12]; a1.q.z = r[13];
+    a0.aux = r[14];
+    a1.aux = 0.f;
     int t = ft.tool[y];
     const float* pa = poses + ((size_t)(env * (k.S + 1) + j) * k.K + t) * 8;
     PoseAdj g0 = pose_adj_zero(), g1 = pose_adj_zero();
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
   __shared__ TileFrames tf;
   __shared__ ContactGeom geo[MAX_FRAMES][GRID_NODES];
   __shared__ ContactGeomAdj gadj[MAX_FRAMES][GRID_NODES];
-  __shared__ float red[MAX_FRAMES][2][14];
+  __shared__ float red[MAX_FRAMES][2][15];
   __shared__ int any_contact[MAX_FRAMES];
   const int l = threadIdx.x, y = threadIdx.y;
   int n_active = *count;
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
   const ToolParams* sT = tp.T;   // tool parameters and the frame table arrive as kernel parameters: no setup barrier
   const FrameTable& ft = tp.ft;
   __shared__ TileFrames tf;
-  __shared__ float red[MAX_FRAMES][2][14];
+  __shared__ float red[MAX_FRAMES][2][15];
   const int l = threadIdx.x, y = threadIdx.y;
   int n_active = min(*count, sc.cap);
   for (int it = blockIdx.x; it < n_active; it += gridDim.x) {
@@ -414,9 +414,7 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4)
         // D = qrot(q0, n/L)
         float3 Nl = (1.f / c.L) * c.nraw, gNl = f3(0, 0, 0);
         qrot_adj(wf[w].F0[f].q, Nl, gD, a0.q, gNl);
-        float3 gpl = local_normal_adj_cached(T, kind, c.pl, c.nraw, c.L, gNl);
-        // dist = sdf(pl)
-        gpl += gdist * local_sdf_grad(T, kind, c.pl);
+        float3 gpl = contact_local_adj(T, kind, wf[w].F0[f].aux, c.pl, c.nraw, c.L, gNl, gdist, a0.aux);   // + dist = sdf(pl)
         // cv = (qrot(q1, pl) + o1 - p) / dt
         float3 gnp = (1.f / k.dt) * gcv;
         a1.o += gnp;
@@ -425,13 +423,15 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4)
         float3 unused = f3(0, 0, 0);
         inv_trans_adj(wf[w].F0[f], gp, gpl, a0, unused);
       }
-      float vals[14] = {a0.o.x, a0.o.y, a0.o.z, a0.q.w, a0.q.x, a0.q.y, a0.q.z,
-                        a1.o.x, a1.o.y, a1.o.z, a1.q.w, a1.q.x, a1.q.y, a1.q.z};
+      float vals[15] = {a0.o.x, a0.o.y, a0.o.z, a0.q.w, a0.q.x, a0.q.y, a0.q.z,
+                        a1.o.x, a1.o.y, a1.o.z, a1.q.w, a1.q.x, a1.q.y, a1.q.z, a0.aux};
 #pragma unroll
-      for (int q = 0; q < 14; q++) vals[q] = warp_sum(vals[q]);
+      for (int q = 0; q < 15; q++) vals[q] = warp_sum(vals[q]);
       if (lane == 0) {
         a0.o = f3(vals[0], vals[1], vals[2]); a0.q.w = vals[3]; a0.q.x = vals[4]; a0.q.y = vals[5]; a0.q.z = vals[6];
         a1.o = f3(vals[7], vals[8], vals[9]); a1.q.w = vals[10]; a1.q.x = vals[11]; a1.q.y = vals[12]; a1.q.z = vals[13];
+        a0.aux = vals[14];
+        a1.aux = 0.f;
         int t = ft.tool[f];
         const float* pa = poses + ((size_t)(env * (k.S + 1) + j) * k.K + t) * 8;
         PoseAdj g0 = pose_adj_zero(), g1 = pose_adj_zero();
@@ -687,7 +687,7 @@ __global__ void __launch_bounds__(KINADJ_CTA)
       ga[4] += gu[4] * (T.action_scale[4] / fs);
       ga[5] += gu[5] * (T.action_scale[5] / fs);
     }
-    if (is_gripper(T.type)) ga[6] += gu[6] * (T.action_scale[6] / fs);
+    if (has_gap(T.type)) ga[6] += gu[6] * (T.action_scale[6] / fs);
   }
 }
 

@@ -440,12 +440,22 @@ struct ContactGeom {   // per (node, frame), shared memory
 DSK_DEV void contact_geometry(const ToolParams& T, int kind, const Frame& F0, const Frame& F1, float3 p, float dt,
                               ContactGeom& g) {
   float3 pl = inv_trans(F0, p);
-  float dist = local_sdf(T, kind, pl);
+  float dist;
+  float3 pn = pl;     // point and shape the normal is taken at
+  int nk = kind;
+  if (kind == SDF_CHOPSTICKS) {   // primitives.py:245-261: min of the two sticks, the nearer one's normal
+    ChopEval c = chop_eval(T, F0.aux, pl);
+    dist = tmin(c.a, c.b);
+    pn = c.a <= c.b ? c.pa : c.pb;
+    nk = SDF_CAPSULE;
+  } else {
+    dist = local_sdf(T, kind, pl);
+  }
   float influence;
   if (contact_active(dist, T.softness, influence)) {
     g.influence = influence;
     float L;
-    float3 n = local_normal_raw(T, kind, pl, L);
+    float3 n = local_normal_raw(T, nk, pn, L);
     g.D = qrot_rn(F0.q, f3(__fdiv_rn(n.x, L), __fdiv_rn(n.y, L), __fdiv_rn(n.z, L)));   // primive_base.py:80-85
     // collider_v (primive_base.py:87-94): the relative position IS the local point
     float3 np = add3_rn(qrot_rn(F1.q, pl), F1.o);

@@ -61,15 +61,18 @@ DSK_DEV Pose load_pose(const float* s) {
 struct Frame {
   float3 o;
   Q4 q;
+  float aux;   // shape parameter that lives in the pose: gap[f] of a Chopsticks tool frame (0 otherwise)
 };
 struct FrameAdj {
   float3 o;
   Q4 q;
+  float aux;
 };
 DSK_DEV FrameAdj frame_adj_zero() {
   FrameAdj a;
   a.o = f3(0, 0, 0);
   a.q.w = a.q.x = a.q.y = a.q.z = 0.f;
+  a.aux = 0.f;
   return a;
 }
 
@@ -78,7 +81,10 @@ DSK_DEV FrameAdj frame_adj_zero() {
 // the rotation, and the rotation adjoint it produces is zero to the same rounding.
 // SDF_CYLINDER (primitives.py:302-336): T.h = radial, T.r = axial half extent.  SDF_TORUS (primitives.py:337-365):
 // major radius tx in T.h, minor radius ty in T.r.  Both have analytic normals.
-enum { SDF_CAPSULE = 0, SDF_BOX = 1, SDF_KNIFE = 2, SDF_SPHERE = 3, SDF_CYLINDER = 4, SDF_TORUS = 5 };
+// SDF_CHOPSTICKS (primitives.py:245-261): two capsules at -+gap/2 along local x, shifted by h/2 along local y, inside the ONE
+// tool frame; sdf = min of the two, normal = the nearer one's.  The gap travels in Frame::aux; the local_* functions are never
+// called with this kind -- the frame-level functions pick the stick and call them with SDF_CAPSULE on the shifted point.
+enum { SDF_CAPSULE = 0, SDF_BOX = 1, SDF_KNIFE = 2, SDF_SPHERE = 3, SDF_CYLINDER = 4, SDF_TORUS = 5, SDF_CHOPSTICKS = 6 };
 // the local shape of a tool's contact frame(s): the tool itself, or one jaw of a Gripper (box jaws, primitives.py:475-483)
 // / Gripper2 (capsule jaws, primitives.py:607-615)
 DSK_DEV int sdf_kind(int tool_type) {
@@ -91,11 +97,14 @@ DSK_DEV int sdf_kind(int tool_type) {
     case DSK_TOOL_SPHERE: return SDF_SPHERE;
     case DSK_TOOL_CYLINDER: return SDF_CYLINDER;
     case DSK_TOOL_TORUS: return SDF_TORUS;
+    case DSK_TOOL_CHOPSTICKS: return SDF_CHOPSTICKS;
     default: return SDF_BOX;   // Box, Gripper
   }
 }
 // tools with two jaws applied sequentially, a gap state and a 7-D action (primitives.py:428, :576)
 DSK_DEV bool is_gripper(int tool_type) { return tool_type == DSK_TOOL_GRIPPER || tool_type == DSK_TOOL_GRIPPER2; }
+// tools with a gap state, an 8-float state and a 7-D action: the grippers and Chopsticks (primitives.py:218)
+DSK_DEV bool has_gap(int tool_type) { return is_gripper(tool_type) || tool_type == DSK_TOOL_CHOPSTICKS; }
 DSK_DEV bool is_rollingpin(int tool_type) { return tool_type == DSK_TOOL_ROLLINGPIN_EXT || tool_type == DSK_TOOL_ROLLINGPIN; }
 
 // ---- local SDFs (value) ----------------------------------------------------------------------
@@ -358,26 +367,86 @@ DSK_DEV void inv_trans_adj(const Frame& F, float3 p, float3 gpl, FrameAdj& gF, f
   gp += gd;
 }
 
+// Chopsticks: the two candidate points in capsule coordinates and their signed distances (primitives.py:245-250)
+struct ChopEval {
+  float3 pa, pb;
+  float a, b;
+};
+DSK_DEV ChopEval chop_eval(const ToolParams& T, float aux, float3 pl) {
+  ChopEval c;
+  float y = sub_rn(pl.y, -T.half_h);            // grid_pos - (0, -h/2, 0)
+  float half = __fdiv_rn(aux, 2.f);
+  c.pa = f3(sub_rn(pl.x, half), y, pl.z);       // p - delta
+  c.pb = f3(add_rn(pl.x, half), y, pl.z);       // p + delta
+  c.a = local_sdf(T, SDF_CAPSULE, c.pa);
+  c.b = local_sdf(T, SDF_CAPSULE, c.pb);
+  return c;
+}
 DSK_DEV float frame_sdf(const ToolParams& T, int kind, const Frame& F, float3 p) {
+  if (kind == SDF_CHOPSTICKS) {
+    ChopEval c = chop_eval(T, F.aux, inv_trans(F, p));
+    return tmin(c.a, c.b);
+  }
   return local_sdf(T, kind, inv_trans(F, p));
 }
 DSK_DEV void frame_sdf_adj(const ToolParams& T, int kind, const Frame& F, float3 p, float gd, FrameAdj& gF,
                            float3& gp) {
   float3 pl = inv_trans(F, p);
+  if (kind == SDF_CHOPSTICKS) {   // min(a, b): a gets the adjoint iff a < b
+    ChopEval c = chop_eval(T, F.aux, pl);
+    bool first = c.a < c.b;
+    float3 g = gd * local_sdf_grad(T, SDF_CAPSULE, first ? c.pa : c.pb);
+    gF.aux += (first ? -0.5f : 0.5f) * g.x;
+    inv_trans_adj(F, p, g, gF, gp);
+    return;
+  }
   float3 g = gd * local_sdf_grad(T, kind, pl);
   inv_trans_adj(F, p, g, gF, gp);
 }
 DSK_DEV float3 frame_normal(const ToolParams& T, int kind, const Frame& F, float3 p) {  // primive_base.py:80-85
+  if (kind == SDF_CHOPSTICKS) {   // primitives.py:253-261: the nearer stick's normal (a <= b)
+    ChopEval c = chop_eval(T, F.aux, inv_trans(F, p));
+    return qrot_rn(F.q, local_normal(T, SDF_CAPSULE, c.a <= c.b ? c.pa : c.pb));
+  }
   return qrot_rn(F.q, local_normal(T, kind, inv_trans(F, p)));
 }
 DSK_DEV void frame_normal_adj(const ToolParams& T, int kind, const Frame& F, float3 p, float3 gD, FrameAdj& gF,
                               float3& gp) {
   float3 pl = inv_trans(F, p);
+  if (kind == SDF_CHOPSTICKS) {
+    ChopEval c = chop_eval(T, F.aux, pl);
+    bool first = c.a <= c.b;
+    float3 ps = first ? c.pa : c.pb;
+    float3 Nl = local_normal(T, SDF_CAPSULE, ps);
+    float3 gNl = f3(0, 0, 0);
+    qrot_adj(F.q, Nl, gD, gF.q, gNl);
+    float3 gpl = local_normal_adj(T, SDF_CAPSULE, ps, gNl);
+    gF.aux += (first ? -0.5f : 0.5f) * gpl.x;
+    inv_trans_adj(F, p, gpl, gF, gp);
+    return;
+  }
   float3 Nl = local_normal(T, kind, pl);
   float3 gNl = f3(0, 0, 0);
   qrot_adj(F.q, Nl, gD, gF.q, gNl);
   float3 gpl = local_normal_adj(T, kind, pl, gNl);
   inv_trans_adj(F, p, gpl, gF, gp);
+}
+// adjoint of the local part of a contact's geometry -- normal N = n / L at the point the forward pass took it and
+// dist = sdf -- w.r.t. the tool-local node position pl (and, for Chopsticks, the gap in Frame::aux); n, L cached by
+// contact_geometry.  Shared by the grid_op.grad kernels and the CPU twin.
+DSK_DEV float3 contact_local_adj(const ToolParams& T, int kind, float aux, float3 pl, float3 nraw, float L, float3 gNl,
+                                 float gdist, float& gaux) {
+  if (kind == SDF_CHOPSTICKS) {
+    ChopEval e = chop_eval(T, aux, pl);
+    bool fn = e.a <= e.b, fd = e.a < e.b;   // normal: the select of primitives.py:259; sdf: min(a, b) -> a iff a < b
+    float3 g1 = local_normal_adj_cached(T, SDF_CAPSULE, fn ? e.pa : e.pb, nraw, L, gNl);
+    float3 g2 = gdist * local_sdf_grad(T, SDF_CAPSULE, fd ? e.pa : e.pb);
+    gaux += (fn ? -0.5f : 0.5f) * g1.x + (fd ? -0.5f : 0.5f) * g2.x;
+    return g1 + g2;
+  }
+  float3 gpl = local_normal_adj_cached(T, kind, pl, nraw, L, gNl);
+  gpl += gdist * local_sdf_grad(T, kind, pl);
+  return gpl;
 }
 // collider_v, primive_base.py:87-94
 DSK_DEV float3 frame_collider_v(const Frame& F0, const Frame& F1, float3 p, float dt) {
@@ -490,6 +559,7 @@ DSK_DEV Frame tool_frame(const Pose& P) {
   Frame F;
   F.o = P.p;
   F.q = P.q;
+  F.aux = P.gap;   // read by the Chopsticks shape only
   return F;
 }
 DSK_DEV Frame jaw_frame(const Pose& P, float flag) {  // Gripper.get_pos, primitives.py:471-473
@@ -497,6 +567,7 @@ DSK_DEV Frame jaw_frame(const Pose& P, float flag) {  // Gripper.get_pos, primit
   float off = mul_rn(__fdiv_rn(P.gap, 2.f), flag);
   F.o = add3_rn(P.p, qrot_rn(P.q, f3(off, 0.f, 0.f)));
   F.q = P.q;
+  F.aux = 0.f;
   return F;
 }
 DSK_DEV void jaw_frame_adj(const Pose& P, float flag, const FrameAdj& gF, PoseAdj& gP) {
@@ -516,6 +587,7 @@ DSK_DEV void tool_frame_adj(const FrameAdj& gF, PoseAdj& gP) {
   gP.q.x += gF.q.x;
   gP.q.y += gF.q.y;
   gP.q.z += gF.q.z;
+  gP.gap += gF.aux;   // non-zero for Chopsticks only
 }
 
 // Primitive.collide / Gripper.collide for one tool at one grid node
@@ -640,7 +712,7 @@ DSK_DEV Pose tool_fk_inc(const ToolParams& T, const Pose& P, const ToolVel& u, c
     x_dir.y = dy;
     N.q = qmul(r.a, qmul(P.q, r.b));
     step = x_dir;
-  } else if (is_gripper(T.type)) {
+  } else if (has_gap(T.type)) {   // Chopsticks (primitives.py:230-234) has no upper clamp: max_gap = +inf (fill_tool)
     N.gap = tmin(tmax(P.gap - u.gap_vel, T.min_gap), T.max_gap);
     N.q = qmul(P.q, r.a);
   } else {
@@ -663,7 +735,7 @@ DSK_DEV Pose tool_fk(const ToolParams& T, const Pose& P, const ToolVel& u) {
     x_dir.y = dy;
     N.q = qmul(w2quat(f3(0.f, -dth, 0.f)), qmul(P.q, w2quat(f3(0.f, dw, 0.f))));
     step = x_dir;
-  } else if (is_gripper(T.type)) {
+  } else if (has_gap(T.type)) {
     N.gap = tmin(tmax(P.gap - u.gap_vel, T.min_gap), T.max_gap);
     N.q = qmul(P.q, w2quat(u.w));
   } else {
@@ -719,7 +791,7 @@ DSK_DEV void tool_fk_adj(const ToolParams& T, const Pose& P, const ToolVel& u, c
     w2quat_adj(f3(0.f, dw, 0.f), gqb, gb);
     gu.v.y += -ga.y;
     gu.v.x += gb.y;
-  } else if (is_gripper(T.type)) {
+  } else if (has_gap(T.type)) {
     gu.v += gstep;
     float a = P.gap - u.gap_vel;
     float m1 = tmax(a, T.min_gap);
@@ -738,7 +810,7 @@ DSK_DEV void tool_fk_adj(const ToolParams& T, const Pose& P, const ToolVel& u, c
     qmul_adj(qw, P.q, gN.q, gqw, gP.q);
     w2quat_adj(u.w, gqw, gu.w);
   }
-  if (!is_gripper(T.type)) gP.gap += gN.gap;
+  if (!has_gap(T.type)) gP.gap += gN.gap;
 }
 DSK_DEV ToolVel action_to_vel(const ToolParams& T, const float* a, int S) {  // set_velocity, primive_base.py:260-268
   ToolVel u;
@@ -749,7 +821,7 @@ DSK_DEV ToolVel action_to_vel(const ToolParams& T, const float* a, int S) {  // 
   if (T.action_dim > 0) {
     u.v = f3(a[0] * T.action_scale[0] / fs, a[1] * T.action_scale[1] / fs, a[2] * T.action_scale[2] / fs);
     if (T.action_dim > 3) u.w = f3(a[3] * T.action_scale[3] / fs, a[4] * T.action_scale[4] / fs, a[5] * T.action_scale[5] / fs);
-    if (is_gripper(T.type)) u.gap_vel = a[6] * T.action_scale[6] / fs;
+    if (has_gap(T.type)) u.gap_vel = a[6] * T.action_scale[6] / fs;
   }
   return u;
 }

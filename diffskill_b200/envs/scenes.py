@@ -115,6 +115,17 @@ GRIPPER2_SYNTHETIC = dict(
     ENV=dict(env_name='Gripper2-synthetic'),
 )
 
+# plb/envs/chopsticks.yml (PlasticineLab's Chopsticks-v1): a rope-like box and the two-stick tool
+CHOPSTICKS = dict(
+    SIMULATOR=dict(n_particles=10000, yield_stress=200., ground_friction=0., gravity=(0, -5, 0)),
+    SHAPES=[dict(shape='box', width=(0.04, 0.04, 0.6), init_pos=(0.5, 0.02, 0.5), color=100)],
+    PRIMITIVES=[
+        dict(shape='Chopsticks', h=0.2, r=0.02, init_pos=(0.5, 0.15, 0.5), init_rot=(1., 0., 0., 0.), init_gap=0.06,
+             color=(0.8, 0.8, 0.8), friction=10., action=dict(dim=7, scale=(0.02, 0.02, 0.02, 0.04, 0.04, 0.04, 0.02))),
+    ],
+    ENV=dict(env_name='Chopsticks-v1'),
+)
+
 SCENES = {
     'LiftSpread-v1': LIFT_SPREAD,
     'GatherMove-v1': GATHER_MOVE,
@@ -124,4 +135,5 @@ SCENES = {
     'Torus-v1': TORUS,
     'Rope-v1': ROPE,
     'Gripper2-synthetic': GRIPPER2_SYNTHETIC,
+    'Chopsticks-v1': CHOPSTICKS,
 }

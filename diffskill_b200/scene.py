@@ -14,11 +14,12 @@ import numpy as np
 from .config import CfgNode, load
 
 (TOOL_CAPSULE, TOOL_ROLLINGPIN_EXT, TOOL_BOX, TOOL_GRIPPER, TOOL_KNIFE, TOOL_SPHERE, TOOL_ROLLINGPIN, TOOL_GRIPPER2,
- TOOL_CYLINDER, TOOL_TORUS) = range(10)
+ TOOL_CYLINDER, TOOL_TORUS, TOOL_CHOPSTICKS) = range(11)
 TOOL_TYPE = {'Capsule': TOOL_CAPSULE, 'RollingPinExt': TOOL_ROLLINGPIN_EXT, 'Box': TOOL_BOX,
              'Gripper': TOOL_GRIPPER, 'Knife': TOOL_KNIFE, 'Sphere': TOOL_SPHERE, 'RollingPin': TOOL_ROLLINGPIN,
-             'Gripper2': TOOL_GRIPPER2, 'Cylinder': TOOL_CYLINDER, 'Torus': TOOL_TORUS}
-GRIPPER_LIKE = (TOOL_GRIPPER, TOOL_GRIPPER2)      # two jaws, gap state, 8-float state (primitives.py:428, :576)
+             'Gripper2': TOOL_GRIPPER2, 'Cylinder': TOOL_CYLINDER, 'Torus': TOOL_TORUS, 'Chopsticks': TOOL_CHOPSTICKS}
+GRIPPER_LIKE = (TOOL_GRIPPER, TOOL_GRIPPER2)      # two jaws applied one after the other (primitives.py:428, :576)
+HAS_GAP = GRIPPER_LIKE + (TOOL_CHOPSTICKS,)       # gap state, 8-float state, 7-D action (+ Chopsticks, primitives.py:218)
 NUM_COLLISION_POINTS = 600  # mpm_simulator.py:59
 
 
@@ -42,10 +43,10 @@ def _primitive_defaults(shape):
         d.update(tx=0.2, ty=0.1)
     elif shape == 'Knife':
         d.update(h=(0.1, 0.1), size=(0.1, 0.1, 0.1), prot=(1.0, 0.0, 0.0, 0.0))
+    elif shape == 'Chopsticks':                                # primitives.py:282-289
+        d.update(h=0.06, r=0.03, minimal_gap=0.06, init_gap=0.06)
     else:
-        # Chopsticks (primitives.py:218-300): its SDF depends on gap[f] inside the tool frame while collider_v ignores the
-        # gap -- it does not fit the (frame, local shape) contact model of the grid kernels and no DiffSkill env uses it
-        raise NotImplementedError(f"tool shape {shape!r} is not built (SURVEY.md section 8f row 4)")
+        raise NotImplementedError(f"tool shape {shape!r} is not a PlasticineLab primitive")
     return CfgNode(d)
 
 
@@ -72,7 +73,7 @@ class ToolSpec:
 
     @property
     def state_dim(self):
-        return 8 if self.type_id in GRIPPER_LIKE else 7
+        return 8 if self.type_id in HAS_GAP else 7
 
 
 def tool_from_cfg(c) -> ToolSpec:
@@ -97,6 +98,11 @@ def tool_from_cfg(c) -> ToolSpec:
         spec.minimal_gap, spec.maximal_gap = float(cfg.minimal_gap), float(cfg.maximal_gap)
         init = init + (float(cfg.init_gap),)
         assert adim == 7, "Gripper2 needs a 7-D action (primitives.py:594-601)"
+    elif t == TOOL_CHOPSTICKS:                                 # primitives.py:218-289: no maximal gap
+        spec.h, spec.r = float(cfg.h), float(cfg.r)
+        spec.minimal_gap, spec.maximal_gap = float(cfg.minimal_gap), 1e30
+        init = init + (float(cfg.init_gap),)
+        assert adim == 7, "Chopsticks needs a 7-D action (primitives.py:228)"
     elif t == TOOL_SPHERE:
         spec.radius = float(cfg.radius)
     elif t == TOOL_BOX:
@@ -176,6 +182,7 @@ def scene_from_cfg(cfg) -> SceneSpec:
     for i, ti in enumerate(tools):
         for j in range(len(tools)):
             if j < len(ti.collision_group) and ti.collision_group[j] > 0:
+                assert ti.type_id != TOOL_CHOPSTICKS, "Chopsticks as the moving tool of a tool-tool collision pair is not built"
                 assert tools[j].type_id in (TOOL_BOX, TOOL_GRIPPER, TOOL_KNIFE), \
                     "tool-tool collision needs a box-like obstacle (mpm_simulator.py:291)"
                 pairs.append((i, j))

@@ -79,7 +79,7 @@ class Loss:
         # [B, capacity, ncols] table: two per 8-dof tool (function.py:23-27), one otherwise
         self.primitives, self._cols, k = [], [], 0
         for p in sim.primitives:
-            w = 2 if p.state_dim == 8 else 1
+            w = getattr(p, 'dist_cols', 2 if p.state_dim == 8 else 1)
             if p.action_dim > 0:
                 self.primitives.append(p)
                 self._cols.append((k, k + w))

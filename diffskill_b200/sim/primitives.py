@@ -297,6 +297,31 @@ class Gripper2(Capsule):
         super().set_state(f, state, env)
 
 
+class Chopsticks(Capsule):
+    """primitives.py:218-300: two capsules (h, r) at -+gap/2 along local x inside ONE tool frame -- sdf = min, the nearer
+    stick's normal, the base class's single contact (collider velocity from the tool pose alone) -- with the gripper's
+    kinematics (right-multiplied rotation, gap' = max(gap - gap_vel, minimal_gap)) and 7-D action."""
+    shape = 'Chopsticks'
+    state_dim = 8
+    dist_cols = 1                                               # one contact-distance column (sdf = min of the sticks)
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        zero = self._zero_grads
+        self.gap = ToolFrameField(self, slice(7, 8), zero)
+        self.gap_vel = type('F', (), {'grad': ZeroOnFillGrad(zero)})()
+        self.minimal_gap = self.cfg.minimal_gap
+        assert self.action_dim == 7                             # primitives.py:228: 3 linear, 3 angle, 1 for grasp
+
+    @property
+    def init_state(self):
+        return tuple(self.cfg.init_pos) + tuple(self.cfg.init_rot) + (self.cfg.init_gap,)
+
+    def set_state(self, f, state, env=None):
+        assert len(state) == 8                                  # primitives.py:274
+        super().set_state(f, state, env)
+
+
 class Cylinder(Primitive):
     """primitives.py:302-336 (cfg.h = radial, cfg.r = axial half extent); the base class's zero init_points."""
     shape = 'Cylinder'
@@ -332,7 +357,7 @@ class Knife(Primitive):
         return action
 
 
-_SHAPES = {c.shape: c for c in (Sphere, Capsule, RollingPin, RollingPinExt, Box, Gripper, Gripper2, Cylinder, Torus, Knife)}
+_SHAPES = {c.shape: c for c in (Sphere, Capsule, RollingPin, RollingPinExt, Box, Gripper, Gripper2, Cylinder, Torus, Knife, Chopsticks)}
 
 
 class Primitives:

@@ -98,7 +98,7 @@ class TaichiEnv:
         k = 0
         for p in self.primitives:
             self.dists_start_idx.append(k)
-            k += 2 if p.state_dim == 8 else 1      # function.py:23-27: two distance columns per 8-dof tool
+            k += getattr(p, 'dist_cols', 2 if p.state_dim == 8 else 1)   # function.py:23-27: two distance columns per gripper
         self.dists_start_idx.append(k)
 
     def set_copy(self, is_copy: bool):

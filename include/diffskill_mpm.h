@@ -47,7 +47,8 @@ enum dsk_tool_type {
   DSK_TOOL_ROLLINGPIN = 6,     /* primitives.py:101 (capsule; RollingPinExt kinematics without the w[0] slide) */
   DSK_TOOL_GRIPPER2 = 7,       /* primitives.py:576 (Gripper with capsule jaws `h`, `r`) */
   DSK_TOOL_CYLINDER = 8,       /* primitives.py:302 (`h` = radial, `r` = axial half extent, as the reference names them) */
-  DSK_TOOL_TORUS = 9           /* primitives.py:337 (major radius cfg.tx in `h`, minor radius cfg.ty in `r`) */
+  DSK_TOOL_TORUS = 9,          /* primitives.py:337 (major radius cfg.tx in `h`, minor radius cfg.ty in `r`) */
+  DSK_TOOL_CHOPSTICKS = 10     /* primitives.py:218 (two capsules `h`, `r` at -+gap/2 inside one tool frame; 8-float state, 7-D action) */
 };
 
 enum dsk_tool_param {

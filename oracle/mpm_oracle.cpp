@@ -180,8 +180,11 @@ inline S length14(const V3<S>& x) {  // primitives.py:13-15
 // ----------------------------------------------------------------------------
 // tools
 // ----------------------------------------------------------------------------
-inline bool is_gripper(int type) {  // tools with two jaws, a gap state and an 8-float state (primitives.py:428, :576)
+inline bool is_gripper(int type) {  // tools with two jaws applied one after the other (primitives.py:428, :576)
   return type == ORC_TOOL_GRIPPER || type == ORC_TOOL_GRIPPER2;
+}
+inline bool has_gap(int type) {  // tools with a gap state, an 8-float state and a 7-D action (+ Chopsticks, primitives.py:218)
+  return is_gripper(type) || type == ORC_TOOL_CHOPSTICKS;
 }
 template <class T>
 struct ToolC {  // constants rounded to T as Taichi rounds python floats into fields/constants
@@ -327,14 +330,39 @@ inline V3<S> normal2(const ToolC<T>& c, const Pose<S>& P, const V3<S>& p, int fl
   b.type = c.type == ORC_TOOL_GRIPPER2 ? ORC_TOOL_CAPSULE : ORC_TOOL_BOX;  // primitives.py:612-615: Capsule._normal
   return qrot(P.rot, local_normal(b, inv_trans(p, gripper_pos(P, flag), P.rot)));
 }
+// Chopsticks (primitives.py:245-261): two capsules at -+gap/2 along local x, shifted by h/2 along local y, inside the ONE
+// tool frame; sdf = min of the two, normal = the nearer one's (a <= b)
+template <class S, class T>
+inline void chopsticks_points(const ToolC<T>& c, const Pose<S>& P, const V3<S>& p, V3<S>& pa, V3<S>& pb) {
+  V3<S> g = inv_trans(p, P.pos, P.rot);
+  V3<S> q{{g[0], g[1] - (-c.h / T(2)), g[2]}};   // grid_pos - (0, -h/2, 0)
+  S half = P.gap / T(2);
+  pa = V3<S>{{q[0] - half, q[1], q[2]}};          // p - delta
+  pb = V3<S>{{q[0] + half, q[1], q[2]}};          // p + delta
+}
 template <class S, class T>
 inline S tool_sdf(const ToolC<T>& c, const Pose<S>& P, const V3<S>& p) {
+  if (c.type == ORC_TOOL_CHOPSTICKS) {
+    V3<S> pa, pb;
+    chopsticks_points(c, P, p, pa, pb);
+    return s_min(length14(capsule_p2(c, pa)) - c.r, length14(capsule_p2(c, pb)) - c.r);
+  }
   if (is_gripper(c.type)) return s_min(sdf2(c, P, p, -1), sdf2(c, P, p, 1));  // primitives.py:485-487
   if (c.type == ORC_TOOL_SPHERE) return length14(p - P.pos) - c.radius;               // primitives.py:28-30
   return local_sdf(c, inv_trans(p, P.pos, P.rot));                                      // primive_base.py:75-78
 }
 template <class S, class T>
 inline V3<S> tool_normal(const ToolC<T>& c, const Pose<S>& P, const V3<S>& p) {
+  if (c.type == ORC_TOOL_CHOPSTICKS) {  // primitives.py:253-261
+    V3<S> pa, pb;
+    chopsticks_points(c, P, p, pa, pb);
+    V3<S> a2 = capsule_p2(c, pa), b2 = capsule_p2(c, pb);
+    S la = length14(a2), lb = length14(b2);
+    T m = val(la - c.r) <= val(lb - c.r) ? T(1) : T(0);
+    V3<S> r;
+    for (int i = 0; i < 3; i++) r[i] = m * (a2[i] / la) + (T(1) - m) * (b2[i] / lb);
+    return qrot(P.rot, r);
+  }
   if (is_gripper(c.type)) {  // primitives.py:489-496
     S a = sdf2(c, P, p, -1), b = sdf2(c, P, p, 1);
     V3<S> an = normal2(c, P, p, -1), bn = normal2(c, P, p, 1);
@@ -420,6 +448,9 @@ inline Pose<S> tool_fk(const ToolC<T>& c, const Pose<S>& P, const V3<S>& v, cons
     V3<S> a1{{S(T(0)), -dth, S(T(0))}}, a2{{S(T(0)), dw, S(T(0))}};
     N.rot = qmul(w2quat(a1), qmul(P.rot, w2quat(a2)));
     step = x_dir;
+  } else if (c.type == ORC_TOOL_CHOPSTICKS) {  // primitives.py:230-234: no upper clamp on the gap
+    N.gap = s_max(P.gap - gap_vel, c.min_gap);
+    N.rot = qmul(P.rot, w2quat(w));
   } else if (is_gripper(c.type)) {  // primitives.py:456-460
     N.gap = s_min(s_max(P.gap - gap_vel, c.min_gap), c.max_gap);
     N.rot = qmul(P.rot, w2quat(w));
@@ -1450,7 +1481,7 @@ struct Sim {
       for (int d = 0; d < 3; d++) t.vel[j * 3 + d] = a[d] * t.c.action_scale[d] / T(nsub);
       if (ad > 3)
         for (int d = 0; d < 3; d++) t.w[j * 3 + d] = a[d + 3] * t.c.action_scale[d + 3] / T(nsub);
-      if (is_gripper(t.c.type)) t.gap_vel[j] = a[6] * t.c.action_scale[6] / T(nsub);
+      if (has_gap(t.c.type)) t.gap_vel[j] = a[6] * t.c.action_scale[6] / T(nsub);
     }
   }
   void set_velocity_grad(int s, int nsub) {
@@ -1463,7 +1494,7 @@ struct Sim {
         for (int d = 0; d < 3; d++) ga[d] += t.g_vel[j * 3 + d] * (t.c.action_scale[d] / T(nsub));
         if (ad > 3)
           for (int d = 0; d < 3; d++) ga[d + 3] += t.g_w[j * 3 + d] * (t.c.action_scale[d + 3] / T(nsub));
-        if (is_gripper(t.c.type)) ga[6] += t.g_gap_vel[j] * (t.c.action_scale[6] / T(nsub));
+        if (has_gap(t.c.type)) ga[6] += t.g_gap_vel[j] * (t.c.action_scale[6] / T(nsub));
       }
     }
   }
@@ -1768,7 +1799,7 @@ void orc_copyframe(void* h, int src, int dst) {
     for (auto& t : S.tools) {
       for (int d = 0; d < 3; d++) t.pos[dst * 3 + d] = t.pos[src * 3 + d];
       for (int d = 0; d < 4; d++) t.rot[dst * 4 + d] = t.rot[src * 4 + d];
-      if (is_gripper(t.c.type)) t.gap[dst] = t.gap[src];
+      if (has_gap(t.c.type)) t.gap[dst] = t.gap[src];
     }
   });
 }
@@ -1836,7 +1867,7 @@ void orc_add_tool_grad(void* h, int f, int tool, const double* g8) {
     auto& t = S.tools[tool];
     add_in(t.g_pos, (size_t)f * 3, g8, 3);
     add_in(t.g_rot, (size_t)f * 4, g8 + 3, 4);
-    if (is_gripper(t.c.type)) add_in(t.g_gap, (size_t)f, g8 + 7, 1);
+    if (has_gap(t.c.type)) add_in(t.g_gap, (size_t)f, g8 + 7, 1);
   });
 }
 void orc_get_tool_vel_grad(void* h, int f, int tool, double* g7) {

@@ -35,7 +35,8 @@ enum orc_tool_type {
   ORC_TOOL_ROLLINGPIN = 6,     /* primitives.py:101 */
   ORC_TOOL_GRIPPER2 = 7,       /* primitives.py:576 (capsule jaws) */
   ORC_TOOL_CYLINDER = 8,       /* primitives.py:302 (h = radial, r = axial half extent) */
-  ORC_TOOL_TORUS = 9           /* primitives.py:337 (tx in h, ty in r) */
+  ORC_TOOL_TORUS = 9,          /* primitives.py:337 (tx in h, ty in r) */
+  ORC_TOOL_CHOPSTICKS = 10     /* primitives.py:218 (two capsules at +-gap/2 inside ONE tool frame) */
 };
 
 typedef struct orc_tool_cfg {

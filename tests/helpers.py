@@ -15,7 +15,7 @@ from diffskill_b200.shapes import Shapes  # noqa: E402
 # the three DiffSkill envs, then legacy PlasticineLab scenes that exercise the remaining tools:
 # Move-v1 Sphere, Rollingpin-v1 RollingPin, Torus-v1 Torus, Rope-v1 Sphere + Cylinder, Gripper2-synthetic Gripper2
 ENVS = ['LiftSpread-v1', 'GatherMove-v1', 'CutRearrange-v1', 'Move-v1', 'Rollingpin-v1', 'Torus-v1', 'Rope-v1',
-        'Gripper2-synthetic']
+        'Gripper2-synthetic', 'Chopsticks-v1']
 
 
 def small_dough(name, n, seed=0):
@@ -42,6 +42,10 @@ def small_dough(name, n, seed=0):
         # piece of rope pressed 9 mm into the side of the pillar (Cylinder radius 0.1 at z = 0.499), the two spheres
         # (moved by tool_start) touching it from the other side
         x = rng.uniform(-1, 1, (n, 3)) * np.array([0.05, 0.03, 0.02]) + np.array([0.392, 0.04, 0.61])
+    elif name == 'Chopsticks-v1':
+        # a piece of the rope between the two sticks (capsules spanning y in [pos.y - h, pos.y] at x = pos.x -+ gap/2, r = 0.02),
+        # 4 mm into each of them
+        x = rng.uniform(-1, 1, (n, 3)) * np.array([0.024, 0.02, 0.06]) + np.array([0.5, 0.05, 0.5])
     elif name == 'Gripper2-synthetic':
         # slab between the two capsule jaws (axis = world y, separated along world z), 5 mm into each
         x = rng.uniform(-1, 1, (n, 3)) * np.array([0.04, 0.03, 0.035]) + np.array([0.5, 0.06, 0.5])
@@ -77,6 +81,9 @@ def tool_start(name, scene):
     elif name == 'Rope-v1':
         st[0][:3] = (0.36, 0.04, 0.655)
         st[1][:3] = (0.42, 0.04, 0.655)
+    elif name == 'Chopsticks-v1':
+        st[0][:3] = (0.5, 0.17, 0.5)      # sticks reach down to y = -0.03 .. 0.17 around the rope piece
+        st[0][7] = 0.08
     elif name == 'Gripper2-synthetic':
         st[0][7] = 0.10
     return st

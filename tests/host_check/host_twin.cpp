@@ -53,7 +53,11 @@ static ToolParams make_tool_h(const dsk_tool_desc& d) {   // fill_tool() of engi
     T.bound_r = (float)std::sqrt(d.h * d.h + d.r * d.r);
   else if (d.type == DSK_TOOL_TORUS)
     T.bound_r = (float)(d.h + d.r);
-  else
+  else if (d.type == DSK_TOOL_CHOPSTICKS) {
+    T.max_gap = 1e30f;
+    double g = std::max(d.maximal_gap > 0 && d.maximal_gap < 1e3 ? d.maximal_gap : 0.0, 1.0);
+    T.bound_r = (float)std::sqrt((g / 2 + d.r) * (g / 2 + d.r) + (d.h + d.r) * (d.h + d.r));
+  } else
     T.bound_r = (float)std::sqrt(d.size[0] * d.size[0] + d.size[1] * d.size[1] + d.size[2] * d.size[2]);
   T.bound_r *= 1.001f;
   return T;
@@ -207,8 +211,7 @@ void hc_substep_grad(const dsk_config* cfg, int N, const float* x, const float* 
           FrameAdj a0 = frame_adj_zero(), a1 = frame_adj_zero();
           float3 Nl = (1.f / f.c.L) * f.c.nraw, gNl = f3(0, 0, 0);
           qrot_adj(f.F0.q, Nl, gD, a0.q, gNl);
-          float3 gpl = local_normal_adj_cached(Tt, kind, f.c.pl, f.c.nraw, f.c.L, gNl);
-          gpl += gdist * local_sdf_grad(Tt, kind, f.c.pl);
+          float3 gpl = contact_local_adj(Tt, kind, f.F0.aux, f.c.pl, f.c.nraw, f.c.L, gNl, gdist, a0.aux);
           float3 gnp = (1.f / k.dt) * gcv;
           a1.o += gnp;
           qrot_adj(f.F1.q, f.c.pl, gnp, a1.q, gpl);

@@ -19,7 +19,7 @@ import pytest
 
 from helpers import ENVS, small_dough, tool_start
 from diffskill_b200.engine import make_config
-from diffskill_b200.scene import GRIPPER_LIKE, TOOL_BOX, TOOL_GRIPPER, TOOL_KNIFE
+from diffskill_b200.scene import HAS_GAP, TOOL_BOX, TOOL_GRIPPER, TOOL_KNIFE
 from oracle import oracle as orc
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -65,7 +65,7 @@ def _setup(name):
         n[:3] += rng.normal(size=3) * 2e-4              # one substep of tool motion
         n[3:7] = q + rng.normal(size=4) * 2e-3
         n[3:7] /= np.linalg.norm(n[3:7])
-        if t.type_id in GRIPPER_LIKE:
+        if t.type_id in HAS_GAP:
             n[7] = s[7] - 3e-4
         st1.append(n)
     st0 = [np.asarray(s, np.float32).astype(np.float64) for s in st0]
@@ -177,19 +177,19 @@ def test_device_forward_kinematics_matches_oracle(name, hc):
                 ref[:3] = a[:3] * sc[:3] / np.float32(scene.substeps)
                 if t.action_dim > 3:
                     ref[3:6] = a[3:6] * sc[3:6] / np.float32(scene.substeps)
-                if t.type_id in GRIPPER_LIKE:
+                if t.type_id in HAS_GAP:
                     ref[6] = a[6] * sc[6] / np.float32(scene.substeps)
             assert np.abs(vel - ref).max() <= 1e-7 * max(np.abs(ref).max(), 1e-3)
             if trial % 2:               # also generic velocities in every slot (w of a 3-D tool is zero in practice)
                 vel = np.asarray(rng.normal(size=7) * 2e-3, np.float32)
-                if t.type_id not in GRIPPER_LIKE:
+                if t.type_id not in HAS_GAP:
                     vel[6] = 0
             st = st0[i].copy()
             if trial >= 10:             # start on a position limit: the clamp's adjoint rule
                 st[:3] = np.asarray(t.upper_bound if trial % 4 < 2 else t.lower_bound)
                 st = np.asarray(st, np.float32).astype(np.float64)
             g = np.asarray(rng.normal(size=8), np.float32)
-            if t.type_id not in GRIPPER_LIKE:
+            if t.type_id not in HAS_GAP:
                 g[7] = 0
             nxt = np.zeros(16, np.float32)
             gout = np.zeros(15, np.float32)
@@ -201,7 +201,7 @@ def test_device_forward_kinematics_matches_oracle(name, hc):
             assert np.abs(nxt[:8] - n64).max() <= max(3 * np.abs(n32 - n64).max(), 3e-7), (name, i, 'fk')
             assert np.abs(nxt[8:] - n64).max() <= max(3 * np.abs(n32 - n64).max(), 3e-7), (name, i, 'fk_inc')
             r, r32, r64 = gout, np.concatenate([gs32, gv32]), np.concatenate([gs64, gv64])
-            if t.type_id not in GRIPPER_LIKE:
+            if t.type_id not in HAS_GAP:
                 # tools without a gap pass g(gap) straight through (the state slot is carried, not used)
                 r[7] = r32[7] = r64[7] = 0
             for sl in (slice(0, 3), slice(3, 7), slice(7, 8), slice(8, 11), slice(11, 14), slice(14, 15)):
