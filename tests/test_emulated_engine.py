@@ -28,7 +28,7 @@ SUBSET = ('test_cell_index_and_sort_bit_exact or test_svd_matches_oracle or test
           'or (test_fine_grained_substeps_equal_whole_step and LiftSpread) '
           'or test_tool_tool_collision_projection '
           'or (test_substep_forward_parity and True and (LiftSpread or GatherMove or CutRearrange or Rope or Torus)) '
-          'or (test_substep_backward_parity and (LiftSpread or CutRearrange or Rope)) '
+          'or (test_substep_backward_parity and (LiftSpread or CutRearrange or Rope or Chopsticks)) '
           'or (test_against_committed_golden_fixture and (GatherMove or Rollingpin or Gripper2)) '
           'or (test_multi_step_action_gradient and (1-256-LiftSpread or 3-1-CutRearrange or 1-256-Rope)) '
           'or (test_multi_step_action_gradient_batched_layout and 1-0-GatherMove)')

@@ -60,7 +60,11 @@ def test_primitive_mirrors_unbound():
     assert a[0] == 0. and a[1] == pytest.approx(8.0)
     assert P[0].inv_action(np.zeros(7), np.zeros(7)) is None
     with pytest.raises(NotImplementedError):
-        Primitives([CfgNode(dict(shape='Chopsticks'))])
+        Primitives([CfgNode(dict(shape='Spatula'))])            # not a PlasticineLab primitive
+    Cs = Primitives([CfgNode(dict(shape='Chopsticks', action=dict(dim=7, scale=(0.02,) * 7)))])   # primitives.py:218-289
+    assert Cs.state_dims == [8] and Cs[0].init_state[-1] == 0.06 and (Cs[0].spec.h, Cs[0].spec.r) == (0.06, 0.03)
+    with pytest.raises(AssertionError):
+        Primitives([CfgNode(dict(shape='Chopsticks'))])         # assert self.action_dim == 7 (primitives.py:228)
     # the legacy PlasticineLab tools with the defaults of their default_config()
     L = Primitives([CfgNode(dict(shape=s)) for s in ('Sphere', 'RollingPin', 'Cylinder', 'Torus')]
                    + [CfgNode(dict(shape='Gripper2', action=dict(dim=7, scale=(0.01,) * 7)))])
