@@ -393,7 +393,10 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
   e->big = (size_t)c->n_envs * c->particle_capacity >= 24576;
   if (const char* v = getenv("DSK_FORCE_BIG")) e->big = atoi(v) != 0;
   if (const char* v = getenv("DSK_BIG_MINB")) e->minb_g2p2g = e->minb_g2p_adj = e->minb_p2g_adj = atoi(v);
-  if (const char* v = getenv("DSK_BIG_BLOCK")) e->big_block = atoi(v) == 64 ? 64 : 128;
+  if (const char* v = getenv("DSK_BIG_BLOCK")) {   // threads per CTA of the batched particle kernels: 64, 96 or 128
+    int b = atoi(v);
+    e->big_block = (b == 64 || b == 96) ? b : 128;
+  }
   if (const char* v = getenv("DSK_MINB_G2P2G")) e->minb_g2p2g = atoi(v);
   if (const char* v = getenv("DSK_MINB_G2P_ADJ")) e->minb_g2p_adj = atoi(v);
   if (const char* v = getenv("DSK_MINB_P2G_ADJ")) e->minb_p2g_adj = atoi(v);
