@@ -16,7 +16,12 @@ __global__ void __launch_bounds__(128, MINB)
           const int* __restrict__ npart, float4* __restrict__ G, TileTrack tt, const StepArgs* __restrict__ args,
           int q, const int* __restrict__ run_if, float* __restrict__ svd_out) {
   DSK_TL(k);
+  const int epoch = load_int_here(&args->epoch_base) + q + 1;   // loaded first: the tile tags are compared with it
   if (run_if && *run_if == 0) return;   // adjoint recompute is skipped when the grid tape of the step is complete
+  prefetch_cta(k, blockDim.x, [&](int col, int ncol) {
+    int t = prefetch_rows(fin, 0, FRAME_COMPS, k.stride, col, ncol, threadIdx.x, 0);
+    prefetch_rows(mat, 0, 3, k.stride, col, ncol, threadIdx.x, t);
+  });
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   int env = min(gid / k.Npad, k.B - 1), p = gid - env * k.Npad;   // a warp never straddles envs (Npad % 128 == 0)
   bool active = gid < k.stride && p < npart[env];
@@ -42,7 +47,7 @@ __global__ void __launch_bounds__(128, MINB)
   float3 ax = f3(k.dx * o.affine.m[0], k.dx * o.affine.m[3], k.dx * o.affine.m[6]);
   float3 ay = f3(k.dx * o.affine.m[1], k.dx * o.affine.m[4], k.dx * o.affine.m[7]);
   float3 az = f3(k.dx * o.affine.m[2], k.dx * o.affine.m[5], k.dx * o.affine.m[8]);
-  scatter27_affine<TS>(k, active, s, Ge, tt, true, env, args->epoch_base + q + 1, make_float4(a0.x, a0.y, a0.z, k.p_mass), ax, ay, az);
+  scatter27_affine<TS>(k, active, s, Ge, tt, true, env, epoch, make_float4(a0.x, a0.y, a0.z, k.p_mass), ax, ay, az);
 }
 
 #define GRID_CTA 64
@@ -326,6 +331,12 @@ __global__ void __launch_bounds__(128, MINB)
             float4* __restrict__ Gnext, TileTrack tt, const StepArgs* __restrict__ args, int qnext,
             float* __restrict__ svd_out) {
   DSK_TL(k);
+  const int epoch = load_int_here(&args->epoch_base) + qnext + 1;   // loaded first: the tile tags are compared with it
+  prefetch_cta(k, blockDim.x, [&](int col, int ncol) {
+    int t = prefetch_rows(fprev, CX, 3, k.stride, col, ncol, threadIdx.x, 0);
+    t = prefetch_rows(fcur, CF, 9, k.stride, col, ncol, threadIdx.x, t);
+    prefetch_rows(mat, 0, 3, k.stride, col, ncol, threadIdx.x, t);
+  });
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   int env = min(gid / k.Npad, k.B - 1), p = gid - env * k.Npad;
   bool active = gid < k.stride && p < npart[env];
@@ -356,7 +367,7 @@ __global__ void __launch_bounds__(128, MINB)
   float3 ax = f3(k.dx * o.affine.m[0], k.dx * o.affine.m[3], k.dx * o.affine.m[6]);
   float3 ay = f3(k.dx * o.affine.m[1], k.dx * o.affine.m[4], k.dx * o.affine.m[7]);
   float3 az = f3(k.dx * o.affine.m[2], k.dx * o.affine.m[5], k.dx * o.affine.m[8]);
-  scatter27_affine<TS>(k, active, s, Gnext + (size_t)env * k.nnode, tt, true, env, args->epoch_base + qnext + 1,
+  scatter27_affine<TS>(k, active, s, Gnext + (size_t)env * k.nnode, tt, true, env, epoch,
                        make_float4(a0.x, a0.y, a0.z, k.p_mass), ax, ay, az);
 }
 
@@ -371,6 +382,7 @@ __global__ void __launch_bounds__(PL_PARTICLES * 3)
                float4* __restrict__ Gnext, TileTrack tt, const StepArgs* __restrict__ args, int qnext,
                float* __restrict__ svd_out) {
   DSK_TL(k);
+  const int epoch = load_int_here(&args->epoch_base) + qnext + 1;   // loaded first: the tile tags are compared with it
   __shared__ float ex[3][9][PL_PARTICLES];
   const int tx = threadIdx.x, pl = threadIdx.y;
   int gid = blockIdx.x * PL_PARTICLES + tx;
@@ -437,7 +449,7 @@ __global__ void __launch_bounds__(PL_PARTICLES * 3)
   float3 ay = f3(k.dx * o.affine.m[1], k.dx * o.affine.m[4], k.dx * o.affine.m[7]);
   float3 az = f3(k.dx * o.affine.m[2], k.dx * o.affine.m[5], k.dx * o.affine.m[8]);
   float3 a0 = k.p_mass * nv - k.dx * mv(o.affine, fxv) + (float)pl * ax;   // plane term folded in
-  scatter9<TS>(k, active, s, pl, oxp, Gnext + (size_t)env * k.nnode, tt, pl == 0, env, args->epoch_base + qnext + 1,
+  scatter9<TS>(k, active, s, pl, oxp, Gnext + (size_t)env * k.nnode, tt, pl == 0, env, epoch,
                 [&](int j, int l) {
                   float w = wxp * s.wy[j] * s.wz[l];
                   float3 a = a0 + (float)j * ay + (float)l * az;

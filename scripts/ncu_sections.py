@@ -71,12 +71,17 @@ def main():
     hdr = rows[0]
     ia, ii, it = hdr.index('Address'), hdr.index('Instructions Executed'), hdr.index('Thread Instructions Executed')
     isrc = hdr.index('Source')
+    stall_cols = [(h, hdr.index(h)) for h in ('# Samples', 'stall_long_sb', 'stall_short_sb', 'stall_wait', 'stall_lg',
+                                               'stall_mio', 'stall_math', 'stall_not_selected', 'stall_selected',
+                                               'stall_branch_resolving', 'stall_no_inst', 'stall_dispatch') if h in hdr]
     base = int(rows[1][ia], 16)
     counts = {}
+    stalls = {}
     for r in rows[1:]:
         if len(r) <= it or not r[ia].startswith('0x'):
             continue
         counts[int(r[ia], 16) - base] = (int(r[ii]), int(r[it]), r[isrc].split()[0] if r[isrc].split() else '')
+        stalls[int(r[ia], 16) - base] = [int(r[c] or 0) for _, c in stall_cols]
     # nvdisasm with line info
     tmp = tempfile.mkdtemp()
     subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(lib)], cwd=tmp, capture_output=True)
@@ -87,6 +92,7 @@ def main():
     fn = re.search(r'void (\w+)', kname).group(1)
     sec_re = re.compile(r'^\s*\.section\s+\.text\.(\S+?),')
     cur, cur_line, per_line = None, None, collections.Counter()
+    stall_line = collections.defaultdict(lambda: [0] * len(stall_cols))
     want = None
     for l in dis.split('\n'):
         m = sec_re.match(l)
@@ -108,6 +114,8 @@ def main():
             off = int(m.group(1), 16)
             if off in counts:
                 per_line[cur_line] += counts[off][1]
+                for q, v in enumerate(stalls[off]):
+                    stall_line[cur_line][q] += v
     # sections by enclosing function
     csrc = os.environ.get('NCU_SRC_DIR') or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'diffskill_b200', 'csrc')
     ranges = {f: function_ranges(os.path.join(csrc, f)) for f in os.listdir(csrc) if f.endswith(('.cuh', '.cu'))}
@@ -130,6 +138,23 @@ def main():
     print('|---|---|---|')
     for s, c in sec.most_common():
         print(f'| {s} | {c / particles:.0f} | {100.0 * c / total:.1f} % |')
+    if stall_cols:
+        # warp-state samples of the same launch by section (the sampler's view of where the warps WAIT)
+        ssec = collections.defaultdict(lambda: [0] * len(stall_cols))
+        for (f, ln), v in stall_line.items():
+            sc = section_of(f, ln)
+            for q, x in enumerate(v):
+                ssec[sc][q] += x
+        tot = sum(v[0] for v in ssec.values()) or 1
+        print('\n| section | ' + ' | '.join(('samples %' if h == '# Samples' else h.replace('stall_', '')) for h, _ in stall_cols) + ' |')
+        print('|---|' + '---|' * len(stall_cols))
+        for sc, v in sorted(ssec.items(), key=lambda kv: -kv[1][0]):
+            print(f'| {sc} | {100.0 * v[0] / tot:.1f} | ' + ' | '.join(f'{100.0 * x / tot:.1f}' for x in v[1:]) + ' |')
+        if os.environ.get('NCU_TOP_LINES'):
+            print('\n| file:line | samples % | long_sb % |')
+            print('|---|---|---|')
+            for (f, ln), v in sorted(stall_line.items(), key=lambda kv: -kv[1][0])[:int(os.environ['NCU_TOP_LINES'])]:
+                print(f'| {f}:{ln} | {100.0 * v[0] / tot:.1f} | {100.0 * v[1] / tot:.1f} |')
     ops = collections.Counter()
     for off, (wi, ti, op) in counts.items():
         ops[op.split('.')[0]] += ti
