@@ -17,11 +17,6 @@ __global__ void __launch_bounds__(128, MINB)
               const float* __restrict__ adj_in, float* __restrict__ adj_out, const int* __restrict__ npart,
               const float4* __restrict__ Gv, float4* __restrict__ Ga) {
   DSK_TL(k);
-  prefetch_cta(k, blockDim.x, [&](int col, int ncol) {
-    int t = prefetch_rows(fin, CX, 3, k.stride, col, ncol, threadIdx.x, 0);
-    t = prefetch_rows(fnext, CX, 3, k.stride, col, ncol, threadIdx.x, t);
-    prefetch_rows(adj_in, CX, 15, k.stride, col, ncol, threadIdx.x, t);
-  });
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   int env = min(gid / k.Npad, k.B - 1), p = gid - env * k.Npad;
   bool active = gid < k.stride && p < npart[env];
@@ -472,13 +467,6 @@ __global__ void __launch_bounds__(128, MINB)
               const float* __restrict__ mat, const int* __restrict__ npart, const float4* __restrict__ Ga,
               const float* __restrict__ svd_in) {
   DSK_TL(k);
-  prefetch_cta(k, blockDim.x, [&](int col, int ncol) {
-    int t = prefetch_rows(fin, 0, FRAME_COMPS, k.stride, col, ncol, threadIdx.x, 0);
-    t = prefetch_rows(svd_in, 0, SVD_COMPS, k.stride, col, ncol, threadIdx.x, t);
-    t = prefetch_rows(adj_in, CF, 9, k.stride, col, ncol, threadIdx.x, t);
-    t = prefetch_rows(adj_out, CX, 3, k.stride, col, ncol, threadIdx.x, t);
-    prefetch_rows(mat, 0, 3, k.stride, col, ncol, threadIdx.x, t);
-  });
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= k.stride) return;
   int env = gid / k.Npad, p = gid - env * k.Npad;

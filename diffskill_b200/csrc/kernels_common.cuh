@@ -96,42 +96,21 @@ DSK_DEV void mark_tile(const TileTrack& t, int gtile, int epoch) {
     if (atomicExch(&t.epoch[gtile], epoch) != epoch) t.list[atomicAdd(t.count, 1)] = gtile;
   }
 }
-// The stencil touches 1 or 2 tiles per axis.  Marking is split in two halves around the scatter: the (up to) eight epoch tags
-// are LOADED before the scatter's shared-memory / shuffle work and COMPARED after it, so that the L2 round trip of the loads is
-// covered by ~600 independent instructions.  (r02j stall samples: with load and compare adjacent -- even with all eight loads
-// issued up front, r02b -- 20 % of k_g2p2g's warp time sat on that compare, `long_scoreboard`.)  Tags of lanes that do not
-// mark read as `epoch` (nothing to do).  A stale tag only costs a redundant atomicExch.
-struct TileTags {
-  int tag[8];
+// Tile marking of a scatter, warp-collective and in three pieces so that no atomic's round trip is waited for in place
+// (r02j stall samples: the per-lane chain "tag load -> atomicExch -> atomicAdd(count) -> store" of the first version cost
+// 20 % of k_g2p2g's warp time, up to 16 dependent L2 round trips per warp and one same-address atomicAdd per tile):
+//   claim_tiles   before the scatter's value build: every marking lane swaps `epoch` into the tags of the (up to) eight
+//                 tiles of its stencil, all atomics issued back to back (duplicates along an axis skipped, no pre-check load);
+//   append_begin  after the shared-memory stores: a tag that came back != epoch means this lane claimed the tile FIRST; the
+//                 winners of the warp are counted with ballots and lane 0 reserves their list slots with ONE atomicAdd;
+//   append_finish after the run reduction: the winners store their tiles.
+// All lanes of the warp must call all three (lanes that do not mark pass want = false).
+struct TileClaim {
+  int tag[8];     // claim_tiles: previous tag of tile c (epoch: nothing won)
+  unsigned won;   // append_begin: bit c set if this lane appends tile c; bits 8.. = its first slot relative to the warp's base
+  int base;       // append_begin, lane 0: the warp's first slot in the list
 };
-// L2 prefetch of the particle rows a CTA is going to read.  The particle arrays are component-major ([comp][stride]), so the
-// CTA's slice of every component is one contiguous segment (512 B for 128 particles): thread r of the CTA issues ONE
-// cp.async.bulk.prefetch.L2 for row r -- no register result, no wait.  The kernels consume their ~25-60 rows in several
-// dependent batches (the register budget cannot hold them all), each a full DRAM round trip (r02h stall samples: 45-55 % of
-// k_p2g_adj's warp time on `long_scoreboard` at first uses of particle data); after the prefetch the later batches are L2
-// hits, and with pf_ahead the CTA one wave later finds even its first batch in L2.
-DSK_DEV void prefetch_l2(const void* p, int bytes) {
-#if defined(__CUDA_ARCH__)
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-#endif
-}
-// rows [row0, row0 + nrows) of `a`, columns [col, col + ncol): row r is taken by thread t0 + r; returns t0 + nrows
-DSK_DEV int prefetch_rows(const float* a, int row0, int nrows, int stride, int col, int ncol, int tid, int t0) {
-  int r = tid - t0;
-  if (a && r >= 0 && r < nrows) prefetch_l2(a + (size_t)(row0 + r) * stride + col, ncol * 4);
-  return t0 + nrows;
-}
-// runs `rows(col, ncol)` for the CTA's own columns and for those of the CTA pf_ahead blocks later
-template <class F>
-DSK_DEV void prefetch_cta(const SimConst& k, int ncol, F rows) {
-#if defined(__CUDA_ARCH__)
-  if (k.pf_ahead < 0) return;
-  int c1 = (int)blockIdx.x * ncol, c2 = ((int)blockIdx.x + k.pf_ahead) * ncol;
-  if (c1 < k.stride) rows(c1, min(ncol, k.stride - c1));
-  if (k.pf_ahead > 0 && c2 < k.stride) rows(c2, min(ncol, k.stride - c2));
-#endif
-}
-// a 32-bit global load the optimiser may not move (it would sink a plain load to its first use)
+// 32-bit global accesses the optimiser may not move (a plain load / atomic would be sunk to its first use)
 DSK_DEV int load_int_here(const int* p) {
 #if defined(__CUDA_ARCH__)
   int v;
@@ -141,29 +120,65 @@ DSK_DEV int load_int_here(const int* p) {
   return *p;
 #endif
 }
+DSK_DEV int exch_int_here(int* p, int v) {
+#if defined(__CUDA_ARCH__)
+  int old;
+  asm volatile("atom.global.exch.b32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+#else
+  return atomicExch(p, v);
+#endif
+}
+DSK_DEV int add_int_here(int* p, int v) {
+#if defined(__CUDA_ARCH__)
+  int old;
+  asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+#else
+  return atomicAdd(p, v);
+#endif
+}
 DSK_DEV int stencil_tile(const SimConst& k, int env, const Stencil& s, int c) {
   const int tx = (s.bx + ((c & 4) ? 2 : 0)) >> 2, ty = (s.by + ((c & 2) ? 2 : 0)) >> 2, tz = (s.bz + ((c & 1) ? 2 : 0)) >> 2;
   return env * k.ntile + (tx * k.nt + ty) * k.nt + tz;
 }
-DSK_DEV void load_tile_tags(const SimConst& k, const TileTrack& t, int env, const Stencil& s, int epoch, bool want,
-                            TileTags& g) {
-#pragma unroll
-  for (int c = 0; c < 8; c++) {
-    int v = epoch;
-    if (want) v = load_int_here(t.epoch + stencil_tile(k, env, s, c));
-    g.tag[c] = v;
-  }
-}
-DSK_DEV void mark_stale_tiles(const SimConst& k, const TileTrack& t, int env, const Stencil& s, int epoch, const TileTags& g) {
+DSK_DEV void claim_tiles(const SimConst& k, const TileTrack& t, int env, const Stencil& s, int epoch, bool want, TileClaim& g) {
   const bool dx = ((s.bx + 2) >> 2) == (s.bx >> 2), dy = ((s.by + 2) >> 2) == (s.by >> 2), dz = ((s.bz + 2) >> 2) == (s.bz >> 2);
 #pragma unroll
   for (int c = 0; c < 8; c++) {
-    bool dup = ((c & 4) && dx) || ((c & 2) && dy) || ((c & 1) && dz);
-    if (!dup && g.tag[c] != epoch) {
-      int gt = stencil_tile(k, env, s, c);
-      if (atomicExch(&t.epoch[gt], epoch) != epoch) t.list[atomicAdd(t.count, 1)] = gt;
-    }
+    const bool dup = ((c & 4) && dx) || ((c & 2) && dy) || ((c & 1) && dz);
+    int v = epoch;
+    if (want && !dup) v = exch_int_here(t.epoch + stencil_tile(k, env, s, c), epoch);
+    g.tag[c] = v;
   }
+}
+DSK_DEV void append_begin(const TileTrack& t, int epoch, TileClaim& g) {
+  const int lane = threadIdx.x & 31;
+  unsigned won = 0;
+#pragma unroll
+  for (int c = 0; c < 8; c++)
+    if (g.tag[c] != epoch) won |= 1u << c;
+  g.won = won;
+  g.base = 0;
+  if (!__any_sync(0xffffffffu, won != 0u)) return;
+  // a lane stores its wins in consecutive slots: exclusive prefix of the per-lane win counts
+  const int mine = __popc(won);
+  int incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int up = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += up;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  g.won = won | ((unsigned)(incl - mine) << 8);
+  if (lane == 0) g.base = add_int_here(t.count, total);
+}
+DSK_DEV void append_finish(const SimConst& k, const TileTrack& t, int env, const Stencil& s, const TileClaim& g) {
+  if (!__any_sync(0xffffffffu, g.won & 0xffu)) return;
+  int at = __shfl_sync(0xffffffffu, g.base, 0) + (int)(g.won >> 8);
+#pragma unroll
+  for (int c = 0; c < 8; c++)
+    if (g.won & (1u << c)) t.list[at++] = stencil_tile(k, env, s, c);
 }
 
 
@@ -367,8 +382,8 @@ DSK_DEV void warp_scatter9_groups(const SimConst& k, bool active, const Stencil&
     if (!(lane & 1) && m < 9) red_add4(&Ge[node_offset(bx + plane, by + m / 3, bz + m % 3, k.nt)], acc[0]);
   }
 }
-// front halves of the two butterflies: groups of equal keys, the tile tags of each group's first lane loaded before and
-// compared after the reduction (see load_tile_tags)
+// front halves of the two butterflies: groups of equal keys; the first lane of each group claims the stencil's tiles before
+// the reduction and appends the ones it won after it (claim_tiles)
 template <class F>
 DSK_DEV void warp_scatter27(const SimConst& k, bool active, const Stencil& s, float4* __restrict__ Ge,
                             const TileTrack& tt, bool mark, int env, int epoch, F val) {
@@ -378,11 +393,13 @@ DSK_DEV void warp_scatter27(const SimConst& k, bool active, const Stencil& s, fl
   if (!act) return;
   // groups of equal keys, adjacent or not: the sort is per env step, so late substeps see a few strays per warp
   unsigned same = __match_any_sync(0xffffffffu, key);
-  const bool marks = mark && active && lane == __ffs(same) - 1;
-  TileTags tags;
-  if (mark) load_tile_tags(k, tt, env, s, epoch, marks, tags);
+  TileClaim claim;
+  if (mark) claim_tiles(k, tt, env, s, epoch, active && lane == __ffs(same) - 1, claim);
   warp_scatter27_groups(k, active, s, Ge, key, act, same, val);
-  if (marks) mark_stale_tiles(k, tt, env, s, epoch, tags);
+  if (mark) {
+    append_begin(tt, epoch, claim);
+    append_finish(k, tt, env, s, claim);
+  }
 }
 template <class F>
 DSK_DEV void warp_scatter9(const SimConst& k, bool active, const Stencil& s, int plane, int oxp,
@@ -392,11 +409,13 @@ DSK_DEV void warp_scatter9(const SimConst& k, bool active, const Stencil& s, int
   unsigned act = __ballot_sync(0xffffffffu, active);
   if (!act) return;
   unsigned same = __match_any_sync(0xffffffffu, key);
-  const bool marks = mark && active && lane == __ffs(same) - 1;
-  TileTags tags;
-  if (mark) load_tile_tags(k, tt, env, s, epoch, marks, tags);
+  TileClaim claim;
+  if (mark) claim_tiles(k, tt, env, s, epoch, active && lane == __ffs(same) - 1, claim);
   warp_scatter9_groups(k, active, s, plane, oxp, Ge, key, act, same, val);
-  if (marks) mark_stale_tiles(k, tt, env, s, epoch, tags);
+  if (mark) {
+    append_begin(tt, epoch, claim);
+    append_finish(k, tt, env, s, claim);
+  }
 }
 // ---- transposed shared-memory scatter (round 2) -------------------------------------------------------------------------
 // The butterfly above costs ~900 instructions per lane and group (124 shuffles, 248 selects, the 27 values re-evaluated
@@ -412,14 +431,14 @@ DSK_DEV void warp_scatter9(const SimConst& k, bool active, const Stencil& s, int
 // run of its own, so that no live run ever covers a row element an inactive lane wrote), the stencil tiles marked once per
 // live run; returns the ballot of run heads (0: no active lane) and the ballot of active lanes
 DSK_DEV unsigned ts_run_heads(const SimConst& k, bool active, const Stencil& s, const TileTrack& tt, bool mark, int env,
-                              int epoch, unsigned& act, TileTags& tags) {
+                              int epoch, unsigned& act, TileClaim& claim) {
   const int lane = threadIdx.x & 31;
   int key = active ? node_offset(s.bx, s.by, s.bz, k.nt) : -1 - lane;
   act = __ballot_sync(0xffffffffu, active);
   int prev = __shfl_up_sync(0xffffffffu, key, 1);
   bool head = lane == 0 || prev != key;
   unsigned heads = __ballot_sync(0xffffffffu, head);
-  if (mark) load_tile_tags(k, tt, env, s, epoch, head && active, tags);   // compared after the reduction (mark_stale_tiles)
+  if (mark) claim_tiles(k, tt, env, s, epoch, head && active, claim);   // results used after the tile is written
   return act ? heads : 0u;
 }
 // second half: for every run lanes 0..26 add up their node's row segment and issue one RED.128
@@ -448,14 +467,15 @@ DSK_DEV void warp_scatter27_ts(const SimConst& k, bool active, const Stencil& s,
                                const TileTrack& tt, bool mark, int env, int epoch, float4* wbuf, F val) {
   const int lane = threadIdx.x & 31;
   unsigned act;
-  TileTags tags;
-  unsigned todo = ts_run_heads(k, active, s, tt, mark, env, epoch, act, tags);
+  TileClaim claim;
+  unsigned todo = ts_run_heads(k, active, s, tt, mark, env, epoch, act, claim);
   if (!todo) return;
 #pragma unroll
   for (int q = 0; q < 27; q++) wbuf[q * TS_ROW + lane] = val(q / 9, (q / 3) % 3, q % 3);
   __syncwarp();
+  if (mark) append_begin(tt, epoch, claim);
   ts_reduce_runs27(k, s, Ge, wbuf, todo, act);
-  if (mark) mark_stale_tiles(k, tt, env, s, epoch, tags);   // tags of lanes that do not mark equal epoch
+  if (mark) append_finish(k, tt, env, s, claim);
   __syncwarp();   // the tile is rewritten by the warp's next scatter
 }
 // Both scatters of a substep have AFFINE contributions: node (i, j, l) receives w_ijl * (A0 + i AX + j AY + l AZ) with
@@ -469,8 +489,8 @@ DSK_DEV void warp_scatter27_ts_affine(const SimConst& k, bool active, const Sten
                                       float3 AY, float3 AZ) {
   const int lane = threadIdx.x & 31;
   unsigned act;
-  TileTags tags;
-  unsigned todo = ts_run_heads(k, active, s, tt, mark, env, epoch, act, tags);
+  TileClaim claim;
+  unsigned todo = ts_run_heads(k, active, s, tt, mark, env, epoch, act, claim);
   if (!todo) return;
   {
     const float2 axl = f2(AX.x, AX.y), axh = f2(AX.z, 0.f), ayl = f2(AY.x, AY.y), ayh = f2(AY.z, 0.f);
@@ -506,8 +526,9 @@ DSK_DEV void warp_scatter27_ts_affine(const SimConst& k, bool active, const Sten
     }
   }
   __syncwarp();
+  if (mark) append_begin(tt, epoch, claim);
   ts_reduce_runs27(k, s, Ge, wbuf, todo, act);
-  if (mark) mark_stale_tiles(k, tt, env, s, epoch, tags);
+  if (mark) append_finish(k, tt, env, s, claim);
   __syncwarp();
 }
 // one x-plane (9 nodes) per thread, for the plane-split kernels: lanes (part, node) = (lane / 9, lane % 9) add every third
@@ -517,12 +538,13 @@ DSK_DEV void warp_scatter9_ts(const SimConst& k, bool active, const Stencil& s, 
                               const TileTrack& tt, bool mark, int env, int epoch, float4* wbuf, F val) {
   const int lane = threadIdx.x & 31;
   unsigned act;
-  TileTags tags;
-  unsigned todo = ts_run_heads(k, active, s, tt, mark, env, epoch, act, tags);
+  TileClaim claim;
+  unsigned todo = ts_run_heads(k, active, s, tt, mark, env, epoch, act, claim);
   if (!todo) return;
 #pragma unroll
   for (int q = 0; q < 9; q++) wbuf[q * TS_ROW + lane] = val(q / 3, q % 3);
   __syncwarp();
+  if (mark) append_begin(tt, epoch, claim);
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const int part = lane / 9, q = lane - part * 9;
   const float4* row = wbuf + (lane < 27 ? q : 0) * TS_ROW;
@@ -539,7 +561,7 @@ DSK_DEV void warp_scatter9_ts(const SimConst& k, bool active, const Stencil& s, 
     float4 a1 = f4shfl_down(acc, 9), a2 = f4shfl_down(acc, 18);
     if (lane < 9) red_add4(&Ge[node_offset(bx + plane, by + q / 3, bz + q % 3, k.nt)], f4add(f4add(acc, a1), a2));
   }
-  if (mark) mark_stale_tiles(k, tt, env, s, epoch, tags);
+  if (mark) append_finish(k, tt, env, s, claim);
   __syncwarp();
 }
 // scatter front ends of the kernels: TS selects the transposed shared-memory version (dynamic shared memory:

@@ -18,10 +18,6 @@ __global__ void __launch_bounds__(128, MINB)
   DSK_TL(k);
   const int epoch = load_int_here(&args->epoch_base) + q + 1;   // loaded first: the tile tags are compared with it
   if (run_if && *run_if == 0) return;   // adjoint recompute is skipped when the grid tape of the step is complete
-  prefetch_cta(k, blockDim.x, [&](int col, int ncol) {
-    int t = prefetch_rows(fin, 0, FRAME_COMPS, k.stride, col, ncol, threadIdx.x, 0);
-    prefetch_rows(mat, 0, 3, k.stride, col, ncol, threadIdx.x, t);
-  });
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   int env = min(gid / k.Npad, k.B - 1), p = gid - env * k.Npad;   // a warp never straddles envs (Npad % 128 == 0)
   bool active = gid < k.stride && p < npart[env];
@@ -332,11 +328,6 @@ __global__ void __launch_bounds__(128, MINB)
             float* __restrict__ svd_out) {
   DSK_TL(k);
   const int epoch = load_int_here(&args->epoch_base) + qnext + 1;   // loaded first: the tile tags are compared with it
-  prefetch_cta(k, blockDim.x, [&](int col, int ncol) {
-    int t = prefetch_rows(fprev, CX, 3, k.stride, col, ncol, threadIdx.x, 0);
-    t = prefetch_rows(fcur, CF, 9, k.stride, col, ncol, threadIdx.x, t);
-    prefetch_rows(mat, 0, 3, k.stride, col, ncol, threadIdx.x, t);
-  });
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   int env = min(gid / k.Npad, k.B - 1), p = gid - env * k.Npad;
   bool active = gid < k.stride && p < npart[env];
