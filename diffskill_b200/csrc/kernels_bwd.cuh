@@ -204,8 +204,8 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
   __shared__ float red[MAX_FRAMES][2][15];
   __shared__ int any_contact[MAX_FRAMES];
   const int l = threadIdx.x, y = threadIdx.y;
-  int n_active = *count;
-  int gt_next = blockIdx.x < n_active ? list[blockIdx.x] : 0;
+  const int n_active = load_int_here(count);    // with the list head: one round trip (list_head, kernels_fwd.cuh)
+  int gt_next = list_head(k, list, blockIdx.x);
   for (int it = blockIdx.x; it < n_active; it += gridDim.x) {
     int gt = gt_next;
     if (it + (int)gridDim.x < n_active) gt_next = list[it + gridDim.x];   // prefetch: shortens the dependent-load chain
@@ -352,23 +352,24 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4)
   const FrameTable& ft = tp.ft;
   __shared__ WarpFrames wf[FLAT_THREADS / 32];
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  int n_active = *count;
   const int l = tid & 63;
-  // software pipeline over the tile loop (see k_grid_flat): next iteration's list entry, (momentum, mass) and adjoint tile
-  // are in flight while the current tile is processed
+  // software pipeline over the tile loop (see k_grid_flat): the tile list runs two iterations ahead, (momentum, mass) and
+  // adjoint tile one iteration ahead of the arithmetic; count and both list heads come in one round trip
   const int it0 = blockIdx.x * FLAT_TILES + (w >> 1), stride = gridDim.x * FLAT_TILES;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  int gt_n = it0 < n_active ? list[it0] : 0;
+  const int n_active = load_int_here(count);
+  int gt_n = list_head(k, list, it0), gt_nn = list_head(k, list, it0 + stride);
   float4 gin_n = it0 < n_active ? G0[((size_t)gt_n << 6) + l] : z4;
   float4 ga_n = it0 < n_active ? Ga[((size_t)gt_n << 6) + l] : z4;
   for (int it = it0; it < n_active; it += stride) {
     const int gt = gt_n;
     const float4 gin = gin_n, ga4 = ga_n;
+    gt_n = gt_nn;
     if (it + stride < n_active) {
-      gt_n = list[it + stride];
       gin_n = G0[((size_t)gt_n << 6) + l];
       ga_n = Ga[((size_t)gt_n << 6) + l];
     }
+    if (it + 2 * stride < n_active) gt_nn = list[it + 2 * stride];
     int env = gt / k.ntile, tile = gt - env * k.ntile;
     int tz = tile % k.nt, ty = (tile / k.nt) % k.nt, tx = tile / (k.nt * k.nt);
     size_t o = ((size_t)gt << 6) + l;

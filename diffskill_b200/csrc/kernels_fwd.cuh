@@ -48,11 +48,19 @@ __global__ void __launch_bounds__(128, MINB)
 
 #define GRID_CTA 64
 // poses: [B][S+1][K][8]; grid kernels use frames j (P0) and j+1 (P1) of the tile's env
-DSK_DEV void clear_tiles(const SimConst& k, const int* __restrict__ list, int count, float4* c0, float4* c1,
+// The grid kernels begin with a handful of scalars that live in device memory (tile counts, the heads of the tile lists, the
+// tape offset, the graph's run_if flag).  Issue is in order: read where they are needed, every one of them stalls the warp for
+// a full L2 round trip at its first use (4-5 in a row at the top of k_grid, ~1.5 us of a 6 us kernel on a single scene).  The
+// kernels therefore load ALL of them first, back to back, with loads the optimiser cannot sink (load_int_here); list heads
+// are read speculatively (clamped index: entries past the count are stale but readable).
+DSK_DEV int list_head(const SimConst& k, const int* list, int i) { return load_int_here(list + min(i, k.B * k.ntile - 1)); }
+
+// `first` = list[blockIdx.x], already loaded (see above)
+DSK_DEV void clear_tiles(const SimConst& k, const int* __restrict__ list, int count, int first, float4* c0, float4* c1,
                          float4* c2) {
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int i = blockIdx.x; i < count; i += gridDim.x) {
-    size_t o = ((size_t)list[i] << 6) + threadIdx.x;  // list holds env*ntile+tile and nnode == ntile*64
+    size_t o = ((size_t)(i == (int)blockIdx.x ? first : list[i]) << 6) + threadIdx.x;  // list holds env*ntile+tile and nnode == ntile*64
     if (c0) c0[o] = z;
     if (c1) c1[o] = z;
     if (c2) c2[o] = z;
@@ -65,7 +73,8 @@ __global__ void __launch_bounds__(GRID_CTA)
     k_end_clear(SimConst k, const int* __restrict__ list, const int* __restrict__ count, float4* c0, float4* c1,
                 float4* c2, int* counts4, int* done) {
   DSK_TL(k);
-  clear_tiles(k, list, *count, c0, c1, c2);
+  const int first = list_head(k, list, blockIdx.x);
+  clear_tiles(k, list, load_int_here(count), first, c0, c1, c2);
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -92,7 +101,8 @@ DSK_DEV void prepare_tile_frame(const SimConst& k, const ToolParams* sT, const F
 __global__ void __launch_bounds__(GRID_CTA)
     k_clear_set(SimConst k, const int* __restrict__ list, const int* __restrict__ count, float4* c0, float4* c1, float4* c2) {
   DSK_TL(k);
-  clear_tiles(k, list, *count, c0, c1, c2);
+  const int first = list_head(k, list, blockIdx.x);
+  clear_tiles(k, list, load_int_here(count), first, c0, c1, c2);
 }
 
 // grid_op over active tiles.  Gin holds (momentum, mass); Gout receives (velocity, mass) and may alias Gin.
@@ -104,20 +114,24 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
            const int* __restrict__ clr_list, const int* __restrict__ clr_count, float4* clr0, float4* clr1,
            float4* clr2, int* zero_count, GridTape tape, const int* __restrict__ run_if) {
   DSK_TL(k);
-  if (run_if && *run_if == 0) return;
+  // every scalar of the prologue in one round trip (see list_head)
+  const int run = run_if ? load_int_here(run_if) : 1;
+  const int n_clr = clr_list ? load_int_here(clr_count) : 0;
+  const int clr_first = clr_list ? list_head(k, clr_list, blockIdx.x) : 0;
+  const int n_active = load_int_here(count);
+  int gt_next = list_head(k, list, blockIdx.x);
+  // grid tape: (momentum, mass) and velocity of every active tile are kept so that substep_grad need not
+  // recompute p2g + grid_op (mpm_simulator.py:330-333 does); tape.base[j] = first tape slot of substep j
+  const int tb = (tape.base && j > 0) ? load_int_here(tape.base + j) : 0;
+  if (!run) return;
   const ToolParams* sT = tp.T;   // tool parameters and the frame table arrive as kernel parameters: no setup barrier
   const FrameTable& ft = tp.ft;
   __shared__ TileFrames tf;
   __shared__ ContactGeom geo[MAX_FRAMES][GRID_NODES];
   const int l = threadIdx.x, y = threadIdx.y, tid = y * GRID_NODES + l;
   if (blockIdx.x == 0 && tid == 0 && zero_count) *zero_count = 0;
-  if (clr_list && y == 0) clear_tiles(k, clr_list, *clr_count, clr0, clr1, clr2);
-  int n_active = *count;
-  // grid tape: (momentum, mass) and velocity of every active tile are kept so that substep_grad need not
-  // recompute p2g + grid_op (mpm_simulator.py:330-333 does); tape.base[j] = first tape slot of substep j
-  int tb = 0;
+  if (clr_list && y == 0) clear_tiles(k, clr_list, n_clr, clr_first, clr0, clr1, clr2);
   if (tape.base) {
-    tb = j == 0 ? 0 : tape.base[j];
     if (blockIdx.x == 0 && tid == 0) {
       tape.base[j + 1] = tb + n_active;
       bool over = tb + n_active > tape.cap;
@@ -125,7 +139,6 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
       else if (over) *tape.overflow = 1;
     }
   }
-  int gt_next = blockIdx.x < n_active ? list[blockIdx.x] : 0;
   for (int it = blockIdx.x; it < n_active; it += gridDim.x) {
     int gt = gt_next;
     if (it + (int)gridDim.x < n_active) gt_next = list[it + gridDim.x];   // prefetch: shortens the dependent-load chain
@@ -184,10 +197,11 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
 struct WarpFrames {   // per warp, shared memory
   Frame F0[MAX_FRAMES], F1[MAX_FRAMES];
 };
-DSK_DEV void clear_tiles_flat(const int* __restrict__ list, int count, float4* c0, float4* c1, float4* c2) {
+DSK_DEV void clear_tiles_flat(const int* __restrict__ list, int count, int first, float4* c0, float4* c1, float4* c2) {
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int i = blockIdx.x * FLAT_TILES + (threadIdx.x >> 6); i < count; i += gridDim.x * FLAT_TILES) {
-    size_t o = ((size_t)list[i] << 6) + (threadIdx.x & 63);
+  const int i0 = blockIdx.x * FLAT_TILES + (threadIdx.x >> 6);
+  for (int i = i0; i < count; i += gridDim.x * FLAT_TILES) {
+    size_t o = ((size_t)(i == i0 ? first : list[i]) << 6) + (threadIdx.x & 63);
     if (c0) c0[o] = z;
     if (c1) c1[o] = z;
     if (c2) c2[o] = z;
@@ -210,17 +224,23 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4)
                 const int* __restrict__ clr_list, const int* __restrict__ clr_count, float4* clr0, float4* clr1,
                 float4* clr2, int* zero_count, GridTape tape, const int* __restrict__ run_if) {
   DSK_TL(k);
-  if (run_if && *run_if == 0) return;
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int it0 = blockIdx.x * FLAT_TILES + (w >> 1), stride = gridDim.x * FLAT_TILES;
+  // every scalar of the prologue in one round trip (see list_head); the tile list runs TWO iterations ahead of the tile
+  // data, which runs one ahead of the arithmetic
+  const int run = run_if ? load_int_here(run_if) : 1;
+  const int n_clr = clr_list ? load_int_here(clr_count) : 0;
+  const int clr_first = clr_list ? list_head(k, clr_list, it0) : 0;
+  const int n_active = load_int_here(count);
+  int gt_n = list_head(k, list, it0), gt_nn = list_head(k, list, it0 + stride);
+  const int tb = (tape.base && j > 0) ? load_int_here(tape.base + j) : 0;
+  if (!run) return;
   const ToolParams* sT = tp.T;   // tool parameters and the frame table arrive as kernel parameters: no setup barrier
   const FrameTable& ft = tp.ft;
   __shared__ WarpFrames wf[FLAT_THREADS / 32];
-  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   if (blockIdx.x == 0 && tid == 0 && zero_count) *zero_count = 0;
-  if (clr_list) clear_tiles_flat(clr_list, *clr_count, clr0, clr1, clr2);
-  int n_active = *count;
-  int tb = 0;
+  if (clr_list) clear_tiles_flat(clr_list, n_clr, clr_first, clr0, clr1, clr2);
   if (tape.base) {   // as in k_grid
-    tb = j == 0 ? 0 : tape.base[j];
     if (blockIdx.x == 0 && tid == 0) {
       tape.base[j + 1] = tb + n_active;
       bool over = tb + n_active > tape.cap;
@@ -232,16 +252,13 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4)
   // software pipeline over the tile loop: the list entry and the tile's 1 KB of the NEXT iteration are loaded before the
   // current tile is processed (list -> grid is a dependent L2 + HBM round trip of ~1 us per iteration otherwise; a batch of
   // 64 envs has ~4 iterations per warp pair)
-  const int it0 = blockIdx.x * FLAT_TILES + (w >> 1), stride = gridDim.x * FLAT_TILES;
-  int gt_n = it0 < n_active ? list[it0] : 0;
   float4 g_n = it0 < n_active ? Gin[((size_t)gt_n << 6) + l] : make_float4(0.f, 0.f, 0.f, 0.f);
   for (int it = it0; it < n_active; it += stride) {
     const int gt = gt_n;
     const float4 g = g_n;
-    if (it + stride < n_active) {
-      gt_n = list[it + stride];
-      g_n = Gin[((size_t)gt_n << 6) + l];
-    }
+    gt_n = gt_nn;
+    if (it + stride < n_active) g_n = Gin[((size_t)gt_n << 6) + l];
+    if (it + 2 * stride < n_active) gt_nn = list[it + 2 * stride];
     int env = gt / k.ntile, tile = gt - env * k.ntile;
     int tz = tile % k.nt, ty = (tile / k.nt) % k.nt, tx = tile / (k.nt * k.nt);
     size_t o = ((size_t)gt << 6) + l;
@@ -282,11 +299,15 @@ __global__ void __launch_bounds__(GRID_NODES)
                    const int* __restrict__ clr_list, const int* __restrict__ clr_count, float4* clr0, float4* clr1,
                    float4* clr2, int* zero_count) {
   DSK_TL(k);
-  if (*tape.overflow) return;   // incomplete tape: the recompute kernels that follow take over
+  // the scalars of the prologue in one round trip (see list_head); this kernel sits on the side branch of the adjoint graph
+  const int over = load_int_here(tape.overflow);
+  const int n_clr = clr_list ? load_int_here(clr_count) : 0;
+  const int clr_first = clr_list ? list_head(k, clr_list, blockIdx.x) : 0;
+  const int tb = j == 0 ? 0 : load_int_here(tape.base + j);
+  const int n = load_int_here(tape.base + j + 1) - tb;
+  if (over) return;   // incomplete tape: the recompute kernels that follow take over
   if (blockIdx.x == 0 && threadIdx.x == 0 && zero_count) *zero_count = 0;
-  if (clr_list) clear_tiles(k, clr_list, *clr_count, clr0, clr1, clr2);
-  int tb = j == 0 ? 0 : tape.base[j];
-  int n = tape.base[j + 1] - tb;
+  if (clr_list) clear_tiles(k, clr_list, n_clr, clr_first, clr0, clr1, clr2);
   if (blockIdx.x == 0 && threadIdx.x == 0) *count = n;
   for (int it = blockIdx.x; it < n; it += gridDim.x) {
     int gt = tape.list[tb + it];

@@ -89,7 +89,7 @@ def main():
     dis = subprocess.run(['nvdisasm', '--print-line-info', os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
     # pick the function whose demangled name matches
     tpl = re.search(r'<\(int\)(\d+)(?:, \(bool\)(\d))?>', kname)
-    fn = re.search(r'void (\w+)', kname).group(1)
+    fn = (re.search(r'void (\w+)', kname) or re.search(r'"Kernel Name","(\w+)', kname)).group(1)
     sec_re = re.compile(r'^\s*\.section\s+\.text\.(\S+?),')
     cur, cur_line, per_line = None, None, collections.Counter()
     stall_line = collections.defaultdict(lambda: [0] * len(stall_cols))
