@@ -352,7 +352,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--step-slots', type=int, default=0,
                     help='substep-frame ring in env steps (1 = pure per-step checkpointing + recompute, H = full tape; '
-                         '0 = auto: H if the tape fits in 16 GB else 1)')
+                         '0 = auto: H if the tape fits in half of the free device memory else 1)')
     ap.add_argument('--grid-tape-mib', type=int, default=8192,
                     help='device memory budget for taping active grid tiles (adjoint skips the p2g/grid_op recompute); 0 = off')
     ap.add_argument('--envs', type=int, default=0, help='override the envs per GPU of the workload (experiments; the JSON says so)')
@@ -393,8 +393,11 @@ def main():
     scene, cfg, xs, targets, actions = make_inputs(spec, rank + args.env_offset, B)
     cap = max(len(x) for x in xs)
     if args.step_slots <= 0:
-        tape_bytes = H * (scene.substeps + 1) * 24 * B * ((cap + 127) // 128 * 128) * 4
-        args.step_slots = H if tape_bytes <= 16e9 else 1
+        # substep frames (24 rows) + SVD tape (21 rows) of every env step, as the reference keeps them (its fields are
+        # [max_steps, n_particles]); taken when they fit in half of the free HBM, else per-step checkpointing + recompute
+        npad = B * ((cap + 127) // 128 * 128)
+        tape_bytes = H * ((scene.substeps + 1) * 24 + scene.substeps * 21) * npad * 4
+        args.step_slots = H if tape_bytes <= 0.5 * torch.cuda.mem_get_info(local_rank)[0] else 1
     eng = Engine(scene, n_envs=B, capacity=cap, max_steps=H, step_slots=args.step_slots, sort=not args.no_sort,
                  device=local_rank, grid_tape_mib=args.grid_tape_mib)
     eng.set_stream(torch.cuda.current_stream().cuda_stream)

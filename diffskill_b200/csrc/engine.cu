@@ -344,6 +344,8 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
   k.Npad = e->Npad;
   k.stride = e->B * e->Npad;
   k.S = e->S;
+  k.pf_ahead = 148 * 4;   // CTAs of a batched particle kernel in flight at once (4 per SM)
+  if (const char* v = getenv("DSK_PREFETCH")) k.pf_ahead = atoi(v);
   k.K = e->K;
   k.npairs = c->n_pairs;
   k.gf_mode = c->ground_friction == 0.0 ? 0 : (c->ground_friction < 10.0 ? 1 : 2);

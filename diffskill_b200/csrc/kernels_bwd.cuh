@@ -494,11 +494,35 @@ DSK_DEV int stage_rows(float* stage, int at, const float* __restrict__ a, int ro
     for (int i = 0; i < n; i++) cp_async4(stage + (at + i) * 32, a + (size_t)(row0 + i) * stride + gid);
   return at + n;
 }
+DSK_DEV void prefetch_l2(const void* p, int bytes) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+#endif
+}
+// Once the CTA's own first rows have arrived (group 0: the load burst of its wave is over) it prefetches into L2 the rows of
+// the CTA `ahead` blocks later -- the one that takes over this SM slot -- so that the next wave's loads are L2 hits: thread r
+// one cp.async.bulk.prefetch.L2 for row r (component-major arrays: the CTA's slice of a row is contiguous).
 struct StagedReady {
+  const float *fin, *mat, *svd, *adj_in, *adj_out;
+  int stride, col, ncol;   // columns of the CTA to prefetch for (ncol = 0: none)
   DSK_DEV_MEMBER void operator()(int group) const {
-    if (group == 0) cp_async_wait<2>();
-    else if (group == 1) cp_async_wait<1>();
-    else cp_async_wait<0>();
+    if (group == 0) {
+      cp_async_wait<2>();
+      if (ncol > 0) {
+        const int r = threadIdx.x;
+        const float* a = nullptr;
+        if (r < FRAME_COMPS) a = fin + (size_t)r * stride;
+        else if (r < FRAME_COMPS + SVD_COMPS) a = svd ? svd + (size_t)(r - FRAME_COMPS) * stride : nullptr;
+        else if (r < FRAME_COMPS + SVD_COMPS + 9) a = adj_in + (size_t)(CF + r - FRAME_COMPS - SVD_COMPS) * stride;
+        else if (r < FRAME_COMPS + SVD_COMPS + 12) a = adj_out + (size_t)(CX + r - FRAME_COMPS - SVD_COMPS - 9) * stride;
+        else if (r < FRAME_COMPS + SVD_COMPS + 15) a = mat ? mat + (size_t)(r - FRAME_COMPS - SVD_COMPS - 12) * stride : nullptr;
+        if (a) prefetch_l2(a + col, ncol * 4);
+      }
+    } else if (group == 1) {
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
   }
 };
 template <int MINB, bool STAGED>
@@ -532,7 +556,10 @@ __global__ void __launch_bounds__(128, MINB)
     }
     ParticleRows r{st, mat ? st + at_mat * 32 : nullptr, svd_in ? st + at_svd * 32 : nullptr, st + (at_fg - CF) * 32,
                    st + (at_xg - CX) * 32, 32, 0};
-    p2g_adj_particle_rows(k, gid, env, r, adj_out, Ga, StagedReady());
+    const int col = ((int)blockIdx.x + k.pf_ahead) * (int)blockDim.x;
+    StagedReady ready{fin, mat, svd_in, adj_in, adj_out, k.stride, col,
+                      (k.pf_ahead > 0 && col < k.stride) ? min((int)blockDim.x, k.stride - col) : 0};
+    p2g_adj_particle_rows(k, gid, env, r, adj_out, Ga, ready);
   } else {
     if (p >= npart[env]) return;
     p2g_adj_particle(k, gid, env, fin, adj_in, adj_out, mat, Ga, svd_in);

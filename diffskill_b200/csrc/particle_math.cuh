@@ -18,6 +18,7 @@ struct SimConst {
   int gf_mode;              // ground friction: 0 zero-normal, 1 Coulomb, 2 stick (mpm_simulator.py:245-258)
   float dt, dx, inv_dx, p_mass, c_stress, c_C, x_hi, x_lo, m_eps, ground_friction;
   float grav[3];            // (dt * g) * 30, mpm_simulator.py:235
+  int pf_ahead;             // staged kernels: prefetch into L2 the rows of CTA blockIdx + pf_ahead (0: off)
   float mu, lam, ys;        // the scene's material; the kernels read these while no per-particle material was set (mat == null)
   int pairs[DSK_MAX_PAIRS][2];
 #ifdef DSK_TIMELINE
