@@ -153,7 +153,6 @@ struct dsk_engine {
   bool mat_uniform = true;  // no per-particle material set: the particle kernels take (mu, lam, yield_stress) from SimConst
   bool flat_grid = false;   // many active tiles: throughput layout of the grid kernels
   bool ts = true;           // batched engines: transposed shared-memory scatter (warp_scatter27_ts_affine) instead of the shuffle butterfly
-  bool stage_on = true;     // batched engines: k_p2g_adj stages its particle rows in shared memory with cp.async (kernels_bwd.cuh)
   bool ts_pl = false;       // ... in the plane-split kernels of single scenes (slower there: r02b liftspread 46.3 vs 42.3 ms)
   cudaStream_t cap_side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -344,8 +343,6 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
   k.Npad = e->Npad;
   k.stride = e->B * e->Npad;
   k.S = e->S;
-  k.pf_ahead = 148 * 4;   // CTAs of a batched particle kernel in flight at once (4 per SM)
-  if (const char* v = getenv("DSK_PREFETCH")) k.pf_ahead = atoi(v);
   k.K = e->K;
   k.npairs = c->n_pairs;
   k.gf_mode = c->ground_friction == 0.0 ? 0 : (c->ground_friction < 10.0 ? 1 : 2);
@@ -406,7 +403,6 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
   e->flat_grid = e->big;
   if (const char* v = getenv("DSK_GRID_CTAS_PER_SM")) e->grid_ctas_per_sm = std::max(1, atoi(v));
   if (const char* v = getenv("DSK_TS")) e->ts = atoi(v) != 0;
-  if (const char* v = getenv("DSK_STAGE")) e->stage_on = atoi(v) != 0;
   if (const char* v = getenv("DSK_TS_PL")) e->ts_pl = atoi(v) != 0;
   if (const char* v = getenv("DSK_FLAT_GRID")) e->flat_grid = atoi(v) != 0;
   e->tool_floats = (size_t)e->B * std::max(1, e->K) * 8;
@@ -714,17 +710,9 @@ static int launch_p2g_adj(dsk_engine* e, const float* fin, const float* ain, flo
     KL(KID_P2G_ADJ, k_p2g_adj_pl<<<cdiv(k.stride, PL_PARTICLES), dim3(PL_PARTICLES, 3), 0, e->qs>>>(k, fin, ain, aout, mat, e->npart, Ga, svd));
   } else {
     const int pb = e->big_block, nb = cdiv(k.stride, pb);
-    const size_t sm = (size_t)(pb / 32) * P2GADJ_ROWS * 32 * sizeof(float);   // staging area: 30 KB for 128 threads
-    if (e->stage_on) {
-      switch (minb_class(e->minb_p2g_adj)) {
-        case 6: KL(KID_P2G_ADJ, (k_p2g_adj<6, true><<<nb, pb, sm, e->qs>>>(k, fin, ain, aout, mat, e->npart, Ga, svd))); break;
-        default: KL(KID_P2G_ADJ, (k_p2g_adj<4, true><<<nb, pb, sm, e->qs>>>(k, fin, ain, aout, mat, e->npart, Ga, svd))); break;
-      }
-    } else {
-      switch (minb_class(e->minb_p2g_adj)) {
-        case 6: KL(KID_P2G_ADJ, (k_p2g_adj<6, false><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, mat, e->npart, Ga, svd))); break;
-        default: KL(KID_P2G_ADJ, (k_p2g_adj<4, false><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, mat, e->npart, Ga, svd))); break;
-      }
+    switch (minb_class(e->minb_p2g_adj)) {
+      case 6: KL(KID_P2G_ADJ, k_p2g_adj<6><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, mat, e->npart, Ga, svd)); break;
+      default: KL(KID_P2G_ADJ, k_p2g_adj<4><<<nb, pb, 0, e->qs>>>(k, fin, ain, aout, mat, e->npart, Ga, svd)); break;
     }
   }
   LAUNCH_CHECK();

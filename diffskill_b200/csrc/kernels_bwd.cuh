@@ -462,70 +462,7 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4)
 
 // p2g.grad + svd_grad + compute_F_tmp.grad fused: gathers adjoints of (grid_v_in, grid_m), reads F.grad[j+1],
 // writes x.grad (adding the g2p part already stored), v.grad, C.grad, F.grad of frame j.
-//
-// The kernel reads ~60 rows of the particle (frame 24, SVD tape 21, F.grad 9, x.grad 3, material 3) in three dependent batches;
-// with plain loads each batch is an exposed DRAM round trip (r02h stall samples: 55 % of the warp time on `long_scoreboard` at
-// the first uses).  STAGED: every thread copies its own element of every row into shared memory with cp.async right at
-// the start -- no registers, no waiting -- in three commit groups, and reads them back (LDS) where they are needed after
-// cp.async.wait_group.  The slots are thread-private ([row][lane] per warp), so no barrier is involved.
-#define P2GADJ_ROWS (FRAME_COMPS + SVD_COMPS + 9 + 3 + 3)
-DSK_DEV void cp_async4(float* dst_shared, const float* src) {
-#if defined(__CUDA_ARCH__)
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_shared)), "l"(src) : "memory");
-#else
-  *dst_shared = *src;
-#endif
-}
-DSK_DEV void cp_async_commit() {
-#if defined(__CUDA_ARCH__)
-  asm volatile("cp.async.commit_group;" ::: "memory");
-#endif
-}
-template <int N>
-DSK_DEV void cp_async_wait() {
-#if defined(__CUDA_ARCH__)
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-#endif
-}
-// copies rows [row0, row0 + n) of a component-major array (element `gid` of each) to stage[(at + i) * 32]; returns at + n
-DSK_DEV int stage_rows(float* stage, int at, const float* __restrict__ a, int row0, int n, int stride, int gid) {
-  if (a)
-#pragma unroll
-    for (int i = 0; i < n; i++) cp_async4(stage + (at + i) * 32, a + (size_t)(row0 + i) * stride + gid);
-  return at + n;
-}
-DSK_DEV void prefetch_l2(const void* p, int bytes) {
-#if defined(__CUDA_ARCH__)
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-#endif
-}
-// Once the CTA's own first rows have arrived (group 0: the load burst of its wave is over) it prefetches into L2 the rows of
-// the CTA `ahead` blocks later -- the one that takes over this SM slot -- so that the next wave's loads are L2 hits: thread r
-// one cp.async.bulk.prefetch.L2 for row r (component-major arrays: the CTA's slice of a row is contiguous).
-struct StagedReady {
-  const float *fin, *mat, *svd, *adj_in, *adj_out;
-  int stride, col, ncol;   // columns of the CTA to prefetch for (ncol = 0: none)
-  DSK_DEV_MEMBER void operator()(int group) const {
-    if (group == 0) {
-      cp_async_wait<2>();
-      if (ncol > 0) {
-        const int r = threadIdx.x;
-        const float* a = nullptr;
-        if (r < FRAME_COMPS) a = fin + (size_t)r * stride;
-        else if (r < FRAME_COMPS + SVD_COMPS) a = svd ? svd + (size_t)(r - FRAME_COMPS) * stride : nullptr;
-        else if (r < FRAME_COMPS + SVD_COMPS + 9) a = adj_in + (size_t)(CF + r - FRAME_COMPS - SVD_COMPS) * stride;
-        else if (r < FRAME_COMPS + SVD_COMPS + 12) a = adj_out + (size_t)(CX + r - FRAME_COMPS - SVD_COMPS - 9) * stride;
-        else if (r < FRAME_COMPS + SVD_COMPS + 15) a = mat ? mat + (size_t)(r - FRAME_COMPS - SVD_COMPS - 12) * stride : nullptr;
-        if (a) prefetch_l2(a + col, ncol * 4);
-      }
-    } else if (group == 1) {
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-  }
-};
-template <int MINB, bool STAGED>
+template <int MINB>
 __global__ void __launch_bounds__(128, MINB)
     k_p2g_adj(SimConst k, const float* __restrict__ fin, const float* __restrict__ adj_in, float* __restrict__ adj_out,
               const float* __restrict__ mat, const int* __restrict__ npart, const float4* __restrict__ Ga,
@@ -534,36 +471,8 @@ __global__ void __launch_bounds__(128, MINB)
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= k.stride) return;
   int env = gid / k.Npad, p = gid - env * k.Npad;
-  if (STAGED) {
-    DSK_DYN_SMEM(float, stage_buf);
-    const int np = npart[env];   // needed only after the copies are on their way
-    float* st = stage_buf + (threadIdx.x >> 5) * (P2GADJ_ROWS * 32) + (threadIdx.x & 31);
-    int at = stage_rows(st, 0, fin, 0, FRAME_COMPS, k.stride, gid);            // rows 0..23: the frame
-    const int at_mat = at;
-    at = stage_rows(st, at, mat, 0, 3, k.stride, gid);                         // 24..26: material
-    cp_async_commit();
-    const int at_svd = at;
-    at = stage_rows(st, at, svd_in, 0, SVD_COMPS, k.stride, gid);              // 27..47: SVD tape
-    cp_async_commit();
-    const int at_fg = at;
-    at = stage_rows(st, at, adj_in, CF, 9, k.stride, gid);                     // 48..56: F.grad[j+1]
-    const int at_xg = at;
-    stage_rows(st, at, adj_out, CX, 3, k.stride, gid);                         // 57..59: x.grad so far
-    cp_async_commit();
-    if (p >= np) {
-      cp_async_wait<0>();
-      return;
-    }
-    ParticleRows r{st, mat ? st + at_mat * 32 : nullptr, svd_in ? st + at_svd * 32 : nullptr, st + (at_fg - CF) * 32,
-                   st + (at_xg - CX) * 32, 32, 0};
-    const int col = ((int)blockIdx.x + k.pf_ahead) * (int)blockDim.x;
-    StagedReady ready{fin, mat, svd_in, adj_in, adj_out, k.stride, col,
-                      (k.pf_ahead > 0 && col < k.stride) ? min((int)blockDim.x, k.stride - col) : 0};
-    p2g_adj_particle_rows(k, gid, env, r, adj_out, Ga, ready);
-  } else {
-    if (p >= npart[env]) return;
-    p2g_adj_particle(k, gid, env, fin, adj_in, adj_out, mat, Ga, svd_in);
-  }
+  if (p >= npart[env]) return;
+  p2g_adj_particle(k, gid, env, fin, adj_in, adj_out, mat, Ga, svd_in);
 }
 
 // plane-split p2g.grad for small engines: three threads per particle gather one x-plane of the stencil each
@@ -633,8 +542,7 @@ __global__ void __launch_bounds__(PL_PARTICLES * 3)
   float gwx[3] = {t[0][9], t[1][9], t[2][9]};
   float gwy[3] = {t[0][10] + t[1][10] + t[2][10], t[0][11] + t[1][11] + t[2][11], t[0][12] + t[1][12] + t[2][12]};
   float gwz[3] = {t[0][13] + t[1][13] + t[2][13], t[0][14] + t[1][14] + t[2][14], t[0][15] + t[1][15] + t[2][15]};
-  p2g_adj_finish(k, gid, s, o, mu, lam, C, F, load_v3(adj_out, CX, k.stride, gid), load_m3(adj_in, CF, k.stride, gid), adj_out,
-                 S0, m0, m1, m2, gwx, gwy, gwz);
+  p2g_adj_finish(k, gid, s, o, mu, lam, C, F, adj_in, adj_out, S0, m0, m1, m2, gwx, gwy, gwz);
 }
 
 // Tool adjoints of one env step: for j = S-1..0: apply_collision_projection.grad, set_surface_points.grad,

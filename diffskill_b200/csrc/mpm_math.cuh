@@ -11,7 +11,6 @@
 #include <cuda_runtime.h>
 
 #define DSK_DEV __device__ __forceinline__
-#define DSK_DEV_MEMBER __device__ __forceinline__   // member functions (the host shim's DSK_DEV is `static inline`)
 #endif
 
 // Transcendentals of the return map and the reciprocals of the Jacobi SVD.  Product build: the hardware approximations

@@ -18,7 +18,6 @@ struct SimConst {
   int gf_mode;              // ground friction: 0 zero-normal, 1 Coulomb, 2 stick (mpm_simulator.py:245-258)
   float dt, dx, inv_dx, p_mass, c_stress, c_C, x_hi, x_lo, m_eps, ground_friction;
   float grav[3];            // (dt * g) * 30, mpm_simulator.py:235
-  int pf_ahead;             // staged kernels: prefetch into L2 the rows of CTA blockIdx + pf_ahead (0: off)
   float mu, lam, ys;        // the scene's material; the kernels read these while no per-particle material was set (mat == null)
   int pairs[DSK_MAX_PAIRS][2];
 #ifdef DSK_TIMELINE
@@ -68,19 +67,16 @@ DSK_DEV void make_stencil(const SimConst& k, float x, float y, float z, Stencil&
 
 // per-particle material (mu, lam, yield_stress): the sorted arrays, or the scene's constants while nobody called
 // dsk_set_material (12 bytes per particle and kernel less)
-DSK_DEV void load_mat_at(const SimConst& k, const float* __restrict__ mat, int stride, int g, float& mu, float& lam, float& ys) {
+DSK_DEV void load_mat(const SimConst& k, const float* __restrict__ mat, int g, float& mu, float& lam, float& ys) {
   if (mat) {
     mu = mat[g];
-    lam = mat[stride + g];
-    ys = mat[2 * stride + g];
+    lam = mat[k.stride + g];
+    ys = mat[2 * k.stride + g];
   } else {
     mu = k.mu;
     lam = k.lam;
     ys = k.ys;
   }
-}
-DSK_DEV void load_mat(const SimConst& k, const float* __restrict__ mat, int g, float& mu, float& lam, float& ys) {
-  load_mat_at(k, mat, k.stride, g, mu, lam, ys);
 }
 DSK_DEV M3 load_m3(const float* __restrict__ f, int comp0, int stride, int gid) {
   M3 A;
@@ -175,20 +171,16 @@ DSK_DEV void store_svd(float* __restrict__ t, int stride, int gid, const P2GPart
   store_m3(t, 12, stride, gid, o.V);
 }
 // p2g_particle for the adjoint: from the tape when there is one
-DSK_DEV void p2g_particle_adj_at(const SimConst& k, const float* __restrict__ svd, int stride, int gid, const M3& C,
-                                 const M3& F, float mu, float lam, float ys, P2GParticle& o) {
+DSK_DEV void p2g_particle_adj(const SimConst& k, const float* __restrict__ svd, int gid, const M3& C, const M3& F, float mu,
+                              float lam, float ys, P2GParticle& o) {
   if (svd) {
-    o.U = load_m3(svd, 0, stride, gid);
-    o.sig = load_v3(svd, 9, stride, gid);
-    o.V = load_m3(svd, 12, stride, gid);
+    o.U = load_m3(svd, 0, k.stride, gid);
+    o.sig = load_v3(svd, 9, k.stride, gid);
+    o.V = load_m3(svd, 12, k.stride, gid);
     p2g_particle_impl<true>(k, C, F, mu, lam, ys, o);
   } else {
     p2g_particle_impl<false>(k, C, F, mu, lam, ys, o);
   }
-}
-DSK_DEV void p2g_particle_adj(const SimConst& k, const float* __restrict__ svd, int gid, const M3& C, const M3& F, float mu,
-                              float lam, float ys, P2GParticle& o) {
-  p2g_particle_adj_at(k, svd, k.stride, gid, C, F, mu, lam, ys, o);
 }
 
 // ---- grid_op for one node ---------------------------------------------------------------------------
@@ -341,8 +333,7 @@ DSK_DEV float3 contact_response_adj(float3 v, float3 D, float3 cv, float influen
 // everything of p2g.grad after the 27-node gather: S0 = sum w G, (m0,m1,m2) = columns of sum w G (x) offset,
 // gw* = adjoints of the per-axis weights
 DSK_DEV void p2g_adj_finish(const SimConst& k, int gid, const Stencil& s, const P2GParticle& o, float mu, float lam,
-                            const M3& C, const M3& F, float3 gx_g2p /* x.grad so far: the g2p part */,
-                            const M3& gFn /* F.grad[j+1] */, float* __restrict__ adj_out,
+                            const M3& C, const M3& F, const float* __restrict__ adj_in, float* __restrict__ adj_out,
                             float3 S0, float3 m0, float3 m1, float3 m2, const float* gwx, const float* gwy,
                             const float* gwz) {
   float3 gv = k.p_mass * S0;
@@ -358,7 +349,7 @@ DSK_DEV void p2g_adj_finish(const SimConst& k, int gid, const Stencil& s, const 
   gf.y += gwy[0] * dw[0] + gwy[1] * dw[1] + gwy[2] * dw[2];
   bspline1_grad(s.fz, dw);
   gf.z += gwz[0] * dw[0] + gwz[1] * dw[1] + gwz[2] * dw[2];
-  float3 gx = gx_g2p + k.inv_dx * gf;
+  float3 gx = load_v3(adj_out, CX, k.stride, gid) + k.inv_dx * gf;
 
   // affine = c_stress * stress + p_mass * C
   M3 gCm, gS;
@@ -382,6 +373,7 @@ DSK_DEV void p2g_adj_finish(const SimConst& k, int gid, const Stencil& s, const 
   }
   float gJ = lam * (2.f * o.J - 1.f) * (gS.m[0] + gS.m[4] + gS.m[8]);
   M3 cf = cof3(o.newF);
+  M3 gFn = load_m3(adj_in, CF, k.stride, gid);  // F.grad[j+1]
 #pragma unroll
   for (int i = 0; i < 9; i++) gN.m[i] += gJ * cf.m[i] + gFn.m[i];
   // R = U V^T
@@ -479,30 +471,17 @@ DSK_DEV void contact_geometry(const ToolParams& T, int kind, const Frame& F0, co
 // p2g.grad + svd_grad + compute_F_tmp.grad of one particle (the whole of k_p2g_adj): gathers the adjoints of
 // (grid_v_in, grid_m) over the 27-node stencil, reads F.grad[j+1], writes x.grad (adding the g2p part already stored),
 // v.grad, C.grad, F.grad of frame j
-// Where the rows of the particle are READ from: the global arrays (component stride k.stride, index gid) or a staged copy
-// (kernels_bwd.cuh: per-warp shared memory filled by cp.async -- component stride 32, index = lane).  adj_in is indexed with
-// CF.., adj_out with CX..; `ready(n)` is called before group n of the rows is first read (0: frame and material, 1: SVD
-// tape, 2: adjoints).
-struct ParticleRows {
-  const float *fin, *mat, *svd, *adj_in, *adj_out;
-  int stride, idx;
-};
-struct RowsAlwaysReady {
-  DSK_DEV_MEMBER void operator()(int) const {}
-};
-template <class Ready>
-DSK_DEV void p2g_adj_particle_rows(const SimConst& k, int gid, int env, const ParticleRows& r, float* __restrict__ adj_out,
-                                   const float4* __restrict__ Ga, Ready ready) {
-  ready(0);
-  float3 x = load_v3(r.fin, CX, r.stride, r.idx);
-  float3 v = load_v3(r.fin, CV, r.stride, r.idx);
-  M3 C = load_m3(r.fin, CC, r.stride, r.idx);
-  M3 F = load_m3(r.fin, CF, r.stride, r.idx);
+DSK_DEV void p2g_adj_particle(const SimConst& k, int gid, int env, const float* __restrict__ fin,
+                              const float* __restrict__ adj_in, float* __restrict__ adj_out, const float* __restrict__ mat,
+                              const float4* __restrict__ Ga, const float* __restrict__ svd_in) {
+  float3 x = load_v3(fin, CX, k.stride, gid);
+  float3 v = load_v3(fin, CV, k.stride, gid);
+  M3 C = load_m3(fin, CC, k.stride, gid);
+  M3 F = load_m3(fin, CF, k.stride, gid);
   float mu, lam, ys;
-  load_mat_at(k, r.mat, r.stride, r.idx, mu, lam, ys);
+  load_mat(k, mat, gid, mu, lam, ys);
   P2GParticle o;
-  ready(1);
-  p2g_particle_adj_at(k, r.svd, r.stride, r.idx, C, F, mu, lam, ys, o);
+  p2g_particle_adj(k, svd_in, gid, C, F, mu, lam, ys, o);
   Stencil s;
   make_stencil(k, x.x, x.y, x.z, s);
   const float4* Gae = Ga + (size_t)env * k.nnode;
@@ -581,15 +560,7 @@ DSK_DEV void p2g_adj_particle_rows(const SimConst& k, int gid, int env, const Pa
     m1 = f3(m1p.x, m1p.y, m1z);
     m2 = f3(m2p.x, m2p.y, m2z);
   }
-  ready(2);
-  p2g_adj_finish(k, gid, s, o, mu, lam, C, F, load_v3(r.adj_out, CX, r.stride, r.idx), load_m3(r.adj_in, CF, r.stride, r.idx),
-                 adj_out, S0, m0, m1, m2, gwx, gwy, gwz);
-}
-DSK_DEV void p2g_adj_particle(const SimConst& k, int gid, int env, const float* __restrict__ fin,
-                              const float* __restrict__ adj_in, float* __restrict__ adj_out, const float* __restrict__ mat,
-                              const float4* __restrict__ Ga, const float* __restrict__ svd_in) {
-  ParticleRows r{fin, mat, svd_in, adj_in, adj_out, k.stride, gid};
-  p2g_adj_particle_rows(k, gid, env, r, adj_out, Ga, RowsAlwaysReady());
+  p2g_adj_finish(k, gid, s, o, mu, lam, C, F, adj_in, adj_out, S0, m0, m1, m2, gwx, gwy, gwz);
 }
 
 // ---- g2p.grad of one particle, around the scatter of the grid_v_out adjoints ------------------------------------------

@@ -3,7 +3,6 @@
 #pragma once
 #include <cmath>
 #define DSK_DEV static inline
-#define DSK_DEV_MEMBER inline
 struct float3 {
   float x, y, z;
 };
