@@ -48,7 +48,10 @@ DSK_DEV void jacobi_pair(SvdCol& p, SvdCol& q) {
     g2 *= 1.8446744e19f;
     n2 = fmaf(d, d, g2 * g2);
   }
-  if (ga != 0.f && n2 > 0.f) {
+  // converged pair: |ga| <= 6e-8 sqrt(al be), the rotation angle is below the rounding of the columns -- skipped.  Jacobi
+  // converges quadratically, so after two sweeps most warps skip all of the remaining six rotations (a warp skips when all
+  // its lanes do); rank-deficient columns (al be = 0) keep the exact test ga != 0.
+  if (ga * ga > 4e-15f * (al * be) && n2 > 0.f) {
     float rh = rsqrt_unbiased(n2);
     float u = fmaf(0.5f * fabsf(d), rh, 0.5f);     // cos^2(theta), in [0.5, 1]
     float y = rsqrt_unbiased(u);
