@@ -83,7 +83,7 @@ struct dsk_engine {
   std::vector<int> h_npart;
   std::vector<StepSlot> slot;
   // sort scratch
-  int *cell_count = nullptr, *key = nullptr, *rank = nullptr, *scan_partial = nullptr;
+  int *cell_count = nullptr, *key = nullptr, *rank = nullptr, *scan_partial = nullptr, *chunk_flag = nullptr;
   // grids: set index = epoch & 1
   float4 *G0[2], *Gv[2], *Ga[2];
   int *tile_epoch[2], *tile_list[2], *tile_count = nullptr;  // tile_count[4] ring
@@ -434,6 +434,7 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
     DA(e->cell_count, (size_t)e->B * k.nnode);
     DA(e->key, k.stride);
     DA(e->scan_partial, (size_t)e->B * cdiv(k.nnode, SCAN_CHUNK));
+    DA(e->chunk_flag, (size_t)e->B * cdiv(k.nnode, SCAN_CHUNK));
     DA(e->rank, k.stride);
     for (int s = 0; s < 2; s++) {
       DA(e->G0[s], (size_t)e->B * k.nnode);
@@ -804,18 +805,19 @@ static int seq_begin_forward(dsk_engine* e, StepSlot& s) {
     KL(KID_SORT, k_apply_perm<<<nb, 256, 0, e->qs>>>(k, e->d_args, e->mat, e->npart, e->perm_cache, s.frames, s.mat, s.perm));
   } else {
     if (e->cfg.sort_particles) {
-      CK(cudaMemsetAsync(e->cell_count, 0, (size_t)e->B * k.nnode * 4, e->qs));
-      KL(KID_SORT, k_sort_bin<<<nb, 256, 0, e->qs>>>(k, e->d_args, e->npart, e->cell_count, e->key, e->rank));
-      {
-        dim3 sg(cdiv(k.nnode, SCAN_CHUNK), e->B);
-        KL(KID_SORT, k_scan_partial<<<sg, SCAN_CTA, 0, e->qs>>>(k, e->cell_count, e->scan_partial));
-        KL(KID_SORT, k_scan_chunks<<<sg, SCAN_CTA, 0, e->qs>>>(k, e->cell_count, e->scan_partial));
-      }
+      // counters and chunk flags are all zero here (k_sort_clear below; zero-initialised)
+      KL(KID_SORT, k_sort_bin<<<nb, 256, 0, e->qs>>>(k, e->d_args, e->npart, e->cell_count, e->key, e->rank, e->chunk_flag));
+      dim3 sg(cdiv(k.nnode, SCAN_CHUNK), e->B);
+      KL(KID_SORT, k_scan_partial<<<sg, SCAN_CTA, 0, e->qs>>>(k, e->cell_count, e->scan_partial, e->chunk_flag));
+      KL(KID_SORT, k_scan_chunks<<<sg, SCAN_CTA, 0, e->qs>>>(k, e->cell_count, e->scan_partial, e->chunk_flag));
     }
     KL(KID_SORT, k_sort_scatter<<<nb, 256, 0, e->qs>>>(k, e->d_args, e->mat, e->npart, e->cell_count, e->key, e->rank,
                                                        e->cfg.sort_particles, s.frames, s.mat, s.perm));
-    if (e->cfg.sort_particles)
+    if (e->cfg.sort_particles) {
+      dim3 sg(cdiv(k.nnode, SCAN_CHUNK), e->B);
+      KL(KID_SORT, k_sort_clear<<<sg, SCAN_CTA, 0, e->qs>>>(k, e->cell_count, e->chunk_flag));
       CK(cudaMemcpyAsync(e->perm_cache, s.perm, (size_t)k.stride * 4, cudaMemcpyDeviceToDevice, e->qs));
+    }
   }
   LAUNCH_CHECK();
   return 0;
