@@ -807,15 +807,15 @@ static int seq_begin_forward(dsk_engine* e, StepSlot& s) {
     if (e->cfg.sort_particles) {
       // counters and chunk flags are all zero here (k_sort_clear below; zero-initialised)
       KL(KID_SORT, k_sort_bin<<<nb, 256, 0, e->qs>>>(k, e->d_args, e->npart, e->cell_count, e->key, e->rank, e->chunk_flag));
-      dim3 sg(cdiv(k.nnode, SCAN_CHUNK), e->B);
-      KL(KID_SORT, k_scan_partial<<<sg, SCAN_CTA, 0, e->qs>>>(k, e->cell_count, e->scan_partial, e->chunk_flag));
-      KL(KID_SORT, k_scan_chunks<<<sg, SCAN_CTA, 0, e->qs>>>(k, e->cell_count, e->scan_partial, e->chunk_flag));
+      const int chunks = cdiv(k.nnode, SCAN_CHUNK), sg = cdiv(e->B * chunks, SCAN_GROUP);
+      KL(KID_SORT, k_scan_partial<<<sg, SCAN_CTA, 0, e->qs>>>(k, e->cell_count, e->scan_partial, e->chunk_flag, chunks));
+      KL(KID_SORT, k_scan_chunks<<<sg, SCAN_CTA, 0, e->qs>>>(k, e->cell_count, e->scan_partial, e->chunk_flag, chunks));
     }
     KL(KID_SORT, k_sort_scatter<<<nb, 256, 0, e->qs>>>(k, e->d_args, e->mat, e->npart, e->cell_count, e->key, e->rank,
                                                        e->cfg.sort_particles, s.frames, s.mat, s.perm));
     if (e->cfg.sort_particles) {
-      dim3 sg(cdiv(k.nnode, SCAN_CHUNK), e->B);
-      KL(KID_SORT, k_sort_clear<<<sg, SCAN_CTA, 0, e->qs>>>(k, e->cell_count, e->chunk_flag));
+      const int chunks = cdiv(k.nnode, SCAN_CHUNK), sg = cdiv(e->B * chunks, SCAN_GROUP);
+      KL(KID_SORT, k_sort_clear<<<sg, SCAN_CTA, 0, e->qs>>>(k, e->cell_count, e->chunk_flag, chunks));
       CK(cudaMemcpyAsync(e->perm_cache, s.perm, (size_t)k.stride * 4, cudaMemcpyDeviceToDevice, e->qs));
     }
   }

@@ -35,9 +35,9 @@ __global__ void k_sort_bin(SimConst k, const StepArgs* __restrict__ args, const 
 }
 // exclusive scan of cell_count per env, in place, in two multi-CTA passes (a single CTA per env is bound by one
 // SM's bandwidth on the n^3-cell histogram), both skipping the chunks no particle fell into:
-//   k_scan_partial: grid (chunks, B): sum of each flagged SCAN_CHUNK-cell chunk (0 for the others)
-//   k_scan_chunks : grid (chunks, B): offset = sum of the preceding chunk sums, then an in-place chunk scan
-//   k_sort_clear  : grid (chunks, B), after the scatter: zeroes the flagged chunks and their flags
+//   k_scan_partial: sum of each flagged SCAN_CHUNK-cell chunk (0 for the others)
+//   k_scan_chunks : offset = sum of the preceding chunk sums of the env, then an in-place chunk scan
+//   k_sort_clear  : after the scatter: zeroes the flagged chunks and their flags
 DSK_DEV int block_sum(int v, int* sh) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -48,64 +48,82 @@ DSK_DEV int block_sum(int v, int* sh) {
   __syncthreads();
   return t;
 }
-__global__ void __launch_bounds__(SCAN_CTA) k_scan_partial(SimConst k, const int* __restrict__ cell_count, int* __restrict__ partial,
-                                                           const int* __restrict__ chunk_flag) {
-  DSK_TL(k);
-  __shared__ int sh[SCAN_CTA / 32];
-  int env = blockIdx.y, chunk = blockIdx.x;
-  if (!chunk_flag[env * gridDim.x + chunk]) {   // block-uniform
-    if (threadIdx.x == 0) partial[env * gridDim.x + chunk] = 0;
-    return;
+// A CTA takes SCAN_GROUP consecutive (env, chunk) pairs (linear index env * chunks + chunk), collects the flagged ones in
+// shared memory -- one flag load per thread, one round trip -- and works through them; launching one CTA per pair costs more
+// in CTA launches (16 384 pairs, ~90 % of them empty) than the whole scan.
+#define SCAN_GROUP 64
+DSK_DEV int flagged_chunks(const int* __restrict__ chunk_flag, int total, int* lst, int* n, int* partial_zero) {
+  if (threadIdx.x == 0) *n = 0;
+  __syncthreads();
+  const int idx = blockIdx.x * SCAN_GROUP + threadIdx.x;
+  if (threadIdx.x < SCAN_GROUP && idx < total) {
+    if (chunk_flag[idx]) lst[atomicAdd(n, 1)] = idx;
+    else if (partial_zero) partial_zero[idx] = 0;
   }
-  const int* c = cell_count + (size_t)env * k.nnode;
-  int lo = chunk * SCAN_CHUNK, hi = min(lo + SCAN_CHUNK, k.nnode);
-  int v = 0;
-  for (int i = lo + threadIdx.x; i < hi; i += SCAN_CTA) v += c[i];
-  int t = block_sum(v, sh);
-  if (threadIdx.x == 0) partial[env * gridDim.x + chunk] = t;
+  __syncthreads();
+  return *n;
+}
+// grid: cdiv(B * chunks, SCAN_GROUP)
+__global__ void __launch_bounds__(SCAN_CTA) k_scan_partial(SimConst k, const int* __restrict__ cell_count, int* __restrict__ partial,
+                                                           const int* __restrict__ chunk_flag, int chunks) {
+  DSK_TL(k);
+  __shared__ int sh[SCAN_CTA / 32], lst[SCAN_GROUP], nl;
+  const int n = flagged_chunks(chunk_flag, k.B * chunks, lst, &nl, partial);
+  for (int q = 0; q < n; q++) {
+    const int idx = lst[q], env = idx / chunks, chunk = idx - env * chunks;
+    const int* c = cell_count + (size_t)env * k.nnode;
+    int lo = chunk * SCAN_CHUNK, hi = min(lo + SCAN_CHUNK, k.nnode);
+    int v = 0;
+    for (int i = lo + threadIdx.x; i < hi; i += SCAN_CTA) v += c[i];
+    int t = block_sum(v, sh);
+    if (threadIdx.x == 0) partial[idx] = t;
+  }
 }
 __global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(SimConst k, int* __restrict__ cell_count, const int* __restrict__ partial,
-                                                          const int* __restrict__ chunk_flag) {
+                                                          const int* __restrict__ chunk_flag, int chunks) {
   DSK_TL(k);
-  __shared__ int sh[SCAN_CTA / 32];
-  __shared__ int wtot[SCAN_CTA / 32];
-  int env = blockIdx.y, chunk = blockIdx.x;
-  if (!chunk_flag[env * gridDim.x + chunk]) return;   // no particle reads the start offsets of an empty chunk
-  int* c = cell_count + (size_t)env * k.nnode;
-  int v = 0;
-  for (int i = threadIdx.x; i < chunk; i += SCAN_CTA) v += partial[env * gridDim.x + i];
-  int carry = block_sum(v, sh);
-  int lo = chunk * SCAN_CHUNK, hi = min(lo + SCAN_CHUNK, k.nnode);
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i0 = lo; i0 < hi; i0 += SCAN_CTA) {
-    int i = i0 + threadIdx.x;
-    int x = i < hi ? c[i] : 0, sc = x;
+  __shared__ int sh[SCAN_CTA / 32], wtot[SCAN_CTA / 32], lst[SCAN_GROUP], nl;
+  const int n = flagged_chunks(chunk_flag, k.B * chunks, lst, &nl, nullptr);   // empty chunks: nobody reads their offsets
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int q = 0; q < n; q++) {
+    const int idx = lst[q], env = idx / chunks, chunk = idx - env * chunks;
+    int* c = cell_count + (size_t)env * k.nnode;
+    int v = 0;
+    for (int i = threadIdx.x; i < chunk; i += SCAN_CTA) v += partial[env * chunks + i];
+    int carry = block_sum(v, sh);
+    int lo = chunk * SCAN_CHUNK, hi = min(lo + SCAN_CHUNK, k.nnode);
+    for (int i0 = lo; i0 < hi; i0 += SCAN_CTA) {
+      int i = i0 + threadIdx.x;
+      int x = i < hi ? c[i] : 0, sc = x;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, sc, o);
-      if (lane >= o) sc += t;
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, sc, o);
+        if (lane >= o) sc += t;
+      }
+      if (lane == 31) wtot[warp] = sc;
+      __syncthreads();
+      int woff = 0, tot = 0;
+      for (int w = 0; w < SCAN_CTA / 32; w++) {
+        if (w < warp) woff += wtot[w];
+        tot += wtot[w];
+      }
+      if (i < hi) c[i] = carry + woff + sc - x;
+      carry += tot;
+      __syncthreads();
     }
-    if (lane == 31) wtot[warp] = sc;
-    __syncthreads();
-    int woff = 0, tot = 0;
-    for (int w = 0; w < SCAN_CTA / 32; w++) {
-      if (w < warp) woff += wtot[w];
-      tot += wtot[w];
-    }
-    if (i < hi) c[i] = carry + woff + sc - x;
-    carry += tot;
-    __syncthreads();
   }
 }
-__global__ void __launch_bounds__(SCAN_CTA) k_sort_clear(SimConst k, int* __restrict__ cell_count, int* __restrict__ chunk_flag) {
+__global__ void __launch_bounds__(SCAN_CTA) k_sort_clear(SimConst k, int* __restrict__ cell_count, int* __restrict__ chunk_flag, int chunks) {
   DSK_TL(k);
-  int env = blockIdx.y, chunk = blockIdx.x;
-  if (!chunk_flag[env * gridDim.x + chunk]) return;
-  int* c = cell_count + (size_t)env * k.nnode;
-  int lo = chunk * SCAN_CHUNK, hi = min(lo + SCAN_CHUNK, k.nnode);
-  for (int i = lo + threadIdx.x; i < hi; i += SCAN_CTA) c[i] = 0;
-  __syncthreads();   // every thread has read the flag
-  if (threadIdx.x == 0) chunk_flag[env * gridDim.x + chunk] = 0;
+  __shared__ int lst[SCAN_GROUP], nl;
+  const int n = flagged_chunks(chunk_flag, k.B * chunks, lst, &nl, nullptr);
+  for (int q = 0; q < n; q++) {
+    const int idx = lst[q], env = idx / chunks, chunk = idx - env * chunks;
+    int* c = cell_count + (size_t)env * k.nnode;
+    int lo = chunk * SCAN_CHUNK, hi = min(lo + SCAN_CHUNK, k.nnode);
+    for (int i = lo + threadIdx.x; i < hi; i += SCAN_CTA) c[i] = 0;
+    if (threadIdx.x == 0) chunk_flag[idx] = 0;   // every flag of the group was read before the barrier in flagged_chunks
+  }
 }
 // scatter checkpoint (canonical order) -> work frame 0 (sorted order); also permutes the material arrays
 __global__ void k_sort_scatter(SimConst k, const StepArgs* __restrict__ args, const float* __restrict__ mat,
