@@ -153,6 +153,8 @@ struct dsk_engine {
   bool mat_uniform = true;  // no per-particle material set: the particle kernels take (mu, lam, yield_stress) from SimConst
   bool flat_grid = false;   // many active tiles: throughput layout of the grid kernels
   bool ts = true;           // batched engines: transposed shared-memory scatter (warp_scatter27_ts_affine) instead of the shuffle butterfly
+  bool perm_smem = true;    // batched engines: frame permutations through shared memory (k_permute_rows)
+  bool perm_opt_in[3] = {false, false, false};
   bool ts_pl = false;       // ... in the plane-split kernels of single scenes (slower there: r02b liftspread 46.3 vs 42.3 ms)
   cudaStream_t cap_side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -403,6 +405,7 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
   e->flat_grid = e->big;
   if (const char* v = getenv("DSK_GRID_CTAS_PER_SM")) e->grid_ctas_per_sm = std::max(1, atoi(v));
   if (const char* v = getenv("DSK_TS")) e->ts = atoi(v) != 0;
+  if (const char* v = getenv("DSK_PERM_SMEM")) e->perm_smem = atoi(v) != 0;
   if (const char* v = getenv("DSK_TS_PL")) e->ts_pl = atoi(v) != 0;
   if (const char* v = getenv("DSK_FLAT_GRID")) e->flat_grid = atoi(v) != 0;
   e->tool_floats = (size_t)e->B * std::max(1, e->K) * 8;
@@ -772,6 +775,33 @@ static int push_args(dsk_engine* e, const StepArgs& a) {
   return 0;
 }
 
+// Frames are permuted through shared memory (k_permute_rows) when a few rows of one env fit there and the batch is large
+// enough to fill the GPU; returns 0 if it launched, 1 if the caller has to use the element-wise kernel, -1 on error.
+// `rows` of the frame are moved by one CTA: the largest divisor of nrows that keeps the CTA at <= 72 KB (3 CTAs per SM).
+static int perm_rows_per_cta(dsk_engine* e, int nrows) {
+  if (!e->big || !e->perm_smem) return 0;
+  const size_t row = (size_t)e->k.Npad * sizeof(float);
+  int best = 0;
+  for (int g = 1; g <= nrows; g++)
+    if (nrows % g == 0 && g * row <= 72 * 1024) best = g;
+  if (!best && row <= 200 * 1024) best = 1;
+  return best;
+}
+template <int MODE>
+static int launch_permute(dsk_engine* e, int kid, const float* in, const float* const* pin, float* out, float* const* pout,
+                          const int* perm, int nrows) {
+  const int g = perm_rows_per_cta(e, nrows);
+  if (!g) return 1;
+  const size_t sm = (size_t)g * e->k.Npad * sizeof(float);
+  if (sm > 48 * 1024 && !e->perm_opt_in[MODE]) {
+    CK(cudaFuncSetAttribute(k_permute_rows<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    e->perm_opt_in[MODE] = true;
+  }
+  KL(kid, (k_permute_rows<MODE><<<dim3(nrows / g, e->B), PERM_CTA, sm, e->qs>>>(e->k, in, pin, out, pout, e->npart, perm, g)));
+  LAUNCH_CHECK();
+  return 0;
+}
+
 // ---- pieces of a sequence (all enqueue on e->qs) --------------------------------------------------------------
 static int seq_begin_forward(dsk_engine* e, StepSlot& s) {
   SimConst& k = e->k;
@@ -802,7 +832,7 @@ static int seq_begin_forward(dsk_engine* e, StepSlot& s) {
     }
   }
   if (e->cfg.sort_particles && !e->seq_full_sort) {
-    KL(KID_SORT, k_apply_perm<<<nb, 256, 0, e->qs>>>(k, e->d_args, e->mat, e->npart, e->perm_cache, s.frames, s.mat, s.perm));
+    KL(KID_SORT, k_apply_perm<<<nb, 256, 0, e->qs>>>(k, e->d_args, e->mat, e->npart, e->perm_cache, s.frames, s.mat, s.perm));   // rare path (DSK_RESORT_INTERVAL > 1)
   } else {
     if (e->cfg.sort_particles) {
       // counters and chunk flags are all zero here (k_sort_clear below; zero-initialised)
@@ -811,8 +841,17 @@ static int seq_begin_forward(dsk_engine* e, StepSlot& s) {
       KL(KID_SORT, k_scan_partial<<<sg, SCAN_CTA, 0, e->qs>>>(k, e->cell_count, e->scan_partial, e->chunk_flag, chunks));
       KL(KID_SORT, k_scan_chunks<<<sg, SCAN_CTA, 0, e->qs>>>(k, e->cell_count, e->scan_partial, e->chunk_flag, chunks));
     }
-    KL(KID_SORT, k_sort_scatter<<<nb, 256, 0, e->qs>>>(k, e->d_args, e->mat, e->npart, e->cell_count, e->key, e->rank,
-                                                       e->cfg.sort_particles, s.frames, s.mat, s.perm));
+    bool moved = false;
+    if (e->cfg.sort_particles && perm_rows_per_cta(e, FRAME_COMPS)) {
+      // permutation first (ints only), then the frame -- and the material rows if there are any -- through shared memory
+      KL(KID_SORT, k_sort_perm<<<nb, 256, 0, e->qs>>>(k, e->npart, e->cell_count, e->key, e->rank, s.perm));
+      if (launch_permute<0>(e, KID_SORT, nullptr, &e->d_args->ck_src, s.frames, nullptr, s.perm, FRAME_COMPS) < 0) return -1;
+      if (!e->mat_uniform && launch_permute<0>(e, KID_SORT, e->mat, nullptr, s.mat, nullptr, s.perm, 3) < 0) return -1;
+      moved = true;
+    }
+    if (!moved)
+      KL(KID_SORT, k_sort_scatter<<<nb, 256, 0, e->qs>>>(k, e->d_args, e->mat, e->npart, e->cell_count, e->key, e->rank,
+                                                         e->cfg.sort_particles, s.frames, s.mat, s.perm));
     if (e->cfg.sort_particles) {
       const int chunks = cdiv(k.nnode, SCAN_CHUNK), sg = cdiv(e->B * chunks, SCAN_GROUP);
       KL(KID_SORT, k_sort_clear<<<sg, SCAN_CTA, 0, e->qs>>>(k, e->cell_count, e->chunk_flag, chunks));
@@ -887,8 +926,12 @@ static int seq_forward_fused(dsk_engine* e, StepSlot& s) {
 static int seq_end_forward(dsk_engine* e, StepSlot& s, bool store) {
   SimConst& k = e->k;
   if (store) {
-    KL(KID_REORDER, k_unsort<<<cdiv(k.stride, 256), 256, 0, e->qs>>>(k, s.frames + (size_t)e->S * e->frame_floats,
-                                                                    e->npart, s.perm, &e->d_args->ck_dst, 0));
+    int rc = launch_permute<1>(e, KID_REORDER, s.frames + (size_t)e->S * e->frame_floats, nullptr, nullptr, &e->d_args->ck_dst,
+                               s.perm, FRAME_COMPS);
+    if (rc < 0) return -1;
+    if (rc > 0)
+      KL(KID_REORDER, k_unsort<<<cdiv(k.stride, 256), 256, 0, e->qs>>>(k, s.frames + (size_t)e->S * e->frame_floats,
+                                                                      e->npart, s.perm, &e->d_args->ck_dst, 0));
     const bool next_kin = e->qs == e->cap_stream && e->seq_next_slot != nullptr && e->K > 0;
     if (e->K > 0 && !e->seq_skip_kin && !next_kin) KL(KID_IO, k_tool_store<<<cdiv(e->B * e->K * 8, 128), 128, 0, e->qs>>>(k, s.poses, e->d_args));
     if (next_kin) CK(cudaStreamWaitEvent(e->qs, e->ev_join2, 0));   // join the lookahead branch
@@ -907,7 +950,12 @@ static int seq_clear(dsk_engine* e, int last_q, bool bwd) {
 static int seq_begin_backward(dsk_engine* e, StepSlot& s) {
   SimConst& k = e->k;
   e->bwd_cur = 0;
-  KL(KID_REORDER, k_gather_sorted<<<cdiv(k.stride, 256), 256, 0, e->qs>>>(k, &e->d_args->adj_in, e->npart, s.perm, e->adjw[0]));
+  {
+    int rc = launch_permute<0>(e, KID_REORDER, nullptr, &e->d_args->adj_in, e->adjw[0], nullptr, s.perm, FRAME_COMPS);
+    if (rc < 0) return -1;
+    if (rc > 0)
+      KL(KID_REORDER, k_gather_sorted<<<cdiv(k.stride, 256), 256, 0, e->qs>>>(k, &e->d_args->adj_in, e->npart, s.perm, e->adjw[0]));
+  }
   if (e->K > 0)
     KL(KID_IO, k_pose_adj_init<<<cdiv(e->B * (e->S + 1) * e->K * 8, 128), 128, 0, e->qs>>>(k, e->pose_adj, e->seq_defer_tools ? nullptr : e->d_args));
   LAUNCH_CHECK();
@@ -968,7 +1016,12 @@ static int enqueue_tool_adjoints(dsk_engine* e, StepSlot& s, const StepArgs* arg
 static int seq_end_backward(dsk_engine* e, StepSlot& s) {
   SimConst& k = e->k;
   if (e->K > 0 && !e->seq_defer_tools && enqueue_tool_adjoints(e, s, e->d_args, false)) return -1;
-  KL(KID_REORDER, k_unsort<<<cdiv(k.stride, 256), 256, 0, e->qs>>>(k, e->adjw[e->bwd_cur], e->npart, s.perm, &e->d_args->adj_out, 1));
+  {
+    int rc = launch_permute<2>(e, KID_REORDER, e->adjw[e->bwd_cur], nullptr, nullptr, &e->d_args->adj_out, s.perm, FRAME_COMPS);
+    if (rc < 0) return -1;
+    if (rc > 0)
+      KL(KID_REORDER, k_unsort<<<cdiv(k.stride, 256), 256, 0, e->qs>>>(k, e->adjw[e->bwd_cur], e->npart, s.perm, &e->d_args->adj_out, 1));
+  }
   LAUNCH_CHECK();
   return 0;
 }
