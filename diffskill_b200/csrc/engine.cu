@@ -775,31 +775,39 @@ static int push_args(dsk_engine* e, const StepArgs& a) {
   return 0;
 }
 
-// Frames are permuted through shared memory (k_permute_rows) when a few rows of one env fit there and the batch is large
-// enough to fill the GPU; returns 0 if it launched, 1 if the caller has to use the element-wise kernel, -1 on error.
-// `rows` of the frame are moved by one CTA: the largest divisor of nrows that keeps the CTA at <= 72 KB (3 CTAs per SM).
+// Frames are permuted through shared memory (k_permute_rows) when rows of one env fit there and the batch is large enough
+// to fill the GPU; launch_permute returns 0 if it launched, 1 if the caller has to use the element-wise kernel, -1 on error.
+// Rows per CTA: the largest of 8, 4, 2 that divides nrows and stays within 48 KB (several CTAs per SM: a batch of 64 envs
+// gives 384 CTAs of 32 KB), else 1 row of up to 200 KB.
 static int perm_rows_per_cta(dsk_engine* e, int nrows) {
   if (!e->big || !e->perm_smem) return 0;
   const size_t row = (size_t)e->k.Npad * sizeof(float);
-  int best = 0;
-  for (int g = 1; g <= nrows; g++)
-    if (nrows % g == 0 && g * row <= 72 * 1024) best = g;
-  if (!best && row <= 200 * 1024) best = 1;
-  return best;
+  for (int g = 8; g >= 2; g >>= 1)
+    if (nrows % g == 0 && g * row <= 48 * 1024) return g;
+  return row <= 200 * 1024 ? 1 : 0;
+}
+template <int MODE, int ROWS>
+static int launch_permute_rows(dsk_engine* e, int kid, const float* in, const float* const* pin, float* out, float* const* pout,
+                               const int* perm, int nrows) {
+  const size_t sm = (size_t)ROWS * e->k.Npad * sizeof(float);
+  if (sm > 48 * 1024 && !e->perm_opt_in[MODE]) {   // only ROWS == 1 gets here
+    CK(cudaFuncSetAttribute(k_permute_rows<MODE, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    e->perm_opt_in[MODE] = true;
+  }
+  KL(kid, (k_permute_rows<MODE, ROWS><<<dim3(nrows / ROWS, e->B), PERM_CTA, sm, e->qs>>>(e->k, in, pin, out, pout, e->npart, perm)));
+  LAUNCH_CHECK();
+  return 0;
 }
 template <int MODE>
 static int launch_permute(dsk_engine* e, int kid, const float* in, const float* const* pin, float* out, float* const* pout,
                           const int* perm, int nrows) {
-  const int g = perm_rows_per_cta(e, nrows);
-  if (!g) return 1;
-  const size_t sm = (size_t)g * e->k.Npad * sizeof(float);
-  if (sm > 48 * 1024 && !e->perm_opt_in[MODE]) {
-    CK(cudaFuncSetAttribute(k_permute_rows<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    e->perm_opt_in[MODE] = true;
+  switch (perm_rows_per_cta(e, nrows)) {
+    case 8: return launch_permute_rows<MODE, 8>(e, kid, in, pin, out, pout, perm, nrows);
+    case 4: return launch_permute_rows<MODE, 4>(e, kid, in, pin, out, pout, perm, nrows);
+    case 2: return launch_permute_rows<MODE, 2>(e, kid, in, pin, out, pout, perm, nrows);
+    case 1: return launch_permute_rows<MODE, 1>(e, kid, in, pin, out, pout, perm, nrows);
+    default: return 1;
   }
-  KL(kid, (k_permute_rows<MODE><<<dim3(nrows / g, e->B), PERM_CTA, sm, e->qs>>>(e->k, in, pin, out, pout, e->npart, perm, g)));
-  LAUNCH_CHECK();
-  return 0;
 }
 
 // ---- pieces of a sequence (all enqueue on e->qs) --------------------------------------------------------------

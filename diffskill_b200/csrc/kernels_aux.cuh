@@ -199,41 +199,56 @@ __global__ void k_gather_sorted(SimConst k, float* const* __restrict__ pck, cons
 // side: every such access moves a 32-byte sector (8x the useful bytes), and the read-modify-write of the adjoint un-sort is
 // worse (r02x timeline, GatherMove x64: 55 us per adjoint reorder, 32 us for the sort's scatter -- 24 MB of useful traffic).
 // Here a CTA takes `rows` rows of ONE env, brings the randomly-addressed side through shared memory and touches global
-// memory with coalesced accesses only.  grid (24 / rows, B), dynamic shared memory rows * Npad floats.
+// memory with coalesced accesses only.  grid (nrows / ROWS, B), dynamic shared memory ROWS * Npad floats.
 //   MODE 0 gather          out[i]        = in[perm[i]]     (canonical -> sorted: sort, cached sort, adjoint checkpoint)
 //   MODE 1 scatter         out[perm[i]]  = in[i]           (sorted -> canonical checkpoint)
 //   MODE 2 scatter-add     out[perm[i]] += in[i]           (sorted adjoint -> canonical adjoint checkpoint)
 // pin / pout: when non-null the array is *pin / *pout (device-resident step arguments, see StepArgs).
 #define PERM_CTA 256
-template <int MODE>
+template <int MODE, int ROWS>
 __global__ void __launch_bounds__(PERM_CTA)
     k_permute_rows(SimConst k, const float* in, const float* const* pin, float* out, float* const* pout,
-                   const int* __restrict__ npart, const int* __restrict__ perm, int rows) {
+                   const int* __restrict__ npart, const int* __restrict__ perm) {
   DSK_TL(k);
   DSK_DYN_SMEM(float, sm);
   const float* __restrict__ src = pin ? *pin : in;
   float* __restrict__ dst = pout ? *pout : out;
-  const int env = blockIdx.y, r0 = blockIdx.x * rows, n = npart[env], base = env * k.Npad;
+  const int env = blockIdx.y, r0 = blockIdx.x * ROWS, n = npart[env], base = env * k.Npad;
+  // ROWS independent accesses per loop iteration (unrolled): the loads of an iteration are all in flight together
   if (MODE == 0) {
-    for (int r = 0; r < rows; r++)
-      for (int p = threadIdx.x; p < n; p += PERM_CTA) sm[r * k.Npad + p] = src[(size_t)(r0 + r) * k.stride + base + p];
+    for (int p = threadIdx.x; p < n; p += PERM_CTA) {
+      float v[ROWS];
+#pragma unroll
+      for (int r = 0; r < ROWS; r++) v[r] = src[(size_t)(r0 + r) * k.stride + base + p];
+#pragma unroll
+      for (int r = 0; r < ROWS; r++) sm[r * k.Npad + p] = v[r];
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += PERM_CTA) {
       const int pi = perm[base + i];
-      for (int r = 0; r < rows; r++) dst[(size_t)(r0 + r) * k.stride + base + i] = sm[r * k.Npad + pi];
+#pragma unroll
+      for (int r = 0; r < ROWS; r++) dst[(size_t)(r0 + r) * k.stride + base + i] = sm[r * k.Npad + pi];
     }
   } else {
     for (int i = threadIdx.x; i < n; i += PERM_CTA) {
       const int pi = perm[base + i];
-      for (int r = 0; r < rows; r++) sm[r * k.Npad + pi] = src[(size_t)(r0 + r) * k.stride + base + i];
+      float v[ROWS];
+#pragma unroll
+      for (int r = 0; r < ROWS; r++) v[r] = src[(size_t)(r0 + r) * k.stride + base + i];
+#pragma unroll
+      for (int r = 0; r < ROWS; r++) sm[r * k.Npad + pi] = v[r];
     }
     __syncthreads();
-    for (int r = 0; r < rows; r++)
-      for (int p = threadIdx.x; p < n; p += PERM_CTA) {
-        float* d = dst + (size_t)(r0 + r) * k.stride + base + p;
-        if (MODE == 2) *d += sm[r * k.Npad + p];
-        else *d = sm[r * k.Npad + p];
+    for (int p = threadIdx.x; p < n; p += PERM_CTA) {
+      float v[ROWS];
+      if (MODE == 2) {
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) v[r] = dst[(size_t)(r0 + r) * k.stride + base + p];
       }
+#pragma unroll
+      for (int r = 0; r < ROWS; r++)
+        dst[(size_t)(r0 + r) * k.stride + base + p] = (MODE == 2 ? v[r] : 0.f) + sm[r * k.Npad + p];
+    }
   }
 }
 // the sort's permutation alone: perm[slot in sorted order] = canonical index (k_sort_scatter without the data movement)
