@@ -154,6 +154,7 @@ struct dsk_engine {
   bool flat_grid = false;   // many active tiles: throughput layout of the grid kernels
   bool ts = true;           // batched engines: transposed shared-memory scatter (warp_scatter27_ts_affine) instead of the shuffle butterfly
   bool perm_smem = true;    // batched engines: frame permutations through shared memory (k_permute_rows)
+  bool perm_smem_small = false;   // ... also for single scenes (DSK_PERM_SMEM_SMALL)
   bool perm_opt_in[3] = {false, false, false};
   bool ts_pl = false;       // ... in the plane-split kernels of single scenes (slower there: r02b liftspread 46.3 vs 42.3 ms)
   cudaStream_t cap_side = nullptr;
@@ -406,6 +407,7 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
   if (const char* v = getenv("DSK_GRID_CTAS_PER_SM")) e->grid_ctas_per_sm = std::max(1, atoi(v));
   if (const char* v = getenv("DSK_TS")) e->ts = atoi(v) != 0;
   if (const char* v = getenv("DSK_PERM_SMEM")) e->perm_smem = atoi(v) != 0;
+  if (const char* v = getenv("DSK_PERM_SMEM_SMALL")) e->perm_smem_small = atoi(v) != 0;
   if (const char* v = getenv("DSK_TS_PL")) e->ts_pl = atoi(v) != 0;
   if (const char* v = getenv("DSK_FLAT_GRID")) e->flat_grid = atoi(v) != 0;
   e->tool_floats = (size_t)e->B * std::max(1, e->K) * 8;
@@ -780,7 +782,7 @@ static int push_args(dsk_engine* e, const StepArgs& a) {
 // Rows per CTA: the largest of 8, 4, 2 that divides nrows and stays within 48 KB (several CTAs per SM: a batch of 64 envs
 // gives 384 CTAs of 32 KB), else 1 row of up to 200 KB.
 static int perm_rows_per_cta(dsk_engine* e, int nrows) {
-  if (!e->big || !e->perm_smem) return 0;
+  if (!e->perm_smem || (!e->big && !e->perm_smem_small)) return 0;
   const size_t row = (size_t)e->k.Npad * sizeof(float);
   for (int g = 8; g >= 2; g >>= 1)
     if (nrows % g == 0 && g * row <= 48 * 1024) return g;
