@@ -232,6 +232,7 @@ static int dalloc(dsk_engine* e, T** p, size_t count, bool zero = true) {
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static float* svd_at(dsk_engine* e, StepSlot& s, int j);
 static size_t kin_smem(dsk_engine* e);
+static int kin_block(dsk_engine* e, bool hidden);
 static void drop_graphs(dsk_engine* e);
 static int ts_opt_in(dsk_engine* e);
 
@@ -629,6 +630,11 @@ static int grid_ctas(dsk_engine* e) { return e->big ? 148 * 8 : 148 * e->grid_ct
 static float* svd_at(dsk_engine* e, StepSlot& s, int j) {
   return s.svd ? s.svd + (size_t)j * SVD_COMPS * e->k.stride : nullptr;
 }
+// Threads per CTA of k_kinematics (one CTA per env).  Without tool-tool pairs the kernel is one pose chain per tool: two warps.
+// With pairs the warps share the collision queries: 32 warps when the kernel is on the critical path; 8 on the lookahead
+// branch, where it has a whole env step to finish -- a 1024-thread CTA needs a whole SM's register file, so next to the
+// particle kernels its CTAs waited ~150 us for SMs to drain and then held them (r02z timeline, GatherMove x64).
+static int kin_block(dsk_engine* e, bool hidden) { return e->k.npairs == 0 ? 64 : (hidden ? 256 : KIN_CTA); }
 static size_t kin_smem(dsk_engine* e) {   // pose chain + the collision samples of every pair
   return (size_t)(e->S + 1) * e->K * 32 + (size_t)e->k.npairs * DSK_NUM_COLLISION_POINTS * 12;
 }
@@ -825,7 +831,7 @@ static int seq_begin_forward(dsk_engine* e, StepSlot& s) {
       CK(cudaEventRecord(e->ev_fork, e->qs));
       CK(cudaStreamWaitEvent(e->cap_side, e->ev_fork, 0));
       if (!e->seq_skip_kin) {
-        KL(KID_KINEMATICS, k_kinematics<<<e->B, KIN_CTA, kin_smem(e), e->cap_side>>>(k, e->d_tools, e->d_args, e->rand_num, s.poses, s.cidx));
+        KL(KID_KINEMATICS, k_kinematics<<<e->B, kin_block(e, false), kin_smem(e), e->cap_side>>>(k, e->d_tools, e->d_args, e->rand_num, s.poses, s.cidx));
         CK(cudaEventRecord(e->ev_join, e->cap_side));
         e->kin_join = true;
       }
@@ -833,12 +839,12 @@ static int seq_begin_forward(dsk_engine* e, StepSlot& s) {
         StepSlot& nx = *e->seq_next_slot;
         const StepArgs* na = e->d_args_kin + e->seq_next_step;
         if (!e->seq_skip_kin) KL(KID_IO, k_tool_store<<<cdiv(e->B * e->K * 8, 128), 128, 0, e->cap_side>>>(k, s.poses, e->d_args));
-        KL(KID_KINEMATICS, k_kinematics<<<e->B, KIN_CTA, kin_smem(e), e->cap_side>>>(k, e->d_tools, na, e->rand_num, nx.poses, nx.cidx));
+        KL(KID_KINEMATICS, k_kinematics<<<e->B, kin_block(e, true), kin_smem(e), e->cap_side>>>(k, e->d_tools, na, e->rand_num, nx.poses, nx.cidx));
         KL(KID_IO, k_tool_store<<<cdiv(e->B * e->K * 8, 128), 128, 0, e->cap_side>>>(k, nx.poses, na));
         CK(cudaEventRecord(e->ev_join2, e->cap_side));
       }
     } else {
-      KL(KID_KINEMATICS, k_kinematics<<<e->B, KIN_CTA, kin_smem(e), e->qs>>>(k, e->d_tools, e->d_args, e->rand_num, s.poses, s.cidx));
+      KL(KID_KINEMATICS, k_kinematics<<<e->B, kin_block(e, false), kin_smem(e), e->qs>>>(k, e->d_tools, e->d_args, e->rand_num, s.poses, s.cidx));
     }
   }
   if (e->cfg.sort_particles && !e->seq_full_sort) {

@@ -397,7 +397,7 @@ __global__ void k_loss_l2(SimConst k, const float* __restrict__ frame, float* __
   if ((threadIdx.x & 31) == 0 && l != 0.f && gid < k.stride) atomicAdd(&loss[env], l);
 }
 
-#define KIN_CTA 1024   // one CTA per env: 32 warps share the S*npairs collision queries of the optimistic pass
+#define KIN_CTA 1024   // largest CTA (one per env): its warps share the S*npairs collision queries of the optimistic pass; see kin_block()
 // One CTA per env: S substeps of forward_kinematics for every tool, then (if any pair) set_surface_points,
 // set_collision_idx (deterministic first minimum) and apply_collision_projection (mpm_simulator.py:286-305).
 // Tool-tool projections are rare, so the kernel is optimistic: (1) the kinematics chain of all S substeps without
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(KIN_CTA)
   __syncthreads();
   if (k.npairs > 0) {   // (2) all collision queries at once, one warp per (substep, pair)
     int warp = tid >> 5, lane = tid & 31;
-    for (int it = warp; it < k.S * k.npairs; it += KIN_CTA / 32) {
+    for (int it = warp; it < k.S * k.npairs; it += (int)(blockDim.x >> 5)) {
       int j = it / k.npairs, c = it - j * k.npairs;
       int ti = k.pairs[c][0], tj = k.pairs[c][1];
       Pose Pi = load_pose(sAll + (size_t)(j + 1) * per + ti * 8), Pj = load_pose(sAll + (size_t)(j + 1) * per + tj * 8);
@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(KIN_CTA)
     __syncthreads();
     if (k.npairs > 0) {
       // all pairs at once: the warps are split evenly between the pairs (every query reads the pre-projection poses)
-      const int wpp = (KIN_CTA / 32) / k.npairs;           // warps per pair (DSK_MAX_PAIRS <= 8 -> at least 4)
+      const int wpp = (int)(blockDim.x >> 5) / k.npairs;   // warps per pair (>= 8 warps per CTA, DSK_MAX_PAIRS <= 8 -> at least 1)
       const int warp = tid >> 5, lane = tid & 31;
       const int c = min(warp / wpp, k.npairs - 1), wq = warp - c * wpp;
       const bool worker = warp < wpp * k.npairs;
