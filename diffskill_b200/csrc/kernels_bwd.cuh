@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4)
   const int l = tid & 63;
   // software pipeline over the tile loop (see k_grid_flat): the tile list runs two iterations ahead, (momentum, mass) and
   // adjoint tile one iteration ahead of the arithmetic; count and both list heads come in one round trip
-  const int it0 = blockIdx.x * FLAT_TILES + (w >> 1), stride = gridDim.x * FLAT_TILES;
+  const int it0 = flat_first_tile(w >> 1), stride = gridDim.x * FLAT_TILES;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const int n_active = load_int_here(count);
   int gt_n = list_head(k, list, it0), gt_nn = list_head(k, list, it0 + stride);

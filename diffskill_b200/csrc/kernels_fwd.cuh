@@ -197,9 +197,14 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
 struct WarpFrames {   // per warp, shared memory
   Frame F0[MAX_FRAMES], F1[MAX_FRAMES];
 };
+// Tile of the list a warp pair starts with; it advances by gridDim.x * FLAT_TILES.  Neighbours in the list go to DIFFERENT
+// CTAs: the tiles a tool touches are neighbours in the list (it is built in particle order) and cost ~10x the others, and
+// with four neighbours per CTA the SMs that got them ran 3x longer than the average (r03d: sm__cycles_active max 43.7 k,
+// avg 15.0 k in k_grid_adj_flat with the gripper in contact; 13.0 k / 11.5 k without contact).
+DSK_DEV int flat_first_tile(int pair) { return (int)blockIdx.x + pair * (int)gridDim.x; }
 DSK_DEV void clear_tiles_flat(const int* __restrict__ list, int count, int first, float4* c0, float4* c1, float4* c2) {
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int i0 = blockIdx.x * FLAT_TILES + (threadIdx.x >> 6);
+  const int i0 = flat_first_tile(threadIdx.x >> 6);
   for (int i = i0; i < count; i += gridDim.x * FLAT_TILES) {
     size_t o = ((size_t)(i == i0 ? first : list[i]) << 6) + (threadIdx.x & 63);
     if (c0) c0[o] = z;
@@ -225,7 +230,7 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4)
                 float4* clr2, int* zero_count, GridTape tape, const int* __restrict__ run_if) {
   DSK_TL(k);
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  const int it0 = blockIdx.x * FLAT_TILES + (w >> 1), stride = gridDim.x * FLAT_TILES;
+  const int it0 = flat_first_tile(w >> 1), stride = gridDim.x * FLAT_TILES;
   // every scalar of the prologue in one round trip (see list_head); the tile list runs TWO iterations ahead of the tile
   // data, which runs one ahead of the arithmetic
   const int run = run_if ? load_int_here(run_if) : 1;
