@@ -143,7 +143,7 @@ struct dsk_engine {
   std::vector<int> tl_kid;
 #endif
   bool big = false;   // enough particles to fill the machine: prefer occupancy over registers
-  float* gadj_scratch[2] = {nullptr, nullptr};   // parked contact adjoints of k_grid_adj (latency layout only)
+  float* gadj_scratch[2] = {nullptr, nullptr};   // parked contact adjoints of k_grid_adj / k_grid_adj_flat
   int* gadj_flags[2] = {nullptr, nullptr};
   int gadj_cap = 0;
   // resident 128-thread CTAs per SM requested from the particle kernels of batched engines (register cap 65536/(128*n))
@@ -449,12 +449,12 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
       DA(e->tile_epoch[s], (size_t)e->B * k.ntile);
       DA(e->tile_list[s], (size_t)e->B * k.ntile);
     }
-    if (!e->flat_grid && !getenv("DSK_NO_GRID_ADJ_SPLIT")) {
-      e->gadj_cap = (int)std::min<size_t>((size_t)e->B * k.ntile, 4096);
+    if (!getenv("DSK_NO_GRID_ADJ_SPLIT")) {
+      e->gadj_cap = (int)std::min<size_t>((size_t)e->B * k.ntile, e->flat_grid ? 32768 : 4096);
       int nf = std::min(e->n_frames, MAX_FRAMES);
       for (int s = 0; s < 2; s++) {
         DA(e->gadj_scratch[s], (size_t)e->gadj_cap * nf * 7 * GRID_NODES);
-        DA(e->gadj_flags[s], (size_t)e->gadj_cap * MAX_FRAMES);
+        DA(e->gadj_flags[s], (size_t)e->gadj_cap * MAX_FRAMES * 2);
       }
     }
     if (kin_smem(e) > 48 * 1024) {
@@ -648,7 +648,7 @@ static dim3 grid_block(dsk_engine* e) { return dim3(GRID_NODES, std::min(e->n_fr
   } while (0)
 #define GRID_ADJ_LAUNCH(e, stream, sc, ...)                                            \
   do {                                                                                 \
-    if ((e)->flat_grid) k_grid_adj_flat<<<148 * 4, FLAT_THREADS, 0, stream>>>(__VA_ARGS__); \
+    if ((e)->flat_grid) k_grid_adj_flat<<<148 * 4, FLAT_THREADS, 0, stream>>>(__VA_ARGS__, sc); \
     else k_grid_adj<<<grid_ctas(e), grid_block(e), 0, stream>>>(__VA_ARGS__, sc);      \
   } while (0)
 
@@ -1059,7 +1059,7 @@ static int enqueue_backward_pipelined(dsk_engine* e, StepSlot& s) {
     TileTrack tt{e->tile_epoch[set], e->tile_list[set], e->tile_count + ((q + 1) & 3)};
     if (q >= 2) {
       CK(cudaStreamWaitEvent(side, e->ev_main[q - 2], 0));
-      if (!e->flat_grid && e->gadj_scratch[0]) {   // position q-2 used this set and parked its contact adjoints
+      if (e->gadj_scratch[0]) {   // position q-2 used this set and parked its contact adjoints
         GridAdjScratch sc{e->gadj_scratch[q & 1], e->gadj_flags[q & 1], e->gadj_cap};
         KL(KID_GRID_ADJ_TOOLS, k_grid_adj_tools<<<grid_ctas(e), grid_block(e), 0, side>>>(
                                    k, e->grid_tools, s.poses, e->S - 1 - (q - 2), e->G0[set], e->tile_list[set],
@@ -1079,7 +1079,7 @@ static int enqueue_backward_pipelined(dsk_engine* e, StepSlot& s) {
     if (launch_g2p_adj(e, fin, fnext, ain, aout, e->Gv[set], e->Ga[set])) return -1;   // on e->qs == mainq
     // the pose adjoints of the contacts leave the critical path: parked here, reduced on the side branch two
     // positions later (before this grid set is cleared); the last two positions do them inline
-    bool park = !e->flat_grid && e->gadj_scratch[0] && q + 2 < e->S;
+    bool park = e->gadj_scratch[0] && q + 2 < e->S;
     GridAdjScratch sc{park ? e->gadj_scratch[q & 1] : nullptr, park ? e->gadj_flags[q & 1] : nullptr, park ? e->gadj_cap : 0};
     KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, mainq, sc, k, e->grid_tools, s.poses, j, e->G0[set], e->Ga[set],
                                                                           tt.list, tt.count, e->pose_adj));

@@ -185,7 +185,7 @@ DSK_DEV void frame_pose_adjoint(const SimConst& k, const ToolParams* sT, const F
 // the contact geometry (gD, gcv, gdist) there and k_grid_adj_tools turns them into pose adjoints on a side branch.
 struct GridAdjScratch {
   float* data;   // [cap][n_frames][7][64], indexed by position in the active-tile list (null: inline pose adjoints)
-  int* flags;    // [cap][MAX_FRAMES] frame had a contact in the tile
+  int* flags;    // [cap][MAX_FRAMES][2] frame had a contact in the tile (two writers: the half tiles of the flat kernel)
   int cap;
 };
 // grid_op.grad over the active tiles, blockDim = (64, n_frames).  G0: (momentum, mass) of the recomputed p2g.
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
       Ga[o] = outv;
     }
     const bool park = sc.data != nullptr && it < sc.cap;   // uniform
-    if (park && l == 0 && y < ft.n && !any) sc.flags[it * MAX_FRAMES + y] = 0;
+    if (park && l == 0 && y < ft.n && !any) sc.flags[(it * MAX_FRAMES + y) * 2] = sc.flags[(it * MAX_FRAMES + y) * 2 + 1] = 0;
     if (!any) {   // no tool near this tile: nothing to differentiate through (uniform branch)
       __syncthreads();
       continue;
@@ -275,7 +275,10 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
     __syncthreads();
     if (park) {
       if (y < ft.n) {
-        if (l == 0) sc.flags[it * MAX_FRAMES + y] = any_contact[y];
+        if (l == 0) {
+          sc.flags[(it * MAX_FRAMES + y) * 2] = any_contact[y];
+          sc.flags[(it * MAX_FRAMES + y) * 2 + 1] = 0;
+        }
         if (any_contact[y]) {
           const ContactGeomAdj& a = gadj[y][l];
           bool hit = geo[y][l].influence >= 0.f;
@@ -309,9 +312,9 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
   int n_active = min(*count, sc.cap);
   for (int it = blockIdx.x; it < n_active; it += gridDim.x) {
     int anyf = 0;
-    for (int f = 0; f < ft.n; f++) anyf |= sc.flags[it * MAX_FRAMES + f];
+    for (int f = 0; f < ft.n; f++) anyf |= sc.flags[(it * MAX_FRAMES + f) * 2] | sc.flags[(it * MAX_FRAMES + f) * 2 + 1];
     if (!anyf) continue;   // uniform
-    const bool fl = y < ft.n && sc.flags[it * MAX_FRAMES + y] != 0;
+    const bool fl = y < ft.n && (sc.flags[(it * MAX_FRAMES + y) * 2] | sc.flags[(it * MAX_FRAMES + y) * 2 + 1]) != 0;
     int gt = list[it];
     int env = gt / k.ntile, tile = gt - env * k.ntile;
     int tz = tile % k.nt, ty = (tile / k.nt) % k.nt, tx = tile / (k.nt * k.nt);
@@ -346,7 +349,7 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
 __global__ void __launch_bounds__(FLAT_THREADS, 4)
     k_grid_adj_flat(SimConst k, const __grid_constant__ GridTools tp, const float* __restrict__ poses, int j,
                     const float4* __restrict__ G0, float4* __restrict__ Ga, const int* __restrict__ list,
-                    const int* __restrict__ count, float* __restrict__ pose_adj) {
+                    const int* __restrict__ count, float* __restrict__ pose_adj, GridAdjScratch sc) {
   DSK_TL(k);
   const ToolParams* sT = tp.T;   // tool parameters and the frame table arrive as kernel parameters: no setup barrier
   const FrameTable& ft = tp.ft;
@@ -395,6 +398,12 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4)
     }
     float3 g = f3(0.f, 0.f, 0.f);
     if (live) g = grid_boundary_adj(k, I0, I1, I2, v, f3(ga4.x, ga4.y, ga4.z));
+    // With a scratch the pose adjoints leave this kernel (and the critical path): the warp parks (gD, gcv, gdist) of its 32
+    // nodes for every frame near the tile and k_grid_adj_tools reduces them on the side branch, as for k_grid_adj.  A tile in
+    // contact is a ~4 000-instruction serial chain in a few divergent lanes otherwise: with the gripper in contact the
+    // slowest SM was busy 3x longer than the average (r03d: 25 us per launch, 9.7 us without contact).
+    const bool park = sc.data != nullptr && it < sc.cap;   // warp-uniform
+    unsigned hitmask = 0;
     // frames in reverse order; every lane of the warp walks the same frames
     for (int a = na - 1; a >= 0; a--) {
       unsigned rest = mask;
@@ -402,7 +411,26 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4)
       int f = __ffs(rest) - 1;
       const ContactGeom& c = geo[a];
       bool hit = c.influence >= 0.f;
-      if (!__any_sync(0xffffffffu, hit)) continue;
+      const bool anyhit = __any_sync(0xffffffffu, hit);
+      if (park) {
+        float3 gD = f3(0, 0, 0), gcv = f3(0, 0, 0);
+        float gdist = 0.f;
+        if (hit) {
+          float ginfl;
+          const ToolParams& T = sT[ft.tool[f]];
+          g = contact_response_adj(vs[a], c.D, c.cv, c.influence, T.friction, ft.flag[f] != 0.f, g, gD, gcv, ginfl);
+          gdist = (c.influence < 1.f) ? (-T.softness * c.influence * ginfl) : 0.f;
+        }
+        if (anyhit) {   // the other half of the tile cannot know: both halves write their nodes whenever THEY had a hit, and
+          hitmask |= 1u << f;   // the reader takes a (tile, frame) if either half flagged it -- see the zero fill below
+        }
+        float* d = sc.data + ((size_t)(it * ft.n + f) * 7) * GRID_NODES + l;
+        d[0 * GRID_NODES] = gD.x;  d[1 * GRID_NODES] = gD.y;  d[2 * GRID_NODES] = gD.z;
+        d[3 * GRID_NODES] = gcv.x; d[4 * GRID_NODES] = gcv.y; d[5 * GRID_NODES] = gcv.z;
+        d[6 * GRID_NODES] = gdist;
+        continue;
+      }
+      if (!anyhit) continue;
       const ToolParams& T = sT[ft.tool[f]];
       FrameAdj a0 = frame_adj_zero(), a1 = frame_adj_zero();
       if (hit) {
@@ -453,6 +481,7 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4)
         }
       }
     }
+    if (park && lane < ft.n) sc.flags[(it * MAX_FRAMES + lane) * 2 + (w & 1)] = (hitmask >> lane) & 1u;   // every flag, every substep
     float4 outv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (live) outv = make_float4(inv * g.x, inv * g.y, inv * g.z, -(inv * inv) * (gin.x * g.x + gin.y * g.y + gin.z * g.z));
     Ga[o] = outv;
