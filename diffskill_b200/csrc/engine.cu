@@ -449,7 +449,9 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
       DA(e->tile_epoch[s], (size_t)e->B * k.ntile);
       DA(e->tile_list[s], (size_t)e->B * k.ntile);
     }
-    if (!getenv("DSK_NO_GRID_ADJ_SPLIT")) {
+    // throughput layout: parking is implemented (k_grid_adj_flat 18.3 -> 11.3 us on GatherMove x64) but the side-branch kernel
+    // then costs 27 us per substep next to the particle kernels and the step gets slower (r03f: 95.8 -> 101.1 ms); opt-in
+    if ((!e->flat_grid || getenv("DSK_FLAT_PARK")) && !getenv("DSK_NO_GRID_ADJ_SPLIT")) {
       e->gadj_cap = (int)std::min<size_t>((size_t)e->B * k.ntile, e->flat_grid ? 32768 : 4096);
       int nf = std::min(e->n_frames, MAX_FRAMES);
       for (int s = 0; s < 2; s++) {
