@@ -520,21 +520,37 @@ def main():
         peak, peak_src = measured_peak()
         total_ms = sum(v[0] for v in prof.values())
         shares = {k: v[0] / total_ms for k, v in prof.items()}
-        dom = max((k for k in prof if k in KERNEL_BYTES), key=lambda k: prof[k][0])
-        bp, bn = KERNEL_BYTES[dom]
-        alg_bytes = bp * n_particles + bn * n_occ
-        dur_ms = prof[dom][0] / prof[dom][1]
-        achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
-        step_bytes = ((192 if fwd_only else 480) * n_particles + (56 if fwd_only else 168) * n_occ) * H * S
-        traffic = None
+        # The eager profile brackets every launch with two events: each launch carries the same few microseconds of launch
+        # latency on top of the kernel (the smallest class average -- one-thread bookkeeping kernels -- measures it).  The
+        # DOMINANT kernel is ranked on the time net of that bracket (round-1 review: the raw eager ranking named a short,
+        # often-launched grid kernel although a particle kernel dominates the replayed graph); `achieved` keeps the raw,
+        # bracket-included duration -- conservative.
+        bracket_ms = min(v[0] / v[1] for v in prof.values() if v[1] > 0)
+        net_ms = {k: max(v[0] - v[1] * bracket_ms, 0.1 * v[0]) for k, v in prof.items()}
+        dom = max((k for k in prof if k in KERNEL_BYTES), key=lambda k: net_ms[k])
         try:
-            tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
-            traffic = tr.get('liftspread' if fwd_only else args.workload, {}).get(dom, {}).get('dram_bytes_per_launch')
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get('liftspread' if fwd_only else args.workload, {})
         except Exception:
-            pass
+            tr = {}
+
+        def kernel_roof(name):
+            bp_, bn_ = KERNEL_BYTES[name]
+            alg = bp_ * n_particles + bn_ * n_occ
+            us = prof[name][0] / prof[name][1] * 1e3
+            return dict(achieved=alg / (us * 1e-6) / 1e9, frac=alg / (us * 1e-6) / 1e9 / peak, algorithmic_bytes_per_launch=alg,
+                        avg_launch_us=us, net_share_of_step=net_ms[name] / sum(net_ms.values()),
+                        traffic=tr.get(name, {}).get('dram_bytes_per_launch'))
+
+        by_kernel = {k: kernel_roof(k) for k in sorted((k for k in prof if k in KERNEL_BYTES), key=lambda k: -net_ms[k])[:4]}
+        alg_bytes = by_kernel[dom]['algorithmic_bytes_per_launch']
+        dur_ms = prof[dom][0] / prof[dom][1]
+        achieved = by_kernel[dom]['achieved']
+        step_bytes = ((192 if fwd_only else 480) * n_particles + (56 if fwd_only else 168) * n_occ) * H * S
+        traffic = by_kernel[dom]['traffic']
         roof = dict(bound='hbm', kernel=dom, achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
                     traffic=traffic, peak_source=peak_src, algorithmic_bytes_per_launch=alg_bytes,
                     avg_launch_us=dur_ms * 1e3, kernel_share_of_step=shares[dom],
+                    event_bracket_us=bracket_ms * 1e3, by_kernel=by_kernel,
                     step_achieved_gbs=step_bytes / (ms_step * 1e-3) / 1e9,
                     step_frac=step_bytes / (ms_step * 1e-3) / 1e9 / peak,
                     method='CUDA events around every launch of one eager (graph-free) iteration on the engine stream',
