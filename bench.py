@@ -527,7 +527,12 @@ def main():
         # bracket-included duration -- conservative.
         bracket_ms = min(v[0] / v[1] for v in prof.values() if v[1] > 0)
         net_ms = {k: max(v[0] - v[1] * bracket_ms, 0.1 * v[0]) for k, v in prof.items()}
-        dom = max((k for k in prof if k in KERNEL_BYTES), key=lambda k: net_ms[k])
+        cand = [k for k in prof if k in KERNEL_BYTES]
+        top = max(net_ms[k] for k in cand)
+        # classes within 15 % of the top are a tie at the resolution of this profile (one eager iteration): the tie goes to the
+        # class that moves more algorithmic bytes -- the one an HBM roofline says something about
+        dom = max((k for k in cand if net_ms[k] >= 0.85 * top),
+                  key=lambda k: KERNEL_BYTES[k][0] * n_particles + KERNEL_BYTES[k][1] * n_occ)
         try:
             tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get('liftspread' if fwd_only else args.workload, {})
         except Exception:

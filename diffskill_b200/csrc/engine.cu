@@ -1009,8 +1009,16 @@ static int seq_substep_grad(dsk_engine* e, StepSlot& s, int q, int j) {
                                GridTape{nullptr, nullptr, nullptr, nullptr, 0}, run_if));
   }
   if (launch_g2p_adj(e, fin, fnext, ain, aout, e->Gv[set], e->Ga[set])) return -1;
-  KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, e->qs, (GridAdjScratch{nullptr, nullptr, 0}), k, e->grid_tools, s.poses, j, e->G0[set], e->Ga[set],
-                                                                      tt.list, tt.count, e->pose_adj));
+  {
+    // same split as in the two-branch graph (the pose adjoints of the contacts are parked and reduced by a second kernel), here
+    // back to back on one stream: the eager per-kernel profile of bench.py then times the kernels the graph replays
+    const bool park = e->gadj_scratch[0] != nullptr;
+    GridAdjScratch sc{park ? e->gadj_scratch[0] : nullptr, park ? e->gadj_flags[0] : nullptr, park ? e->gadj_cap : 0};
+    KL(KID_GRID_ADJ, GRID_ADJ_LAUNCH(e, e->qs, sc, k, e->grid_tools, s.poses, j, e->G0[set], e->Ga[set], tt.list, tt.count, e->pose_adj));
+    if (park)
+      KL(KID_GRID_ADJ_TOOLS, k_grid_adj_tools<<<grid_ctas(e), grid_block(e), 0, e->qs>>>(k, e->grid_tools, s.poses, j, e->G0[set], tt.list,
+                                                                                          tt.count, e->pose_adj, sc));
+  }
   if (launch_p2g_adj(e, fin, ain, aout, (e->mat_uniform ? nullptr : s.mat), e->Ga[set], svd_at(e, s, j))) return -1;
   LAUNCH_CHECK();
   e->bwd_cur ^= 1;
