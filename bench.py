@@ -535,6 +535,8 @@ def main():
                   key=lambda k: KERNEL_BYTES[k][0] * n_particles + KERNEL_BYTES[k][1] * n_occ)
         try:
             tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get('liftspread' if fwd_only else args.workload, {})
+            if args.envs > 0 or world > 1:   # the captures are per workload at its single-GPU size
+                tr = {}
         except Exception:
             tr = {}
 
