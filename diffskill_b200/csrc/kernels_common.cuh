@@ -453,9 +453,9 @@ DSK_DEV void warp_scatter9(const SimConst& k, bool active, const Stencil& s, int
 // run of its own, so that no live run ever covers a row element an inactive lane wrote), the stencil tiles marked once per
 // live run; returns the ballot of run heads (0: no active lane) and the ballot of active lanes
 DSK_DEV unsigned ts_run_heads(const SimConst& k, bool active, const Stencil& s, const TileTrack& tt, bool mark, int env,
-                              int epoch, unsigned& act, TileClaim& claim, int& key) {
+                              int epoch, unsigned& act, TileClaim& claim) {
   const int lane = threadIdx.x & 31;
-  key = active ? node_offset(s.bx, s.by, s.bz, k.nt) : -1 - lane;
+  int key = active ? node_offset(s.bx, s.by, s.bz, k.nt) : -1 - lane;
   act = __ballot_sync(0xffffffffu, active);
   int prev = __shfl_up_sync(0xffffffffu, key, 1);
   bool head = lane == 0 || prev != key;
@@ -463,34 +463,24 @@ DSK_DEV unsigned ts_run_heads(const SimConst& k, bool active, const Stencil& s, 
   if (mark) claim_tiles(k, tt, env, s, epoch, active, claim);   // results used after the tile is written
   return act ? heads : 0u;
 }
-// node (i, j, l) of the stencil whose base cell has the tile-major offset kb (tile << 6 | x << 4 | y << 2 | z)
-DSK_DEV int stencil_node_of(int kb, int i, int j, int l, int nt) {
-  const int x = ((kb >> 4) & 3) + i, y = ((kb >> 2) & 3) + j, z = (kb & 3) + l;
-  const int tile = (kb >> 6) + (x >> 2) * nt * nt + (y >> 2) * nt + (z >> 2);
-  return (tile << 6) | ((x & 3) << 4) | ((y & 3) << 2) | (z & 3);
-}
-// second half: lanes 0..26 walk their node's row ONCE, left to right, and issue one RED.128 wherever a run ends.  The loop is
-// fully unrolled: the 32 LDS.128 have immediate offsets and are issued ahead of the additions, the branches on the (warp-
-// uniform) run-end bits are uniform, and a run costs one shuffle of the base cell's offset instead of three shuffles and an
-// offset computation from scratch (the first version looped over the runs with a dynamic inner loop: ~45 instructions per run
-// plus 6 per element, and 17-19 % of the warp time of the two scatter kernels, `profiles/r03d_ncu_sections_gathermove64.md`).
-// A dead run is one inactive lane, whose row elements are zero.
-DSK_DEV void ts_reduce_runs27(const SimConst& k, int key, float4* __restrict__ Ge, const float4* wbuf, unsigned heads,
+// second half: for every run lanes 0..26 add up their node's row segment and issue one RED.128
+DSK_DEV void ts_reduce_runs27(const SimConst& k, const Stencil& s, float4* __restrict__ Ge, const float4* wbuf, unsigned todo,
                               unsigned act) {
   const int lane = threadIdx.x & 31;
   const int i = lane / 9, j = (lane / 3) % 3, l = lane % 3;   // stencil node owned by lanes 0..26
   const float4* row = wbuf + (lane < 27 ? lane : 0) * TS_ROW;
-  const unsigned tails = (heads >> 1) | 0x80000000u;          // lane t ends a run iff lane t + 1 starts one
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int t = 0; t < 32; t++) {
-    acc = f4add(acc, row[t]);
-    if ((tails >> t) & 1u) {
-      if ((act >> t) & 1u) {   // live runs end at an active lane
-        const int kb = __shfl_sync(0xffffffffu, key, t);
-        if (lane < 27) red_add4(&Ge[stencil_node_of(kb, i, j, l, k.nt)], acc);
-      }
-      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  while (todo) {
+    int h = __ffs(todo) - 1;
+    todo &= todo - 1;
+    int e = todo ? __ffs(todo) - 1 : 32;   // the run is [h, e)
+    if (!((act >> h) & 1u)) continue;      // dead run (inactive lane)
+    int bx = __shfl_sync(0xffffffffu, s.bx, h), by = __shfl_sync(0xffffffffu, s.by, h),
+        bz = __shfl_sync(0xffffffffu, s.bz, h);
+    if (lane < 27) {
+      float4 acc = row[h];
+#pragma unroll 4
+      for (int t = h + 1; t < e; t++) acc = f4add(acc, row[t]);
+      red_add4(&Ge[node_offset(bx + i, by + j, bz + l, k.nt)], acc);
     }
   }
 }
@@ -500,14 +490,13 @@ DSK_DEV void warp_scatter27_ts(const SimConst& k, bool active, const Stencil& s,
   const int lane = threadIdx.x & 31;
   unsigned act;
   TileClaim claim;
-  int key;
-  unsigned todo = ts_run_heads(k, active, s, tt, mark, env, epoch, act, claim, key);
+  unsigned todo = ts_run_heads(k, active, s, tt, mark, env, epoch, act, claim);
   if (!todo) return;
 #pragma unroll
   for (int q = 0; q < 27; q++) wbuf[q * TS_ROW + lane] = val(q / 9, (q / 3) % 3, q % 3);
   __syncwarp();
   if (mark) append_begin(tt, epoch, claim);
-  ts_reduce_runs27(k, key, Ge, wbuf, todo, act);
+  ts_reduce_runs27(k, s, Ge, wbuf, todo, act);
   if (mark) append_finish(k, tt, env, s, claim);
   __syncwarp();   // the tile is rewritten by the warp's next scatter
 }
@@ -523,8 +512,7 @@ DSK_DEV void warp_scatter27_ts_affine(const SimConst& k, bool active, const Sten
   const int lane = threadIdx.x & 31;
   unsigned act;
   TileClaim claim;
-  int key;
-  unsigned todo = ts_run_heads(k, active, s, tt, mark, env, epoch, act, claim, key);
+  unsigned todo = ts_run_heads(k, active, s, tt, mark, env, epoch, act, claim);
   if (!todo) return;
   {
     const float2 axl = f2(AX.x, AX.y), axh = f2(AX.z, 0.f), ayl = f2(AY.x, AY.y), ayh = f2(AY.z, 0.f);
@@ -561,7 +549,7 @@ DSK_DEV void warp_scatter27_ts_affine(const SimConst& k, bool active, const Sten
   }
   __syncwarp();
   if (mark) append_begin(tt, epoch, claim);
-  ts_reduce_runs27(k, key, Ge, wbuf, todo, act);
+  ts_reduce_runs27(k, s, Ge, wbuf, todo, act);
   if (mark) append_finish(k, tt, env, s, claim);
   __syncwarp();
 }
@@ -573,8 +561,7 @@ DSK_DEV void warp_scatter9_ts(const SimConst& k, bool active, const Stencil& s, 
   const int lane = threadIdx.x & 31;
   unsigned act;
   TileClaim claim;
-  int key;
-  unsigned todo = ts_run_heads(k, active, s, tt, mark, env, epoch, act, claim, key);
+  unsigned todo = ts_run_heads(k, active, s, tt, mark, env, epoch, act, claim);
   if (!todo) return;
 #pragma unroll
   for (int q = 0; q < 9; q++) wbuf[q * TS_ROW + lane] = val(q / 3, q % 3);
