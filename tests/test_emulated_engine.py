@@ -31,7 +31,8 @@ SUBSET = ('test_cell_index_and_sort_bit_exact or test_svd_matches_oracle or test
           'or (test_substep_backward_parity and (LiftSpread or CutRearrange or Rope or Chopsticks)) '
           'or (test_against_committed_golden_fixture and (GatherMove or Rollingpin or Gripper2)) '
           'or (test_multi_step_action_gradient and (1-256-LiftSpread or 3-1-CutRearrange or 1-256-Rope)) '
-          'or (test_multi_step_action_gradient_batched_layout and 1-0-GatherMove)')
+          'or (test_multi_step_action_gradient_batched_layout and 1-0-GatherMove) '
+          'or (test_sort_and_frame_permutation_batched_layout and GatherMove)')
 
 
 @pytest.fixture(scope='module')

@@ -68,6 +68,37 @@ def test_cell_index_and_sort_bit_exact(name):
     assert np.array_equal(occ, o.occupancy(0))           # bit-exact grid occupancy
 
 
+@pytest.mark.parametrize('name', ['GatherMove-v1', 'CutRearrange-v1'])
+def test_sort_and_frame_permutation_batched_layout(name, monkeypatch):
+    """The sort path of batched engines -- histogram scanned over flagged chunks only, permutation from k_sort_perm, frames
+    moved through shared memory by k_permute_rows (gather into sorted order, scatter back to the caller's order) -- is a pure
+    permutation: sorted by the same bit-exact keys, and one whole env step reproduces the single-scene path's particles in the
+    CALLER's order to rounding (the two paths use different scatter variants, so not bit for bit)."""
+    scene, small, o = make_pair(name, n=3000)
+    monkeypatch.setenv('DSK_FORCE_BIG', '1')
+    monkeypatch.setenv('DSK_FLAT_GRID', '1')
+    _, big, _ = make_pair(name, n=3000)
+    base, key = big.debug_cell_index(0)
+    assert np.array_equal(base, o.cell_index(0)[0])
+    act = actions_for(scene, 1, scale=0.7)[0][None]
+    for e in (small, big):
+        e.set_action(0, act)
+        e.forward_step(0)
+    perm = big.debug_sort_order()
+    assert np.array_equal(np.sort(perm), np.arange(len(perm)))   # a permutation
+    assert (np.diff(key[perm]) >= 0).all()                       # sorted by key
+    for a, b, q in zip(small.get_particles(1), big.get_particles(1), 'xvFC'):
+        err = relerr(b, a)
+        record_parity('sort_and_frame_permutation_batched_layout', name, q, err, tol=1e-4,
+                      config='n=3000, one env step, vs the single-scene path')
+        assert err < 1e-4, (q, err)
+    # a second step sorts again from the un-permuted checkpoint: the histogram and its chunk flags must have been cleaned up
+    for e in (small, big):
+        e.set_action(1, act)
+        e.forward_step(1)
+    assert relerr(big.get_particles(2)[0], small.get_particles(2)[0]) < 1e-4
+
+
 def _fwd_errs(scene, eng, o, s):
     x, v, F, C = eng.get_particles(s + 1)
     ox, ov, oF, oC = o.get_frame(s + 1)
