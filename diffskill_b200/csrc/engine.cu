@@ -153,6 +153,7 @@ struct dsk_engine {
   bool mat_uniform = true;  // no per-particle material set: the particle kernels take (mu, lam, yield_stress) from SimConst
   bool flat_grid = false;   // many active tiles: throughput layout of the grid kernels
   bool ts = true;           // batched engines: transposed shared-memory scatter (warp_scatter27_ts_affine) instead of the shuffle butterfly
+  int flat_fwd_ctas_per_sm = 4, flat_adj_ctas_per_sm = 4;   // grid of the throughput-layout grid kernels (4 CTAs are resident per SM)
   bool perm_smem = true;    // batched engines: frame permutations through shared memory (k_permute_rows)
   bool perm_smem_small = false;   // ... also for single scenes (DSK_PERM_SMEM_SMALL)
   bool perm_opt_in[3] = {false, false, false};
@@ -408,6 +409,8 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
   if (const char* v = getenv("DSK_GRID_CTAS_PER_SM")) e->grid_ctas_per_sm = std::max(1, atoi(v));
   if (const char* v = getenv("DSK_TS")) e->ts = atoi(v) != 0;
   if (const char* v = getenv("DSK_PERM_SMEM")) e->perm_smem = atoi(v) != 0;
+  if (const char* v = getenv("DSK_FLAT_FWD_CTAS")) e->flat_fwd_ctas_per_sm = std::max(1, atoi(v));
+  if (const char* v = getenv("DSK_FLAT_ADJ_CTAS")) e->flat_adj_ctas_per_sm = std::max(1, atoi(v));
   if (const char* v = getenv("DSK_PERM_SMEM_SMALL")) e->perm_smem_small = atoi(v) != 0;
   if (const char* v = getenv("DSK_TS_PL")) e->ts_pl = atoi(v) != 0;
   if (const char* v = getenv("DSK_FLAT_GRID")) e->flat_grid = atoi(v) != 0;
@@ -645,12 +648,12 @@ static dim3 grid_block(dsk_engine* e) { return dim3(GRID_NODES, std::min(e->n_fr
 // latency layout (node x frame)
 #define GRID_FWD_LAUNCH(e, stream, ...)                                            \
   do {                                                                             \
-    if ((e)->flat_grid) k_grid_flat<<<148 * 4, FLAT_THREADS, 0, stream>>>(__VA_ARGS__); \
+    if ((e)->flat_grid) k_grid_flat<<<148 * (e)->flat_fwd_ctas_per_sm, FLAT_THREADS, 0, stream>>>(__VA_ARGS__); \
     else k_grid<<<grid_ctas(e), grid_block(e), 0, stream>>>(__VA_ARGS__);          \
   } while (0)
 #define GRID_ADJ_LAUNCH(e, stream, sc, ...)                                            \
   do {                                                                                 \
-    if ((e)->flat_grid) k_grid_adj_flat<<<148 * 4, FLAT_THREADS, 0, stream>>>(__VA_ARGS__, sc); \
+    if ((e)->flat_grid) k_grid_adj_flat<<<148 * (e)->flat_adj_ctas_per_sm, FLAT_THREADS, 0, stream>>>(__VA_ARGS__, sc); \
     else k_grid_adj<<<grid_ctas(e), grid_block(e), 0, stream>>>(__VA_ARGS__, sc);      \
   } while (0)
 

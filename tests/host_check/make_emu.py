@@ -74,8 +74,8 @@ def build(verbose=False, flags=(), so=None):
     src = src.replace('#include "../../include/diffskill_mpm.h"', f'#include "{os.path.join(ROOT, "include", "diffskill_mpm.h")}"')
     # persistent grids are sized for 148 SMs; the emulation walks the blocks of a launch one after the other, so it uses a
     # handful (every kernel is a grid-stride loop: the grid size is a launch parameter, not part of the algorithm)
-    for old, new in (('return e->big ? 148 * 8 : 148 * e->grid_ctas_per_sm;', 'return 3;'), ('k_grid_flat<<<148 * 4,', 'k_grid_flat<<<3,'),
-                     ('k_grid_adj_flat<<<148 * 4,', 'k_grid_adj_flat<<<3,')):
+    for old, new in (('return e->big ? 148 * 8 : 148 * e->grid_ctas_per_sm;', 'return 3;'), ('k_grid_flat<<<148 * (e)->flat_fwd_ctas_per_sm,', 'k_grid_flat<<<3,'),
+                     ('k_grid_adj_flat<<<148 * (e)->flat_adj_ctas_per_sm,', 'k_grid_adj_flat<<<3,')):
         assert src.count(old) == 1, old
         src = src.replace(old, new)
     gen = os.path.join(GEN, 'engine_emu.cpp')
