@@ -371,7 +371,6 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4)
     if (it + stride < n_active) {
       gin_n = G0[((size_t)gt_n << 6) + l];
       ga_n = Ga[((size_t)gt_n << 6) + l];
-      prefetch_tile_poses(k, poses, gt_n, j, lane);
     }
     if (it + 2 * stride < n_active) gt_nn = list[it + 2 * stride];
     int env = gt / k.ntile, tile = gt - env * k.ntile;

@@ -197,16 +197,6 @@ __global__ void __launch_bounds__(GRID_NODES * MAX_FRAMES)
 struct WarpFrames {   // per warp, shared memory
   Frame F0[MAX_FRAMES], F1[MAX_FRAMES];
 };
-// The poses of the NEXT tile's env (frames j and j+1 of all tools: 64 K bytes, contiguous) are pulled into L1 while the current
-// tile is processed: prepare_frame's pose loads are the one dependent global round trip left in an iteration of the tile loop
-// (list and tile data are already one / two iterations ahead).  A prefetch needs no register.
-DSK_DEV void prefetch_tile_poses(const SimConst& k, const float* __restrict__ poses, int gt, int j, int lane) {
-#if defined(__CUDA_ARCH__)
-  const int env = gt / k.ntile;
-  const char* a = (const char*)(poses + (size_t)(env * (k.S + 1) + j) * k.K * 8);
-  if (lane * 128 < 2 * k.K * 8 * 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(a + lane * 128));
-#endif
-}
 // Tile of the list a warp pair starts with; it advances by gridDim.x * FLAT_TILES.  Neighbours in the list go to DIFFERENT
 // CTAs: the tiles a tool touches are neighbours in the list (it is built in particle order) and cost ~10x the others, and
 // with four neighbours per CTA the SMs that got them ran 3x longer than the average (r03d: sm__cycles_active max 43.7 k,
@@ -272,10 +262,7 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4)
     const int gt = gt_n;
     const float4 g = g_n;
     gt_n = gt_nn;
-    if (it + stride < n_active) {
-      g_n = Gin[((size_t)gt_n << 6) + l];
-      prefetch_tile_poses(k, poses, gt_n, j, lane);
-    }
+    if (it + stride < n_active) g_n = Gin[((size_t)gt_n << 6) + l];
     if (it + 2 * stride < n_active) gt_nn = list[it + 2 * stride];
     int env = gt / k.ntile, tile = gt - env * k.ntile;
     int tz = tile % k.nt, ty = (tile / k.nt) % k.nt, tx = tile / (k.nt * k.nt);
