@@ -153,8 +153,6 @@ struct dsk_engine {
   bool mat_uniform = true;  // no per-particle material set: the particle kernels take (mu, lam, yield_stress) from SimConst
   bool flat_grid = false;   // many active tiles: throughput layout of the grid kernels
   bool ts = true;           // batched engines: transposed shared-memory scatter (warp_scatter27_ts_affine) instead of the shuffle butterfly
-  int kin_parts = 8;        // CTAs per env of k_kinematics on the critical path (tool-tool pairs only)
-  int *kin_first = nullptr, *kin_done = nullptr;   // [B] first-hit minimum / ticket of the split kinematics kernel
   int flat_fwd_ctas_per_sm = 4, flat_adj_ctas_per_sm = 4;   // grid of the throughput-layout grid kernels (4 CTAs are resident per SM)
   bool perm_smem = true;    // batched engines: frame permutations through shared memory (k_permute_rows)
   bool perm_smem_small = false;   // ... also for single scenes (DSK_PERM_SMEM_SMALL)
@@ -235,8 +233,6 @@ static int dalloc(dsk_engine* e, T** p, size_t count, bool zero = true) {
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static float* svd_at(dsk_engine* e, StepSlot& s, int j);
 static size_t kin_smem(dsk_engine* e);
-static int kin_parts(dsk_engine* e);
-static dim3 kin_grid(dsk_engine* e);
 static int kin_block(dsk_engine* e, bool hidden);
 static void drop_graphs(dsk_engine* e);
 static int ts_opt_in(dsk_engine* e);
@@ -413,7 +409,6 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
   if (const char* v = getenv("DSK_GRID_CTAS_PER_SM")) e->grid_ctas_per_sm = std::max(1, atoi(v));
   if (const char* v = getenv("DSK_TS")) e->ts = atoi(v) != 0;
   if (const char* v = getenv("DSK_PERM_SMEM")) e->perm_smem = atoi(v) != 0;
-  if (const char* v = getenv("DSK_KIN_PARTS")) e->kin_parts = std::max(1, std::min(32, atoi(v)));
   if (const char* v = getenv("DSK_FLAT_FWD_CTAS")) e->flat_fwd_ctas_per_sm = std::max(1, atoi(v));
   if (const char* v = getenv("DSK_FLAT_ADJ_CTAS")) e->flat_adj_ctas_per_sm = std::max(1, atoi(v));
   if (const char* v = getenv("DSK_PERM_SMEM_SMALL")) e->perm_smem_small = atoi(v) != 0;
@@ -504,9 +499,6 @@ int dsk_create(const dsk_config* c, dsk_engine** out) {
     DA(e->actions, (size_t)e->H * e->B * std::max(1, e->A));
     DA(e->action_grad, (size_t)e->H * e->B * std::max(1, e->A));
     DA(e->rand_num, (size_t)std::max(1, k.npairs) * DSK_NUM_COLLISION_POINTS * 3);
-    DA(e->kin_first, e->B);
-    DA(e->kin_done, e->B);
-    CK(cudaMemset(e->kin_first, 0x7f, (size_t)e->B * sizeof(int)));   // KIN_NO_HIT
     e->stage_floats = std::max<size_t>((size_t)k.stride * 24, (size_t)e->B * k.nnode * 4);
     DA(e->stage, e->stage_floats);
     CK(cudaMemcpy(e->d_tools, e->h_tools.data(), sizeof(ToolParams) * std::max(1, e->K), cudaMemcpyHostToDevice));
@@ -647,11 +639,7 @@ static float* svd_at(dsk_engine* e, StepSlot& s, int j) {
 // With pairs the warps share the collision queries: 32 warps when the kernel is on the critical path; 8 on the lookahead
 // branch, where it has a whole env step to finish -- a 1024-thread CTA needs a whole SM's register file, so next to the
 // particle kernels its CTAs waited ~150 us for SMs to drain and then held them (r02z timeline, GatherMove x64).
-static int kin_block(dsk_engine* e, bool hidden) { return e->k.npairs == 0 ? 64 : (hidden || kin_parts(e) > 1 ? 256 : KIN_CTA); }
-// CTAs per env on the critical path: the S x pairs collision queries (600 surface points each) of one env on ONE SM cost
-// ~150 us per env step for 64 envs with two pairs (r02z timeline); eight CTAs of eight warps share them
-static int kin_parts(dsk_engine* e) { return e->k.npairs == 0 ? 1 : e->kin_parts; }
-static dim3 kin_grid(dsk_engine* e) { return dim3(e->B, kin_parts(e)); }
+static int kin_block(dsk_engine* e, bool hidden) { return e->k.npairs == 0 ? 64 : (hidden ? 256 : KIN_CTA); }
 static size_t kin_smem(dsk_engine* e) {   // pose chain + the collision samples of every pair
   return (size_t)(e->S + 1) * e->K * 32 + (size_t)e->k.npairs * DSK_NUM_COLLISION_POINTS * 12;
 }
@@ -848,7 +836,7 @@ static int seq_begin_forward(dsk_engine* e, StepSlot& s) {
       CK(cudaEventRecord(e->ev_fork, e->qs));
       CK(cudaStreamWaitEvent(e->cap_side, e->ev_fork, 0));
       if (!e->seq_skip_kin) {
-        KL(KID_KINEMATICS, k_kinematics<<<kin_grid(e), kin_block(e, false), kin_smem(e), e->cap_side>>>(k, e->d_tools, e->d_args, e->rand_num, s.poses, s.cidx, e->kin_first, e->kin_done));
+        KL(KID_KINEMATICS, k_kinematics<<<e->B, kin_block(e, false), kin_smem(e), e->cap_side>>>(k, e->d_tools, e->d_args, e->rand_num, s.poses, s.cidx));
         CK(cudaEventRecord(e->ev_join, e->cap_side));
         e->kin_join = true;
       }
@@ -856,12 +844,12 @@ static int seq_begin_forward(dsk_engine* e, StepSlot& s) {
         StepSlot& nx = *e->seq_next_slot;
         const StepArgs* na = e->d_args_kin + e->seq_next_step;
         if (!e->seq_skip_kin) KL(KID_IO, k_tool_store<<<cdiv(e->B * e->K * 8, 128), 128, 0, e->cap_side>>>(k, s.poses, e->d_args));
-        KL(KID_KINEMATICS, k_kinematics<<<e->B, kin_block(e, true), kin_smem(e), e->cap_side>>>(k, e->d_tools, na, e->rand_num, nx.poses, nx.cidx, e->kin_first, e->kin_done));
+        KL(KID_KINEMATICS, k_kinematics<<<e->B, kin_block(e, true), kin_smem(e), e->cap_side>>>(k, e->d_tools, na, e->rand_num, nx.poses, nx.cidx));
         KL(KID_IO, k_tool_store<<<cdiv(e->B * e->K * 8, 128), 128, 0, e->cap_side>>>(k, nx.poses, na));
         CK(cudaEventRecord(e->ev_join2, e->cap_side));
       }
     } else {
-      KL(KID_KINEMATICS, k_kinematics<<<kin_grid(e), kin_block(e, false), kin_smem(e), e->qs>>>(k, e->d_tools, e->d_args, e->rand_num, s.poses, s.cidx, e->kin_first, e->kin_done));
+      KL(KID_KINEMATICS, k_kinematics<<<e->B, kin_block(e, false), kin_smem(e), e->qs>>>(k, e->d_tools, e->d_args, e->rand_num, s.poses, s.cidx));
     }
   }
   if (e->cfg.sort_particles && !e->seq_full_sort) {

@@ -397,7 +397,6 @@ __global__ void k_loss_l2(SimConst k, const float* __restrict__ frame, float* __
   if ((threadIdx.x & 31) == 0 && l != 0.f && gid < k.stride) atomicAdd(&loss[env], l);
 }
 
-#define KIN_NO_HIT 0x7f7f7f7f   // rest value of kin_first (a byte pattern: cudaMemset)
 #define KIN_CTA 1024   // largest CTA (one per env): its warps share the S*npairs collision queries of the optimistic pass; see kin_block()
 // One CTA per env: S substeps of forward_kinematics for every tool, then (if any pair) set_surface_points,
 // set_collision_idx (deterministic first minimum) and apply_collision_projection (mpm_simulator.py:286-305).
@@ -407,8 +406,7 @@ __global__ void k_loss_l2(SimConst k, const float* __restrict__ frame, float* __
 __global__ void __launch_bounds__(KIN_CTA)
     k_kinematics(SimConst k, const ToolParams* __restrict__ tools, const StepArgs* __restrict__ args,
                  const float* __restrict__ rand_num, float* __restrict__ poses /*[B][S+1][K][8]*/,
-                 int* __restrict__ cidx /*[B][S+1][npairs]*/, int* __restrict__ kin_first /*[B]*/,
-                 int* __restrict__ kin_done /*[B]*/) {
+                 int* __restrict__ cidx /*[B][S+1][npairs]*/) {
   DSK_TL(k);
   const float* __restrict__ state0 = args->tool_src;  // [B][K][8]
   const float* __restrict__ action = args->action;    // [B][A] or null
@@ -443,14 +441,9 @@ __global__ void __launch_bounds__(KIN_CTA)
     }
   }
   __syncthreads();
-  // gridDim.y CTAs per env share the queries of (2) when the kernel is on the critical path (the per-step entry points): every
-  // CTA builds the cheap chain (1) for itself, the LAST one to finish -- a ticket per env -- takes the global first hit and goes
-  // on alone.  On the lookahead branch of the multi-step calls gridDim.y = 1.
-  const int part = blockIdx.y, nparts = gridDim.y;
   if (k.npairs > 0) {   // (2) all collision queries at once, one warp per (substep, pair)
     int warp = tid >> 5, lane = tid & 31;
-    const int nw = (int)(blockDim.x >> 5);
-    for (int it = warp + part * nw; it < k.S * k.npairs; it += nw * nparts) {
+    for (int it = warp; it < k.S * k.npairs; it += (int)(blockDim.x >> 5)) {
       int j = it / k.npairs, c = it - j * k.npairs;
       int ti = k.pairs[c][0], tj = k.pairs[c][1];
       Pose Pi = load_pose(sAll + (size_t)(j + 1) * per + ti * 8), Pj = load_pose(sAll + (size_t)(j + 1) * per + tj * 8);
@@ -485,20 +478,6 @@ __global__ void __launch_bounds__(KIN_CTA)
       }
     }
     __syncthreads();
-    if (nparts > 1) {
-      __shared__ int s_last;
-      if (tid == 0) {
-        atomicMin(&kin_first[env], s_first);
-        __threadfence();                                   // cidx and the minimum before the ticket
-        s_last = atomicAdd(&kin_done[env], 1) == nparts - 1;
-        if (s_last) {
-          s_first = atomicExch(&kin_first[env], KIN_NO_HIT);   // final minimum; both counters back to their rest values
-          kin_done[env] = 0;
-        }
-      }
-      __syncthreads();
-      if (!s_last) return;
-    }
   }
   const int j0 = s_first;   // first substep whose frame needs a projection (S: none)
   float* out = poses + (size_t)env * (k.S + 1) * k.K * 8;
