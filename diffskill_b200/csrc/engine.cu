@@ -640,412 +640,6 @@ static float* svd_at(dsk_engine* e, StepSlot& s, int j) {
 // branch, where it has a whole env step to finish and a 1024-thread CTA would hold a whole SM's register file next to the
 // particle kernels for as long as it runs (~150 us per env step when a tool touches an obstacle from the first substep on
 // and every substep takes the sequential path: GatherMove x64, r02z timeline).
-static int kin_block(dsk_engine* e, bool hidden);
-static void drop_graphs(dsk_engine* e);
-static int ts_opt_in(dsk_engine* e);
-
-static void fill_tool(ToolParams& T, const dsk_tool_desc& d) {
-  memset(&T, 0, sizeof T);
-  T.type = d.type;
-  T.action_dim = d.action_dim;
-  for (int j = 0; j < 8; j++) T.action_scale[j] = (float)d.action_scale[j];
-  T.friction = (float)d.friction;
-  T.softness = (float)d.softness;
-  for (int j = 0; j < 3; j++) {
-    T.lo[j] = (float)d.lower_bound[j];
-    T.hi[j] = (float)d.upper_bound[j];
-    T.size[j] = (float)d.size[j];
-  }
-  T.h = (float)d.h;
-  T.half_h = (float)(d.h / 2);
-  T.r = (float)d.r;
-  T.prism_h0 = (float)d.prism_h[0];
-  T.prism_h1 = (float)d.prism_h[1];
-  float w = (float)d.prot[0], x = (float)d.prot[1], y = (float)d.prot[2], z = (float)d.prot[3];
-  T.prot = Q4{w, x, y, z};
-  // normalised conjugate in fp32 with the reference's operation order (primitives.py:713-714)
-  volatile float n2 = w * w;
-  n2 = n2 + x * x;
-  n2 = n2 + y * y;
-  n2 = n2 + z * z;
-  volatile float inv = 1.0f / sqrtf(n2);
-  T.prot_inv = Q4{inv * w, inv * -x, inv * -y, inv * -z};
-  T.min_gap = (float)d.minimal_gap;
-  T.max_gap = (float)d.maximal_gap;
-  // radius of a sphere around the contact-frame origin (tool position, or a jaw's position) that contains the shape
-  if (d.type == DSK_TOOL_CAPSULE || d.type == DSK_TOOL_ROLLINGPIN_EXT || d.type == DSK_TOOL_ROLLINGPIN ||
-      d.type == DSK_TOOL_GRIPPER2)
-    T.bound_r = (float)(d.h / 2 + d.r);
-  else if (d.type == DSK_TOOL_SPHERE)
-    T.bound_r = (float)d.r;
-  else if (d.type == DSK_TOOL_CYLINDER)   // radial extent h, axial half extent r
-    T.bound_r = (float)std::sqrt(d.h * d.h + d.r * d.r);
-  else if (d.type == DSK_TOOL_TORUS)      // major + minor radius
-    T.bound_r = (float)(d.h + d.r);
-  else if (d.type == DSK_TOOL_CHOPSTICKS) {   // two capsules spanning local y in [-h, 0] at x = -+gap/2; no upper clamp on the gap
-    T.max_gap = 1e30f;
-    double g = std::max(d.maximal_gap > 0 && d.maximal_gap < 1e3 ? d.maximal_gap : 0.0, 1.0);   // a gap never exceeds the unit box
-    T.bound_r = (float)std::sqrt((g / 2 + d.r) * (g / 2 + d.r) + (d.h + d.r) * (d.h + d.r));
-  }
-  else
-    T.bound_r = (float)std::sqrt(d.size[0] * d.size[0] + d.size[1] * d.size[1] + d.size[2] * d.size[2]);
-  T.bound_r *= 1.001f;
-}
-static bool host_is_gripper(int type) { return type == DSK_TOOL_GRIPPER || type == DSK_TOOL_GRIPPER2; }
-// host mirror of build_frame_table: one contact frame per tool, two (the jaws) per gripper
-static void sync_grid_tools(dsk_engine* e) {
-  GridTools& g = e->grid_tools;
-  memset(&g, 0, sizeof g);
-  int n = 0;
-  for (int t = 0; t < e->K; t++) {
-    g.T[t] = e->h_tools[t];
-    if (host_is_gripper(e->h_tools[t].type)) {
-      if (n + 2 > MAX_FRAMES) break;
-      g.ft.tool[n] = t; g.ft.flag[n++] = -1.f;
-      g.ft.tool[n] = t; g.ft.flag[n++] = 1.f;
-    } else {
-      if (n + 1 > MAX_FRAMES) break;
-      g.ft.tool[n] = t; g.ft.flag[n++] = 0.f;
-    }
-  }
-  g.ft.n = n;
-}
-
-extern "C" {
-
-const char* dsk_last_error(void) { return g_err.c_str(); }
-int dsk_abi_version(void) { return DSK_ABI_VERSION; }
-int dsk_sizeof_config(void) { return (int)sizeof(dsk_config); }
-int dsk_sizeof_tool_desc(void) { return (int)sizeof(dsk_tool_desc); }
-
-int dsk_create(const dsk_config* c, dsk_engine** out) {
-  if (!c || !out) return fail("null argument");
-  if (c->abi_version != DSK_ABI_VERSION) return fail("ABI version mismatch: header %d, library %d", c->abi_version, DSK_ABI_VERSION);
-  if (c->n_grid % 4 != 0 || c->n_grid < 8) return fail("n_grid must be a multiple of 4 (got %d)", c->n_grid);
-  if (c->n_envs < 1 || c->particle_capacity < 1 || c->substeps < 1 || c->max_steps < 1) return fail("bad sizes");
-  if (c->n_tools < 0 || c->n_tools > DSK_MAX_TOOLS || c->n_pairs < 0 || c->n_pairs > DSK_MAX_PAIRS) return fail("too many tools/pairs");
-  int ndev = 0;
-  CK(cudaGetDeviceCount(&ndev));
-  if (c->device < 0 || c->device >= ndev) return fail("CUDA device %d not available (%d devices)", c->device, ndev);
-  CK(cudaSetDevice(c->device));
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, c->device));
-  if (prop.major < 10) return fail("this library contains sm_100a code only; device is sm_%d%d", prop.major, prop.minor);
-  dsk_engine* e = new dsk_engine();
-  e->cfg = *c;
-  e->B = c->n_envs;
-  e->Npad = (c->particle_capacity + 127) / 128 * 128;
-  e->S = c->substeps;
-  e->H = c->max_steps;
-  e->K = c->n_tools;
-  e->slots = std::max(1, std::min(c->step_slots, c->max_steps));
-  if (c->grid_tape_mib > 0) {
-    size_t per_slot = ((size_t)c->grid_tape_mib << 20) / e->slots;
-    e->tape_cap = (int)std::min<size_t>(per_slot / 2052, (size_t)1 << 30);
-    if (e->tape_cap < c->substeps * 8) e->tape_cap = 0;
-  }
-  e->tape_overflow.assign(e->slots, 1);
-  SimConst& k = e->k;
-  memset(&k, 0, sizeof k);
-  k.n = c->n_grid;
-  k.nt = k.n / 4;
-  k.ntile = k.nt * k.nt * k.nt;
-  k.nnode = k.n * k.n * k.n;
-  k.B = e->B;
-  k.Npad = e->Npad;
-  k.stride = e->B * e->Npad;
-  k.S = e->S;
-  k.K = e->K;
-  k.npairs = c->n_pairs;
-  k.gf_mode = c->ground_friction == 0.0 ? 0 : (c->ground_friction < 10.0 ? 1 : 2);
-  k.dt = (float)c->dt;
-  k.dx = (float)c->dx;
-  k.inv_dx = (float)c->inv_dx;
-  k.p_mass = (float)c->p_mass;
-  k.c_stress = (float)(-c->dt * c->p_vol * 4 * c->inv_dx * c->inv_dx);  // mpm_simulator.py:214
-  k.c_C = (float)(4 * c->inv_dx);                                       // :279
-  k.x_hi = (float)(1. - 3 * c->dx);                                     // :283
-  k.x_lo = (float)(c->lower_bound * c->dx);
-  k.m_eps = 1e-12f;
-  k.ground_friction = (float)c->ground_friction;
-  k.mu = (float)c->mu;
-  k.lam = (float)c->lam;
-  k.ys = (float)c->yield_stress;
-  for (int d = 0; d < 3; d++) {
-    volatile float t = k.dt * (float)c->gravity[d];
-    k.grav[d] = t * 30.f;
-  }
-  for (int i = 0; i < c->n_pairs; i++) {
-    k.pairs[i][0] = c->pairs[i][0];
-    k.pairs[i][1] = c->pairs[i][1];
-    if (c->pairs[i][0] < 0 || c->pairs[i][0] >= e->K || c->pairs[i][1] < 0 || c->pairs[i][1] >= e->K) {
-      delete e;
-      return fail("bad collision pair");
-    }
-  }
-  e->A = 0;
-  e->ncols = 0;
-  e->h_tools.resize(std::max(1, e->K));
-  for (int i = 0; i < e->K; i++) {
-    fill_tool(e->h_tools[i], c->tools[i]);
-    e->A += c->tools[i].action_dim;
-    e->ncols += host_is_gripper(c->tools[i].type) ? 2 : 1;
-    e->n_frames = std::max(1, e->ncols);
-    if (c->tools[i].type < 0 || c->tools[i].type > DSK_TOOL_CHOPSTICKS) {
-      delete e;
-      return fail("unknown tool type %d", c->tools[i].type);
-    }
-  }
-  e->frame_floats = (size_t)FRAME_COMPS * k.stride;
-#ifdef DSK_TIMELINE
-  e->k.tl = nullptr;
-  e->k.tl_slot = -1;
-#endif
-  // measured crossover (GatherMove 8 vs 16 envs, LiftSpread 2 envs): ~24-32 k particles, i.e. ~1.5 warps per scheduler
-  e->big = (size_t)c->n_envs * c->particle_capacity >= 24576;
-  if (const char* v = getenv("DSK_FORCE_BIG")) e->big = atoi(v) != 0;
-  if (const char* v = getenv("DSK_BIG_MINB")) e->minb_g2p2g = e->minb_g2p_adj = e->minb_p2g_adj = atoi(v);
-  if (const char* v = getenv("DSK_BIG_BLOCK")) {   // threads per CTA of the batched particle kernels: 64, 96 or 128
-    int b = atoi(v);
-    e->big_block = (b == 64 || b == 96) ? b : 128;
-  }
-  if (const char* v = getenv("DSK_MINB_G2P2G")) e->minb_g2p2g = atoi(v);
-  if (const char* v = getenv("DSK_MINB_G2P_ADJ")) e->minb_g2p_adj = atoi(v);
-  if (const char* v = getenv("DSK_MINB_P2G_ADJ")) e->minb_p2g_adj = atoi(v);
-  e->flat_grid = e->big;
-  if (const char* v = getenv("DSK_GRID_CTAS_PER_SM")) e->grid_ctas_per_sm = std::max(1, atoi(v));
-  if (const char* v = getenv("DSK_TS")) e->ts = atoi(v) != 0;
-  if (const char* v = getenv("DSK_PERM_SMEM")) e->perm_smem = atoi(v) != 0;
-  if (const char* v = getenv("DSK_FLAT_FWD_CTAS")) e->flat_fwd_ctas_per_sm = std::max(1, atoi(v));
-  if (const char* v = getenv("DSK_FLAT_ADJ_CTAS")) e->flat_adj_ctas_per_sm = std::max(1, atoi(v));
-  if (const char* v = getenv("DSK_PERM_SMEM_SMALL")) e->perm_smem_small = atoi(v) != 0;
-  if (const char* v = getenv("DSK_TS_PL")) e->ts_pl = atoi(v) != 0;
-  if (const char* v = getenv("DSK_FLAT_GRID")) e->flat_grid = atoi(v) != 0;
-  e->tool_floats = (size_t)e->B * std::max(1, e->K) * 8;
-  int rc = [&]() -> int {
-    DA(e->ckpt, (size_t)(e->H + 1) * e->frame_floats);
-    DA(e->adj_ckpt, (size_t)(e->H + 1) * e->frame_floats);
-    DA(e->adjw[0], e->frame_floats);
-    DA(e->adjw[1], e->frame_floats);
-    DA(e->mat, (size_t)3 * k.stride);
-    DA(e->npart, e->B);
-    e->h_npart.assign(e->B, 0);
-    e->slot.resize(e->slots);
-    if (e->tape_cap > 0) DA(e->tape_flags, e->slots);
-    for (auto& s : e->slot) {
-      if (e->tape_cap > 0) s.tape.overflow = e->tape_flags + (&s - e->slot.data());
-      DA(s.frames, (size_t)(e->S + 1) * e->frame_floats);
-      DA(s.mat, (size_t)3 * k.stride);
-      DA(s.perm, k.stride);
-      DA(s.poses, (size_t)(e->S + 1) * e->tool_floats);
-      DA(s.cidx, (size_t)e->B * (e->S + 1) * std::max(1, k.npairs));
-      if (!getenv("DSK_NO_SVD_TAPE")) DA(s.svd, (size_t)e->S * SVD_COMPS * k.stride);
-      if (e->tape_cap > 0) {
-        s.tape.cap = e->tape_cap;
-        DA(s.tape.base, e->S + 1);
-        DA(s.tape.list, e->tape_cap);
-        DA(s.tape.data, (size_t)e->tape_cap * 128);
-      }
-    }
-    DA(e->cell_count, (size_t)e->B * k.nnode);
-    DA(e->key, k.stride);
-    DA(e->scan_partial, (size_t)e->B * cdiv(k.nnode, SCAN_CHUNK));
-    DA(e->chunk_flag, (size_t)e->B * cdiv(k.nnode, SCAN_CHUNK));
-    DA(e->rank, k.stride);
-    for (int s = 0; s < 2; s++) {
-      DA(e->G0[s], (size_t)e->B * k.nnode);
-      DA(e->Gv[s], (size_t)e->B * k.nnode);
-      DA(e->Ga[s], (size_t)e->B * k.nnode);
-      DA(e->tile_epoch[s], (size_t)e->B * k.ntile);
-      DA(e->tile_list[s], (size_t)e->B * k.ntile);
-    }
-    // throughput layout: parking is implemented (k_grid_adj_flat 18.3 -> 11.3 us on GatherMove x64) but the side-branch kernel
-    // then costs 27 us per substep next to the particle kernels and the step gets slower (r03f: 95.8 -> 101.1 ms); opt-in
-    if ((!e->flat_grid || getenv("DSK_FLAT_PARK")) && !getenv("DSK_NO_GRID_ADJ_SPLIT")) {
-      e->gadj_cap = (int)std::min<size_t>((size_t)e->B * k.ntile, e->flat_grid ? 32768 : 4096);
-      int nf = std::min(e->n_frames, MAX_FRAMES);
-      for (int s = 0; s < 2; s++) {
-        DA(e->gadj_scratch[s], (size_t)e->gadj_cap * nf * 7 * GRID_NODES);
-        DA(e->gadj_flags[s], (size_t)e->gadj_cap * MAX_FRAMES * 2);
-      }
-    }
-    if (kin_smem(e) > 48 * 1024) {
-      if (kin_smem(e) > 200 * 1024) return fail("tool kinematics kernel needs %zu bytes of shared memory", kin_smem(e));
-      CK(cudaFuncSetAttribute(k_kinematics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kin_smem(e)));
-    }
-    if (ts_opt_in(e)) return -1;
-    DA(e->tile_count, 4);
-    DA(e->done, 1);
-    DA(e->d_args, 1);
-    DA(e->loss, e->B);
-    e->graphs.resize(e->slots);
-    CK(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&e->cap_side, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
-    e->ev_restored.resize(e->S);
-    e->ev_main.resize(e->S);
-    for (int i = 0; i < e->S; i++) {
-      CK(cudaEventCreateWithFlags(&e->ev_restored[i], cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&e->ev_main[i], cudaEventDisableTiming));
-    }
-    DA(e->perm_cache, k.stride);
-    if (getenv("DSK_RESORT_INTERVAL")) e->resort_interval = std::max(1, atoi(getenv("DSK_RESORT_INTERVAL")));
-    e->use_graphs = getenv("DSK_NO_GRAPHS") == nullptr;
-    DA(e->d_tools, std::max(1, e->K));
-    DA(e->tool_ckpt, (size_t)(e->H + 1) * e->tool_floats);
-    DA(e->tool_adj_ckpt, (size_t)(e->H + 1) * e->tool_floats);
-    DA(e->pose_adj_buf[0], (size_t)(e->S + 1) * e->tool_floats);
-    DA(e->pose_adj_buf[1], (size_t)(e->S + 1) * e->tool_floats);
-    e->pose_adj = e->pose_adj_buf[0];
-    CK(cudaStreamCreateWithFlags(&e->tool_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) {
-      CK(cudaEventCreateWithFlags(&e->ev_bwd_main[i], cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&e->ev_bwd_tools[i], cudaEventDisableTiming));
-    }
-    DA(e->actions, (size_t)e->H * e->B * std::max(1, e->A));
-    DA(e->action_grad, (size_t)e->H * e->B * std::max(1, e->A));
-    DA(e->rand_num, (size_t)std::max(1, k.npairs) * DSK_NUM_COLLISION_POINTS * 3);
-    e->stage_floats = std::max<size_t>((size_t)k.stride * 24, (size_t)e->B * k.nnode * 4);
-    DA(e->stage, e->stage_floats);
-    CK(cudaMemcpy(e->d_tools, e->h_tools.data(), sizeof(ToolParams) * std::max(1, e->K), cudaMemcpyHostToDevice));
-    sync_grid_tools(e);
-    // material fill, mpm_simulator.py:85-87
-    std::vector<float> m((size_t)3 * k.stride);
-    for (int i = 0; i < k.stride; i++) {
-      m[i] = (float)c->mu;
-      m[k.stride + i] = (float)c->lam;
-      m[2 * (size_t)k.stride + i] = (float)c->yield_stress;
-    }
-    CK(cudaMemcpy(e->mat, m.data(), m.size() * 4, cudaMemcpyHostToDevice));
-    return 0;
-  }();
-  if (rc) {
-    for (void* p : e->allocs) cudaFree(p);
-    delete e;
-    return -1;
-  }
-  *out = e;
-  return 0;
-}
-
-int dsk_destroy(dsk_engine* e) {
-  if (!e) return 0;
-  cudaSetDevice(e->cfg.device);
-  cudaStreamSynchronize(e->stream);
-  drop_graphs(e);
-#ifdef DSK_TIMELINE
-  if (e->d_tl) cudaFree(e->d_tl);
-#endif
-  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
-  if (e->ev_join2) cudaEventDestroy(e->ev_join2);
-  if (e->cap_side) cudaStreamDestroy(e->cap_side);
-  if (e->tool_stream) cudaStreamDestroy(e->tool_stream);
-  for (int i = 0; i < 2; i++) {
-    if (e->ev_bwd_main[i]) cudaEventDestroy(e->ev_bwd_main[i]);
-    if (e->ev_bwd_tools[i]) cudaEventDestroy(e->ev_bwd_tools[i]);
-  }
-  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
-  if (e->ev_join) cudaEventDestroy(e->ev_join);
-  for (auto ev : e->ev_restored) cudaEventDestroy(ev);
-  for (auto ev : e->ev_main) cudaEventDestroy(ev);
-  for (auto& r : e->prof) {
-    cudaEventDestroy(r.a);
-    cudaEventDestroy(r.b);
-  }
-  for (auto ev : e->ev_pool) cudaEventDestroy(ev);
-  for (void* p : e->allocs) cudaFree(p);
-  delete e;
-  return 0;
-}
-int dsk_set_stream(dsk_engine* e, void* s) {
-  CKE(e);
-  e->stream = (cudaStream_t)s;
-  e->qs = e->stream;
-  return 0;
-}
-int dsk_synchronize(dsk_engine* e) {
-  CKE(e);
-  CK(cudaStreamSynchronize(e->stream));
-  return 0;
-}
-int dsk_set_rand_num(dsk_engine* e, const double* rn) {
-  CKE(e);
-  size_t n = (size_t)e->k.npairs * DSK_NUM_COLLISION_POINTS * 3;
-  if (!n) return 0;
-  std::vector<float> f(n);
-  for (size_t i = 0; i < n; i++) f[i] = (float)rn[i];
-  CK(cudaMemcpyAsync(e->rand_num, f.data(), n * 4, cudaMemcpyHostToDevice, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
-  return 0;
-}
-int dsk_launch_count(dsk_engine* e, int64_t* n) {
-  if (!e) return fail("null engine");
-  *n = e->launches;
-  return 0;
-}
-int dsk_memory_bytes(dsk_engine* e, int64_t* n) {
-  if (!e) return fail("null engine");
-  *n = e->bytes;
-  return 0;
-}
-
-}  // extern "C"
-
-// -------------------------------------------------------------------------------------------------------
-// internal scheduling
-//
-// A "sequence" is the kernel train of one env step: forward (sort, kinematics, S x {p2g, grid_op, g2p}, store),
-// recompute (the same without the store) or backward (gather, S x {p2g, grid_op, g2p_adj, grid_op_adj,
-// p2g_adj}, tool adjoints, scatter).  Every sequence starts and ends with all grids zero and all tile counters
-// zero, and takes its step-dependent pointers from the device-resident StepArgs, so each of the three is
-// captured ONCE per step slot into a CUDA graph and replayed for every env step.
-// -------------------------------------------------------------------------------------------------------
-static int check_step(dsk_engine* e, int step, const char* what) {
-  if (step < 0 || step > e->H) return fail("%s: step %d outside [0, %d] (max_steps of this engine)", what, step, e->H);
-  return 0;
-}
-static void invalidate_slots(dsk_engine* e, int step) {
-  // a checkpoint was overwritten: substep frames simulated from it are stale
-  for (auto& s : e->slot)
-    if (s.src_step == step) s.src_step = -1;
-}
-static void invalidate_all(dsk_engine* e) {
-  for (auto& s : e->slot) s.src_step = -1;
-}
-static void drop_graphs(dsk_engine* e) {
-  for (auto& g : e->graphs)
-    for (auto& x : g.ex)
-      if (x) {
-        cudaGraphExecDestroy(x);
-        x = nullptr;
-      }
-}
-
-// one staging copy in: host or device source -> device pointer valid on the stream
-static int stage_in(dsk_engine* e, const float* src, size_t n, int on_device, size_t offset, const float** out) {
-  if (!src) {
-    *out = nullptr;
-    return 0;
-  }
-  if (on_device) {
-    *out = src;
-    return 0;
-  }
-  if (offset + n > e->stage_floats) return fail("staging buffer too small");
-  CK(cudaMemcpyAsync(e->stage + offset, src, n * 4, cudaMemcpyHostToDevice, e->stream));
-  *out = e->stage + offset;
-  return 0;
-}
-
-static int grid_ctas(dsk_engine* e) { return e->big ? 148 * 8 : 148 * e->grid_ctas_per_sm; }
-static float* svd_at(dsk_engine* e, StepSlot& s, int j) {
-  return s.svd ? s.svd + (size_t)j * SVD_COMPS * e->k.stride : nullptr;
-}
-// Threads per CTA of k_kinematics (one CTA per env).  Without tool-tool pairs the kernel is one pose chain per tool: two warps.
-// With pairs the warps share the collision queries: 32 warps when the kernel is on the critical path; 8 on the lookahead
-// branch, where it has a whole env step to finish -- a 1024-thread CTA needs a whole SM's register file, so next to the
-// particle kernels its CTAs waited ~150 us for SMs to drain and then held them (r02z timeline, GatherMove x64).
 static int kin_block(dsk_engine* e, bool hidden) { return e->k.npairs == 0 ? 64 : (hidden ? 256 : KIN_CTA); }
 static size_t kin_smem(dsk_engine* e) {   // pose chain + the collision samples of every pair
   return (size_t)(e->S + 1) * e->K * 32 + (size_t)e->k.npairs * DSK_NUM_COLLISION_POINTS * 12;
